@@ -1,0 +1,416 @@
+"""TEST INFRASTRUCTURE — the CPU/torch oracle for the PQ3D promptable-query-decoder hot path.
+
+A from-first-principles, *functional* restatement (plain torch ops over a flat state_dict) of the
+reference algorithm.  It is the checker for the CUDA path: only `tests/`,
+`__graft_entry__.smoke()` and `bench.py`'s cpu_baseline / `--impl reference` legs may import it,
+never the product package `pq3d_b200`.
+
+Parity pin: the reference holds no golden vectors / known-answer tests for this path (SURVEY.md
+§4, §8c), so the oracle is pinned against OUTPUTS OF THE REFERENCE ITSELF, run in this container
+by `oracle/ref_loader.py` (`tests/test_oracle_vs_reference.py`, fp32, <=1e-5) and against the
+committed fixtures under `tests/golden/` which `oracle/make_golden.py` generated from the real
+reference modules.
+
+The op sequence inside `mha()` deliberately mirrors torch's
+`F.multi_head_attention_forward(need_weights=True)` branch (linear -> baddbmm/bmm -> softmax ->
+bmm -> linear) so that under `torch.autocast('cuda', torch.bfloat16)` it rounds at exactly the
+points the reference does — that is the "reference GPU path" timed beside the kernels.
+
+Every function cites the reference file:line it follows (paths relative to /root/reference, or
+`torch/` for the installed PyTorch).  Masks: True = ignore everywhere in here.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import Callable, Dict, List, Optional, Sequence
+
+import torch
+import torch.nn.functional as F
+
+Tensor = torch.Tensor
+SD = Dict[str, Tensor]
+
+
+@dataclass
+class DecoderCfg:
+    """kwargs of QueryMaskEncoder.__init__ (modules/grounding/query_encoder.py:53-54)."""
+    memories: Sequence[str] = ()
+    memory_dropout: float = 0.0
+    hidden_size: int = 768
+    num_attention_heads: int = 12
+    num_layers: int = 4
+    spatial_selfattn: bool = False
+    structure: str = "sequential"
+    drop_memories_test: Sequence[str] = field(default_factory=list)
+    use_self_mask: bool = False
+    num_blocks: int = 1
+
+
+# --------------------------------------------------------------------------------------------
+# primitives
+# --------------------------------------------------------------------------------------------
+def layer_norm(x: Tensor, sd: SD, prefix: str, eps: float = 1e-5) -> Tensor:
+    return F.layer_norm(x, (x.shape[-1],), sd[prefix + "weight"], sd[prefix + "bias"], eps)
+
+
+def mha(q_in: Tensor, k_in: Tensor, v_in: Tensor, sd: SD, prefix: str, nhead: int,
+        key_padding_mask: Optional[Tensor], attn_mask: Optional[Tensor], add_zero_attn: bool) -> Tensor:
+    """nn.MultiheadAttention(batch_first=True) forward, eval mode, need_weights=True branch.
+
+    torch/nn/functional.py:5867-5873 (separate q/k/v in-projections from the packed weight),
+    :6585-6602 (add_zero_attn: one zero key/value appended AFTER projection, masks padded with
+    False), :6608-6620 (key padding merged into the float mask), :6630-6654 (scaled q, baddbmm,
+    softmax, bmm, out_proj).  Inputs are (B, L, E) / (B, S, E); bool masks, True = ignore.
+    """
+    B, L, E = q_in.shape
+    S = k_in.shape[1]
+    dh = E // nhead
+    w, b = sd[prefix + "in_proj_weight"], sd[prefix + "in_proj_bias"]
+    q = F.linear(q_in, w[:E], b[:E])
+    k = F.linear(k_in, w[E:2 * E], b[E:2 * E])
+    v = F.linear(v_in, w[2 * E:], b[2 * E:])
+    # (B, L, H, dh) -> (B*H, L, dh); row b*H + h, as the reference's view/transpose produces
+    q = q.view(B, L, nhead, dh).transpose(1, 2).reshape(B * nhead, L, dh)
+    k = k.view(B, S, nhead, dh).transpose(1, 2).reshape(B * nhead, S, dh)
+    v = v.view(B, S, nhead, dh).transpose(1, 2).reshape(B * nhead, S, dh)
+
+    fmask = None
+    if attn_mask is not None:
+        assert attn_mask.dtype == torch.bool and attn_mask.shape == (B * nhead, L, S)
+        fmask = torch.zeros(attn_mask.shape, dtype=q_in.dtype, device=q_in.device).masked_fill_(attn_mask, float("-inf"))
+    kpm = None
+    if key_padding_mask is not None:
+        assert key_padding_mask.dtype == torch.bool and key_padding_mask.shape == (B, S)
+        kpm = torch.zeros(key_padding_mask.shape, dtype=q_in.dtype, device=q_in.device).masked_fill_(key_padding_mask, float("-inf"))
+    if add_zero_attn:
+        k = torch.cat([k, k.new_zeros(B * nhead, 1, dh)], dim=1)
+        v = torch.cat([v, v.new_zeros(B * nhead, 1, dh)], dim=1)
+        if fmask is not None:
+            fmask = F.pad(fmask, (0, 1))
+        if kpm is not None:
+            kpm = F.pad(kpm, (0, 1))
+    S2 = k.shape[1]
+    if kpm is not None:
+        kpm = kpm.view(B, 1, 1, S2).expand(-1, nhead, -1, -1).reshape(B * nhead, 1, S2)
+        fmask = kpm if fmask is None else fmask + kpm
+
+    q_scaled = q * math.sqrt(1.0 / float(dh))
+    if fmask is not None:
+        scores = torch.baddbmm(fmask, q_scaled, k.transpose(-2, -1))
+    else:
+        scores = torch.bmm(q_scaled, k.transpose(-2, -1))
+    probs = F.softmax(scores, dim=-1)
+    out = torch.bmm(probs, v)                                   # (B*H, L, dh)
+    out = out.view(B, nhead, L, dh).transpose(1, 2).reshape(B, L, E)
+    return F.linear(out, sd[prefix + "out_proj.weight"], sd[prefix + "out_proj.bias"])
+
+
+def cross_attention_layer(tgt: Tensor, memory: Tensor, sd: SD, prefix: str, nhead: int,
+                          attn_mask: Optional[Tensor], key_padding_mask: Optional[Tensor],
+                          pos: Optional[Tensor], query_pos: Optional[Tensor]) -> Tensor:
+    """CrossAttentionLayer.forward_post (modules/grounding/query_encoder.py:288-307);
+    MHA built with add_zero_attn=True (:268-270)."""
+    q_in = tgt if query_pos is None else tgt + query_pos
+    k_in = memory if pos is None else memory + pos
+    upd = mha(q_in, k_in, memory, sd, prefix + "multihead_attn.", nhead, key_padding_mask, attn_mask, True)
+    return layer_norm(tgt + upd, sd, prefix + "norm.")
+
+
+def self_attention_layer(tgt: Tensor, sd: SD, prefix: str, nhead: int,
+                         key_padding_mask: Optional[Tensor], query_pos: Optional[Tensor]) -> Tensor:
+    """SelfAttentionLayer.forward_post (query_encoder.py:213-227): q = k = tgt+pos, v = tgt."""
+    x = tgt if query_pos is None else tgt + query_pos
+    upd = mha(x, x, tgt, sd, prefix + "self_attn.", nhead, key_padding_mask, None, False)
+    return layer_norm(tgt + upd, sd, prefix + "norm.")
+
+
+def spatial_mha(x: Tensor, v_in: Tensor, pairwise_locs: Tensor, sd: SD, prefix: str, nhead: int,
+                key_padding_mask: Optional[Tensor]) -> Tensor:
+    """MultiHeadAttentionSpatial.forward, fusion 'mul', spatial_multihead=True
+    (modules/layers/transformers.py:189-240)."""
+    B, L, E = x.shape
+    dh = E // nhead
+
+    def heads(t):  # 'b l (head k) -> head b l k'
+        return t.view(B, L, nhead, dh).permute(2, 0, 1, 3)
+
+    q = heads(F.linear(x, sd[prefix + "w_qs.weight"], sd[prefix + "w_qs.bias"]))
+    k = heads(F.linear(x, sd[prefix + "w_ks.weight"], sd[prefix + "w_ks.bias"]))
+    v = heads(F.linear(v_in, sd[prefix + "w_vs.weight"], sd[prefix + "w_vs.bias"]))
+    attn = torch.einsum("hblk,hbtk->hblt", q, k) / math.sqrt(dh)                      # :193
+    loc = F.linear(pairwise_locs, sd[prefix + "pairwise_loc_fc.weight"], sd[prefix + "pairwise_loc_fc.bias"])
+    loc = F.relu(loc.permute(3, 0, 1, 2))                                            # (H,B,L,T) :196-199
+    if key_padding_mask is not None:                                                 # :220-226
+        m = key_padding_mask.view(1, B, 1, L).expand(nhead, B, L, L)
+        attn = attn.masked_fill(m, float("-inf"))
+        loc = loc.masked_fill(m, 0)
+    fused = torch.log(torch.clamp(loc, min=1e-6)) + attn                             # :231-232
+    fused = torch.softmax(fused, 3)
+    assert not torch.isnan(fused).any()                                              # :235
+    out = torch.einsum("hblt,hbtv->hblv", fused, v)
+    out = out.permute(1, 2, 0, 3).reshape(B, L, E)
+    return F.linear(out, sd[prefix + "fc.weight"], sd[prefix + "fc.bias"])
+
+
+def spatial_self_attention_layer(tgt: Tensor, sd: SD, prefix: str, nhead: int,
+                                 key_padding_mask: Optional[Tensor], query_pos: Optional[Tensor],
+                                 pairwise_locs: Tensor) -> Tensor:
+    """SpatialSelfAttentionLayer.forward_post (query_encoder.py:438-452)."""
+    x = tgt if query_pos is None else tgt + query_pos
+    upd = spatial_mha(x, tgt, pairwise_locs, sd, prefix + "self_attn.", nhead, key_padding_mask)
+    return layer_norm(tgt + upd, sd, prefix + "norm.")
+
+
+def ffn_layer(tgt: Tensor, sd: SD, prefix: str) -> Tensor:
+    """FFNLayer.forward_post, relu (query_encoder.py:384-388)."""
+    h = F.relu(F.linear(tgt, sd[prefix + "linear1.weight"], sd[prefix + "linear1.bias"]))
+    upd = F.linear(h, sd[prefix + "linear2.weight"], sd[prefix + "linear2.bias"])
+    return layer_norm(tgt + upd, sd, prefix + "norm.")
+
+
+# --------------------------------------------------------------------------------------------
+# one decoder layer / the stacked decoder
+# --------------------------------------------------------------------------------------------
+def query_encoder_layer(query: Tensor, input_dict: dict, pairwise_locs: Optional[Tensor], sd: SD,
+                        prefix: str, cfg: DecoderCfg) -> Tensor:
+    """QueryEncoderLayer.forward in eval mode (query_encoder.py:114-181)."""
+    H = cfg.num_attention_heads
+    _, query_masks, query_pos = input_dict["query"]
+    mem_index = {m: j for j, m in enumerate(cfg.memories)}            # memory2ca, :105
+
+    def one_ca(q, memory):
+        feat, mask, pos = input_dict[memory]
+        kpm, am = (mask, None) if mask.ndim == 2 else (None, mask)     # :121-126
+        return cross_attention_layer(q, feat, sd, f"{prefix}cross_attn_list.{mem_index[memory]}.", H,
+                                     am, kpm, pos, query_pos)
+
+    def sequential_ca(q, memories):                                    # :117-129
+        for m in memories:
+            q = one_ca(q, m)
+        return q
+
+    def parallel_ca(q, memories):                                      # :131-154 (eval branch)
+        assert "prompt" not in memories
+        return torch.stack([one_ca(q, m) for m in memories], dim=1).mean(dim=1)
+
+    memories = [m for m in cfg.memories if m not in cfg.drop_memories_test]   # :156
+    if cfg.structure == "sequential":
+        query = sequential_ca(query, memories)
+    elif cfg.structure == "parallel":
+        query = parallel_ca(query, memories)
+    elif cfg.structure == "mixed":                                     # :162-165
+        query = parallel_ca(query, [m for m in memories if m != "prompt"])
+        query = sequential_ca(query, ["prompt"])
+    elif cfg.structure == "gate":                                      # :166-170
+        prompt = sequential_ca(query, ["prompt"])
+        gate = torch.sigmoid(F.linear(prompt, sd[prefix + "gate_proj.weight"], sd[prefix + "gate_proj.bias"]))
+        update = parallel_ca(query, [m for m in cfg.memories if m != "prompt"])
+        query = (1.0 - gate) * query + gate * update
+    else:
+        raise NotImplementedError(f"Unknow structure type: {cfg.structure}")
+
+    if cfg.spatial_selfattn:                                           # :174-178
+        query = spatial_self_attention_layer(query, sd, prefix + "self_attn.", H, query_masks, query_pos, pairwise_locs)
+    else:
+        query = self_attention_layer(query, sd, prefix + "self_attn.", H, query_masks, query_pos)
+    return ffn_layer(query, sd, prefix + "ffn.")                        # :179
+
+
+def query_mask_encoder(sd: SD, cfg: DecoderCfg, input_dict: dict, pairwise_locs: Optional[Tensor],
+                       mask_head: Optional[Callable] = None, prefix: str = ""):
+    """QueryMaskEncoder.forward (query_encoder.py:69-94).  Mutates input_dict like the reference."""
+    predictions_class, predictions_mask = [], []
+    query = input_dict["query"][0]
+    voxel_feat = input_dict["voxel"][0] if "voxel" in input_dict else None
+    attn_mask = None
+    for _block in range(cfg.num_blocks):
+        for i in range(cfg.num_layers):
+            if mask_head is not None:
+                output_class, outputs_mask, attn_mask = mask_head(query)
+                predictions_class.append(output_class)
+                predictions_mask.append(outputs_mask)
+            if cfg.use_self_mask:
+                attn_mask[attn_mask.all(-1)] = False                      # :83
+                attn_mask = attn_mask.repeat_interleave(cfg.num_attention_heads, 0)
+                for memory in input_dict.keys():
+                    if memory in ("query", "prompt"):
+                        continue
+                    input_dict[memory][1] = attn_mask                      # :85-88 (overwrite)
+            if isinstance(voxel_feat, list):
+                input_dict["voxel"][0] = voxel_feat[i]                     # :90-91
+            query = query_encoder_layer(query, input_dict, pairwise_locs, sd,
+                                        f"{prefix}unified_encoder.{i}.", cfg)
+    return query, predictions_class, predictions_mask
+
+
+# --------------------------------------------------------------------------------------------
+# mask head (in-loop consumer/producer of the attention mask)
+# --------------------------------------------------------------------------------------------
+def mlp_head(x: Tensor, sd: SD, prefix: str) -> Tensor:
+    """get_mlp_head: Linear-ReLU-LayerNorm(eps 1e-12)-Dropout-Linear (modules/utils.py:18-25)."""
+    h = F.relu(F.linear(x, sd[prefix + "0.weight"], sd[prefix + "0.bias"]))
+    h = F.layer_norm(h, (h.shape[-1],), sd[prefix + "2.weight"], sd[prefix + "2.bias"], 1e-12)
+    return F.linear(h, sd[prefix + "4.weight"], sd[prefix + "4.bias"])
+
+
+def mask_head_seg_level(query: Tensor, sd: SD, prefix: str, seg_fts_for_match: list, seg_masks: Tensor,
+                        filter_out_classes=None, offline_attn_masks: Optional[Tensor] = None,
+                        skip_prediction: bool = False):
+    """MaskHeadSegLevel.forward + MaskPredictionLayer (modules/heads/mask_head.py:24-57)."""
+    if skip_prediction:
+        return None, None, offline_attn_masks
+    cls_logits = mlp_head(query, sd, prefix + "cls_head.")
+    if filter_out_classes is not None:
+        cls_logits[..., filter_out_classes] = float("-inf")
+    logits_sum, valid_sum = 0, 0
+    for j, (feat, mask, _pos) in enumerate(seg_fts_for_match):
+        qp = F.linear(query, sd[f"{prefix}mask_pred_list.{j}.q_proj.weight"], sd[f"{prefix}mask_pred_list.{j}.q_proj.bias"])
+        kp = F.linear(feat, sd[f"{prefix}mask_pred_list.{j}.k_proj.weight"])
+        logits = torch.einsum("bld,bmd->blm", kp, qp)                     # (B, S, N)
+        valid = mask[..., None].logical_not()
+        logits_sum = logits_sum + logits * valid
+        valid_sum = valid_sum + valid
+    mask_logits = logits_sum / (valid_sum + 1e-8)
+    mask_logits[seg_masks] = -1e6
+    if offline_attn_masks is not None:
+        attn_mask = offline_attn_masks
+    else:
+        attn_mask = mask_logits.sigmoid().permute(0, 2, 1).detach() < 0.5
+    return cls_logits, mask_logits, attn_mask
+
+
+# --------------------------------------------------------------------------------------------
+# geometry / positional producers (cheap, fp32)
+# --------------------------------------------------------------------------------------------
+def calc_pairwise_locs(centers: Tensor, eps: float = 1e-10) -> Tensor:
+    """calc_pairwise_locs(pairwise_rel_type='center', spatial_dist_norm=True, spatial_dim=5)
+    (modules/utils.py:38-68): (B, N, 3) -> (B, N, N, 5)."""
+    d = centers[:, :, None, :] - centers[:, None, :, :]
+    dist = torch.sqrt((d ** 2).sum(3) + eps)
+    mx = dist.flatten(1).max(dim=1)[0]
+    norm = dist / mx[:, None, None]
+    dist2d = torch.sqrt((d[..., :2] ** 2).sum(3) + eps)
+    return torch.stack([norm, d[..., 2] / dist, dist2d / dist, d[..., 1] / dist2d, d[..., 0] / dist2d], dim=3)
+
+
+def fourier_pos(xyz: Tensor, gauss_B: Tensor, coord_min: Tensor, coord_max: Tensor) -> Tensor:
+    """PositionEmbeddingCoordsSine(pos_type='fourier', normalize=True).forward, returned already
+    permuted to (B, L, d_pos) (modules/third_party/mask3d/position_embedding.py:13-43,127-156;
+    model/query3d_unified.py:22-24, fp32 / no autocast)."""
+    with torch.autocast(device_type=xyz.device.type, enabled=False):
+        x = xyz.float()
+        src_diff = coord_max[:, None, :] - coord_min[:, None, :]
+        x = ((x - coord_min[:, None, :]) * 1.0) / src_diff + 0.0
+        x = x * (2 * math.pi)
+        proj = (x.reshape(-1, 3) @ gauss_B).view(x.shape[0], x.shape[1], -1)
+        return torch.cat([proj.sin(), proj.cos()], dim=2)
+
+
+def coordinate_encoder(xyz: Tensor, sd: SD, prefix: str, coord_min: Tensor, coord_max: Tensor) -> Tensor:
+    """CoordinateEncoder.forward (model/query3d_unified.py:15-27): fourier -> Linear -> LN."""
+    pos = fourier_pos(xyz, sd[prefix + "pos_enc.gauss_B"], coord_min, coord_max)
+    pos = F.linear(pos, sd[prefix + "feat_proj.0.weight"], sd[prefix + "feat_proj.0.bias"])
+    return F.layer_norm(pos, (pos.shape[-1],), sd[prefix + "feat_proj.1.weight"], sd[prefix + "feat_proj.1.bias"])
+
+
+def linear_ln(x: Tensor, sd: SD, prefix: str) -> Tensor:
+    """nn.Sequential(Linear, LayerNorm) — ObjectEncoder.input_feat_proj
+    (modules/vision/object_encoder.py:33-38,73) and the dim_loc>3 coord/box encoders
+    (model/query3d_unified.py:62-69)."""
+    h = F.linear(x, sd[prefix + "0.weight"], sd[prefix + "0.bias"])
+    return F.layer_norm(h, (h.shape[-1],), sd[prefix + "1.weight"], sd[prefix + "1.bias"])
+
+
+# --------------------------------------------------------------------------------------------
+# the model boundary
+# --------------------------------------------------------------------------------------------
+@dataclass
+class ModelCfg:
+    """The cfg.model.* keys Query3DUnified reads (model/query3d_unified.py:31-78)."""
+    memories: Sequence[str]
+    decoder: DecoderCfg
+    dim_loc: int = 3
+    heads: Sequence[str] = ("mask",)
+    use_offline_voxel_fts: bool = True
+    skip_query_encoder_mask_pred: bool = False
+    filter_out_classes: Optional[List[int]] = None
+    memories_for_match: Sequence[str] = ()
+    projected_memories: Sequence[str] = ("mv", "pc", "voxel")   # ObjectEncoder use_projection=True
+
+
+def query3d_unified_forward(sd: SD, cfg: ModelCfg, data_dict: dict) -> dict:
+    """Query3DUnified.forward, eval mode (model/query3d_unified.py:110-222), restricted to the
+    in-scope producers: offline voxel features (ObjectEncoder projection, or an already projected
+    multi-scale list passed as data_dict['voxel_seg_fts_multiscale']), mv / pc ObjectEncoder
+    projections, prompt features given as data_dict['prompt_feat'] (CLIP tower is out of scope),
+    and the 'mask' / 'ground' heads."""
+    input_dict = {}
+    qmask = data_dict["query_pad_masks"].logical_not()                         # :113
+    query_locs = data_dict["query_locs"][:, :, :cfg.dim_loc]
+    cmin, cmax = data_dict["coord_min"], data_dict["coord_max"]
+    fts_locs = data_dict["seg_center"]
+    if cfg.dim_loc > 3:                                                         # :117-118,127-132
+        query_pos = linear_ln(query_locs[:, :, :3], sd, "coord_encoder.") + linear_ln(query_locs[:, :, 3:6], sd, "box_encoder.")
+        fts_pos = linear_ln(fts_locs[:, :, :3], sd, "coord_encoder.") + linear_ln(fts_locs[:, :, 3:6], sd, "box_encoder.")
+        fts_pos = fts_pos + linear_ln(fts_locs[:, :, 3:6], sd, "box_encoder.")   # added twice in the reference
+    else:
+        query_pos = coordinate_encoder(query_locs[:, :, :3], sd, "coord_encoder.", cmin, cmax)
+        fts_pos = coordinate_encoder(fts_locs[:, :, :3], sd, "coord_encoder.", cmin, cmax)
+    input_dict["query"] = (torch.zeros_like(query_pos), qmask, query_pos)       # :121-123
+
+    def obj_enc(name, x):
+        return linear_ln(x, sd, f"{name}_encoder.input_feat_proj.") if name in cfg.projected_memories else x
+
+    for m in cfg.memories:                                                      # :133-160
+        if m == "prompt":
+            feat, mask, pos = data_dict["prompt_feat"], data_dict["prompt_pad_masks"].logical_not(), None
+        elif m in ("mv", "pc"):
+            feat = obj_enc(m, data_dict[f"{m}_seg_fts"])
+            mask, pos = data_dict[f"{m}_seg_pad_masks"].logical_not(), fts_pos
+        elif m == "voxel":
+            if "voxel_seg_fts_multiscale" in data_dict:
+                feat = list(data_dict["voxel_seg_fts_multiscale"])
+                mask = data_dict["seg_pad_masks"].logical_not()
+            else:
+                feat = obj_enc(m, data_dict["voxel_seg_fts"])
+                mask = data_dict["voxel_seg_pad_masks"].logical_not()
+            pos = fts_pos
+        else:
+            raise NotImplementedError(m)
+        input_dict[m] = [feat, mask, pos]
+
+    seg_fts_for_match = []                                                      # :167-174
+    for m in cfg.memories:
+        if m in ("voxel", "mv", "pc"):
+            feats = list(input_dict[m])
+            if isinstance(feats[0], list):
+                feats[0] = feats[0][-1]
+            seg_fts_for_match.append(feats)
+    seg_masks = data_dict["seg_pad_masks"].logical_not()
+    has_mask_head = "mask" in cfg.heads
+
+    def mask_head(query, skip=cfg.skip_query_encoder_mask_pred):
+        return mask_head_seg_level(query, sd, "mask_head.", seg_fts_for_match, seg_masks,
+                                   cfg.filter_out_classes, None, skip)
+
+    pairwise = calc_pairwise_locs(query_locs[:, :, :3]) if cfg.decoder.spatial_selfattn else None  # :182-187
+    query, pcls, pmask = query_mask_encoder(sd, cfg.decoder, input_dict, pairwise,
+                                            mask_head if has_mask_head else None, prefix="unified_encoder.")
+    data_dict["query_feat"] = query
+    for head in cfg.heads:                                                      # :193-220
+        if head == "mask":
+            if cfg.skip_query_encoder_mask_pred:
+                pcls, pmask = [], []
+            c, m_, _ = mask_head(query, skip=False)
+            pcls.append(c)
+            pmask.append(m_)
+            data_dict["predictions_class"], data_dict["predictions_mask"] = pcls, pmask
+        elif head == "ground":
+            logits = mlp_head(query, sd, "ground_head.og3d_head.").squeeze(2)   # grounding_head.py:51-55
+            logits = logits.masked_fill(data_dict["query_pad_masks"].logical_not(), float("-inf"))
+            data_dict["ground_logits"] = logits
+            data_dict["og3d_logits"] = logits
+        else:
+            raise NotImplementedError(head)
+    return data_dict

@@ -1,0 +1,116 @@
+"""CPU, this container only: the restatement equals the REAL reference modules imported from
+/root/reference (skipped on the GPU box, where the tree is absent), plus the known-answer
+properties of SURVEY.md §8c that need no reference at all."""
+import pytest
+import torch
+
+import _cases as C
+from oracle import ref_loader, restatement as O
+from pq3d_b200 import synth
+
+needs_ref = pytest.mark.skipif(not ref_loader.available(), reason="/root/reference not present")
+
+
+@needs_ref
+@pytest.mark.parametrize("base,over", [
+    ("c1", dict(N=64, S=96, num_layers=2)),
+    ("c3", dict(B=2, N=30, S=70, T=7, num_layers=2)),
+    ("c2", dict(B=2, N=17, S=40, num_layers=1, structure="sequential")),
+])
+def test_decoder_matches_live_reference(base, over):
+    ns = ref_loader.load()
+    case = dict(base=base, over=over, wseed=21, sharp=3.0)
+    w = C.build_workload(case)
+    sd = synth.decoder_state_dict(w, seed=21, sharp=3.0)
+    enc = ns.query_encoder.QueryMaskEncoder(None, **w.decoder_kwargs()).eval()
+    enc.load_state_dict(sd, strict=True)
+    inp, pw, _ = synth.make_decoder_inputs(w)
+    with torch.no_grad():
+        ref, _, _ = enc(synth.clone_input_dict(inp), pw)
+    out = C.oracle_decoder(case)["query"]
+    assert (ref - out).abs().max() / ref.abs().max() <= 1e-5
+
+
+@needs_ref
+def test_pairwise_locs_matches_live_reference():
+    ns = ref_loader.load()
+    c = torch.rand(3, 50, 3, generator=torch.Generator().manual_seed(3)) * 5
+    ref = ns.utils.calc_pairwise_locs(c, None, pairwise_rel_type="center", spatial_dist_norm=True, spatial_dim=5)
+    assert torch.allclose(O.calc_pairwise_locs(c), ref, rtol=1e-6, atol=1e-7)
+    assert torch.allclose(synth.pairwise_locs_cpu(c), ref, rtol=1e-6, atol=1e-7)
+
+
+@needs_ref
+def test_state_dict_schema_matches_live_reference():
+    ns = ref_loader.load()
+    for kw in (dict(memories=["mv", "pc", "voxel", "prompt"], spatial_selfattn=True, structure="mixed"),
+               dict(memories=["pc"], spatial_selfattn=False, structure="gate", num_layers=2)):
+        enc = ns.query_encoder.QueryMaskEncoder(None, **kw)
+        ref = {k: tuple(v.shape) for k, v in enc.state_dict().items()}
+        assert synth.decoder_param_shapes(**kw) == ref
+        assert list(synth.decoder_param_shapes(**kw)) == list(ref)          # same order too
+
+
+# ---- known-answer properties ---------------------------------------------------------------
+def _one_ca(S=40, N=9, seed=5):
+    w = synth.Workload("t", 2, N, S, ["pc"], "parallel", num_layers=1)
+    sd = synth.decoder_state_dict(w, seed=seed, sharp=3.0)
+    inp, pw, _ = synth.make_decoder_inputs(w)
+    return w, sd, inp
+
+
+def test_all_keys_masked_returns_ln_of_bias():
+    """add_zero_attn: with every key masked the only attended key is the zero one, so the update is
+    out_proj.bias and the layer returns LN(tgt + out_proj.bias)."""
+    w, sd, inp = _one_ca()
+    p = "unified_encoder.0.cross_attn_list.0."
+    tgt = torch.randn(2, w.N, 768, generator=torch.Generator().manual_seed(1))
+    feat, mask, pos = inp["pc"]
+    out = O.cross_attention_layer(tgt, feat, sd, p, 12, None, torch.ones_like(mask), pos, inp["query"][2])
+    exp = O.layer_norm(tgt + sd[p + "multihead_attn.out_proj.bias"], sd, p + "norm.")
+    assert torch.allclose(out, exp, atol=1e-5)
+
+
+def test_padding_invariance_and_permutation_equivariance():
+    w, sd, inp = _one_ca()
+    p = "unified_encoder.0.cross_attn_list.0."
+    tgt = torch.randn(2, w.N, 768, generator=torch.Generator().manual_seed(2))
+    feat, mask, pos = inp["pc"]
+    qp = inp["query"][2]
+    base = O.cross_attention_layer(tgt, feat, sd, p, 12, None, mask, pos, qp)
+    # appending masked tokens changes nothing
+    feat2 = torch.cat([feat, torch.randn(2, 7, 768)], 1)
+    pos2 = torch.cat([pos, torch.randn(2, 7, 768)], 1)
+    mask2 = torch.cat([mask, torch.ones(2, 7, dtype=torch.bool)], 1)
+    assert torch.allclose(O.cross_attention_layer(tgt, feat2, sd, p, 12, None, mask2, pos2, qp), base, atol=2e-6)
+    # permuting segment order (with masks alike) changes nothing
+    perm = torch.randperm(feat.shape[1], generator=torch.Generator().manual_seed(3))
+    out = O.cross_attention_layer(tgt, feat[:, perm], sd, p, 12, None, mask[:, perm], pos[:, perm], qp)
+    assert torch.allclose(out, base, atol=2e-6)
+
+
+def test_parallel_with_one_memory_equals_sequential():
+    for structure in ("parallel", "sequential"):
+        pass
+    wp = synth.Workload("t", 2, 11, 30, ["pc"], "parallel", num_layers=2)
+    ws = synth.Workload("t", 2, 11, 30, ["pc"], "sequential", num_layers=2)
+    sd = synth.decoder_state_dict(wp, seed=9)
+    inp, pw, _ = synth.make_decoder_inputs(wp)
+    a, _, _ = O.query_mask_encoder(sd, O.DecoderCfg(**wp.decoder_kwargs()), synth.clone_input_dict(inp), pw)
+    b, _, _ = O.query_mask_encoder(sd, O.DecoderCfg(**ws.decoder_kwargs()), synth.clone_input_dict(inp), pw)
+    assert torch.allclose(a, b, atol=1e-6)
+
+
+def test_fully_masked_rows_become_fully_visible():
+    """QueryMaskEncoder: attn_mask[attn_mask.all(-1)] = False (query_encoder.py:83)."""
+    w = synth.Workload("t", 1, 6, 20, ["pc"], "parallel", num_layers=1, use_self_mask=True)
+    sd = synth.decoder_state_dict(w, seed=4)
+    inp, pw, _ = synth.make_decoder_inputs(w)
+    am = torch.zeros(1, 6, 20, dtype=torch.bool)
+    am[0, 2] = True                                   # row 2 would see nothing
+    head_all = lambda q: (None, None, am.clone())
+    am2 = am.clone(); am2[0, 2] = False
+    head_vis = lambda q: (None, None, am2.clone())
+    a, _, _ = O.query_mask_encoder(sd, O.DecoderCfg(**w.decoder_kwargs()), synth.clone_input_dict(inp), pw, head_all)
+    b, _, _ = O.query_mask_encoder(sd, O.DecoderCfg(**w.decoder_kwargs()), synth.clone_input_dict(inp), pw, head_vis)
+    assert torch.equal(a, b)
