@@ -1,0 +1,116 @@
+/* pq3d_b200 — C ABI of the B200-native promptable-query-decoder kernels.
+ *
+ * The reference (PQ3D) has no FFI on this path: the decoder is PyTorch eager code
+ * (modules/grounding/query_encoder.py, modules/layers/transformers.py, modules/heads/mask_head.py)
+ * that bottoms out in torch.nn.functional.  Each entry point below names the reference call site it
+ * replaces.  A host in any language binds these with plain pointers and sizes (ctypes in this repo:
+ * pq3d_b200/_lib.py; INTEGRATION.md shows the reference-side stub).
+ *
+ * Conventions
+ *   - every pointer except `stream` and the pointer TABLES (`K`, `Vt`, `mask_bits` in
+ *     pq3d_attention_fwd are host arrays of device pointers; `mem_masks_dev` in
+ *     pq3d_mask_head_finalize is a DEVICE array of device pointers) is a device pointer owned by the
+ *     caller; nothing is allocated or freed by the library and no global state is kept
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued asynchronously on it
+ *   - bf16 tensors are `void*`; "ld*" are leading dimensions in ELEMENTS
+ *   - bool masks are uint8 with 1 = ignore (PyTorch convention, model/query3d_unified.py:125)
+ *   - return 0 on success, <0 on error (-1 invalid argument, -2 CUDA error, -3 unsupported);
+ *     pq3d_last_error() returns a thread-local message.  The library never calls exit().
+ *   - requires an sm_100a device (tcgen05 / TMEM / TMA); there is no fallback path.
+ */
+#ifndef PQ3D_B200_H_
+#define PQ3D_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+const char* pq3d_last_error(void);
+int pq3d_abi_version(void);
+
+/* C[g] = epilogue(A[g] · W[g]ᵀ), bf16 operands, fp32 accumulation on tcgen05 tensor cores.
+ *   A: [a_rows_total, lda] bf16, group g starts at row g*a_group_rows, uses M rows, K columns
+ *   W: [w_rows_total, ldw] bf16, group g starts at row g*w_group_rows, uses N rows (nn.Linear layout)
+ *   C: out_fp32 ? float : bf16, element (g, m, n) at C[g*c_group_stride + m*ldc + n]
+ *   epilogue: x = acc + bias[g*bias_group_stride + (bias_along_m ? m : n)];
+ *             if (n < alpha_ncols) x *= alpha;  if (relu) x = max(x, 0);
+ *             if (row_zero && row_zero[g*row_zero_group_stride + m]) x = 0
+ *   block_n: 0 = auto, or 64 / 128 / 256 (tile width).  K must be a multiple of 64.
+ * Replaces every nn.Linear on the path: MHA in/out projections (torch/nn/functional.py:5867-5873,
+ * :6653), w_qs/w_ks/w_vs/fc (modules/layers/transformers.py:180-185,190-192,238), FFN
+ * (modules/grounding/query_encoder.py:384), mask-head q_proj/k_proj and their einsum
+ * (modules/heads/mask_head.py:52-56), cls MLP (modules/utils.py:18-25). */
+int pq3d_linear_bf16(const void* A, int64_t lda, int64_t a_rows_total, int64_t a_group_rows,
+                     const void* W, int64_t ldw, int64_t w_rows_total, int64_t w_group_rows,
+                     void* C, int64_t ldc, int64_t c_group_stride, int out_fp32,
+                     const float* bias, int64_t bias_group_stride, int bias_along_m,
+                     const uint8_t* row_zero, int64_t row_zero_group_stride,
+                     int M, int N, int K, int groups, float alpha, int alpha_ncols, int relu,
+                     int block_n, void* stream);
+
+/* Masked softmax attention for n_mem (<= 4) memories in one launch, head_dim = 64.
+ *   Q : bf16 [B*Nq, ldq]; memory i / head h at columns i*q_mem_stride + h*64; already scaled by 1/8
+ *   K[i] : bf16 [B*S_pitch[i], ldk[i]]; head h at columns k_col0[i] + h*64
+ *   Vt[i]: bf16 [vt_rows[i], ldvt[i]] — V TRANSPOSED: row vt_row0[i] + h*64 + d, column b*S_pitch[i] + s
+ *   mask_bits[i]: packed by pq3d_pack_mask (1 = ignore), word address
+ *                 b*mask_b_stride + h*mask_h_stride + n*mask_q_stride + s/32; NULL = nothing masked
+ *   O : bf16, element (i, b, n, h*64+d) at O[i*o_mem_stride + (b*Nq+n)*ldo + h*64 + d]
+ *   zero_attn: nn.MultiheadAttention(add_zero_attn=True) — one extra never-masked key with score 0
+ *              and value 0 (torch/nn/functional.py:6585-6602), handled analytically
+ *   pairwise_locs [B,Nq,Nq,5] fp32 + loc_w [H,5] + loc_b [H] (or all NULL): adds
+ *              log(max(relu(loc·w_h + b_h), 1e-6)) to the scores — MultiHeadAttentionSpatial 'mul'
+ *              (modules/layers/transformers.py:196-199,231-233); requires S == Nq.
+ * Replaces torch/nn/functional.py:6630-6647 as called from CrossAttentionLayer.forward_post
+ * (modules/grounding/query_encoder.py:297-303) and modules/layers/transformers.py:193-237. */
+int pq3d_attention_fwd(int n_mem, const void* Q, int64_t ldq, int64_t q_mem_stride,
+                       const void* const* K, const int64_t* ldk, const int64_t* k_col0,
+                       const void* const* Vt, const int64_t* ldvt, const int64_t* vt_row0, const int64_t* vt_rows,
+                       const int32_t* S, const int32_t* S_pitch,
+                       const uint32_t* const* mask_bits, const int64_t* mask_b_stride,
+                       const int64_t* mask_h_stride, const int64_t* mask_q_stride,
+                       void* O, int64_t ldo, int64_t o_mem_stride, int B, int H, int Nq, int zero_attn,
+                       const float* pairwise_locs, const float* loc_w, const float* loc_b, void* stream);
+
+/* xv = bf16(feat), xk = bf16(feat + pos) with rows padded to S_pitch (zero-filled); pos may be NULL
+ * (then xk = xv values), either output may be NULL.  feat/pos: fp32 [B,S,D].
+ * Replaces CrossAttentionLayer.with_pos_embed + the autocast input casts
+ * (modules/grounding/query_encoder.py:285-286,298-300). */
+int pq3d_ingest_memory(const float* feat, const float* pos, void* xk, void* xv, int B, int S, int S_pitch, int D,
+                       void* stream);
+
+/* out = (1/G) * sum_g LayerNorm_g(residual + y[g]); y: fp32 [G][R,D] (group stride in elements) or NULL,
+ * residual fp32 [R,D] or NULL, gamma/beta fp32 [G,D].  Optional outputs (NULL to skip): out_f32,
+ * out_bf16 = bf16(out), out_pos_bf16 = bf16(out + pos).  D multiple of 128, <= 1024.
+ * Replaces `tgt = norm(tgt + dropout(tgt2))` (modules/grounding/query_encoder.py:304-305,386-387,
+ * 449-450) and parallel_ca's mean over memories (:153). */
+int pq3d_add_layernorm(const float* y, int64_t y_group_stride, const float* residual, const float* gamma,
+                       const float* beta, int G, float eps, int R, int D, const float* pos, float* out_f32,
+                       void* out_bf16, void* out_pos_bf16, void* stream);
+
+/* bits[row, w] packs mask[row, 32w .. 32w+31] (1 = ignore), W = 4*ceil(S/128) words per row, bits past S set.
+ * unmask_full_rows: rows that are entirely masked become entirely visible
+ * (`attn_mask[attn_mask.all(-1)] = False`, modules/grounding/query_encoder.py:83); mask_fixed (optional,
+ * [rows,S]) receives the bool mask after that fix-up. */
+int pq3d_pack_mask(const uint8_t* mask, uint32_t* bits, int64_t rows, int S, int unmask_full_rows,
+                   uint8_t* mask_fixed, void* stream);
+
+/* mask_logits[b,s,n] = raw[b,s,n] / (#memories valid at (b,s) + 1e-8), -1e6 where seg_masks[b,s];
+ * attn_mask[b,n,s] = sigmoid(mask_logits[b,s,n]) < 0.5.  mem_masks_dev: device array of n_mem device
+ * pointers to uint8 [B,S] (1 = ignore).  Replaces modules/heads/mask_head.py:36-43. */
+int pq3d_mask_head_finalize(const float* raw, const uint8_t* const* mem_masks_dev, int n_mem,
+                            const uint8_t* seg_masks, float* mask_logits, uint8_t* attn_mask, int B, int S, int N,
+                            void* stream);
+
+/* out = (1 - sigmoid(g)) * query + sigmoid(g) * update  (structure 'gate', query_encoder.py:166-170). */
+int pq3d_gate_mix(const float* gate_logits, const float* query, const float* update, float* out, int64_t n,
+                  void* stream);
+
+/* out = bf16(x + add) (add may be NULL); n multiple of 4. */
+int pq3d_cast_bf16(const float* x, const float* add, void* out, int64_t n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PQ3D_B200_H_ */

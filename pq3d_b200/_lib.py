@@ -1,0 +1,68 @@
+"""ctypes binding of include/pq3d_b200.h.  The product path has no fallback: if the shared library
+is missing (or a call fails) this raises, loudly."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import re
+from typing import Dict, List
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "_C", "libpq3d_b200.so")
+HEADER = os.path.join(os.path.dirname(HERE), "include", "pq3d_b200.h")
+
+_i64, _i32, _f32, _vp = C.c_int64, C.c_int, C.c_float, C.c_void_p
+_pp = C.POINTER(C.c_void_p)
+_pi64 = C.POINTER(C.c_int64)
+_pi32 = C.POINTER(C.c_int32)
+
+SIGNATURES: Dict[str, list] = {
+    "pq3d_linear_bf16": [_vp, _i64, _i64, _i64, _vp, _i64, _i64, _i64, _vp, _i64, _i64, _i32, _vp, _i64, _i32,
+                         _vp, _i64, _i32, _i32, _i32, _i32, _f32, _i32, _i32, _i32, _vp],
+    "pq3d_attention_fwd": [_i32, _vp, _i64, _i64, _pp, _pi64, _pi64, _pp, _pi64, _pi64, _pi64, _pi32, _pi32,
+                           _pp, _pi64, _pi64, _pi64, _vp, _i64, _i64, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp],
+    "pq3d_ingest_memory": [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp],
+    "pq3d_add_layernorm": [_vp, _i64, _vp, _vp, _vp, _i32, _f32, _i32, _i32, _vp, _vp, _vp, _vp, _vp],
+    "pq3d_pack_mask": [_vp, _vp, _i64, _i32, _i32, _vp, _vp],
+    "pq3d_mask_head_finalize": [_vp, _vp, _i32, _vp, _vp, _vp, _i32, _i32, _i32, _vp],
+    "pq3d_gate_mix": [_vp, _vp, _vp, _vp, _i64, _vp],
+    "pq3d_cast_bf16": [_vp, _vp, _vp, _i64, _vp],
+}
+
+
+def declared_symbols() -> List[str]:
+    """Every function include/pq3d_b200.h declares."""
+    txt = open(HEADER).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(pq3d_[a-z0-9_]+)\s*\(", txt)))
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"pq3d_b200: CUDA extension {LIB_PATH} is missing — run `python -m pq3d_b200.build` "
+                "(there is no CPU or PyTorch fallback for the decoder kernels)")
+        l = C.CDLL(LIB_PATH)
+        l.pq3d_last_error.restype = C.c_char_p
+        l.pq3d_last_error.argtypes = []
+        l.pq3d_abi_version.restype = C.c_int
+        for name, args in SIGNATURES.items():
+            fn = getattr(l, name)
+            fn.argtypes = args
+            fn.restype = C.c_int
+        _lib = l
+    return _lib
+
+
+class Pq3dError(RuntimeError):
+    pass
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        raise Pq3dError(f"{what} failed (code {rc}): {lib().pq3d_last_error().decode()}")

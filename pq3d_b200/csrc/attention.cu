@@ -1,0 +1,426 @@
+// pq3d_attention_fwd: masked softmax attention of N queries over a scene memory, on tcgen05.
+//
+// Replaces the core of nn.MultiheadAttention(add_zero_attn=True) inside CrossAttentionLayer
+// (modules/grounding/query_encoder.py:288-307 -> torch/nn/functional.py:6585-6647: zero key/value
+// appended after projection, float -inf mask, baddbmm, softmax, bmm) and, with the spatial-bias
+// option, MultiHeadAttentionSpatial fusion 'mul' (modules/layers/transformers.py:189-240:
+// softmax(log(clamp(relu(W5 . pairwise_locs + b), 1e-6)) + q.k/sqrt(dh))).
+//
+// Inputs are already projected: Q (pre-scaled by 1/sqrt(dh)), K as [token, feature] and V TRANSPOSED
+// as [feature, token] (the projection GEMM writes V^T directly by swapping its operands), so every
+// MMA operand is K-major and TMA-loadable with the 128-byte swizzle.
+//
+// One CTA = (head, scene, memory, 128-query tile).  192 threads:
+//   warp 0      TMA producer: Q tile once, then K (pass 1) / K + V^T (pass 2) tiles of 128 keys into
+//               a 3-stage ring
+//   warp 1      tcgen05.mma issuer: S = Q K^T (128x128, fp32 in TMEM, double-buffered),
+//               O += P V (128x64 in TMEM); P comes from shared memory (bf16, swizzled K-major)
+//   warps 2..5  softmax, one query row per thread (TMEM lane = row): pass 1 row maxima, pass 2
+//               p = exp2((s - m) log2e), row sums, P tiles; finalize with the analytic zero-attn
+//               column (score 0, value 0: denominator += exp(-m), m >= 0) and store O as bf16.
+// Two passes over K instead of an online-softmax rescale of O: N <= 128 queries per CTA make the
+// second QK^T cheap on the tensor pipe, and O never needs a TMEM read-modify-write.
+// Masks arrive bit-packed (1 = ignore), 128 keys = one uint4 per row per tile; key-padding masks
+// broadcast over rows with a zero row stride.  Bits past S are set by the packer.
+#include <cstring>
+
+#include "host_common.h"
+#include "ptx.cuh"
+
+namespace pq3d {
+
+constexpr int kMaxMem = 4;
+constexpr int kAttnThreads = 192;
+constexpr int kKvTile = 128;
+constexpr int kKvStages = 3;
+constexpr int kHeadDim = 64;
+
+struct AttnMaps {
+  CUtensorMap q;
+  CUtensorMap k[kMaxMem];
+  CUtensorMap vt[kMaxMem];
+};
+
+struct AttnMem {
+  const uint32_t* mask_bits;  // may be null (nothing masked; tail handled by S)
+  int64_t mask_b_stride, mask_h_stride, mask_q_stride;  // in 32-bit words
+  int32_t S;
+  int32_t k_col0;
+  int32_t vt_row0;
+  int32_t pad_;
+};
+
+struct AttnParams {
+  AttnMem mem[kMaxMem];
+  __nv_bfloat16* O;
+  int64_t ldo, o_mem_stride;
+  int32_t q_mem_stride;
+  int32_t B, H, Nq, q_tiles;
+  int32_t zero_attn;
+  const float* pairwise_locs;  // [B, Nq, Nq, 5] or null
+  const float* loc_w;          // [H, 5]
+  const float* loc_b;          // [H]
+};
+
+constexpr int kQBytes = 128 * kHeadDim * 2;           // 16 KB
+constexpr int kKBytes = kKvTile * kHeadDim * 2;       // 16 KB
+constexpr int kVBytes = kHeadDim * kKvTile * 2;       // 16 KB (two [64 x 64] boxes)
+constexpr int kPBytes = 128 * kKvTile * 2;            // 32 KB (two [128 x 64] swizzle-atom columns)
+constexpr int kAttnSmem = kQBytes + kKvStages * (kKBytes + kVBytes) + 2 * kPBytes + 1024 + 256;
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__global__ void __launch_bounds__(kAttnThreads, 1)
+attention_fwd_kernel(const __grid_constant__ AttnMaps maps, const AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sKV = sQ + kQBytes;
+  uint8_t* sP = sKV + kKvStages * (kKBytes + kVBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * kPBytes);
+  uint64_t* q_full = bars;
+  uint64_t* kv_full = bars + 1;
+  uint64_t* kv_empty = kv_full + kKvStages;
+  uint64_t* s_full = kv_empty + kKvStages;
+  uint64_t* s_empty = s_full + 2;
+  uint64_t* p_full = s_empty + 2;
+  uint64_t* p_empty = p_full + 2;
+  uint64_t* o_full = p_empty + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int h = blockIdx.x;
+  const int b = blockIdx.y;
+  const int mi = blockIdx.z / p.q_tiles;
+  const int qt = blockIdx.z % p.q_tiles;
+  const AttnMem& mem = p.mem[mi];
+  const int T = (mem.S + kKvTile - 1) / kKvTile;
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&maps.q);
+    tma_prefetch_desc(&maps.k[mi]);
+    tma_prefetch_desc(&maps.vt[mi]);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < kKvStages; ++s) {
+      mbar_init(&kv_full[s], 1);
+      mbar_init(&kv_empty[s], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&s_empty[i], 4);
+      mbar_init(&p_full[i], 4);
+      mbar_init(&p_empty[i], 1);
+    }
+    mbar_init(o_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_S0 = tmem_base;        // columns [0,128) and [128,256): S double buffer
+  const uint32_t tmem_O = tmem_base + 256;   // columns [256,320): O
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (elect_one()) {
+      mbar_arrive_expect_tx(q_full, kQBytes);
+      tma_load_3d(sQ, &maps.q, q_full, mi * p.q_mem_stride + h * kHeadDim, qt * 128, b);
+      int it = 0;
+      for (int pass = 0; pass < 2; ++pass) {
+        for (int t = 0; t < T; ++t, ++it) {
+          const int s = it % kKvStages;
+          mbar_wait(&kv_empty[s], ((it / kKvStages) & 1) ^ 1, 100 + s);
+          uint8_t* sk = sKV + s * (kKBytes + kVBytes);
+          mbar_arrive_expect_tx(&kv_full[s], pass == 0 ? kKBytes : kKBytes + kVBytes);
+          tma_load_3d(sk, &maps.k[mi], &kv_full[s], mem.k_col0 + h * kHeadDim, t * kKvTile, b);
+          if (pass == 1) {
+            tma_load_3d(sk + kKBytes, &maps.vt[mi], &kv_full[s], t * kKvTile, b, mem.vt_row0 + h * kHeadDim);
+            tma_load_3d(sk + kKBytes + kVBytes / 2, &maps.vt[mi], &kv_full[s], t * kKvTile + 64, b,
+                        mem.vt_row0 + h * kHeadDim);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (elect_one()) {
+      constexpr uint32_t idesc_s = umma_idesc_bf16(128, kKvTile);
+      constexpr uint32_t idesc_o = umma_idesc_bf16(128, kHeadDim);
+      const uint32_t q_addr = smem_u32(sQ);
+      int it = 0, g = 0;
+      auto issue_s = [&](bool release_kv) {
+        const int s = it % kKvStages;
+        mbar_wait(&kv_full[s], (it / kKvStages) & 1, 200 + s);
+        const int sb = g & 1;
+        mbar_wait(&s_empty[sb], ((g >> 1) & 1) ^ 1, 210 + sb);
+        tc_fence_after();
+        const uint32_t k_addr = smem_u32(sKV + s * (kKBytes + kVBytes));
+#pragma unroll
+        for (int k = 0; k < kHeadDim / 16; ++k)
+          umma_ss(tmem_S0 + sb * kKvTile, umma_desc_k_sw128(q_addr + k * 32), umma_desc_k_sw128(k_addr + k * 32),
+                  idesc_s, k != 0 ? 1u : 0u);
+        if (release_kv) tc_commit(&kv_empty[s]);
+        tc_commit(&s_full[sb]);
+        ++it;
+        ++g;
+      };
+      mbar_wait(q_full, 0, 220);
+      for (int t = 0; t < T; ++t) issue_s(true);  // pass 1: scores only
+      const int it2 = it;                         // ring position of pass-2 tile 0
+      issue_s(false);
+      for (int t = 0; t < T; ++t) {
+        if (t + 1 < T) issue_s(false);
+        const int pb = t & 1;
+        mbar_wait(&p_full[pb], (t >> 1) & 1, 230 + pb);
+        tc_fence_after();
+        const int s = (it2 + t) % kKvStages;
+        const uint32_t v_addr = smem_u32(sKV + s * (kKBytes + kVBytes) + kKBytes);
+        const uint32_t p_addr = smem_u32(sP + pb * kPBytes);
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_ss(tmem_O, umma_desc_k_sw128(p_addr + j * (kPBytes / 2) + k * 32),
+                    umma_desc_k_sw128(v_addr + j * (kVBytes / 2) + k * 32), idesc_o, (t | j | k) != 0 ? 1u : 0u);
+        }
+        tc_commit(&kv_empty[s]);
+        tc_commit(&p_empty[pb]);
+      }
+      tc_commit(o_full);
+    }
+  } else {
+    // ------------------------------------------------------------------ softmax warps
+    const int quad = warp & 3;
+    const int r = quad * 32 + lane_id();          // row in the query tile == TMEM lane
+    const int n = qt * 128 + r;                   // query index in the scene
+    const int n_c = n < p.Nq ? n : p.Nq - 1;      // clamped for reads
+    const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
+    const uint32_t* mrow = mem.mask_bits == nullptr
+                               ? nullptr
+                               : mem.mask_bits + b * mem.mask_b_stride + h * mem.mask_h_stride + n_c * mem.mask_q_stride;
+    const bool spatial = p.pairwise_locs != nullptr;
+    float lw0 = 0, lw1 = 0, lw2 = 0, lw3 = 0, lw4 = 0, lb = 0;
+    const float* loc_row = nullptr;
+    if (spatial) {
+      lw0 = p.loc_w[h * 5 + 0]; lw1 = p.loc_w[h * 5 + 1]; lw2 = p.loc_w[h * 5 + 2];
+      lw3 = p.loc_w[h * 5 + 3]; lw4 = p.loc_w[h * 5 + 4]; lb = p.loc_b[h];
+      loc_row = p.pairwise_locs + (static_cast<int64_t>(b) * p.Nq + n_c) * p.Nq * 5;
+    }
+    constexpr float kLog2e = 1.4426950408889634f;
+    const float kNegInf = __int_as_float(0xff800000);
+
+    auto mask_words = [&](int t) -> uint4 {
+      if (mrow != nullptr) return __ldg(reinterpret_cast<const uint4*>(mrow) + t);
+      // no mask tensor: only the tail past S is ignored
+      uint4 w;
+      uint32_t* wp = reinterpret_cast<uint32_t*>(&w);
+      for (int c = 0; c < 4; ++c) {
+        const int rem = mem.S - (t * kKvTile + c * 32);
+        wp[c] = rem >= 32 ? 0u : (rem <= 0 ? 0xffffffffu : (0xffffffffu << rem));
+      }
+      return w;
+    };
+    auto score = [&](uint32_t raw, int key, uint32_t word, int j) -> float {
+      float s = __uint_as_float(raw);
+      if (spatial && key < mem.S) {
+        const float* l5 = loc_row + key * 5;
+        float v = fmaf(l5[0], lw0, fmaf(l5[1], lw1, fmaf(l5[2], lw2, fmaf(l5[3], lw3, fmaf(l5[4], lw4, lb)))));
+        s += __logf(fmaxf(fmaxf(v, 0.f), 1e-6f));
+      }
+      return ((word >> j) & 1u) ? kNegInf : s;
+    };
+
+    int g = 0;
+    float m_run = kNegInf;
+    for (int t = 0; t < T; ++t, ++g) {  // ---- pass 1: row maxima
+      const int sb = g & 1;
+      const uint4 mw = mask_words(t);
+      const uint32_t* mwp = reinterpret_cast<const uint32_t*>(&mw);
+      mbar_wait(&s_full[sb], (g >> 1) & 1, 300 + sb);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t acc[32];
+        tmem_ld_32x32(tmem_S0 + sb * kKvTile + lane_off + c * 32, acc);
+        tmem_ld_wait();
+        const uint32_t word = mwp[c];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) m_run = fmaxf(m_run, score(acc[j], t * kKvTile + c * 32 + j, word, j));
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane_id() == 0) mbar_arrive(&s_empty[sb]);
+    }
+    const float m = p.zero_attn ? fmaxf(m_run, 0.f) : m_run;
+    const float m_l2 = (m == kNegInf ? 0.f : m) * kLog2e;
+    float l = 0.f;
+    for (int t = 0; t < T; ++t, ++g) {  // ---- pass 2: probabilities
+      const int sb = g & 1;
+      const int pb = t & 1;
+      const uint4 mw = mask_words(t);
+      const uint32_t* mwp = reinterpret_cast<const uint32_t*>(&mw);
+      mbar_wait(&s_full[sb], (g >> 1) & 1, 310 + sb);
+      mbar_wait(&p_empty[pb], ((t >> 1) & 1) ^ 1, 320 + pb);
+      tc_fence_after();
+      uint8_t* prow = sP + pb * kPBytes + r * 128;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t acc[32];
+        tmem_ld_32x32(tmem_S0 + sb * kKvTile + lane_off + c * 32, acc);
+        tmem_ld_wait();
+        const uint32_t word = mwp[c];
+        float pv[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float s = score(acc[j], t * kKvTile + c * 32 + j, word, j);
+          const float e = ex2_approx(fmaf(s, kLog2e, -m_l2));  // ex2(-inf) = 0 for masked keys
+          pv[j] = e;
+          l += e;
+        }
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
+          uint4 u;
+          u.x = pack_bf16x2(pv[q4 * 8 + 0], pv[q4 * 8 + 1]);
+          u.y = pack_bf16x2(pv[q4 * 8 + 2], pv[q4 * 8 + 3]);
+          u.z = pack_bf16x2(pv[q4 * 8 + 4], pv[q4 * 8 + 5]);
+          u.w = pack_bf16x2(pv[q4 * 8 + 6], pv[q4 * 8 + 7]);
+          const int ci = c * 4 + q4;                 // 16-byte chunk index along the 128 keys
+          const int atom = ci >> 3, cc = ci & 7;     // swizzle-atom column, chunk inside its 128-B row
+          *reinterpret_cast<uint4*>(prow + atom * (kPBytes / 2) + ((cc ^ (r & 7)) << 4)) = u;
+        }
+      }
+      tc_fence_before();
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane_id() == 0) {
+        mbar_arrive(&s_empty[sb]);
+        mbar_arrive(&p_full[pb]);
+      }
+    }
+    // ---- finalize: zero-attn column, normalise, store
+    if (p.zero_attn) l += ex2_approx(-m_l2);
+    const float inv = 1.f / l;
+    mbar_wait(o_full, 0, 330);
+    tc_fence_after();
+    __nv_bfloat16* orow = p.O + mi * p.o_mem_stride + (static_cast<int64_t>(b) * p.Nq + n_c) * p.ldo + h * kHeadDim;
+#pragma unroll 1
+    for (int c = 0; c < 2; ++c) {
+      uint32_t acc[32];
+      tmem_ld_32x32(tmem_O + lane_off + c * 32, acc);
+      tmem_ld_wait();
+      if (n < p.Nq) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          uint4 u;
+          u.x = pack_bf16x2(__uint_as_float(acc[j]) * inv, __uint_as_float(acc[j + 1]) * inv);
+          u.y = pack_bf16x2(__uint_as_float(acc[j + 2]) * inv, __uint_as_float(acc[j + 3]) * inv);
+          u.z = pack_bf16x2(__uint_as_float(acc[j + 4]) * inv, __uint_as_float(acc[j + 5]) * inv);
+          u.w = pack_bf16x2(__uint_as_float(acc[j + 6]) * inv, __uint_as_float(acc[j + 7]) * inv);
+          *reinterpret_cast<uint4*>(orow + c * 32 + j) = u;
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+}  // namespace pq3d
+
+using namespace pq3d;
+
+extern "C" int pq3d_attention_fwd(int n_mem, const void* Q, int64_t ldq, int64_t q_mem_stride, const void* const* K,
+                                  const int64_t* ldk, const int64_t* k_col0, const void* const* Vt,
+                                  const int64_t* ldvt, const int64_t* vt_row0, const int64_t* vt_rows,
+                                  const int32_t* S, const int32_t* S_pitch, const uint32_t* const* mask_bits,
+                                  const int64_t* mask_b_stride, const int64_t* mask_h_stride,
+                                  const int64_t* mask_q_stride, void* O, int64_t ldo, int64_t o_mem_stride, int B,
+                                  int H, int Nq, int zero_attn, const float* pairwise_locs, const float* loc_w,
+                                  const float* loc_b, void* stream) {
+  PQ3D_CHECK_ARG(n_mem >= 1 && n_mem <= kMaxMem, "pq3d_attention_fwd: n_mem=%d not in [1,%d]", n_mem, kMaxMem);
+  PQ3D_CHECK_ARG(Q && O && K && Vt && S && S_pitch, "pq3d_attention_fwd: null argument");
+  PQ3D_CHECK_ARG(B > 0 && H > 0 && Nq > 0, "pq3d_attention_fwd: bad shape B=%d H=%d Nq=%d", B, H, Nq);
+  PQ3D_CHECK_ARG(ldq % 8 == 0 && ldo % 8 == 0 && (reinterpret_cast<uintptr_t>(Q) & 15) == 0 &&
+                     (reinterpret_cast<uintptr_t>(O) & 15) == 0 && (o_mem_stride % 8) == 0,
+                 "pq3d_attention_fwd: Q / O must be 16-byte aligned with leading dimensions multiple of 8");
+  PQ3D_CHECK_ARG((pairwise_locs == nullptr) || (loc_w && loc_b), "pq3d_attention_fwd: spatial bias needs loc_w and loc_b");
+  AttnMaps maps;          // filled per call; passed by value to the launch
+  AttnParams p;
+  memset(&p, 0, sizeof(p));
+  {
+    uint64_t dims[3] = {(uint64_t)ldq, (uint64_t)Nq, (uint64_t)B};
+    uint64_t strides[2] = {(uint64_t)ldq * 2, (uint64_t)Nq * ldq * 2};
+    uint32_t box[3] = {(uint32_t)kHeadDim, 128u, 1u};
+    int rc = make_tmap_bf16(&maps.q, Q, 3, dims, strides, box);
+    if (rc != PQ3D_OK) return rc;
+  }
+  for (int i = 0; i < n_mem; ++i) {
+    PQ3D_CHECK_ARG(S[i] > 0 && S_pitch[i] >= S[i] && S_pitch[i] % 8 == 0,
+                   "pq3d_attention_fwd: memory %d: S=%d S_pitch=%d (pitch must be >= S and a multiple of 8)", i, S[i],
+                   S_pitch[i]);
+    PQ3D_CHECK_ARG(ldk[i] % 8 == 0 && ldvt[i] % 8 == 0 && ldvt[i] >= (int64_t)B * S_pitch[i] &&
+                       (reinterpret_cast<uintptr_t>(K[i]) & 15) == 0 && (reinterpret_cast<uintptr_t>(Vt[i]) & 15) == 0,
+                   "pq3d_attention_fwd: memory %d: K / V^T alignment or leading dimension", i);
+    {
+      uint64_t dims[3] = {(uint64_t)ldk[i], (uint64_t)S[i], (uint64_t)B};
+      uint64_t strides[2] = {(uint64_t)ldk[i] * 2, (uint64_t)S_pitch[i] * ldk[i] * 2};
+      uint32_t box[3] = {(uint32_t)kHeadDim, (uint32_t)kKvTile, 1u};
+      int rc = make_tmap_bf16(&maps.k[i], K[i], 3, dims, strides, box);
+      if (rc != PQ3D_OK) return rc;
+    }
+    {
+      uint64_t dims[3] = {(uint64_t)S[i], (uint64_t)B, (uint64_t)vt_rows[i]};
+      uint64_t strides[2] = {(uint64_t)S_pitch[i] * 2, (uint64_t)ldvt[i] * 2};
+      uint32_t box[3] = {64u, 1u, (uint32_t)kHeadDim};
+      int rc = make_tmap_bf16(&maps.vt[i], Vt[i], 3, dims, strides, box);
+      if (rc != PQ3D_OK) return rc;
+    }
+    AttnMem& m = p.mem[i];
+    m.mask_bits = mask_bits ? mask_bits[i] : nullptr;
+    m.mask_b_stride = mask_bits ? mask_b_stride[i] : 0;
+    m.mask_h_stride = mask_bits ? mask_h_stride[i] : 0;
+    m.mask_q_stride = mask_bits ? mask_q_stride[i] : 0;
+    PQ3D_CHECK_ARG(m.mask_bits == nullptr || ((reinterpret_cast<uintptr_t>(m.mask_bits) & 15) == 0 &&
+                                              m.mask_b_stride % 4 == 0 && m.mask_h_stride % 4 == 0 &&
+                                              m.mask_q_stride % 4 == 0),
+                   "pq3d_attention_fwd: memory %d: packed mask must be 16-byte aligned with strides multiple of 4 words", i);
+    m.S = S[i];
+    m.k_col0 = (int32_t)k_col0[i];
+    m.vt_row0 = (int32_t)vt_row0[i];
+  }
+  for (int i = n_mem; i < kMaxMem; ++i) {
+    maps.k[i] = maps.k[0];
+    maps.vt[i] = maps.vt[0];
+  }
+  p.O = reinterpret_cast<__nv_bfloat16*>(O);
+  p.ldo = ldo;
+  p.o_mem_stride = o_mem_stride;
+  p.q_mem_stride = (int32_t)q_mem_stride;
+  p.B = B;
+  p.H = H;
+  p.Nq = Nq;
+  p.q_tiles = (Nq + 127) / 128;
+  p.zero_attn = zero_attn;
+  p.pairwise_locs = pairwise_locs;
+  p.loc_w = loc_w;
+  p.loc_b = loc_b;
+  static bool configured = false;
+  if (!configured) {
+    PQ3D_CUDA(cudaFuncSetAttribute(attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
+    configured = true;
+  }
+  dim3 grid(H, B, n_mem * p.q_tiles);
+  attention_fwd_kernel<<<grid, kAttnThreads, kAttnSmem, reinterpret_cast<cudaStream_t>(stream)>>>(maps, p);
+  PQ3D_CUDA(cudaGetLastError());
+  return PQ3D_OK;
+}

@@ -1,0 +1,301 @@
+// HBM-bound companions of the tensor-core kernels: memory ingest (fp32 -> bf16, +pos), residual +
+// LayerNorm (+ mean over memories, + bf16 operand emission), mask bit-packing and the mask-head
+// finalisation.  All are streaming kernels: 16-byte accesses, one warp per 768-wide row.
+#include "host_common.h"
+#include "ptx.cuh"
+
+namespace pq3d {
+
+// ------------------------------------------------------------------------------------------------
+// ingest: x_v = bf16(feat), x_k = bf16(feat + pos); rows s in [S, S_pitch) are zero-filled so that
+// masked P (= 0) times padded V stays 0.   CrossAttentionLayer.with_pos_embed
+// (modules/grounding/query_encoder.py:285-286,298-300).
+// ------------------------------------------------------------------------------------------------
+__global__ void ingest_kernel(const float* __restrict__ feat, const float* __restrict__ pos,
+                              __nv_bfloat16* __restrict__ xk, __nv_bfloat16* __restrict__ xv, int B, int S,
+                              int S_pitch, int D) {
+  const int vec_per_row = D / 8;
+  const int64_t total = static_cast<int64_t>(B) * S_pitch * vec_per_row;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int v = static_cast<int>(i % vec_per_row);
+    const int64_t row = i / vec_per_row;
+    const int s = static_cast<int>(row % S_pitch);
+    const int b = static_cast<int>(row / S_pitch);
+    uint4 ok = make_uint4(0, 0, 0, 0), ov = make_uint4(0, 0, 0, 0);
+    if (s < S) {
+      const int64_t src = (static_cast<int64_t>(b) * S + s) * D + v * 8;
+      const float4 f0 = __ldg(reinterpret_cast<const float4*>(feat + src));
+      const float4 f1 = __ldg(reinterpret_cast<const float4*>(feat + src) + 1);
+      ov.x = pack_bf16x2(f0.x, f0.y); ov.y = pack_bf16x2(f0.z, f0.w);
+      ov.z = pack_bf16x2(f1.x, f1.y); ov.w = pack_bf16x2(f1.z, f1.w);
+      if (pos != nullptr) {
+        const float4 p0 = __ldg(reinterpret_cast<const float4*>(pos + src));
+        const float4 p1 = __ldg(reinterpret_cast<const float4*>(pos + src) + 1);
+        ok.x = pack_bf16x2(f0.x + p0.x, f0.y + p0.y); ok.y = pack_bf16x2(f0.z + p0.z, f0.w + p0.w);
+        ok.z = pack_bf16x2(f1.x + p1.x, f1.y + p1.y); ok.w = pack_bf16x2(f1.z + p1.z, f1.w + p1.w);
+      }
+    }
+    const int64_t dst = row * D + v * 8;
+    if (xv != nullptr) *reinterpret_cast<uint4*>(xv + dst) = ov;
+    if (xk != nullptr) *reinterpret_cast<uint4*>(xk + dst) = (pos != nullptr) ? ok : ov;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// add_layernorm: out = (1/G) * sum_g LN_g(residual + y_g)   (post-norm residual blocks,
+// query_encoder.py:304-305,449-450,386-387; the mean over memories is parallel_ca's eval branch,
+// :153).  Optionally emits the bf16 operands of the next GEMMs: bf16(out) and bf16(out + pos).
+// One warp per row; two-pass variance in fp32.
+// ------------------------------------------------------------------------------------------------
+constexpr int kLnMaxVec = 8;  // D <= 1024
+
+__global__ void add_layernorm_kernel(const float* __restrict__ y, int64_t y_group_stride,
+                                     const float* __restrict__ residual, const float* __restrict__ gamma,
+                                     const float* __restrict__ beta, int G, float eps, int R, int D,
+                                     const float* __restrict__ pos, float* __restrict__ out_f32,
+                                     __nv_bfloat16* __restrict__ out_bf16, __nv_bfloat16* __restrict__ out_pos_bf16) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= R) return;
+  const int lane = threadIdx.x & 31;
+  const int nv = D / 128;  // float4 chunks per lane
+  float4 res[kLnMaxVec], acc[kLnMaxVec];
+#pragma unroll
+  for (int i = 0; i < kLnMaxVec; ++i) {
+    acc[i] = make_float4(0, 0, 0, 0);
+    res[i] = make_float4(0, 0, 0, 0);
+    if (i < nv && residual != nullptr)
+      res[i] = __ldg(reinterpret_cast<const float4*>(residual + static_cast<int64_t>(row) * D) + i * 32 + lane);
+  }
+  const float inv_d = 1.f / static_cast<float>(D);
+  for (int g = 0; g < G; ++g) {
+    float4 x[kLnMaxVec];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < kLnMaxVec; ++i) {
+      if (i < nv) {
+        float4 v = res[i];
+        if (y != nullptr) {
+          const float4 t =
+              __ldg(reinterpret_cast<const float4*>(y + g * y_group_stride + static_cast<int64_t>(row) * D) + i * 32 + lane);
+          v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
+        }
+        x[i] = v;
+        sum += (v.x + v.y) + (v.z + v.w);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum * inv_d;
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < kLnMaxVec; ++i) {
+      if (i < nv) {
+        const float a = x[i].x - mean, b = x[i].y - mean, c = x[i].z - mean, d = x[i].w - mean;
+        sq += (a * a + b * b) + (c * c + d * d);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    const float rstd = rsqrtf(sq * inv_d + eps);
+#pragma unroll
+    for (int i = 0; i < kLnMaxVec; ++i) {
+      if (i < nv) {
+        const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma + g * D) + i * 32 + lane);
+        const float4 be = __ldg(reinterpret_cast<const float4*>(beta + g * D) + i * 32 + lane);
+        acc[i].x += (x[i].x - mean) * rstd * ga.x + be.x;
+        acc[i].y += (x[i].y - mean) * rstd * ga.y + be.y;
+        acc[i].z += (x[i].z - mean) * rstd * ga.z + be.z;
+        acc[i].w += (x[i].w - mean) * rstd * ga.w + be.w;
+      }
+    }
+  }
+  const float inv_g = 1.f / static_cast<float>(G);
+#pragma unroll
+  for (int i = 0; i < kLnMaxVec; ++i) {
+    if (i < nv) {
+      float4 o = acc[i];
+      if (G > 1) { o.x *= inv_g; o.y *= inv_g; o.z *= inv_g; o.w *= inv_g; }
+      const int64_t off = static_cast<int64_t>(row) * D + (i * 32 + lane) * 4;
+      if (out_f32 != nullptr) *reinterpret_cast<float4*>(out_f32 + off) = o;
+      if (out_bf16 != nullptr)
+        *reinterpret_cast<uint2*>(out_bf16 + off) = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
+      if (out_pos_bf16 != nullptr) {
+        float4 q = o;
+        if (pos != nullptr) {
+          const float4 pp = __ldg(reinterpret_cast<const float4*>(pos + off));
+          q.x += pp.x; q.y += pp.y; q.z += pp.z; q.w += pp.w;
+        }
+        *reinterpret_cast<uint2*>(out_pos_bf16 + off) = make_uint2(pack_bf16x2(q.x, q.y), pack_bf16x2(q.z, q.w));
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// pack_mask: bool bytes [rows, S] (1 = ignore) -> bits [rows, W], W = 4*ceil(S/128) words; bits past
+// S are set.  unmask_full_rows implements `attn_mask[attn_mask.all(-1)] = False`
+// (query_encoder.py:83): a query that would see nothing sees everything.  One warp per row.
+// ------------------------------------------------------------------------------------------------
+__global__ void pack_mask_kernel(const uint8_t* __restrict__ mask, uint32_t* __restrict__ bits, int64_t rows, int S,
+                                 int W, int unmask_full_rows, uint8_t* __restrict__ mask_fixed) {
+  const int64_t row = blockIdx.x * static_cast<int64_t>(blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const uint8_t* src = mask + row * S;
+  bool all_masked = true;
+  if (unmask_full_rows) {
+    for (int s0 = 0; s0 < S; s0 += 32) {
+      const int s = s0 + lane;
+      const bool mk = (s < S) ? (src[s] != 0) : true;
+      if (!__all_sync(0xffffffffu, mk)) { all_masked = false; break; }
+    }
+  } else {
+    all_masked = false;
+  }
+  for (int w = 0; w < W; ++w) {
+    const int s = w * 32 + lane;
+    bool mk = (s < S) ? (src[s] != 0) : true;
+    if (all_masked && s < S) mk = false;
+    const uint32_t word = __ballot_sync(0xffffffffu, mk);
+    if (lane == 0) bits[row * W + w] = word;
+    if (mask_fixed != nullptr && s < S) mask_fixed[row * S + s] = mk ? 1 : 0;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// mask_head_finalize (modules/heads/mask_head.py:36-43): raw = sum_m valid_m * (k_m . q_m) arrives
+// as [B, S, N] fp32;  mask_logits = raw / (sum_m valid_m + 1e-8);  mask_logits[seg_pad] = -1e6;
+// attn_mask[b, n, s] = sigmoid(mask_logits[b, s, n]) < 0.5   (transposed, bool bytes).
+// 32x32 tiles through shared memory so both the [S,N] read/write and the [N,S] write coalesce.
+// ------------------------------------------------------------------------------------------------
+__global__ void mask_head_finalize_kernel(const float* __restrict__ raw, const uint8_t* const* __restrict__ mem_masks,
+                                          int n_mem, const uint8_t* __restrict__ seg_masks,
+                                          float* __restrict__ mask_logits, uint8_t* __restrict__ attn_mask, int S,
+                                          int N) {
+  __shared__ uint8_t tile[32][33];
+  const int b = blockIdx.z;
+  const int s0 = blockIdx.x * 32, n0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int s = s0 + i, n = n0 + threadIdx.x;
+    uint8_t am = 0;
+    if (s < S && n < N) {
+      int cnt = 0;
+      for (int m = 0; m < n_mem; ++m) cnt += (mem_masks[m][static_cast<int64_t>(b) * S + s] == 0) ? 1 : 0;
+      const int64_t idx = (static_cast<int64_t>(b) * S + s) * N + n;
+      float v = __fdiv_rn(raw[idx], static_cast<float>(cnt) + 1e-8f);
+      if (seg_masks[static_cast<int64_t>(b) * S + s] != 0) v = -1e6f;
+      mask_logits[idx] = v;
+      const float sg = __fdiv_rn(1.f, 1.f + expf(-v));
+      am = sg < 0.5f ? 1 : 0;
+    }
+    tile[i][threadIdx.x] = am;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int n = n0 + i, s = s0 + threadIdx.x;
+    if (n < N && s < S) attn_mask[(static_cast<int64_t>(b) * N + n) * S + s] = tile[threadIdx.x][i];
+  }
+}
+
+// gate mix for structure 'gate' (query_encoder.py:166-170): out = (1 - sigmoid(g)) * q + sigmoid(g) * u
+__global__ void gate_mix_kernel(const float* __restrict__ gate_logits, const float* __restrict__ query,
+                                const float* __restrict__ update, float* __restrict__ out, int64_t n) {
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const float g = __fdiv_rn(1.f, 1.f + expf(-gate_logits[i]));
+    out[i] = (1.f - g) * query[i] + g * update[i];
+  }
+}
+
+// plain fp32 -> bf16 cast (+ optional add), for operands that do not pass through a LayerNorm
+__global__ void cast_bf16_kernel(const float* __restrict__ x, const float* __restrict__ add,
+                                 __nv_bfloat16* __restrict__ out, int64_t n4) {
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n4;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
+    if (add != nullptr) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(add) + i);
+      v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
+    }
+    reinterpret_cast<uint2*>(out)[i] = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+  }
+}
+
+}  // namespace pq3d
+
+using namespace pq3d;
+
+static inline int grid_for(int64_t work_items, int threads) {
+  int64_t blocks = (work_items + threads - 1) / threads;
+  const int64_t cap = static_cast<int64_t>(sm_count()) * 16;
+  return static_cast<int>(blocks < 1 ? 1 : (blocks > cap ? cap : blocks));
+}
+
+extern "C" int pq3d_ingest_memory(const float* feat, const float* pos, void* xk, void* xv, int B, int S, int S_pitch,
+                                  int D, void* stream) {
+  PQ3D_CHECK_ARG(feat && (xk || xv), "pq3d_ingest_memory: null argument");
+  PQ3D_CHECK_ARG(B > 0 && S > 0 && S_pitch >= S && D % 8 == 0, "pq3d_ingest_memory: bad shape B=%d S=%d pitch=%d D=%d",
+                 B, S, S_pitch, D);
+  PQ3D_CHECK_ARG((reinterpret_cast<uintptr_t>(feat) & 15) == 0 && (reinterpret_cast<uintptr_t>(pos) & 15) == 0 &&
+                     (reinterpret_cast<uintptr_t>(xk) & 15) == 0 && (reinterpret_cast<uintptr_t>(xv) & 15) == 0,
+                 "pq3d_ingest_memory: pointers must be 16-byte aligned");
+  const int64_t total = static_cast<int64_t>(B) * S_pitch * (D / 8);
+  ingest_kernel<<<grid_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      feat, pos, reinterpret_cast<__nv_bfloat16*>(xk), reinterpret_cast<__nv_bfloat16*>(xv), B, S, S_pitch, D);
+  PQ3D_CUDA(cudaGetLastError());
+  return PQ3D_OK;
+}
+
+extern "C" int pq3d_add_layernorm(const float* y, int64_t y_group_stride, const float* residual, const float* gamma,
+                                  const float* beta, int G, float eps, int R, int D, const float* pos, float* out_f32,
+                                  void* out_bf16, void* out_pos_bf16, void* stream) {
+  PQ3D_CHECK_ARG((y || residual) && gamma && beta, "pq3d_add_layernorm: null argument");
+  PQ3D_CHECK_ARG(G >= 1 && R > 0 && D % 128 == 0 && D <= 128 * kLnMaxVec, "pq3d_add_layernorm: bad shape G=%d R=%d D=%d",
+                 G, R, D);
+  const int warps = 4;
+  add_layernorm_kernel<<<(R + warps - 1) / warps, warps * 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      y, y_group_stride, residual, gamma, beta, G, eps, R, D, pos, out_f32, reinterpret_cast<__nv_bfloat16*>(out_bf16),
+      reinterpret_cast<__nv_bfloat16*>(out_pos_bf16));
+  PQ3D_CUDA(cudaGetLastError());
+  return PQ3D_OK;
+}
+
+extern "C" int pq3d_pack_mask(const uint8_t* mask, uint32_t* bits, int64_t rows, int S, int unmask_full_rows,
+                              uint8_t* mask_fixed, void* stream) {
+  PQ3D_CHECK_ARG(mask && bits && rows > 0 && S > 0, "pq3d_pack_mask: bad argument");
+  const int W = ((S + 127) / 128) * 4;
+  const int warps = 8;
+  pack_mask_kernel<<<static_cast<unsigned>((rows + warps - 1) / warps), warps * 32, 0,
+                     reinterpret_cast<cudaStream_t>(stream)>>>(mask, bits, rows, S, W, unmask_full_rows, mask_fixed);
+  PQ3D_CUDA(cudaGetLastError());
+  return PQ3D_OK;
+}
+
+extern "C" int pq3d_mask_head_finalize(const float* raw, const uint8_t* const* mem_masks_dev, int n_mem,
+                                       const uint8_t* seg_masks, float* mask_logits, uint8_t* attn_mask, int B, int S,
+                                       int N, void* stream) {
+  PQ3D_CHECK_ARG(raw && mem_masks_dev && seg_masks && mask_logits && attn_mask && n_mem >= 1,
+                 "pq3d_mask_head_finalize: bad argument");
+  dim3 grid((S + 31) / 32, (N + 31) / 32, B), block(32, 8);
+  mask_head_finalize_kernel<<<grid, block, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      raw, mem_masks_dev, n_mem, seg_masks, mask_logits, attn_mask, S, N);
+  PQ3D_CUDA(cudaGetLastError());
+  return PQ3D_OK;
+}
+
+extern "C" int pq3d_gate_mix(const float* gate_logits, const float* query, const float* update, float* out, int64_t n,
+                             void* stream) {
+  PQ3D_CHECK_ARG(gate_logits && query && update && out && n > 0, "pq3d_gate_mix: bad argument");
+  gate_mix_kernel<<<grid_for(n, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(gate_logits, query, update, out, n);
+  PQ3D_CUDA(cudaGetLastError());
+  return PQ3D_OK;
+}
+
+extern "C" int pq3d_cast_bf16(const float* x, const float* add, void* out, int64_t n, void* stream) {
+  PQ3D_CHECK_ARG(x && out && n > 0 && n % 4 == 0, "pq3d_cast_bf16: n=%lld must be a positive multiple of 4", (long long)n);
+  cast_bf16_kernel<<<grid_for(n / 4, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      x, add, reinterpret_cast<__nv_bfloat16*>(out), n / 4);
+  PQ3D_CUDA(cudaGetLastError());
+  return PQ3D_OK;
+}

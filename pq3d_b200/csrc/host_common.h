@@ -1,0 +1,50 @@
+// Host-side plumbing shared by every C-ABI entry point: error reporting (return code +
+// pq3d_last_error(), never exit() — contrast the reference's CUDA_CHECK_ERRORS,
+// modules/third_party/pointnet2/_ext_src/include/cuda_utils.h:29-39) and TMA tensor-map encoding
+// through the driver entry point (no link-time dependency on libcuda).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+
+#define PQ3D_OK 0
+#define PQ3D_ERR_INVALID -1
+#define PQ3D_ERR_CUDA -2
+#define PQ3D_ERR_UNSUPPORTED -3
+
+namespace pq3d {
+
+int set_error(int code, const char* fmt, ...);
+const char* last_error();
+
+#define PQ3D_CHECK_ARG(cond, ...) \
+  do {                            \
+    if (!(cond)) return ::pq3d::set_error(PQ3D_ERR_INVALID, __VA_ARGS__); \
+  } while (0)
+
+#define PQ3D_CUDA(call)                                                                        \
+  do {                                                                                         \
+    cudaError_t e__ = (call);                                                                  \
+    if (e__ != cudaSuccess)                                                                    \
+      return ::pq3d::set_error(PQ3D_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), \
+                               __FILE__, __LINE__);                                            \
+  } while (0)
+
+// bf16 tensor map, 128-byte swizzle, zero OOB fill.  dims/strides innermost-first; strides in BYTES
+// for dims 1..rank-1 (dim 0 is contiguous).  Returns PQ3D_OK or an error code.
+int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                   const uint32_t* box);
+
+inline int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return n;
+}
+
+}  // namespace pq3d

@@ -1,0 +1,196 @@
+"""Tensor-level wrappers over the C ABI (include/pq3d_b200.h): dtype / contiguity / device checks
+live here (the mirror of the reference extension's CHECK_* macros,
+modules/third_party/pointnet2/_ext_src/include/utils.h:5-25); the kernels see raw pointers.
+All launches go to torch's current CUDA stream, so they are CUDA-graph capturable."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import _lib
+
+bf16 = torch.bfloat16
+LAUNCHES = 0          # kernels launched through this module (bench.py reports it as gpu_launches)
+
+
+def _count(n=1):
+    global LAUNCHES
+    LAUNCHES += n
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _chk(t: torch.Tensor, dtype, name: str, ndim: Optional[int] = None):
+    if not t.is_cuda:
+        raise ValueError(f"{name} must be a CUDA tensor (pq3d_b200 has no CPU path)")
+    if t.dtype != dtype:
+        raise TypeError(f"{name} must be {dtype}, got {t.dtype}")
+    if ndim is not None and t.ndim != ndim:
+        raise ValueError(f"{name} must be {ndim}-D, got shape {tuple(t.shape)}")
+
+
+def pad8(n: int) -> int:
+    return (n + 7) // 8 * 8
+
+
+def mask_words(S: int) -> int:
+    return (S + 127) // 128 * 4
+
+
+def linear(A: torch.Tensor, W: torch.Tensor, out: torch.Tensor, *, M: int, N: int, K: int,
+           bias: Optional[torch.Tensor] = None, bias_along_m: bool = False, bias_group_stride: int = 0,
+           groups: int = 1, a_group_rows: int = 0, w_group_rows: int = 0, ldc: Optional[int] = None,
+           c_group_stride: int = 0, row_zero: Optional[torch.Tensor] = None, row_zero_group_stride: int = 0,
+           alpha: float = 1.0, alpha_ncols: int = 0, relu: bool = False, block_n: int = 0) -> torch.Tensor:
+    """out[g] = epilogue(A[g] @ W[g].T); A, W are 2-D bf16 views with unit inner stride."""
+    _chk(A, bf16, "A", 2)
+    _chk(W, bf16, "W", 2)
+    if A.stride(1) != 1 or W.stride(1) != 1:
+        raise ValueError("A and W need unit stride along K")
+    if out.dtype not in (bf16, torch.float32):
+        raise TypeError("out must be bf16 or fp32")
+    if bias is not None:
+        _chk(bias, torch.float32, "bias")
+    if row_zero is not None and row_zero.dtype not in (torch.bool, torch.uint8):
+        raise TypeError("row_zero must be bool/uint8")
+    ldc = out.stride(-2) if ldc is None else ldc
+    rc = _lib.lib().pq3d_linear_bf16(
+        A.data_ptr(), A.stride(0), A.shape[0], a_group_rows, W.data_ptr(), W.stride(0), W.shape[0], w_group_rows,
+        out.data_ptr(), ldc, c_group_stride, int(out.dtype == torch.float32), _p(bias), bias_group_stride,
+        int(bias_along_m), _p(row_zero), row_zero_group_stride, M, N, K, groups, float(alpha), alpha_ncols,
+        int(relu), block_n, _stream())
+    _lib.check(rc, "pq3d_linear_bf16")
+    _count()
+    return out
+
+
+class AttnMemory:
+    """One memory's projected operands for `attention` (see pq3d_attention_fwd)."""
+    __slots__ = ("K", "k_col0", "Vt", "vt_row0", "S", "S_pitch", "mask_bits", "mask_b_stride", "mask_h_stride",
+                 "mask_q_stride")
+
+    def __init__(self, K, k_col0, Vt, vt_row0, S, S_pitch, mask_bits=None, mask_b_stride=0, mask_h_stride=0,
+                 mask_q_stride=0):
+        self.K, self.k_col0, self.Vt, self.vt_row0 = K, k_col0, Vt, vt_row0
+        self.S, self.S_pitch = S, S_pitch
+        self.mask_bits, self.mask_b_stride = mask_bits, mask_b_stride
+        self.mask_h_stride, self.mask_q_stride = mask_h_stride, mask_q_stride
+
+
+def attention(Q: torch.Tensor, q_mem_stride: int, mems: Sequence[AttnMemory], O: torch.Tensor, o_mem_stride: int,
+              B: int, H: int, Nq: int, zero_attn: bool, pairwise_locs: Optional[torch.Tensor] = None,
+              loc_w: Optional[torch.Tensor] = None, loc_b: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _chk(Q, bf16, "Q", 2)
+    _chk(O, bf16, "O")
+    n = len(mems)
+    vp = C.c_void_p * n
+    i64 = C.c_int64 * n
+    i32 = C.c_int32 * n
+    for m in mems:
+        _chk(m.K, bf16, "K", 2)
+        _chk(m.Vt, bf16, "Vt", 2)
+        if m.mask_bits is not None:
+            _chk(m.mask_bits, torch.int32, "mask_bits")
+    if pairwise_locs is not None:
+        _chk(pairwise_locs, torch.float32, "pairwise_locs", 4)
+        if not pairwise_locs.is_contiguous() or tuple(pairwise_locs.shape) != (B, Nq, Nq, 5):
+            raise ValueError("pairwise_locs must be contiguous (B, Nq, Nq, 5)")
+        _chk(loc_w, torch.float32, "loc_w")
+        _chk(loc_b, torch.float32, "loc_b")
+    has_mask = any(m.mask_bits is not None for m in mems)
+    rc = _lib.lib().pq3d_attention_fwd(
+        n, Q.data_ptr(), Q.stride(0), q_mem_stride,
+        vp(*[m.K.data_ptr() for m in mems]), i64(*[m.K.stride(0) for m in mems]), i64(*[m.k_col0 for m in mems]),
+        vp(*[m.Vt.data_ptr() for m in mems]), i64(*[m.Vt.stride(0) for m in mems]), i64(*[m.vt_row0 for m in mems]),
+        i64(*[m.Vt.shape[0] for m in mems]), i32(*[m.S for m in mems]), i32(*[m.S_pitch for m in mems]),
+        vp(*[_p(m.mask_bits) for m in mems]) if has_mask else None,
+        i64(*[m.mask_b_stride for m in mems]), i64(*[m.mask_h_stride for m in mems]),
+        i64(*[m.mask_q_stride for m in mems]),
+        O.data_ptr(), O.stride(-2), o_mem_stride, B, H, Nq, int(zero_attn),
+        _p(pairwise_locs), _p(loc_w), _p(loc_b), _stream())
+    _lib.check(rc, "pq3d_attention_fwd")
+    _count()
+    return O
+
+
+def ingest_memory(feat: torch.Tensor, pos: Optional[torch.Tensor], xk: Optional[torch.Tensor],
+                  xv: Optional[torch.Tensor], S_pitch: int):
+    _chk(feat, torch.float32, "feat", 3)
+    if not feat.is_contiguous():
+        raise ValueError("feat must be contiguous (B, S, D)")
+    B, S, D = feat.shape
+    if pos is not None:
+        _chk(pos, torch.float32, "pos", 3)
+        if not pos.is_contiguous() or pos.shape != feat.shape:
+            raise ValueError("pos must be contiguous and shaped like feat")
+    rc = _lib.lib().pq3d_ingest_memory(feat.data_ptr(), _p(pos), _p(xk), _p(xv), B, S, S_pitch, D, _stream())
+    _lib.check(rc, "pq3d_ingest_memory")
+    _count()
+
+
+def add_layernorm(y: Optional[torch.Tensor], residual: Optional[torch.Tensor], gamma: torch.Tensor,
+                  beta: torch.Tensor, eps: float, R: int, D: int, G: int = 1, y_group_stride: int = 0,
+                  pos: Optional[torch.Tensor] = None, out_f32: Optional[torch.Tensor] = None,
+                  out_bf16: Optional[torch.Tensor] = None, out_pos_bf16: Optional[torch.Tensor] = None):
+    for t, nm in ((y, "y"), (residual, "residual"), (gamma, "gamma"), (beta, "beta"), (pos, "pos"), (out_f32, "out_f32")):
+        if t is not None:
+            _chk(t, torch.float32, nm)
+    for t, nm in ((out_bf16, "out_bf16"), (out_pos_bf16, "out_pos_bf16")):
+        if t is not None:
+            _chk(t, bf16, nm)
+    rc = _lib.lib().pq3d_add_layernorm(_p(y), y_group_stride, _p(residual), gamma.data_ptr(), beta.data_ptr(), G,
+                                       float(eps), R, D, _p(pos), _p(out_f32), _p(out_bf16), _p(out_pos_bf16),
+                                       _stream())
+    _lib.check(rc, "pq3d_add_layernorm")
+    _count()
+
+
+def pack_mask(mask: torch.Tensor, bits: Optional[torch.Tensor] = None, unmask_full_rows: bool = False,
+              mask_fixed: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """bool (..., S) -> int32 (..., W) packed bits, 1 = ignore."""
+    if mask.dtype != torch.bool:
+        raise TypeError(f"mask must be torch.bool (PyTorch mask convention), got {mask.dtype}")
+    if not mask.is_cuda or not mask.is_contiguous():
+        raise ValueError("mask must be a contiguous CUDA tensor")
+    S = mask.shape[-1]
+    rows = mask.numel() // S
+    if bits is None:
+        bits = torch.empty(mask.shape[:-1] + (mask_words(S),), dtype=torch.int32, device=mask.device)
+    rc = _lib.lib().pq3d_pack_mask(mask.data_ptr(), bits.data_ptr(), rows, S, int(unmask_full_rows),
+                                   _p(mask_fixed), _stream())
+    _lib.check(rc, "pq3d_pack_mask")
+    _count()
+    return bits
+
+
+def mask_head_finalize(raw: torch.Tensor, mem_mask_ptrs: torch.Tensor, n_mem: int, seg_masks: torch.Tensor,
+                       mask_logits: torch.Tensor, attn_mask: torch.Tensor, B: int, S: int, N: int):
+    _chk(raw, torch.float32, "raw")
+    _chk(mask_logits, torch.float32, "mask_logits")
+    rc = _lib.lib().pq3d_mask_head_finalize(raw.data_ptr(), mem_mask_ptrs.data_ptr(), n_mem, seg_masks.data_ptr(),
+                                            mask_logits.data_ptr(), attn_mask.data_ptr(), B, S, N, _stream())
+    _lib.check(rc, "pq3d_mask_head_finalize")
+    _count()
+
+
+def gate_mix(gate_logits, query, update, out):
+    rc = _lib.lib().pq3d_gate_mix(gate_logits.data_ptr(), query.data_ptr(), update.data_ptr(), out.data_ptr(),
+                                  out.numel(), _stream())
+    _lib.check(rc, "pq3d_gate_mix")
+    _count()
+
+
+def cast_bf16(x: torch.Tensor, out: torch.Tensor, add: Optional[torch.Tensor] = None):
+    _chk(x, torch.float32, "x")
+    _chk(out, bf16, "out")
+    rc = _lib.lib().pq3d_cast_bf16(x.data_ptr(), _p(add), out.data_ptr(), x.numel(), _stream())
+    _lib.check(rc, "pq3d_cast_bf16")
+    _count()

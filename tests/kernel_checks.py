@@ -1,0 +1,294 @@
+"""GPU kernel checks, one per process so a trapping kernel cannot poison the others.
+
+    python tests/kernel_checks.py list
+    python tests/kernel_checks.py <check-name>        # exit 0 = pass
+
+Each check feeds a C-ABI kernel bf16-rounded random operands and compares against the same math in
+plain torch fp32 on the SAME rounded operands, so the only differences are accumulation order and
+the output rounding.  Tolerances (||a-b||inf / ||b||inf):
+  fp32 outputs : 1e-3 (north-star tolerance; observed ~1e-6)
+  bf16 outputs : 2^-8 = 3.9e-3 (one bf16 ulp of the largest element — the output format's own resolution)
+  bool / packed-bit outputs : exact
+"""
+import math
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+import torch
+
+from pq3d_b200 import ops
+
+DEV = "cuda"
+TOL_F32 = 1e-3
+TOL_BF16 = 2.0 ** -8
+
+
+def rel(a, b):
+    return ((a.float() - b.float()).abs().max() / b.float().abs().max().clamp_min(1e-12)).item()
+
+
+def gen(seed):
+    return torch.Generator(device="cpu").manual_seed(seed)
+
+
+def rnd(shape, g, scale=1.0):
+    return (torch.randn(shape, generator=g) * scale).to(DEV)
+
+
+# ------------------------------------------------------------------------------------------- GEMM
+def _gemm_case(M, N, K, block_n, out_dtype=torch.bfloat16, bias=True, bias_along_m=False, relu=False, alpha=1.0,
+               alpha_ncols=0, groups=1, row_zero=False, ldc_pad=0, seed=0):
+    g = gen(seed)
+    A = rnd((groups * M, K), g).bfloat16()
+    W = rnd((groups * N, K), g, 0.05).bfloat16()
+    bvec = rnd((groups, M if bias_along_m else N), g) if bias else None
+    rz = (torch.rand(groups, M, generator=g) < 0.3).to(DEV) if row_zero else None
+    ldc = N + ldc_pad
+    out = torch.full((groups, M, ldc), float("nan"), dtype=out_dtype, device=DEV)
+    ops.linear(A, W, out, M=M, N=N, K=K, bias=bvec, bias_along_m=bias_along_m,
+               bias_group_stride=(bvec.shape[1] if bias and groups > 1 else 0), groups=groups,
+               a_group_rows=M if groups > 1 else 0, w_group_rows=N if groups > 1 else 0, ldc=ldc,
+               c_group_stride=M * ldc, row_zero=rz, row_zero_group_stride=M if groups > 1 else 0,
+               alpha=alpha, alpha_ncols=alpha_ncols, relu=relu, block_n=block_n)
+    torch.cuda.synchronize()
+    ref = torch.einsum("gmk,gnk->gmn", A.float().view(groups, M, K).double(), W.float().view(groups, N, K).double())
+    if bias:
+        ref = ref + (bvec.double()[:, :, None] if bias_along_m else bvec.double()[:, None, :])
+    if alpha_ncols:
+        ref[:, :, :alpha_ncols] *= alpha
+    if relu:
+        ref = ref.clamp_min(0)
+    if row_zero:
+        ref = ref.masked_fill(rz[:, :, None], 0.0)
+    got = out[:, :, :N]
+    assert not torch.isnan(got.float()).any(), "unwritten / NaN outputs"
+    if ldc_pad:
+        assert torch.isnan(out[:, :, N:].float()).all(), "wrote outside the N columns"
+    e = rel(got, ref)
+    tol = TOL_F32 if out_dtype == torch.float32 else TOL_BF16
+    print(f"gemm M={M} N={N} K={K} bn={block_n} {out_dtype} groups={groups}: rel {e:.2e} (tol {tol:.1e})")
+    assert e <= tol
+
+
+def check_gemm_min():
+    _gemm_case(128, 64, 64, 64, torch.float32, bias=False)
+    _gemm_case(128, 128, 128, 128, torch.float32)
+    _gemm_case(128, 256, 192, 256, torch.float32)
+
+
+def check_gemm_shapes():
+    _gemm_case(400, 768, 768, 64, torch.float32, seed=1)
+    _gemm_case(400, 2304, 768, 64, torch.bfloat16, alpha=0.125, alpha_ncols=2304, seed=2)
+    _gemm_case(1000, 1536, 768, 128, torch.bfloat16, seed=3)
+    _gemm_case(2048, 3072, 768, 256, torch.bfloat16, seed=4)
+    _gemm_case(400, 768, 2048, 64, torch.float32, seed=5)          # FFN2: long K, ring wraps
+    _gemm_case(400, 2048, 768, 0, torch.bfloat16, relu=True, seed=6)  # auto tile
+    _gemm_case(333, 1536, 768, 128, torch.bfloat16, alpha=0.125, alpha_ncols=768, seed=7)
+
+
+def check_gemm_epilogues():
+    _gemm_case(3072, 520, 768, 128, torch.bfloat16, bias_along_m=True, seed=8)     # V^T form
+    _gemm_case(400, 201, 768, 64, torch.float32, seed=9)                           # cls head: unaligned N
+    _gemm_case(300, 100, 2304, 128, torch.float32, groups=4, bias=False, seed=10)  # mask logits per scene
+    _gemm_case(400, 768, 768, 64, torch.float32, groups=3, seed=11)                # per-memory out-proj
+    _gemm_case(500, 768, 768, 128, torch.bfloat16, bias=False, row_zero=True, seed=12)
+    _gemm_case(130, 72, 128, 64, torch.bfloat16, ldc_pad=8, seed=13)
+
+
+# -------------------------------------------------------------------------------------- attention
+def _attn_ref(Q, K, V, mask, zero_attn, bias=None):
+    """Q (B,H,N,64) pre-scaled, K/V (B,H,S,64), mask (B,H,N,S) bool, fp64 math."""
+    s = torch.einsum("bhnd,bhsd->bhns", Q.double(), K.double())
+    if bias is not None:
+        s = s + bias.double()
+    s = s.masked_fill(mask, float("-inf"))
+    if zero_attn:
+        s = torch.cat([s, torch.zeros_like(s[..., :1])], -1)
+    p = torch.softmax(s, -1)
+    if zero_attn:
+        p = p[..., :-1]
+    return torch.einsum("bhns,bhsd->bhnd", p, V.double())
+
+
+def _attn_case(B, H, Nq, S_list, mask_kind, zero_attn=True, spatial=False, seed=0, scale=1.0):
+    g = gen(seed)
+    n_mem = len(S_list)
+    D = H * 64
+    Q = rnd((B * Nq, n_mem * D), g, scale).bfloat16()
+    O = torch.full((n_mem, B * Nq, D), float("nan"), dtype=torch.bfloat16, device=DEV)
+    mems, refs = [], []
+    pw = lw = lb = None
+    if spatial:
+        pw = torch.rand(B, Nq, Nq, 5, generator=g).to(DEV)
+        lw = rnd((H, 5), g, 0.7)
+        lb = rnd((H,), g, 0.3)
+    for i, S in enumerate(S_list):
+        Sp = ops.pad8(S)
+        L = 2                                    # pretend two layers are stacked; use layer 1
+        Kb = rnd((B * Sp, L * D), g, scale).bfloat16()
+        Vt = rnd((L * D, B * Sp), g).bfloat16()
+        if mask_kind == "kpm":
+            m = (torch.rand(B, S, generator=g) < 0.3).to(DEV)
+            bits = ops.pack_mask(m)
+            strides = (bits.stride(0), 0, 0)
+            full = m[:, None, None, :].expand(B, H, Nq, S)
+        elif mask_kind == "attn":
+            m = (torch.rand(B, Nq, S, generator=g) < 0.5).to(DEV)
+            m[:, 3] = True                      # a fully masked row
+            bits = ops.pack_mask(m)
+            strides = (bits.stride(0), 0, bits.stride(1))
+            full = m[:, None].expand(B, H, Nq, S)
+        elif mask_kind == "attn_heads":
+            m = (torch.rand(B * H, Nq, S, generator=g) < 0.5).to(DEV)
+            bits = ops.pack_mask(m)
+            strides = (H * bits.stride(0), bits.stride(0), bits.stride(1))
+            full = m.view(B, H, Nq, S)
+        else:
+            bits, strides = None, (0, 0, 0)
+            full = torch.zeros(B, H, Nq, S, dtype=torch.bool, device=DEV)
+        mems.append(ops.AttnMemory(Kb, D, Vt, D, S, Sp, bits, *strides))
+        Qh = Q.view(B, Nq, n_mem, H, 64)[:, :, i].permute(0, 2, 1, 3).float()
+        Kh = Kb.view(B, Sp, L, H, 64)[:, :S, 1].permute(0, 2, 1, 3).float()
+        Vh = Vt.view(L, H, 64, B, Sp)[1, :, :, :, :S].permute(2, 0, 3, 1).float()
+        bias = None
+        if spatial:
+            loc = torch.relu(torch.einsum("bnmd,hd->bhnm", pw, lw) + lb[None, :, None, None])
+            bias = torch.log(loc.clamp_min(1e-6))
+        refs.append(_attn_ref(Qh, Kh, Vh, full, zero_attn, bias))
+    ops.attention(Q, D, mems, O, O.stride(0), B, H, Nq, zero_attn, pw, lw, lb)
+    torch.cuda.synchronize()
+    for i in range(n_mem):
+        got = O[i].view(B, Nq, H, 64).permute(0, 2, 1, 3).float()
+        ref = refs[i]
+        ok_rows = ~torch.isnan(ref).any(-1)          # (no zero-attn and all masked -> NaN in both)
+        assert not torch.isnan(got[ok_rows]).any(), "NaN in attention output"
+        # P is rounded to bf16 before the PV product and O is stored as bf16: two bf16 roundings
+        e = ((got[ok_rows] - ref[ok_rows]).abs().max() / ref[ok_rows].abs().max()).item()
+        print(f"attn B={B} H={H} Nq={Nq} S={S_list[i]} mask={mask_kind} zero={zero_attn} spatial={spatial}: rel {e:.2e}")
+        assert e <= 2 * TOL_BF16
+
+
+def check_attn_basic():
+    _attn_case(1, 1, 100, [128], "none", seed=1)
+    _attn_case(2, 2, 100, [300], "kpm", seed=2)
+    _attn_case(2, 12, 100, [1000], "kpm", seed=3, scale=1.5)
+
+
+def check_attn_masks():
+    _attn_case(2, 3, 100, [260], "attn", seed=4)
+    _attn_case(2, 3, 64, [150], "attn_heads", seed=5)
+    _attn_case(1, 2, 200, [333], "attn", seed=6)          # two query tiles
+    _attn_case(2, 2, 100, [32], "kpm", seed=7)            # prompt-sized memory
+    _attn_case(2, 4, 100, [520, 520, 520], "kpm", seed=8)  # three memories in one launch
+
+
+def check_attn_spatial():
+    _attn_case(2, 12, 100, [100], "kpm", zero_attn=False, spatial=True, seed=9)
+    _attn_case(1, 2, 37, [37], "none", zero_attn=False, spatial=True, seed=10)
+
+
+def check_attn_long():
+    _attn_case(1, 2, 100, [4096], "kpm", seed=11, scale=2.0)
+
+
+# ------------------------------------------------------------------------------------ elementwise
+def check_ingest():
+    g = gen(20)
+    for (B, S, D, with_pos) in [(2, 100, 768, True), (3, 37, 768, False), (1, 2048, 768, True)]:
+        Sp = ops.pad8(S)
+        feat, pos = rnd((B, S, D), g), (rnd((B, S, D), g) if with_pos else None)
+        xk = torch.full((B, Sp, D), float("nan"), dtype=torch.bfloat16, device=DEV)
+        xv = torch.full_like(xk, float("nan"))
+        ops.ingest_memory(feat, pos, xk, xv, Sp)
+        torch.cuda.synchronize()
+        assert torch.equal(xv[:, :S], feat.bfloat16())
+        assert torch.equal(xk[:, :S], (feat + pos).bfloat16() if with_pos else feat.bfloat16())
+        assert (xv[:, S:] == 0).all() and (xk[:, S:] == 0).all()
+    print("ingest: exact")
+
+
+def check_add_layernorm():
+    g = gen(21)
+    for (G, R, D, eps) in [(1, 400, 768, 1e-5), (3, 400, 768, 1e-5), (1, 77, 768, 1e-12), (1, 50, 384, 1e-12)]:
+        y, res, pos = rnd((G, R, D), g), rnd((R, D), g), rnd((R, D), g)
+        gamma, beta = 1 + 0.1 * rnd((G, D), g), 0.1 * rnd((G, D), g)
+        o32 = torch.empty(R, D, device=DEV)
+        ob = torch.empty(R, D, dtype=torch.bfloat16, device=DEV)
+        op = torch.empty_like(ob)
+        ops.add_layernorm(y, res, gamma, beta, eps, R, D, G=G, y_group_stride=R * D, pos=pos, out_f32=o32,
+                          out_bf16=ob, out_pos_bf16=op)
+        torch.cuda.synchronize()
+        ref = sum(torch.nn.functional.layer_norm((res + y[i]).double(), (D,), gamma[i].double(), beta[i].double(), eps)
+                  for i in range(G)) / G
+        e = rel(o32, ref)
+        print(f"add_layernorm G={G} R={R} D={D}: rel {e:.2e}")
+        assert e <= 1e-5
+        assert torch.equal(ob, o32.bfloat16()) and torch.equal(op, (o32 + pos).bfloat16())
+    # plain LayerNorm of one tensor (no residual): the cls-head LN
+    y = rnd((1, 10, 768), g)
+    o32 = torch.empty(10, 768, device=DEV)
+    ones, zeros = torch.ones(1, 768, device=DEV), torch.zeros(1, 768, device=DEV)
+    ops.add_layernorm(y, None, ones, zeros, 1e-12, 10, 768, out_f32=o32)
+    torch.cuda.synchronize()
+    assert rel(o32, torch.nn.functional.layer_norm(y[0].double(), (768,), eps=1e-12)) <= 1e-5
+
+
+def check_pack_mask():
+    g = gen(22)
+    for (rows, S) in [((4,), 100), ((2, 50), 333), ((3, 7), 128), ((2, 5), 4096)]:
+        m = (torch.rand(*rows, S, generator=g) < 0.5)
+        m[..., 0, :] = True                       # fully masked rows
+        md = m.to(DEV)
+        bits = ops.pack_mask(md)
+        fixed = torch.empty_like(md)
+        bits_fix = ops.pack_mask(md, unmask_full_rows=True, mask_fixed=fixed.view(torch.uint8))
+        torch.cuda.synchronize()
+        W = ops.mask_words(S)
+
+        def expect(mm):
+            pad = torch.ones(*mm.shape[:-1], W * 32, dtype=torch.bool)
+            pad[..., :S] = mm
+            w = pad.view(*mm.shape[:-1], W, 32).long()
+            return (w << torch.arange(32)).sum(-1)
+        got = bits.cpu().long() & 0xFFFFFFFF
+        assert torch.equal(got, expect(m)), "pack mismatch"
+        m2 = m.clone()
+        m2[m2.all(-1)] = False
+        assert torch.equal(bits_fix.cpu().long() & 0xFFFFFFFF, expect(m2)), "pack+fixup mismatch"
+        assert torch.equal(fixed.cpu(), m2)
+    print("pack_mask: exact")
+
+
+def check_mask_head_finalize():
+    g = gen(23)
+    B, S, N, n_mem = 2, 150, 40, 3
+    raw = rnd((B, S, N), g, 3.0)
+    raw[0, 0, :5] = torch.tensor([0.0, -0.0, 1e-9, -1e-9, -1e-6])
+    mem_masks = [(torch.rand(B, S, generator=g) < 0.3).to(DEV) for _ in range(n_mem)]
+    mem_masks[0][0, 5] = mem_masks[1][0, 5] = mem_masks[2][0, 5] = True          # no memory valid
+    seg = (torch.rand(B, S, generator=g) < 0.1).to(DEV)
+    ptrs = torch.tensor([m.data_ptr() for m in mem_masks], dtype=torch.int64, device=DEV)
+    logits = torch.empty(B, S, N, device=DEV)
+    am = torch.empty(B, N, S, dtype=torch.bool, device=DEV)
+    ops.mask_head_finalize(raw, ptrs, n_mem, seg, logits, am, B, S, N)
+    torch.cuda.synchronize()
+    valid = sum(m[..., None].logical_not() for m in mem_masks)
+    ref = raw / (valid + 1e-8)                    # modules/heads/mask_head.py:36
+    ref[seg] = -1e6
+    ref_am = ref.sigmoid().permute(0, 2, 1) < 0.5
+    assert torch.equal(logits, ref), f"mask logits differ: {(logits - ref).abs().max()}"
+    assert torch.equal(am, ref_am), f"attn mask differs in {(am != ref_am).sum()} places"
+    print("mask_head_finalize: bit-exact vs torch")
+
+
+CHECKS = {k[6:]: v for k, v in list(globals().items()) if k.startswith("check_")}
+
+if __name__ == "__main__":
+    if len(sys.argv) < 2 or sys.argv[1] == "list":
+        print("\n".join(CHECKS))
+        sys.exit(0)
+    torch.manual_seed(0)
+    CHECKS[sys.argv[1]]()
+    print("PASS", sys.argv[1])

@@ -1,0 +1,45 @@
+"""CPU: the C-ABI shared library loads and exports every symbol include/pq3d_b200.h declares
+(no compute calls without a GPU), and bad arguments come back as error codes, not crashes."""
+import ctypes
+
+import pytest
+
+from pq3d_b200 import _lib, build
+
+
+@pytest.fixture(scope="module")
+def lib():
+    build.build()
+    return _lib.lib()
+
+
+def test_exports_match_header(lib):
+    declared = _lib.declared_symbols()
+    assert len(declared) >= 9
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/pq3d_b200.h but not exported"
+    for name in _lib.SIGNATURES:
+        assert name in declared, f"{name} bound in _lib.py but missing from the header"
+
+
+def test_abi_version(lib):
+    assert lib.pq3d_abi_version() == 1
+
+
+def test_bad_arguments_return_error_codes(lib):
+    rc = lib.pq3d_linear_bf16(None, 0, 0, 0, None, 0, 0, 0, None, 0, 0, 0, None, 0, 0, None, 0, 1, 1, 1, 1, 1.0, 0, 0,
+                              0, None)
+    assert rc == -1 and b"null operand" in lib.pq3d_last_error()
+    buf = ctypes.create_string_buffer(64)
+    p = ctypes.addressof(buf)
+    rc = lib.pq3d_linear_bf16(p, 8, 1, 0, p, 8, 1, 0, p, 8, 0, 0, None, 0, 0, None, 0, 1, 1, 7, 1, 1.0, 0, 0, 0, None)
+    assert rc == -1 and b"multiple of 64" in lib.pq3d_last_error()
+    rc = lib.pq3d_pack_mask(None, None, 0, 0, 0, None, None)
+    assert rc == -1
+
+
+def test_missing_library_fails_loudly(monkeypatch):
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/libpq3d_b200.so")
+    with pytest.raises(RuntimeError, match="no CPU or PyTorch fallback"):
+        _lib.lib()
