@@ -1,0 +1,510 @@
+"""Host-side mirror of the reference decoder modules (modules/grounding/query_encoder.py,
+modules/layers/transformers.py:158-240) running on the sm_100a kernels behind the C ABI.
+
+Same class names, constructor kwargs, parameter names/shapes (state_dict keys of SURVEY.md §8b) and
+forward signatures as the reference, so a reference checkpoint loads with strict=True and
+`cfg.model.unified_encoder.name: QueryMaskEncoder` resolves to this class when registered
+(pq3d_b200/registry.py).  nn.Linear / nn.LayerNorm are used purely as parameter containers; all
+arithmetic goes through `pq3d_b200.ops` (there is no PyTorch or CPU fallback).
+
+Scope of this round: the inference path (eval mode, no autograd).  Training-mode forward (dropout,
+memory dropout) and backward kernels are not built yet and raise instead of silently falling back.
+"""
+from __future__ import annotations
+
+import math
+from typing import Callable, Dict, List, Optional, Sequence, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import ops
+
+bf16 = torch.bfloat16
+
+
+# --------------------------------------------------------------------------------------------
+# parameter containers (identical names / shapes to the reference)
+# --------------------------------------------------------------------------------------------
+class _MHAParams(nn.Module):
+    """Parameters of nn.MultiheadAttention(d_model, nhead): packed in-projection + out_proj."""
+
+    def __init__(self, d_model: int, nhead: int):
+        super().__init__()
+        self.embed_dim, self.num_heads = d_model, nhead
+        self.in_proj_weight = nn.Parameter(torch.empty(3 * d_model, d_model))
+        self.in_proj_bias = nn.Parameter(torch.zeros(3 * d_model))
+        self.out_proj = nn.Linear(d_model, d_model)
+
+
+class CrossAttentionLayer(nn.Module):
+    """modules/grounding/query_encoder.py:257-351 (post-norm; MHA with add_zero_attn=True)."""
+
+    def __init__(self, d_model, nhead, dropout=0.0, activation="relu", normalize_before=False, batch_first=False):
+        super().__init__()
+        if normalize_before:
+            raise NotImplementedError("pre-norm is never enabled on the reference path (query_encoder.py:97,103)")
+        self.multihead_attn = _MHAParams(d_model, nhead)
+        self.norm = nn.LayerNorm(d_model)
+        self.dropout_p = dropout
+
+
+class SelfAttentionLayer(nn.Module):
+    """modules/grounding/query_encoder.py:184-254 (stock MHA self-attention, no zero-attn)."""
+
+    def __init__(self, d_model, nhead, dropout=0.0, activation="relu", normalize_before=False, batch_first=False):
+        super().__init__()
+        if normalize_before:
+            raise NotImplementedError("pre-norm is never enabled on the reference path")
+        self.self_attn = _MHAParams(d_model, nhead)
+        self.norm = nn.LayerNorm(d_model)
+        self.dropout_p = dropout
+
+
+class MultiHeadAttentionSpatial(nn.Module):
+    """modules/layers/transformers.py:158-187, spatial_attn_fusion='mul', spatial_multihead=True,
+    spatial_dim=5 — the only values reachable from SpatialSelfAttentionLayer's defaults."""
+
+    def __init__(self, d_model, n_head, dropout=0.1, spatial_multihead=True, spatial_dim=5, spatial_attn_fusion="mul"):
+        super().__init__()
+        if spatial_attn_fusion != "mul" or not spatial_multihead or spatial_dim != 5:
+            raise NotImplementedError("only fusion='mul', spatial_multihead=True, spatial_dim=5 are on the PQ3D path")
+        self.n_head, self.d_model = n_head, d_model
+        self.w_qs = nn.Linear(d_model, d_model)
+        self.w_ks = nn.Linear(d_model, d_model)
+        self.w_vs = nn.Linear(d_model, d_model)
+        self.fc = nn.Linear(d_model, d_model)
+        self.pairwise_loc_fc = nn.Linear(spatial_dim, n_head)
+
+
+class SpatialSelfAttentionLayer(nn.Module):
+    """modules/grounding/query_encoder.py:402-483."""
+
+    def __init__(self, d_model, nhead, dropout=0.0, activation="relu", normalize_before=False, batch_first=False,
+                 spatial_multihead=True, spatial_dim=5, spatial_attn_fusion="mul"):
+        super().__init__()
+        if normalize_before:
+            raise NotImplementedError("pre-norm is never enabled on the reference path")
+        self.self_attn = MultiHeadAttentionSpatial(d_model, nhead, dropout, spatial_multihead, spatial_dim,
+                                                   spatial_attn_fusion)
+        self.norm = nn.LayerNorm(d_model)
+        self.dropout_p = dropout
+
+
+class FFNLayer(nn.Module):
+    """modules/grounding/query_encoder.py:354-399 (relu, post-norm)."""
+
+    def __init__(self, d_model, dim_feedforward=2048, dropout=0.0, activation="relu", normalize_before=False):
+        super().__init__()
+        if activation != "relu" or normalize_before:
+            raise NotImplementedError("the reference path uses relu / post-norm (query_encoder.py:97)")
+        self.linear1 = nn.Linear(d_model, dim_feedforward)
+        self.linear2 = nn.Linear(dim_feedforward, d_model)
+        self.norm = nn.LayerNorm(d_model)
+        self.dropout_p = dropout
+
+
+class QueryEncoderLayer(nn.Module):
+    """modules/grounding/query_encoder.py:96-112."""
+
+    def __init__(self, d_model, nhead, memories, dim_feedforward=2048, dropout=0.1, activation="relu", prenorm=False,
+                 spatial_selfattn=False, structure="mixed", memory_dropout=0, drop_memories_test=[]):
+        super().__init__()
+        sa = SpatialSelfAttentionLayer if spatial_selfattn else SelfAttentionLayer
+        self.self_attn = sa(d_model, nhead, dropout=dropout, activation=activation, normalize_before=prenorm,
+                            batch_first=True)
+        self.cross_attn_list = nn.ModuleList(
+            [CrossAttentionLayer(d_model, nhead, dropout=dropout, activation=activation, normalize_before=prenorm,
+                                 batch_first=True) for _ in memories])
+        self.ffn = FFNLayer(d_model, dim_feedforward, dropout=dropout, activation=activation, normalize_before=prenorm)
+        self.structure = structure
+        self.memories = list(memories)
+        self.memory_dropout = memory_dropout
+        self.drop_memories_test = list(drop_memories_test)
+        if structure == "gate":
+            self.gate_proj = nn.Linear(d_model, d_model)
+        if structure not in ("sequential", "parallel", "mixed", "gate"):
+            raise NotImplementedError(f"Unknow structure type: {structure}")
+
+
+def _reference_init(encoder: "QueryMaskEncoder"):
+    """Init parity: per-sublayer xavier on dim>1 params, deep-copied across
+    memories and layers (modules/utils.py:28-32), then _init_weights_bert over every nn.Linear /
+    nn.LayerNorm (modules/weights.py:3-19) — which leaves only the bare MHA in_proj_weight xavier."""
+    template: Dict[Tuple[str, tuple], torch.Tensor] = {}
+    with torch.no_grad():
+        for name, p in encoder.named_parameters():
+            if name.endswith("in_proj_weight"):
+                kind = "self" if ".self_attn." in name else "cross"
+                key = (kind, tuple(p.shape))
+                if key not in template:
+                    t = torch.empty_like(p)
+                    nn.init.xavier_uniform_(t)
+                    template[key] = t
+                p.copy_(template[key])
+            elif name.endswith("in_proj_bias"):
+                p.zero_()
+        for m in encoder.modules():
+            if isinstance(m, nn.Linear):
+                m.weight.normal_(mean=0.0, std=0.02)
+                if m.bias is not None:
+                    m.bias.zero_()
+            elif isinstance(m, nn.LayerNorm):
+                m.bias.zero_()
+                m.weight.fill_(1.0)
+
+
+# --------------------------------------------------------------------------------------------
+# packed weights
+# --------------------------------------------------------------------------------------------
+class _Packed:
+    """bf16 operand copies of the fp32 parameters, laid out for the kernels:
+       per memory  : Wk / Wv stacked over layers   [L*D, D]  (K/V projections hoisted out of the layer loop)
+       per layer   : per CA group Wq stacked over the group's memories [g*D, D], out_proj [g*D, D],
+                     LN gamma/beta [g, D]; self-attention [Wq;Wk] [2D, D], Wv, fc; FFN W1, W2."""
+
+    def __init__(self, enc: "QueryMaskEncoder", device):
+        D, L = enc.hidden_size, enc.num_layers
+        layers = enc.unified_encoder
+        mems = enc.memories
+        f32 = dict(device=device, dtype=torch.float32)
+
+        def w16(t):
+            return t.detach().to(device=device, dtype=bf16).contiguous()
+
+        def f(t):
+            return t.detach().to(**f32).contiguous()
+
+        self.wk, self.bk, self.wv, self.bv = {}, {}, {}, {}
+        for j, m in enumerate(mems):
+            ipw = [layers[i].cross_attn_list[j].multihead_attn.in_proj_weight for i in range(L)]
+            ipb = [layers[i].cross_attn_list[j].multihead_attn.in_proj_bias for i in range(L)]
+            self.wk[m] = w16(torch.cat([w[D:2 * D] for w in ipw], 0))
+            self.bk[m] = f(torch.cat([b[D:2 * D] for b in ipb], 0))
+            self.wv[m] = w16(torch.cat([w[2 * D:] for w in ipw], 0))
+            self.bv[m] = f(torch.cat([b[2 * D:] for b in ipb], 0))
+        self.layers = []
+        for i in range(L):
+            lay = layers[i]
+            d = {"groups": {}}
+            for grp in enc._all_groups():
+                idx = [mems.index(m) for m in grp]
+                cas = [lay.cross_attn_list[j] for j in idx]
+                d["groups"][grp] = dict(
+                    wq=w16(torch.cat([c.multihead_attn.in_proj_weight[:D] for c in cas], 0)),
+                    bq=f(torch.cat([c.multihead_attn.in_proj_bias[:D] for c in cas], 0)),
+                    wo=w16(torch.cat([c.multihead_attn.out_proj.weight for c in cas], 0)),
+                    bo=f(torch.stack([c.multihead_attn.out_proj.bias for c in cas], 0)),
+                    gamma=f(torch.stack([c.norm.weight for c in cas], 0)),
+                    beta=f(torch.stack([c.norm.bias for c in cas], 0)),
+                    eps=cas[0].norm.eps)
+            sa = lay.self_attn
+            if isinstance(sa, SpatialSelfAttentionLayer):
+                a = sa.self_attn
+                d["sa"] = dict(wqk=w16(torch.cat([a.w_qs.weight, a.w_ks.weight], 0)),
+                               bqk=f(torch.cat([a.w_qs.bias, a.w_ks.bias], 0)),
+                               wv=w16(a.w_vs.weight), bv=f(a.w_vs.bias), wo=w16(a.fc.weight), bo=f(a.fc.bias),
+                               loc_w=f(a.pairwise_loc_fc.weight), loc_b=f(a.pairwise_loc_fc.bias))
+            else:
+                a = sa.self_attn
+                d["sa"] = dict(wqk=w16(a.in_proj_weight[:2 * D]), bqk=f(a.in_proj_bias[:2 * D]),
+                               wv=w16(a.in_proj_weight[2 * D:]), bv=f(a.in_proj_bias[2 * D:]),
+                               wo=w16(a.out_proj.weight), bo=f(a.out_proj.bias), loc_w=None, loc_b=None)
+            d["sa"].update(gamma=f(sa.norm.weight)[None], beta=f(sa.norm.bias)[None], eps=sa.norm.eps)
+            ffn = lay.ffn
+            d["ffn"] = dict(w1=w16(ffn.linear1.weight), b1=f(ffn.linear1.bias), w2=w16(ffn.linear2.weight),
+                            b2=f(ffn.linear2.bias), gamma=f(ffn.norm.weight)[None], beta=f(ffn.norm.bias)[None],
+                            eps=ffn.norm.eps, F=ffn.linear1.out_features)
+            if lay.structure == "gate":
+                d["gate"] = dict(w=w16(lay.gate_proj.weight), b=f(lay.gate_proj.bias))
+            self.layers.append(d)
+
+
+class _MemState:
+    """Per-forward projected state of one memory."""
+    __slots__ = ("name", "S", "S_pitch", "K", "Vt", "bits", "strides", "per_layer_mask")
+
+
+# --------------------------------------------------------------------------------------------
+# the decoder
+# --------------------------------------------------------------------------------------------
+class QueryMaskEncoder(nn.Module):
+    """Drop-in for modules/grounding/query_encoder.py:51-94: same kwargs, same
+    `.forward(input_dict, pairwise_locs, mask_head=None) -> (query, predictions_class, predictions_mask)`,
+    `.spatial_selfattn` attribute read by the model (model/query3d_unified.py:182)."""
+
+    def __init__(self, cfg=None, memories=[], memory_dropout=0.0, hidden_size=768, num_attention_heads=12,
+                 num_layers=4, share_layer=False, spatial_selfattn=False, structure="sequential",
+                 drop_memories_test=[], use_self_mask=False, num_blocks=1):
+        super().__init__()
+        if hidden_size % num_attention_heads != 0 or hidden_size // num_attention_heads != 64:
+            raise NotImplementedError("the sm_100a attention kernel is specialised for head_dim = 64")
+        if hidden_size % 128 != 0:
+            raise NotImplementedError("hidden_size must be a multiple of 128")
+        self.spatial_selfattn = spatial_selfattn
+        memories = list(memories)
+        if share_layer:
+            layer = QueryEncoderLayer(hidden_size, num_attention_heads, memories, spatial_selfattn=spatial_selfattn,
+                                      structure=structure, memory_dropout=memory_dropout,
+                                      drop_memories_test=drop_memories_test)
+            self.unified_encoder = nn.ModuleList([layer] * num_layers)
+        else:
+            self.unified_encoder = nn.ModuleList(
+                [QueryEncoderLayer(hidden_size, num_attention_heads, memories, spatial_selfattn=spatial_selfattn,
+                                   structure=structure, memory_dropout=memory_dropout,
+                                   drop_memories_test=drop_memories_test) for _ in range(num_layers)])
+        self.memories = memories
+        self.structure = structure
+        self.hidden_size = hidden_size
+        self.num_layers = num_layers
+        self.memory_dropout = memory_dropout
+        self.scene_meomories = [x for x in memories if x != "prompt"]     # (sic) reference attribute name
+        self.drop_memories_test = list(drop_memories_test)
+        self.use_self_mask = use_self_mask
+        self.num_heads = num_attention_heads
+        self.num_blocks = num_blocks
+        _reference_init(self)
+        self._packed: Optional[_Packed] = None
+        self._packed_key = None
+        self._ws: Dict[tuple, dict] = {}
+
+    # ---- structure -> cross-attention program ------------------------------------------------
+    def _active(self) -> List[str]:
+        return [m for m in self.memories if m not in self.drop_memories_test]      # eval, :156
+
+    def _program(self) -> List[Tuple[str, ...]]:
+        act = self._active()
+        if self.structure == "sequential":
+            return [(m,) for m in act]
+        if self.structure == "parallel":
+            assert "prompt" not in act
+            return [tuple(act)]
+        if self.structure == "mixed":
+            return [tuple(m for m in act if m != "prompt"), ("prompt",)]
+        if self.structure == "gate":
+            return [("prompt",), tuple(m for m in self.memories if m != "prompt")]
+        raise NotImplementedError(self.structure)
+
+    def _all_groups(self):
+        return list(dict.fromkeys(g for g in self._program() if len(g) > 0))
+
+    # ---- packed weights ------------------------------------------------------------------------
+    def packed(self, device) -> _Packed:
+        key = (str(device), tuple(self.drop_memories_test), tuple(p._version for p in self.parameters()),
+               tuple(p.data_ptr() for p in self.parameters()))
+        if self._packed is None or self._packed_key != key:
+            self._packed = _Packed(self, device)
+            self._packed_key = key
+            self._ws.clear()
+        return self._packed
+
+    def _buf(self, ws: dict, name: str, shape, dtype, device):
+        t = ws.get(name)
+        if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype:
+            t = torch.empty(shape, dtype=dtype, device=device)
+            ws[name] = t
+        return t
+
+    # ---- forward -------------------------------------------------------------------------------
+    def forward(self, input_dict: dict, pairwise_locs: Optional[torch.Tensor], mask_head: Optional[Callable] = None):
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            raise NotImplementedError(
+                "pq3d_b200.QueryMaskEncoder: backward kernels are not built yet — call under torch.no_grad() "
+                "(inference path); there is deliberately no PyTorch autograd fallback")
+        if self.training:
+            raise NotImplementedError("pq3d_b200.QueryMaskEncoder: training-mode forward (dropout / memory dropout) "
+                                      "is not built yet — call .eval()")
+        query, query_masks, query_pos = input_dict["query"]
+        dev = query.device
+        B, N, D = query.shape
+        H, L = self.num_heads, self.num_layers
+        R = B * N
+        pk = self.packed(dev)
+        program = self._program()
+        active = [m for g in program for m in g]
+        key = (B, N, tuple((m, tuple(input_dict[m][0][0].shape if isinstance(input_dict[m][0], list)
+                                     else input_dict[m][0].shape)) for m in active))
+        ws = self._ws.setdefault(key, {})
+        buf = lambda name, shape, dtype: self._buf(ws, name, shape, dtype, dev)  # noqa: E731
+
+        # ---------------- memory side: ingest + hoisted K / V^T projections for all layers
+        voxel_feat = input_dict["voxel"][0] if "voxel" in input_dict else None
+        states: Dict[str, _MemState] = {}
+        for m in active:
+            feat, mask, pos = input_dict[m]
+            multi = isinstance(feat, list)
+            f0 = feat[0] if multi else feat
+            S = f0.shape[1]
+            Sp = ops.pad8(S)
+            st = _MemState()
+            st.name, st.S, st.S_pitch = m, S, Sp
+            nsrc = L if multi else 1
+            xv = buf(f"xv_{m}", (nsrc * B * Sp, D), bf16)
+            xk = buf(f"xk_{m}", (nsrc * B * Sp, D), bf16) if pos is not None else xv
+            for i in range(nsrc):
+                fi = (feat[i] if multi else feat).contiguous()
+                sl = slice(i * B * Sp, (i + 1) * B * Sp)
+                ops.ingest_memory(fi.float() if fi.dtype != torch.float32 else fi,
+                                  None if pos is None else pos.contiguous(), xk[sl] if pos is not None else None,
+                                  xv[sl], Sp)
+            st.K = buf(f"K_{m}", (B * Sp, L * D), bf16)
+            st.Vt = buf(f"Vt_{m}", (L * D, B * Sp), bf16)
+            if multi:
+                ops.linear(xk, pk.wk[m], st.K, M=B * Sp, N=D, K=D, bias=pk.bk[m], bias_group_stride=D, groups=L,
+                           a_group_rows=B * Sp, w_group_rows=D, ldc=L * D, c_group_stride=D)
+                ops.linear(pk.wv[m], xv, st.Vt, M=D, N=B * Sp, K=D, bias=pk.bv[m], bias_along_m=True,
+                           bias_group_stride=D, groups=L, a_group_rows=D, w_group_rows=B * Sp, ldc=B * Sp,
+                           c_group_stride=D * B * Sp)
+            else:
+                ops.linear(xk, pk.wk[m], st.K, M=B * Sp, N=L * D, K=D, bias=pk.bk[m])
+                ops.linear(pk.wv[m], xv, st.Vt, M=L * D, N=B * Sp, K=D, bias=pk.bv[m], bias_along_m=True)
+            self._set_mask(st, mask, B, N, H, ws, dev)
+            states[m] = st
+
+        # ---------------- query side state
+        q32 = buf("q32", (R, D), torch.float32)
+        q32.copy_(query.reshape(R, D))
+        qpos = buf("qpos", (R, D), torch.float32)
+        qpos.copy_(query_pos.reshape(R, D))
+        xq = buf("xq", (R, D), bf16)       # bf16(query + query_pos): q/k operand
+        xv_q = buf("xvq", (R, D), bf16)    # bf16(query): v operand
+        ops.cast_bf16(q32, xq, add=qpos)
+        ops.cast_bf16(q32, xv_q)
+        qbits = ops.pack_mask(query_masks.contiguous(), buf("qbits", (B, ops.mask_words(N)), torch.int32))
+        pw = None
+        if self.spatial_selfattn:
+            if pairwise_locs is None:
+                raise ValueError("spatial_selfattn=True needs pairwise_locs (B, N, N, 5)")
+            pw = buf("pw", (B, N, N, 5), torch.float32)
+            pw.copy_(pairwise_locs)
+
+        predictions_class, predictions_mask = [], []
+        attn_mask = None
+        for _block in range(self.num_blocks):
+            for i in range(L):
+                if mask_head is not None:
+                    output_class, outputs_mask, attn_mask = mask_head(q32.view(B, N, D))
+                    predictions_class.append(output_class)
+                    predictions_mask.append(outputs_mask)
+                if self.use_self_mask:
+                    if attn_mask is None:
+                        raise ValueError("use_self_mask=True needs a mask_head that returns an attention mask")
+                    fixed = buf("am_fixed", (B, N, attn_mask.shape[-1]), torch.bool)
+                    bits = ops.pack_mask(attn_mask.contiguous(),
+                                         buf("am_bits", (B, N, ops.mask_words(attn_mask.shape[-1])), torch.int32),
+                                         unmask_full_rows=True, mask_fixed=fixed.view(torch.uint8))
+                    for m in input_dict.keys():
+                        if m in ("query", "prompt"):
+                            continue
+                        # the reference stores attn_mask.repeat_interleave(H, 0) here (query_encoder.py:84-88);
+                        # the kernels read the packed (B, N, S) bits with a zero head stride instead
+                        input_dict[m][1] = fixed
+                        if m in states:
+                            st = states[m]
+                            st.bits, st.strides = bits, (bits.stride(0), 0, bits.stride(1))
+                if isinstance(voxel_feat, list):
+                    input_dict["voxel"][0] = voxel_feat[i]
+                self._layer(i, pk, program, states, ws, dev, B, N, D, H, q32, qpos, xq, xv_q, qbits, pw)
+        return q32.view(B, N, D).clone(), predictions_class, predictions_mask
+
+    def _set_mask(self, st: _MemState, mask: torch.Tensor, B, N, H, ws, dev):
+        if mask.dtype != torch.bool:
+            raise TypeError(f"memory '{st.name}': masks must be torch.bool (True = ignore), got {mask.dtype}")
+        W = ops.mask_words(st.S)
+        if mask.ndim == 2:                                    # key padding (B, S)
+            if tuple(mask.shape) != (B, st.S):
+                raise ValueError(f"memory '{st.name}': key padding mask {tuple(mask.shape)} != {(B, st.S)}")
+            st.bits = ops.pack_mask(mask.contiguous(), self._buf(ws, f"bits2_{st.name}", (B, W), torch.int32, dev))
+            st.strides = (W, 0, 0)
+        elif mask.ndim == 3:                                  # attn mask (B*H, N, S), row b*H + h
+            if tuple(mask.shape) != (B * H, N, st.S):
+                raise RuntimeError(f"The shape of the 3D attn_mask is {tuple(mask.shape)}, but should be {(B * H, N, st.S)}.")
+            st.bits = ops.pack_mask(mask.contiguous(), self._buf(ws, f"bits3_{st.name}", (B * H, N, W), torch.int32, dev))
+            st.strides = (H * N * W, N * W, W)
+        else:
+            raise ValueError(f"memory '{st.name}': mask must be 2-D or 3-D")
+
+    def _cross_group(self, grp, i, pk, states, ws, dev, B, N, D, H, x_in, tag):
+        """Q projection for the group's memories, one attention launch, grouped out-projection.
+        Returns y [g, R, D] fp32 (pre-residual updates)."""
+        R, g = B * N, len(grp)
+        w = pk.layers[i]["groups"][grp]
+        Q = self._buf(ws, f"Q_{tag}", (R, g * D), bf16, dev)
+        ops.linear(x_in, w["wq"], Q, M=R, N=g * D, K=D, bias=w["bq"], alpha=0.125, alpha_ncols=g * D)
+        O = self._buf(ws, f"O_{tag}", (g, R, D), bf16, dev)
+        mems = [ops.AttnMemory(states[m].K, i * D, states[m].Vt, i * D, states[m].S, states[m].S_pitch,
+                               states[m].bits, *states[m].strides) for m in grp]
+        ops.attention(Q, D, mems, O, R * D, B, H, N, True)
+        y = self._buf(ws, f"y_{tag}", (g, R, D), torch.float32, dev)
+        ops.linear(O.view(g * R, D), w["wo"], y, M=R, N=D, K=D, bias=w["bo"], bias_group_stride=D, groups=g,
+                   a_group_rows=R, w_group_rows=D, ldc=D, c_group_stride=R * D)
+        return y, w
+
+    def _layer(self, i, pk, program, states, ws, dev, B, N, D, H, q32, qpos, xq, xv_q, qbits, pw):
+        R = B * N
+        lw = pk.layers[i]
+        if self.structure == "gate":
+            grp_p, grp_s = program
+            y, w = self._cross_group(grp_p, i, pk, states, ws, dev, B, N, D, H, xq, "p")
+            pb = self._buf(ws, "gate_p16", (R, D), bf16, dev)
+            ops.add_layernorm(y, q32, w["gamma"], w["beta"], w["eps"], R, D, G=1, out_bf16=pb)
+            gl = self._buf(ws, "gate_logits", (R, D), torch.float32, dev)
+            ops.linear(pb, lw["gate"]["w"], gl, M=R, N=D, K=D, bias=lw["gate"]["b"])
+            y, w = self._cross_group(grp_s, i, pk, states, ws, dev, B, N, D, H, xq, "s")
+            upd = self._buf(ws, "gate_upd", (R, D), torch.float32, dev)
+            ops.add_layernorm(y, q32, w["gamma"], w["beta"], w["eps"], R, D, G=len(grp_s), y_group_stride=R * D,
+                              out_f32=upd)
+            ops.gate_mix(gl, q32, upd, q32)
+            ops.cast_bf16(q32, xq, add=qpos)
+            ops.cast_bf16(q32, xv_q)
+        else:
+            for gi, grp in enumerate(program):
+                if len(grp) == 0:
+                    continue
+                y, w = self._cross_group(grp, i, pk, states, ws, dev, B, N, D, H, xq, f"g{gi}")
+                ops.add_layernorm(y, q32, w["gamma"], w["beta"], w["eps"], R, D, G=len(grp), y_group_stride=R * D,
+                                  pos=qpos, out_f32=q32, out_bf16=xv_q, out_pos_bf16=xq)
+        # ---- query self-attention (spatially biased when configured)
+        sa = lw["sa"]
+        QK = self._buf(ws, "sa_QK", (R, 2 * D), bf16, dev)
+        ops.linear(xq, sa["wqk"], QK, M=R, N=2 * D, K=D, bias=sa["bqk"], alpha=0.125, alpha_ncols=D)
+        Np = ops.pad8(N)
+        if Np != N:
+            raise NotImplementedError("query count must be a multiple of 8 (TMA stride alignment of V^T)")
+        Vt = self._buf(ws, "sa_Vt", (D, B * Np), bf16, dev)
+        ops.linear(sa["wv"], xv_q, Vt, M=D, N=R, K=D, bias=sa["bv"], bias_along_m=True)
+        Os = self._buf(ws, "sa_O", (1, R, D), bf16, dev)
+        mem = ops.AttnMemory(QK, D, Vt, 0, N, Np, qbits, qbits.stride(0), 0, 0)
+        ops.attention(QK, 0, [mem], Os, R * D, B, H, N, False, pw if sa["loc_w"] is not None else None,
+                      sa["loc_w"], sa["loc_b"])
+        ys = self._buf(ws, "sa_y", (R, D), torch.float32, dev)
+        ops.linear(Os.view(R, D), sa["wo"], ys, M=R, N=D, K=D, bias=sa["bo"])
+        ops.add_layernorm(ys, q32, sa["gamma"], sa["beta"], sa["eps"], R, D, out_f32=q32, out_bf16=xv_q)
+        # ---- FFN
+        ff = lw["ffn"]
+        h = self._buf(ws, "ffn_h", (R, ff["F"]), bf16, dev)
+        ops.linear(xv_q, ff["w1"], h, M=R, N=ff["F"], K=D, bias=ff["b1"], relu=True)
+        yf = self._buf(ws, "ffn_y", (R, D), torch.float32, dev)
+        ops.linear(h, ff["w2"], yf, M=R, N=D, K=ff["F"], bias=ff["b2"])
+        ops.add_layernorm(yf, q32, ff["gamma"], ff["beta"], ff["eps"], R, D, pos=qpos, out_f32=q32, out_bf16=xv_q,
+                          out_pos_bf16=xq)
+
+
+class QueryEncoder(QueryMaskEncoder):
+    """modules/grounding/query_encoder.py:11-49: the mask-less variant (`forward(input_dict,
+    pairwise_locs) -> query`).  Its eval-time `dropout_memory` zeroing of dropped memories is the
+    reference's behaviour for `drop_memories_test` here (feat and pos zeroed, memory still attended)."""
+
+    def __init__(self, cfg=None, memories=[], memory_dropout=0.0, hidden_size=768, num_attention_heads=12,
+                 num_layers=4, share_layer=False, spatial_selfattn=False, structure="sequential",
+                 drop_memories_test=[]):
+        super().__init__(cfg, memories, memory_dropout, hidden_size, num_attention_heads, num_layers, share_layer,
+                         spatial_selfattn, structure, [], False, 1)
+        self._zero_memories = list(drop_memories_test)
+
+    def forward(self, input_dict, pairwise_locs):
+        for m in self._zero_memories:                      # dropout_memory, eval branch (:31-36)
+            if m in input_dict and m != "prompt":
+                input_dict[m][0].zero_()
+                input_dict[m][2].zero_()
+        return super().forward(input_dict, pairwise_locs, None)[0]
