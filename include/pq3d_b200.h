@@ -110,6 +110,18 @@ int pq3d_gate_mix(const float* gate_logits, const float* query, const float* upd
 /* out = bf16(x + add) (add may be NULL); n multiple of 4. */
 int pq3d_cast_bf16(const float* x, const float* add, void* out, int64_t n, void* stream);
 
+/* Fourier positional features as the bf16 operand of CoordinateEncoder.feat_proj:
+ * xyz' = (xyz - min)/(max - min); out[b,l,:] = [sin(2*pi*xyz'·gauss_B), cos(...)], gauss_B fp32 [3, d_pos/2].
+ * xyz: fp32, point (b,l) at xyz + (b*L+l)*xyz_stride.  Replaces model/query3d_unified.py:22-24 ->
+ * modules/third_party/mask3d/position_embedding.py:38-43,127-156. */
+int pq3d_fourier_pos(const float* xyz, int xyz_stride, const float* coord_min, const float* coord_max,
+                     const float* gauss_B, void* out_bf16, int B, int L, int d_pos, void* stream);
+
+/* out[b,i,j,:] = [d/max_b d, dz/d, d2/d, dy/d2, dx/d2] for query centres (fp32, row stride c_stride),
+ * d = sqrt(|ci-cj|^2 + eps), d2 over xy.  Replaces calc_pairwise_locs(..., 'center', spatial_dist_norm=True,
+ * spatial_dim=5), modules/utils.py:38-68. */
+int pq3d_pairwise_locs(const float* centers, int c_stride, float* out, int B, int N, float eps, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -261,8 +261,9 @@ def mask_head_seg_level(query: Tensor, sd: SD, prefix: str, seg_fts_for_match: l
     if skip_prediction:
         return None, None, offline_attn_masks
     cls_logits = mlp_head(query, sd, prefix + "cls_head.")
-    if filter_out_classes is not None:
-        cls_logits[..., filter_out_classes] = float("-inf")
+    # NB the reference indexes unconditionally (mask_head.py:28); with filter_out_classes=None the
+    # index `[..., None]` addresses every class, so all logits become -inf.  Reproduced as is.
+    cls_logits[..., filter_out_classes] = float("-inf")
     logits_sum, valid_sum = 0, 0
     for j, (feat, mask, _pos) in enumerate(seg_fts_for_match):
         qp = F.linear(query, sd[f"{prefix}mask_pred_list.{j}.q_proj.weight"], sd[f"{prefix}mask_pred_list.{j}.q_proj.bias"])

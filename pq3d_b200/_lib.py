@@ -27,6 +27,8 @@ SIGNATURES: Dict[str, list] = {
     "pq3d_mask_head_finalize": [_vp, _vp, _i32, _vp, _vp, _vp, _i32, _i32, _i32, _vp],
     "pq3d_gate_mix": [_vp, _vp, _vp, _vp, _i64, _vp],
     "pq3d_cast_bf16": [_vp, _vp, _vp, _i64, _vp],
+    "pq3d_fourier_pos": [_vp, _i32, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp],
+    "pq3d_pairwise_locs": [_vp, _i32, _vp, _i32, _i32, _f32, _vp],
 }
 
 

@@ -222,6 +222,81 @@ __global__ void cast_bf16_kernel(const float* __restrict__ x, const float* __res
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// fourier_pos: CoordinateEncoder's Fourier features (model/query3d_unified.py:15-27 ->
+// modules/third_party/mask3d/position_embedding.py:38-43,127-156): xyz' = (xyz - min) / (max - min),
+// proj = 2*pi*xyz' . gauss_B[3, D/2], out = [sin(proj), cos(proj)] emitted as the bf16 GEMM operand
+// of feat_proj (the reference computes this part in fp32 with autocast disabled).
+// ------------------------------------------------------------------------------------------------
+__global__ void fourier_pos_kernel(const float* __restrict__ xyz, int xyz_stride, const float* __restrict__ cmin,
+                                   const float* __restrict__ cmax, const float* __restrict__ gauss_B,
+                                   __nv_bfloat16* __restrict__ out, int B, int L, int half) {
+  const int64_t total = static_cast<int64_t>(B) * L * half;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int j = static_cast<int>(i % half);
+    const int64_t pt = i / half;
+    const int b = static_cast<int>(pt / L);
+    const float* p = xyz + pt * xyz_stride;
+    float proj = 0.f;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      const float lo = cmin[b * 3 + d], hi = cmax[b * 3 + d];
+      float x = __fdiv_rn((p[d] - lo) * 1.0f, hi - lo) + 0.0f;   // shift_scale_points with dst range [0,1]
+      x *= 6.283185307179586f;
+      proj = fmaf(x, gauss_B[d * half + j], proj);
+    }
+    float sn, cs;
+    sincosf(proj, &sn, &cs);
+    out[pt * (2 * half) + j] = __float2bfloat16_rn(sn);
+    out[pt * (2 * half) + half + j] = __float2bfloat16_rn(cs);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// pairwise_locs: calc_pairwise_locs(centers, None, 'center', spatial_dist_norm=True, spatial_dim=5)
+// (modules/utils.py:38-68).  One block per scene: pass 1 block-reduces the scene's max distance,
+// pass 2 writes [d/max, dz/d, d2/d, dy/d2, dx/d2].
+// ------------------------------------------------------------------------------------------------
+__global__ void pairwise_locs_kernel(const float* __restrict__ centers, int c_stride, float* __restrict__ out, int N,
+                                     float eps) {
+  __shared__ float red[32];
+  __shared__ float s_max;
+  const int b = blockIdx.x;
+  const float* c = centers + static_cast<int64_t>(b) * N * c_stride;
+  float mx = 0.f;
+  for (int i = threadIdx.x; i < N * N; i += blockDim.x) {
+    const int a = i / N, t = i % N;
+    const float dx = c[a * c_stride] - c[t * c_stride], dy = c[a * c_stride + 1] - c[t * c_stride + 1],
+                dz = c[a * c_stride + 2] - c[t * c_stride + 2];
+    mx = fmaxf(mx, sqrtf(dx * dx + dy * dy + dz * dz + eps));
+  }
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if (threadIdx.x == 0) s_max = v;
+  }
+  __syncthreads();
+  const float maxd = s_max;
+  float* o = out + static_cast<int64_t>(b) * N * N * 5;
+  for (int i = threadIdx.x; i < N * N; i += blockDim.x) {
+    const int a = i / N, t = i % N;
+    const float dx = c[a * c_stride] - c[t * c_stride], dy = c[a * c_stride + 1] - c[t * c_stride + 1],
+                dz = c[a * c_stride + 2] - c[t * c_stride + 2];
+    const float d = sqrtf(dx * dx + dy * dy + dz * dz + eps);
+    const float d2 = sqrtf(dx * dx + dy * dy + eps);
+    o[i * 5 + 0] = __fdiv_rn(d, maxd);
+    o[i * 5 + 1] = __fdiv_rn(dz, d);
+    o[i * 5 + 2] = __fdiv_rn(d2, d);
+    o[i * 5 + 3] = __fdiv_rn(dy, d2);
+    o[i * 5 + 4] = __fdiv_rn(dx, d2);
+  }
+}
+
 }  // namespace pq3d
 
 using namespace pq3d;
@@ -296,6 +371,25 @@ extern "C" int pq3d_cast_bf16(const float* x, const float* add, void* out, int64
   PQ3D_CHECK_ARG(x && out && n > 0 && n % 4 == 0, "pq3d_cast_bf16: n=%lld must be a positive multiple of 4", (long long)n);
   cast_bf16_kernel<<<grid_for(n / 4, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       x, add, reinterpret_cast<__nv_bfloat16*>(out), n / 4);
+  PQ3D_CUDA(cudaGetLastError());
+  return PQ3D_OK;
+}
+
+extern "C" int pq3d_fourier_pos(const float* xyz, int xyz_stride, const float* coord_min, const float* coord_max,
+                                const float* gauss_B, void* out_bf16, int B, int L, int d_pos, void* stream) {
+  PQ3D_CHECK_ARG(xyz && coord_min && coord_max && gauss_B && out_bf16, "pq3d_fourier_pos: null argument");
+  PQ3D_CHECK_ARG(B > 0 && L > 0 && d_pos > 0 && d_pos % 2 == 0 && xyz_stride >= 3, "pq3d_fourier_pos: bad shape");
+  const int64_t total = static_cast<int64_t>(B) * L * (d_pos / 2);
+  fourier_pos_kernel<<<grid_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      xyz, xyz_stride, coord_min, coord_max, gauss_B, reinterpret_cast<__nv_bfloat16*>(out_bf16), B, L, d_pos / 2);
+  PQ3D_CUDA(cudaGetLastError());
+  return PQ3D_OK;
+}
+
+extern "C" int pq3d_pairwise_locs(const float* centers, int c_stride, float* out, int B, int N, float eps,
+                                  void* stream) {
+  PQ3D_CHECK_ARG(centers && out && B > 0 && N > 0 && c_stride >= 3, "pq3d_pairwise_locs: bad argument");
+  pairwise_locs_kernel<<<B, 512, 0, reinterpret_cast<cudaStream_t>(stream)>>>(centers, c_stride, out, N, eps);
   PQ3D_CUDA(cudaGetLastError());
   return PQ3D_OK;
 }

@@ -194,3 +194,32 @@ def cast_bf16(x: torch.Tensor, out: torch.Tensor, add: Optional[torch.Tensor] = 
     rc = _lib.lib().pq3d_cast_bf16(x.data_ptr(), _p(add), out.data_ptr(), x.numel(), _stream())
     _lib.check(rc, "pq3d_cast_bf16")
     _count()
+
+
+def fourier_pos(xyz: torch.Tensor, coord_min: torch.Tensor, coord_max: torch.Tensor, gauss_B: torch.Tensor,
+                out: torch.Tensor):
+    """xyz (B, L, >=3) fp32 (last-dim stride 1) -> out (B*L, d_pos) bf16."""
+    _chk(xyz, torch.float32, "xyz", 3)
+    _chk(out, bf16, "out")
+    B, L = xyz.shape[:2]
+    if xyz.stride(2) != 1 or xyz.stride(0) != L * xyz.stride(1):
+        xyz = xyz.contiguous()
+    rc = _lib.lib().pq3d_fourier_pos(xyz.data_ptr(), xyz.stride(1), coord_min.contiguous().data_ptr(),
+                                     coord_max.contiguous().data_ptr(), gauss_B.contiguous().data_ptr(),
+                                     out.data_ptr(), B, L, 2 * gauss_B.shape[1], _stream())
+    _lib.check(rc, "pq3d_fourier_pos")
+    _count()
+
+
+def pairwise_locs(centers: torch.Tensor, out: Optional[torch.Tensor] = None, eps: float = 1e-10) -> torch.Tensor:
+    """centers (B, N, >=3) fp32 -> (B, N, N, 5) fp32."""
+    _chk(centers, torch.float32, "centers", 3)
+    B, N = centers.shape[:2]
+    if centers.stride(2) != 1 or centers.stride(0) != N * centers.stride(1):
+        centers = centers.contiguous()
+    if out is None:
+        out = torch.empty(B, N, N, 5, dtype=torch.float32, device=centers.device)
+    rc = _lib.lib().pq3d_pairwise_locs(centers.data_ptr(), centers.stride(1), out.data_ptr(), B, N, eps, _stream())
+    _lib.check(rc, "pq3d_pairwise_locs")
+    _count()
+    return out

@@ -1,0 +1,339 @@
+"""Query3DUnified — the drop-in model boundary (model/query3d_unified.py:29-238).
+
+Same constructor (`Query3DUnified(cfg)`), `forward(data_dict) -> data_dict` (mutates and returns the
+same dict) and `get_opt_params()`; same attribute / parameter names so stage-1 / stage-2 checkpoints
+load.  `cfg` may be an omegaconf DictConfig, a plain nested dict or any attribute mapping.
+
+In scope here: coordinate encoders, ObjectEncoder projection
+branches, prompt features supplied as `data_dict['prompt_feat']`, pairwise geometry, the decoder,
+the mask / ground heads.  Out of scope (raise, never silently fall back): MinkowskiEngine voxel
+backbone, PointNet++ tokenizer, CLIP / T5 towers.
+"""
+from __future__ import annotations
+
+from copy import copy
+from functools import partial
+from typing import Any, Dict, Optional
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .mask_head import MaskHeadSegLevel, MlpHeadRunner, mlp_head_params
+from .query_encoder import QueryEncoder, QueryMaskEncoder
+
+bf16 = torch.bfloat16
+
+
+# ---- cfg access that works for DictConfig / dict / attr-dict --------------------------------
+def cfg_get(cfg: Any, key: str, default=None):
+    if cfg is None:
+        return default
+    if isinstance(cfg, dict):
+        return cfg.get(key, default)
+    if hasattr(cfg, "get"):
+        try:
+            return cfg.get(key, default)
+        except TypeError:
+            pass
+    return getattr(cfg, key, default)
+
+
+def cfg_path(cfg: Any, path: str, default=None):
+    cur = cfg
+    for k in path.split("."):
+        cur = cfg_get(cur, k, None)
+        if cur is None:
+            return default
+    return cur
+
+
+def cfg_plain(cfg: Any):
+    """cfg2dict (common/type_utils.py:6-7) without requiring omegaconf."""
+    try:
+        from omegaconf import OmegaConf, DictConfig, ListConfig      # type: ignore
+        if isinstance(cfg, (DictConfig, ListConfig)):
+            return OmegaConf.to_container(cfg, resolve=True)
+    except Exception:
+        pass
+    if isinstance(cfg, dict) or (hasattr(cfg, "keys") and hasattr(cfg, "__getitem__")):
+        return {k: cfg_plain(cfg[k]) for k in cfg.keys()}
+    if isinstance(cfg, (list, tuple)):
+        return [cfg_plain(v) for v in cfg]
+    return cfg
+
+
+class LinearLN(nn.Sequential):
+    """nn.Sequential(Linear, LayerNorm) evaluated by the GEMM + LayerNorm kernels."""
+
+    def __init__(self, d_in, d_out):
+        super().__init__(nn.Linear(d_in, d_out), nn.LayerNorm(d_out))
+        self._key, self._w = None, None
+
+    def _weights(self, dev):
+        ps = list(self.parameters())
+        key = (str(dev), tuple(p._version for p in ps), tuple(p.data_ptr() for p in ps))
+        if self._key != key:
+            w = self[0].weight.detach()
+            k_pad = (w.shape[1] + 63) // 64 * 64           # tensor-core K granularity; zero columns are exact
+            if k_pad != w.shape[1]:
+                w = torch.nn.functional.pad(w, (0, k_pad - w.shape[1]))
+            self._w = dict(w=w.to(dev, bf16).contiguous(), b=self[0].bias.detach().float().to(dev),
+                           g=self[1].weight.detach().float().to(dev)[None].contiguous(),
+                           be=self[1].bias.detach().float().to(dev)[None].contiguous(), eps=self[1].eps, k=k_pad)
+            self._key = key
+        return self._w
+
+    def run16(self, x16: torch.Tensor, R: int, out32: torch.Tensor):
+        w = self._weights(x16.device)
+        D = w["w"].shape[0]
+        y = torch.empty(R, D, dtype=torch.float32, device=x16.device)
+        ops.linear(x16, w["w"], y, M=R, N=D, K=w["k"], bias=w["b"])
+        ops.add_layernorm(y, None, w["g"], w["be"], w["eps"], R, D, out_f32=out32)
+        return out32
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        lead, din = x.shape[:-1], x.shape[-1]
+        R = x.numel() // din
+        w = self._weights(x.device)
+        x2 = x.reshape(R, din).float()
+        if w["k"] != din:
+            x2 = torch.nn.functional.pad(x2, (0, w["k"] - din))
+        x16 = torch.empty(R, w["k"], dtype=bf16, device=x.device)
+        ops.cast_bf16(x2.contiguous(), x16)
+        out = torch.empty(R, w["w"].shape[0], dtype=torch.float32, device=x.device)
+        return self.run16(x16, R, out).view(*lead, -1)
+
+
+class CoordinateEncoder(nn.Module):
+    """model/query3d_unified.py:15-27: Fourier features (fp32, Gaussian matrix buffer `pos_enc.gauss_B`)
+    -> Linear -> LayerNorm."""
+
+    class _PosEnc(nn.Module):
+        def __init__(self, d_pos, d_in=3, gauss_scale=1.0):
+            super().__init__()
+            self.register_buffer("gauss_B", torch.empty(d_in, d_pos // 2).normal_() * gauss_scale)
+
+    def __init__(self, hidden_size, use_projection=True):
+        super().__init__()
+        if not use_projection:
+            raise NotImplementedError("CoordinateEncoder is always built with use_projection=True on this path")
+        self.pos_enc = CoordinateEncoder._PosEnc(hidden_size)
+        self.feat_proj = LinearLN(hidden_size, hidden_size)
+
+    def forward(self, coords, input_range):
+        B, L = coords.shape[:2]
+        D = self.pos_enc.gauss_B.shape[1] * 2
+        x16 = torch.empty(B * L, D, dtype=bf16, device=coords.device)
+        ops.fourier_pos(coords.float(), input_range[0].float(), input_range[1].float(), self.pos_enc.gauss_B.float(), x16)
+        out = torch.empty(B * L, D, dtype=torch.float32, device=coords.device)
+        return self.feat_proj.run16(x16, B * L, out).view(B, L, D)
+
+
+class ObjectEncoder(nn.Module):
+    """Projection branch of modules/vision/object_encoder.py:14-79: Linear(Cin->D) + LayerNorm
+    (+ Dropout, identity in eval).  The PointNet++ backbone and the cls head are upstream feature
+    extraction, out of scope."""
+
+    def __init__(self, cfg=None, backbone="none", input_feat_size=768, hidden_size=768, freeze_backbone=False,
+                 use_projection=False, tgt_cls_num=607, pretrained=None, dropout=0.1, use_cls_head=True):
+        super().__init__()
+        if backbone != "none":
+            raise NotImplementedError("ObjectEncoder backbone='pointnet++' (frozen tokenizer) is out of scope; "
+                                      "feed its per-object features with backbone='none'")
+        if use_cls_head:
+            raise NotImplementedError("ObjectEncoder.use_cls_head=True is not on the Query3DUnified path "
+                                      "(all shipped configs set it to False)")
+        self.use_projection = use_projection
+        if use_projection:
+            self.input_feat_proj = LinearLN(input_feat_size, hidden_size)
+        elif input_feat_size != hidden_size:
+            raise AssertionError("input_feat_size should be equal to hidden_size!")
+        with torch.no_grad():                                     # _init_weights_bert (modules/weights.py)
+            for m in self.modules():
+                if isinstance(m, nn.Linear):
+                    m.weight.normal_(0.0, 0.02)
+                    m.bias.zero_()
+
+    def forward(self, obj_feats, data_dict=None, **kwargs):
+        if self.training:
+            raise NotImplementedError("pq3d_b200.ObjectEncoder: inference path only — call .eval()")
+        return self.input_feat_proj(obj_feats) if self.use_projection else obj_feats
+
+
+class GroundHead(nn.Module):
+    """modules/heads/grounding_head.py:42-55."""
+
+    def __init__(self, cfg=None, input_size=768, hidden_size=768, dropout=0.3):
+        super().__init__()
+        self.og3d_head = mlp_head_params(input_size, hidden_size, 1, dropout=dropout)
+        self._run = MlpHeadRunner(self.og3d_head)
+
+    def forward(self, obj_embeds, obj_masks=None, **kwargs):
+        B, N, D = obj_embeds.shape
+        x16 = torch.empty(B * N, D, dtype=bf16, device=obj_embeds.device)
+        ops.cast_bf16(obj_embeds.reshape(B * N, D).contiguous().float(), x16)
+        logits = self._run(x16, B * N).view(B, N)
+        if obj_masks is not None:
+            logits = logits.masked_fill_(obj_masks.logical_not(), -float("inf"))
+        return logits
+
+
+MODULES = {"QueryMaskEncoder": QueryMaskEncoder, "QueryEncoder": QueryEncoder, "MaskHeadSegLevel": MaskHeadSegLevel,
+           "ObjectEncoder": ObjectEncoder, "GroundHead": GroundHead}
+
+
+def build_module_by_name(cfg):
+    """modules/build.py:24-31 against this package's own name -> class table."""
+    name = cfg_get(cfg, "name")
+    if name not in MODULES:
+        raise NotImplementedError(f"Unknown module: {name} (pq3d_b200 provides {sorted(MODULES)})")
+    args = cfg_get(cfg, "args")
+    kwargs = cfg_plain(args) if args is not None else {}
+    return MODULES[name](cfg, **kwargs)
+
+
+class Query3DUnified(nn.Module):
+    def __init__(self, cfg):
+        super().__init__()
+        self.cfg = cfg
+        model = cfg_get(cfg, "model")
+        self.memories = list(cfg_get(model, "memories"))
+        self.heads = list(cfg_get(model, "heads"))
+        self.use_offline_voxel_fts = cfg_get(model, "use_offline_voxel_fts", False)
+        self.use_offline_attn_mask = cfg_get(model, "use_offline_attn_mask", False)
+        self.inputs = self.memories[:]
+        self.pairwise_rel_type = cfg_path(model, "obj_loc.pairwise_rel_type")
+        self.spatial_dim = cfg_path(model, "obj_loc.spatial_dim")
+        self.num_heads = cfg_path(model, "unified_encoder.args.num_attention_heads")
+        self.skip_query_encoder_mask_pred = cfg_get(model, "skip_query_encoder_mask_pred", False)
+        if self.pairwise_rel_type != "center" or self.spatial_dim != 5:
+            raise NotImplementedError("only pairwise_rel_type='center', spatial_dim=5 (all shipped configs)")
+        self.prompt_types = ["txt", "loc"]
+        for inp in self.inputs:
+            if inp == "prompt":
+                # txt_encoder (frozen CLIP tower + projection) is out of scope: prompt features enter
+                # as data_dict['prompt_feat'] (B, T, hidden); see prompt_encoder()
+                continue
+            if inp == "voxel" and not self.use_offline_voxel_fts:
+                raise NotImplementedError("online voxel features need the MinkowskiEngine sparse-conv backbone "
+                                          "(out of scope); set model.use_offline_voxel_fts=True")
+            setattr(self, inp + "_encoder", build_module_by_name(cfg_get(model, inp + "_encoder")))
+        dim_loc = cfg_path(model, "obj_loc.dim_loc")
+        hidden_size = cfg_get(model, "hidden_size")
+        self.dim_loc, self.hidden_size = dim_loc, hidden_size
+        if dim_loc > 3:
+            self.coord_encoder = LinearLN(3, hidden_size)
+            self.box_encoder = LinearLN(3, hidden_size)
+        else:
+            self.coord_encoder = CoordinateEncoder(hidden_size)
+        self.unified_encoder = build_module_by_name(cfg_get(model, "unified_encoder"))
+        for head in self.heads:
+            if head == "generation":
+                raise NotImplementedError("the T5 generation head is out of scope (needs pretrained weights)")
+            setattr(self, head + "_head", build_module_by_name(cfg_get(model, head + "_head")))
+
+    def prompt_encoder(self, data_dict):
+        """model/query3d_unified.py:80-108 with the text tower factored out: `prompt_feat` (B,T,D) is
+        whatever txt_encoder would have produced; returns (feat, mask True=ignore)."""
+        if "prompt_feat" not in data_dict:
+            raise NotImplementedError("pq3d_b200.Query3DUnified takes precomputed prompt features in "
+                                      "data_dict['prompt_feat'] (the CLIP text tower is out of scope)")
+        return data_dict["prompt_feat"], data_dict["prompt_pad_masks"].logical_not()
+
+    def forward(self, data_dict):
+        input_dict = {}
+        mask = data_dict["query_pad_masks"].logical_not()
+        query_locs = data_dict["query_locs"][:, :, :self.dim_loc]
+        coord_min, coord_max = data_dict["coord_min"], data_dict["coord_max"]
+        fts_locs = data_dict["seg_center"]
+        if self.dim_loc > 3:
+            query_pos = self.coord_encoder(query_locs[:, :, :3]) + self.box_encoder(query_locs[:, :, 3:6])
+            box_pos = self.box_encoder(fts_locs[:, :, 3:6])
+            # the reference adds box_encoder(fts_locs[..., 3:6]) twice (query3d_unified.py:128,131-132)
+            fts_pos = self.coord_encoder(fts_locs[:, :, :3]) + box_pos
+            fts_pos += box_pos
+        else:
+            query_pos = self.coord_encoder(query_locs[:, :, :3], input_range=[coord_min, coord_max])
+            fts_pos = self.coord_encoder(fts_locs[:, :, :3], input_range=[coord_min, coord_max])
+        input_dict["query"] = (torch.zeros_like(query_pos), mask, query_pos)
+        for inp in self.inputs:
+            feat, mask, pos = None, None, None
+            if inp == "prompt":
+                feat, mask = self.prompt_encoder(data_dict)
+            elif inp == "mv":
+                feat = self.mv_encoder(obj_feats=data_dict["mv_seg_fts"])
+                mask = data_dict["mv_seg_pad_masks"].logical_not()
+                pos = fts_pos
+            elif inp == "pc":
+                feat = self.pc_encoder(obj_feats=data_dict["pc_seg_fts"])
+                mask = data_dict["pc_seg_pad_masks"].logical_not()
+                pos = fts_pos
+            elif inp == "voxel":
+                feat = self.voxel_encoder(data_dict["voxel_seg_fts"])
+                mask = data_dict["voxel_seg_pad_masks"].logical_not()
+                pos = fts_pos
+            else:
+                raise NotImplementedError(f"Unknow input type: {inp}")
+            input_dict[inp] = [feat, mask, pos]
+        offline_attn_masks = data_dict["offline_attn_mask"] if self.use_offline_attn_mask else None
+        seg_fts_for_match = []
+        for inp in self.inputs:
+            if inp in ("voxel", "mv", "pc"):
+                feats = copy(input_dict[inp][:])
+                if isinstance(feats[0], list):
+                    assert inp == "voxel"
+                    feats[0] = feats[0][-1]
+                seg_fts_for_match.append(feats)
+        if hasattr(self, "mask_head"):
+            mask_head_partial = partial(self.mask_head, seg_fts_for_match=seg_fts_for_match,
+                                        seg_masks=data_dict["seg_pad_masks"].logical_not(),
+                                        offline_attn_masks=offline_attn_masks,
+                                        skip_prediction=self.skip_query_encoder_mask_pred)
+        else:
+            mask_head_partial = None
+        pairwise_locs = ops.pairwise_locs(query_locs[:, :, :3].float()) if self.unified_encoder.spatial_selfattn else None
+
+        query, predictions_class, predictions_mask = self.unified_encoder(input_dict, pairwise_locs, mask_head_partial)
+
+        for head in self.heads:
+            if head == "ground":
+                logits = self.ground_head(query, data_dict["query_pad_masks"])
+                data_dict["ground_logits"] = logits
+                data_dict["og3d_logits"] = logits
+                data_dict["ground_label"] = data_dict.get("tgt_object_id")
+            elif head == "mask":
+                if self.skip_query_encoder_mask_pred:
+                    mask_head_partial = partial(self.mask_head, seg_fts_for_match=seg_fts_for_match,
+                                                seg_masks=data_dict["seg_pad_masks"].logical_not(),
+                                                offline_attn_masks=offline_attn_masks, skip_prediction=False)
+                    predictions_class, predictions_mask = [], []
+                pred_logits, pred_masks, _ = mask_head_partial(query=query)
+                predictions_class.append(pred_logits)
+                predictions_mask.append(pred_masks)
+                data_dict["predictions_class"] = predictions_class
+                data_dict["predictions_mask"] = predictions_mask
+            else:
+                raise NotImplementedError(f"Unknow head type: {head}")
+        return data_dict
+
+    def get_opt_params(self):
+        """model/query3d_unified.py:224-238 with optim/utils.py:1-18 inlined: per-submodule groups,
+        weight decay 0.01 except names containing 'bias' / 'LayerNorm.bias' / 'LayerNorm.weight'."""
+        default_lr = cfg_path(self.cfg, "solver.lr")
+        groups = []
+        no_decay = ["bias", "LayerNorm.bias", "LayerNorm.weight"]
+        for name, module in self._modules.items():
+            lr = cfg_get(cfg_path(self.cfg, "model." + name), "lr", None) or default_lr
+            if lr != default_lr:
+                print(f"Change lr from default {default_lr} to {lr} for {name} module.")
+            decay, nodecay = [], []
+            for n, p in module.named_parameters():
+                if not p.requires_grad:
+                    continue
+                (nodecay if any(nd in n for nd in no_decay) else decay).append(p)
+            groups += [{"params": decay, "name": name, "weight_decay": 0.01, "lr": lr},
+                       {"params": nodecay, "name": name, "weight_decay": 0.0, "lr": lr}]
+        optimized = [p for g in groups for p in g["params"]]
+        assert len(optimized) == len(list(self.parameters())), "Some parameters are not optimized!"
+        return groups

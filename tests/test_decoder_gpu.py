@@ -1,0 +1,233 @@
+"""GPU parity of the host-side mirror modules (running the sm_100a kernels through the C ABI)
+against (1) the golden fixtures the REAL reference produced in fp32 and (2) the oracle restatement
+run on the same GPU in fp32 and under torch.autocast(bf16) — the reference's own mixed-precision path.
+
+Tolerance.  north_star asks for 1e-3 rel on bf16.  bf16 operands alone perturb a 768-long dot product
+by ~1.6e-3 relative, so no bf16-operand implementation (the reference's autocast path included) is
+within 1e-3 of the fp32 result end to end; what CAN be asserted, and is, is
+  (a) err(ours, fp32) <= 1.25 * err(reference-under-autocast, fp32) + 1e-3   [||.||inf / ||.||inf]
+      i.e. we are at least as close to the fp32 reference as the reference's bf16 path is, and
+  (b) an absolute cap of 3e-2 on the same metric,
+with the measured values printed.  The 1e-3 bar itself is asserted where it is meaningful: per kernel,
+on identical bf16-rounded operands, for fp32 outputs (tests/kernel_checks.py).
+Bool masks: exact wherever the fp32 logit is not within rounding distance of the threshold.
+"""
+import pytest
+import torch
+
+import _cases as C
+from oracle import restatement as O
+from pq3d_b200 import synth
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def rel(a, b):
+    a, b = a.float().cpu(), b.float().cpu()
+    fin = torch.isfinite(b) & (b.abs() < 1e5)
+    return ((a[fin] - b[fin]).abs().max() / b[fin].abs().max().clamp_min(1e-12)).item()
+
+
+def check_close(name, ours, gold, ref_bf16):
+    e_ours, e_ref = rel(ours, gold), rel(ref_bf16, gold)
+    print(f"{name}: err(ours, fp32 reference) = {e_ours:.3e}; err(autocast-bf16 oracle, fp32 reference) = {e_ref:.3e}")
+    assert torch.isfinite(ours.float()).all() or not torch.isfinite(gold).all()
+    assert e_ours <= 1.25 * e_ref + 1e-3, f"{name}: {e_ours:.3e} worse than the reference's own bf16 path {e_ref:.3e}"
+    assert e_ours <= 3e-2
+
+
+def build_decoder(w, sd):
+    from pq3d_b200.query_encoder import QueryMaskEncoder
+    enc = QueryMaskEncoder(None, **w.decoder_kwargs()).eval()
+    enc.load_state_dict(sd, strict=True)
+    return enc.to(DEV)
+
+
+def oracle_autocast(fn):
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+        return fn()
+
+
+@pytest.mark.parametrize("name", C.golden_files("decoder"))
+def test_decoder_vs_golden(name):
+    g = C.load_golden(name)
+    case = g["case"]
+    w = C.build_workload(case)
+    sd = synth.decoder_state_dict(w, seed=case["wseed"], sharp=case["sharp"])
+    enc = build_decoder(w, sd)
+    inp, pw, _ = synth.make_decoder_inputs(w, device=DEV)
+    with torch.no_grad():
+        q, pc, pm = enc(synth.clone_input_dict(inp), pw)
+    torch.cuda.synchronize()
+    assert pc == [] and pm == []
+    ref16 = oracle_autocast(lambda: O.query_mask_encoder(C.to_dev(sd, DEV), O.DecoderCfg(**w.decoder_kwargs()),
+                                                         synth.clone_input_dict(inp), pw)[0])
+    check_close(name, q, g["out"]["query"], ref16)
+
+
+@pytest.mark.parametrize("name", C.golden_files("maskhead"))
+def test_maskhead_vs_golden(name):
+    from functools import partial
+    from pq3d_b200.mask_head import MaskHeadSegLevel
+    g = C.load_golden(name)
+    case, gold = g["case"], g["out"]
+    w = C.build_workload(case)
+    sd = synth.decoder_state_dict(w, seed=case["wseed"], sharp=case["sharp"])
+    n_match = len([m for m in w.memories if m in synth.SCENE_MEMORIES])
+    sd_mh = synth.draw_state_dict(synth.mask_head_param_shapes(n_match), case["wseed"] + 100)
+    enc = build_decoder(w, sd)
+    mh = MaskHeadSegLevel(None, 768, 201, memories_for_match=list(w.memories), filter_out_classes=[0, 2]).eval()
+    mh.load_state_dict(sd_mh, strict=True)
+    mh = mh.to(DEV)
+    inp, pw, d = synth.make_decoder_inputs(w, device=DEV)
+    head = partial(mh, seg_fts_for_match=C.mask_head_inputs(w, inp), seg_masks=(~d["seg_pad_masks"]).to(DEV),
+                   offline_attn_masks=None, skip_prediction=False)
+    with torch.no_grad():
+        q, pc, pm = enc(synth.clone_input_dict(inp), pw, head)
+        c, m, a = head(query=q)
+    torch.cuda.synchronize()
+    assert len(pm) == int(gold["n_pred"])
+    ref16 = oracle_autocast(lambda: C.oracle_maskhead(case, device=DEV))
+    check_close(name + ".query", q, gold["query"], ref16["query"])
+    check_close(name + ".pred_mask_first", pm[0], gold["pred_mask_first"], ref16["pred_mask_first"])
+    check_close(name + ".final_mask", m, gold["final_mask"], ref16["final_mask"])
+    check_close(name + ".final_class", c, gold["final_class"], ref16["final_class"])
+    assert torch.equal(torch.isinf(c).cpu(), torch.isinf(gold["final_class"])), "filtered classes must be -inf"
+    assert torch.equal((m == -1e6).cpu(), gold["final_mask"] == -1e6), "padded segments must be exactly -1e6"
+    # first-call mask: inputs are identical (query = 0), so it differs from fp32 only by bf16 rounding of logits
+    am0 = (pm[0].sigmoid().permute(0, 2, 1) < 0.5).cpu()
+    gm0 = gold["pred_mask_first"].sigmoid().permute(0, 2, 1) < 0.5
+    diff = am0 != gm0
+    lg = gold["pred_mask_first"].permute(0, 2, 1)
+    scale = lg[lg.abs() < 1e5].abs().max()
+    assert (lg[diff].abs() <= 2e-2 * scale).all(), "attention-mask bits differ away from the decision threshold"
+    print(f"{name}: first-call attn-mask bits differing from fp32 reference: {int(diff.sum())} / {diff.numel()} "
+          f"(all within 2e-2*max|logit| of the threshold)")
+    # the bool mask we return is exactly sigmoid(our logits) < 0.5
+    assert torch.equal(a.cpu(), (m.sigmoid().permute(0, 2, 1) < 0.5).cpu())
+
+
+@pytest.mark.parametrize("name", C.golden_files("model"))
+def test_model_vs_golden(name):
+    from pq3d_b200.query3d_unified import Query3DUnified
+    g = C.load_golden(name)
+    case, gold = g["case"], g["out"]
+    w, cfg = C.model_cfg(case)
+    sd = synth.draw_state_dict(synth.model_param_shapes(cfg), case["wseed"], case["sharp"])
+    model = Query3DUnified(cfg).eval()
+    model.load_state_dict(sd, strict=True)
+    model = model.to(DEV)
+    d = C.to_dev(synth.make_model_data_dict(w, cfg), DEV)
+    with torch.no_grad():
+        out = model(d)
+    torch.cuda.synchronize()
+    ref16 = oracle_autocast(lambda: C.oracle_model(case, device=DEV))
+    if "mask" in case["heads"]:
+        assert len(out["predictions_mask"]) == int(gold["n_pred"])
+        check_close(name + ".pred_mask_last", out["predictions_mask"][-1], gold["pred_mask_last"], ref16["pred_mask_last"])
+        check_close(name + ".pred_class_last", out["predictions_class"][-1], gold["pred_class_last"], ref16["pred_class_last"])
+    if "ground" in case["heads"]:
+        check_close(name + ".ground_logits", out["ground_logits"], gold["ground_logits"], ref16["ground_logits"])
+        assert torch.equal(torch.isinf(out["ground_logits"]).cpu(), torch.isinf(gold["ground_logits"]))
+
+
+# ---- full-size, size-independent properties (BASELINE config 3 per-GPU shard) ------------------
+@pytest.fixture(scope="module")
+def c3():
+    w = synth.workload("c3")
+    sd = synth.decoder_state_dict(w, seed=0, sharp=2.0)
+    enc = build_decoder(w, sd)
+    inp, pw, d = synth.make_decoder_inputs(w, device=DEV)
+    with torch.no_grad():
+        base = enc(synth.clone_input_dict(inp), pw)[0]
+    return w, sd, enc, inp, pw, base
+
+
+def test_c3_matches_oracle_on_gpu(c3):
+    w, sd, enc, inp, pw, base = c3
+    sdd = C.to_dev(sd, DEV)
+    cfg = O.DecoderCfg(**w.decoder_kwargs())
+    torch.backends.cuda.matmul.allow_tf32 = False
+    with torch.no_grad():
+        ref32 = O.query_mask_encoder(sdd, cfg, synth.clone_input_dict(inp), pw)[0]
+    ref16 = oracle_autocast(lambda: O.query_mask_encoder(sdd, cfg, synth.clone_input_dict(inp), pw)[0])
+    check_close("c3 (B=4,N=100,S=2048,[mv,pc,voxel,prompt],mixed)", base, ref32, ref16)
+
+
+def test_c3_padding_invariance(c3):
+    """Appending masked tokens must not change the output beyond tile-order rounding."""
+    w, sd, enc, inp, pw, base = c3
+    inp2 = synth.clone_input_dict(inp)
+    g = torch.Generator().manual_seed(5)
+    pad = 136
+    newpos = None
+    for m in ("mv", "pc", "voxel"):
+        feat, mask, pos = inp2[m]
+        B = feat.shape[0]
+        if newpos is None:
+            newpos = torch.cat([pos, torch.randn(B, pad, 768, generator=g).to(DEV)], 1)
+        inp2[m] = [torch.cat([feat, torch.randn(B, pad, 768, generator=g).to(DEV)], 1),
+                   torch.cat([mask, torch.ones(B, pad, dtype=torch.bool, device=DEV)], 1), newpos]
+    with torch.no_grad():
+        out = enc(inp2, pw)[0]
+    e = rel(out, base)
+    print(f"padding invariance: {e:.3e}")
+    assert e <= 1e-3
+
+
+def test_c3_permutation_equivariance(c3):
+    w, sd, enc, inp, pw, base = c3
+    inp2 = synth.clone_input_dict(inp)
+    S = inp["mv"][0].shape[1]
+    perm = torch.randperm(S, generator=torch.Generator().manual_seed(6)).to(DEV)
+    for m in ("mv", "pc", "voxel"):
+        feat, mask, pos = inp2[m]
+        inp2[m] = [feat[:, perm].contiguous(), mask[:, perm].contiguous(), pos[:, perm].contiguous()]
+    with torch.no_grad():
+        out = enc(inp2, pw)[0]
+    e = rel(out, base)
+    print(f"permutation equivariance: {e:.3e}")
+    assert e <= 5e-3          # P is rounded to bf16 per 128-key tile; a permutation regroups the tiles
+
+
+def test_c3_idempotent_and_input_not_clobbered(c3):
+    w, sd, enc, inp, pw, base = c3
+    before = inp["mv"][0].clone()
+    with torch.no_grad():
+        again = enc(synth.clone_input_dict(inp), pw)[0]
+    assert torch.equal(again, base), "same inputs must give bit-identical outputs"
+    assert torch.equal(inp["mv"][0], before)
+
+
+def test_all_keys_masked_gives_ln_of_bias():
+    """Known answer: with every key masked only the zero-attn key is attended, so one sequential
+    cross-attention layer returns LN(tgt + out_proj.bias) before self-attention/FFN; checked on the
+    attention kernel directly: O must be exactly 0."""
+    from pq3d_b200 import ops
+    B, H, N, S = 2, 12, 100, 300
+    D = H * 64
+    Q = torch.randn(B * N, D, device=DEV).bfloat16()
+    Sp = ops.pad8(S)
+    K = torch.randn(B * Sp, D, device=DEV).bfloat16()
+    Vt = torch.randn(D, B * Sp, device=DEV).bfloat16()
+    bits = ops.pack_mask(torch.ones(B, S, dtype=torch.bool, device=DEV))
+    O_ = torch.full((1, B * N, D), float("nan"), dtype=torch.bfloat16, device=DEV)
+    ops.attention(Q, 0, [ops.AttnMemory(K, 0, Vt, 0, S, Sp, bits, bits.stride(0), 0, 0)], O_, B * N * D, B, H, N, True)
+    torch.cuda.synchronize()
+    assert (O_ == 0).all()
+
+
+def test_rejects_non_bool_masks_and_training_mode():
+    w = synth.Workload("t", 1, 16, 64, ["pc"], "parallel", num_layers=1)
+    enc = build_decoder(w, synth.decoder_state_dict(w, seed=1))
+    inp, pw, _ = synth.make_decoder_inputs(w, device=DEV)
+    bad = synth.clone_input_dict(inp)
+    bad["pc"][1] = bad["pc"][1].float()
+    with torch.no_grad(), pytest.raises(TypeError):
+        enc(bad, pw)
+    with pytest.raises(NotImplementedError):
+        enc(synth.clone_input_dict(inp), pw)              # grad enabled: no silent autograd fallback
+    enc.train()
+    with torch.no_grad(), pytest.raises(NotImplementedError):
+        enc(synth.clone_input_dict(inp), pw)
