@@ -53,7 +53,8 @@ int pq3d_linear_bf16(const void* A, int64_t lda, int64_t a_rows_total, int64_t a
 /* Masked softmax attention for n_mem (<= 4) memories in one launch, head_dim = 64.
  *   Q : bf16 [B*Nq, ldq]; memory i / head h at columns i*q_mem_stride + h*64; already scaled by 1/8
  *   K[i] : bf16 [B*S_pitch[i], ldk[i]]; head h at columns k_col0[i] + h*64
- *   Vt[i]: bf16 [vt_rows[i], ldvt[i]] — V TRANSPOSED: row vt_row0[i] + h*64 + d, column b*S_pitch[i] + s
+ *   Vt[i]: bf16 [vt_rows[i], ldvt[i]] — V TRANSPOSED: row vt_row0[i] + h*64 + d, column b*Vt_pitch[i] + s
+ *          (Vt_pitch multiple of 8: TMA strides are 16-byte granular; pad columns must hold finite values)
  *   mask_bits[i]: packed by pq3d_pack_mask (1 = ignore), word address
  *                 b*mask_b_stride + h*mask_h_stride + n*mask_q_stride + s/32; NULL = nothing masked
  *   O : bf16, element (i, b, n, h*64+d) at O[i*o_mem_stride + (b*Nq+n)*ldo + h*64 + d]
@@ -67,7 +68,7 @@ int pq3d_linear_bf16(const void* A, int64_t lda, int64_t a_rows_total, int64_t a
 int pq3d_attention_fwd(int n_mem, const void* Q, int64_t ldq, int64_t q_mem_stride,
                        const void* const* K, const int64_t* ldk, const int64_t* k_col0,
                        const void* const* Vt, const int64_t* ldvt, const int64_t* vt_row0, const int64_t* vt_rows,
-                       const int32_t* S, const int32_t* S_pitch,
+                       const int32_t* S, const int32_t* S_pitch, const int32_t* Vt_pitch,
                        const uint32_t* const* mask_bits, const int64_t* mask_b_stride,
                        const int64_t* mask_h_stride, const int64_t* mask_q_stride,
                        void* O, int64_t ldo, int64_t o_mem_stride, int B, int H, int Nq, int zero_attn,

@@ -342,13 +342,14 @@ using namespace pq3d;
 extern "C" int pq3d_attention_fwd(int n_mem, const void* Q, int64_t ldq, int64_t q_mem_stride, const void* const* K,
                                   const int64_t* ldk, const int64_t* k_col0, const void* const* Vt,
                                   const int64_t* ldvt, const int64_t* vt_row0, const int64_t* vt_rows,
-                                  const int32_t* S, const int32_t* S_pitch, const uint32_t* const* mask_bits,
+                                  const int32_t* S, const int32_t* S_pitch, const int32_t* Vt_pitch,
+                                  const uint32_t* const* mask_bits,
                                   const int64_t* mask_b_stride, const int64_t* mask_h_stride,
                                   const int64_t* mask_q_stride, void* O, int64_t ldo, int64_t o_mem_stride, int B,
                                   int H, int Nq, int zero_attn, const float* pairwise_locs, const float* loc_w,
                                   const float* loc_b, void* stream) {
   PQ3D_CHECK_ARG(n_mem >= 1 && n_mem <= kMaxMem, "pq3d_attention_fwd: n_mem=%d not in [1,%d]", n_mem, kMaxMem);
-  PQ3D_CHECK_ARG(Q && O && K && Vt && S && S_pitch, "pq3d_attention_fwd: null argument");
+  PQ3D_CHECK_ARG(Q && O && K && Vt && S && S_pitch && Vt_pitch, "pq3d_attention_fwd: null argument");
   PQ3D_CHECK_ARG(B > 0 && H > 0 && Nq > 0, "pq3d_attention_fwd: bad shape B=%d H=%d Nq=%d", B, H, Nq);
   PQ3D_CHECK_ARG(ldq % 8 == 0 && ldo % 8 == 0 && (reinterpret_cast<uintptr_t>(Q) & 15) == 0 &&
                      (reinterpret_cast<uintptr_t>(O) & 15) == 0 && (o_mem_stride % 8) == 0,
@@ -365,10 +366,10 @@ extern "C" int pq3d_attention_fwd(int n_mem, const void* Q, int64_t ldq, int64_t
     if (rc != PQ3D_OK) return rc;
   }
   for (int i = 0; i < n_mem; ++i) {
-    PQ3D_CHECK_ARG(S[i] > 0 && S_pitch[i] >= S[i] && S_pitch[i] % 8 == 0,
-                   "pq3d_attention_fwd: memory %d: S=%d S_pitch=%d (pitch must be >= S and a multiple of 8)", i, S[i],
-                   S_pitch[i]);
-    PQ3D_CHECK_ARG(ldk[i] % 8 == 0 && ldvt[i] % 8 == 0 && ldvt[i] >= (int64_t)B * S_pitch[i] &&
+    PQ3D_CHECK_ARG(S[i] > 0 && S_pitch[i] >= S[i] && Vt_pitch[i] >= S[i] && Vt_pitch[i] % 8 == 0,
+                   "pq3d_attention_fwd: memory %d: S=%d S_pitch=%d Vt_pitch=%d (pitches must be >= S, Vt_pitch a "
+                   "multiple of 8)", i, S[i], S_pitch[i], Vt_pitch[i]);
+    PQ3D_CHECK_ARG(ldk[i] % 8 == 0 && ldvt[i] % 8 == 0 && ldvt[i] >= (int64_t)B * Vt_pitch[i] &&
                        (reinterpret_cast<uintptr_t>(K[i]) & 15) == 0 && (reinterpret_cast<uintptr_t>(Vt[i]) & 15) == 0,
                    "pq3d_attention_fwd: memory %d: K / V^T alignment or leading dimension", i);
     {
@@ -380,7 +381,7 @@ extern "C" int pq3d_attention_fwd(int n_mem, const void* Q, int64_t ldq, int64_t
     }
     {
       uint64_t dims[3] = {(uint64_t)S[i], (uint64_t)B, (uint64_t)vt_rows[i]};
-      uint64_t strides[2] = {(uint64_t)S_pitch[i] * 2, (uint64_t)ldvt[i] * 2};
+      uint64_t strides[2] = {(uint64_t)Vt_pitch[i] * 2, (uint64_t)ldvt[i] * 2};
       uint32_t box[3] = {64u, 1u, (uint32_t)kHeadDim};
       int rc = make_tmap_bf16(&maps.vt[i], Vt[i], 3, dims, strides, box);
       if (rc != PQ3D_OK) return rc;

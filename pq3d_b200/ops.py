@@ -74,13 +74,14 @@ def linear(A: torch.Tensor, W: torch.Tensor, out: torch.Tensor, *, M: int, N: in
 
 class AttnMemory:
     """One memory's projected operands for `attention` (see pq3d_attention_fwd)."""
-    __slots__ = ("K", "k_col0", "Vt", "vt_row0", "S", "S_pitch", "mask_bits", "mask_b_stride", "mask_h_stride",
-                 "mask_q_stride")
+    __slots__ = ("K", "k_col0", "Vt", "vt_row0", "S", "S_pitch", "Vt_pitch", "mask_bits", "mask_b_stride",
+                 "mask_h_stride", "mask_q_stride")
 
     def __init__(self, K, k_col0, Vt, vt_row0, S, S_pitch, mask_bits=None, mask_b_stride=0, mask_h_stride=0,
-                 mask_q_stride=0):
+                 mask_q_stride=0, Vt_pitch=None):
         self.K, self.k_col0, self.Vt, self.vt_row0 = K, k_col0, Vt, vt_row0
         self.S, self.S_pitch = S, S_pitch
+        self.Vt_pitch = S_pitch if Vt_pitch is None else Vt_pitch
         self.mask_bits, self.mask_b_stride = mask_bits, mask_b_stride
         self.mask_h_stride, self.mask_q_stride = mask_h_stride, mask_q_stride
 
@@ -111,6 +112,7 @@ def attention(Q: torch.Tensor, q_mem_stride: int, mems: Sequence[AttnMemory], O:
         vp(*[m.K.data_ptr() for m in mems]), i64(*[m.K.stride(0) for m in mems]), i64(*[m.k_col0 for m in mems]),
         vp(*[m.Vt.data_ptr() for m in mems]), i64(*[m.Vt.stride(0) for m in mems]), i64(*[m.vt_row0 for m in mems]),
         i64(*[m.Vt.shape[0] for m in mems]), i32(*[m.S for m in mems]), i32(*[m.S_pitch for m in mems]),
+        i32(*[m.Vt_pitch for m in mems]),
         vp(*[_p(m.mask_bits) for m in mems]) if has_mask else None,
         i64(*[m.mask_b_stride for m in mems]), i64(*[m.mask_h_stride for m in mems]),
         i64(*[m.mask_q_stride for m in mems]),

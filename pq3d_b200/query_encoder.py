@@ -299,10 +299,10 @@ class QueryMaskEncoder(nn.Module):
             self._ws.clear()
         return self._packed
 
-    def _buf(self, ws: dict, name: str, shape, dtype, device):
+    def _buf(self, ws: dict, name: str, shape, dtype, device, zero: bool = False):
         t = ws.get(name)
         if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype:
-            t = torch.empty(shape, dtype=dtype, device=device)
+            t = (torch.zeros if zero else torch.empty)(shape, dtype=dtype, device=device)
             ws[name] = t
         return t
 
@@ -515,13 +515,14 @@ class QueryMaskEncoder(nn.Module):
         sa = lw["sa"]
         QK = self._buf(ws, "sa_QK", (R, 2 * D), bf16, dev)
         ops.linear(xq, sa["wqk"], QK, M=R, N=2 * D, K=D, bias=sa["bqk"], alpha=0.125, alpha_ncols=D)
+        # V^T [D, B*Np]: scene b's queries at columns b*Np .. b*Np+N (Np = N rounded up to 8 for the TMA
+        # stride); one GEMM group per scene, pad columns stay at their zero initialisation
         Np = ops.pad8(N)
-        if Np != N:
-            raise NotImplementedError("query count must be a multiple of 8 (TMA stride alignment of V^T)")
-        Vt = self._buf(ws, "sa_Vt", (D, B * Np), bf16, dev)
-        ops.linear(sa["wv"], xv_q, Vt, M=D, N=R, K=D, bias=sa["bv"], bias_along_m=True)
+        Vt = self._buf(ws, "sa_Vt", (D, B * Np), bf16, dev, zero=True)
+        ops.linear(sa["wv"], xv_q, Vt, M=D, N=N, K=D, bias=sa["bv"], bias_along_m=True, groups=B, a_group_rows=0,
+                   w_group_rows=N, ldc=B * Np, c_group_stride=Np)
         Os = self._buf(ws, "sa_O", (1, R, D), bf16, dev)
-        mem = ops.AttnMemory(QK, D, Vt, 0, N, Np, qbits, qbits.stride(0), 0, 0)
+        mem = ops.AttnMemory(QK, D, Vt, 0, N, N, qbits, qbits.stride(0), 0, 0, Vt_pitch=Np)
         ops.attention(QK, 0, [mem], Os, R * D, B, H, N, False, pw if sa["loc_w"] is not None else None,
                       sa["loc_w"], sa["loc_b"])
         ys = self._buf(ws, "sa_y", (R, D), torch.float32, dev)
