@@ -29,6 +29,8 @@ extern "C" {
 
 const char* pq3d_last_error(void);
 int pq3d_abi_version(void);
+/* Debug only: per-CTA timeline of pq3d_linear_bf16 (8 x uint64 per CTA) into a device buffer; NULL disables. */
+int pq3d_debug_set_timeline(void* buf);
 
 /* C[g] = epilogue(A[g] · W[g]ᵀ), bf16 operands, fp32 accumulation on tcgen05 tensor cores.
  *   A: [a_rows_total, lda] bf16, group g starts at row g*a_group_rows, uses M rows, K columns

@@ -10,13 +10,15 @@
 // as [feature, token] (the projection GEMM writes V^T directly by swapping its operands), so every
 // MMA operand is K-major and TMA-loadable with the 128-byte swizzle.
 //
-// One CTA = (head, scene, memory, 128-query tile).  192 threads:
+// One CTA = (head, scene, memory, 128-query tile).  576 threads:
 //   warp 0      TMA producer: Q tile once, then K (pass 1) / K + V^T (pass 2) tiles of 128 keys into
 //               a 3-stage ring
 //   warp 1      tcgen05.mma issuer: S = Q K^T (128x128, fp32 in TMEM, double-buffered),
 //               O += P V (128x64 in TMEM); P comes from shared memory (bf16, swizzled K-major)
-//   warps 2..5  softmax, one query row per thread (TMEM lane = row): pass 1 row maxima, pass 2
-//               p = exp2((s - m) log2e), row sums, P tiles; finalize with the analytic zero-attn
+//   warps 2..17 softmax: 16 warps, four per TMEM lane quadrant, each owning one 32-key column chunk
+//               of every 128-key tile for its 32 query rows (TMEM lane = row): pass 1 partial row
+//               maxima, pass 2 p = exp2((s - m) log2e), partial row sums, P tiles; partials are
+//               combined through shared memory once per pass; finalize with the analytic zero-attn
 //               column (score 0, value 0: denominator += exp(-m), m >= 0) and store O as bf16.
 // Two passes over K instead of an online-softmax rescale of O: N <= 128 queries per CTA make the
 // second QK^T cheap on the tensor pipe, and O never needs a TMEM read-modify-write.
@@ -30,7 +32,8 @@
 namespace pq3d {
 
 constexpr int kMaxMem = 4;
-constexpr int kAttnThreads = 192;
+constexpr int kSoftmaxWarps = 16;                       // 4 per TMEM lane quadrant, one 32-key chunk each
+constexpr int kAttnThreads = 64 + 32 * kSoftmaxWarps;
 constexpr int kKvTile = 128;
 constexpr int kKvStages = 3;
 constexpr int kHeadDim = 64;
@@ -66,7 +69,7 @@ constexpr int kQBytes = 128 * kHeadDim * 2;           // 16 KB
 constexpr int kKBytes = kKvTile * kHeadDim * 2;       // 16 KB
 constexpr int kVBytes = kHeadDim * kKvTile * 2;       // 16 KB (two [64 x 64] boxes)
 constexpr int kPBytes = 128 * kKvTile * 2;            // 32 KB (two [128 x 64] swizzle-atom columns)
-constexpr int kAttnSmem = kQBytes + kKvStages * (kKBytes + kVBytes) + 2 * kPBytes + 1024 + 256;
+constexpr int kAttnSmem = kQBytes + kKvStages * (kKBytes + kVBytes) + 2 * kPBytes + 1024 + 256 + 2048 /*row partials*/;
 
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
@@ -91,6 +94,7 @@ attention_fwd_kernel(const __grid_constant__ AttnMaps maps, const AttnParams p) 
   uint64_t* p_empty = p_full + 2;
   uint64_t* o_full = p_empty + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
+  float* s_part = reinterpret_cast<float*>(sP + 2 * kPBytes + 256);   // [4 column chunks][128 rows]
 
   const int warp = threadIdx.x >> 5;
   const int h = blockIdx.x;
@@ -111,8 +115,8 @@ attention_fwd_kernel(const __grid_constant__ AttnMaps maps, const AttnParams p) 
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&s_full[i], 1);
-      mbar_init(&s_empty[i], 4);
-      mbar_init(&p_full[i], 4);
+      mbar_init(&s_empty[i], kSoftmaxWarps);
+      mbar_init(&p_full[i], kSoftmaxWarps);
       mbar_init(&p_empty[i], 1);
     }
     mbar_init(o_full, 1);
@@ -215,16 +219,12 @@ attention_fwd_kernel(const __grid_constant__ AttnMaps maps, const AttnParams p) 
     constexpr float kLog2e = 1.4426950408889634f;
     const float kNegInf = __int_as_float(0xff800000);
 
-    auto mask_words = [&](int t) -> uint4 {
-      if (mrow != nullptr) return __ldg(reinterpret_cast<const uint4*>(mrow) + t);
-      // no mask tensor: only the tail past S is ignored
-      uint4 w;
-      uint32_t* wp = reinterpret_cast<uint32_t*>(&w);
-      for (int c = 0; c < 4; ++c) {
-        const int rem = mem.S - (t * kKvTile + c * 32);
-        wp[c] = rem >= 32 ? 0u : (rem <= 0 ? 0xffffffffu : (0xffffffffu << rem));
-      }
-      return w;
+    // Each of the 4 warps that share a TMEM lane quadrant owns one 32-key column chunk of every tile.
+    const int cc = (warp - 2) >> 2;
+    auto mask_word = [&](int t) -> uint32_t {
+      if (mrow != nullptr) return __ldg(mrow + t * 4 + cc);
+      const int rem = mem.S - (t * kKvTile + cc * 32);       // no mask tensor: only the tail past S is ignored
+      return rem >= 32 ? 0u : (rem <= 0 ? 0xffffffffu : (0xffffffffu << rem));
     };
     auto score = [&](uint32_t raw, int key, uint32_t word, int j) -> float {
       float s = __uint_as_float(raw);
@@ -238,81 +238,76 @@ attention_fwd_kernel(const __grid_constant__ AttnMaps maps, const AttnParams p) 
 
     int g = 0;
     float m_run = kNegInf;
-    for (int t = 0; t < T; ++t, ++g) {  // ---- pass 1: row maxima
+    for (int t = 0; t < T; ++t, ++g) {  // ---- pass 1: row maxima (partial: this warp's columns)
       const int sb = g & 1;
-      const uint4 mw = mask_words(t);
-      const uint32_t* mwp = reinterpret_cast<const uint32_t*>(&mw);
+      const uint32_t word = mask_word(t);
       mbar_wait(&s_full[sb], (g >> 1) & 1, 300 + sb);
       tc_fence_after();
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t acc[32];
-        tmem_ld_32x32(tmem_S0 + sb * kKvTile + lane_off + c * 32, acc);
-        tmem_ld_wait();
-        const uint32_t word = mwp[c];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) m_run = fmaxf(m_run, score(acc[j], t * kKvTile + c * 32 + j, word, j));
-      }
+      uint32_t acc[32];
+      tmem_ld_32x32(tmem_S0 + sb * kKvTile + lane_off + cc * 32, acc);
+      tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane_id() == 0) mbar_arrive(&s_empty[sb]);
+      if (lane_id() == 0) mbar_arrive(&s_empty[sb]);     // values are in registers: release the buffer early
+#pragma unroll
+      for (int j = 0; j < 32; ++j) m_run = fmaxf(m_run, score(acc[j], t * kKvTile + cc * 32 + j, word, j));
     }
+    s_part[cc * 128 + r] = m_run;
+    asm volatile("bar.sync 1, 512;" ::: "memory");
+    m_run = fmaxf(fmaxf(s_part[r], s_part[128 + r]), fmaxf(s_part[256 + r], s_part[384 + r]));
+    asm volatile("bar.sync 1, 512;" ::: "memory");        // s_part is reused for the row sums
     const float m = p.zero_attn ? fmaxf(m_run, 0.f) : m_run;
     const float m_l2 = (m == kNegInf ? 0.f : m) * kLog2e;
     float l = 0.f;
     for (int t = 0; t < T; ++t, ++g) {  // ---- pass 2: probabilities
       const int sb = g & 1;
       const int pb = t & 1;
-      const uint4 mw = mask_words(t);
-      const uint32_t* mwp = reinterpret_cast<const uint32_t*>(&mw);
+      const uint32_t word = mask_word(t);
       mbar_wait(&s_full[sb], (g >> 1) & 1, 310 + sb);
-      mbar_wait(&p_empty[pb], ((t >> 1) & 1) ^ 1, 320 + pb);
       tc_fence_after();
-      uint8_t* prow = sP + pb * kPBytes + r * 128;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t acc[32];
-        tmem_ld_32x32(tmem_S0 + sb * kKvTile + lane_off + c * 32, acc);
-        tmem_ld_wait();
-        const uint32_t word = mwp[c];
-        float pv[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float s = score(acc[j], t * kKvTile + c * 32 + j, word, j);
-          const float e = ex2_approx(fmaf(s, kLog2e, -m_l2));  // ex2(-inf) = 0 for masked keys
-          pv[j] = e;
-          l += e;
-        }
-#pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4) {
-          uint4 u;
-          u.x = pack_bf16x2(pv[q4 * 8 + 0], pv[q4 * 8 + 1]);
-          u.y = pack_bf16x2(pv[q4 * 8 + 2], pv[q4 * 8 + 3]);
-          u.z = pack_bf16x2(pv[q4 * 8 + 4], pv[q4 * 8 + 5]);
-          u.w = pack_bf16x2(pv[q4 * 8 + 6], pv[q4 * 8 + 7]);
-          const int ci = c * 4 + q4;                 // 16-byte chunk index along the 128 keys
-          const int atom = ci >> 3, cc = ci & 7;     // swizzle-atom column, chunk inside its 128-B row
-          *reinterpret_cast<uint4*>(prow + atom * (kPBytes / 2) + ((cc ^ (r & 7)) << 4)) = u;
-        }
-      }
+      uint32_t acc[32];
+      tmem_ld_32x32(tmem_S0 + sb * kKvTile + lane_off + cc * 32, acc);
+      tmem_ld_wait();
       tc_fence_before();
+      __syncwarp();
+      if (lane_id() == 0) mbar_arrive(&s_empty[sb]);
+      float pv[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float s = score(acc[j], t * kKvTile + cc * 32 + j, word, j);
+        const float e = ex2_approx(fmaf(s, kLog2e, -m_l2));  // ex2(-inf) = 0 for masked keys
+        pv[j] = e;
+        l += e;
+      }
+      mbar_wait(&p_empty[pb], ((t >> 1) & 1) ^ 1, 320 + pb);
+      uint8_t* prow = sP + pb * kPBytes + r * 128;
+#pragma unroll
+      for (int q4 = 0; q4 < 4; ++q4) {
+        uint4 u;
+        u.x = pack_bf16x2(pv[q4 * 8 + 0], pv[q4 * 8 + 1]);
+        u.y = pack_bf16x2(pv[q4 * 8 + 2], pv[q4 * 8 + 3]);
+        u.z = pack_bf16x2(pv[q4 * 8 + 4], pv[q4 * 8 + 5]);
+        u.w = pack_bf16x2(pv[q4 * 8 + 6], pv[q4 * 8 + 7]);
+        const int ci = cc * 4 + q4;                // 16-byte chunk index along the 128 keys
+        const int atom = ci >> 3, c8 = ci & 7;     // swizzle-atom column, chunk inside its 128-B row
+        *reinterpret_cast<uint4*>(prow + atom * (kPBytes / 2) + ((c8 ^ (r & 7)) << 4)) = u;
+      }
       fence_proxy_async_smem();
       __syncwarp();
-      if (lane_id() == 0) {
-        mbar_arrive(&s_empty[sb]);
-        mbar_arrive(&p_full[pb]);
-      }
+      if (lane_id() == 0) mbar_arrive(&p_full[pb]);
     }
-    // ---- finalize: zero-attn column, normalise, store
+    // ---- finalize: combine the partial row sums, zero-attn column, normalise, store
+    s_part[cc * 128 + r] = l;
+    asm volatile("bar.sync 1, 512;" ::: "memory");
+    l = (s_part[r] + s_part[128 + r]) + (s_part[256 + r] + s_part[384 + r]);
     if (p.zero_attn) l += ex2_approx(-m_l2);
     const float inv = 1.f / l;
     mbar_wait(o_full, 0, 330);
     tc_fence_after();
-    __nv_bfloat16* orow = p.O + mi * p.o_mem_stride + (static_cast<int64_t>(b) * p.Nq + n_c) * p.ldo + h * kHeadDim;
-#pragma unroll 1
-    for (int c = 0; c < 2; ++c) {
+    if (cc < 2) {                                  // 64 output columns: two of the four warps per quadrant
+      __nv_bfloat16* orow = p.O + mi * p.o_mem_stride + (static_cast<int64_t>(b) * p.Nq + n_c) * p.ldo + h * kHeadDim;
       uint32_t acc[32];
-      tmem_ld_32x32(tmem_O + lane_off + c * 32, acc);
+      tmem_ld_32x32(tmem_O + lane_off + cc * 32, acc);
       tmem_ld_wait();
       if (n < p.Nq) {
 #pragma unroll
@@ -322,7 +317,7 @@ attention_fwd_kernel(const __grid_constant__ AttnMaps maps, const AttnParams p) 
           u.y = pack_bf16x2(__uint_as_float(acc[j + 2]) * inv, __uint_as_float(acc[j + 3]) * inv);
           u.z = pack_bf16x2(__uint_as_float(acc[j + 4]) * inv, __uint_as_float(acc[j + 5]) * inv);
           u.w = pack_bf16x2(__uint_as_float(acc[j + 6]) * inv, __uint_as_float(acc[j + 7]) * inv);
-          *reinterpret_cast<uint4*>(orow + c * 32 + j) = u;
+          *reinterpret_cast<uint4*>(orow + cc * 32 + j) = u;
         }
       }
     }

@@ -6,15 +6,21 @@
 // mask-head projections (modules/heads/mask_head.py:46-57).  The K/V projection is 85 % of the
 // decoder's FLOPs, so this is the dominant kernel.
 //
-// One CTA = one 128 x BN output tile.  Warp roles (192 threads):
+// Persistent: grid = min(#tiles, #SMs); each CTA walks 128 x BN output tiles (n fastest, so CTAs
+// running at the same time share A rows in L2).  Warp roles (192 threads):
 //   warp 0      TMA producer: A tile [128 x 64] and W tile [BN x 64] per k-block, 128B-swizzled,
-//               into a kStages-deep shared-memory ring guarded by full/empty mbarriers
-//   warp 1      TMEM allocation + single-thread tcgen05.mma issue (M=128, N=BN, K=16, bf16 -> fp32
-//               accumulators in TMEM); tcgen05.commit releases ring slots / signals the epilogue
-//   warps 2..5  epilogue: tcgen05.ld the accumulator (lane = row, 32 columns per load), apply
-//               (+bias) * alpha, optional ReLU / row zeroing, convert, 16-byte global stores
-// Groups (blockIdx.z) shift the A / W / C / bias bases: per-memory out-projections, per-layer
-// multi-scale voxel K/V projections and per-scene mask-logit products run as one launch.
+//               into a 192 KB shared-memory ring guarded by full/empty mbarriers; runs ahead across
+//               tile boundaries
+//   warp 1      TMEM allocation + single-thread tcgen05.mma issue (M=128, N=BN, K=16, bf16 -> fp32)
+//               into one of TWO accumulator buffers in TMEM; tcgen05.commit releases ring slots and
+//               publishes the finished accumulator
+//   warps 2..5  epilogue, overlapped with the next tile's main loop: tcgen05.ld (lane = row),
+//               (acc + bias) * alpha, ReLU / row zeroing, convert, stage one [32 rows x 128 B] box
+//               per warp in swizzled shared memory (double-buffered) and TMA-store it; tails in M / N
+//               are clipped by the tensor map.  C whose leading dimension is not 16-byte granular
+//               (the 201-class logits) takes a direct-store path.
+// Groups shift the A / W / C / bias bases: per-memory out-projections, per-layer multi-scale voxel
+// K/V projections, per-scene V^T and mask-logit products run as one launch.
 #include "host_common.h"
 #include "ptx.cuh"
 
@@ -31,167 +37,271 @@ struct LinearParams {
   int32_t a_group_rows;     // row offset of group g in the A tensor map = g * a_group_rows
   int32_t w_group_rows;
   int32_t M, N, K;
+  int32_t num_m, num_n, num_tiles;
   int32_t out_fp32;
   int32_t bias_along_m;
   int32_t relu;
   int32_t alpha_ncols;      // columns n < alpha_ncols are scaled by alpha (n >= : unscaled)
   float alpha;
-  int32_t vec_ok;           // ldc / base alignment allow 16-byte stores
+  int32_t tma_store;        // C is 16-byte granular: epilogue goes through shared memory + TMA store
+  unsigned long long* dbg;  // optional per-CTA timeline (pq3d_debug_set_timeline), 8 slots per CTA
 };
 
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;  // 64 bf16 = 128 B = one swizzle atom row
 constexpr int kGemmThreads = 192;
+constexpr int kBoxBytes = 32 * 128;  // one epilogue box: 32 rows x 128 B
 
 template <int BN>
 struct GemmCfg {
   static constexpr int kABytes = kBlockM * kBlockK * 2;
   static constexpr int kBBytes = BN * kBlockK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);     // 192 KB of operands in flight
+  static constexpr int kRingBytes = kStages * kStageBytes;
+  static constexpr int kStagingBytes = 4 * 2 * kBoxBytes;                    // 4 warps x double buffer
+  static constexpr int kBarBytes = 256;
+  static constexpr int kSmemBytes = kRingBytes + kStagingBytes + kBarBytes + 2 * BN * 4;
+  static constexpr uint32_t kTmemCols = 2 * BN;                              // two accumulator buffers
+  static_assert(kSmemBytes <= 232448, "exceeds the 227 KB shared-memory limit");
 };
 
 template <int BN>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 linear_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
-                   const LinearParams p) {
+                   const __grid_constant__ CUtensorMap tmap_c, const LinearParams p) {
   using Cfg = GemmCfg<BN>;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* staging = smem + Cfg::kRingBytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + Cfg::kStagingBytes);
   uint64_t* empty_bar = full_bar + Cfg::kStages;
-  uint64_t* accum_bar = empty_bar + Cfg::kStages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+  uint64_t* tfull_bar = empty_bar + Cfg::kStages;   // accumulator buffer ready   (MMA -> epilogue)
+  uint64_t* tempty_bar = tfull_bar + 2;             // accumulator buffer drained (epilogue -> MMA)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  float* s_bias = reinterpret_cast<float*>(staging + Cfg::kStagingBytes + Cfg::kBarBytes);
 
   const int warp = threadIdx.x >> 5;
-  const int m0 = blockIdx.y * kBlockM;
-  const int n0 = blockIdx.x * BN;
-  const int g = blockIdx.z;
   const int num_kb = p.K / kBlockK;
+  const int tiles_per_group = p.num_m * p.num_n;
 
+  if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) {
+    printf("pq3d: dynamic shared memory is not 1024-byte aligned\n");
+    __trap();
+  }
   if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_w);
+    if (p.tma_store) tma_prefetch_desc(&tmap_c);
     for (int s = 0; s < Cfg::kStages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(accum_bar, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 4);
+    }
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc<(BN < 32 ? 32 : BN)>(tmem_slot);
+  if (warp == 1) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  unsigned long long* dbg = p.dbg == nullptr ? nullptr : p.dbg + 8ull * blockIdx.x;
+  if (dbg != nullptr && threadIdx.x == 0) {
+    dbg[0] = global_timer_ns();
+    dbg[1] = clock64();
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    dbg[7] = smid;
+  }
 
   if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
     if (elect_one()) {
-      const int a_row = g * p.a_group_rows + m0;
-      const int w_row = g * p.w_group_rows + n0;
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % Cfg::kStages;
-        const uint32_t ph = (kb / Cfg::kStages) & 1;
-        mbar_wait(&empty_bar[s], ph ^ 1, 100 + s);
-        uint8_t* sa = smem + s * Cfg::kStageBytes;
-        mbar_arrive_expect_tx(&full_bar[s], Cfg::kStageBytes);
-        tma_load_2d(sa, &tmap_a, &full_bar[s], kb * kBlockK, a_row);
-        tma_load_2d(sa + Cfg::kABytes, &tmap_w, &full_bar[s], kb * kBlockK, w_row);
+      int it = 0;
+      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+        const int g = t / tiles_per_group, rem = t % tiles_per_group;
+        const int a_row = g * p.a_group_rows + (rem / p.num_n) * kBlockM;
+        const int w_row = g * p.w_group_rows + (rem % p.num_n) * BN;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % Cfg::kStages;
+          mbar_wait(&empty_bar[s], ((it / Cfg::kStages) & 1) ^ 1, 100 + s);
+          uint8_t* sa = smem + s * Cfg::kStageBytes;
+          mbar_arrive_expect_tx(&full_bar[s], Cfg::kStageBytes);
+          tma_load_2d(sa, &tmap_a, &full_bar[s], kb * kBlockK, a_row);
+          tma_load_2d(sa + Cfg::kABytes, &tmap_w, &full_bar[s], kb * kBlockK, w_row);
+        }
       }
     }
   } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
     if (elect_one()) {
       constexpr uint32_t idesc = umma_idesc_bf16(kBlockM, BN);
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % Cfg::kStages;
-        const uint32_t ph = (kb / Cfg::kStages) & 1;
-        mbar_wait(&full_bar[s], ph, 200 + s);
+      int it = 0, lt = 0;
+      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++lt) {
+        const int buf = lt & 1;
+        mbar_wait(&tempty_bar[buf], ((lt >> 1) & 1) ^ 1, 210 + buf);
         tc_fence_after();
-        const uint32_t sa = smem_u32(smem + s * Cfg::kStageBytes);
-        const uint32_t sb = sa + Cfg::kABytes;
+        const uint32_t tmem_acc = tmem_base + buf * BN;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % Cfg::kStages;
+          mbar_wait(&full_bar[s], (it / Cfg::kStages) & 1, 200 + s);
+          tc_fence_after();
+          if (dbg != nullptr && it == 0) dbg[2] = clock64();
+          const uint32_t sa = smem_u32(smem + s * Cfg::kStageBytes);
+          const uint32_t sb = sa + Cfg::kABytes;
 #pragma unroll
-        for (int k = 0; k < kBlockK / 16; ++k) {
-          // advancing 16 bf16 (32 B) along K inside the 128-byte swizzle atom = +32 B on the start address
-          umma_ss(tmem_base, umma_desc_k_sw128(sa + k * 32), umma_desc_k_sw128(sb + k * 32), idesc,
-                  (kb | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < kBlockK / 16; ++k) {
+            // advancing 16 bf16 (32 B) along K inside the 128-byte swizzle atom = +32 B on the start address
+            umma_ss(tmem_acc, umma_desc_k_sw128(sa + k * 32), umma_desc_k_sw128(sb + k * 32), idesc,
+                    (kb | k) != 0 ? 1u : 0u);
+          }
+          tc_commit(&empty_bar[s]);
         }
-        tc_commit(&empty_bar[s]);
+        tc_commit(&tfull_bar[buf]);
       }
-      tc_commit(accum_bar);
+      if (dbg != nullptr) {
+        dbg[3] = clock64();
+        dbg[4] = lt;
+      }
     }
   } else {
-    // epilogue warps 2..5 -> TMEM lane quadrant (warp % 4)
-    const int quad = warp & 3;
-    const int row_in_tile = quad * 32 + lane_id();
-    const int m = m0 + row_in_tile;
-    mbar_wait(accum_bar, 0, 300);
-    tc_fence_after();
-    const bool row_ok = m < p.M;
-    const bool zero_row = row_ok && p.row_zero != nullptr && p.row_zero[g * p.row_zero_group_stride + m] != 0;
-    const float bias_m = (p.bias != nullptr && p.bias_along_m && row_ok) ? p.bias[g * p.bias_group_stride + m] : 0.f;
-    const float* bias_n = (p.bias != nullptr && !p.bias_along_m) ? p.bias + g * p.bias_group_stride : nullptr;
-    uint8_t* c_row = reinterpret_cast<uint8_t*>(p.C) +
-                     (static_cast<int64_t>(g) * p.c_group_stride + static_cast<int64_t>(m) * p.ldc) *
-                         (p.out_fp32 ? 4 : 2);
-#pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      uint32_t acc[32];
-      tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + c0, acc);
-      tmem_ld_wait();
-      const int n_base = n0 + c0;
-      if (!row_ok || n_base >= p.N) continue;
-      float v[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const int n = n_base + j;
-        float x = __uint_as_float(acc[j]);
-        if (bias_n != nullptr && n < p.N) x += __ldg(bias_n + n);
-        x += bias_m;
-        if (n < p.alpha_ncols) x *= p.alpha;
-        if (p.relu) x = fmaxf(x, 0.f);
-        v[j] = zero_row ? 0.f : x;
+    // ------------------------------------------------------------------ epilogue warps 2..5
+    const int quad = warp & 3;   // TMEM lane quadrant this warp may access
+    const int r = lane_id();
+    uint8_t* stage = staging + (warp - 2) * 2 * kBoxBytes;
+    int lt = 0, bx = 0;
+    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++lt) {
+      const int g = t / tiles_per_group, rem = t % tiles_per_group;
+      const int m0 = (rem / p.num_n) * kBlockM, n0 = (rem % p.num_n) * BN;
+      const int buf = lt & 1;
+      float* bias_s = s_bias + buf * BN;
+      for (int c = threadIdx.x - 64; c < BN; c += 128) {
+        const int n = n0 + c;
+        bias_s[c] = (p.bias != nullptr && !p.bias_along_m && n < p.N) ? p.bias[g * p.bias_group_stride + n] : 0.f;
       }
-      const bool full = n_base + 32 <= p.N;
-      if (p.out_fp32) {
-        float* dst = reinterpret_cast<float*>(c_row) + n_base;
-        if (full && p.vec_ok) {
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const int m = m0 + quad * 32 + r;
+      const bool row_ok = m < p.M;
+      const bool zero_row = row_ok && p.row_zero != nullptr && p.row_zero[g * p.row_zero_group_stride + m] != 0;
+      const float bias_m = (p.bias != nullptr && p.bias_along_m && row_ok) ? p.bias[g * p.bias_group_stride + m] : 0.f;
+      const float lo = p.relu ? 0.f : __int_as_float(0xff800000);
+      mbar_wait(&tfull_bar[buf], (lt >> 1) & 1, 300 + buf);
+      tc_fence_after();
+      const uint32_t tmem_row = tmem_base + buf * BN + (static_cast<uint32_t>(quad * 32) << 16);
+
+      // 32 accumulator columns [c0, c0+32) of this thread's row -> finished fp32 values
+      auto load_chunk = [&](int c0, float (&v)[32]) {
+        uint32_t acc[32];
+        tmem_ld_32x32(tmem_row + c0, acc);
+        tmem_ld_wait();
+        const bool uniform = (n0 + c0 + 32 <= p.alpha_ncols) || (n0 + c0 >= p.alpha_ncols);
+        const float sc = (n0 + c0 < p.alpha_ncols) ? p.alpha : 1.f;
 #pragma unroll
-          for (int j = 0; j < 32; j += 4)
-            *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-        } else {
-          for (int j = 0; j < 32; ++j)
-            if (n_base + j < p.N) dst[j] = v[j];
+        for (int j = 0; j < 32; j += 4) {
+          const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c0 + j);
+          const float bj[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            float x = __uint_as_float(acc[j + q]) + bj[q] + bias_m;
+            x *= uniform ? sc : ((n0 + c0 + j + q < p.alpha_ncols) ? p.alpha : 1.f);
+            x = fmaxf(x, lo);
+            v[j + q] = zero_row ? 0.f : x;
+          }
+        }
+      };
+      auto release_accumulator = [&]() {
+        tc_fence_before();
+        __syncwarp();
+        if (r == 0) mbar_arrive(&tempty_bar[buf]);
+      };
+      auto claim_box = [&]() -> uint8_t* {   // double-buffered staging: wait until the box used 2 stores ago was read
+        if (bx >= 2 && r == 0) tma_store_wait_read<1>();
+        __syncwarp();
+        return stage + (bx++ & 1) * kBoxBytes;
+      };
+      auto store_box = [&](uint8_t* box, int c0) {
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (r == 0) {
+          tma_store_3d(&tmap_c, box, n0 + c0, m0 + quad * 32, g);
+          tma_store_commit();
+        }
+      };
+
+      if (p.tma_store && p.out_fp32) {
+        const int n_boxes = min(BN, p.N - n0 + 31) / 32;            // one box = 32 fp32 columns
+        for (int b = 0; b < n_boxes; ++b) {
+          float v[32];
+          load_chunk(b * 32, v);
+          if (b == n_boxes - 1) release_accumulator();
+          uint8_t* box = claim_box() + r * 128;
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<float4*>(box + ((j ^ (r & 7)) << 4)) =
+                make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          store_box(box - r * 128, b * 32);
+        }
+      } else if (p.tma_store) {
+        const int n_boxes = min(BN, p.N - n0 + 63) / 64;            // one box = 64 bf16 columns = two TMEM loads
+        for (int b = 0; b < n_boxes; ++b) {
+          float v0[32], v1[32];
+          load_chunk(b * 64, v0);
+          load_chunk(b * 64 + 32, v1);
+          if (b == n_boxes - 1) release_accumulator();
+          uint8_t* box = claim_box() + r * 128;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint4 u;
+            u.x = pack_bf16x2(v0[8 * j + 0], v0[8 * j + 1]);
+            u.y = pack_bf16x2(v0[8 * j + 2], v0[8 * j + 3]);
+            u.z = pack_bf16x2(v0[8 * j + 4], v0[8 * j + 5]);
+            u.w = pack_bf16x2(v0[8 * j + 6], v0[8 * j + 7]);
+            *reinterpret_cast<uint4*>(box + ((j ^ (r & 7)) << 4)) = u;
+            u.x = pack_bf16x2(v1[8 * j + 0], v1[8 * j + 1]);
+            u.y = pack_bf16x2(v1[8 * j + 2], v1[8 * j + 3]);
+            u.z = pack_bf16x2(v1[8 * j + 4], v1[8 * j + 5]);
+            u.w = pack_bf16x2(v1[8 * j + 6], v1[8 * j + 7]);
+            *reinterpret_cast<uint4*>(box + (((4 + j) ^ (r & 7)) << 4)) = u;
+          }
+          store_box(box - r * 128, b * 64);
         }
       } else {
-        __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(c_row) + n_base;
-        if (full && p.vec_ok) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            uint4 u;
-            u.x = pack_bf16x2(v[j], v[j + 1]);
-            u.y = pack_bf16x2(v[j + 2], v[j + 3]);
-            u.z = pack_bf16x2(v[j + 4], v[j + 5]);
-            u.w = pack_bf16x2(v[j + 6], v[j + 7]);
-            *reinterpret_cast<uint4*>(dst + j) = u;
+        // Unaligned C (leading dimension not 16-byte granular): direct stores.
+        uint8_t* c_row = reinterpret_cast<uint8_t*>(p.C) +
+                         (static_cast<int64_t>(g) * p.c_group_stride + static_cast<int64_t>(m) * p.ldc) *
+                             (p.out_fp32 ? 4 : 2);
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          if (n0 + c0 >= p.N) break;
+          float v[32];
+          load_chunk(c0, v);
+          if (!row_ok) continue;
+          for (int j = 0; j < 32; ++j) {
+            const int n = n0 + c0 + j;
+            if (n >= p.N) break;
+            if (p.out_fp32) reinterpret_cast<float*>(c_row)[n] = v[j];
+            else reinterpret_cast<__nv_bfloat16*>(c_row)[n] = __float2bfloat16_rn(v[j]);
           }
-        } else {
-          for (int j = 0; j < 32; ++j)
-            if (n_base + j < p.N) dst[j] = __float2bfloat16_rn(v[j]);
         }
+        release_accumulator();
       }
     }
+    if (r == 0) tma_store_wait_all();   // outstanding bulk stores must finish reading smem before exit
+    __syncwarp();
     tc_fence_before();
+    if (dbg != nullptr && threadIdx.x == 64) dbg[5] = clock64();
   }
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<(BN < 32 ? 32 : BN)>(tmem_base);
+    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
   }
+  if (dbg != nullptr && threadIdx.x == 0) dbg[6] = clock64();
 }
 
 template <int BN>
-static int launch_linear(const CUtensorMap& ta, const CUtensorMap& tw, const LinearParams& p, int groups,
+static int launch_linear(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& tc, const LinearParams& p,
                          cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
   static bool configured = false;
@@ -200,8 +310,8 @@ static int launch_linear(const CUtensorMap& ta, const CUtensorMap& tw, const Lin
                                    Cfg::kSmemBytes));
     configured = true;
   }
-  dim3 grid((p.N + BN - 1) / BN, (p.M + kBlockM - 1) / kBlockM, groups);
-  linear_bf16_kernel<BN><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tw, p);
+  const int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
+  linear_bf16_kernel<BN><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tw, tc, p);
   PQ3D_CUDA(cudaGetLastError());
   return PQ3D_OK;
 }
@@ -209,6 +319,14 @@ static int launch_linear(const CUtensorMap& ta, const CUtensorMap& tw, const Lin
 }  // namespace pq3d
 
 using namespace pq3d;
+
+static unsigned long long* g_timeline = nullptr;
+// Debug only: when set, every linear_bf16 CTA records {globaltimer at start, clock at start, first operands
+// landed, last MMA issued, #tiles, epilogue done, exit, smid} into buf[8 * blockIdx.x].
+extern "C" int pq3d_debug_set_timeline(void* buf) {
+  g_timeline = reinterpret_cast<unsigned long long*>(buf);
+  return PQ3D_OK;
+}
 
 extern "C" int pq3d_linear_bf16(const void* A, int64_t lda, int64_t a_rows_total, int64_t a_group_rows,
                                 const void* W, int64_t ldw, int64_t w_rows_total, int64_t w_group_rows, void* C,
@@ -229,10 +347,10 @@ extern "C" int pq3d_linear_bf16(const void* A, int64_t lda, int64_t a_rows_total
                      w_rows_total >= (int64_t)(groups - 1) * w_group_rows + N,
                  "pq3d_linear_bf16: group offsets exceed the operand extents");
   if (block_n == 0) {
-    // skinny problems (few CTAs): narrow tiles for parallelism; big ones: 128x256 tiles
+    // big problems: 128x256 tiles; fewer than a wave of those: narrower tiles for parallelism
     const int64_t tiles256 = (int64_t)((M + 127) / 128) * ((N + 255) / 256) * groups;
     const int64_t tiles128 = (int64_t)((M + 127) / 128) * ((N + 127) / 128) * groups;
-    block_n = tiles256 >= 2 * sm_count() ? 256 : (tiles128 >= sm_count() ? 128 : 64);
+    block_n = tiles256 >= sm_count() ? 256 : (tiles128 >= sm_count() ? 128 : 64);
   }
   PQ3D_CHECK_ARG(block_n == 64 || block_n == 128 || block_n == 256, "pq3d_linear_bf16: block_n=%d not in {64,128,256}",
                  block_n);
@@ -265,18 +383,32 @@ extern "C" int pq3d_linear_bf16(const void* A, int64_t lda, int64_t a_rows_total
   p.M = M;
   p.N = N;
   p.K = K;
+  p.num_m = (M + kBlockM - 1) / kBlockM;
+  p.num_n = (N + block_n - 1) / block_n;
+  p.num_tiles = p.num_m * p.num_n * groups;
   p.out_fp32 = out_fp32;
   p.bias_along_m = bias_along_m;
   p.relu = relu;
   p.alpha_ncols = alpha_ncols;
   p.alpha = alpha;
+  p.dbg = g_timeline;
   const int esz = out_fp32 ? 4 : 2;
-  p.vec_ok = ((reinterpret_cast<uintptr_t>(C) & 15) == 0) && ((ldc * esz) % 16 == 0) &&
-             ((c_group_stride * esz) % 16 == 0);
+  p.tma_store = ((reinterpret_cast<uintptr_t>(C) & 15) == 0) && ((ldc * esz) % 16 == 0) &&
+                ((c_group_stride * esz) % 16 == 0);
+  CUtensorMap tc = ta;   // placeholder when the direct-store path is taken
+  if (p.tma_store) {
+    // {N, M, groups}: tails in N and M are clipped by TMA, a tile never spills into the next group
+    uint64_t dims[3] = {(uint64_t)N, (uint64_t)M, (uint64_t)groups};
+    uint64_t gs = groups > 1 ? (uint64_t)c_group_stride * esz : (uint64_t)ldc * esz * (uint64_t)M;
+    uint64_t strides[2] = {(uint64_t)ldc * esz, gs};
+    uint32_t box[3] = {(uint32_t)(128 / esz), 32u, 1u};
+    int rc = make_tmap(&tc, C, esz, 3, dims, strides, box);
+    if (rc != PQ3D_OK) return rc;
+  }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   switch (block_n) {
-    case 64: return launch_linear<64>(ta, tw, p, groups, st);
-    case 128: return launch_linear<128>(ta, tw, p, groups, st);
-    default: return launch_linear<256>(ta, tw, p, groups, st);
+    case 64: return launch_linear<64>(ta, tw, tc, p, st);
+    case 128: return launch_linear<128>(ta, tw, tc, p, st);
+    default: return launch_linear<256>(ta, tw, tc, p, st);
   }
 }

@@ -34,8 +34,12 @@ const char* last_error();
 
 // bf16 tensor map, 128-byte swizzle, zero OOB fill.  dims/strides innermost-first; strides in BYTES
 // for dims 1..rank-1 (dim 0 is contiguous).  Returns PQ3D_OK or an error code.
-int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                   const uint32_t* box);
+int make_tmap(CUtensorMap* out, const void* base, int elem_bytes /*2 = bf16, 4 = fp32*/, int rank,
+              const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box);
+inline int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                          const uint64_t* strides_bytes, const uint32_t* box) {
+  return make_tmap(out, base, 2, rank, dims, strides_bytes, box);
+}
 
 inline int sm_count() {
   static int n = 0;
