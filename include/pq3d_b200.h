@@ -31,6 +31,7 @@ const char* pq3d_last_error(void);
 int pq3d_abi_version(void);
 /* Debug only: per-CTA timeline of pq3d_linear_bf16 (8 x uint64 per CTA) into a device buffer; NULL disables. */
 int pq3d_debug_set_timeline(void* buf);
+int pq3d_debug_set_attention_timeline(void* buf);
 
 /* C[g] = epilogue(A[g] · W[g]ᵀ), bf16 operands, fp32 accumulation on tcgen05 tensor cores.
  *   A: [a_rows_total, lda] bf16, group g starts at row g*a_group_rows, uses M rows, K columns
@@ -62,9 +63,9 @@ int pq3d_linear_bf16(const void* A, int64_t lda, int64_t a_rows_total, int64_t a
  *   O : bf16, element (i, b, n, h*64+d) at O[i*o_mem_stride + (b*Nq+n)*ldo + h*64 + d]
  *   zero_attn: nn.MultiheadAttention(add_zero_attn=True) — one extra never-masked key with score 0
  *              and value 0 (torch/nn/functional.py:6585-6602), handled analytically
- *   pairwise_locs [B,Nq,Nq,5] fp32 + loc_w [H,5] + loc_b [H] (or all NULL): adds
- *              log(max(relu(loc·w_h + b_h), 1e-6)) to the scores — MultiHeadAttentionSpatial 'mul'
- *              (modules/layers/transformers.py:196-199,231-233); requires S == Nq.
+ *   score_bias (or NULL): fp32 [B,H,Nq,bias_ld] added to the scores before masking, rows padded to a
+ *              multiple of 128 keys — the spatial term of MultiHeadAttentionSpatial 'mul'
+ *              (modules/layers/transformers.py:231-233), produced by pq3d_spatial_bias.
  * Replaces torch/nn/functional.py:6630-6647 as called from CrossAttentionLayer.forward_post
  * (modules/grounding/query_encoder.py:297-303) and modules/layers/transformers.py:193-237. */
 int pq3d_attention_fwd(int n_mem, const void* Q, int64_t ldq, int64_t q_mem_stride,
@@ -74,7 +75,13 @@ int pq3d_attention_fwd(int n_mem, const void* Q, int64_t ldq, int64_t q_mem_stri
                        const uint32_t* const* mask_bits, const int64_t* mask_b_stride,
                        const int64_t* mask_h_stride, const int64_t* mask_q_stride,
                        void* O, int64_t ldo, int64_t o_mem_stride, int B, int H, int Nq, int zero_attn,
-                       const float* pairwise_locs, const float* loc_w, const float* loc_b, void* stream);
+                       const float* score_bias, int64_t bias_ld, void* stream);
+
+/* Score bias of MultiHeadAttentionSpatial 'mul' for L layers at once:
+ * out[l,b,h,n,m] = log(max(relu(pairwise_locs[b,n,m,:] · loc_w[l,h,:] + loc_b[l,h]), 1e-6)), rows padded to ld
+ * (pad columns are left untouched).  Replaces modules/layers/transformers.py:196-199,231-232. */
+int pq3d_spatial_bias(const float* pairwise_locs, const float* loc_w, const float* loc_b, float* out, int L, int B,
+                      int H, int N, int64_t ld, void* stream);
 
 /* xv = bf16(feat), xk = bf16(feat + pos) with rows padded to S_pitch (zero-filled); pos may be NULL
  * (then xk = xv values), either output may be NULL.  feat/pos: fp32 [B,S,D].

@@ -2,17 +2,17 @@
 //
 // Replaces the core of nn.MultiheadAttention(add_zero_attn=True) inside CrossAttentionLayer
 // (modules/grounding/query_encoder.py:288-307 -> torch/nn/functional.py:6585-6647: zero key/value
-// appended after projection, float -inf mask, baddbmm, softmax, bmm) and, with the spatial-bias
-// option, MultiHeadAttentionSpatial fusion 'mul' (modules/layers/transformers.py:189-240:
-// softmax(log(clamp(relu(W5 . pairwise_locs + b), 1e-6)) + q.k/sqrt(dh))).
+// appended after projection, float -inf mask, baddbmm, softmax, bmm) and, with an additive score
+// bias, MultiHeadAttentionSpatial fusion 'mul' (modules/layers/transformers.py:189-240:
+// softmax(log(clamp(relu(W5 . pairwise_locs + b), 1e-6)) + q.k/sqrt(dh)); the bias tensor comes from
+// pq3d_spatial_bias).
 //
 // Inputs are already projected: Q (pre-scaled by 1/sqrt(dh)), K as [token, feature] and V TRANSPOSED
 // as [feature, token] (the projection GEMM writes V^T directly by swapping its operands), so every
 // MMA operand is K-major and TMA-loadable with the 128-byte swizzle.
 //
 // One CTA = (head, scene, memory, 128-query tile).  576 threads:
-//   warp 0      TMA producer: Q tile once, then K (pass 1) / K + V^T (pass 2) tiles of 128 keys into
-//               a 3-stage ring
+//   warp 0      TMA producer: Q tile once, then K / K + V^T tiles of 128 keys into a 3-stage ring
 //   warp 1      tcgen05.mma issuer: S = Q K^T (128x128, fp32 in TMEM, double-buffered),
 //               O += P V (128x64 in TMEM); P comes from shared memory (bf16, swizzled K-major)
 //   warps 2..17 softmax: 16 warps, four per TMEM lane quadrant, each owning one 32-key column chunk
@@ -21,9 +21,11 @@
 //               combined through shared memory once per pass; finalize with the analytic zero-attn
 //               column (score 0, value 0: denominator += exp(-m), m >= 0) and store O as bf16.
 // Two passes over K instead of an online-softmax rescale of O: N <= 128 queries per CTA make the
-// second QK^T cheap on the tensor pipe, and O never needs a TMEM read-modify-write.
-// Masks arrive bit-packed (1 = ignore), 128 keys = one uint4 per row per tile; key-padding masks
-// broadcast over rows with a zero row stride.  Bits past S are set by the packer.
+// second QK^T cheap on the tensor pipe, and O never needs a TMEM read-modify-write.  Memories of at
+// most 256 keys (the language prompt, the query self-attention) keep both score tiles resident in
+// TMEM, so their QK^T runs once and pass 2 re-reads it.
+// Masks arrive bit-packed (1 = ignore), one word per 32 keys; key-padding masks broadcast over rows
+// with a zero row stride.  Bits past S are set by the packer.
 #include <cstring>
 
 #include "host_common.h"
@@ -60,16 +62,16 @@ struct AttnParams {
   int32_t q_mem_stride;
   int32_t B, H, Nq, q_tiles;
   int32_t zero_attn;
-  const float* pairwise_locs;  // [B, Nq, Nq, 5] or null
-  const float* loc_w;          // [H, 5]
-  const float* loc_b;          // [H]
+  const float* score_bias;     // [B, H, Nq, bias_ld] fp32 added to the scores, or null
+  int64_t bias_ld;
+  unsigned long long* dbg;
 };
 
 constexpr int kQBytes = 128 * kHeadDim * 2;           // 16 KB
 constexpr int kKBytes = kKvTile * kHeadDim * 2;       // 16 KB
 constexpr int kVBytes = kHeadDim * kKvTile * 2;       // 16 KB (two [64 x 64] boxes)
 constexpr int kPBytes = 128 * kKvTile * 2;            // 32 KB (two [128 x 64] swizzle-atom columns)
-constexpr int kAttnSmem = kQBytes + kKvStages * (kKBytes + kVBytes) + 2 * kPBytes + 1024 + 256 + 2048 /*row partials*/;
+constexpr int kAttnSmem = kQBytes + kKvStages * (kKBytes + kVBytes) + 2 * kPBytes + 256 + 2048 /*row partials*/;
 
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
@@ -79,8 +81,7 @@ __device__ __forceinline__ float ex2_approx(float x) {
 
 __global__ void __launch_bounds__(kAttnThreads, 1)
 attention_fwd_kernel(const __grid_constant__ AttnMaps maps, const AttnParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sQ = smem;
   uint8_t* sKV = sQ + kQBytes;
   uint8_t* sP = sKV + kKvStages * (kKBytes + kVBytes);
@@ -103,7 +104,12 @@ attention_fwd_kernel(const __grid_constant__ AttnMaps maps, const AttnParams p) 
   const int qt = blockIdx.z % p.q_tiles;
   const AttnMem& mem = p.mem[mi];
   const int T = (mem.S + kKvTile - 1) / kKvTile;
+  const bool resident = T <= 2;   // all score tiles fit the two TMEM buffers: one QK^T pass
 
+  if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) {
+    printf("pq3d: dynamic shared memory is not 1024-byte aligned\n");
+    __trap();
+  }
   if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&maps.q);
     tma_prefetch_desc(&maps.k[mi]);
@@ -129,6 +135,13 @@ attention_fwd_kernel(const __grid_constant__ AttnMaps maps, const AttnParams p) 
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_S0 = tmem_base;        // columns [0,128) and [128,256): S double buffer
   const uint32_t tmem_O = tmem_base + 256;   // columns [256,320): O
+  pdl_sync();
+  unsigned long long* dbg =
+      p.dbg == nullptr ? nullptr : p.dbg + 8ull * (blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z));
+  if (dbg != nullptr && threadIdx.x == 64) {
+    dbg[0] = global_timer_ns();
+    dbg[1] = clock64();
+  }
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -136,7 +149,7 @@ attention_fwd_kernel(const __grid_constant__ AttnMaps maps, const AttnParams p) 
       mbar_arrive_expect_tx(q_full, kQBytes);
       tma_load_3d(sQ, &maps.q, q_full, mi * p.q_mem_stride + h * kHeadDim, qt * 128, b);
       int it = 0;
-      for (int pass = 0; pass < 2; ++pass) {
+      for (int pass = resident ? 1 : 0; pass < 2; ++pass) {
         for (int t = 0; t < T; ++t, ++it) {
           const int s = it % kKvStages;
           mbar_wait(&kv_empty[s], ((it / kKvStages) & 1) ^ 1, 100 + s);
@@ -162,7 +175,7 @@ attention_fwd_kernel(const __grid_constant__ AttnMaps maps, const AttnParams p) 
         const int s = it % kKvStages;
         mbar_wait(&kv_full[s], (it / kKvStages) & 1, 200 + s);
         const int sb = g & 1;
-        mbar_wait(&s_empty[sb], ((g >> 1) & 1) ^ 1, 210 + sb);
+        if (!resident) mbar_wait(&s_empty[sb], ((g >> 1) & 1) ^ 1, 210 + sb);
         tc_fence_after();
         const uint32_t k_addr = smem_u32(sKV + s * (kKBytes + kVBytes));
 #pragma unroll
@@ -174,16 +187,11 @@ attention_fwd_kernel(const __grid_constant__ AttnMaps maps, const AttnParams p) 
         ++it;
         ++g;
       };
-      mbar_wait(q_full, 0, 220);
-      for (int t = 0; t < T; ++t) issue_s(true);  // pass 1: scores only
-      const int it2 = it;                         // ring position of pass-2 tile 0
-      issue_s(false);
-      for (int t = 0; t < T; ++t) {
-        if (t + 1 < T) issue_s(false);
+      auto issue_pv = [&](int t, int ring_pos) {
         const int pb = t & 1;
         mbar_wait(&p_full[pb], (t >> 1) & 1, 230 + pb);
         tc_fence_after();
-        const int s = (it2 + t) % kKvStages;
+        const int s = ring_pos % kKvStages;
         const uint32_t v_addr = smem_u32(sKV + s * (kKBytes + kVBytes) + kKBytes);
         const uint32_t p_addr = smem_u32(sP + pb * kPBytes);
 #pragma unroll
@@ -195,12 +203,26 @@ attention_fwd_kernel(const __grid_constant__ AttnMaps maps, const AttnParams p) 
         }
         tc_commit(&kv_empty[s]);
         tc_commit(&p_empty[pb]);
+      };
+      mbar_wait(q_full, 0, 220);
+      if (resident) {
+        for (int t = 0; t < T; ++t) issue_s(false);           // scores once, both tiles stay in TMEM
+        for (int t = 0; t < T; ++t) issue_pv(t, t);
+      } else {
+        for (int t = 0; t < T; ++t) issue_s(true);            // pass 1: scores only
+        const int it2 = it;                                   // ring position of pass-2 tile 0
+        issue_s(false);
+        for (int t = 0; t < T; ++t) {
+          if (t + 1 < T) issue_s(false);
+          issue_pv(t, it2 + t);
+        }
       }
       tc_commit(o_full);
     }
   } else {
     // ------------------------------------------------------------------ softmax warps
     const int quad = warp & 3;
+    const int cc = (warp - 2) >> 2;               // which 32-key chunk of every tile this warp owns
     const int r = quad * 32 + lane_id();          // row in the query tile == TMEM lane
     const int n = qt * 128 + r;                   // query index in the scene
     const int n_c = n < p.Nq ? n : p.Nq - 1;      // clamped for reads
@@ -208,32 +230,37 @@ attention_fwd_kernel(const __grid_constant__ AttnMaps maps, const AttnParams p) 
     const uint32_t* mrow = mem.mask_bits == nullptr
                                ? nullptr
                                : mem.mask_bits + b * mem.mask_b_stride + h * mem.mask_h_stride + n_c * mem.mask_q_stride;
-    const bool spatial = p.pairwise_locs != nullptr;
-    float lw0 = 0, lw1 = 0, lw2 = 0, lw3 = 0, lw4 = 0, lb = 0;
-    const float* loc_row = nullptr;
-    if (spatial) {
-      lw0 = p.loc_w[h * 5 + 0]; lw1 = p.loc_w[h * 5 + 1]; lw2 = p.loc_w[h * 5 + 2];
-      lw3 = p.loc_w[h * 5 + 3]; lw4 = p.loc_w[h * 5 + 4]; lb = p.loc_b[h];
-      loc_row = p.pairwise_locs + (static_cast<int64_t>(b) * p.Nq + n_c) * p.Nq * 5;
-    }
+    const float* brow = p.score_bias == nullptr
+                            ? nullptr
+                            : p.score_bias + ((static_cast<int64_t>(b) * p.H + h) * p.Nq + n_c) * p.bias_ld;
     constexpr float kLog2e = 1.4426950408889634f;
     const float kNegInf = __int_as_float(0xff800000);
 
-    // Each of the 4 warps that share a TMEM lane quadrant owns one 32-key column chunk of every tile.
-    const int cc = (warp - 2) >> 2;
     auto mask_word = [&](int t) -> uint32_t {
       if (mrow != nullptr) return __ldg(mrow + t * 4 + cc);
       const int rem = mem.S - (t * kKvTile + cc * 32);       // no mask tensor: only the tail past S is ignored
       return rem >= 32 ? 0u : (rem <= 0 ? 0xffffffffu : (0xffffffffu << rem));
     };
-    auto score = [&](uint32_t raw, int key, uint32_t word, int j) -> float {
-      float s = __uint_as_float(raw);
-      if (spatial && key < mem.S) {
-        const float* l5 = loc_row + key * 5;
-        float v = fmaf(l5[0], lw0, fmaf(l5[1], lw1, fmaf(l5[2], lw2, fmaf(l5[3], lw3, fmaf(l5[4], lw4, lb)))));
-        s += __logf(fmaxf(fmaxf(v, 0.f), 1e-6f));
+    // this warp's 32 scores of tile t (buffer sb): TMEM -> registers, + bias, masked -> -inf
+    auto load_scores = [&](int t, int sb, uint32_t word, float (&sc)[32]) {
+      uint32_t acc[32];
+      tmem_ld_32x32(tmem_S0 + sb * kKvTile + lane_off + cc * 32, acc);
+      if (brow != nullptr) {
+        const float4* b4 = reinterpret_cast<const float4*>(brow + t * kKvTile + cc * 32);
+        float bias[32];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 v = __ldg(b4 + j);
+          bias[4 * j] = v.x; bias[4 * j + 1] = v.y; bias[4 * j + 2] = v.z; bias[4 * j + 3] = v.w;
+        }
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) sc[j] = ((word >> j) & 1u) ? kNegInf : __uint_as_float(acc[j]) + bias[j];
+      } else {
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) sc[j] = ((word >> j) & 1u) ? kNegInf : __uint_as_float(acc[j]);
       }
-      return ((word >> j) & 1u) ? kNegInf : s;
     };
 
     int g = 0;
@@ -243,51 +270,54 @@ attention_fwd_kernel(const __grid_constant__ AttnMaps maps, const AttnParams p) 
       const uint32_t word = mask_word(t);
       mbar_wait(&s_full[sb], (g >> 1) & 1, 300 + sb);
       tc_fence_after();
-      uint32_t acc[32];
-      tmem_ld_32x32(tmem_S0 + sb * kKvTile + lane_off + cc * 32, acc);
-      tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane_id() == 0) mbar_arrive(&s_empty[sb]);     // values are in registers: release the buffer early
+      float sc[32];
+      load_scores(t, sb, word, sc);
+      if (!resident) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane_id() == 0) mbar_arrive(&s_empty[sb]);     // values are in registers: release the buffer early
+      }
 #pragma unroll
-      for (int j = 0; j < 32; ++j) m_run = fmaxf(m_run, score(acc[j], t * kKvTile + cc * 32 + j, word, j));
+      for (int j = 0; j < 32; ++j) m_run = fmaxf(m_run, sc[j]);
     }
     s_part[cc * 128 + r] = m_run;
     asm volatile("bar.sync 1, 512;" ::: "memory");
     m_run = fmaxf(fmaxf(s_part[r], s_part[128 + r]), fmaxf(s_part[256 + r], s_part[384 + r]));
     asm volatile("bar.sync 1, 512;" ::: "memory");        // s_part is reused for the row sums
+    if (dbg != nullptr && threadIdx.x == 64) dbg[2] = clock64();
     const float m = p.zero_attn ? fmaxf(m_run, 0.f) : m_run;
     const float m_l2 = (m == kNegInf ? 0.f : m) * kLog2e;
     float l = 0.f;
+    if (resident) g = 0;                 // pass 2 re-reads the resident score tiles
     for (int t = 0; t < T; ++t, ++g) {  // ---- pass 2: probabilities
       const int sb = g & 1;
       const int pb = t & 1;
       const uint32_t word = mask_word(t);
-      mbar_wait(&s_full[sb], (g >> 1) & 1, 310 + sb);
-      tc_fence_after();
-      uint32_t acc[32];
-      tmem_ld_32x32(tmem_S0 + sb * kKvTile + lane_off + cc * 32, acc);
-      tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane_id() == 0) mbar_arrive(&s_empty[sb]);
-      float pv[32];
+      if (!resident) {
+        mbar_wait(&s_full[sb], (g >> 1) & 1, 310 + sb);
+        tc_fence_after();
+      }
+      float sc[32];
+      load_scores(t, sb, word, sc);
+      if (!resident) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane_id() == 0) mbar_arrive(&s_empty[sb]);
+      }
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
-        const float s = score(acc[j], t * kKvTile + cc * 32 + j, word, j);
-        const float e = ex2_approx(fmaf(s, kLog2e, -m_l2));  // ex2(-inf) = 0 for masked keys
-        pv[j] = e;
-        l += e;
+        sc[j] = ex2_approx(fmaf(sc[j], kLog2e, -m_l2));    // ex2(-inf) = 0 for masked keys
+        l += sc[j];
       }
       mbar_wait(&p_empty[pb], ((t >> 1) & 1) ^ 1, 320 + pb);
       uint8_t* prow = sP + pb * kPBytes + r * 128;
 #pragma unroll
       for (int q4 = 0; q4 < 4; ++q4) {
         uint4 u;
-        u.x = pack_bf16x2(pv[q4 * 8 + 0], pv[q4 * 8 + 1]);
-        u.y = pack_bf16x2(pv[q4 * 8 + 2], pv[q4 * 8 + 3]);
-        u.z = pack_bf16x2(pv[q4 * 8 + 4], pv[q4 * 8 + 5]);
-        u.w = pack_bf16x2(pv[q4 * 8 + 6], pv[q4 * 8 + 7]);
+        u.x = pack_bf16x2(sc[q4 * 8 + 0], sc[q4 * 8 + 1]);
+        u.y = pack_bf16x2(sc[q4 * 8 + 2], sc[q4 * 8 + 3]);
+        u.z = pack_bf16x2(sc[q4 * 8 + 4], sc[q4 * 8 + 5]);
+        u.w = pack_bf16x2(sc[q4 * 8 + 6], sc[q4 * 8 + 7]);
         const int ci = cc * 4 + q4;                // 16-byte chunk index along the 128 keys
         const int atom = ci >> 3, c8 = ci & 7;     // swizzle-atom column, chunk inside its 128-B row
         *reinterpret_cast<uint4*>(prow + atom * (kPBytes / 2) + ((c8 ^ (r & 7)) << 4)) = u;
@@ -296,6 +326,7 @@ attention_fwd_kernel(const __grid_constant__ AttnMaps maps, const AttnParams p) 
       __syncwarp();
       if (lane_id() == 0) mbar_arrive(&p_full[pb]);
     }
+    if (dbg != nullptr && threadIdx.x == 64) dbg[3] = clock64();
     // ---- finalize: combine the partial row sums, zero-attn column, normalise, store
     s_part[cc * 128 + r] = l;
     asm volatile("bar.sync 1, 512;" ::: "memory");
@@ -322,11 +353,36 @@ attention_fwd_kernel(const __grid_constant__ AttnMaps maps, const AttnParams p) 
       }
     }
     tc_fence_before();
+    if (dbg != nullptr && threadIdx.x == 64) dbg[4] = clock64();
   }
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc<512>(tmem_base);
+  }
+  if (dbg != nullptr && threadIdx.x == 64) dbg[5] = clock64();
+}
+
+// score bias of the spatial self-attention for every layer at once: out[l][b][h][n][m] =
+// log(max(relu(loc[b,n,m,:] . w[l,h,:] + bias[l,h]), 1e-6))   (modules/layers/transformers.py:196-199,231-232)
+__global__ void spatial_bias_kernel(const float* __restrict__ locs, const float* __restrict__ w,
+                                    const float* __restrict__ bias, float* __restrict__ out, int L, int B, int H, int N,
+                                    int ld) {
+  pdl_sync();
+  const int64_t pairs = static_cast<int64_t>(B) * N * N;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < pairs;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int m = static_cast<int>(i % N);
+    const int n = static_cast<int>((i / N) % N);
+    const int b = static_cast<int>(i / (static_cast<int64_t>(N) * N));
+    const float* l5 = locs + i * 5;
+    const float l0 = l5[0], l1 = l5[1], l2 = l5[2], l3 = l5[3], l4 = l5[4];
+    for (int lh = 0; lh < L * H; ++lh) {
+      const float* wv = w + lh * 5;
+      const float v = fmaf(l0, wv[0], fmaf(l1, wv[1], fmaf(l2, wv[2], fmaf(l3, wv[3], fmaf(l4, wv[4], bias[lh])))));
+      const int l = lh / H, hh = lh % H;
+      out[(((static_cast<int64_t>(l) * B + b) * H + hh) * N + n) * ld + m] = __logf(fmaxf(fmaxf(v, 0.f), 1e-6f));
+    }
   }
 }
 
@@ -334,22 +390,38 @@ attention_fwd_kernel(const __grid_constant__ AttnMaps maps, const AttnParams p) 
 
 using namespace pq3d;
 
+static unsigned long long* g_attn_timeline = nullptr;
+extern "C" int pq3d_debug_set_attention_timeline(void* buf) {
+  g_attn_timeline = reinterpret_cast<unsigned long long*>(buf);
+  return PQ3D_OK;
+}
+
+extern "C" int pq3d_spatial_bias(const float* pairwise_locs, const float* loc_w, const float* loc_b, float* out, int L,
+                                 int B, int H, int N, int64_t ld, void* stream) {
+  PQ3D_CHECK_ARG(pairwise_locs && loc_w && loc_b && out, "pq3d_spatial_bias: null argument");
+  PQ3D_CHECK_ARG(L > 0 && B > 0 && H > 0 && N > 0 && ld >= N && ld % 4 == 0, "pq3d_spatial_bias: bad shape");
+  const int64_t pairs = static_cast<int64_t>(B) * N * N;
+  int blocks = static_cast<int>((pairs + 255) / 256);
+  if (blocks > sm_count() * 16) blocks = sm_count() * 16;
+  PQ3D_CUDA(launch_kernel(spatial_bias_kernel, dim3(blocks), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream),
+                          pairwise_locs, loc_w, loc_b, out, L, B, H, N, static_cast<int>(ld)));
+  return PQ3D_OK;
+}
+
 extern "C" int pq3d_attention_fwd(int n_mem, const void* Q, int64_t ldq, int64_t q_mem_stride, const void* const* K,
                                   const int64_t* ldk, const int64_t* k_col0, const void* const* Vt,
                                   const int64_t* ldvt, const int64_t* vt_row0, const int64_t* vt_rows,
                                   const int32_t* S, const int32_t* S_pitch, const int32_t* Vt_pitch,
-                                  const uint32_t* const* mask_bits,
-                                  const int64_t* mask_b_stride, const int64_t* mask_h_stride,
-                                  const int64_t* mask_q_stride, void* O, int64_t ldo, int64_t o_mem_stride, int B,
-                                  int H, int Nq, int zero_attn, const float* pairwise_locs, const float* loc_w,
-                                  const float* loc_b, void* stream) {
+                                  const uint32_t* const* mask_bits, const int64_t* mask_b_stride,
+                                  const int64_t* mask_h_stride, const int64_t* mask_q_stride, void* O, int64_t ldo,
+                                  int64_t o_mem_stride, int B, int H, int Nq, int zero_attn, const float* score_bias,
+                                  int64_t bias_ld, void* stream) {
   PQ3D_CHECK_ARG(n_mem >= 1 && n_mem <= kMaxMem, "pq3d_attention_fwd: n_mem=%d not in [1,%d]", n_mem, kMaxMem);
   PQ3D_CHECK_ARG(Q && O && K && Vt && S && S_pitch && Vt_pitch, "pq3d_attention_fwd: null argument");
   PQ3D_CHECK_ARG(B > 0 && H > 0 && Nq > 0, "pq3d_attention_fwd: bad shape B=%d H=%d Nq=%d", B, H, Nq);
   PQ3D_CHECK_ARG(ldq % 8 == 0 && ldo % 8 == 0 && (reinterpret_cast<uintptr_t>(Q) & 15) == 0 &&
                      (reinterpret_cast<uintptr_t>(O) & 15) == 0 && (o_mem_stride % 8) == 0,
                  "pq3d_attention_fwd: Q / O must be 16-byte aligned with leading dimensions multiple of 8");
-  PQ3D_CHECK_ARG((pairwise_locs == nullptr) || (loc_w && loc_b), "pq3d_attention_fwd: spatial bias needs loc_w and loc_b");
   AttnMaps maps;          // filled per call; passed by value to the launch
   AttnParams p;
   memset(&p, 0, sizeof(p));
@@ -367,6 +439,11 @@ extern "C" int pq3d_attention_fwd(int n_mem, const void* Q, int64_t ldq, int64_t
     PQ3D_CHECK_ARG(ldk[i] % 8 == 0 && ldvt[i] % 8 == 0 && ldvt[i] >= (int64_t)B * Vt_pitch[i] &&
                        (reinterpret_cast<uintptr_t>(K[i]) & 15) == 0 && (reinterpret_cast<uintptr_t>(Vt[i]) & 15) == 0,
                    "pq3d_attention_fwd: memory %d: K / V^T alignment or leading dimension", i);
+    PQ3D_CHECK_ARG(score_bias == nullptr ||
+                       (bias_ld % 4 == 0 && bias_ld >= ((S[i] + kKvTile - 1) / kKvTile) * kKvTile &&
+                        (reinterpret_cast<uintptr_t>(score_bias) & 15) == 0),
+                   "pq3d_attention_fwd: score_bias rows must be 16-byte aligned and padded to a multiple of %d keys",
+                   kKvTile);
     {
       uint64_t dims[3] = {(uint64_t)ldk[i], (uint64_t)S[i], (uint64_t)B};
       uint64_t strides[2] = {(uint64_t)ldk[i] * 2, (uint64_t)S_pitch[i] * ldk[i] * 2};
@@ -386,10 +463,6 @@ extern "C" int pq3d_attention_fwd(int n_mem, const void* Q, int64_t ldq, int64_t
     m.mask_b_stride = mask_bits ? mask_b_stride[i] : 0;
     m.mask_h_stride = mask_bits ? mask_h_stride[i] : 0;
     m.mask_q_stride = mask_bits ? mask_q_stride[i] : 0;
-    PQ3D_CHECK_ARG(m.mask_bits == nullptr || ((reinterpret_cast<uintptr_t>(m.mask_bits) & 15) == 0 &&
-                                              m.mask_b_stride % 4 == 0 && m.mask_h_stride % 4 == 0 &&
-                                              m.mask_q_stride % 4 == 0),
-                   "pq3d_attention_fwd: memory %d: packed mask must be 16-byte aligned with strides multiple of 4 words", i);
     m.S = S[i];
     m.k_col0 = (int32_t)k_col0[i];
     m.vt_row0 = (int32_t)vt_row0[i];
@@ -407,16 +480,16 @@ extern "C" int pq3d_attention_fwd(int n_mem, const void* Q, int64_t ldq, int64_t
   p.Nq = Nq;
   p.q_tiles = (Nq + 127) / 128;
   p.zero_attn = zero_attn;
-  p.pairwise_locs = pairwise_locs;
-  p.loc_w = loc_w;
-  p.loc_b = loc_b;
+  p.score_bias = score_bias;
+  p.bias_ld = bias_ld;
+  p.dbg = g_attn_timeline;
   static bool configured = false;
   if (!configured) {
     PQ3D_CUDA(cudaFuncSetAttribute(attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
     configured = true;
   }
   dim3 grid(H, B, n_mem * p.q_tiles);
-  attention_fwd_kernel<<<grid, kAttnThreads, kAttnSmem, reinterpret_cast<cudaStream_t>(stream)>>>(maps, p);
-  PQ3D_CUDA(cudaGetLastError());
+  PQ3D_CUDA(launch_kernel(attention_fwd_kernel, grid, dim3(kAttnThreads), kAttnSmem,
+                          reinterpret_cast<cudaStream_t>(stream), maps, p));
   return PQ3D_OK;
 }

@@ -14,6 +14,7 @@ namespace pq3d {
 __global__ void ingest_kernel(const float* __restrict__ feat, const float* __restrict__ pos,
                               __nv_bfloat16* __restrict__ xk, __nv_bfloat16* __restrict__ xv, int B, int S,
                               int S_pitch, int D) {
+  pdl_sync();
   const int vec_per_row = D / 8;
   const int64_t total = static_cast<int64_t>(B) * S_pitch * vec_per_row;
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
@@ -48,87 +49,90 @@ __global__ void ingest_kernel(const float* __restrict__ feat, const float* __res
 // :153).  Optionally emits the bf16 operands of the next GEMMs: bf16(out) and bf16(out + pos).
 // One warp per row; two-pass variance in fp32.
 // ------------------------------------------------------------------------------------------------
-constexpr int kLnMaxVec = 8;  // D <= 1024
+constexpr int kLnMaxVec = 8;   // D <= 1024
+constexpr int kLnMaxGroups = 4;
 
+// NV = D / 128 float4 chunks per lane.  Every global load (residual, all groups' y, affines of group 0)
+// is issued before the first reduction, so a row costs one memory round trip, not one per stage.
+template <int NV>
 __global__ void add_layernorm_kernel(const float* __restrict__ y, int64_t y_group_stride,
                                      const float* __restrict__ residual, const float* __restrict__ gamma,
-                                     const float* __restrict__ beta, int G, float eps, int R, int D,
+                                     const float* __restrict__ beta, int G, float eps, int R,
                                      const float* __restrict__ pos, float* __restrict__ out_f32,
                                      __nv_bfloat16* __restrict__ out_bf16, __nv_bfloat16* __restrict__ out_pos_bf16) {
+  pdl_sync();
+  constexpr int D = NV * 128;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= R) return;
   const int lane = threadIdx.x & 31;
-  const int nv = D / 128;  // float4 chunks per lane
-  float4 res[kLnMaxVec], acc[kLnMaxVec];
+  const int64_t base = static_cast<int64_t>(row) * D;
+  float4 res[NV], acc[NV], pp[NV];
+  float4 yv[kLnMaxGroups][NV];
 #pragma unroll
-  for (int i = 0; i < kLnMaxVec; ++i) {
+  for (int i = 0; i < NV; ++i) {
     acc[i] = make_float4(0, 0, 0, 0);
-    res[i] = make_float4(0, 0, 0, 0);
-    if (i < nv && residual != nullptr)
-      res[i] = __ldg(reinterpret_cast<const float4*>(residual + static_cast<int64_t>(row) * D) + i * 32 + lane);
+    res[i] = residual != nullptr ? __ldg(reinterpret_cast<const float4*>(residual + base) + i * 32 + lane)
+                                 : make_float4(0, 0, 0, 0);
+    pp[i] = (pos != nullptr && out_pos_bf16 != nullptr) ? __ldg(reinterpret_cast<const float4*>(pos + base) + i * 32 + lane)
+                                                        : make_float4(0, 0, 0, 0);
   }
-  const float inv_d = 1.f / static_cast<float>(D);
-  for (int g = 0; g < G; ++g) {
-    float4 x[kLnMaxVec];
-    float sum = 0.f;
 #pragma unroll
-    for (int i = 0; i < kLnMaxVec; ++i) {
-      if (i < nv) {
-        float4 v = res[i];
-        if (y != nullptr) {
-          const float4 t =
-              __ldg(reinterpret_cast<const float4*>(y + g * y_group_stride + static_cast<int64_t>(row) * D) + i * 32 + lane);
-          v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
-        }
-        x[i] = v;
-        sum += (v.x + v.y) + (v.z + v.w);
+  for (int g = 0; g < kLnMaxGroups; ++g) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+      yv[g][i] = (g < G && y != nullptr) ? __ldg(reinterpret_cast<const float4*>(y + g * y_group_stride + base) + i * 32 + lane)
+                                         : make_float4(0, 0, 0, 0);
+  }
+  constexpr float inv_d = 1.f / static_cast<float>(D);
+#pragma unroll
+  for (int g = 0; g < kLnMaxGroups; ++g) {
+    if (g < G) {
+      float4 ga[NV], be[NV];
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        ga[i] = __ldg(reinterpret_cast<const float4*>(gamma + g * D) + i * 32 + lane);
+        be[i] = __ldg(reinterpret_cast<const float4*>(beta + g * D) + i * 32 + lane);
       }
-    }
+      float4 x[NV];
+      float sum = 0.f;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    const float mean = sum * inv_d;
-    float sq = 0.f;
+      for (int i = 0; i < NV; ++i) {
+        x[i] = make_float4(res[i].x + yv[g][i].x, res[i].y + yv[g][i].y, res[i].z + yv[g][i].z, res[i].w + yv[g][i].w);
+        sum += (x[i].x + x[i].y) + (x[i].z + x[i].w);
+      }
 #pragma unroll
-    for (int i = 0; i < kLnMaxVec; ++i) {
-      if (i < nv) {
+      for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      const float mean = sum * inv_d;
+      float sq = 0.f;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
         const float a = x[i].x - mean, b = x[i].y - mean, c = x[i].z - mean, d = x[i].w - mean;
         sq += (a * a + b * b) + (c * c + d * d);
       }
-    }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
-    const float rstd = rsqrtf(sq * inv_d + eps);
+      for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+      const float rstd = rsqrtf(sq * inv_d + eps);
 #pragma unroll
-    for (int i = 0; i < kLnMaxVec; ++i) {
-      if (i < nv) {
-        const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma + g * D) + i * 32 + lane);
-        const float4 be = __ldg(reinterpret_cast<const float4*>(beta + g * D) + i * 32 + lane);
-        acc[i].x += (x[i].x - mean) * rstd * ga.x + be.x;
-        acc[i].y += (x[i].y - mean) * rstd * ga.y + be.y;
-        acc[i].z += (x[i].z - mean) * rstd * ga.z + be.z;
-        acc[i].w += (x[i].w - mean) * rstd * ga.w + be.w;
+      for (int i = 0; i < NV; ++i) {
+        acc[i].x += (x[i].x - mean) * rstd * ga[i].x + be[i].x;
+        acc[i].y += (x[i].y - mean) * rstd * ga[i].y + be[i].y;
+        acc[i].z += (x[i].z - mean) * rstd * ga[i].z + be[i].z;
+        acc[i].w += (x[i].w - mean) * rstd * ga[i].w + be[i].w;
       }
     }
   }
   const float inv_g = 1.f / static_cast<float>(G);
 #pragma unroll
-  for (int i = 0; i < kLnMaxVec; ++i) {
-    if (i < nv) {
-      float4 o = acc[i];
-      if (G > 1) { o.x *= inv_g; o.y *= inv_g; o.z *= inv_g; o.w *= inv_g; }
-      const int64_t off = static_cast<int64_t>(row) * D + (i * 32 + lane) * 4;
-      if (out_f32 != nullptr) *reinterpret_cast<float4*>(out_f32 + off) = o;
-      if (out_bf16 != nullptr)
-        *reinterpret_cast<uint2*>(out_bf16 + off) = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
-      if (out_pos_bf16 != nullptr) {
-        float4 q = o;
-        if (pos != nullptr) {
-          const float4 pp = __ldg(reinterpret_cast<const float4*>(pos + off));
-          q.x += pp.x; q.y += pp.y; q.z += pp.z; q.w += pp.w;
-        }
-        *reinterpret_cast<uint2*>(out_pos_bf16 + off) = make_uint2(pack_bf16x2(q.x, q.y), pack_bf16x2(q.z, q.w));
-      }
-    }
+  for (int i = 0; i < NV; ++i) {
+    float4 o = acc[i];
+    if (G > 1) { o.x *= inv_g; o.y *= inv_g; o.z *= inv_g; o.w *= inv_g; }
+    const int64_t off = base + (i * 32 + lane) * 4;
+    if (out_f32 != nullptr) *reinterpret_cast<float4*>(out_f32 + off) = o;
+    if (out_bf16 != nullptr)
+      *reinterpret_cast<uint2*>(out_bf16 + off) = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
+    if (out_pos_bf16 != nullptr)
+      *reinterpret_cast<uint2*>(out_pos_bf16 + off) =
+          make_uint2(pack_bf16x2(o.x + pp[i].x, o.y + pp[i].y), pack_bf16x2(o.z + pp[i].z, o.w + pp[i].w));
   }
 }
 
@@ -139,21 +143,19 @@ __global__ void add_layernorm_kernel(const float* __restrict__ y, int64_t y_grou
 // ------------------------------------------------------------------------------------------------
 __global__ void pack_mask_kernel(const uint8_t* __restrict__ mask, uint32_t* __restrict__ bits, int64_t rows, int S,
                                  int W, int unmask_full_rows, uint8_t* __restrict__ mask_fixed) {
-  const int64_t row = blockIdx.x * static_cast<int64_t>(blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= rows) return;
-  const int lane = threadIdx.x & 31;
+  pdl_sync();
+  // one block per row; warp w packs words w, w + nwarps, ...; the all-masked test is a block-wide AND
+  const int64_t row = blockIdx.x;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const uint8_t* src = mask + row * S;
-  bool all_masked = true;
+  int all_masked = 1;
   if (unmask_full_rows) {
-    for (int s0 = 0; s0 < S; s0 += 32) {
-      const int s = s0 + lane;
-      const bool mk = (s < S) ? (src[s] != 0) : true;
-      if (!__all_sync(0xffffffffu, mk)) { all_masked = false; break; }
-    }
+    for (int s = threadIdx.x; s < S; s += blockDim.x) all_masked &= (src[s] != 0);
+    all_masked = __syncthreads_and(all_masked);
   } else {
-    all_masked = false;
+    all_masked = 0;
   }
-  for (int w = 0; w < W; ++w) {
+  for (int w = wid; w < W; w += nw) {
     const int s = w * 32 + lane;
     bool mk = (s < S) ? (src[s] != 0) : true;
     if (all_masked && s < S) mk = false;
@@ -173,6 +175,7 @@ __global__ void mask_head_finalize_kernel(const float* __restrict__ raw, const u
                                           int n_mem, const uint8_t* __restrict__ seg_masks,
                                           float* __restrict__ mask_logits, uint8_t* __restrict__ attn_mask, int S,
                                           int N) {
+  pdl_sync();
   __shared__ uint8_t tile[32][33];
   const int b = blockIdx.z;
   const int s0 = blockIdx.x * 32, n0 = blockIdx.y * 32;
@@ -201,6 +204,7 @@ __global__ void mask_head_finalize_kernel(const float* __restrict__ raw, const u
 // gate mix for structure 'gate' (query_encoder.py:166-170): out = (1 - sigmoid(g)) * q + sigmoid(g) * u
 __global__ void gate_mix_kernel(const float* __restrict__ gate_logits, const float* __restrict__ query,
                                 const float* __restrict__ update, float* __restrict__ out, int64_t n) {
+  pdl_sync();
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     const float g = __fdiv_rn(1.f, 1.f + expf(-gate_logits[i]));
@@ -211,6 +215,7 @@ __global__ void gate_mix_kernel(const float* __restrict__ gate_logits, const flo
 // plain fp32 -> bf16 cast (+ optional add), for operands that do not pass through a LayerNorm
 __global__ void cast_bf16_kernel(const float* __restrict__ x, const float* __restrict__ add,
                                  __nv_bfloat16* __restrict__ out, int64_t n4) {
+  pdl_sync();
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n4;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
@@ -232,6 +237,7 @@ __global__ void cast_bf16_kernel(const float* __restrict__ x, const float* __res
 __global__ void fourier_pos_kernel(const float* __restrict__ xyz, int xyz_stride, const float* __restrict__ cmin,
                                    const float* __restrict__ cmax, const float* __restrict__ gauss_B,
                                    __nv_bfloat16* __restrict__ out, int B, int L, int half) {
+  pdl_sync();
   const int64_t total = static_cast<int64_t>(B) * L * half;
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
@@ -261,6 +267,7 @@ __global__ void fourier_pos_kernel(const float* __restrict__ xyz, int xyz_stride
 // ------------------------------------------------------------------------------------------------
 __global__ void pairwise_locs_kernel(const float* __restrict__ centers, int c_stride, float* __restrict__ out, int N,
                                      float eps) {
+  pdl_sync();
   __shared__ float red[32];
   __shared__ float s_max;
   const int b = blockIdx.x;
@@ -316,9 +323,9 @@ extern "C" int pq3d_ingest_memory(const float* feat, const float* pos, void* xk,
                      (reinterpret_cast<uintptr_t>(xk) & 15) == 0 && (reinterpret_cast<uintptr_t>(xv) & 15) == 0,
                  "pq3d_ingest_memory: pointers must be 16-byte aligned");
   const int64_t total = static_cast<int64_t>(B) * S_pitch * (D / 8);
-  ingest_kernel<<<grid_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      feat, pos, reinterpret_cast<__nv_bfloat16*>(xk), reinterpret_cast<__nv_bfloat16*>(xv), B, S, S_pitch, D);
-  PQ3D_CUDA(cudaGetLastError());
+  PQ3D_CUDA(launch_kernel(ingest_kernel, dim3(grid_for(total, 256)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream),
+                          feat, pos, reinterpret_cast<__nv_bfloat16*>(xk), reinterpret_cast<__nv_bfloat16*>(xv), B, S,
+                          S_pitch, D));
   return PQ3D_OK;
 }
 
@@ -328,11 +335,24 @@ extern "C" int pq3d_add_layernorm(const float* y, int64_t y_group_stride, const 
   PQ3D_CHECK_ARG((y || residual) && gamma && beta, "pq3d_add_layernorm: null argument");
   PQ3D_CHECK_ARG(G >= 1 && R > 0 && D % 128 == 0 && D <= 128 * kLnMaxVec, "pq3d_add_layernorm: bad shape G=%d R=%d D=%d",
                  G, R, D);
-  const int warps = 4;
-  add_layernorm_kernel<<<(R + warps - 1) / warps, warps * 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      y, y_group_stride, residual, gamma, beta, G, eps, R, D, pos, out_f32, reinterpret_cast<__nv_bfloat16*>(out_bf16),
-      reinterpret_cast<__nv_bfloat16*>(out_pos_bf16));
-  PQ3D_CUDA(cudaGetLastError());
+  PQ3D_CHECK_ARG(G <= kLnMaxGroups, "pq3d_add_layernorm: G=%d exceeds %d", G, kLnMaxGroups);
+  const int warps = 2;
+  const dim3 grid((R + warps - 1) / warps), block(warps * 32);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  __nv_bfloat16* o16 = reinterpret_cast<__nv_bfloat16*>(out_bf16);
+  __nv_bfloat16* op16 = reinterpret_cast<__nv_bfloat16*>(out_pos_bf16);
+#define PQ3D_LN_CASE(NV)                                                                                          \
+  case NV:                                                                                                        \
+    err = launch_kernel(add_layernorm_kernel<NV>, grid, block, 0, st, y, y_group_stride, residual, gamma, beta, G, \
+                        eps, R, pos, out_f32, o16, op16);                                                          \
+    break;
+  cudaError_t err = cudaSuccess;
+  switch (D / 128) {
+    PQ3D_LN_CASE(1) PQ3D_LN_CASE(2) PQ3D_LN_CASE(3) PQ3D_LN_CASE(4) PQ3D_LN_CASE(5) PQ3D_LN_CASE(6) PQ3D_LN_CASE(7)
+    PQ3D_LN_CASE(8)
+  }
+#undef PQ3D_LN_CASE
+  PQ3D_CUDA(err);
   return PQ3D_OK;
 }
 
@@ -340,10 +360,9 @@ extern "C" int pq3d_pack_mask(const uint8_t* mask, uint32_t* bits, int64_t rows,
                               uint8_t* mask_fixed, void* stream) {
   PQ3D_CHECK_ARG(mask && bits && rows > 0 && S > 0, "pq3d_pack_mask: bad argument");
   const int W = ((S + 127) / 128) * 4;
-  const int warps = 8;
-  pack_mask_kernel<<<static_cast<unsigned>((rows + warps - 1) / warps), warps * 32, 0,
-                     reinterpret_cast<cudaStream_t>(stream)>>>(mask, bits, rows, S, W, unmask_full_rows, mask_fixed);
-  PQ3D_CUDA(cudaGetLastError());
+  const int threads = S >= 1024 ? 256 : (S >= 256 ? 128 : 32);
+  PQ3D_CUDA(launch_kernel(pack_mask_kernel, dim3(static_cast<unsigned>(rows)), dim3(threads), 0,
+                          reinterpret_cast<cudaStream_t>(stream), mask, bits, rows, S, W, unmask_full_rows, mask_fixed));
   return PQ3D_OK;
 }
 
@@ -353,25 +372,23 @@ extern "C" int pq3d_mask_head_finalize(const float* raw, const uint8_t* const* m
   PQ3D_CHECK_ARG(raw && mem_masks_dev && seg_masks && mask_logits && attn_mask && n_mem >= 1,
                  "pq3d_mask_head_finalize: bad argument");
   dim3 grid((S + 31) / 32, (N + 31) / 32, B), block(32, 8);
-  mask_head_finalize_kernel<<<grid, block, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      raw, mem_masks_dev, n_mem, seg_masks, mask_logits, attn_mask, S, N);
-  PQ3D_CUDA(cudaGetLastError());
+  PQ3D_CUDA(launch_kernel(mask_head_finalize_kernel, grid, block, 0, reinterpret_cast<cudaStream_t>(stream), raw,
+                          mem_masks_dev, n_mem, seg_masks, mask_logits, attn_mask, S, N));
   return PQ3D_OK;
 }
 
 extern "C" int pq3d_gate_mix(const float* gate_logits, const float* query, const float* update, float* out, int64_t n,
                              void* stream) {
   PQ3D_CHECK_ARG(gate_logits && query && update && out && n > 0, "pq3d_gate_mix: bad argument");
-  gate_mix_kernel<<<grid_for(n, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(gate_logits, query, update, out, n);
-  PQ3D_CUDA(cudaGetLastError());
+  PQ3D_CUDA(launch_kernel(gate_mix_kernel, dim3(grid_for(n, 256)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream),
+                          gate_logits, query, update, out, n));
   return PQ3D_OK;
 }
 
 extern "C" int pq3d_cast_bf16(const float* x, const float* add, void* out, int64_t n, void* stream) {
   PQ3D_CHECK_ARG(x && out && n > 0 && n % 4 == 0, "pq3d_cast_bf16: n=%lld must be a positive multiple of 4", (long long)n);
-  cast_bf16_kernel<<<grid_for(n / 4, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      x, add, reinterpret_cast<__nv_bfloat16*>(out), n / 4);
-  PQ3D_CUDA(cudaGetLastError());
+  PQ3D_CUDA(launch_kernel(cast_bf16_kernel, dim3(grid_for(n / 4, 256)), dim3(256), 0,
+                          reinterpret_cast<cudaStream_t>(stream), x, add, reinterpret_cast<__nv_bfloat16*>(out), n / 4));
   return PQ3D_OK;
 }
 
@@ -380,16 +397,16 @@ extern "C" int pq3d_fourier_pos(const float* xyz, int xyz_stride, const float* c
   PQ3D_CHECK_ARG(xyz && coord_min && coord_max && gauss_B && out_bf16, "pq3d_fourier_pos: null argument");
   PQ3D_CHECK_ARG(B > 0 && L > 0 && d_pos > 0 && d_pos % 2 == 0 && xyz_stride >= 3, "pq3d_fourier_pos: bad shape");
   const int64_t total = static_cast<int64_t>(B) * L * (d_pos / 2);
-  fourier_pos_kernel<<<grid_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      xyz, xyz_stride, coord_min, coord_max, gauss_B, reinterpret_cast<__nv_bfloat16*>(out_bf16), B, L, d_pos / 2);
-  PQ3D_CUDA(cudaGetLastError());
+  PQ3D_CUDA(launch_kernel(fourier_pos_kernel, dim3(grid_for(total, 256)), dim3(256), 0,
+                          reinterpret_cast<cudaStream_t>(stream), xyz, xyz_stride, coord_min, coord_max, gauss_B,
+                          reinterpret_cast<__nv_bfloat16*>(out_bf16), B, L, d_pos / 2));
   return PQ3D_OK;
 }
 
 extern "C" int pq3d_pairwise_locs(const float* centers, int c_stride, float* out, int B, int N, float eps,
                                   void* stream) {
   PQ3D_CHECK_ARG(centers && out && B > 0 && N > 0 && c_stride >= 3, "pq3d_pairwise_locs: bad argument");
-  pairwise_locs_kernel<<<B, 512, 0, reinterpret_cast<cudaStream_t>(stream)>>>(centers, c_stride, out, N, eps);
-  PQ3D_CUDA(cudaGetLastError());
+  PQ3D_CUDA(launch_kernel(pairwise_locs_kernel, dim3(B), dim3(512), 0, reinterpret_cast<cudaStream_t>(stream), centers,
+                          c_stride, out, N, eps));
   return PQ3D_OK;
 }

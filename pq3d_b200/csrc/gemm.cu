@@ -107,6 +107,7 @@ linear_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_sync();   // everything above overlapped the previous kernel's tail; global memory is touched only below
   unsigned long long* dbg = p.dbg == nullptr ? nullptr : p.dbg + 8ull * blockIdx.x;
   if (dbg != nullptr && threadIdx.x == 0) {
     dbg[0] = global_timer_ns();
@@ -287,7 +288,7 @@ linear_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         release_accumulator();
       }
     }
-    if (r == 0) tma_store_wait_all();   // outstanding bulk stores must finish reading smem before exit
+    if (r == 0) tma_store_wait_read<0>();   // bulk stores must finish READING smem before exit (writes complete at grid end)
     __syncwarp();
     tc_fence_before();
     if (dbg != nullptr && threadIdx.x == 64) dbg[5] = clock64();
@@ -311,8 +312,7 @@ static int launch_linear(const CUtensorMap& ta, const CUtensorMap& tw, const CUt
     configured = true;
   }
   const int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
-  linear_bf16_kernel<BN><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tw, tc, p);
-  PQ3D_CUDA(cudaGetLastError());
+  PQ3D_CUDA(launch_kernel(linear_bf16_kernel<BN>, dim3(grid), dim3(kGemmThreads), Cfg::kSmemBytes, stream, ta, tw, tc, p));
   return PQ3D_OK;
 }
 

@@ -1,5 +1,6 @@
 #include "host_common.h"
 
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -15,6 +16,15 @@ int set_error(int code, const char* fmt, ...) {
   return code;
 }
 const char* last_error() { return g_err; }
+
+bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("PQ3D_PDL");
+    on = (e == nullptr || e[0] != '0') ? 1 : 0;
+  }
+  return on == 1;
+}
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,

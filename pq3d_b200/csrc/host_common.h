@@ -41,6 +41,28 @@ inline int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const ui
   return make_tmap(out, base, 2, rank, dims, strides_bytes, box);
 }
 
+// Programmatic dependent launch (PDL): every kernel in this library starts with
+// `griddepcontrol.launch_dependents; griddepcontrol.wait;` after its private set-up, so launching with
+// the programmatic-stream-serialization attribute lets kernel N+1's set-up (barrier init, TMEM
+// allocation, tensor-map prefetch, launch latency) overlap kernel N's tail.  PQ3D_PDL=0 disables it.
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                 Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 inline int sm_count() {
   static int n = 0;
   if (n == 0) {

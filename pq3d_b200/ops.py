@@ -87,8 +87,8 @@ class AttnMemory:
 
 
 def attention(Q: torch.Tensor, q_mem_stride: int, mems: Sequence[AttnMemory], O: torch.Tensor, o_mem_stride: int,
-              B: int, H: int, Nq: int, zero_attn: bool, pairwise_locs: Optional[torch.Tensor] = None,
-              loc_w: Optional[torch.Tensor] = None, loc_b: Optional[torch.Tensor] = None) -> torch.Tensor:
+              B: int, H: int, Nq: int, zero_attn: bool, score_bias: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """score_bias: optional fp32 (B, H, Nq, ld) added to the scores (ld = keys padded to a multiple of 128)."""
     _chk(Q, bf16, "Q", 2)
     _chk(O, bf16, "O")
     n = len(mems)
@@ -100,12 +100,12 @@ def attention(Q: torch.Tensor, q_mem_stride: int, mems: Sequence[AttnMemory], O:
         _chk(m.Vt, bf16, "Vt", 2)
         if m.mask_bits is not None:
             _chk(m.mask_bits, torch.int32, "mask_bits")
-    if pairwise_locs is not None:
-        _chk(pairwise_locs, torch.float32, "pairwise_locs", 4)
-        if not pairwise_locs.is_contiguous() or tuple(pairwise_locs.shape) != (B, Nq, Nq, 5):
-            raise ValueError("pairwise_locs must be contiguous (B, Nq, Nq, 5)")
-        _chk(loc_w, torch.float32, "loc_w")
-        _chk(loc_b, torch.float32, "loc_b")
+    bias_ld = 0
+    if score_bias is not None:
+        _chk(score_bias, torch.float32, "score_bias", 4)
+        if not score_bias.is_contiguous() or tuple(score_bias.shape[:3]) != (B, H, Nq):
+            raise ValueError("score_bias must be contiguous (B, H, Nq, ld)")
+        bias_ld = score_bias.shape[3]
     has_mask = any(m.mask_bits is not None for m in mems)
     rc = _lib.lib().pq3d_attention_fwd(
         n, Q.data_ptr(), Q.stride(0), q_mem_stride,
@@ -116,11 +116,31 @@ def attention(Q: torch.Tensor, q_mem_stride: int, mems: Sequence[AttnMemory], O:
         vp(*[_p(m.mask_bits) for m in mems]) if has_mask else None,
         i64(*[m.mask_b_stride for m in mems]), i64(*[m.mask_h_stride for m in mems]),
         i64(*[m.mask_q_stride for m in mems]),
-        O.data_ptr(), O.stride(-2), o_mem_stride, B, H, Nq, int(zero_attn),
-        _p(pairwise_locs), _p(loc_w), _p(loc_b), _stream())
+        O.data_ptr(), O.stride(-2), o_mem_stride, B, H, Nq, int(zero_attn), _p(score_bias), bias_ld, _stream())
     _lib.check(rc, "pq3d_attention_fwd")
     _count()
     return O
+
+
+def bias_ld(S: int) -> int:
+    return (S + 127) // 128 * 128
+
+
+def spatial_bias(pairwise_locs: torch.Tensor, loc_w: torch.Tensor, loc_b: torch.Tensor, out: torch.Tensor):
+    """pairwise_locs (B,N,N,5), loc_w (L,H,5), loc_b (L,H) -> out (L,B,H,N,ld) fp32."""
+    _chk(pairwise_locs, torch.float32, "pairwise_locs", 4)
+    _chk(loc_w, torch.float32, "loc_w", 3)
+    _chk(loc_b, torch.float32, "loc_b", 2)
+    _chk(out, torch.float32, "out", 5)
+    L, B, H, N, ld = out.shape
+    if not (pairwise_locs.is_contiguous() and loc_w.is_contiguous() and loc_b.is_contiguous() and out.is_contiguous()):
+        raise ValueError("spatial_bias operands must be contiguous")
+    if tuple(pairwise_locs.shape) != (B, N, N, 5) or tuple(loc_w.shape) != (L, H, 5) or tuple(loc_b.shape) != (L, H):
+        raise ValueError("spatial_bias shape mismatch")
+    rc = _lib.lib().pq3d_spatial_bias(pairwise_locs.data_ptr(), loc_w.data_ptr(), loc_b.data_ptr(), out.data_ptr(),
+                                      L, B, H, N, ld, _stream())
+    _lib.check(rc, "pq3d_spatial_bias")
+    _count()
 
 
 def ingest_memory(feat: torch.Tensor, pos: Optional[torch.Tensor], xk: Optional[torch.Tensor],

@@ -218,11 +218,26 @@ class _Packed:
             if lay.structure == "gate":
                 d["gate"] = dict(w=w16(lay.gate_proj.weight), b=f(lay.gate_proj.bias))
             self.layers.append(d)
+        self._fused_kv = {}
+        if self.layers[0]["sa"]["loc_w"] is not None:
+            self.loc_w = torch.stack([d["sa"]["loc_w"] for d in self.layers], 0).contiguous()      # (L, H, 5)
+            self.loc_b = torch.stack([d["sa"]["loc_b"] for d in self.layers], 0).contiguous()      # (L, H)
+        else:
+            self.loc_w = self.loc_b = None
+
+
+    def _fused(self, mems):
+        if mems not in self._fused_kv:
+            self._fused_kv[mems] = (torch.cat([self.wk[m] for m in mems], 0), torch.cat([self.bk[m] for m in mems], 0),
+                                    torch.cat([self.wv[m] for m in mems], 0), torch.cat([self.bv[m] for m in mems], 0))
+        return self._fused_kv[mems]
+
+    fused_kv = _fused
 
 
 class _MemState:
     """Per-forward projected state of one memory."""
-    __slots__ = ("name", "S", "S_pitch", "multi", "xk", "xv", "K", "Vt", "bits", "strides")
+    __slots__ = ("name", "S", "S_pitch", "multi", "per_layer", "xk", "xv", "K", "Vt", "bits", "strides")
 
 
 # --------------------------------------------------------------------------------------------
@@ -268,6 +283,11 @@ class QueryMaskEncoder(nn.Module):
         self._packed_key = None
         self._ws: Dict[tuple, dict] = {}
         self.use_cuda_graph = True
+        # K / V^T of all layers are hoisted into one grouped GEMM per forward.  Projecting layer by layer (so a
+        # layer's 75 MB stays L2-resident for its attention) was measured at config 3: the attention kernel did not
+        # speed up (it is bound by TMEM->register bandwidth, not HBM) and the narrower GEMMs cost +63 us/step, so
+        # the per-layer mode is off unless the hoisted buffers would exceed this many bytes.
+        self.kv_hoist_bytes = 8 << 30
 
     # ---- structure -> cross-attention program ------------------------------------------------
     def _active(self) -> List[str]:
@@ -331,6 +351,21 @@ class QueryMaskEncoder(nn.Module):
         # ---------------- prologue (eager): everything that reads caller-owned tensors lands in static buffers
         voxel_feat = input_dict["voxel"][0] if "voxel" in input_dict else None
         states: Dict[str, _MemState] = {}
+        # memories with one feature tensor, a positional table and the same token count share one set of
+        # buffers so that their K / V^T projections run as ONE grouped GEMM launch each
+        fused = [m for m in active if not isinstance(input_dict[m][0], list) and input_dict[m][2] is not None]
+        if len(fused) >= 2 and len({input_dict[m][0].shape[1] for m in fused}) == 1:
+            nf = len(fused)
+            Sp = ops.pad8(input_dict[fused[0]][0].shape[1])
+            tag = "+".join(fused)
+            xk_all, xv_all = buf(f"xk_{tag}", (nf * B * Sp, D), bf16), buf(f"xv_{tag}", (nf * B * Sp, D), bf16)
+            # K / V^T of all L layers for these memories: nf*B*Sp*L*D*4 bytes (302 MB at config 3); past
+            # kv_hoist_bytes project layer by layer into one layer-sized buffer instead (bounds memory).
+            per_layer = self.num_blocks == 1 and nf * B * Sp * L * D * 4 > self.kv_hoist_bytes
+            Lk = 1 if per_layer else L
+            K_all, Vt_all = buf(f"K_{tag}", (nf, B * Sp, Lk * D), bf16), buf(f"Vt_{tag}", (nf, Lk * D, B * Sp), bf16)
+        else:
+            fused, per_layer = [], False
         for m in active:
             feat, mask, pos = input_dict[m]
             multi = isinstance(feat, list)
@@ -339,17 +374,23 @@ class QueryMaskEncoder(nn.Module):
             Sp = ops.pad8(S)
             st = _MemState()
             st.name, st.S, st.S_pitch, st.multi = m, S, Sp, multi
+            st.per_layer = per_layer and m in fused
             nsrc = L if multi else 1
-            st.xv = buf(f"xv_{m}", (nsrc * B * Sp, D), bf16)
-            st.xk = buf(f"xk_{m}", (nsrc * B * Sp, D), bf16) if pos is not None else st.xv
+            if m in fused:
+                j = fused.index(m)
+                st.xv, st.xk = xv_all[j * B * Sp:(j + 1) * B * Sp], xk_all[j * B * Sp:(j + 1) * B * Sp]
+                st.K, st.Vt = K_all[j], Vt_all[j]
+            else:
+                st.xv = buf(f"xv_{m}", (nsrc * B * Sp, D), bf16)
+                st.xk = buf(f"xk_{m}", (nsrc * B * Sp, D), bf16) if pos is not None else st.xv
+                st.K = buf(f"K_{m}", (B * Sp, L * D), bf16)
+                st.Vt = buf(f"Vt_{m}", (L * D, B * Sp), bf16)
             for i in range(nsrc):
                 fi = (feat[i] if multi else feat).contiguous()
                 sl = slice(i * B * Sp, (i + 1) * B * Sp)
                 ops.ingest_memory(fi.float() if fi.dtype != torch.float32 else fi,
                                   None if pos is None else pos.contiguous().float(),
                                   st.xk[sl] if pos is not None else None, st.xv[sl], Sp)
-            st.K = buf(f"K_{m}", (B * Sp, L * D), bf16)
-            st.Vt = buf(f"Vt_{m}", (L * D, B * Sp), bf16)
             self._set_mask(st, mask, B, N, H, ws, dev)
             states[m] = st
         q32 = buf("q32", (R, D), torch.float32)
@@ -365,10 +406,26 @@ class QueryMaskEncoder(nn.Module):
                 raise ValueError("spatial_selfattn=True needs pairwise_locs (B, N, N, 5)")
             pw = buf("pw", (B, N, N, 5), torch.float32)
             pw.copy_(pairwise_locs)
+        # spatial score bias of all L layers, computed once per forward from the (layer independent) geometry
+        sbias = buf("sbias", (L, B, H, N, ops.bias_ld(N)), torch.float32) if pk.loc_w is not None else None
+
+        def project_fused(l0, nl):
+            """K / V^T of layers [l0, l0+nl) for the fused memories: one grouped GEMM launch each."""
+            nf, Sp = len(fused), states[fused[0]].S_pitch
+            wk, bk, wv, bv = pk.fused_kv(tuple(fused))
+            ops.linear(xk_all, wk[l0 * D:], K_all, M=B * Sp, N=nl * D, K=D, bias=bk[l0 * D:], bias_group_stride=L * D,
+                       groups=nf, a_group_rows=B * Sp, w_group_rows=L * D, ldc=nl * D, c_group_stride=B * Sp * nl * D)
+            ops.linear(wv[l0 * D:], xv_all, Vt_all, M=nl * D, N=B * Sp, K=D, bias=bv[l0 * D:], bias_along_m=True,
+                       bias_group_stride=L * D, groups=nf, a_group_rows=L * D, w_group_rows=B * Sp, ldc=B * Sp,
+                       c_group_stride=nl * D * B * Sp)
 
         def project_memories():
             """Hoisted K / V^T projections of every memory for all L layers (query independent)."""
+            if fused and not per_layer:
+                project_fused(0, L)
             for m in active:
+                if m in fused:
+                    continue
                 st = states[m]
                 Sp = st.S_pitch
                 if st.multi:
@@ -382,8 +439,13 @@ class QueryMaskEncoder(nn.Module):
                     ops.linear(pk.wv[m], st.xv, st.Vt, M=L * D, N=B * Sp, K=D, bias=pk.bv[m], bias_along_m=True)
             ops.cast_bf16(q32, xq, add=qpos)
             ops.cast_bf16(q32, xv_q)
+            if sbias is not None:
+                ops.spatial_bias(pw, pk.loc_w, pk.loc_b, sbias)
 
-        run_layer = lambda i: self._layer(i, pk, program, states, ws, dev, B, N, D, H, q32, qpos, xq, xv_q, qbits, pw)  # noqa: E731
+        def run_layer(i):
+            if per_layer:
+                project_fused(i, 1)
+            self._layer(i, pk, program, states, ws, dev, B, N, D, H, q32, qpos, xq, xv_q, qbits, sbias)
 
         predictions_class, predictions_mask = [], []
         if mask_head is None and not self.use_self_mask:
@@ -479,15 +541,16 @@ class QueryMaskEncoder(nn.Module):
         Q = self._buf(ws, f"Q_{tag}", (R, g * D), bf16, dev)
         ops.linear(x_in, w["wq"], Q, M=R, N=g * D, K=D, bias=w["bq"], alpha=0.125, alpha_ncols=g * D)
         O = self._buf(ws, f"O_{tag}", (g, R, D), bf16, dev)
-        mems = [ops.AttnMemory(states[m].K, i * D, states[m].Vt, i * D, states[m].S, states[m].S_pitch,
-                               states[m].bits, *states[m].strides) for m in grp]
+        mems = [ops.AttnMemory(states[m].K, 0 if states[m].per_layer else i * D, states[m].Vt,
+                               0 if states[m].per_layer else i * D, states[m].S, states[m].S_pitch, states[m].bits,
+                               *states[m].strides) for m in grp]
         ops.attention(Q, D, mems, O, R * D, B, H, N, True)
         y = self._buf(ws, f"y_{tag}", (g, R, D), torch.float32, dev)
         ops.linear(O.view(g * R, D), w["wo"], y, M=R, N=D, K=D, bias=w["bo"], bias_group_stride=D, groups=g,
                    a_group_rows=R, w_group_rows=D, ldc=D, c_group_stride=R * D)
         return y, w
 
-    def _layer(self, i, pk, program, states, ws, dev, B, N, D, H, q32, qpos, xq, xv_q, qbits, pw):
+    def _layer(self, i, pk, program, states, ws, dev, B, N, D, H, q32, qpos, xq, xv_q, qbits, sbias):
         R = B * N
         lw = pk.layers[i]
         if self.structure == "gate":
@@ -523,8 +586,7 @@ class QueryMaskEncoder(nn.Module):
                    w_group_rows=N, ldc=B * Np, c_group_stride=Np)
         Os = self._buf(ws, "sa_O", (1, R, D), bf16, dev)
         mem = ops.AttnMemory(QK, D, Vt, 0, N, N, qbits, qbits.stride(0), 0, 0, Vt_pitch=Np)
-        ops.attention(QK, 0, [mem], Os, R * D, B, H, N, False, pw if sa["loc_w"] is not None else None,
-                      sa["loc_w"], sa["loc_b"])
+        ops.attention(QK, 0, [mem], Os, R * D, B, H, N, False, None if sbias is None else sbias[i])
         ys = self._buf(ws, "sa_y", (R, D), torch.float32, dev)
         ops.linear(Os.view(R, D), sa["wo"], ys, M=R, N=D, K=D, bias=sa["bo"])
         ops.add_layernorm(ys, q32, sa["gamma"], sa["beta"], sa["eps"], R, D, out_f32=q32, out_bf16=xv_q)

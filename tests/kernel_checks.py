@@ -157,7 +157,12 @@ def _attn_case(B, H, Nq, S_list, mask_kind, zero_attn=True, spatial=False, seed=
             loc = torch.relu(torch.einsum("bnmd,hd->bhnm", pw, lw) + lb[None, :, None, None])
             bias = torch.log(loc.clamp_min(1e-6))
         refs.append(_attn_ref(Qh, Kh, Vh, full, zero_attn, bias))
-    ops.attention(Q, D, mems, O, O.stride(0), B, H, Nq, zero_attn, pw, lw, lb)
+    sbias = None
+    if spatial:
+        sbias = torch.full((1, B, H, Nq, ops.bias_ld(Nq)), float("nan"), device=DEV)
+        ops.spatial_bias(pw, lw[None].contiguous(), lb[None].contiguous(), sbias)
+        sbias = sbias[0]
+    ops.attention(Q, D, mems, O, O.stride(0), B, H, Nq, zero_attn, sbias)
     torch.cuda.synchronize()
     for i in range(n_mem):
         got = O[i].view(B, Nq, H, 64).permute(0, 2, 1, 3).float()
@@ -187,6 +192,14 @@ def check_attn_masks():
 def check_attn_spatial():
     _attn_case(2, 12, 100, [100], "kpm", zero_attn=False, spatial=True, seed=9)
     _attn_case(1, 2, 37, [37], "none", zero_attn=False, spatial=True, seed=10)
+    _attn_case(1, 2, 200, [200], "kpm", zero_attn=False, spatial=True, seed=14)   # two query tiles, two resident key tiles
+
+
+def check_attn_resident():
+    """Memories of <= 256 keys keep their score tiles in TMEM (single QK^T pass)."""
+    _attn_case(2, 3, 100, [256], "kpm", seed=15)
+    _attn_case(2, 3, 100, [129], "attn", seed=16)
+    _attn_case(2, 3, 100, [257], "kpm", seed=17)           # just past the resident limit: streaming path
 
 
 def check_attn_long():

@@ -104,6 +104,20 @@ if __name__ == "__main__":
         us3 = timeit(lambda: ops.attention(Q, D, mems, O, B * Nq * D, B, H, Nq, True))
         us1 = timeit(lambda: ops.attention(Q, D, mems[:1], O, B * Nq * D, B, H, Nq, True))
         print(f"  S={S}: 3 memories {us3:.1f} us, 1 memory {us1:.1f} us")
+        if S in (128, 2048):
+            n_cta = H * B * 3
+            tb = torch.zeros(n_cta * 8, dtype=torch.int64, device=dev)
+            lib = _lib.lib()
+            lib.pq3d_debug_set_attention_timeline(tb.data_ptr())
+            ops.attention(Q, D, mems, O, B * Nq * D, B, H, Nq, True)
+            torch.cuda.synchronize()
+            lib.pq3d_debug_set_attention_timeline(None)
+            t = tb.view(n_cta, 8).cpu().double()
+            for name, i in (("pass 1 done", 2), ("pass 2 done", 3), ("output stored", 4), ("exit", 5)):
+                v = t[:, i] - t[:, 1]
+                print(f"      [attention timeline S={S}] {name:14s} median {v.median().item():8.0f} max {v.max().item():8.0f} cycles after setup")
+            span = (t[:, 0].max() - t[:, 0].min()) / 1e3
+            print(f"      CTA start spread {span:.1f} us")
     print("== elementwise")
     R = 400
     y, res, pos = torch.randn(3, R, D, device=dev), torch.randn(R, D, device=dev), torch.randn(R, D, device=dev)
