@@ -1,0 +1,7 @@
+#!/bin/bash
+mkdir -p gpurun_out
+export PQ3D_PDL=0   # serialised profiling: no overlap between kernels
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 300 -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 3 --warmup 3 --no-graph --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1; echo "ncu list rc=$?"
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:linear_bf16_kernel -s 3 -c 1 -f -o gpurun_out/prof_gemm python tools/ncu_targets.py gemm > gpurun_out/ncu_gemm.log 2>&1; echo "ncu gemm rc=$?"
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:attention_fwd -s 3 -c 1 -f -o gpurun_out/prof_attn python tools/ncu_targets.py attn > gpurun_out/ncu_attn.log 2>&1; echo "ncu attn rc=$?"
+ls -la gpurun_out/*.ncu-rep
