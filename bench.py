@@ -248,10 +248,54 @@ def main():
     for _ in range(e2e_steps):
         step_e2e()
     torch.cuda.synchronize()
+    t_serial = torch.tensor([time.perf_counter() - t0], device=dev)
+
+    # Same work, software-pipelined the way a serving loop would run it: two device input sets; the H2D copy
+    # of batch i+1 (copy stream) overlaps the forward of batch i; the D2H read of batch i follows its forward.
+    # Every step still moves its own inputs host->device and its result device->host inside the timed region.
+    copy_stream = torch.cuda.Stream(device=dev)
+    main_stream = torch.cuda.current_stream()
+    sets = []
+    for _ in range(2):
+        d_inp, memo = dict_to(inp_pin, lambda t: torch.empty(t.shape, dtype=t.dtype, device=dev))
+        sets.append(dict(inp=d_inp, pairs=[(memo[id(t)], t) for t in pinned.values()], pw=torch.empty_like(pw_pin, device=dev),
+                         h2d_done=torch.cuda.Event(), consumed=torch.cuda.Event(),
+                         out=torch.empty(w.B, w.N, w.hidden_size, dtype=torch.float32).pin_memory()))
+
+    def issue_h2d(i):
+        st = sets[i % 2]
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(st["consumed"])          # the forward that last read this set has finished
+            for dst, src in st["pairs"]:
+                dst.copy_(src, non_blocking=True)
+            st["pw"].copy_(pw_pin, non_blocking=True)
+            st["h2d_done"].record(copy_stream)
+
+    def run_pipelined(n):
+        for st in sets:
+            st["consumed"].record(main_stream)
+        issue_h2d(0)
+        for i in range(n):
+            if i + 1 < n:
+                issue_h2d(i + 1)
+            st = sets[i % 2]
+            main_stream.wait_event(st["h2d_done"])
+            with torch.no_grad():
+                q = enc(synth.clone_input_dict(st["inp"]), st["pw"])[0]
+            st["consumed"].record(main_stream)
+            st["out"].copy_(q, non_blocking=True)
+        torch.cuda.synchronize()
+
+    run_pipelined(4)
+    barrier()
+    t0 = time.perf_counter()
+    run_pipelined(e2e_steps)
     t_e2e = torch.tensor([time.perf_counter() - t0], device=dev)
     if world > 1:
         dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t_serial, op=dist.ReduceOp.MAX)
     e2e_value = world * w.B * w.N * e2e_steps / t_e2e.item()
+    e2e_serial = world * w.B * w.N * e2e_steps / t_serial.item()
 
     if rank != 0:
         if world > 1:
@@ -326,7 +370,10 @@ def main():
                            cuda_graph=enc.use_cuda_graph),
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": e2e_steps, "timing": "wall clock around H2D(pinned)->forward->D2H per step, max over ranks"},
+                    "steps": e2e_steps, "serial_value": e2e_serial,
+                    "timing": "wall clock, max over ranks; every step copies its inputs from pinned host memory and reads its "
+                              "result back; value = double-buffered (H2D of step i+1 overlaps forward of step i), "
+                              "serial_value = strictly H2D->forward->D2H one step at a time"},
             "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu}
     print(json.dumps(line), flush=True)
     if world > 1:

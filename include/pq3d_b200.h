@@ -32,6 +32,8 @@ int pq3d_abi_version(void);
 /* Debug only: per-CTA timeline of pq3d_linear_bf16 (8 x uint64 per CTA) into a device buffer; NULL disables. */
 int pq3d_debug_set_timeline(void* buf);
 int pq3d_debug_set_attention_timeline(void* buf);
+/* Testing hook: 1 = long memories always take the running-max (two-pass) attention schedule. */
+int pq3d_debug_force_two_pass(int on);
 
 /* C[g] = epilogue(A[g] · W[g]ᵀ), bf16 operands, fp32 accumulation on tcgen05 tensor cores.
  *   A: [a_rows_total, lda] bf16, group g starts at row g*a_group_rows, uses M rows, K columns
@@ -54,16 +56,18 @@ int pq3d_linear_bf16(const void* A, int64_t lda, int64_t a_rows_total, int64_t a
                      int block_n, void* stream);
 
 /* Masked softmax attention for n_mem (<= 4) memories in one launch, head_dim = 64.
- *   Q : bf16 [B*Nq, ldq]; memory i / head h at columns i*q_mem_stride + h*64; already scaled by 1/8
+ *   Q : bf16 [B*Nq, ldq]; memory i / head h at columns i*q_mem_stride + h*64; already scaled by
+ *       log2(e)/sqrt(64) — scores are handled in the log2 domain (a probability is one ex2)
  *   K[i] : bf16 [B*S_pitch[i], ldk[i]]; head h at columns k_col0[i] + h*64
  *   Vt[i]: bf16 [vt_rows[i], ldvt[i]] — V TRANSPOSED: row vt_row0[i] + h*64 + d, column b*Vt_pitch[i] + s
  *          (Vt_pitch multiple of 8: TMA strides are 16-byte granular; pad columns must hold finite values)
  *   mask_bits[i]: packed by pq3d_pack_mask (1 = ignore), word address
  *                 b*mask_b_stride + h*mask_h_stride + n*mask_q_stride + s/32; NULL = nothing masked
+ *   kv_tiles[i]:  optional device int32 [B] from pq3d_pack_mask(active_tiles): key tiles past it are skipped
  *   O : bf16, element (i, b, n, h*64+d) at O[i*o_mem_stride + (b*Nq+n)*ldo + h*64 + d]
  *   zero_attn: nn.MultiheadAttention(add_zero_attn=True) — one extra never-masked key with score 0
  *              and value 0 (torch/nn/functional.py:6585-6602), handled analytically
- *   score_bias (or NULL): fp32 [B,H,Nq,bias_ld] added to the scores before masking, rows padded to a
+ *   score_bias (or NULL): fp32 [B,H,Nq,bias_ld], log2 domain, added to the scores before masking, rows padded to a
  *              multiple of 128 keys — the spatial term of MultiHeadAttentionSpatial 'mul'
  *              (modules/layers/transformers.py:231-233), produced by pq3d_spatial_bias.
  * Replaces torch/nn/functional.py:6630-6647 as called from CrossAttentionLayer.forward_post
@@ -73,12 +77,12 @@ int pq3d_attention_fwd(int n_mem, const void* Q, int64_t ldq, int64_t q_mem_stri
                        const void* const* Vt, const int64_t* ldvt, const int64_t* vt_row0, const int64_t* vt_rows,
                        const int32_t* S, const int32_t* S_pitch, const int32_t* Vt_pitch,
                        const uint32_t* const* mask_bits, const int64_t* mask_b_stride,
-                       const int64_t* mask_h_stride, const int64_t* mask_q_stride,
+                       const int64_t* mask_h_stride, const int64_t* mask_q_stride, const int32_t* const* kv_tiles,
                        void* O, int64_t ldo, int64_t o_mem_stride, int B, int H, int Nq, int zero_attn,
                        const float* score_bias, int64_t bias_ld, void* stream);
 
 /* Score bias of MultiHeadAttentionSpatial 'mul' for L layers at once:
- * out[l,b,h,n,m] = log(max(relu(pairwise_locs[b,n,m,:] · loc_w[l,h,:] + loc_b[l,h]), 1e-6)), rows padded to ld
+ * out[l,b,h,n,m] = log2(max(relu(pairwise_locs[b,n,m,:] · loc_w[l,h,:] + loc_b[l,h]), 1e-6)), rows padded to ld
  * (pad columns are left untouched).  Replaces modules/layers/transformers.py:196-199,231-232. */
 int pq3d_spatial_bias(const float* pairwise_locs, const float* loc_w, const float* loc_b, float* out, int L, int B,
                       int H, int N, int64_t ld, void* stream);
@@ -102,9 +106,11 @@ int pq3d_add_layernorm(const float* y, int64_t y_group_stride, const float* resi
 /* bits[row, w] packs mask[row, 32w .. 32w+31] (1 = ignore), W = 4*ceil(S/128) words per row, bits past S set.
  * unmask_full_rows: rows that are entirely masked become entirely visible
  * (`attn_mask[attn_mask.all(-1)] = False`, modules/grounding/query_encoder.py:83); mask_fixed (optional,
- * [rows,S]) receives the bool mask after that fix-up. */
+ * [rows,S]) receives the bool mask after that fix-up.  active_tiles (optional, int32 [rows/rows_per_batch]) receives,
+ * per batch entry, the number of leading 128-key tiles that contain a visible key for at least one of its rows —
+ * pq3d_attention_fwd skips the rest (trailing padding of ragged scenes). */
 int pq3d_pack_mask(const uint8_t* mask, uint32_t* bits, int64_t rows, int S, int unmask_full_rows,
-                   uint8_t* mask_fixed, void* stream);
+                   uint8_t* mask_fixed, int32_t* active_tiles, int64_t rows_per_batch, void* stream);
 
 /* mask_logits[b,s,n] = raw[b,s,n] / (#memories valid at (b,s) + 1e-8), -1e6 where seg_masks[b,s];
  * attn_mask[b,n,s] = sigmoid(mask_logits[b,s,n]) < 0.5.  mem_masks_dev: device array of n_mem device

@@ -7,23 +7,30 @@
 // softmax(log(clamp(relu(W5 . pairwise_locs + b), 1e-6)) + q.k/sqrt(dh)); the bias tensor comes from
 // pq3d_spatial_bias).
 //
-// Inputs are already projected: Q (pre-scaled by 1/sqrt(dh)), K as [token, feature] and V TRANSPOSED
-// as [feature, token] (the projection GEMM writes V^T directly by swapping its operands), so every
-// MMA operand is K-major and TMA-loadable with the 128-byte swizzle.
+// Inputs are already projected: Q pre-scaled by log2(e)/sqrt(dh) — scores live in the log2 domain so
+// a probability is one ex2 —, K as [token, feature] and V TRANSPOSED as [feature, token] (the
+// projection GEMM writes V^T directly by swapping its operands), so every MMA operand is K-major and
+// TMA-loadable with the 128-byte swizzle.
 //
 // One CTA = (head, scene, memory, 128-query tile).  576 threads:
 //   warp 0      TMA producer: Q tile once, then K / K + V^T tiles of 128 keys into a 3-stage ring
 //   warp 1      tcgen05.mma issuer: S = Q K^T (128x128, fp32 in TMEM, double-buffered),
 //               O += P V (128x64 in TMEM); P comes from shared memory (bf16, swizzled K-major)
 //   warps 2..17 softmax: 16 warps, four per TMEM lane quadrant, each owning one 32-key column chunk
-//               of every 128-key tile for its 32 query rows (TMEM lane = row): pass 1 partial row
-//               maxima, pass 2 p = exp2((s - m) log2e), partial row sums, P tiles; partials are
-//               combined through shared memory once per pass; finalize with the analytic zero-attn
-//               column (score 0, value 0: denominator += exp(-m), m >= 0) and store O as bf16.
-// Two passes over K instead of an online-softmax rescale of O: N <= 128 queries per CTA make the
-// second QK^T cheap on the tensor pipe, and O never needs a TMEM read-modify-write.  Memories of at
-// most 256 keys (the language prompt, the query self-attention) keep both score tiles resident in
-// TMEM, so their QK^T runs once and pass 2 re-reads it.
+//               of every 128-key tile for its 32 query rows (TMEM lane = row); per-row partials are
+//               combined through shared memory once per pass.
+// Three schedules:
+//   ONE_PASS   (add_zero_attn, > 256 keys — the scene memories): the zero-attn key pins a score of 0
+//              into every row, so 0 is a natural softmax reference: p = ex2(s) with NO running max, no
+//              rescale of O and a single sweep over K/V.  Scores far below 0 underflow to the weight
+//              they deserve next to the zero-attn key; only very large scores could overflow, which is
+//              detected on the row sums (l > 2^100) and then the CTA redoes the tile loop as TWO_PASS.
+//   TWO_PASS   row maxima first (QK^T only), then p = ex2(s - m), row sums and PV.  N <= 128 queries
+//              per CTA make the second QK^T cheap on the tensor pipe and O never needs a rescale.
+//   RESIDENT   memories of <= 256 keys (language prompt, query self-attention): both score tiles stay
+//              in TMEM, QK^T runs once and the second sweep re-reads them.
+// add_zero_attn is analytic everywhere: the extra key has score 0 and value 0, so it only adds
+// ex2(0 - m) to the denominator; fully masked rows give exactly 0, never NaN.
 // Masks arrive bit-packed (1 = ignore), one word per 32 keys; key-padding masks broadcast over rows
 // with a zero row stride.  Bits past S are set by the packer.
 #include <cstring>
@@ -40,6 +47,8 @@ constexpr int kKvTile = 128;
 constexpr int kKvStages = 3;
 constexpr int kHeadDim = 64;
 
+enum AttnMode : int { kResident = 0, kTwoPass = 1, kOnePass = 2 };
+
 struct AttnMaps {
   CUtensorMap q;
   CUtensorMap k[kMaxMem];
@@ -48,6 +57,7 @@ struct AttnMaps {
 
 struct AttnMem {
   const uint32_t* mask_bits;  // may be null (nothing masked; tail handled by S)
+  const int32_t* kv_tiles;    // optional [B]: number of leading 128-key tiles that hold a visible key
   int64_t mask_b_stride, mask_h_stride, mask_q_stride;  // in 32-bit words
   int32_t S;
   int32_t k_col0;
@@ -62,7 +72,8 @@ struct AttnParams {
   int32_t q_mem_stride;
   int32_t B, H, Nq, q_tiles;
   int32_t zero_attn;
-  const float* score_bias;     // [B, H, Nq, bias_ld] fp32 added to the scores, or null
+  int32_t force_two_pass;      // testing hook: never take the ONE_PASS schedule
+  const float* score_bias;     // [B, H, Nq, bias_ld] fp32 (log2 domain) added to the scores, or null
   int64_t bias_ld;
   unsigned long long* dbg;
 };
@@ -71,6 +82,7 @@ constexpr int kQBytes = 128 * kHeadDim * 2;           // 16 KB
 constexpr int kKBytes = kKvTile * kHeadDim * 2;       // 16 KB
 constexpr int kVBytes = kHeadDim * kKvTile * 2;       // 16 KB (two [64 x 64] boxes)
 constexpr int kPBytes = 128 * kKvTile * 2;            // 32 KB (two [128 x 64] swizzle-atom columns)
+constexpr int kNumBars = 1 + 2 * kKvStages + 8 + 1;   // q_full, kv_full/empty, s_full/empty, p_full/empty, o_full
 constexpr int kAttnSmem = kQBytes + kKvStages * (kKBytes + kVBytes) + 2 * kPBytes + 256 + 2048 /*row partials*/;
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -79,32 +91,307 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
+struct AttnCtx {
+  uint8_t *sQ, *sKV, *sP;
+  uint64_t *q_full, *kv_full, *kv_empty, *s_full, *s_empty, *p_full, *p_empty, *o_full;
+  float* s_part;
+  uint32_t tmem_S0, tmem_O;
+  int h, b, mi, qt, T;
+};
+
+__device__ __forceinline__ void init_barriers(const AttnCtx& c) {
+  mbar_init(c.q_full, 1);
+  for (int s = 0; s < kKvStages; ++s) {
+    mbar_init(&c.kv_full[s], 1);
+    mbar_init(&c.kv_empty[s], 1);
+  }
+  for (int i = 0; i < 2; ++i) {
+    mbar_init(&c.s_full[i], 1);
+    mbar_init(&c.s_empty[i], kSoftmaxWarps);
+    mbar_init(&c.p_full[i], kSoftmaxWarps);
+    mbar_init(&c.p_empty[i], 1);
+  }
+  mbar_init(c.o_full, 1);
+  fence_mbar_init();
+}
+
+// ---------------------------------------------------------------------------------------------------
+// TMA producer (one elected lane)
+// ---------------------------------------------------------------------------------------------------
+template <int MODE>
+__device__ __forceinline__ void attn_producer(const AttnMaps& maps, const AttnParams& p, const AttnMem& mem,
+                                              const AttnCtx& c) {
+  mbar_arrive_expect_tx(c.q_full, kQBytes);
+  tma_load_3d(c.sQ, &maps.q, c.q_full, c.mi * p.q_mem_stride + c.h * kHeadDim, c.qt * 128, c.b);
+  int it = 0;
+  for (int pass = (MODE == kTwoPass ? 0 : 1); pass < 2; ++pass) {
+    for (int t = 0; t < c.T; ++t, ++it) {
+      const int s = it % kKvStages;
+      mbar_wait(&c.kv_empty[s], ((it / kKvStages) & 1) ^ 1, 100 + s);
+      uint8_t* sk = c.sKV + s * (kKBytes + kVBytes);
+      mbar_arrive_expect_tx(&c.kv_full[s], pass == 0 ? kKBytes : kKBytes + kVBytes);
+      tma_load_3d(sk, &maps.k[c.mi], &c.kv_full[s], mem.k_col0 + c.h * kHeadDim, t * kKvTile, c.b);
+      if (pass == 1) {
+        tma_load_3d(sk + kKBytes, &maps.vt[c.mi], &c.kv_full[s], t * kKvTile, c.b, mem.vt_row0 + c.h * kHeadDim);
+        tma_load_3d(sk + kKBytes + kVBytes / 2, &maps.vt[c.mi], &c.kv_full[s], t * kKvTile + 64, c.b,
+                    mem.vt_row0 + c.h * kHeadDim);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// MMA issuer (one elected lane)
+// ---------------------------------------------------------------------------------------------------
+template <int MODE>
+__device__ __forceinline__ void attn_mma(const AttnCtx& c) {
+  constexpr uint32_t idesc_s = umma_idesc_bf16(128, kKvTile);
+  constexpr uint32_t idesc_o = umma_idesc_bf16(128, kHeadDim);
+  const uint32_t q_addr = smem_u32(c.sQ);
+  int it = 0, g = 0;
+  auto issue_s = [&](bool release_kv) {
+    const int s = it % kKvStages;
+    mbar_wait(&c.kv_full[s], (it / kKvStages) & 1, 200 + s);
+    const int sb = g & 1;
+    if (MODE != kResident) mbar_wait(&c.s_empty[sb], ((g >> 1) & 1) ^ 1, 210 + sb);
+    tc_fence_after();
+    const uint32_t k_addr = smem_u32(c.sKV + s * (kKBytes + kVBytes));
+#pragma unroll
+    for (int k = 0; k < kHeadDim / 16; ++k)
+      umma_ss(c.tmem_S0 + sb * kKvTile, umma_desc_k_sw128(q_addr + k * 32), umma_desc_k_sw128(k_addr + k * 32),
+              idesc_s, k != 0 ? 1u : 0u);
+    if (release_kv) tc_commit(&c.kv_empty[s]);
+    tc_commit(&c.s_full[sb]);
+    ++it;
+    ++g;
+  };
+  auto issue_pv = [&](int t, int ring_pos) {
+    const int pb = t & 1;
+    mbar_wait(&c.p_full[pb], (t >> 1) & 1, 230 + pb);
+    tc_fence_after();
+    const int s = ring_pos % kKvStages;
+    const uint32_t v_addr = smem_u32(c.sKV + s * (kKBytes + kVBytes) + kKBytes);
+    const uint32_t p_addr = smem_u32(c.sP + pb * kPBytes);
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        umma_ss(c.tmem_O, umma_desc_k_sw128(p_addr + j * (kPBytes / 2) + k * 32),
+                umma_desc_k_sw128(v_addr + j * (kVBytes / 2) + k * 32), idesc_o, (t | j | k) != 0 ? 1u : 0u);
+    }
+    tc_commit(&c.kv_empty[s]);
+    tc_commit(&c.p_empty[pb]);
+  };
+  mbar_wait(c.q_full, 0, 220);
+  if (MODE == kResident) {
+    for (int t = 0; t < c.T; ++t) issue_s(false);           // scores once, both tiles stay in TMEM
+    for (int t = 0; t < c.T; ++t) issue_pv(t, t);
+  } else {
+    if (MODE == kTwoPass)
+      for (int t = 0; t < c.T; ++t) issue_s(true);          // pass 1: scores only
+    const int it2 = it;                                     // ring position of the PV sweep's tile 0
+    issue_s(false);
+    for (int t = 0; t < c.T; ++t) {
+      if (t + 1 < c.T) issue_s(false);                      // keep one QK^T ahead of the softmax
+      issue_pv(t, it2 + t);
+    }
+  }
+  tc_commit(c.o_full);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// softmax warps.  Returns true when the ONE_PASS row sums overflowed their safe range.
+// ---------------------------------------------------------------------------------------------------
+template <int MODE>
+__device__ __forceinline__ bool attn_softmax(const AttnParams& p, const AttnMem& mem, const AttnCtx& c, int warp,
+                                             unsigned long long* dbg) {
+  const int quad = warp & 3;
+  const int cc = (warp - 2) >> 2;               // which 32-key chunk of every tile this warp owns
+  const int r = quad * 32 + lane_id();          // row in the query tile == TMEM lane
+  const int n = c.qt * 128 + r;                 // query index in the scene
+  const int n_c = n < p.Nq ? n : p.Nq - 1;      // clamped for reads
+  const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
+  const uint32_t* mrow = mem.mask_bits == nullptr ? nullptr
+                                                  : mem.mask_bits + c.b * mem.mask_b_stride +
+                                                        c.h * mem.mask_h_stride + n_c * mem.mask_q_stride;
+  const float* brow = p.score_bias == nullptr
+                          ? nullptr
+                          : p.score_bias + ((static_cast<int64_t>(c.b) * p.H + c.h) * p.Nq + n_c) * p.bias_ld;
+  const float kNegInf = __int_as_float(0xff800000);
+
+  auto mask_word = [&](int t) -> uint32_t {
+    if (mrow != nullptr) return __ldg(mrow + t * 4 + cc);
+    const int rem = mem.S - (t * kKvTile + cc * 32);       // no mask tensor: only the tail past S is ignored
+    return rem >= 32 ? 0u : (rem <= 0 ? 0xffffffffu : (0xffffffffu << rem));
+  };
+  // this warp's 32 scores of tile t (buffer sb): TMEM -> registers (+ bias); masked keys -> -inf.
+  // The select is skipped when no lane of the warp has a masked key in this chunk (the common case).
+  auto load_scores = [&](int t, int sb, uint32_t word, float (&sc)[32]) {
+    uint32_t acc[32];
+    tmem_ld_32x32(c.tmem_S0 + sb * kKvTile + lane_off + cc * 32, acc);
+    const bool any_masked = __any_sync(0xffffffffu, word != 0u);
+    if (brow != nullptr) {
+      const float4* b4 = reinterpret_cast<const float4*>(brow + t * kKvTile + cc * 32);
+      float bias[32];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 v = __ldg(b4 + j);
+        bias[4 * j] = v.x; bias[4 * j + 1] = v.y; bias[4 * j + 2] = v.z; bias[4 * j + 3] = v.w;
+      }
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) sc[j] = __uint_as_float(acc[j]) + bias[j];
+    } else {
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) sc[j] = __uint_as_float(acc[j]);
+    }
+    if (any_masked) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) sc[j] = ((word >> j) & 1u) ? kNegInf : sc[j];
+    }
+  };
+  auto release_scores = [&](int sb) {
+    tc_fence_before();
+    __syncwarp();
+    if (lane_id() == 0) mbar_arrive(&c.s_empty[sb]);
+  };
+  auto write_probs = [&](int pb, const float (&pr)[32]) {
+    uint8_t* prow = c.sP + pb * kPBytes + r * 128;
+#pragma unroll
+    for (int q4 = 0; q4 < 4; ++q4) {
+      uint4 u;
+      u.x = pack_bf16x2(pr[q4 * 8 + 0], pr[q4 * 8 + 1]);
+      u.y = pack_bf16x2(pr[q4 * 8 + 2], pr[q4 * 8 + 3]);
+      u.z = pack_bf16x2(pr[q4 * 8 + 4], pr[q4 * 8 + 5]);
+      u.w = pack_bf16x2(pr[q4 * 8 + 6], pr[q4 * 8 + 7]);
+      const int ci = cc * 4 + q4;                // 16-byte chunk index along the 128 keys
+      const int atom = ci >> 3, c8 = ci & 7;     // swizzle-atom column, chunk inside its 128-B row
+      *reinterpret_cast<uint4*>(prow + atom * (kPBytes / 2) + ((c8 ^ (r & 7)) << 4)) = u;
+    }
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane_id() == 0) mbar_arrive(&c.p_full[pb]);
+  };
+
+  int g = 0;
+  float m = 0.f;                                 // ONE_PASS: the zero-attn score is the reference
+  if (MODE != kOnePass) {
+    float m_run = kNegInf;
+    for (int t = 0; t < c.T; ++t, ++g) {         // ---- sweep 1: row maxima (partial: this warp's columns)
+      const int sb = g & 1;
+      const uint32_t word = mask_word(t);
+      mbar_wait(&c.s_full[sb], (g >> 1) & 1, 300 + sb);
+      tc_fence_after();
+      float sc[32];
+      load_scores(t, sb, word, sc);
+      if (MODE == kTwoPass) release_scores(sb);  // values are in registers: free the buffer early
+#pragma unroll
+      for (int j = 0; j < 32; ++j) m_run = fmaxf(m_run, sc[j]);
+    }
+    c.s_part[cc * 128 + r] = m_run;
+    asm volatile("bar.sync 1, 512;" ::: "memory");
+    m_run = fmaxf(fmaxf(c.s_part[r], c.s_part[128 + r]), fmaxf(c.s_part[256 + r], c.s_part[384 + r]));
+    asm volatile("bar.sync 1, 512;" ::: "memory");        // s_part is reused for the row sums
+    m = p.zero_attn ? fmaxf(m_run, 0.f) : m_run;
+    if (m == kNegInf) m = 0.f;
+    if (MODE == kResident) g = 0;                // sweep 2 re-reads the resident score tiles
+  }
+  if (dbg != nullptr && threadIdx.x == 64) dbg[2] = clock64();
+  float l = 0.f;
+  for (int t = 0; t < c.T; ++t, ++g) {           // ---- probabilities, row sums, P tiles
+    const int sb = g & 1;
+    const int pb = t & 1;
+    const uint32_t word = mask_word(t);
+    if (MODE != kResident) {
+      mbar_wait(&c.s_full[sb], (g >> 1) & 1, 310 + sb);
+      tc_fence_after();
+    }
+    float sc[32];
+    load_scores(t, sb, word, sc);
+    if (MODE != kResident) release_scores(sb);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      sc[j] = ex2_approx(MODE == kOnePass ? sc[j] : sc[j] - m);    // ex2(-inf) = 0 for masked keys
+      l += sc[j];
+    }
+    mbar_wait(&c.p_empty[pb], ((t >> 1) & 1) ^ 1, 320 + pb);
+    write_probs(pb, sc);
+  }
+  if (dbg != nullptr && threadIdx.x == 64) dbg[3] = clock64();
+  // ---- finalize: combine the partial row sums, zero-attn column, normalise, store
+  c.s_part[cc * 128 + r] = l;
+  asm volatile("bar.sync 1, 512;" ::: "memory");
+  l = (c.s_part[r] + c.s_part[128 + r]) + (c.s_part[256 + r] + c.s_part[384 + r]);
+  const bool overflow = (MODE == kOnePass) && !(l < 1.2676506e30f);   // 2^100; also catches inf / NaN
+  if (p.zero_attn) l += ex2_approx(-m);
+  const float inv = 1.f / l;
+  mbar_wait(c.o_full, 0, 330);
+  tc_fence_after();
+  if (cc < 2) {                                  // 64 output columns: two of the four warps per quadrant
+    __nv_bfloat16* orow =
+        p.O + c.mi * p.o_mem_stride + (static_cast<int64_t>(c.b) * p.Nq + n_c) * p.ldo + c.h * kHeadDim;
+    uint32_t acc[32];
+    tmem_ld_32x32(c.tmem_O + lane_off + cc * 32, acc);
+    tmem_ld_wait();
+    if (n < p.Nq) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) {
+        uint4 u;
+        u.x = pack_bf16x2(__uint_as_float(acc[j]) * inv, __uint_as_float(acc[j + 1]) * inv);
+        u.y = pack_bf16x2(__uint_as_float(acc[j + 2]) * inv, __uint_as_float(acc[j + 3]) * inv);
+        u.z = pack_bf16x2(__uint_as_float(acc[j + 4]) * inv, __uint_as_float(acc[j + 5]) * inv);
+        u.w = pack_bf16x2(__uint_as_float(acc[j + 6]) * inv, __uint_as_float(acc[j + 7]) * inv);
+        *reinterpret_cast<uint4*>(orow + cc * 32 + j) = u;
+      }
+    }
+  }
+  tc_fence_before();
+  if (dbg != nullptr && threadIdx.x == 64) dbg[4] = clock64();
+  return overflow && n < p.Nq;
+}
+
+template <int MODE>
+__device__ __forceinline__ bool attn_run(const AttnMaps& maps, const AttnParams& p, const AttnMem& mem,
+                                         const AttnCtx& c, int warp, unsigned long long* dbg) {
+  bool overflow = false;
+  if (warp == 0) {
+    if (elect_one()) attn_producer<MODE>(maps, p, mem, c);
+  } else if (warp == 1) {
+    if (elect_one()) attn_mma<MODE>(c);
+  } else {
+    overflow = attn_softmax<MODE>(p, mem, c, warp, dbg);
+  }
+  return overflow;
+}
+
 __global__ void __launch_bounds__(kAttnThreads, 1)
 attention_fwd_kernel(const __grid_constant__ AttnMaps maps, const AttnParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t* sQ = smem;
-  uint8_t* sKV = sQ + kQBytes;
-  uint8_t* sP = sKV + kKvStages * (kKBytes + kVBytes);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * kPBytes);
-  uint64_t* q_full = bars;
-  uint64_t* kv_full = bars + 1;
-  uint64_t* kv_empty = kv_full + kKvStages;
-  uint64_t* s_full = kv_empty + kKvStages;
-  uint64_t* s_empty = s_full + 2;
-  uint64_t* p_full = s_empty + 2;
-  uint64_t* p_empty = p_full + 2;
-  uint64_t* o_full = p_empty + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
-  float* s_part = reinterpret_cast<float*>(sP + 2 * kPBytes + 256);   // [4 column chunks][128 rows]
+  AttnCtx c;
+  c.sQ = smem;
+  c.sKV = c.sQ + kQBytes;
+  c.sP = c.sKV + kKvStages * (kKBytes + kVBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(c.sP + 2 * kPBytes);
+  c.q_full = bars;
+  c.kv_full = bars + 1;
+  c.kv_empty = c.kv_full + kKvStages;
+  c.s_full = c.kv_empty + kKvStages;
+  c.s_empty = c.s_full + 2;
+  c.p_full = c.s_empty + 2;
+  c.p_empty = c.p_full + 2;
+  c.o_full = c.p_empty + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(c.o_full + 1);
+  uint32_t* redo_flag = tmem_slot + 1;
+  c.s_part = reinterpret_cast<float*>(c.sP + 2 * kPBytes + 256);   // [4 column chunks][128 rows]
 
   const int warp = threadIdx.x >> 5;
-  const int h = blockIdx.x;
-  const int b = blockIdx.y;
-  const int mi = blockIdx.z / p.q_tiles;
-  const int qt = blockIdx.z % p.q_tiles;
-  const AttnMem& mem = p.mem[mi];
-  const int T = (mem.S + kKvTile - 1) / kKvTile;
-  const bool resident = T <= 2;   // all score tiles fit the two TMEM buffers: one QK^T pass
+  c.h = blockIdx.x;
+  c.b = blockIdx.y;
+  c.mi = blockIdx.z / p.q_tiles;
+  c.qt = blockIdx.z % p.q_tiles;
+  const AttnMem& mem = p.mem[c.mi];
+  c.T = (mem.S + kKvTile - 1) / kKvTile;
 
   if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) {
     printf("pq3d: dynamic shared memory is not 1024-byte aligned\n");
@@ -112,30 +399,23 @@ attention_fwd_kernel(const __grid_constant__ AttnMaps maps, const AttnParams p) 
   }
   if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&maps.q);
-    tma_prefetch_desc(&maps.k[mi]);
-    tma_prefetch_desc(&maps.vt[mi]);
-    mbar_init(q_full, 1);
-    for (int s = 0; s < kKvStages; ++s) {
-      mbar_init(&kv_full[s], 1);
-      mbar_init(&kv_empty[s], 1);
-    }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&s_full[i], 1);
-      mbar_init(&s_empty[i], kSoftmaxWarps);
-      mbar_init(&p_full[i], kSoftmaxWarps);
-      mbar_init(&p_empty[i], 1);
-    }
-    mbar_init(o_full, 1);
-    fence_mbar_init();
+    tma_prefetch_desc(&maps.k[c.mi]);
+    tma_prefetch_desc(&maps.vt[c.mi]);
+    init_barriers(c);
+    *redo_flag = 0;
   }
   if (warp == 1) tmem_alloc<512>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_S0 = tmem_base;        // columns [0,128) and [128,256): S double buffer
-  const uint32_t tmem_O = tmem_base + 256;   // columns [256,320): O
+  c.tmem_S0 = tmem_base;        // columns [0,128) and [128,256): S double buffer
+  c.tmem_O = tmem_base + 256;   // columns [256,320): O
   pdl_sync();
+  if (mem.kv_tiles != nullptr) {          // ragged scenes: skip the trailing tiles that are padding for every query
+    const int act = __ldg(mem.kv_tiles + c.b);
+    c.T = act < 1 ? 1 : (act < c.T ? act : c.T);
+  }
   unsigned long long* dbg =
       p.dbg == nullptr ? nullptr : p.dbg + 8ull * (blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z));
   if (dbg != nullptr && threadIdx.x == 64) {
@@ -143,217 +423,25 @@ attention_fwd_kernel(const __grid_constant__ AttnMaps maps, const AttnParams p) 
     dbg[1] = clock64();
   }
 
-  if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
-    if (elect_one()) {
-      mbar_arrive_expect_tx(q_full, kQBytes);
-      tma_load_3d(sQ, &maps.q, q_full, mi * p.q_mem_stride + h * kHeadDim, qt * 128, b);
-      int it = 0;
-      for (int pass = resident ? 1 : 0; pass < 2; ++pass) {
-        for (int t = 0; t < T; ++t, ++it) {
-          const int s = it % kKvStages;
-          mbar_wait(&kv_empty[s], ((it / kKvStages) & 1) ^ 1, 100 + s);
-          uint8_t* sk = sKV + s * (kKBytes + kVBytes);
-          mbar_arrive_expect_tx(&kv_full[s], pass == 0 ? kKBytes : kKBytes + kVBytes);
-          tma_load_3d(sk, &maps.k[mi], &kv_full[s], mem.k_col0 + h * kHeadDim, t * kKvTile, b);
-          if (pass == 1) {
-            tma_load_3d(sk + kKBytes, &maps.vt[mi], &kv_full[s], t * kKvTile, b, mem.vt_row0 + h * kHeadDim);
-            tma_load_3d(sk + kKBytes + kVBytes / 2, &maps.vt[mi], &kv_full[s], t * kKvTile + 64, b,
-                        mem.vt_row0 + h * kHeadDim);
-          }
-        }
+  if (c.T <= 2) {
+    attn_run<kResident>(maps, p, mem, c, warp, dbg);
+  } else if (p.zero_attn && !p.force_two_pass) {
+    if (attn_run<kOnePass>(maps, p, mem, c, warp, dbg)) *redo_flag = 1;   // benign race: all writers store 1
+    __syncthreads();                       // every pipeline of the first attempt has drained
+    if (*redo_flag != 0) {                 // some row sum left the safe range: redo with running maxima
+      if (threadIdx.x == 0) {
+        for (int i = 0; i < kNumBars; ++i)
+          asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(&bars[i])) : "memory");
+        init_barriers(c);
       }
-    }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (elect_one()) {
-      constexpr uint32_t idesc_s = umma_idesc_bf16(128, kKvTile);
-      constexpr uint32_t idesc_o = umma_idesc_bf16(128, kHeadDim);
-      const uint32_t q_addr = smem_u32(sQ);
-      int it = 0, g = 0;
-      auto issue_s = [&](bool release_kv) {
-        const int s = it % kKvStages;
-        mbar_wait(&kv_full[s], (it / kKvStages) & 1, 200 + s);
-        const int sb = g & 1;
-        if (!resident) mbar_wait(&s_empty[sb], ((g >> 1) & 1) ^ 1, 210 + sb);
-        tc_fence_after();
-        const uint32_t k_addr = smem_u32(sKV + s * (kKBytes + kVBytes));
-#pragma unroll
-        for (int k = 0; k < kHeadDim / 16; ++k)
-          umma_ss(tmem_S0 + sb * kKvTile, umma_desc_k_sw128(q_addr + k * 32), umma_desc_k_sw128(k_addr + k * 32),
-                  idesc_s, k != 0 ? 1u : 0u);
-        if (release_kv) tc_commit(&kv_empty[s]);
-        tc_commit(&s_full[sb]);
-        ++it;
-        ++g;
-      };
-      auto issue_pv = [&](int t, int ring_pos) {
-        const int pb = t & 1;
-        mbar_wait(&p_full[pb], (t >> 1) & 1, 230 + pb);
-        tc_fence_after();
-        const int s = ring_pos % kKvStages;
-        const uint32_t v_addr = smem_u32(sKV + s * (kKBytes + kVBytes) + kKBytes);
-        const uint32_t p_addr = smem_u32(sP + pb * kPBytes);
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_ss(tmem_O, umma_desc_k_sw128(p_addr + j * (kPBytes / 2) + k * 32),
-                    umma_desc_k_sw128(v_addr + j * (kVBytes / 2) + k * 32), idesc_o, (t | j | k) != 0 ? 1u : 0u);
-        }
-        tc_commit(&kv_empty[s]);
-        tc_commit(&p_empty[pb]);
-      };
-      mbar_wait(q_full, 0, 220);
-      if (resident) {
-        for (int t = 0; t < T; ++t) issue_s(false);           // scores once, both tiles stay in TMEM
-        for (int t = 0; t < T; ++t) issue_pv(t, t);
-      } else {
-        for (int t = 0; t < T; ++t) issue_s(true);            // pass 1: scores only
-        const int it2 = it;                                   // ring position of pass-2 tile 0
-        issue_s(false);
-        for (int t = 0; t < T; ++t) {
-          if (t + 1 < T) issue_s(false);
-          issue_pv(t, it2 + t);
-        }
-      }
-      tc_commit(o_full);
+      tc_fence_before();
+      __syncthreads();
+      tc_fence_after();
+      attn_run<kTwoPass>(maps, p, mem, c, warp, dbg);
+      if (dbg != nullptr && threadIdx.x == 64) dbg[6] = 1;
     }
   } else {
-    // ------------------------------------------------------------------ softmax warps
-    const int quad = warp & 3;
-    const int cc = (warp - 2) >> 2;               // which 32-key chunk of every tile this warp owns
-    const int r = quad * 32 + lane_id();          // row in the query tile == TMEM lane
-    const int n = qt * 128 + r;                   // query index in the scene
-    const int n_c = n < p.Nq ? n : p.Nq - 1;      // clamped for reads
-    const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
-    const uint32_t* mrow = mem.mask_bits == nullptr
-                               ? nullptr
-                               : mem.mask_bits + b * mem.mask_b_stride + h * mem.mask_h_stride + n_c * mem.mask_q_stride;
-    const float* brow = p.score_bias == nullptr
-                            ? nullptr
-                            : p.score_bias + ((static_cast<int64_t>(b) * p.H + h) * p.Nq + n_c) * p.bias_ld;
-    constexpr float kLog2e = 1.4426950408889634f;
-    const float kNegInf = __int_as_float(0xff800000);
-
-    auto mask_word = [&](int t) -> uint32_t {
-      if (mrow != nullptr) return __ldg(mrow + t * 4 + cc);
-      const int rem = mem.S - (t * kKvTile + cc * 32);       // no mask tensor: only the tail past S is ignored
-      return rem >= 32 ? 0u : (rem <= 0 ? 0xffffffffu : (0xffffffffu << rem));
-    };
-    // this warp's 32 scores of tile t (buffer sb): TMEM -> registers, + bias, masked -> -inf
-    auto load_scores = [&](int t, int sb, uint32_t word, float (&sc)[32]) {
-      uint32_t acc[32];
-      tmem_ld_32x32(tmem_S0 + sb * kKvTile + lane_off + cc * 32, acc);
-      if (brow != nullptr) {
-        const float4* b4 = reinterpret_cast<const float4*>(brow + t * kKvTile + cc * 32);
-        float bias[32];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float4 v = __ldg(b4 + j);
-          bias[4 * j] = v.x; bias[4 * j + 1] = v.y; bias[4 * j + 2] = v.z; bias[4 * j + 3] = v.w;
-        }
-        tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 32; ++j) sc[j] = ((word >> j) & 1u) ? kNegInf : __uint_as_float(acc[j]) + bias[j];
-      } else {
-        tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 32; ++j) sc[j] = ((word >> j) & 1u) ? kNegInf : __uint_as_float(acc[j]);
-      }
-    };
-
-    int g = 0;
-    float m_run = kNegInf;
-    for (int t = 0; t < T; ++t, ++g) {  // ---- pass 1: row maxima (partial: this warp's columns)
-      const int sb = g & 1;
-      const uint32_t word = mask_word(t);
-      mbar_wait(&s_full[sb], (g >> 1) & 1, 300 + sb);
-      tc_fence_after();
-      float sc[32];
-      load_scores(t, sb, word, sc);
-      if (!resident) {
-        tc_fence_before();
-        __syncwarp();
-        if (lane_id() == 0) mbar_arrive(&s_empty[sb]);     // values are in registers: release the buffer early
-      }
-#pragma unroll
-      for (int j = 0; j < 32; ++j) m_run = fmaxf(m_run, sc[j]);
-    }
-    s_part[cc * 128 + r] = m_run;
-    asm volatile("bar.sync 1, 512;" ::: "memory");
-    m_run = fmaxf(fmaxf(s_part[r], s_part[128 + r]), fmaxf(s_part[256 + r], s_part[384 + r]));
-    asm volatile("bar.sync 1, 512;" ::: "memory");        // s_part is reused for the row sums
-    if (dbg != nullptr && threadIdx.x == 64) dbg[2] = clock64();
-    const float m = p.zero_attn ? fmaxf(m_run, 0.f) : m_run;
-    const float m_l2 = (m == kNegInf ? 0.f : m) * kLog2e;
-    float l = 0.f;
-    if (resident) g = 0;                 // pass 2 re-reads the resident score tiles
-    for (int t = 0; t < T; ++t, ++g) {  // ---- pass 2: probabilities
-      const int sb = g & 1;
-      const int pb = t & 1;
-      const uint32_t word = mask_word(t);
-      if (!resident) {
-        mbar_wait(&s_full[sb], (g >> 1) & 1, 310 + sb);
-        tc_fence_after();
-      }
-      float sc[32];
-      load_scores(t, sb, word, sc);
-      if (!resident) {
-        tc_fence_before();
-        __syncwarp();
-        if (lane_id() == 0) mbar_arrive(&s_empty[sb]);
-      }
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        sc[j] = ex2_approx(fmaf(sc[j], kLog2e, -m_l2));    // ex2(-inf) = 0 for masked keys
-        l += sc[j];
-      }
-      mbar_wait(&p_empty[pb], ((t >> 1) & 1) ^ 1, 320 + pb);
-      uint8_t* prow = sP + pb * kPBytes + r * 128;
-#pragma unroll
-      for (int q4 = 0; q4 < 4; ++q4) {
-        uint4 u;
-        u.x = pack_bf16x2(sc[q4 * 8 + 0], sc[q4 * 8 + 1]);
-        u.y = pack_bf16x2(sc[q4 * 8 + 2], sc[q4 * 8 + 3]);
-        u.z = pack_bf16x2(sc[q4 * 8 + 4], sc[q4 * 8 + 5]);
-        u.w = pack_bf16x2(sc[q4 * 8 + 6], sc[q4 * 8 + 7]);
-        const int ci = cc * 4 + q4;                // 16-byte chunk index along the 128 keys
-        const int atom = ci >> 3, c8 = ci & 7;     // swizzle-atom column, chunk inside its 128-B row
-        *reinterpret_cast<uint4*>(prow + atom * (kPBytes / 2) + ((c8 ^ (r & 7)) << 4)) = u;
-      }
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane_id() == 0) mbar_arrive(&p_full[pb]);
-    }
-    if (dbg != nullptr && threadIdx.x == 64) dbg[3] = clock64();
-    // ---- finalize: combine the partial row sums, zero-attn column, normalise, store
-    s_part[cc * 128 + r] = l;
-    asm volatile("bar.sync 1, 512;" ::: "memory");
-    l = (s_part[r] + s_part[128 + r]) + (s_part[256 + r] + s_part[384 + r]);
-    if (p.zero_attn) l += ex2_approx(-m_l2);
-    const float inv = 1.f / l;
-    mbar_wait(o_full, 0, 330);
-    tc_fence_after();
-    if (cc < 2) {                                  // 64 output columns: two of the four warps per quadrant
-      __nv_bfloat16* orow = p.O + mi * p.o_mem_stride + (static_cast<int64_t>(b) * p.Nq + n_c) * p.ldo + h * kHeadDim;
-      uint32_t acc[32];
-      tmem_ld_32x32(tmem_O + lane_off + cc * 32, acc);
-      tmem_ld_wait();
-      if (n < p.Nq) {
-#pragma unroll
-        for (int j = 0; j < 32; j += 8) {
-          uint4 u;
-          u.x = pack_bf16x2(__uint_as_float(acc[j]) * inv, __uint_as_float(acc[j + 1]) * inv);
-          u.y = pack_bf16x2(__uint_as_float(acc[j + 2]) * inv, __uint_as_float(acc[j + 3]) * inv);
-          u.z = pack_bf16x2(__uint_as_float(acc[j + 4]) * inv, __uint_as_float(acc[j + 5]) * inv);
-          u.w = pack_bf16x2(__uint_as_float(acc[j + 6]) * inv, __uint_as_float(acc[j + 7]) * inv);
-          *reinterpret_cast<uint4*>(orow + cc * 32 + j) = u;
-        }
-      }
-    }
-    tc_fence_before();
-    if (dbg != nullptr && threadIdx.x == 64) dbg[4] = clock64();
+    attn_run<kTwoPass>(maps, p, mem, c, warp, dbg);
   }
   __syncthreads();
   if (warp == 1) {
@@ -363,8 +451,9 @@ attention_fwd_kernel(const __grid_constant__ AttnMaps maps, const AttnParams p) 
   if (dbg != nullptr && threadIdx.x == 64) dbg[5] = clock64();
 }
 
-// score bias of the spatial self-attention for every layer at once: out[l][b][h][n][m] =
-// log(max(relu(loc[b,n,m,:] . w[l,h,:] + bias[l,h]), 1e-6))   (modules/layers/transformers.py:196-199,231-232)
+// score bias of the spatial self-attention for every layer at once, in the log2 domain:
+// out[l][b][h][n][m] = log2(max(relu(loc[b,n,m,:] . w[l,h,:] + bias[l,h]), 1e-6))
+// (modules/layers/transformers.py:196-199,231-232)
 __global__ void spatial_bias_kernel(const float* __restrict__ locs, const float* __restrict__ w,
                                     const float* __restrict__ bias, float* __restrict__ out, int L, int B, int H, int N,
                                     int ld) {
@@ -381,7 +470,7 @@ __global__ void spatial_bias_kernel(const float* __restrict__ locs, const float*
       const float* wv = w + lh * 5;
       const float v = fmaf(l0, wv[0], fmaf(l1, wv[1], fmaf(l2, wv[2], fmaf(l3, wv[3], fmaf(l4, wv[4], bias[lh])))));
       const int l = lh / H, hh = lh % H;
-      out[(((static_cast<int64_t>(l) * B + b) * H + hh) * N + n) * ld + m] = __logf(fmaxf(fmaxf(v, 0.f), 1e-6f));
+      out[(((static_cast<int64_t>(l) * B + b) * H + hh) * N + n) * ld + m] = __log2f(fmaxf(fmaxf(v, 0.f), 1e-6f));
     }
   }
 }
@@ -391,8 +480,14 @@ __global__ void spatial_bias_kernel(const float* __restrict__ locs, const float*
 using namespace pq3d;
 
 static unsigned long long* g_attn_timeline = nullptr;
+static int g_force_two_pass = 0;
 extern "C" int pq3d_debug_set_attention_timeline(void* buf) {
   g_attn_timeline = reinterpret_cast<unsigned long long*>(buf);
+  return PQ3D_OK;
+}
+// Testing hook: 1 = always use the running-max (two-pass) schedule for long memories.
+extern "C" int pq3d_debug_force_two_pass(int on) {
+  g_force_two_pass = on;
   return PQ3D_OK;
 }
 
@@ -413,7 +508,8 @@ extern "C" int pq3d_attention_fwd(int n_mem, const void* Q, int64_t ldq, int64_t
                                   const int64_t* ldvt, const int64_t* vt_row0, const int64_t* vt_rows,
                                   const int32_t* S, const int32_t* S_pitch, const int32_t* Vt_pitch,
                                   const uint32_t* const* mask_bits, const int64_t* mask_b_stride,
-                                  const int64_t* mask_h_stride, const int64_t* mask_q_stride, void* O, int64_t ldo,
+                                  const int64_t* mask_h_stride, const int64_t* mask_q_stride,
+                                  const int32_t* const* kv_tiles, void* O, int64_t ldo,
                                   int64_t o_mem_stride, int B, int H, int Nq, int zero_attn, const float* score_bias,
                                   int64_t bias_ld, void* stream) {
   PQ3D_CHECK_ARG(n_mem >= 1 && n_mem <= kMaxMem, "pq3d_attention_fwd: n_mem=%d not in [1,%d]", n_mem, kMaxMem);
@@ -463,6 +559,7 @@ extern "C" int pq3d_attention_fwd(int n_mem, const void* Q, int64_t ldq, int64_t
     m.mask_b_stride = mask_bits ? mask_b_stride[i] : 0;
     m.mask_h_stride = mask_bits ? mask_h_stride[i] : 0;
     m.mask_q_stride = mask_bits ? mask_q_stride[i] : 0;
+    m.kv_tiles = kv_tiles ? kv_tiles[i] : nullptr;
     m.S = S[i];
     m.k_col0 = (int32_t)k_col0[i];
     m.vt_row0 = (int32_t)vt_row0[i];
@@ -480,6 +577,7 @@ extern "C" int pq3d_attention_fwd(int n_mem, const void* Q, int64_t ldq, int64_t
   p.Nq = Nq;
   p.q_tiles = (Nq + 127) / 128;
   p.zero_attn = zero_attn;
+  p.force_two_pass = g_force_two_pass;
   p.score_bias = score_bias;
   p.bias_ld = bias_ld;
   p.dbg = g_attn_timeline;

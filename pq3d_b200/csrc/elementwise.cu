@@ -142,8 +142,11 @@ __global__ void add_layernorm_kernel(const float* __restrict__ y, int64_t y_grou
 // (query_encoder.py:83): a query that would see nothing sees everything.  One warp per row.
 // ------------------------------------------------------------------------------------------------
 __global__ void pack_mask_kernel(const uint8_t* __restrict__ mask, uint32_t* __restrict__ bits, int64_t rows, int S,
-                                 int W, int unmask_full_rows, uint8_t* __restrict__ mask_fixed) {
+                                 int W, int unmask_full_rows, uint8_t* __restrict__ mask_fixed,
+                                 int32_t* __restrict__ active_tiles, int64_t rows_per_batch) {
   pdl_sync();
+  __shared__ int s_last;
+  if (threadIdx.x == 0) s_last = 0;
   // one block per row; warp w packs words w, w + nwarps, ...; the all-masked test is a block-wide AND
   const int64_t row = blockIdx.x;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
@@ -155,6 +158,7 @@ __global__ void pack_mask_kernel(const uint8_t* __restrict__ mask, uint32_t* __r
   } else {
     all_masked = 0;
   }
+  int last = 0;   // 1 + index of the last 128-key tile of this row that has a visible key
   for (int w = wid; w < W; w += nw) {
     const int s = w * 32 + lane;
     bool mk = (s < S) ? (src[s] != 0) : true;
@@ -162,6 +166,14 @@ __global__ void pack_mask_kernel(const uint8_t* __restrict__ mask, uint32_t* __r
     const uint32_t word = __ballot_sync(0xffffffffu, mk);
     if (lane == 0) bits[row * W + w] = word;
     if (mask_fixed != nullptr && s < S) mask_fixed[row * S + s] = mk ? 1 : 0;
+    if (word != 0xffffffffu) last = max(last, w / 4 + 1);
+  }
+  if (active_tiles != nullptr) {
+    // trailing fully-masked key tiles (padding of ragged scenes) are skipped by the attention kernel
+    if (!unmask_full_rows) __syncthreads();   // s_last initialised (the fix-up path already synchronised)
+    if (lane == 0 && last > 0) atomicMax(&s_last, last);
+    __syncthreads();
+    if (threadIdx.x == 0 && s_last > 0) atomicMax(&active_tiles[row / rows_per_batch], s_last);
   }
 }
 
@@ -357,12 +369,19 @@ extern "C" int pq3d_add_layernorm(const float* y, int64_t y_group_stride, const 
 }
 
 extern "C" int pq3d_pack_mask(const uint8_t* mask, uint32_t* bits, int64_t rows, int S, int unmask_full_rows,
-                              uint8_t* mask_fixed, void* stream) {
+                              uint8_t* mask_fixed, int32_t* active_tiles, int64_t rows_per_batch, void* stream) {
   PQ3D_CHECK_ARG(mask && bits && rows > 0 && S > 0, "pq3d_pack_mask: bad argument");
+  PQ3D_CHECK_ARG(active_tiles == nullptr || (rows_per_batch > 0 && rows % rows_per_batch == 0),
+                 "pq3d_pack_mask: rows=%lld must be a multiple of rows_per_batch=%lld", (long long)rows,
+                 (long long)rows_per_batch);
+  if (active_tiles != nullptr)
+    PQ3D_CUDA(cudaMemsetAsync(active_tiles, 0, sizeof(int32_t) * (rows / rows_per_batch),
+                              reinterpret_cast<cudaStream_t>(stream)));
   const int W = ((S + 127) / 128) * 4;
   const int threads = S >= 1024 ? 256 : (S >= 256 ? 128 : 32);
   PQ3D_CUDA(launch_kernel(pack_mask_kernel, dim3(static_cast<unsigned>(rows)), dim3(threads), 0,
-                          reinterpret_cast<cudaStream_t>(stream), mask, bits, rows, S, W, unmask_full_rows, mask_fixed));
+                          reinterpret_cast<cudaStream_t>(stream), mask, bits, rows, S, W, unmask_full_rows, mask_fixed,
+                          active_tiles, rows_per_batch));
   return PQ3D_OK;
 }
 

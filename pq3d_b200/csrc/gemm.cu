@@ -188,6 +188,7 @@ linear_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       const bool zero_row = row_ok && p.row_zero != nullptr && p.row_zero[g * p.row_zero_group_stride + m] != 0;
       const float bias_m = (p.bias != nullptr && p.bias_along_m && row_ok) ? p.bias[g * p.bias_group_stride + m] : 0.f;
       const float lo = p.relu ? 0.f : __int_as_float(0xff800000);
+      const bool plain = !p.relu && p.row_zero == nullptr;      // warp-uniform: (acc + bias) only
       mbar_wait(&tfull_bar[buf], (lt >> 1) & 1, 300 + buf);
       tc_fence_after();
       const uint32_t tmem_row = tmem_base + buf * BN + (static_cast<uint32_t>(quad * 32) << 16);
@@ -199,6 +200,24 @@ linear_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         tmem_ld_wait();
         const bool uniform = (n0 + c0 + 32 <= p.alpha_ncols) || (n0 + c0 >= p.alpha_ncols);
         const float sc = (n0 + c0 < p.alpha_ncols) ? p.alpha : 1.f;
+        // the epilogue warps are the throughput limit of the persistent schedule (one warp per SMSP):
+        // the plain bias-add case (K / V projections, out-projections) must cost one FADD per element
+        if (plain && sc == 1.f) {
+          if (p.bias_along_m) {                                  // column bias is all zero
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]) + bias_m;
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c0 + j);
+              v[j] = __uint_as_float(acc[j]) + b4.x;
+              v[j + 1] = __uint_as_float(acc[j + 1]) + b4.y;
+              v[j + 2] = __uint_as_float(acc[j + 2]) + b4.z;
+              v[j + 3] = __uint_as_float(acc[j + 3]) + b4.w;
+            }
+          }
+          return;
+        }
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
           const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c0 + j);

@@ -12,6 +12,8 @@ import torch
 from . import _lib
 
 bf16 = torch.bfloat16
+LOG2E = 1.4426950408889634
+Q_SCALE = LOG2E / 8.0     # attention kernels take Q pre-scaled by log2(e)/sqrt(head_dim=64): scores in the log2 domain
 LAUNCHES = 0          # kernels launched through this module (bench.py reports it as gpu_launches)
 
 
@@ -75,10 +77,11 @@ def linear(A: torch.Tensor, W: torch.Tensor, out: torch.Tensor, *, M: int, N: in
 class AttnMemory:
     """One memory's projected operands for `attention` (see pq3d_attention_fwd)."""
     __slots__ = ("K", "k_col0", "Vt", "vt_row0", "S", "S_pitch", "Vt_pitch", "mask_bits", "mask_b_stride",
-                 "mask_h_stride", "mask_q_stride")
+                 "mask_h_stride", "mask_q_stride", "kv_tiles")
 
     def __init__(self, K, k_col0, Vt, vt_row0, S, S_pitch, mask_bits=None, mask_b_stride=0, mask_h_stride=0,
-                 mask_q_stride=0, Vt_pitch=None):
+                 mask_q_stride=0, Vt_pitch=None, kv_tiles=None):
+        self.kv_tiles = kv_tiles
         self.K, self.k_col0, self.Vt, self.vt_row0 = K, k_col0, Vt, vt_row0
         self.S, self.S_pitch = S, S_pitch
         self.Vt_pitch = S_pitch if Vt_pitch is None else Vt_pitch
@@ -116,6 +119,7 @@ def attention(Q: torch.Tensor, q_mem_stride: int, mems: Sequence[AttnMemory], O:
         vp(*[_p(m.mask_bits) for m in mems]) if has_mask else None,
         i64(*[m.mask_b_stride for m in mems]), i64(*[m.mask_h_stride for m in mems]),
         i64(*[m.mask_q_stride for m in mems]),
+        vp(*[_p(m.kv_tiles) for m in mems]) if any(m.kv_tiles is not None for m in mems) else None,
         O.data_ptr(), O.stride(-2), o_mem_stride, B, H, Nq, int(zero_attn), _p(score_bias), bias_ld, _stream())
     _lib.check(rc, "pq3d_attention_fwd")
     _count()
@@ -176,8 +180,9 @@ def add_layernorm(y: Optional[torch.Tensor], residual: Optional[torch.Tensor], g
 
 
 def pack_mask(mask: torch.Tensor, bits: Optional[torch.Tensor] = None, unmask_full_rows: bool = False,
-              mask_fixed: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """bool (..., S) -> int32 (..., W) packed bits, 1 = ignore."""
+              mask_fixed: Optional[torch.Tensor] = None, active_tiles: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """bool (..., S) -> int32 (..., W) packed bits, 1 = ignore.  active_tiles: optional int32 (mask.shape[0],) that
+    receives per leading-dim entry the number of 128-key tiles up to the last visible key."""
     if mask.dtype != torch.bool:
         raise TypeError(f"mask must be torch.bool (PyTorch mask convention), got {mask.dtype}")
     if not mask.is_cuda or not mask.is_contiguous():
@@ -186,8 +191,14 @@ def pack_mask(mask: torch.Tensor, bits: Optional[torch.Tensor] = None, unmask_fu
     rows = mask.numel() // S
     if bits is None:
         bits = torch.empty(mask.shape[:-1] + (mask_words(S),), dtype=torch.int32, device=mask.device)
+    rpb = 0
+    if active_tiles is not None:
+        _chk(active_tiles, torch.int32, "active_tiles", 1)
+        if active_tiles.shape[0] != mask.shape[0]:
+            raise ValueError("active_tiles must have one entry per leading-dimension index of the mask")
+        rpb = rows // mask.shape[0]
     rc = _lib.lib().pq3d_pack_mask(mask.data_ptr(), bits.data_ptr(), rows, S, int(unmask_full_rows),
-                                   _p(mask_fixed), _stream())
+                                   _p(mask_fixed), _p(active_tiles), rpb, _stream())
     _lib.check(rc, "pq3d_pack_mask")
     _count()
     return bits

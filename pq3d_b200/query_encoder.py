@@ -237,7 +237,7 @@ class _Packed:
 
 class _MemState:
     """Per-forward projected state of one memory."""
-    __slots__ = ("name", "S", "S_pitch", "multi", "per_layer", "xk", "xv", "K", "Vt", "bits", "strides")
+    __slots__ = ("name", "S", "S_pitch", "multi", "per_layer", "xk", "xv", "K", "Vt", "bits", "strides", "tiles")
 
 
 # --------------------------------------------------------------------------------------------
@@ -472,9 +472,11 @@ class QueryMaskEncoder(nn.Module):
                     if attn_mask is None:
                         raise ValueError("use_self_mask=True needs a mask_head that returns an attention mask")
                     fixed = buf("am_fixed", (B, N, attn_mask.shape[-1]), torch.bool)
+                    am_tiles = buf("am_tiles", (B,), torch.int32)
                     bits = ops.pack_mask(attn_mask.contiguous(),
                                          buf("am_bits", (B, N, ops.mask_words(attn_mask.shape[-1])), torch.int32),
-                                         unmask_full_rows=True, mask_fixed=fixed.view(torch.uint8))
+                                         unmask_full_rows=True, mask_fixed=fixed.view(torch.uint8),
+                                         active_tiles=am_tiles)
                     for m in input_dict.keys():
                         if m in ("query", "prompt"):
                             continue
@@ -483,7 +485,7 @@ class QueryMaskEncoder(nn.Module):
                         input_dict[m][1] = fixed
                         if m in states:
                             st = states[m]
-                            st.bits, st.strides = bits, (bits.stride(0), 0, bits.stride(1))
+                            st.bits, st.strides, st.tiles = bits, (bits.stride(0), 0, bits.stride(1)), am_tiles
                 if isinstance(voxel_feat, list):
                     input_dict["voxel"][0] = voxel_feat[i]
                 run_layer(i)
@@ -523,11 +525,14 @@ class QueryMaskEncoder(nn.Module):
         if mask.ndim == 2:                                    # key padding (B, S)
             if tuple(mask.shape) != (B, st.S):
                 raise ValueError(f"memory '{st.name}': key padding mask {tuple(mask.shape)} != {(B, st.S)}")
-            st.bits = ops.pack_mask(mask.contiguous(), self._buf(ws, f"bits2_{st.name}", (B, W), torch.int32, dev))
+            st.tiles = self._buf(ws, f"tiles2_{st.name}", (B,), torch.int32, dev)
+            st.bits = ops.pack_mask(mask.contiguous(), self._buf(ws, f"bits2_{st.name}", (B, W), torch.int32, dev),
+                                    active_tiles=st.tiles)
             st.strides = (W, 0, 0)
         elif mask.ndim == 3:                                  # attn mask (B*H, N, S), row b*H + h
             if tuple(mask.shape) != (B * H, N, st.S):
                 raise RuntimeError(f"The shape of the 3D attn_mask is {tuple(mask.shape)}, but should be {(B * H, N, st.S)}.")
+            st.tiles = None      # per-head masks: (B*H) leading entries; tail trimming not wired for this layout
             st.bits = ops.pack_mask(mask.contiguous(), self._buf(ws, f"bits3_{st.name}", (B * H, N, W), torch.int32, dev))
             st.strides = (H * N * W, N * W, W)
         else:
@@ -539,11 +544,11 @@ class QueryMaskEncoder(nn.Module):
         R, g = B * N, len(grp)
         w = pk.layers[i]["groups"][grp]
         Q = self._buf(ws, f"Q_{tag}", (R, g * D), bf16, dev)
-        ops.linear(x_in, w["wq"], Q, M=R, N=g * D, K=D, bias=w["bq"], alpha=0.125, alpha_ncols=g * D)
+        ops.linear(x_in, w["wq"], Q, M=R, N=g * D, K=D, bias=w["bq"], alpha=ops.Q_SCALE, alpha_ncols=g * D)
         O = self._buf(ws, f"O_{tag}", (g, R, D), bf16, dev)
         mems = [ops.AttnMemory(states[m].K, 0 if states[m].per_layer else i * D, states[m].Vt,
                                0 if states[m].per_layer else i * D, states[m].S, states[m].S_pitch, states[m].bits,
-                               *states[m].strides) for m in grp]
+                               *states[m].strides, kv_tiles=states[m].tiles) for m in grp]
         ops.attention(Q, D, mems, O, R * D, B, H, N, True)
         y = self._buf(ws, f"y_{tag}", (g, R, D), torch.float32, dev)
         ops.linear(O.view(g * R, D), w["wo"], y, M=R, N=D, K=D, bias=w["bo"], bias_group_stride=D, groups=g,
@@ -577,7 +582,7 @@ class QueryMaskEncoder(nn.Module):
         # ---- query self-attention (spatially biased when configured)
         sa = lw["sa"]
         QK = self._buf(ws, "sa_QK", (R, 2 * D), bf16, dev)
-        ops.linear(xq, sa["wqk"], QK, M=R, N=2 * D, K=D, bias=sa["bqk"], alpha=0.125, alpha_ncols=D)
+        ops.linear(xq, sa["wqk"], QK, M=R, N=2 * D, K=D, bias=sa["bqk"], alpha=ops.Q_SCALE, alpha_ncols=D)
         # V^T [D, B*Np]: scene b's queries at columns b*Np .. b*Np+N (Np = N rounded up to 8 for the TMA
         # stride); one GEMM group per scene, pad columns stay at their zero initialisation
         Np = ops.pad8(N)

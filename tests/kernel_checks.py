@@ -99,10 +99,12 @@ def check_gemm_epilogues():
 
 # -------------------------------------------------------------------------------------- attention
 def _attn_ref(Q, K, V, mask, zero_attn, bias=None):
-    """Q (B,H,N,64) pre-scaled, K/V (B,H,S,64), mask (B,H,N,S) bool, fp64 math."""
+    """Q (B,H,N,64) pre-scaled INTO THE LOG2 DOMAIN (kernel contract), K/V (B,H,S,64), mask (B,H,N,S) bool,
+    bias in log2 units; fp64 math."""
     s = torch.einsum("bhnd,bhsd->bhns", Q.double(), K.double())
     if bias is not None:
         s = s + bias.double()
+    s = s * math.log(2.0)
     s = s.masked_fill(mask, float("-inf"))
     if zero_attn:
         s = torch.cat([s, torch.zeros_like(s[..., :1])], -1)
@@ -155,7 +157,7 @@ def _attn_case(B, H, Nq, S_list, mask_kind, zero_attn=True, spatial=False, seed=
         bias = None
         if spatial:
             loc = torch.relu(torch.einsum("bnmd,hd->bhnm", pw, lw) + lb[None, :, None, None])
-            bias = torch.log(loc.clamp_min(1e-6))
+            bias = torch.log2(loc.clamp_min(1e-6))
         refs.append(_attn_ref(Qh, Kh, Vh, full, zero_attn, bias))
     sbias = None
     if spatial:
@@ -202,8 +204,60 @@ def check_attn_resident():
     _attn_case(2, 3, 100, [257], "kpm", seed=17)           # just past the resident limit: streaming path
 
 
+def check_attn_ragged_tiles():
+    """pack_mask's active-tile counts let the attention kernel skip trailing padding tiles; results must not change."""
+    g = gen(30)
+    B, H, Nq, S = 3, 2, 100, 1000
+    D = H * 64
+    lens = [1000, 130, 400]
+    m = torch.arange(S)[None, :] >= torch.tensor(lens)[:, None]
+    m = (m | (torch.rand(B, S, generator=g) < 0.1)).to(DEV)
+    tiles = torch.full((B,), -1, dtype=torch.int32, device=DEV)
+    bits = ops.pack_mask(m, active_tiles=tiles)
+    torch.cuda.synchronize()
+    assert tiles.tolist() == [8, 2, 4], tiles.tolist()
+    Q = rnd((B * Nq, D), g).bfloat16()
+    Sp = ops.pad8(S)
+    Kb, Vt = rnd((B * Sp, D), g).bfloat16(), rnd((D, B * Sp), g).bfloat16()
+    outs = []
+    for kt in (None, tiles):
+        O = torch.full((1, B * Nq, D), float("nan"), dtype=torch.bfloat16, device=DEV)
+        ops.attention(Q, 0, [ops.AttnMemory(Kb, 0, Vt, 0, S, Sp, bits, bits.stride(0), 0, 0, kv_tiles=kt)], O,
+                      B * Nq * D, B, H, Nq, True)
+        torch.cuda.synchronize()
+        outs.append(O)
+    assert not torch.isnan(outs[1].float()).any()
+    assert torch.equal(outs[0], outs[1]), "skipping fully masked tiles changed the result"
+    # per-query masks: tile count is the max over the scene's rows; the all-masked fix-up makes a row fully visible
+    am = torch.ones(2, 5, 300, dtype=torch.bool, device=DEV)
+    am[0, :, :100] = False
+    am[1, 0, :10] = False            # rows 1..4 of scene 1 stay fully masked
+    t2 = torch.zeros(2, dtype=torch.int32, device=DEV)
+    ops.pack_mask(am, active_tiles=t2)
+    t3 = torch.zeros(2, dtype=torch.int32, device=DEV)
+    ops.pack_mask(am, unmask_full_rows=True, active_tiles=t3)
+    torch.cuda.synchronize()
+    assert t2.tolist() == [1, 1] and t3.tolist() == [1, 3], (t2.tolist(), t3.tolist())
+    print("ragged tiles: counts exact, outputs bit-identical with and without skipping")
+
+
 def check_attn_long():
     _attn_case(1, 2, 100, [4096], "kpm", seed=11, scale=2.0)
+
+
+def check_attn_schedules():
+    """Long zero-attn memories take the one-pass schedule (reference score 0, no running max); row sums
+    beyond 2^100 make the CTA redo the sweep with running maxima; both must match the fp64 softmax."""
+    from pq3d_b200 import _lib
+    _attn_case(2, 4, 100, [700], "kpm", seed=18, scale=1.0)              # one pass
+    _attn_case(2, 4, 100, [700], "attn", seed=19, scale=1.0)
+    _attn_case(2, 4, 100, [700], "kpm", seed=20, scale=4.5)              # scores ~ +-160 (log2): overflow -> redo
+    _lib.lib().pq3d_debug_force_two_pass(1)
+    try:
+        _attn_case(2, 4, 100, [700], "kpm", seed=18, scale=1.0)          # forced running-max schedule
+    finally:
+        _lib.lib().pq3d_debug_force_two_pass(0)
+    _attn_case(2, 4, 100, [700], "kpm", zero_attn=False, seed=21)        # no zero-attn: running-max schedule
 
 
 # ------------------------------------------------------------------------------------ elementwise

@@ -34,7 +34,7 @@ def test_bad_arguments_return_error_codes(lib):
     p = ctypes.addressof(buf)
     rc = lib.pq3d_linear_bf16(p, 8, 1, 0, p, 8, 1, 0, p, 8, 0, 0, None, 0, 0, None, 0, 1, 1, 7, 1, 1.0, 0, 0, 0, None)
     assert rc == -1 and b"multiple of 64" in lib.pq3d_last_error()
-    rc = lib.pq3d_pack_mask(None, None, 0, 0, 0, None, None)
+    rc = lib.pq3d_pack_mask(None, None, 0, 0, 0, None, None, 0, None)
     assert rc == -1
 
 
