@@ -21,6 +21,8 @@
 //               (the 201-class logits) takes a direct-store path.
 // Groups shift the A / W / C / bias bases: per-memory out-projections, per-layer multi-scale voxel
 // K/V projections, per-scene V^T and mask-logit products run as one launch.
+#include <cstdlib>
+
 #include "host_common.h"
 #include "ptx.cuh"
 
@@ -45,6 +47,7 @@ struct LinearParams {
   float alpha;
   int32_t tma_store;        // C is 16-byte granular: epilogue goes through shared memory + TMA store
   unsigned long long* dbg;  // optional per-CTA timeline (pq3d_debug_set_timeline), 8 slots per CTA
+  int32_t dbg_flags;        // PQ3D_GEMM_DEBUG: 1 = skip the TMA stores, 2 = skip staging + stores (WRONG RESULTS; timing only)
 };
 
 constexpr int kBlockM = 128;
@@ -52,12 +55,12 @@ constexpr int kBlockK = 64;  // 64 bf16 = 128 B = one swizzle atom row
 constexpr int kGemmThreads = 192;
 constexpr int kBoxBytes = 32 * 128;  // one epilogue box: 32 rows x 128 B
 
-template <int BN>
+template <int BN, int CL>
 struct GemmCfg {
   static constexpr int kABytes = kBlockM * kBlockK * 2;
-  static constexpr int kBBytes = BN * kBlockK * 2;
+  static constexpr int kBBytes = (BN / CL) * kBlockK * 2;                    // a CTA pair splits the W tile
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);     // 192 KB of operands in flight
+  static constexpr int kStages = 196608 / kStageBytes;                       // 192 KB of operands in flight
   static constexpr int kRingBytes = kStages * kStageBytes;
   static constexpr int kStagingBytes = 4 * 2 * kBoxBytes;                    // 4 warps x double buffer
   static constexpr int kBarBytes = 256;
@@ -66,11 +69,16 @@ struct GemmCfg {
   static_assert(kSmemBytes <= 232448, "exceeds the 227 KB shared-memory limit");
 };
 
-template <int BN>
+// CL = 2: a CTA pair (cluster of 2, tcgen05 cta_group::2) computes a 256 x BN tile.  Each CTA stages its own 128
+// rows of A and HALF of the W tile; the leader CTA's single MMA thread issues M = 256 instructions that read
+// both shared memories and write both tensor memories.  With one CTA per tile the shared-memory port is the
+// limit (MMA operand reads 96 B/clk + TMA fill 96 B/clk against 128 B/clk: measured 66 % of the MMA floor, and
+// multicasting W into both CTAs changed nothing); the pair halves the W traffic on both sides of that port.
+template <int BN, int CL>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 linear_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
                    const __grid_constant__ CUtensorMap tmap_c, const LinearParams p) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, CL>;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* staging = smem + Cfg::kRingBytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + Cfg::kStagingBytes);
@@ -82,7 +90,9 @@ linear_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
 
   const int warp = threadIdx.x >> 5;
   const int num_kb = p.K / kBlockK;
-  const int tiles_per_group = p.num_m * p.num_n;
+  const int rank = CL > 1 ? static_cast<int>(cluster_ctarank()) : 0;
+  const int first_tile = blockIdx.x / CL, tile_step = gridDim.x / CL;   // p.num_tiles counts tile PAIRS when CL = 2
+  const int tiles_per_group = ((p.num_m + CL - 1) / CL) * p.num_n;
 
   if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) {
     printf("pq3d: dynamic shared memory is not 1024-byte aligned\n");
@@ -98,13 +108,15 @@ linear_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 4);
+      mbar_init(&tempty_bar[i], 4 * CL);   // pair: the leader's barrier collects the epilogue warps of both CTAs
     }
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  if (warp == 1) {
+    if (CL > 1) tmem_alloc_pair<Cfg::kTmemCols>(tmem_slot); else tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  }
   tc_fence_before();
-  __syncthreads();
+  if (CL > 1) cluster_sync_all(); else __syncthreads();   // peers' barriers exist before anything signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_sync();   // everything above overlapped the previous kernel's tail; global memory is touched only below
@@ -121,26 +133,35 @@ linear_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     // ------------------------------------------------------------------ TMA producer
     if (elect_one()) {
       int it = 0;
-      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+      for (int t = first_tile; t < p.num_tiles; t += tile_step) {
         const int g = t / tiles_per_group, rem = t % tiles_per_group;
-        const int a_row = g * p.a_group_rows + (rem / p.num_n) * kBlockM;
+        const int a_row = g * p.a_group_rows + ((rem / p.num_n) * CL + rank) * kBlockM;
         const int w_row = g * p.w_group_rows + (rem % p.num_n) * BN;
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           const int s = it % Cfg::kStages;
           mbar_wait(&empty_bar[s], ((it / Cfg::kStages) & 1) ^ 1, 100 + s);
           uint8_t* sa = smem + s * Cfg::kStageBytes;
-          mbar_arrive_expect_tx(&full_bar[s], Cfg::kStageBytes);
-          tma_load_2d(sa, &tmap_a, &full_bar[s], kb * kBlockK, a_row);
-          tma_load_2d(sa + Cfg::kABytes, &tmap_w, &full_bar[s], kb * kBlockK, w_row);
+          if (CL > 1) {
+            // both CTAs' bytes are counted on the LEADER's barrier (its MMA thread is the only consumer)
+            const uint32_t lead_bar = mapa_u32(smem_u32(&full_bar[s]), 0);
+            if (rank == 0) mbar_arrive_expect_tx(&full_bar[s], CL * Cfg::kStageBytes);
+            tma_load_2d_pair(sa, &tmap_a, lead_bar, kb * kBlockK, a_row);
+            tma_load_2d_pair(sa + Cfg::kABytes, &tmap_w, lead_bar, kb * kBlockK, w_row + rank * (BN / CL));
+          } else {
+            mbar_arrive_expect_tx(&full_bar[s], Cfg::kStageBytes);
+            tma_load_2d(sa, &tmap_a, &full_bar[s], kb * kBlockK, a_row);
+            tma_load_2d(sa + Cfg::kABytes, &tmap_w, &full_bar[s], kb * kBlockK, w_row);
+          }
         }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (elect_one()) {
-      constexpr uint32_t idesc = umma_idesc_bf16(kBlockM, BN);
+    // ------------------------------------------------------------------ MMA issuer (pair: leader CTA only)
+    if (rank == 0 && elect_one()) {
+      constexpr uint32_t idesc = umma_idesc_bf16(kBlockM * CL, BN);
+      constexpr uint16_t kPairMask = static_cast<uint16_t>((1u << CL) - 1);
       int it = 0, lt = 0;
-      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++lt) {
+      for (int t = first_tile; t < p.num_tiles; t += tile_step, ++lt) {
         const int buf = lt & 1;
         mbar_wait(&tempty_bar[buf], ((lt >> 1) & 1) ^ 1, 210 + buf);
         tc_fence_after();
@@ -155,12 +176,18 @@ linear_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
 #pragma unroll
           for (int k = 0; k < kBlockK / 16; ++k) {
             // advancing 16 bf16 (32 B) along K inside the 128-byte swizzle atom = +32 B on the start address
-            umma_ss(tmem_acc, umma_desc_k_sw128(sa + k * 32), umma_desc_k_sw128(sb + k * 32), idesc,
-                    (kb | k) != 0 ? 1u : 0u);
+            if (CL > 1)
+              umma_ss_pair(tmem_acc, umma_desc_k_sw128(sa + k * 32), umma_desc_k_sw128(sb + k * 32), idesc,
+                           (kb | k) != 0 ? 1u : 0u);
+            else
+              umma_ss(tmem_acc, umma_desc_k_sw128(sa + k * 32), umma_desc_k_sw128(sb + k * 32), idesc,
+                      (kb | k) != 0 ? 1u : 0u);
           }
-          tc_commit(&empty_bar[s]);
+          if (CL > 1) tc_commit_pair(&empty_bar[s], kPairMask);   // frees the slot in BOTH CTAs
+          else tc_commit(&empty_bar[s]);
         }
-        tc_commit(&tfull_bar[buf]);
+        if (CL > 1) tc_commit_pair(&tfull_bar[buf], kPairMask);   // each CTA's epilogue reads its own TMEM half
+        else tc_commit(&tfull_bar[buf]);
       }
       if (dbg != nullptr) {
         dbg[3] = clock64();
@@ -173,9 +200,9 @@ linear_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     const int r = lane_id();
     uint8_t* stage = staging + (warp - 2) * 2 * kBoxBytes;
     int lt = 0, bx = 0;
-    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++lt) {
+    for (int t = first_tile; t < p.num_tiles; t += tile_step, ++lt) {
       const int g = t / tiles_per_group, rem = t % tiles_per_group;
-      const int m0 = (rem / p.num_n) * kBlockM, n0 = (rem % p.num_n) * BN;
+      const int m0 = ((rem / p.num_n) * CL + rank) * kBlockM, n0 = (rem % p.num_n) * BN;
       const int buf = lt & 1;
       float* bias_s = s_bias + buf * BN;
       for (int c = threadIdx.x - 64; c < BN; c += 128) {
@@ -234,7 +261,10 @@ linear_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       auto release_accumulator = [&]() {
         tc_fence_before();
         __syncwarp();
-        if (r == 0) mbar_arrive(&tempty_bar[buf]);
+        if (r == 0) {
+          if (CL > 1) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[buf]), 0));   // the leader's barrier
+          else mbar_arrive(&tempty_bar[buf]);
+        }
       };
       auto claim_box = [&]() -> uint8_t* {   // double-buffered staging: wait until the box used 2 stores ago was read
         if (bx >= 2 && r == 0) tma_store_wait_read<1>();
@@ -244,7 +274,7 @@ linear_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       auto store_box = [&](uint8_t* box, int c0) {
         fence_proxy_async_smem();
         __syncwarp();
-        if (r == 0) {
+        if (r == 0 && !(p.dbg_flags & 3)) {
           tma_store_3d(&tmap_c, box, n0 + c0, m0 + quad * 32, g);
           tma_store_commit();
         }
@@ -271,6 +301,7 @@ linear_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
           load_chunk(b * 64 + 32, v1);
           if (b == n_boxes - 1) release_accumulator();
           uint8_t* box = claim_box() + r * 128;
+          if (p.dbg_flags & 2) continue;
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             uint4 u;
@@ -312,26 +343,28 @@ linear_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     tc_fence_before();
     if (dbg != nullptr && threadIdx.x == 64) dbg[5] = clock64();
   }
-  __syncthreads();
+  if (CL > 1) cluster_sync_all(); else __syncthreads();   // no CTA leaves while its peer may still signal it
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+    if (CL > 1) tmem_dealloc_pair<Cfg::kTmemCols>(tmem_base); else tmem_dealloc<Cfg::kTmemCols>(tmem_base);
   }
   if (dbg != nullptr && threadIdx.x == 0) dbg[6] = clock64();
 }
 
-template <int BN>
+template <int BN, int CL>
 static int launch_linear(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& tc, const LinearParams& p,
                          cudaStream_t stream) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, CL>;
   static bool configured = false;
   if (!configured) {
-    PQ3D_CUDA(cudaFuncSetAttribute(linear_bf16_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    PQ3D_CUDA(cudaFuncSetAttribute(linear_bf16_kernel<BN, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    Cfg::kSmemBytes));
     configured = true;
   }
-  const int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
-  PQ3D_CUDA(launch_kernel(linear_bf16_kernel<BN>, dim3(grid), dim3(kGemmThreads), Cfg::kSmemBytes, stream, ta, tw, tc, p));
+  const int max_clusters = sm_count() / CL;
+  const int grid = CL * (p.num_tiles < max_clusters ? p.num_tiles : max_clusters);
+  PQ3D_CUDA(launch_kernel_cluster(linear_bf16_kernel<BN, CL>, dim3(grid), dim3(kGemmThreads), Cfg::kSmemBytes, stream,
+                                  CL, ta, tw, tc, p));
   return PQ3D_OK;
 }
 
@@ -374,6 +407,15 @@ extern "C" int pq3d_linear_bf16(const void* A, int64_t lda, int64_t a_rows_total
   PQ3D_CHECK_ARG(block_n == 64 || block_n == 128 || block_n == 256, "pq3d_linear_bf16: block_n=%d not in {64,128,256}",
                  block_n);
 
+  // CTA pairs (cta_group::2, 256 x 256 tiles) whenever there are at least two row tiles and more than a wave of work
+  // (PQ3D_GEMM_CLUSTER=0 disables, for A/B measurements)
+  static const bool cluster_ok = [] {
+    const char* e = getenv("PQ3D_GEMM_CLUSTER");
+    return e == nullptr || e[0] != '0';
+  }();
+  const int num_m_tiles = (M + kBlockM - 1) / kBlockM;
+  const int cl = (cluster_ok && block_n == 256 && num_m_tiles >= 2 &&
+                  (int64_t)num_m_tiles * ((N + 255) / 256) * groups >= 2 * sm_count()) ? 2 : 1;
   CUtensorMap ta, tw;
   {
     uint64_t dims[2] = {(uint64_t)K, (uint64_t)a_rows_total};
@@ -385,7 +427,7 @@ extern "C" int pq3d_linear_bf16(const void* A, int64_t lda, int64_t a_rows_total
   {
     uint64_t dims[2] = {(uint64_t)K, (uint64_t)w_rows_total};
     uint64_t strides[1] = {(uint64_t)ldw * 2};
-    uint32_t box[2] = {(uint32_t)kBlockK, (uint32_t)block_n};
+    uint32_t box[2] = {(uint32_t)kBlockK, (uint32_t)(block_n / cl)};   // each CTA of a pair fetches its half
     int rc = make_tmap_bf16(&tw, W, 2, dims, strides, box);
     if (rc != PQ3D_OK) return rc;
   }
@@ -404,13 +446,18 @@ extern "C" int pq3d_linear_bf16(const void* A, int64_t lda, int64_t a_rows_total
   p.K = K;
   p.num_m = (M + kBlockM - 1) / kBlockM;
   p.num_n = (N + block_n - 1) / block_n;
-  p.num_tiles = p.num_m * p.num_n * groups;
+  p.num_tiles = ((p.num_m + cl - 1) / cl) * p.num_n * groups;   // tile PAIRS when cl = 2
   p.out_fp32 = out_fp32;
   p.bias_along_m = bias_along_m;
   p.relu = relu;
   p.alpha_ncols = alpha_ncols;
   p.alpha = alpha;
   p.dbg = g_timeline;
+  static const int dbg_flags = [] {
+    const char* e = getenv("PQ3D_GEMM_DEBUG");
+    return e == nullptr ? 0 : atoi(e);
+  }();
+  p.dbg_flags = dbg_flags;
   const int esz = out_fp32 ? 4 : 2;
   p.tma_store = ((reinterpret_cast<uintptr_t>(C) & 15) == 0) && ((ldc * esz) % 16 == 0) &&
                 ((c_group_stride * esz) % 16 == 0);
@@ -426,8 +473,8 @@ extern "C" int pq3d_linear_bf16(const void* A, int64_t lda, int64_t a_rows_total
   }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   switch (block_n) {
-    case 64: return launch_linear<64>(ta, tw, tc, p, st);
-    case 128: return launch_linear<128>(ta, tw, tc, p, st);
-    default: return launch_linear<256>(ta, tw, tc, p, st);
+    case 64: return launch_linear<64, 1>(ta, tw, tc, p, st);
+    case 128: return launch_linear<128, 1>(ta, tw, tc, p, st);
+    default: return cl == 2 ? launch_linear<256, 2>(ta, tw, tc, p, st) : launch_linear<256, 1>(ta, tw, tc, p, st);
   }
 }

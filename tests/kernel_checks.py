@@ -88,6 +88,15 @@ def check_gemm_shapes():
     _gemm_case(333, 1536, 768, 128, torch.bfloat16, alpha=0.125, alpha_ncols=768, seed=7)
 
 
+def check_gemm_pair():
+    """Problems with more than two waves of 128x256 tiles run on CTA pairs (cta_group::2, 256-row tiles)."""
+    _gemm_case(8192, 3072, 768, 256, torch.bfloat16, seed=40)
+    _gemm_case(640, 15360, 128, 256, torch.bfloat16, seed=41)                      # odd number of row tiles
+    _gemm_case(4224 - 50, 768, 768, 256, torch.bfloat16, groups=3, seed=42)        # grouped, ragged last pair
+    _gemm_case(3072, 8192, 768, 256, torch.bfloat16, bias_along_m=True, seed=43)   # V^T form
+    _gemm_case(8192, 1024, 256, 256, torch.float32, relu=True, seed=44)
+
+
 def check_gemm_epilogues():
     _gemm_case(3072, 520, 768, 128, torch.bfloat16, bias_along_m=True, seed=8)     # V^T form
     _gemm_case(400, 201, 768, 64, torch.float32, seed=9)                           # cls head: unaligned N
@@ -227,7 +236,9 @@ def check_attn_ragged_tiles():
         torch.cuda.synchronize()
         outs.append(O)
     assert not torch.isnan(outs[1].float()).any()
-    assert torch.equal(outs[0], outs[1]), "skipping fully masked tiles changed the result"
+    # a trimmed scene may take a different schedule (<= 2 tiles: resident, running max) than the full-length
+    # sweep (one pass, reference 0): same math, different rounding -> compare within the bf16 output resolution
+    assert rel(outs[1], outs[0]) <= 2 * TOL_BF16, "skipping fully masked tiles changed the result"
     # per-query masks: tile count is the max over the scene's rows; the all-masked fix-up makes a row fully visible
     am = torch.ones(2, 5, 300, dtype=torch.bool, device=DEV)
     am[0, :, :100] = False
@@ -238,7 +249,7 @@ def check_attn_ragged_tiles():
     ops.pack_mask(am, unmask_full_rows=True, active_tiles=t3)
     torch.cuda.synchronize()
     assert t2.tolist() == [1, 1] and t3.tolist() == [1, 3], (t2.tolist(), t3.tolist())
-    print("ragged tiles: counts exact, outputs bit-identical with and without skipping")
+    print(f"ragged tiles: counts exact, outputs equal within {rel(outs[1], outs[0]):.1e} with and without skipping")
 
 
 def check_attn_long():
