@@ -185,7 +185,7 @@ def main():
     enc.load_state_dict(synth.decoder_state_dict(w, seed=0), strict=True)   # identical weights on every rank
     enc = enc.to(dev)
     enc.use_cuda_graph = not args.no_graph
-    inp_host, pw_host, _ = synth.make_decoder_inputs(w, rank=rank)          # this rank's scenes
+    inp_host, pw_host, _dd = synth.make_decoder_inputs(w, rank=rank)        # this rank's scenes
     to_dev = lambda x: x.to(dev, non_blocking=True)  # noqa: E731
 
     def dict_to(d, f):
@@ -204,9 +204,30 @@ def main():
 
     (inp_dev, _), pw_dev = dict_to(inp_host, to_dev), to_dev(pw_host)
 
+    # configs with use_self_mask (BASELINE config 4) run the in-loop mask head, as Query3DUnified wires it
+    mask_head = None
+    if w.use_self_mask:
+        from functools import partial
+        from pq3d_b200.mask_head import MaskHeadSegLevel
+        scene_mems = [m for m in w.memories if m in synth.SCENE_MEMORIES]
+        mh = MaskHeadSegLevel(None, w.hidden_size, 201, memories_for_match=list(w.memories), filter_out_classes=[0, 2]).eval()
+        mh.load_state_dict(synth.draw_state_dict(synth.mask_head_param_shapes(len(scene_mems)), 100), strict=True)
+        mh = mh.to(dev)
+        seg_pad = to_dev(~_dd["seg_pad_masks"])
+
+        def make_head(inp):
+            feats = []
+            for m in scene_mems:
+                f = list(inp[m])
+                if isinstance(f[0], list):
+                    f[0] = f[0][-1]
+                feats.append(f)
+            return partial(mh, seg_fts_for_match=feats, seg_masks=seg_pad, offline_attn_masks=None, skip_prediction=False)
+        mask_head = make_head(inp_dev)
+
     def step_resident():
         with torch.no_grad():
-            return enc(synth.clone_input_dict(inp_dev), pw_dev)[0]
+            return enc(synth.clone_input_dict(inp_dev), pw_dev, mask_head)[0]
 
     for _ in range(max(args.warmup, 3)):
         step_resident()
@@ -237,7 +258,8 @@ def main():
 
     def step_e2e():
         with torch.no_grad():
-            q = enc(dict_to(inp_pin, to_dev)[0], to_dev(pw_pin))[0]
+            d_in = dict_to(inp_pin, to_dev)[0]
+            q = enc(d_in, to_dev(pw_pin), None if mask_head is None else make_head(d_in))[0]
         out_host.copy_(q, non_blocking=True)
 
     for _ in range(3):
@@ -281,7 +303,7 @@ def main():
             st = sets[i % 2]
             main_stream.wait_event(st["h2d_done"])
             with torch.no_grad():
-                q = enc(synth.clone_input_dict(st["inp"]), st["pw"])[0]
+                q = enc(synth.clone_input_dict(st["inp"]), st["pw"], None if mask_head is None else make_head(st["inp"]))[0]
             st["consumed"].record(main_stream)
             st["out"].copy_(q, non_blocking=True)
         torch.cuda.synchronize()

@@ -460,6 +460,45 @@ class QueryMaskEncoder(nn.Module):
                 input_dict["voxel"][0] = voxel_feat[L - 1]
             return q32.view(B, N, D).clone(), predictions_class, predictions_mask
 
+        mh = self._own_mask_head(mask_head)
+        if mh is not None:
+            # ---------------- our own MaskHeadSegLevel in the loop: its hoisted part runs once here, its per-layer
+            # part writes static buffers, so blocks x layers x (mask head + mask packing + layer) is one CUDA graph
+            kw = mask_head.keywords
+            mh.prepare(kw["seg_fts_for_match"], kw["seg_masks"])
+            S_m, C = kw["seg_masks"].shape[1], mh.cls_head[4].out_features
+            n_calls = self.num_blocks * L
+            cls_buf = buf("mh_cls", (n_calls, B, N, C), torch.float32)
+            logit_buf = buf("mh_logits", (n_calls, B, S_m, N), torch.float32)
+            attn_buf = buf("mh_attn", (B, N, S_m), torch.bool)
+            fixed = buf("am_fixed", (B, N, S_m), torch.bool)
+            am_bits = buf("am_bits", (B, N, ops.mask_words(S_m)), torch.int32)
+            am_tiles = buf("am_tiles", (B,), torch.int32)
+
+            def body():
+                project_memories()
+                for k in range(n_calls):
+                    mh.run_into(q32, B, N, cls_buf[k], logit_buf[k], attn_buf)
+                    if self.use_self_mask:
+                        ops.pack_mask(attn_buf, am_bits, unmask_full_rows=True, mask_fixed=fixed.view(torch.uint8),
+                                      active_tiles=am_tiles)
+                        for st in states.values():
+                            if st.name != "prompt":
+                                st.bits, st.strides, st.tiles = am_bits, (am_bits.stride(0), 0, am_bits.stride(1)), am_tiles
+                    run_layer(k % L)
+            self._run_body(ws, body)
+            predictions_class = [cls_buf[k].clone() for k in range(n_calls)]
+            predictions_mask = [logit_buf[k].clone() for k in range(n_calls)]
+            if self.use_self_mask:
+                out_mask = fixed.clone()
+                for m in input_dict.keys():
+                    if m not in ("query", "prompt"):
+                        input_dict[m][1] = out_mask      # reference: attn_mask.repeat_interleave(H, 0), see below
+            if isinstance(voxel_feat, list):
+                input_dict["voxel"][0] = voxel_feat[L - 1]
+            return q32.view(B, N, D).clone(), predictions_class, predictions_mask
+
+        # ---------------- generic mask_head callable: eager loop
         project_memories()
         attn_mask = None
         for _block in range(self.num_blocks):
@@ -490,6 +529,21 @@ class QueryMaskEncoder(nn.Module):
                     input_dict["voxel"][0] = voxel_feat[i]
                 run_layer(i)
         return q32.view(B, N, D).clone(), predictions_class, predictions_mask
+
+    @staticmethod
+    def _own_mask_head(mask_head):
+        """Our MaskHeadSegLevel wired the way Query3DUnified wires it (functools.partial with keyword tensors,
+        predictions enabled, no offline masks) -> the module, else None."""
+        import functools
+        from .mask_head import MaskHeadSegLevel
+        if not isinstance(mask_head, functools.partial) or mask_head.args:
+            return None
+        owner = getattr(mask_head.func, "__self__", mask_head.func)
+        kw = mask_head.keywords
+        if (not isinstance(owner, MaskHeadSegLevel) or kw.get("skip_prediction", False)
+                or kw.get("offline_attn_masks") is not None or "seg_fts_for_match" not in kw or "seg_masks" not in kw):
+            return None
+        return owner
 
     def _run_body(self, ws: dict, body: Callable):
         """First call per shape: eager (allocates the workspace, configures kernels).  Second call:
