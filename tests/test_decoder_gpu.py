@@ -157,6 +157,43 @@ def test_c3_matches_oracle_on_gpu(c3):
     check_close("c3 (B=4,N=100,S=2048,[mv,pc,voxel,prompt],mixed)", base, ref32, ref16)
 
 
+def test_c4_ragged_selfmask_matches_oracle_on_gpu():
+    """BASELINE config 4 at full size: ragged scenes (S_b in [128, 4096]), 200 queries (two query tiles), in-loop mask
+    head, per-query self masks with the all-masked-row fix-up, trailing padding tiles skipped — whole loop in one graph."""
+    from functools import partial
+    from pq3d_b200.mask_head import MaskHeadSegLevel
+    w = synth.workload("c4")
+    w.num_layers = 2                               # the mask feedback loop is chaotic; two layers keep bf16 noise bounded
+    sd = synth.decoder_state_dict(w, seed=0, sharp=1.0)
+    sd_mh = synth.draw_state_dict(synth.mask_head_param_shapes(3), 100)
+    enc = build_decoder(w, sd)
+    mh = MaskHeadSegLevel(None, 768, 201, memories_for_match=list(w.memories), filter_out_classes=[0, 2]).eval()
+    mh.load_state_dict(sd_mh, strict=True)
+    mh = mh.to(DEV)
+    inp, pw, d = synth.make_decoder_inputs(w, device=DEV)
+    seg_masks = (~d["seg_pad_masks"]).to(DEV)
+    head = partial(mh, seg_fts_for_match=C.mask_head_inputs(w, inp), seg_masks=seg_masks, offline_attn_masks=None,
+                   skip_prediction=False)
+    outs = []
+    with torch.no_grad():
+        for _ in range(3):                         # eager, capture, replay
+            q, pc, pm = enc(synth.clone_input_dict(inp), pw, head)
+            outs.append((q, pm[0].clone(), pm[-1].clone()))
+    torch.cuda.synchronize()
+    assert torch.equal(outs[0][0], outs[2][0]) and torch.equal(outs[1][2], outs[2][2]), "graph replay differs from eager"
+    sdd, sdm = C.to_dev(sd, DEV), C.to_dev(sd_mh, DEV)
+    cfg = O.DecoderCfg(**w.decoder_kwargs())
+    ohead = partial(O.mask_head_seg_level, sd=sdm, prefix="", seg_fts_for_match=C.mask_head_inputs(w, inp),
+                    seg_masks=seg_masks, filter_out_classes=[0, 2])
+    torch.backends.cuda.matmul.allow_tf32 = False
+    with torch.no_grad():
+        r32 = O.query_mask_encoder(sdd, cfg, synth.clone_input_dict(inp), pw, ohead)
+    r16 = oracle_autocast(lambda: O.query_mask_encoder(sdd, cfg, synth.clone_input_dict(inp), pw, ohead))
+    check_close("c4.pred_mask_first", outs[2][1], r32[2][0], r16[2][0])
+    check_close("c4.query", outs[2][0], r32[0], r16[0])
+    assert len(pm) == len(r32[2]) == 2
+
+
 def test_c3_padding_invariance(c3):
     """Appending masked tokens must not change the output beyond tile-order rounding."""
     w, sd, enc, inp, pw, base = c3
