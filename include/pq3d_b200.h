@@ -55,6 +55,16 @@ int pq3d_linear_bf16(const void* A, int64_t lda, int64_t a_rows_total, int64_t a
                      int M, int N, int K, int groups, float alpha, int alpha_ncols, int relu,
                      int block_n, void* stream);
 
+/* Strided batched GEMM on the same kernel: C[g1,g2] = alpha * A[g1,g2] · W[g1,g2]ᵀ for G1 x G2 problems whose operands
+ * are strided views, e.g. the per-(scene, head) slices of [tokens, heads*64] tensors.  Element (g1, g2, row, k) of A at
+ * A[g1*a_g1_stride + g2*a_g2_stride + row*a_row_stride + k] (strides in elements, all 16-byte granular, non-zero);
+ * same for W (rows = N) and C.  K multiple of 64.  Used by the attention backward products (dP = dO·Vᵀ, dV = Pᵀ·dO,
+ * dQ = dS·K, dK = dSᵀ·Q — torch autograd of torch/nn/functional.py:6630-6647 in the reference's training step). */
+int pq3d_bgemm_bf16(const void* A, int64_t a_row_stride, int64_t a_g2_stride, int64_t a_g1_stride,
+                    const void* W, int64_t w_row_stride, int64_t w_g2_stride, int64_t w_g1_stride,
+                    void* C, int64_t c_row_stride, int64_t c_g2_stride, int64_t c_g1_stride, int out_fp32,
+                    int M, int N, int K, int G2, int G1, float alpha, int block_n, void* stream);
+
 /* Masked softmax attention for n_mem (<= 4) memories in one launch, head_dim = 64.
  *   Q : bf16 [B*Nq, ldq]; memory i / head h at columns i*q_mem_stride + h*64; already scaled by
  *       log2(e)/sqrt(64) — scores are handled in the log2 domain (a probability is one ex2)
@@ -70,6 +80,9 @@ int pq3d_linear_bf16(const void* A, int64_t lda, int64_t a_rows_total, int64_t a
  *   score_bias (or NULL): fp32 [B,H,Nq,bias_ld], log2 domain, added to the scores before masking, rows padded to a
  *              multiple of 128 keys — the spatial term of MultiHeadAttentionSpatial 'mul'
  *              (modules/layers/transformers.py:231-233), produced by pq3d_spatial_bias.
+ *   stat_m / stat_l (or NULL): fp32 [n_mem][B][H][Nq] (memory stride stat_mem_stride) receive, per row, the softmax
+ *              reference m (log2 domain) and the denominator l (zero-attn term included): P = ex2(s - m) / l —
+ *              what the backward needs to recompute the probabilities.
  * Replaces torch/nn/functional.py:6630-6647 as called from CrossAttentionLayer.forward_post
  * (modules/grounding/query_encoder.py:297-303) and modules/layers/transformers.py:193-237. */
 int pq3d_attention_fwd(int n_mem, const void* Q, int64_t ldq, int64_t q_mem_stride,
@@ -79,7 +92,8 @@ int pq3d_attention_fwd(int n_mem, const void* Q, int64_t ldq, int64_t q_mem_stri
                        const uint32_t* const* mask_bits, const int64_t* mask_b_stride,
                        const int64_t* mask_h_stride, const int64_t* mask_q_stride, const int32_t* const* kv_tiles,
                        void* O, int64_t ldo, int64_t o_mem_stride, int B, int H, int Nq, int zero_attn,
-                       const float* score_bias, int64_t bias_ld, void* stream);
+                       const float* score_bias, int64_t bias_ld, float* stat_m, float* stat_l,
+                       int64_t stat_mem_stride, void* stream);
 
 /* Score bias of MultiHeadAttentionSpatial 'mul' for L layers at once:
  * out[l,b,h,n,m] = log2(max(relu(pairwise_locs[b,n,m,:] · loc_w[l,h,:] + loc_b[l,h]), 1e-6)), rows padded to ld
@@ -137,6 +151,44 @@ int pq3d_fourier_pos(const float* xyz, int xyz_stride, const float* coord_min, c
  * d = sqrt(|ci-cj|^2 + eps), d2 over xy.  Replaces calc_pairwise_locs(..., 'center', spatial_dist_norm=True,
  * spatial_dim=5), modules/utils.py:38-68. */
 int pq3d_pairwise_locs(const float* centers, int c_stride, float* out, int B, int N, float eps, void* stream);
+
+/* ---- backward companions (training step: autograd of the reference's decoder, trainer/query3d_trainer.py:18-28) ---- */
+
+/* out_t[b1,b2][c][r] = bf16(scale * in[b1,b2][r][c] * (gate > 0 ? 1 : 0)) for r < R, zero for R <= r < Rp; optional
+ * un-transposed bf16 copy out_c.  in: fp32 (in_fp32) or bf16; gate (optional, bf16, same indexing as in): ReLU backward.
+ * Puts activations / gradients into the K-major layout pq3d_linear_bf16 needs for wgrad (dW = dYᵀ·X). */
+int pq3d_transpose_cast(const void* in, int in_fp32, int64_t ld_in, int64_t in_b1, int64_t in_b2,
+                        const void* gate, int64_t ld_gate, int64_t gate_b1, int64_t gate_b2,
+                        void* out_t, int64_t ld_t, int64_t t_b1, int64_t t_b2,
+                        void* out_c, int64_t ld_c, int64_t c_b1, int64_t c_b2,
+                        int R, int C, int Rp, int B1, int B2, float scale, void* stream);
+
+/* out[c] (+)= sum_r in[r][c] — bias gradients. */
+int pq3d_colsum(const float* in, int64_t ld, float* out, int R, int C, int accumulate, void* stream);
+
+/* Backward of pq3d_add_layernorm: d_x[g] (grad of residual + y[g]), d_res = sum_g d_x[g], d_gamma / d_beta accumulated
+ * with atomics into zero-initialised fp32 [G,D].  Any output may be NULL. */
+int pq3d_layernorm_bwd(const float* y, int64_t y_group_stride, const float* residual, const float* gamma,
+                       const float* d_out, int G, float eps, int R, int D, float* d_x, int64_t dx_group_stride,
+                       float* d_res, float* d_gamma, float* d_beta, void* stream);
+
+/* delta[b,h,n] = sum_d dO[b*N+n, h*64+d] * O[b*N+n, h*64+d] (bf16 in, fp32 out). */
+int pq3d_attn_delta(const void* dO, const void* O, int64_t ld, float* delta, int B, int H, int N, void* stream);
+
+/* Softmax backward on recomputed scores: P = ex2(S2 + bias - m)/l (0 where masked), dS2 = ln2 * P * (dP - delta);
+ * S2, dP fp32 [B,H,N,ld]; outputs bf16 P, dS [B,H,N,ld] and transposed Pt, dSt [B,H,ld,Np] (columns n >= N zero). */
+int pq3d_softmax_bwd(const float* S2, const float* dP, const float* delta, const float* m, const float* l,
+                     const float* bias, int64_t bias_ld, const uint32_t* mask_bits, int64_t mask_b_stride,
+                     int64_t mask_h_stride, int64_t mask_q_stride, void* P, void* dS, void* Pt, void* dSt,
+                     int B, int H, int N, int S, int ld, int Np, void* stream);
+
+/* Gradients of pairwise_loc_fc (modules/layers/transformers.py:196-199) from dS2 of the spatial self-attention:
+ * d_w [H,5], d_b [H] accumulated with atomics (zero-initialise). */
+int pq3d_spatial_bias_bwd(const float* pairwise_locs, const float* loc_w, const float* loc_b, const void* dS,
+                          int64_t ld, float* d_w, float* d_b, int B, int H, int N, void* stream);
+
+/* out = a + b (+ c), fp32, n multiple of 4. */
+int pq3d_add3(const float* a, const float* b, const float* c, float* out, int64_t n, void* stream);
 
 #ifdef __cplusplus
 }

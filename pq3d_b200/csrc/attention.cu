@@ -75,6 +75,8 @@ struct AttnParams {
   int32_t force_two_pass;      // testing hook: never take the ONE_PASS schedule
   const float* score_bias;     // [B, H, Nq, bias_ld] fp32 (log2 domain) added to the scores, or null
   int64_t bias_ld;
+  float *stat_m, *stat_l;      // optional [n_mem][B][H][Nq]: softmax reference and denominator, saved for the backward
+  int64_t stat_mem_stride;
   unsigned long long* dbg;
 };
 
@@ -326,6 +328,11 @@ __device__ __forceinline__ bool attn_softmax(const AttnParams& p, const AttnMem&
   const bool overflow = (MODE == kOnePass) && !(l < 1.2676506e30f);   // 2^100; also catches inf / NaN
   if (p.zero_attn) l += ex2_approx(-m);
   const float inv = 1.f / l;
+  if (p.stat_m != nullptr && cc == 0 && n < p.Nq) {
+    const int64_t si = c.mi * p.stat_mem_stride + (static_cast<int64_t>(c.b) * p.H + c.h) * p.Nq + n;
+    p.stat_m[si] = m;
+    p.stat_l[si] = l;
+  }
   mbar_wait(c.o_full, 0, 330);
   tc_fence_after();
   if (cc < 2) {                                  // 64 output columns: two of the four warps per quadrant
@@ -511,7 +518,8 @@ extern "C" int pq3d_attention_fwd(int n_mem, const void* Q, int64_t ldq, int64_t
                                   const int64_t* mask_h_stride, const int64_t* mask_q_stride,
                                   const int32_t* const* kv_tiles, void* O, int64_t ldo,
                                   int64_t o_mem_stride, int B, int H, int Nq, int zero_attn, const float* score_bias,
-                                  int64_t bias_ld, void* stream) {
+                                  int64_t bias_ld, float* stat_m, float* stat_l, int64_t stat_mem_stride,
+                                  void* stream) {
   PQ3D_CHECK_ARG(n_mem >= 1 && n_mem <= kMaxMem, "pq3d_attention_fwd: n_mem=%d not in [1,%d]", n_mem, kMaxMem);
   PQ3D_CHECK_ARG(Q && O && K && Vt && S && S_pitch && Vt_pitch, "pq3d_attention_fwd: null argument");
   PQ3D_CHECK_ARG(B > 0 && H > 0 && Nq > 0, "pq3d_attention_fwd: bad shape B=%d H=%d Nq=%d", B, H, Nq);
@@ -580,6 +588,10 @@ extern "C" int pq3d_attention_fwd(int n_mem, const void* Q, int64_t ldq, int64_t
   p.force_two_pass = g_force_two_pass;
   p.score_bias = score_bias;
   p.bias_ld = bias_ld;
+  p.stat_m = stat_m;
+  p.stat_l = stat_l;
+  p.stat_mem_stride = stat_mem_stride;
+  PQ3D_CHECK_ARG((stat_m == nullptr) == (stat_l == nullptr), "pq3d_attention_fwd: stat_m and stat_l go together");
   p.dbg = g_attn_timeline;
   static bool configured = false;
   if (!configured) {

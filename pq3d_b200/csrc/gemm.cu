@@ -22,6 +22,7 @@
 // Groups shift the A / W / C / bias bases: per-memory out-projections, per-layer multi-scale voxel
 // K/V projections, per-scene V^T and mask-logit products run as one launch.
 #include <cstdlib>
+#include <cstring>
 
 #include "host_common.h"
 #include "ptx.cuh"
@@ -47,6 +48,8 @@ struct LinearParams {
   float alpha;
   int32_t tma_store;        // C is 16-byte granular: epilogue goes through shared memory + TMA store
   unsigned long long* dbg;  // optional per-CTA timeline (pq3d_debug_set_timeline), 8 slots per CTA
+  int32_t batched;          // operands / result addressed through 4-D tensor maps {inner, rows, g2, g1} (pq3d_bgemm_bf16)
+  int32_t G2;               // size of the inner group level when batched (group g -> g1 = g / G2, g2 = g % G2)
   int32_t dbg_flags;        // PQ3D_GEMM_DEBUG: 1 = skip the TMA stores, 2 = skip staging + stores (WRONG RESULTS; timing only)
 };
 
@@ -149,8 +152,14 @@ linear_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
             tma_load_2d_pair(sa + Cfg::kABytes, &tmap_w, lead_bar, kb * kBlockK, w_row + rank * (BN / CL));
           } else {
             mbar_arrive_expect_tx(&full_bar[s], Cfg::kStageBytes);
-            tma_load_2d(sa, &tmap_a, &full_bar[s], kb * kBlockK, a_row);
-            tma_load_2d(sa + Cfg::kABytes, &tmap_w, &full_bar[s], kb * kBlockK, w_row);
+            if (p.batched) {      // strided batches: per-group offsets live in the tensor maps' outer dimensions
+              const int m_tile = (rem / p.num_n) * kBlockM, n_tile = (rem % p.num_n) * BN;
+              tma_load_4d(sa, &tmap_a, &full_bar[s], kb * kBlockK, m_tile, g % p.G2, g / p.G2);
+              tma_load_4d(sa + Cfg::kABytes, &tmap_w, &full_bar[s], kb * kBlockK, n_tile, g % p.G2, g / p.G2);
+            } else {
+              tma_load_2d(sa, &tmap_a, &full_bar[s], kb * kBlockK, a_row);
+              tma_load_2d(sa + Cfg::kABytes, &tmap_w, &full_bar[s], kb * kBlockK, w_row);
+            }
           }
         }
       }
@@ -275,7 +284,8 @@ linear_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         fence_proxy_async_smem();
         __syncwarp();
         if (r == 0 && !(p.dbg_flags & 3)) {
-          tma_store_3d(&tmap_c, box, n0 + c0, m0 + quad * 32, g);
+          if (p.batched) tma_store_4d(&tmap_c, box, n0 + c0, m0 + quad * 32, g % p.G2, g / p.G2);
+          else tma_store_3d(&tmap_c, box, n0 + c0, m0 + quad * 32, g);
           tma_store_commit();
         }
       };
@@ -458,6 +468,8 @@ extern "C" int pq3d_linear_bf16(const void* A, int64_t lda, int64_t a_rows_total
     return e == nullptr ? 0 : atoi(e);
   }();
   p.dbg_flags = dbg_flags;
+  p.batched = 0;
+  p.G2 = 1;
   const int esz = out_fp32 ? 4 : 2;
   p.tma_store = ((reinterpret_cast<uintptr_t>(C) & 15) == 0) && ((ldc * esz) % 16 == 0) &&
                 ((c_group_stride * esz) % 16 == 0);
@@ -476,5 +488,84 @@ extern "C" int pq3d_linear_bf16(const void* A, int64_t lda, int64_t a_rows_total
     case 64: return launch_linear<64, 1>(ta, tw, tc, p, st);
     case 128: return launch_linear<128, 1>(ta, tw, tc, p, st);
     default: return cl == 2 ? launch_linear<256, 2>(ta, tw, tc, p, st) : launch_linear<256, 1>(ta, tw, tc, p, st);
+  }
+}
+
+// Strided batched GEMM: C[g1,g2] = alpha * A[g1,g2] · W[g1,g2]ᵀ for G1 x G2 independent problems whose operands are
+// strided views (e.g. per-(scene, head) slices of [tokens, heads*64] tensors).  Same kernel; the per-group offsets are
+// the outer two dimensions of 4-D tensor maps, so rows past M / N are zero-filled on load and clipped on store PER GROUP.
+extern "C" int pq3d_bgemm_bf16(const void* A, int64_t a_row_stride, int64_t a_g2_stride, int64_t a_g1_stride,
+                               const void* W, int64_t w_row_stride, int64_t w_g2_stride, int64_t w_g1_stride, void* C,
+                               int64_t c_row_stride, int64_t c_g2_stride, int64_t c_g1_stride, int out_fp32, int M,
+                               int N, int K, int G2, int G1, float alpha, int block_n, void* stream) {
+  PQ3D_CHECK_ARG(A && W && C, "pq3d_bgemm_bf16: null operand");
+  PQ3D_CHECK_ARG(M > 0 && N > 0 && K > 0 && G1 > 0 && G2 > 0 && K % kBlockK == 0,
+                 "pq3d_bgemm_bf16: bad shape M=%d N=%d K=%d G1=%d G2=%d (K must be a multiple of %d)", M, N, K, G1, G2,
+                 kBlockK);
+  const int esz = out_fp32 ? 4 : 2;
+  auto ok16 = [](int64_t elems, int sz) { return (elems * sz) % 16 == 0; };
+  PQ3D_CHECK_ARG(ok16(a_row_stride, 2) && ok16(a_g2_stride, 2) && ok16(a_g1_stride, 2) && ok16(w_row_stride, 2) &&
+                     ok16(w_g2_stride, 2) && ok16(w_g1_stride, 2) && ok16(c_row_stride, esz) &&
+                     ok16(c_g2_stride, esz) && ok16(c_g1_stride, esz) &&
+                     (reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0 &&
+                     (reinterpret_cast<uintptr_t>(C) & 15) == 0,
+                 "pq3d_bgemm_bf16: every base pointer and stride must be 16-byte granular");
+  if (block_n == 0) {
+    const int64_t t256 = (int64_t)((M + 127) / 128) * ((N + 255) / 256) * G1 * G2;
+    const int64_t t128 = (int64_t)((M + 127) / 128) * ((N + 127) / 128) * G1 * G2;
+    block_n = (N > 128 && t256 >= sm_count()) ? 256 : ((N > 64 && t128 >= sm_count()) ? 128 : 64);
+  }
+  PQ3D_CHECK_ARG(block_n == 64 || block_n == 128 || block_n == 256, "pq3d_bgemm_bf16: block_n=%d", block_n);
+  // a stride of 0 elements (broadcast operand) is not representable in a tensor map: use a dimension of extent 1
+  auto dim_of = [](int64_t stride, int n) { return stride == 0 ? 1 : n; };
+  auto str_of = [](int64_t stride, int64_t fallback) { return stride == 0 ? fallback : stride; };
+  CUtensorMap ta, tw, tc;
+  {
+    uint64_t dims[4] = {(uint64_t)K, (uint64_t)M, (uint64_t)dim_of(a_g2_stride, G2), (uint64_t)dim_of(a_g1_stride, G1)};
+    uint64_t strides[3] = {(uint64_t)a_row_stride * 2, (uint64_t)str_of(a_g2_stride, a_row_stride) * 2,
+                           (uint64_t)str_of(a_g1_stride, a_row_stride) * 2};
+    uint32_t box[4] = {(uint32_t)kBlockK, (uint32_t)kBlockM, 1u, 1u};
+    int rc = make_tmap_bf16(&ta, A, 4, dims, strides, box);
+    if (rc != PQ3D_OK) return rc;
+  }
+  {
+    uint64_t dims[4] = {(uint64_t)K, (uint64_t)N, (uint64_t)dim_of(w_g2_stride, G2), (uint64_t)dim_of(w_g1_stride, G1)};
+    uint64_t strides[3] = {(uint64_t)w_row_stride * 2, (uint64_t)str_of(w_g2_stride, w_row_stride) * 2,
+                           (uint64_t)str_of(w_g1_stride, w_row_stride) * 2};
+    uint32_t box[4] = {(uint32_t)kBlockK, (uint32_t)block_n, 1u, 1u};
+    int rc = make_tmap_bf16(&tw, W, 4, dims, strides, box);
+    if (rc != PQ3D_OK) return rc;
+  }
+  {
+    uint64_t dims[4] = {(uint64_t)N, (uint64_t)M, (uint64_t)G2, (uint64_t)G1};
+    uint64_t strides[3] = {(uint64_t)c_row_stride * esz, (uint64_t)c_g2_stride * esz, (uint64_t)c_g1_stride * esz};
+    uint32_t box[4] = {(uint32_t)(128 / esz), 32u, 1u, 1u};
+    int rc = make_tmap(&tc, C, esz, 4, dims, strides, box);
+    if (rc != PQ3D_OK) return rc;
+  }
+  PQ3D_CHECK_ARG(a_g2_stride != 0 && a_g1_stride != 0 && w_g2_stride != 0 && w_g1_stride != 0,
+                 "pq3d_bgemm_bf16: broadcast (zero-stride) operands are not supported; pass G=1 for that level");
+  LinearParams p;
+  memset(&p, 0, sizeof(p));
+  p.C = C;
+  p.M = M;
+  p.N = N;
+  p.K = K;
+  p.num_m = (M + kBlockM - 1) / kBlockM;
+  p.num_n = (N + block_n - 1) / block_n;
+  p.num_tiles = p.num_m * p.num_n * G1 * G2;
+  p.out_fp32 = out_fp32;
+  p.alpha = alpha;
+  p.alpha_ncols = alpha == 1.f ? 0 : N;
+  p.tma_store = 1;
+  p.batched = 1;
+  p.G2 = G2;
+  p.ldc = c_row_stride;
+  p.dbg = nullptr;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  switch (block_n) {
+    case 64: return launch_linear<64, 1>(ta, tw, tc, p, st);
+    case 128: return launch_linear<128, 1>(ta, tw, tc, p, st);
+    default: return launch_linear<256, 1>(ta, tw, tc, p, st);
   }
 }

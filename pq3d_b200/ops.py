@@ -5,7 +5,7 @@ All launches go to torch's current CUDA stream, so they are CUDA-graph capturabl
 from __future__ import annotations
 
 import ctypes as C
-from typing import List, Optional, Sequence
+from typing import List, Optional, Sequence, Tuple
 
 import torch
 
@@ -74,6 +74,27 @@ def linear(A: torch.Tensor, W: torch.Tensor, out: torch.Tensor, *, M: int, N: in
     return out
 
 
+def bgemm(A: torch.Tensor, W: torch.Tensor, C: torch.Tensor, *, alpha: float = 1.0, block_n: int = 0) -> torch.Tensor:
+    """C[g1, g2] = alpha * A[g1, g2] @ W[g1, g2].T over 4-D strided views (G1, G2, rows, K) with unit inner stride."""
+    _chk(A, bf16, "A", 4)
+    _chk(W, bf16, "W", 4)
+    if C.dtype not in (bf16, torch.float32) or C.ndim != 4:
+        raise TypeError("C must be a 4-D bf16 or fp32 tensor")
+    G1, G2, M, K = A.shape
+    N = W.shape[2]
+    if tuple(W.shape) != (G1, G2, N, K) or tuple(C.shape) != (G1, G2, M, N):
+        raise ValueError(f"bgemm shape mismatch: A {tuple(A.shape)} W {tuple(W.shape)} C {tuple(C.shape)}")
+    if A.stride(3) != 1 or W.stride(3) != 1 or C.stride(3) != 1:
+        raise ValueError("bgemm operands need unit inner stride")
+    rc = _lib.lib().pq3d_bgemm_bf16(
+        A.data_ptr(), A.stride(2), A.stride(1), A.stride(0), W.data_ptr(), W.stride(2), W.stride(1), W.stride(0),
+        C.data_ptr(), C.stride(2), C.stride(1), C.stride(0), int(C.dtype == torch.float32), M, N, K, G2, G1,
+        float(alpha), block_n, _stream())
+    _lib.check(rc, "pq3d_bgemm_bf16")
+    _count()
+    return C
+
+
 class AttnMemory:
     """One memory's projected operands for `attention` (see pq3d_attention_fwd)."""
     __slots__ = ("K", "k_col0", "Vt", "vt_row0", "S", "S_pitch", "Vt_pitch", "mask_bits", "mask_b_stride",
@@ -90,7 +111,8 @@ class AttnMemory:
 
 
 def attention(Q: torch.Tensor, q_mem_stride: int, mems: Sequence[AttnMemory], O: torch.Tensor, o_mem_stride: int,
-              B: int, H: int, Nq: int, zero_attn: bool, score_bias: Optional[torch.Tensor] = None) -> torch.Tensor:
+              B: int, H: int, Nq: int, zero_attn: bool, score_bias: Optional[torch.Tensor] = None,
+              stats: Optional[Tuple[torch.Tensor, torch.Tensor]] = None) -> torch.Tensor:
     """score_bias: optional fp32 (B, H, Nq, ld) added to the scores (ld = keys padded to a multiple of 128)."""
     _chk(Q, bf16, "Q", 2)
     _chk(O, bf16, "O")
@@ -120,7 +142,9 @@ def attention(Q: torch.Tensor, q_mem_stride: int, mems: Sequence[AttnMemory], O:
         i64(*[m.mask_b_stride for m in mems]), i64(*[m.mask_h_stride for m in mems]),
         i64(*[m.mask_q_stride for m in mems]),
         vp(*[_p(m.kv_tiles) for m in mems]) if any(m.kv_tiles is not None for m in mems) else None,
-        O.data_ptr(), O.stride(-2), o_mem_stride, B, H, Nq, int(zero_attn), _p(score_bias), bias_ld, _stream())
+        O.data_ptr(), O.stride(-2), o_mem_stride, B, H, Nq, int(zero_attn), _p(score_bias), bias_ld,
+        None if stats is None else stats[0].data_ptr(), None if stats is None else stats[1].data_ptr(),
+        0 if stats is None else B * H * Nq, _stream())
     _lib.check(rc, "pq3d_attention_fwd")
     _count()
     return O
@@ -256,3 +280,86 @@ def pairwise_locs(centers: torch.Tensor, out: Optional[torch.Tensor] = None, eps
     _lib.check(rc, "pq3d_pairwise_locs")
     _count()
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# backward companions
+# ------------------------------------------------------------------------------------------------
+def pad64(n: int) -> int:
+    return (n + 63) // 64 * 64
+
+
+def transpose_cast(x: torch.Tensor, out_t: Optional[torch.Tensor], out_c: Optional[torch.Tensor] = None,
+                   gate: Optional[torch.Tensor] = None, scale: float = 1.0):
+    """x: (B1, B2, R, C) strided view (fp32 or bf16, unit inner stride).  out_t: (B1, B2, C, Rp) bf16 receives the
+    transpose (columns R..Rp zero), out_c: (B1, B2, R, C) bf16 the cast copy; gate (bf16, like x): ReLU backward."""
+    if x.ndim == 2:
+        x = x[None, None]
+        out_t = None if out_t is None else out_t[None, None]
+        out_c = None if out_c is None else out_c[None, None]
+        gate = None if gate is None else gate[None, None]
+    if x.dtype not in (torch.float32, bf16) or x.stride(3) != 1:
+        raise TypeError("transpose_cast input must be fp32/bf16 with unit inner stride")
+    B1, B2, R, Cc = x.shape
+    Rp = R if out_t is None else out_t.shape[3]
+    for t, nm in ((out_t, "out_t"), (out_c, "out_c"), (gate, "gate")):
+        if t is not None:
+            _chk(t, bf16, nm, 4)
+            if t.stride(3) != 1:
+                raise ValueError(f"{nm} needs unit inner stride")
+
+    def st(t):
+        return (0, 0, 0) if t is None else (t.stride(2), t.stride(0), t.stride(1))
+    rc = _lib.lib().pq3d_transpose_cast(x.data_ptr(), int(x.dtype == torch.float32), x.stride(2), x.stride(0), x.stride(1),
+                                        _p(gate), *st(gate), _p(out_t), *st(out_t), _p(out_c), *st(out_c), R, Cc, Rp,
+                                        B1, B2, float(scale), _stream())
+    _lib.check(rc, "pq3d_transpose_cast")
+    _count()
+
+
+def colsum(x: torch.Tensor, out: torch.Tensor, accumulate: bool = False):
+    _chk(x, torch.float32, "x", 2)
+    _chk(out, torch.float32, "out")
+    rc = _lib.lib().pq3d_colsum(x.data_ptr(), x.stride(0), out.data_ptr(), x.shape[0], x.shape[1], int(accumulate), _stream())
+    _lib.check(rc, "pq3d_colsum")
+    _count()
+
+
+def layernorm_bwd(y, residual, gamma, d_out, eps, R, D, G=1, y_group_stride=0, d_x=None, dx_group_stride=0, d_res=None,
+                  d_gamma=None, d_beta=None):
+    rc = _lib.lib().pq3d_layernorm_bwd(_p(y), y_group_stride, _p(residual), gamma.data_ptr(), d_out.data_ptr(), G,
+                                       float(eps), R, D, _p(d_x), dx_group_stride, _p(d_res), _p(d_gamma), _p(d_beta),
+                                       _stream())
+    _lib.check(rc, "pq3d_layernorm_bwd")
+    _count()
+
+
+def attn_delta(dO: torch.Tensor, O: torch.Tensor, delta: torch.Tensor, B: int, H: int, N: int):
+    _chk(dO, bf16, "dO", 2)
+    _chk(O, bf16, "O", 2)
+    rc = _lib.lib().pq3d_attn_delta(dO.data_ptr(), O.data_ptr(), dO.stride(0), delta.data_ptr(), B, H, N, _stream())
+    _lib.check(rc, "pq3d_attn_delta")
+    _count()
+
+
+def softmax_bwd(S2, dP, delta, m, l, P, dS, Pt, dSt, B, H, N, S, ld, Np, bias=None, mask_bits=None,
+                mask_strides=(0, 0, 0)):
+    rc = _lib.lib().pq3d_softmax_bwd(S2.data_ptr(), dP.data_ptr(), delta.data_ptr(), m.data_ptr(), l.data_ptr(),
+                                     _p(bias), 0 if bias is None else bias.shape[-1], _p(mask_bits), *mask_strides,
+                                     P.data_ptr(), dS.data_ptr(), Pt.data_ptr(), dSt.data_ptr(), B, H, N, S, ld, Np,
+                                     _stream())
+    _lib.check(rc, "pq3d_softmax_bwd")
+    _count()
+
+
+def spatial_bias_bwd(pairwise_locs, loc_w, loc_b, dS, ld, d_w, d_b, B, H, N):
+    rc = _lib.lib().pq3d_spatial_bias_bwd(pairwise_locs.data_ptr(), loc_w.data_ptr(), loc_b.data_ptr(), dS.data_ptr(), ld,
+                                          d_w.data_ptr(), d_b.data_ptr(), B, H, N, _stream())
+    _lib.check(rc, "pq3d_spatial_bias_bwd")
+    _count()
+
+
+def add3(a, b, c, out):
+    rc = _lib.lib().pq3d_add3(a.data_ptr(), b.data_ptr(), _p(c), out.data_ptr(), out.numel(), _stream())
+    _lib.check(rc, "pq3d_add3")
+    _count()

@@ -97,6 +97,38 @@ def check_gemm_pair():
     _gemm_case(8192, 1024, 256, 256, torch.float32, relu=True, seed=44)
 
 
+def check_bgemm():
+    """Strided batched GEMM: per-(scene, head) slices of packed [tokens, heads*64] tensors, ragged M / N per group."""
+    g = gen(50)
+    B, H, N, S, D = 3, 4, 100, 300, 256
+    Q = rnd((B * N, D), g).bfloat16()                 # [B*N, H*64]
+    Kt = rnd((B * S, 2 * D), g).bfloat16()            # [B*S, L*H*64], use layer 1
+    # scores[b,h] = Q_bh [N,64] @ K_bh[S,64]^T  (fp32 out)
+    A = Q.view(B, N, H, 64).permute(0, 2, 1, 3)
+    W = Kt.view(B, S, 2, H, 64)[:, :, 1].permute(0, 2, 1, 3)
+    Sc = torch.full((B, H, N, 304), float("nan"), device=DEV)
+    ops.bgemm(A, W, Sc[..., :S].as_strided((B, H, N, S), Sc.stride()), alpha=0.5)
+    torch.cuda.synchronize()
+    ref = 0.5 * torch.einsum("bhnd,bhsd->bhns", A.double(), W.double())
+    e = rel(Sc[..., :S], ref)
+    assert torch.isnan(Sc[..., S:]).all(), "wrote past N"
+    print(f"bgemm scores (fp32): rel {e:.2e}")
+    assert e <= TOL_F32
+    # dV[b,h] = P^T [S, Np] @ dO^T[64, Np]^T with Np = 128 (zero padded contraction), bf16 out into a packed [B*S, D] tensor
+    Np = 128
+    Pt = torch.zeros(B, H, S, Np, device=DEV, dtype=torch.bfloat16)
+    Pt[..., :N] = rnd((B, H, S, N), g, 0.1).bfloat16()
+    dOt = torch.zeros(B, H, 64, Np, device=DEV, dtype=torch.bfloat16)
+    dOt[..., :N] = rnd((B, H, 64, N), g).bfloat16()
+    dV = torch.full((B * S, D), float("nan"), device=DEV, dtype=torch.bfloat16)
+    ops.bgemm(Pt, dOt, dV.view(B, S, H, 64).permute(0, 2, 1, 3))
+    torch.cuda.synchronize()
+    ref = torch.einsum("bhsn,bhdn->bhsd", Pt.double(), dOt.double())
+    e = rel(dV.view(B, S, H, 64).permute(0, 2, 1, 3), ref)
+    print(f"bgemm dV (bf16, strided store): rel {e:.2e}")
+    assert e <= TOL_BF16
+
+
 def check_gemm_epilogues():
     _gemm_case(3072, 520, 768, 128, torch.bfloat16, bias_along_m=True, seed=8)     # V^T form
     _gemm_case(400, 201, 768, 64, torch.float32, seed=9)                           # cls head: unaligned N
@@ -359,6 +391,133 @@ def check_mask_head_finalize():
     assert torch.equal(logits, ref), f"mask logits differ: {(logits - ref).abs().max()}"
     assert torch.equal(am, ref_am), f"attn mask differs in {(am != ref_am).sum()} places"
     print("mask_head_finalize: bit-exact vs torch")
+
+
+# ------------------------------------------------------------------------------------ backward pieces
+def check_bwd_elementwise():
+    g = gen(60)
+    # transpose_cast with relu gate, 2-level batches over packed heads
+    B, N, H = 3, 100, 4
+    x = rnd((B * N, H * 64), g)
+    gate = rnd((B * N, H * 64), g).bfloat16()
+    xv = x.view(B, N, H, 64).permute(0, 2, 1, 3)
+    gv = gate.view(B, N, H, 64).permute(0, 2, 1, 3)
+    out_t = torch.full((B, H, 64, 128), float("nan"), dtype=torch.bfloat16, device=DEV)
+    out_c = torch.full((B, H, N, 64), float("nan"), dtype=torch.bfloat16, device=DEV)
+    ops.transpose_cast(xv, out_t, out_c, gate=gv, scale=0.5)
+    torch.cuda.synchronize()
+    ref = (0.5 * xv * (gv.float() > 0)).bfloat16()
+    assert torch.equal(out_c, ref) and torch.equal(out_t[..., :N], ref.transpose(2, 3)) and (out_t[..., N:] == 0).all()
+    # 2-D fp32 -> bf16 transpose with padding (wgrad operand)
+    y = rnd((400, 768), g)
+    yt = torch.full((768, 448), float("nan"), dtype=torch.bfloat16, device=DEV)
+    ops.transpose_cast(y, yt)
+    torch.cuda.synchronize()
+    assert torch.equal(yt[:, :400], y.bfloat16().t()) and (yt[:, 400:] == 0).all()
+    # colsum
+    cs = torch.empty(768, device=DEV)
+    ops.colsum(y, cs)
+    ops.colsum(y, cs, accumulate=True)
+    torch.cuda.synchronize()
+    assert rel(cs, 2 * y.double().sum(0)) <= 1e-5
+    # add3
+    a, b, c = rnd((400, 768), g), rnd((400, 768), g), rnd((400, 768), g)
+    o = torch.empty_like(a)
+    ops.add3(a, b, c, o)
+    torch.cuda.synchronize()
+    assert torch.equal(o, a + b + c)
+    print("transpose_cast / colsum / add3: exact")
+
+
+def check_layernorm_bwd():
+    g = gen(61)
+    for (G, R, D) in [(1, 400, 768), (3, 400, 768), (1, 77, 384)]:
+        y = rnd((G, R, D), g).requires_grad_(True)
+        res = rnd((R, D), g).requires_grad_(True)
+        gamma = (1 + 0.1 * rnd((G, D), g)).requires_grad_(True)
+        beta = (0.1 * rnd((G, D), g)).requires_grad_(True)
+        d_out = rnd((R, D), g)
+        out = sum(torch.nn.functional.layer_norm((res + y[i]).double(), (D,), gamma[i].double(), beta[i].double(), 1e-5)
+                  for i in range(G)) / G
+        out.backward(d_out.double())
+        d_x = torch.empty(G, R, D, device=DEV)
+        d_res = torch.empty(R, D, device=DEV)
+        d_g, d_b = torch.zeros(G, D, device=DEV), torch.zeros(G, D, device=DEV)
+        ops.layernorm_bwd(y.detach(), res.detach(), gamma.detach(), d_out, 1e-5, R, D, G=G, y_group_stride=R * D, d_x=d_x,
+                          dx_group_stride=R * D, d_res=d_res, d_gamma=d_g, d_beta=d_b)
+        torch.cuda.synchronize()
+        e = max(rel(d_x, y.grad), rel(d_res, res.grad), rel(d_g, gamma.grad), rel(d_b, beta.grad))
+        print(f"layernorm_bwd G={G} R={R} D={D}: rel {e:.2e}")
+        assert e <= 1e-4
+
+
+def check_attention_bwd():
+    """The attention backward as the decoder composes it: forward kernel (saves m, l), score recompute and the four
+    gradient products on the batched GEMM, softmax backward — against autograd of the fp64 softmax attention."""
+    g = gen(62)
+    B, H, N, S = 2, 3, 100, 300
+    D, Sp, Np, ld = H * 64, ops.pad8(300), 128, ops.pad64(300)
+    ln2 = math.log(2.0)
+    Q2 = rnd((B * N, D), g).bfloat16()                       # log2-domain queries
+    Kb = rnd((B * Sp, D), g).bfloat16()
+    Vb = rnd((B * Sp, D), g).bfloat16()
+    kpm = (torch.rand(B, S, generator=g) < 0.2).to(DEV)
+    bits = ops.pack_mask(kpm)
+    Vt = torch.zeros(D, B * Sp, dtype=torch.bfloat16, device=DEV)
+    Vt.copy_(Vb.t())
+    Kt = Kb.t().contiguous()
+    O = torch.empty(1, B * N, D, dtype=torch.bfloat16, device=DEV)
+    st_m, st_l = torch.empty(B, H, N, device=DEV), torch.empty(B, H, N, device=DEV)
+    ops.attention(Q2, 0, [ops.AttnMemory(Kb, 0, Vt, 0, S, Sp, bits, bits.stride(0), 0, 0)], O, B * N * D, B, H, N, True,
+                  stats=(st_m, st_l))
+    dO = rnd((B * N, D), g).bfloat16()
+    # reference (fp64 autograd)
+    q = Q2.double().view(B, N, H, 64).permute(0, 2, 1, 3).requires_grad_(True)
+    k = Kb.double().view(B, Sp, H, 64)[:, :S].permute(0, 2, 1, 3).requires_grad_(True)
+    v = Vb.double().view(B, Sp, H, 64)[:, :S].permute(0, 2, 1, 3).requires_grad_(True)
+    s = (q @ k.transpose(-1, -2)) * ln2
+    s = s.masked_fill(kpm[:, None, None, :], float("-inf"))
+    s = torch.cat([s, torch.zeros_like(s[..., :1])], -1)
+    pr = torch.softmax(s, -1)[..., :-1]
+    o_ref = pr @ v
+    o_ref.backward(dO.double().view(B, N, H, 64).permute(0, 2, 1, 3))
+    # ours
+    Qv = Q2.view(B, N, H, 64).permute(0, 2, 1, 3)
+    Kv = Kb.view(B, Sp, H, 64).permute(0, 2, 1, 3)[:, :, :S]
+    S2 = torch.zeros(B, H, N, ld, device=DEV)
+    ops.bgemm(Qv, Kv, S2[..., :S].as_strided((B, H, N, S), S2.stride()))
+    dOv = dO.view(B, N, H, 64).permute(0, 2, 1, 3)
+    Vv = Vb.view(B, Sp, H, 64).permute(0, 2, 1, 3)[:, :, :S]
+    dP = torch.zeros(B, H, N, ld, device=DEV)
+    ops.bgemm(dOv, Vv, dP[..., :S].as_strided((B, H, N, S), dP.stride()))
+    delta = torch.empty(B, H, N, device=DEV)
+    ops.attn_delta(dO, O[0], delta, B, H, N)
+    P = torch.empty(B, H, N, ld, dtype=torch.bfloat16, device=DEV)
+    dS = torch.empty_like(P)
+    Pt = torch.empty(B, H, ld, Np, dtype=torch.bfloat16, device=DEV)
+    dSt = torch.empty_like(Pt)
+    ops.softmax_bwd(S2, dP, delta, st_m, st_l, P, dS, Pt, dSt, B, H, N, S, ld, Np, mask_bits=bits,
+                    mask_strides=(bits.stride(0), 0, 0))
+    dOt = torch.empty(B, H, 64, Np, dtype=torch.bfloat16, device=DEV)
+    Q2t = torch.empty(B, H, 64, Np, dtype=torch.bfloat16, device=DEV)
+    ops.transpose_cast(dOv, dOt)
+    ops.transpose_cast(Qv, Q2t)
+    dV = torch.zeros(B * Sp, D, dtype=torch.bfloat16, device=DEV)
+    dK = torch.zeros(B * Sp, D, dtype=torch.bfloat16, device=DEV)
+    dQ = torch.empty(B * N, D, dtype=torch.bfloat16, device=DEV)
+    ops.bgemm(Pt[:, :, :S], dOt, dV.view(B, Sp, H, 64).permute(0, 2, 1, 3)[:, :, :S])
+    ops.bgemm(dSt[:, :, :S], Q2t, dK.view(B, Sp, H, 64).permute(0, 2, 1, 3)[:, :, :S])
+    Ktv = Kt.view(H, 64, B, Sp).permute(2, 0, 1, 3)            # (B, H, 64, Sp): K^T per head
+    Ktp = torch.zeros(B, H, 64, ld, dtype=torch.bfloat16, device=DEV)
+    Ktp[..., :S] = Ktv[..., :S]
+    ops.bgemm(dS, Ktp, dQ.view(B, N, H, 64).permute(0, 2, 1, 3))
+    torch.cuda.synchronize()
+    e_p = rel(P[..., :S], pr)
+    e_v = rel(dV.view(B, Sp, H, 64)[:, :S].permute(0, 2, 1, 3), v.grad)
+    e_k = rel(dK.view(B, Sp, H, 64)[:, :S].permute(0, 2, 1, 3), k.grad)
+    e_q = rel(dQ.view(B, N, H, 64).permute(0, 2, 1, 3), q.grad)
+    print(f"attention backward: P {e_p:.2e}  dV {e_v:.2e}  dK {e_k:.2e}  dQ {e_q:.2e}")
+    assert max(e_p, e_v, e_k, e_q) <= 4 * TOL_BF16       # P, dS and the outputs are each rounded to bf16
 
 
 CHECKS = {k[6:]: v for k, v in list(globals().items()) if k.startswith("check_")}
