@@ -163,8 +163,9 @@ int pq3d_transpose_cast(const void* in, int in_fp32, int64_t ld_in, int64_t in_b
                         void* out_c, int64_t ld_c, int64_t c_b1, int64_t c_b2,
                         int R, int C, int Rp, int B1, int B2, float scale, void* stream);
 
-/* out[c] (+)= sum_r in[r][c] — bias gradients. */
-int pq3d_colsum(const float* in, int64_t ld, float* out, int R, int C, int accumulate, void* stream);
+/* out[c] (+)= sum_r in[r][c] * (gate[r][c] > 0 ? 1 : 0) — bias gradients; in fp32 or bf16, gate optional (bf16). */
+int pq3d_colsum(const void* in, int in_fp32, int64_t ld, const void* gate, int64_t ld_gate, float* out, int R, int C,
+                int accumulate, void* stream);
 
 /* Backward of pq3d_add_layernorm: d_x[g] (grad of residual + y[g]), d_res = sum_g d_x[g], d_gamma / d_beta accumulated
  * with atomics into zero-initialised fp32 [G,D].  Any output may be NULL. */

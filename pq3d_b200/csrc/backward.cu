@@ -62,14 +62,20 @@ __global__ void transpose_cast_kernel(const TransposeParams p) {
 // ------------------------------------------------------------------------------------------------
 // colsum: out[c] (+)= sum_r in[r][c]  (bias gradients).  One block per 32 columns.
 // ------------------------------------------------------------------------------------------------
-__global__ void colsum_kernel(const float* __restrict__ in, int64_t ld, float* __restrict__ out, int R, int C,
-                              int accumulate) {
+__global__ void colsum_kernel(const void* __restrict__ in, int in_fp32, int64_t ld, const __nv_bfloat16* __restrict__ gate,
+                              int64_t ld_gate, float* __restrict__ out, int R, int C, int accumulate) {
   pdl_sync();
   __shared__ float part[8][33];
   const int c = blockIdx.x * 32 + threadIdx.x;
   float s = 0.f;
   if (c < C)
-    for (int r = threadIdx.y; r < R; r += blockDim.y) s += in[static_cast<int64_t>(r) * ld + c];
+    for (int r = threadIdx.y; r < R; r += blockDim.y) {
+      const int64_t off = static_cast<int64_t>(r) * ld + c;
+      float v = in_fp32 ? reinterpret_cast<const float*>(in)[off]
+                        : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(in)[off]);
+      if (gate != nullptr && !(__bfloat162float(gate[static_cast<int64_t>(r) * ld_gate + c]) > 0.f)) v = 0.f;
+      s += v;
+    }
   part[threadIdx.y][threadIdx.x] = s;
   __syncthreads();
   if (threadIdx.y == 0 && c < C) {
@@ -350,10 +356,11 @@ extern "C" int pq3d_transpose_cast(const void* in, int in_fp32, int64_t ld_in, i
   return PQ3D_OK;
 }
 
-extern "C" int pq3d_colsum(const float* in, int64_t ld, float* out, int R, int C, int accumulate, void* stream) {
+extern "C" int pq3d_colsum(const void* in, int in_fp32, int64_t ld, const void* gate, int64_t ld_gate, float* out, int R,
+                           int C, int accumulate, void* stream) {
   PQ3D_CHECK_ARG(in && out && R > 0 && C > 0, "pq3d_colsum: bad argument");
   PQ3D_CUDA(launch_kernel(colsum_kernel, dim3((C + 31) / 32), dim3(32, 8), 0, reinterpret_cast<cudaStream_t>(stream), in,
-                          ld, out, R, C, accumulate));
+                          in_fp32, ld, reinterpret_cast<const __nv_bfloat16*>(gate), ld_gate, out, R, C, accumulate));
   return PQ3D_OK;
 }
 

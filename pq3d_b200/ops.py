@@ -317,10 +317,14 @@ def transpose_cast(x: torch.Tensor, out_t: Optional[torch.Tensor], out_c: Option
     _count()
 
 
-def colsum(x: torch.Tensor, out: torch.Tensor, accumulate: bool = False):
-    _chk(x, torch.float32, "x", 2)
+def colsum(x: torch.Tensor, out: torch.Tensor, accumulate: bool = False, gate: Optional[torch.Tensor] = None):
+    """out[c] (+)= sum_r x[r, c] * (gate[r, c] > 0); x fp32 or bf16 2-D view with unit inner stride."""
+    if x.dtype not in (torch.float32, bf16) or x.ndim != 2 or x.stride(1) != 1:
+        raise TypeError("colsum input must be a 2-D fp32/bf16 view with unit inner stride")
     _chk(out, torch.float32, "out")
-    rc = _lib.lib().pq3d_colsum(x.data_ptr(), x.stride(0), out.data_ptr(), x.shape[0], x.shape[1], int(accumulate), _stream())
+    rc = _lib.lib().pq3d_colsum(x.data_ptr(), int(x.dtype == torch.float32), x.stride(0), _p(gate),
+                                0 if gate is None else gate.stride(0), out.data_ptr(), x.shape[0], x.shape[1],
+                                int(accumulate), _stream())
     _lib.check(rc, "pq3d_colsum")
     _count()
 

@@ -7,8 +7,9 @@ forward signatures as the reference, so a reference checkpoint loads with strict
 (pq3d_b200/registry.py).  nn.Linear / nn.LayerNorm are used purely as parameter containers; all
 arithmetic goes through `pq3d_b200.ops` (there is no PyTorch or CPU fallback).
 
-Scope of this round: the inference path (eval mode, no autograd).  Training-mode forward (dropout,
-memory dropout) and backward kernels are not built yet and raise instead of silently falling back.
+Inference (eval mode, no autograd) replays one CUDA graph per forward.  With gradients enabled the forward and
+backward run through pq3d_b200/train_engine.py (same kernels + backward.cu; dropout-free); what that path does
+not cover raises instead of silently falling back.
 """
 from __future__ import annotations
 
@@ -283,6 +284,7 @@ class QueryMaskEncoder(nn.Module):
         self._packed_key = None
         self._ws: Dict[tuple, dict] = {}
         self.use_cuda_graph = True
+        self.train_dropout = 0.1      # the reference's sublayer dropout; the training path requires 0.0 (no RNG kernels)
         # K / V^T of all layers are hoisted into one grouped GEMM per forward.  Projecting layer by layer (so a
         # layer's 75 MB stays L2-resident for its attention) was measured at config 3: the attention kernel did not
         # speed up (it is bound by TMEM->register bandwidth, not HBM) and the narrower GEMMs cost +63 us/step, so
@@ -328,13 +330,19 @@ class QueryMaskEncoder(nn.Module):
 
     # ---- forward -------------------------------------------------------------------------------
     def forward(self, input_dict: dict, pairwise_locs: Optional[torch.Tensor], mask_head: Optional[Callable] = None):
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            raise NotImplementedError(
-                "pq3d_b200.QueryMaskEncoder: backward kernels are not built yet — call under torch.no_grad() "
-                "(inference path); there is deliberately no PyTorch autograd fallback")
+        if torch.is_grad_enabled() and (any(p.requires_grad for p in self.parameters())
+                                        or input_dict["query"][0].requires_grad):
+            # training path: forward + backward composed from the same kernels (train_engine.py); scope limits raise
+            if mask_head is not None or self.use_self_mask:
+                raise NotImplementedError(
+                    "pq3d_b200.QueryMaskEncoder: the in-loop mask head / use_self_mask have no backward kernels yet — "
+                    "train with mask_head=None, or call under torch.no_grad(); there is deliberately no PyTorch "
+                    "autograd fallback")
+            from . import train_engine
+            return train_engine.run(self, input_dict, pairwise_locs), [], []
         if self.training:
-            raise NotImplementedError("pq3d_b200.QueryMaskEncoder: training-mode forward (dropout / memory dropout) "
-                                      "is not built yet — call .eval()")
+            raise NotImplementedError("pq3d_b200.QueryMaskEncoder: training-mode forward without gradients (dropout / "
+                                      "memory dropout) is not built — call .eval() for inference")
         query, query_masks, query_pos = input_dict["query"]
         dev = query.device
         B, N, D = query.shape

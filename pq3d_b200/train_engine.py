@@ -1,0 +1,467 @@
+"""Training path of the decoder: forward that keeps what the backward needs, and the backward itself,
+both composed from the sm_100a kernels behind the C ABI (no torch autograd through PyTorch ops, no fallback).
+
+What the reference does here is plain autograd through modules/grounding/query_encoder.py (trainer/
+query3d_trainer.py:18-28: forward, loss, backward, AdamW).  This module gives `QueryMaskEncoder` the same
+contract — `enc(input_dict, pairwise_locs)` under grad mode returns a tensor attached to the graph, and
+`loss.backward()` fills `.grad` of every decoder parameter plus the gradients of the query / memory inputs —
+through ONE `torch.autograd.Function` whose backward runs:
+
+  GEMM-shaped work   dgrad  d_x = d_y W        -> pq3d_linear_bf16 with a transposed bf16 weight copy
+                     wgrad  dW = d_y^T x        -> pq3d_linear_bf16 on operands transposed by pq3d_transpose_cast
+                     attention: S2 recompute, dP = dO V^T, dV = P^T dO, dK = dS^T Q, dQ = dS K -> pq3d_bgemm_bf16
+  streaming work     LayerNorm backward, softmax backward (both orientations), bias column sums, the
+                     spatial-bias backward -> backward.cu
+
+Scope (raises otherwise): structures sequential / parallel / mixed, num_blocks = 1, one feature tensor per
+memory, no in-loop mask head, dropout disabled (`enc.train_dropout = 0.0`, memory_dropout = 0).
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+from . import ops
+
+bf16 = torch.bfloat16
+f32 = torch.float32
+
+
+def _e(shape, dtype, dev):
+    return torch.empty(shape, dtype=dtype, device=dev)
+
+
+def _z(shape, dtype, dev):
+    return torch.zeros(shape, dtype=dtype, device=dev)
+
+
+class _Mem:
+    __slots__ = ("name", "S", "Sp", "xk", "xv", "K", "Vt", "bits", "strides", "tiles", "has_pos", "S_pitch")
+
+
+def _heads(t2d: torch.Tensor, B: int, rows: int, pitch: int, H: int, col0: int = 0) -> torch.Tensor:
+    """(B*pitch, ld) row-major tensor -> strided (B, H, rows, 64) view of columns [col0, col0 + H*64)."""
+    ld = t2d.stride(0)
+    return t2d.as_strided((B, H, rows, 64), (pitch * ld, 64, ld, 1), t2d.storage_offset() + col0)
+
+
+class TrainTranspose:
+    """Transposed bf16 weight copies for the dgrad GEMMs, cached per packed-weight object."""
+
+    def __init__(self, pk):
+        self.pk, self.cache = pk, {}
+
+    def get(self, key, w: torch.Tensor) -> torch.Tensor:
+        t = self.cache.get(key)
+        if t is None:
+            t = self.cache[key] = w.t().contiguous()
+        return t
+
+
+# ------------------------------------------------------------------------------------------------
+# forward
+# ------------------------------------------------------------------------------------------------
+def forward(enc, query, query_pos, query_masks, mems: List[Tuple[str, torch.Tensor, torch.Tensor, Optional[torch.Tensor]]],
+            pairwise_locs):
+    """mems: [(name, feat (B,S,D), mask bool, pos or None)] for the active memories.  Returns (q_out (B,N,D) fp32, saved)."""
+    dev = query.device
+    B, N, D = query.shape
+    H, L = enc.num_heads, enc.num_layers
+    R = B * N
+    pk = enc.packed(dev)
+    program = [g for g in enc._program() if len(g) > 0]
+    sv: Dict = dict(B=B, N=N, D=D, H=H, L=L, R=R, program=program, pk=pk, layers=[], mems={})
+
+    ws: Dict = {}
+    for name, feat, mask, pos in mems:
+        S = feat.shape[1]
+        Sp = ops.pad64(S)
+        st = _Mem()
+        st.name, st.S, st.Sp, st.S_pitch, st.has_pos = name, S, Sp, Sp, pos is not None
+        st.xv = _e((B * Sp, D), bf16, dev)
+        st.xk = _e((B * Sp, D), bf16, dev) if pos is not None else st.xv
+        ops.ingest_memory(feat.detach().contiguous().float(), None if pos is None else pos.detach().contiguous().float(),
+                          st.xk if pos is not None else None, st.xv, Sp)
+        st.K = _e((B * Sp, L * D), bf16, dev)
+        st.Vt = _e((L * D, B * Sp), bf16, dev)
+        ops.linear(st.xk, pk.wk[name], st.K, M=B * Sp, N=L * D, K=D, bias=pk.bk[name])
+        ops.linear(pk.wv[name], st.xv, st.Vt, M=L * D, N=B * Sp, K=D, bias=pk.bv[name], bias_along_m=True)
+        enc._set_mask(st, mask, B, N, H, ws, dev)
+        sv["mems"][name] = st
+
+    q32 = query.detach().reshape(R, D).float().contiguous()
+    qpos = query_pos.detach().reshape(R, D).float().contiguous()
+    xq, xv = _e((R, D), bf16, dev), _e((R, D), bf16, dev)
+    ops.cast_bf16(q32, xq, add=qpos)
+    ops.cast_bf16(q32, xv)
+    qbits = ops.pack_mask(query_masks.contiguous())
+    sbias = pw = None
+    if pk.loc_w is not None:
+        if pairwise_locs is None:
+            raise ValueError("spatial_selfattn=True needs pairwise_locs (B, N, N, 5)")
+        pw = pairwise_locs.detach().float().contiguous()
+        sbias = _e((L, B, H, N, ops.bias_ld(N)), f32, dev)
+        ops.spatial_bias(pw, pk.loc_w, pk.loc_b, sbias)
+    sv.update(qpos=qpos, qbits=qbits, sbias=sbias, pw=pw)
+    Np = ops.pad8(N)
+
+    for i in range(L):
+        lw = pk.layers[i]
+        lay = dict(groups=[])
+        for grp in program:
+            g = len(grp)
+            w = lw["groups"][grp]
+            Q = _e((R, g * D), bf16, dev)
+            ops.linear(xq, w["wq"], Q, M=R, N=g * D, K=D, bias=w["bq"], alpha=ops.Q_SCALE, alpha_ncols=g * D)
+            O = _e((g, R, D), bf16, dev)
+            st_m, st_l = _e((g, B, H, N), f32, dev), _e((g, B, H, N), f32, dev)
+            am = [ops.AttnMemory(sv["mems"][m].K, i * D, sv["mems"][m].Vt, i * D, sv["mems"][m].S, sv["mems"][m].Sp,
+                                 sv["mems"][m].bits, *sv["mems"][m].strides, kv_tiles=sv["mems"][m].tiles) for m in grp]
+            ops.attention(Q, D, am, O, R * D, B, H, N, True, stats=(st_m, st_l))
+            y = _e((g, R, D), f32, dev)
+            ops.linear(O.view(g * R, D), w["wo"], y, M=R, N=D, K=D, bias=w["bo"], bias_group_stride=D, groups=g,
+                       a_group_rows=R, w_group_rows=D, ldc=D, c_group_stride=R * D)
+            q_new, xq_new, xv_new = _e((R, D), f32, dev), _e((R, D), bf16, dev), _e((R, D), bf16, dev)
+            ops.add_layernorm(y, q32, w["gamma"], w["beta"], w["eps"], R, D, G=g, y_group_stride=R * D, pos=qpos,
+                              out_f32=q_new, out_bf16=xv_new, out_pos_bf16=xq_new)
+            lay["groups"].append(dict(grp=grp, xq=xq, Q=Q, O=O, m=st_m, l=st_l, y=y, res=q32))
+            q32, xq, xv = q_new, xq_new, xv_new
+        sa = lw["sa"]
+        QK = _e((R, 2 * D), bf16, dev)
+        ops.linear(xq, sa["wqk"], QK, M=R, N=2 * D, K=D, bias=sa["bqk"], alpha=ops.Q_SCALE, alpha_ncols=D)
+        Vt = _z((D, B * Np), bf16, dev)
+        ops.linear(sa["wv"], xv, Vt, M=D, N=N, K=D, bias=sa["bv"], bias_along_m=True, groups=B, a_group_rows=0,
+                   w_group_rows=N, ldc=B * Np, c_group_stride=Np)
+        Os = _e((1, R, D), bf16, dev)
+        s_m, s_l = _e((1, B, H, N), f32, dev), _e((1, B, H, N), f32, dev)
+        mem = ops.AttnMemory(QK, D, Vt, 0, N, N, qbits, qbits.stride(0), 0, 0, Vt_pitch=Np)
+        ops.attention(QK, 0, [mem], Os, R * D, B, H, N, False, None if sbias is None else sbias[i], stats=(s_m, s_l))
+        ys = _e((R, D), f32, dev)
+        ops.linear(Os.view(R, D), sa["wo"], ys, M=R, N=D, K=D, bias=sa["bo"])
+        q_new, xv_new = _e((R, D), f32, dev), _e((R, D), bf16, dev)
+        ops.add_layernorm(ys, q32, sa["gamma"], sa["beta"], sa["eps"], R, D, out_f32=q_new, out_bf16=xv_new)
+        lay["sa"] = dict(xq=xq, xv=xv, QK=QK, Vt=Vt, O=Os, m=s_m, l=s_l, y=ys, res=q32)
+        q32, xv = q_new, xv_new
+        ff = lw["ffn"]
+        F = ff["F"]
+        h = _e((R, F), bf16, dev)
+        ops.linear(xv, ff["w1"], h, M=R, N=F, K=D, bias=ff["b1"], relu=True)
+        yf = _e((R, D), f32, dev)
+        ops.linear(h, ff["w2"], yf, M=R, N=D, K=F, bias=ff["b2"])
+        q_new, xq_new, xv_new = _e((R, D), f32, dev), _e((R, D), bf16, dev), _e((R, D), bf16, dev)
+        ops.add_layernorm(yf, q32, ff["gamma"], ff["beta"], ff["eps"], R, D, pos=qpos, out_f32=q_new, out_bf16=xv_new,
+                          out_pos_bf16=xq_new)
+        lay["ffn"] = dict(xv=xv, h=h, y=yf, res=q32)
+        q32, xq, xv = q_new, xq_new, xv_new
+        sv["layers"].append(lay)
+    return q32.view(B, N, D), sv
+
+
+# ------------------------------------------------------------------------------------------------
+# backward
+# ------------------------------------------------------------------------------------------------
+class _Bwd:
+    def __init__(self, enc, sv):
+        self.enc, self.sv = enc, sv
+        self.pk = sv["pk"]
+        tt = getattr(self.pk, "_train_t", None)
+        if tt is None:
+            tt = self.pk._train_t = TrainTranspose(self.pk)
+        self.tt = tt
+        self.B, self.N, self.D, self.H, self.L, self.R = (sv[k] for k in ("B", "N", "D", "H", "L", "R"))
+        self.Rp = ops.pad64(self.R)
+        self.grads: Dict[str, torch.Tensor] = {}
+        self.dev = sv["qpos"].device
+
+    # ---- small helpers --------------------------------------------------------------------------
+    def acc(self, name: str, g: torch.Tensor):
+        name = self.sv["canon"].get(name, name)           # share_layer: one parameter under several names
+        if name in self.grads:
+            self.grads[name] = self.grads[name] + g
+        else:
+            self.grads[name] = g
+
+    def tcast(self, x, rows, cols, want_c=False, gate=None):
+        """x [rows, cols] (fp32/bf16) -> (bf16 x^T [cols, pad64(rows)], bf16 copy or None)."""
+        xt = _e((cols, ops.pad64(rows)), bf16, self.dev)
+        xc = _e((rows, cols), bf16, self.dev) if want_c else None
+        ops.transpose_cast(x, xt, xc, gate=gate)
+        return xt, xc
+
+    def wgrad(self, dyT, xT, n_out, n_in):
+        """dW [n_out, n_in] = dy^T x from the K-major transposes (contraction over padded rows)."""
+        dW = _e((n_out, n_in), f32, self.dev)
+        ops.linear(dyT, xT, dW, M=n_out, N=n_in, K=dyT.shape[1])
+        return dW
+
+    def dgrad(self, dy16, w_t, n_in, out_dtype=f32):
+        """d_x [rows, n_in] = dy W, W^T given as [n_in, n_out] bf16."""
+        rows, n_out = dy16.shape
+        dx = _e((rows, n_in), out_dtype, self.dev)
+        ops.linear(dy16, w_t, dx, M=rows, N=n_in, K=n_out)
+        return dx
+
+    def colsum(self, x, gate=None):
+        out = _e((x.shape[1],), f32, self.dev)
+        ops.colsum(x, out, gate=gate)
+        return out
+
+    # ---- attention backward for one (scene batch, key set) -----------------------------------------
+    def attention_bwd(self, Qv, Kv, Vv, Ktp, dO2d, O2d, st_m, st_l, S, ld, dQv, dKv, dVv, bias=None, mask_bits=None,
+                      mask_strides=(0, 0, 0)):
+        """Qv (B,H,N,64) log2-domain queries; Kv, Vv (B,H,S,64); Ktp (B,H,64,ld) K^T with zero/finite pad;
+        dO2d, O2d [R, D]; outputs written through the strided views dQv (scaled by Q_SCALE), dKv, dVv.
+        Returns dS (bf16 [B,H,N,ld]) for the spatial-bias backward."""
+        B, H, N, dev = self.B, self.H, self.N, self.dev
+        Npad = ops.pad64(N)
+        S2 = _e((B, H, N, ld), f32, dev)
+        dP = _e((B, H, N, ld), f32, dev)
+        sub = lambda t: t.as_strided((B, H, N, S), t.stride())     # noqa: E731
+        ops.bgemm(Qv, Kv, sub(S2))
+        dOv = _heads(dO2d, B, N, N, H)
+        ops.bgemm(dOv, Vv, sub(dP))
+        delta = _e((B, H, N), f32, dev)
+        ops.attn_delta(dO2d, O2d, delta, B, H, N)
+        P, dS = _e((B, H, N, ld), bf16, dev), _e((B, H, N, ld), bf16, dev)
+        Pt, dSt = _e((B, H, ld, Npad), bf16, dev), _e((B, H, ld, Npad), bf16, dev)
+        ops.softmax_bwd(S2, dP, delta, st_m, st_l, P, dS, Pt, dSt, B, H, N, S, ld, Npad, bias=bias, mask_bits=mask_bits,
+                        mask_strides=mask_strides)
+        dOt, Qt = _e((B, H, 64, Npad), bf16, dev), _e((B, H, 64, Npad), bf16, dev)
+        ops.transpose_cast(dOv, dOt)
+        ops.transpose_cast(Qv, Qt)
+        ops.bgemm(Pt[:, :, :S], dOt, dVv)
+        ops.bgemm(dSt[:, :, :S], Qt, dKv)
+        ops.bgemm(dS, Ktp, dQv, alpha=ops.Q_SCALE)
+        return dS
+
+    # ---- blocks ---------------------------------------------------------------------------------------
+    def ffn_bwd(self, i, s, d_out):
+        R, D, dev = self.R, self.D, self.dev
+        ff = self.pk.layers[i]["ffn"]
+        F = ff["F"]
+        pre = f"unified_encoder.{i}.ffn."
+        d_y = _e((R, D), f32, dev)
+        dg, db = _z((1, D), f32, dev), _z((1, D), f32, dev)
+        ops.layernorm_bwd(s["y"], s["res"], ff["gamma"], d_out, ff["eps"], R, D, d_x=d_y, d_gamma=dg, d_beta=db)
+        self.acc(pre + "norm.weight", dg[0]); self.acc(pre + "norm.bias", db[0])
+        self.acc(pre + "linear2.bias", self.colsum(d_y))
+        d_yT, d_y16 = self.tcast(d_y, R, D, want_c=True)
+        hT, _ = self.tcast(s["h"], R, F)
+        self.acc(pre + "linear2.weight", self.wgrad(d_yT, hT, D, F))
+        d_h = self.dgrad(d_y16, self.tt.get(("ffn2", i), ff["w2"]), F)
+        self.acc(pre + "linear1.bias", self.colsum(d_h, gate=s["h"]))
+        d_preT, d_pre16 = self.tcast(d_h, R, F, want_c=True, gate=s["h"])
+        xvT, _ = self.tcast(s["xv"], R, D)
+        self.acc(pre + "linear1.weight", self.wgrad(d_preT, xvT, F, D))
+        d_xv = self.dgrad(d_pre16, self.tt.get(("ffn1", i), ff["w1"]), D)
+        d_in = _e((R, D), f32, dev)
+        ops.add3(d_y, d_xv, None, d_in)
+        return d_in
+
+    def sa_bwd(self, i, s, d_out, d_pos):
+        R, D, B, N, H, dev = self.R, self.D, self.B, self.N, self.H, self.dev
+        sa = self.pk.layers[i]["sa"]
+        spatial = sa["loc_w"] is not None
+        pre = f"unified_encoder.{i}.self_attn."
+        d_y = _e((R, D), f32, dev)
+        dg, db = _z((1, D), f32, dev), _z((1, D), f32, dev)
+        ops.layernorm_bwd(s["y"], s["res"], sa["gamma"], d_out, sa["eps"], R, D, d_x=d_y, d_gamma=dg, d_beta=db)
+        self.acc(pre + "norm.weight", dg[0]); self.acc(pre + "norm.bias", db[0])
+        d_bo = self.colsum(d_y)
+        d_yT, d_y16 = self.tcast(d_y, R, D, want_c=True)
+        O2d = s["O"].view(R, D)
+        OT, _ = self.tcast(O2d, R, D)
+        d_wo = self.wgrad(d_yT, OT, D, D)
+        dO = self.dgrad(d_y16, self.tt.get(("sa_o", i), sa["wo"]), D, out_dtype=bf16)
+        # operands of the attention backward
+        QK = s["QK"]
+        Np8, ld = ops.pad8(N), ops.pad64(N)
+        Qv, Kv = _heads(QK, B, N, N, H, 0), _heads(QK, B, N, N, H, D)
+        V = _e((R, D), bf16, dev)                                       # V back in row-major from V^T [D, B*Np8]
+        Vt = s["Vt"]
+        ops.transpose_cast(Vt.as_strided((B, 1, D, N), (Np8, 0, Vt.stride(0), 1)), V.view(B, 1, N, D))
+        Vv = _heads(V, B, N, N, H)
+        Ktp = _e((B, H, 64, ld), bf16, dev)
+        ops.transpose_cast(Kv, Ktp)
+        dQK = _e((R, 2 * D), bf16, dev)
+        dV = _e((R, D), bf16, dev)
+        qbits = self.sv["qbits"]
+        bias = None if self.sv["sbias"] is None else self.sv["sbias"][i]
+        dS = self.attention_bwd(Qv, Kv, Vv, Ktp, dO, O2d, s["m"][0], s["l"][0], N, ld, _heads(dQK, B, N, N, H, 0),
+                                _heads(dQK, B, N, N, H, D), _heads(dV, B, N, N, H), bias=bias, mask_bits=qbits,
+                                mask_strides=(qbits.stride(0), 0, 0))
+        d_bqk = self.colsum(dQK)
+        dQKT, _ = self.tcast(dQK, R, 2 * D)
+        xqT, _ = self.tcast(s["xq"], R, D)
+        d_wqk = self.wgrad(dQKT, xqT, 2 * D, D)
+        d_xq = self.dgrad(dQK, self.tt.get(("sa_qk", i), sa["wqk"]), D)
+        d_bv = self.colsum(dV)
+        dVT, _ = self.tcast(dV, R, D)
+        xvT, _ = self.tcast(s["xv"], R, D)
+        d_wv = self.wgrad(dVT, xvT, D, D)
+        d_xv = self.dgrad(dV, self.tt.get(("sa_v", i), sa["wv"]), D)
+        if spatial:
+            a = pre + "self_attn."
+            self.acc(a + "w_qs.weight", d_wqk[:D]); self.acc(a + "w_ks.weight", d_wqk[D:])
+            self.acc(a + "w_qs.bias", d_bqk[:D]); self.acc(a + "w_ks.bias", d_bqk[D:])
+            self.acc(a + "w_vs.weight", d_wv); self.acc(a + "w_vs.bias", d_bv)
+            self.acc(a + "fc.weight", d_wo); self.acc(a + "fc.bias", d_bo)
+            d_lw, d_lb = _z((H, 5), f32, dev), _z((H,), f32, dev)
+            ops.spatial_bias_bwd(self.sv["pw"], sa["loc_w"], sa["loc_b"], dS, ld, d_lw, d_lb, B, H, N)
+            self.acc(a + "pairwise_loc_fc.weight", d_lw); self.acc(a + "pairwise_loc_fc.bias", d_lb)
+        else:
+            a = pre + "self_attn."
+            self.acc(a + "in_proj_weight", torch.cat([d_wqk, d_wv], 0))
+            self.acc(a + "in_proj_bias", torch.cat([d_bqk, d_bv], 0))
+            self.acc(a + "out_proj.weight", d_wo); self.acc(a + "out_proj.bias", d_bo)
+        d_in = _e((R, D), f32, dev)
+        ops.add3(d_y, d_xq, d_xv, d_in)
+        ops.add3(d_pos, d_xq, None, d_pos)
+        return d_in
+
+    def group_bwd(self, i, s, d_out, d_pos, mem_grads):
+        R, D, B, N, H, dev = self.R, self.D, self.B, self.N, self.H, self.dev
+        grp = s["grp"]
+        g = len(grp)
+        w = self.pk.layers[i]["groups"][grp]
+        idx = [self.enc.memories.index(m) for m in grp]
+        d_y = _e((g, R, D), f32, dev)
+        d_res = _e((R, D), f32, dev)
+        dg, db = _z((g, D), f32, dev), _z((g, D), f32, dev)
+        ops.layernorm_bwd(s["y"], s["res"], w["gamma"], d_out, w["eps"], R, D, G=g, y_group_stride=R * D, d_x=d_y,
+                          dx_group_stride=R * D, d_res=d_res, d_gamma=dg, d_beta=db)
+        dQ = _e((R, g * D), bf16, dev)
+        for jj, (m, j) in enumerate(zip(grp, idx)):
+            pre = f"unified_encoder.{i}.cross_attn_list.{j}."
+            st = self.sv["mems"][m]
+            self.acc(pre + "norm.weight", dg[jj]); self.acc(pre + "norm.bias", db[jj])
+            self.acc(pre + "multihead_attn.out_proj.bias", self.colsum(d_y[jj]))
+            d_yT, d_y16 = self.tcast(d_y[jj], R, D, want_c=True)
+            O2d = s["O"][jj]
+            OT, _ = self.tcast(O2d, R, D)
+            self.acc(pre + "multihead_attn.out_proj.weight", self.wgrad(d_yT, OT, D, D))
+            dO = self.dgrad(d_y16, self.tt.get(("ca_o", i, grp, jj), w["wo"][jj * D:(jj + 1) * D]), D, out_dtype=bf16)
+            mg = mem_grads[m]
+            S, Sp = st.S, st.Sp
+            Qv = _heads(s["Q"], B, N, N, H, jj * D)
+            Kv = _heads(st.K, B, S, Sp, H, i * D)
+            Vv = _heads(mg["V"], B, S, Sp, H, i * D)
+            Kt = mg["Kt"]                                               # [L*D, B*Sp]
+            Ktp = Kt.as_strided((B, H, 64, Sp), (Sp, 64 * Kt.stride(0), Kt.stride(0), 1), i * D * Kt.stride(0))
+            self.attention_bwd(Qv, Kv, Vv, Ktp, dO, O2d, s["m"][jj], s["l"][jj], S, Sp, _heads(dQ, B, N, N, H, jj * D),
+                               _heads(mg["dK"], B, S, Sp, H, i * D), _heads(mg["dV"], B, S, Sp, H, i * D),
+                               mask_bits=st.bits, mask_strides=st.strides)
+        d_bq = self.colsum(dQ)
+        dQT, _ = self.tcast(dQ, R, g * D)
+        xqT, _ = self.tcast(s["xq"], R, D)
+        d_wq = self.wgrad(dQT, xqT, g * D, D)
+        d_xq = self.dgrad(dQ, self.tt.get(("ca_q", i, grp), w["wq"]), D)
+        mg_q = mem_grads["_q"]
+        for jj, j in enumerate(idx):
+            mg_q[(i, j)] = (d_wq[jj * D:(jj + 1) * D], d_bq[jj * D:(jj + 1) * D])
+        d_in = _e((R, D), f32, dev)
+        ops.add3(d_res, d_xq, None, d_in)
+        ops.add3(d_pos, d_xq, None, d_pos)
+        return d_in
+
+    # ---- whole decoder ------------------------------------------------------------------------------------
+    def run(self, d_out: torch.Tensor):
+        sv, B, N, D, L, R, dev = self.sv, self.B, self.N, self.D, self.L, self.R, self.dev
+        mem_grads: Dict = {"_q": {}}
+        for name, st in sv["mems"].items():
+            V = _e((B * st.Sp, L * D), bf16, dev)
+            ops.transpose_cast(st.Vt, V)                               # V^T [L*D, B*Sp] -> V [B*Sp, L*D]
+            Kt = _e((L * D, B * st.Sp), bf16, dev)
+            ops.transpose_cast(st.K, Kt)
+            mem_grads[name] = dict(V=V, Kt=Kt, dK=_z((B * st.Sp, L * D), bf16, dev), dV=_z((B * st.Sp, L * D), bf16, dev))
+        d_q = d_out.detach().reshape(R, D).float().contiguous()
+        d_pos = _z((R, D), f32, dev)
+        for i in reversed(range(L)):
+            lay = sv["layers"][i]
+            d_q = self.ffn_bwd(i, lay["ffn"], d_q)
+            d_q = self.sa_bwd(i, lay["sa"], d_q, d_pos)
+            for s in reversed(lay["groups"]):
+                d_q = self.group_bwd(i, s, d_q, d_pos, mem_grads)
+        # memory side: weight / bias gradients of the hoisted K and V projections, input gradients
+        d_mem = {}
+        for name, st in sv["mems"].items():
+            mg = mem_grads[name]
+            j = self.enc.memories.index(name)
+            rows = B * st.Sp
+            d_bk, d_bv = self.colsum(mg["dK"]), self.colsum(mg["dV"])
+            dKT, _ = self.tcast(mg["dK"], rows, L * D)
+            xkT, _ = self.tcast(st.xk, rows, D)
+            d_wk = self.wgrad(dKT, xkT, L * D, D)
+            dVT, _ = self.tcast(mg["dV"], rows, L * D)
+            xvT = xkT if not st.has_pos else self.tcast(st.xv, rows, D)[0]
+            d_wv = self.wgrad(dVT, xvT, L * D, D)
+            d_xk = self.dgrad(mg["dK"], self.tt.get(("mem_k", name), self.pk.wk[name]), D)
+            d_xv = self.dgrad(mg["dV"], self.tt.get(("mem_v", name), self.pk.wv[name]), D)
+            for i in range(L):
+                pre = f"unified_encoder.{i}.cross_attn_list.{j}.multihead_attn."
+                d_wq, d_bq = mem_grads["_q"][(i, j)]
+                sl = slice(i * D, (i + 1) * D)
+                self.acc(pre + "in_proj_weight", torch.cat([d_wq, d_wk[sl], d_wv[sl]], 0))
+                self.acc(pre + "in_proj_bias", torch.cat([d_bq, d_bk[sl], d_bv[sl]], 0))
+            d_feat = _e((rows, D), f32, dev)
+            ops.add3(d_xk, d_xv, None, d_feat)
+            d_mem[name] = (d_feat.view(B, st.Sp, D)[:, :st.S], d_xk.view(B, st.Sp, D)[:, :st.S] if st.has_pos else None)
+        return d_q.view(B, N, D), d_pos.view(B, N, D), d_mem, self.grads
+
+
+class DecoderFunction(torch.autograd.Function):
+    """forward(enc, meta, query, query_pos, feat_0, pos_0, ..., *params) -> decoded queries (B, N, D)."""
+
+    @staticmethod
+    def forward(ctx, enc, meta, query, query_pos, *rest):
+        n = len(meta["names"])
+        feats, poss = rest[0:2 * n:2], rest[1:2 * n:2]
+        mems = [(meta["names"][k], feats[k], meta["masks"][k], poss[k]) for k in range(n)]
+        out, sv = forward(enc, query, query_pos, meta["query_masks"], mems, meta["pairwise_locs"])
+        sv["canon"] = meta["canon"]
+        ctx.enc, ctx.sv, ctx.meta = enc, sv, meta
+        ctx.in_dtypes = (query.dtype, query_pos.dtype, [None if t is None else t.dtype for t in rest[:2 * n]])
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        enc, sv, meta = ctx.enc, ctx.sv, ctx.meta
+        d_q, d_pos, d_mem, grads = _Bwd(enc, sv).run(d_out)
+        ctx.sv = None
+        out = [None, None, d_q.to(ctx.in_dtypes[0]), d_pos.to(ctx.in_dtypes[1])]
+        for k, name in enumerate(meta["names"]):
+            d_feat, d_p = d_mem[name]
+            out.append(d_feat.to(ctx.in_dtypes[2][2 * k]) if ctx.needs_input_grad[4 + 2 * k] else None)
+            out.append(d_p.to(ctx.in_dtypes[2][2 * k + 1])
+                       if d_p is not None and ctx.needs_input_grad[5 + 2 * k] else None)
+        for pname, p in meta["param_names"]:
+            g = grads.get(pname)
+            out.append(None if g is None else g.reshape(p.shape).to(p.dtype))
+        return tuple(out)
+
+
+def run(enc, input_dict: dict, pairwise_locs):
+    """Entry used by QueryMaskEncoder.forward when gradients are enabled."""
+    if enc.structure == "gate":
+        raise NotImplementedError("pq3d_b200 training path: structure='gate' is inference-only in this build")
+    if enc.num_blocks != 1:
+        raise NotImplementedError("pq3d_b200 training path: num_blocks must be 1")
+    if enc.training and (getattr(enc, "train_dropout", 0.1) > 0 or enc.memory_dropout > 0):
+        raise NotImplementedError(
+            "pq3d_b200 training path: dropout / memory dropout kernels are not built — set "
+            "`encoder.train_dropout = 0.0` and memory_dropout=0 (or call .eval()) to train without dropout")
+    query, query_masks, query_pos = input_dict["query"]
+    names = [m for g in enc._program() for m in g]
+    masks, flat = [], []
+    for m in names:
+        feat, mask, pos = input_dict[m]
+        if isinstance(feat, list):
+            raise NotImplementedError("pq3d_b200 training path: multi-scale (list) memory features are inference-only")
+        masks.append(mask)
+        flat += [feat, pos]
+    params = list(enc.named_parameters())
+    first = {id(p): n for n, p in reversed(params)}
+    canon = {n: first[id(p)] for n, p in enc.named_parameters(remove_duplicate=False)}
+    meta = dict(canon=canon, names=names, masks=masks, query_masks=query_masks, pairwise_locs=pairwise_locs, param_names=params)
+    return DecoderFunction.apply(enc, meta, query, query_pos, *flat, *[p for _, p in params])

@@ -266,7 +266,9 @@ def test_rejects_non_bool_masks_and_training_mode():
     with torch.no_grad(), pytest.raises(TypeError):
         enc(bad, pw)
     with pytest.raises(NotImplementedError):
-        enc(synth.clone_input_dict(inp), pw)              # grad enabled: no silent autograd fallback
+        enc(synth.clone_input_dict(inp), pw, lambda q: (None, None, None))   # grad enabled + mask head: no backward
     enc.train()
     with torch.no_grad(), pytest.raises(NotImplementedError):
-        enc(synth.clone_input_dict(inp), pw)
+        enc(synth.clone_input_dict(inp), pw)              # train-mode forward without grads: dropout not built
+    with pytest.raises(NotImplementedError):
+        enc(synth.clone_input_dict(inp), pw)              # train mode with the reference's dropout 0.1: refuses

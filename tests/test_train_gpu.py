@@ -1,0 +1,149 @@
+"""Gradient parity of the training path (pq3d_b200/train_engine.py: forward + backward composed from the sm_100a
+kernels) against torch autograd through the oracle restatement of the reference decoder, same weights, same inputs,
+same upstream gradient.  The reference trains by plain autograd through modules/grounding/query_encoder.py
+(trainer/query3d_trainer.py:18-28), under bf16 autocast on GPU.
+
+Tolerance, written here: per tensor, with e(x) = ||x - g32||inf / ||g32||inf against the fp32-autograd gradient g32,
+    e(ours) <= 1.5 * e(oracle under autocast-bf16) + 2e-2   and   e(ours) <= max(6e-2, 1.25 * e(autocast oracle))
+(gradients pass through twice as many bf16-rounded products as the forward; the oracle's own bf16 path is the
+yardstick).  Tensors whose true gradient is zero — the key biases: softmax is shift invariant — are measured against
+1e-3 of the largest parameter gradient instead of their own (rounding-noise) norm.
+"""
+import pytest
+import torch
+
+import _cases as C
+from oracle import restatement as O
+from pq3d_b200 import synth
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def rel(a, b, floor=1e-20):
+    a, b = a.float(), b.float()
+    return ((a - b).abs().max() / b.abs().max().clamp_min(floor)).item()
+
+
+def _inputs(w, seed):
+    inp, pw, _ = synth.make_decoder_inputs(w, device=DEV)
+    g = torch.Generator().manual_seed(seed)
+    q, qm, qp = inp["query"]
+    inp["query"] = (torch.randn(q.shape, generator=g).to(DEV) * 0.5, qm, qp)
+    up = torch.randn(q.shape, generator=g).to(DEV)
+    return inp, pw, up
+
+
+def _leafify(inp):
+    """Fresh leaf tensors (requires_grad) for query, query_pos, every memory feature and positional table."""
+    out, leaves = {}, {}
+    q, qm, qp = inp["query"]
+    leaves["query"], leaves["query_pos"] = q.clone().requires_grad_(True), qp.clone().requires_grad_(True)
+    out["query"] = (leaves["query"], qm, leaves["query_pos"])
+    pos_leaf = {}
+    for m, (feat, mask, pos) in ((k, v) for k, v in inp.items() if k != "query"):
+        leaves[f"{m}.feat"] = feat.clone().requires_grad_(True)
+        p = None
+        if pos is not None:
+            if id(pos) not in pos_leaf:
+                pos_leaf[id(pos)] = pos.clone().requires_grad_(True)
+                leaves[f"pos[{m}..]"] = pos_leaf[id(pos)]
+            p = pos_leaf[id(pos)]
+        out[m] = [leaves[f"{m}.feat"], mask, p]
+    return out, leaves
+
+
+def _oracle_grads(sd, cfg, inp, pw, up, autocast):
+    sdd = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    x, leaves = _leafify(inp)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+        out = O.query_mask_encoder(sdd, cfg, x, pw)[0]
+    (out.float() * up).sum().backward()
+    g = {k: v.grad for k, v in sdd.items()}
+    g.update({k: v.grad for k, v in leaves.items()})
+    return out.detach(), g
+
+
+def _run_case(w, seed=3):
+    from pq3d_b200.query_encoder import QueryMaskEncoder
+    sd = C.to_dev(synth.decoder_state_dict(w, seed=seed, sharp=1.0), DEV)
+    enc = QueryMaskEncoder(None, **w.decoder_kwargs())
+    enc.load_state_dict(sd, strict=True)
+    enc = enc.to(DEV).train()
+    enc.train_dropout = 0.0
+    inp, pw, up = _inputs(w, seed + 1)
+    cfg = O.DecoderCfg(**w.decoder_kwargs())
+    out32, g32 = _oracle_grads(sd, cfg, inp, pw, up, autocast=False)
+    out16, g16 = _oracle_grads(sd, cfg, inp, pw, up, autocast=True)
+    x, leaves = _leafify(inp)
+    out, pc, pm = enc(x, pw)
+    assert pc == [] and pm == [] and out.requires_grad
+    (out * up).sum().backward()
+    torch.cuda.synchronize()
+    ours = {k: p.grad for k, p in enc.named_parameters()}
+    ours.update({k: v.grad for k, v in leaves.items()})
+    print(f"forward: err(ours) {rel(out, out32):.3e}  err(autocast oracle) {rel(out16, out32):.3e}")
+    worst = []
+    floor = 1e-3 * max(float(v.abs().max()) for k, v in g32.items() if v is not None and k in sd)
+    for k, ref in g32.items():
+        if ref is None:
+            assert ours.get(k) is None or float(ours[k].abs().max()) == 0.0, f"{k}: oracle has no gradient"
+            continue
+        assert ours.get(k) is not None, f"{k}: no gradient produced"
+        assert ours[k].shape == ref.shape, f"{k}: {tuple(ours[k].shape)} != {tuple(ref.shape)}"
+        if k.endswith("w_ks.bias"):        # true gradient is exactly zero (softmax shift invariance): noise bound only
+            assert float(ours[k].abs().max()) <= floor, f"{k}: {float(ours[k].abs().max()):.3e} > {floor:.3e}"
+            continue
+        e, e16 = rel(ours[k], ref, floor), rel(g16[k], ref, floor)
+        worst.append((e, e16, k))
+    worst.sort(reverse=True)
+    for e, e16, k in worst[:8]:
+        print(f"  {k}: ours {e:.3e}  autocast oracle {e16:.3e}")
+    for e, e16, k in worst:
+        assert e <= 1.5 * e16 + 2e-2 and e <= max(6e-2, 1.25 * e16), f"{k}: gradient error {e:.3e} (autocast oracle {e16:.3e})"
+    return enc
+
+
+def test_grads_mixed_spatial_prompt():
+    """BASELINE config 5's structure at reduced size: mixed = [mv, pc, voxel] in parallel then the prompt, spatial
+    self-attention, ragged key padding, N not a multiple of 8."""
+    w = synth.Workload("t5", 2, 100, 300, ["mv", "pc", "voxel", "prompt"], "mixed", T=20, num_layers=2,
+                       ragged=(150, 300))
+    _run_case(w)
+
+
+def test_grads_sequential_plain_selfattn():
+    w = synth.Workload("tseq", 2, 48, 200, ["pc", "voxel"], "sequential", num_layers=2, spatial_selfattn=False)
+    _run_case(w)
+
+
+def test_grads_parallel_single_layer_long_memory():
+    """More than two key tiles per memory (one-pass / two-pass attention schedules) and a 64-multiple query count."""
+    w = synth.Workload("tpar", 1, 64, 700, ["mv", "voxel"], "parallel", num_layers=1)
+    _run_case(w)
+
+
+def test_training_step_updates_weights_and_is_repeatable():
+    """fwd + bwd + AdamW for three steps: loss finite, parameters move, packed weights follow the updates."""
+    w = synth.Workload("tstep", 2, 100, 256, ["mv", "pc", "voxel", "prompt"], "mixed", T=16, num_layers=2)
+    from pq3d_b200.query_encoder import QueryMaskEncoder
+    enc = QueryMaskEncoder(None, **w.decoder_kwargs()).to(DEV).train()
+    enc.train_dropout = 0.0
+    opt = torch.optim.AdamW(enc.parameters(), lr=1e-3, betas=(0.9, 0.98))
+    inp, pw, up = _inputs(w, 11)
+    target = torch.randn_like(up)
+    losses = []
+    before = {k: p.detach().clone() for k, p in enc.named_parameters()}
+    for _ in range(3):
+        opt.zero_grad(set_to_none=True)
+        out = enc(synth.clone_input_dict(inp), pw)[0]
+        loss = ((out - target) ** 2).mean()
+        loss.backward()
+        opt.step()
+        losses.append(loss.item())
+    print("losses", losses)
+    assert all(torch.isfinite(torch.tensor(losses)))
+    assert losses[-1] < losses[0]
+    moved = [k for k, p in enc.named_parameters() if not torch.equal(p.detach(), before[k])]
+    assert len(moved) == len(before), "every decoder parameter must receive a gradient"
