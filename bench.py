@@ -30,6 +30,7 @@ sys.path.insert(0, ROOT)
 
 METRIC = "decoder queries/sec (N=100, 2048 seg-tokens, bf16)"
 UNIT = "queries/s"
+TRAIN_METRIC = "decoder training queries/sec (fwd+bwd+AdamW step, N=100, 2048 seg-tokens, bf16)"
 
 
 def parse():
@@ -43,6 +44,8 @@ def parse():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--train", action="store_true",
+                    help="training step (fwd + bwd + AdamW, gradient all-reduce for N>1); implied by --workload c5")
     return ap.parse_args()
 
 
@@ -57,9 +60,10 @@ def workload_config(w, n_gpus):
 # ------------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the oracle port on host cores
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_run(w, steps, warmup, budget_s):
-    """Times the reference algorithm (oracle restatement == reference modules to 1e-5, fp32, eval)
-    on the host cores with all threads, on a BOUNDED sample: one scene of the workload per step."""
+def cpu_reference_run(w, steps, warmup, budget_s, train=False):
+    """Times the reference algorithm (oracle restatement == reference modules to 1e-5, fp32)
+    on the host cores with all threads, on a BOUNDED sample: one scene of the workload per step.
+    train=True: forward + autograd backward + AdamW, what trainer/query3d_trainer.py:18-28 does per step."""
     import torch
     from oracle import restatement as O
     from pq3d_b200 import synth
@@ -74,10 +78,20 @@ def cpu_reference_run(w, steps, warmup, budget_s):
     inp, pw, _ = synth.make_decoder_inputs(ws)
     times = []
     t_begin = time.perf_counter()
-    with torch.no_grad():
+    if train:
+        sd = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+        opt = torch.optim.AdamW(list(sd.values()), lr=1e-4, betas=(0.9, 0.98))
+        target = torch.randn(ws.B, ws.N, ws.hidden_size)
+    with torch.set_grad_enabled(train):
         for i in range(warmup + steps):
             t0 = time.perf_counter()
-            O.query_mask_encoder(sd, cfg, synth.clone_input_dict(inp), pw)
+            if train:
+                opt.zero_grad(set_to_none=True)
+                out = O.query_mask_encoder(sd, cfg, synth.clone_input_dict(inp), pw)[0]
+                ((out - target) ** 2).mean().backward()
+                opt.step()
+            else:
+                O.query_mask_encoder(sd, cfg, synth.clone_input_dict(inp), pw)
             dt = time.perf_counter() - t0
             if i >= warmup:
                 times.append(dt)
@@ -88,15 +102,17 @@ def cpu_reference_run(w, steps, warmup, budget_s):
     med = statistics.median(times)
     return {"value": ws.B * ws.N / med, "unit": UNIT, "cores": cores, "kind": "port",
             "sample": f"1 of {w.B} scenes per step (N={ws.N}, S={ws.S}, same memories/layers), fp32, "
-                      f"{len(times)} timed forwards, median {med * 1e3:.1f} ms",
+                      f"{len(times)} timed {'training steps (fwd+bwd+AdamW)' if train else 'forwards'}, "
+                      f"median {med * 1e3:.1f} ms",
             "ms_per_step": med * 1e3, "steps": len(times)}
 
 
 def run_reference_arm(args, w, rank, world):
     if rank != 0:
         return
-    r = cpu_reference_run(w, args.steps, min(args.warmup, 3), budget_s=120.0)
-    line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
+    train = args.train or w.name == "c5"
+    r = cpu_reference_run(w, args.steps, min(args.warmup, 3), budget_s=120.0, train=train)
+    line = {"impl": "reference", "metric": TRAIN_METRIC if train else METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": r["steps"], "warmup": min(args.warmup, 3), "ms_per_step": r["ms_per_step"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(w, args.gpus),
@@ -153,6 +169,173 @@ class ClockSampler(threading.Thread):
 
 
 # ------------------------------------------------------------------------------------------------
+# training step (BASELINE config 5): fwd + bwd + AdamW, one flat gradient all-reduce per step for N > 1
+# ------------------------------------------------------------------------------------------------
+def run_train(args, w, enc, inp_host, pw_host, rank, world, local_rank, dev, barrier):
+    import torch
+    import torch.distributed as dist
+    from pq3d_b200 import ops, synth
+    from pq3d_b200.dist import FlatGradAllReduce
+
+    enc.train()
+    enc.train_dropout = 0.0          # dropout-free training path (no RNG kernels in this build); stated in config
+    params = list(enc.parameters())
+    graphed = not args.no_graph
+    opt = torch.optim.AdamW(params, lr=1e-4, betas=(0.9, 0.98), fused=True, capturable=graphed)
+    reducer = FlatGradAllReduce(params) if world > 1 else None
+    g = torch.Generator().manual_seed(99 + rank)
+    target_host = torch.randn(w.B, w.N, w.hidden_size, generator=g).pin_memory()
+
+    def pin_all(d):
+        memo = {}
+
+        def f(t):
+            if isinstance(t, torch.Tensor):
+                if id(t) not in memo:
+                    memo[id(t)] = t.pin_memory()
+                return memo[id(t)]
+            if isinstance(t, (list, tuple)):
+                return type(t)(f(x) for x in t)
+            return t
+        return {k: f(v) for k, v in d.items()}, memo
+
+    def to_device(d):
+        memo = {}
+
+        def f(t):
+            if isinstance(t, torch.Tensor):
+                if id(t) not in memo:
+                    memo[id(t)] = t.to(dev, non_blocking=True)
+                return memo[id(t)]
+            if isinstance(t, (list, tuple)):
+                return type(t)(f(x) for x in t)
+            return t
+        return {k: f(v) for k, v in d.items()}
+
+    inp_pin, pinned = pin_all(inp_host)
+    pw_pin = pw_host.pin_memory()
+    inp_dev, pw_dev, target_dev = to_device(inp_pin), pw_pin.to(dev), target_host.to(dev)
+
+    def loss_fn(out, target):
+        return ((out - target) ** 2).mean()
+
+    if graphed:
+        # forward + loss + backward + all-reduce + AdamW replayed as one CUDA graph (pq3d_b200/training.py); a new
+        # batch is copied into the captured input buffers (device->device here, host->device in the e2e loop)
+        from pq3d_b200.training import GraphedTrainStep
+        gstep = GraphedTrainStep(enc, opt, loss_fn, reducer)
+
+        def train_step(inp, pw, target):
+            return gstep(inp, pw, target)
+    else:
+        def train_step(inp, pw, target):
+            opt.zero_grad(set_to_none=True)
+            out = enc(synth.clone_input_dict(inp), pw)[0]
+            loss = loss_fn(out, target)
+            loss.backward()
+            if reducer is not None:
+                reducer()
+            opt.step()
+            return loss
+
+    for _ in range(max(args.warmup, 3) + (4 if graphed else 0)):     # graph mode: 3 eager calls + capture come first
+        train_step(inp_dev, pw_dev, target_dev)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    l0 = ops.LAUNCHES
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        loss = train_step(inp_dev, pw_dev, target_dev)
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    launches = ops.LAUNCHES - l0
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_per_step = ms.item() / args.steps
+    value = world * w.B * w.N / (ms_per_step * 1e-3)
+
+    # e2e: every step copies its batch from pinned host memory and reads the loss back
+    h2d = (sum(t.numel() * t.element_size() for t in pinned.values()) + pw_pin.numel() * pw_pin.element_size()
+           + target_host.numel() * 4)
+    e2e_steps = max(10, args.steps // 4)
+
+    def step_e2e():
+        if graphed:       # pinned host tensors are copied straight into the graph's input buffers
+            return train_step(inp_pin, pw_pin, target_host).item()
+        return train_step(to_device(inp_pin), pw_pin.to(dev, non_blocking=True),
+                          target_host.to(dev, non_blocking=True)).item()
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        last_loss = step_e2e()
+    torch.cuda.synchronize()
+    t_e2e = torch.tensor([time.perf_counter() - t0], device=dev)
+    if world > 1:
+        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+    e2e_value = world * w.B * w.N * e2e_steps / t_e2e.item()
+    if rank != 0:
+        return
+
+    # roofline of the dominant backward kernel: weight gradient of the hoisted K (or V) projection of one memory,
+    # dW [L*D, D] = dK^T [L*D, B*Sp] . xk^T [D, B*Sp]^T  — pq3d_linear_bf16, contraction over all tokens
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:  # noqa: BLE001
+        pass
+    Sp = ops.pad64(w.S)
+    M, Nn, Kk = w.num_layers * w.hidden_size, w.hidden_size, w.B * Sp
+    A = torch.randn(M, Kk, device=dev).bfloat16()
+    Wt = torch.randn(Nn, Kk, device=dev).bfloat16()
+    Cw = torch.empty(M, Nn, dtype=torch.float32, device=dev)
+    for _ in range(5):
+        ops.linear(A, Wt, Cw, M=M, N=Nn, K=Kk)
+    torch.cuda.synchronize()
+    reps = 50
+    r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    r0.record()
+    for _ in range(reps):
+        ops.linear(A, Wt, Cw, M=M, N=Nn, K=Kk)
+    r1.record()
+    torch.cuda.synchronize()
+    k_ms = r0.elapsed_time(r1) / reps
+    flops = 2.0 * M * Nn * w.B * w.S
+    achieved = flops / (k_ms * 1e-3) / 1e12
+    peak = peaks.get("bf16_tflops", 1590.0)
+    roofline = {"bound": "tensor",
+                "kernel": f"linear_bf16_kernel (wgrad of a hoisted K/V projection: [M={M}, N={Nn}, K={Kk}], 6 such per step)",
+                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst; kernel timed alone)" if peaks else "fallback 1590",
+                "us_per_launch": k_ms * 1e3, "flops_per_launch": flops}
+    cpu = None
+    if not args.no_cpu_baseline:
+        cpu = cpu_reference_run(w, steps=1000, warmup=1, budget_s=args.cpu_seconds, train=True)
+        cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    line = {"metric": TRAIN_METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": dict(workload_config(w, world), mode="training step: forward + backward + AdamW (torch fused AdamW)"
+                           + (", whole step replayed as one CUDA graph" if graphed else ", eager launches")
+                           + (", one flat NCCL all-reduce (mean) over all gradients" if world > 1 else ""),
+                           dropout="0.0 (the training path has no RNG kernels; the reference trains with 0.1)",
+                           l2="per-step working set > 1 GB (saved K/V^T, dK/dV, score tiles) exceeds the 126 MB L2; no flush",
+                           parallelism=f"batch-axis shard x{world}, weights replicated, gradient all-reduce"),
+            "clocks": clocks, "final_loss": last_loss,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                    "steps": e2e_steps,
+                    "timing": "wall clock, max over ranks; each step copies its batch from pinned host memory, runs "
+                              "fwd+bwd+all-reduce+AdamW and reads the loss back"},
+            "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", 0))
@@ -187,6 +370,11 @@ def main():
     enc.use_cuda_graph = not args.no_graph
     inp_host, pw_host, _dd = synth.make_decoder_inputs(w, rank=rank)        # this rank's scenes
     to_dev = lambda x: x.to(dev, non_blocking=True)  # noqa: E731
+    if args.train or w.name == "c5":
+        run_train(args, w, enc, inp_host, pw_host, rank, world, local_rank, dev, barrier)
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     def dict_to(d, f):
         """Apply f to every tensor once (tensors shared between memories, e.g. fts_pos, stay shared)."""

@@ -177,7 +177,8 @@ int pq3d_layernorm_bwd(const float* y, int64_t y_group_stride, const float* resi
 int pq3d_attn_delta(const void* dO, const void* O, int64_t ld, float* delta, int B, int H, int N, void* stream);
 
 /* Softmax backward on recomputed scores: P = ex2(S2 + bias - m)/l (0 where masked), dS2 = ln2 * P * (dP - delta);
- * S2, dP fp32 [B,H,N,ld]; outputs bf16 P, dS [B,H,N,ld] and transposed Pt, dSt [B,H,ld,Np] (columns n >= N zero). */
+ * S2, dP fp32 [B,H,N,ld]; outputs bf16 P (optional, may be NULL), dS [B,H,N,ld] and transposed Pt, dSt [B,H,ld,Np]
+ * (columns n >= N zero).  ld multiple of 32, Np of 8. */
 int pq3d_softmax_bwd(const float* S2, const float* dP, const float* delta, const float* m, const float* l,
                      const float* bias, int64_t bias_ld, const uint32_t* mask_bits, int64_t mask_b_stride,
                      int64_t mask_h_stride, int64_t mask_q_stride, void* P, void* dS, void* Pt, void* dSt,

@@ -59,29 +59,117 @@ __global__ void transpose_cast_kernel(const TransposeParams p) {
   }
 }
 
+// Vectorised variant (16-byte global accesses, 64x64 tiles) for the common case: C, Rp, every pitch and batch stride
+// multiples of 8 elements and 16-byte aligned bases.  Same semantics as transpose_cast_kernel.
+constexpr int kTcPitch = 66;   // bf16 elements per shared-memory tile row (33 words: conflict-light both ways)
+
+__global__ void __launch_bounds__(256) transpose_cast_vec_kernel(const TransposeParams p) {
+  pdl_sync();
+  __shared__ __align__(16) __nv_bfloat16 tile[64 * kTcPitch];      // tile[c][r]
+  const int b1 = blockIdx.z / p.B2, b2 = blockIdx.z % p.B2;
+  const int r0 = blockIdx.y * 64, c0 = blockIdx.x * 64;
+  const int t = threadIdx.x;
+  const int chunk = t & 7;
+#pragma unroll
+  for (int it = 0; it < 2; ++it) {
+    const int rl = (t >> 3) + it * 32;
+    const int r = r0 + rl, c = c0 + chunk * 8;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = 0.f;
+    if (r < p.R && c < p.C) {
+      const int64_t off = b1 * p.in_b1 + b2 * p.in_b2 + static_cast<int64_t>(r) * p.ld_in + c;
+      if (p.in_fp32) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.in) + off));
+        const float4 b = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.in) + off) + 1);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+      } else {
+        const uint4 a = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.in) + off));
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&a);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { v[2 * j] = __bfloat162float(h[j].x); v[2 * j + 1] = __bfloat162float(h[j].y); }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] *= p.scale;
+      if (p.gate != nullptr) {
+        const uint4 g = __ldg(reinterpret_cast<const uint4*>(p.gate + b1 * p.gate_b1 + b2 * p.gate_b2 +
+                                                             static_cast<int64_t>(r) * p.ld_gate + c));
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&g);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (!(__bfloat162float(h[j].x) > 0.f)) v[2 * j] = 0.f;
+          if (!(__bfloat162float(h[j].y) > 0.f)) v[2 * j + 1] = 0.f;
+        }
+      }
+      if (p.out_c != nullptr) {
+        uint4 o;
+        o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]); o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+        *reinterpret_cast<uint4*>(p.out_c + b1 * p.c_b1 + b2 * p.c_b2 + static_cast<int64_t>(r) * p.ld_c + c) = o;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) tile[(chunk * 8 + j) * kTcPitch + rl] = __float2bfloat16_rn(v[j]);
+  }
+  __syncthreads();
+  if (p.out_t == nullptr) return;
+#pragma unroll
+  for (int it = 0; it < 2; ++it) {
+    const int cl = (t >> 3) + it * 32;
+    const int c = c0 + cl, r = r0 + chunk * 8;
+    if (c < p.C && r < p.Rp) {
+      const uint32_t* src = reinterpret_cast<const uint32_t*>(&tile[cl * kTcPitch + chunk * 8]);
+      uint4 o;
+      o.x = src[0]; o.y = src[1]; o.z = src[2]; o.w = src[3];
+      *reinterpret_cast<uint4*>(p.out_t + b1 * p.t_b1 + b2 * p.t_b2 + static_cast<int64_t>(c) * p.ld_t + r) = o;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
-// colsum: out[c] (+)= sum_r in[r][c]  (bias gradients).  One block per 32 columns.
+// colsum: out[c] (+)= sum_r in[r][c] * (gate[r][c] > 0)  (bias gradients).  Each block takes 64 columns x one chunk of
+// rows: a warp reads one row segment of 64 columns per step (2 columns per lane: 128 B of bf16 / 256 B of fp32,
+// coalesced), the 8 warps stride over the chunk's rows; partial sums meet in shared memory and leave with one atomicAdd
+// per column (the host zero-fills `out` first unless accumulating).  C must be even.
 // ------------------------------------------------------------------------------------------------
 __global__ void colsum_kernel(const void* __restrict__ in, int in_fp32, int64_t ld, const __nv_bfloat16* __restrict__ gate,
-                              int64_t ld_gate, float* __restrict__ out, int R, int C, int accumulate) {
+                              int64_t ld_gate, float* __restrict__ out, int R, int C, int rows_per_block) {
   pdl_sync();
-  __shared__ float part[8][33];
-  const int c = blockIdx.x * 32 + threadIdx.x;
-  float s = 0.f;
-  if (c < C)
-    for (int r = threadIdx.y; r < R; r += blockDim.y) {
+  __shared__ float part[8][64];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int c = blockIdx.x * 64 + lane * 2;
+  const int r_begin = blockIdx.y * rows_per_block;
+  const int r_end = min(R, r_begin + rows_per_block);
+  float s0 = 0.f, s1 = 0.f;
+  if (c < C) {
+    for (int r = r_begin + wid; r < r_end; r += 8) {
       const int64_t off = static_cast<int64_t>(r) * ld + c;
-      float v = in_fp32 ? reinterpret_cast<const float*>(in)[off]
-                        : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(in)[off]);
-      if (gate != nullptr && !(__bfloat162float(gate[static_cast<int64_t>(r) * ld_gate + c]) > 0.f)) v = 0.f;
-      s += v;
+      float v0, v1;
+      if (in_fp32) {
+        const float2 v = *reinterpret_cast<const float2*>(reinterpret_cast<const float*>(in) + off);
+        v0 = v.x; v1 = v.y;
+      } else {
+        const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(reinterpret_cast<const __nv_bfloat16*>(in) + off);
+        v0 = __bfloat162float(v.x); v1 = __bfloat162float(v.y);
+      }
+      if (gate != nullptr) {
+        const __nv_bfloat162 gt = *reinterpret_cast<const __nv_bfloat162*>(gate + static_cast<int64_t>(r) * ld_gate + c);
+        if (!(__bfloat162float(gt.x) > 0.f)) v0 = 0.f;
+        if (!(__bfloat162float(gt.y) > 0.f)) v1 = 0.f;
+      }
+      s0 += v0; s1 += v1;
     }
-  part[threadIdx.y][threadIdx.x] = s;
+  }
+  part[wid][lane * 2] = s0;
+  part[wid][lane * 2 + 1] = s1;
   __syncthreads();
-  if (threadIdx.y == 0 && c < C) {
-    float t = 0.f;
-    for (int i = 0; i < blockDim.y; ++i) t += part[i][threadIdx.x];
-    out[c] = accumulate ? out[c] + t : t;
+  if (threadIdx.x < 64) {
+    const int cc = blockIdx.x * 64 + threadIdx.x;
+    if (cc < C) {
+      float t = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) t += part[i][threadIdx.x];
+      atomicAdd(&out[cc], t);
+    }
   }
 }
 
@@ -229,41 +317,71 @@ struct SoftmaxBwdParams {
   int B, H, N, S, ld, Np;
 };
 
-__global__ void softmax_bwd_kernel(const SoftmaxBwdParams p) {
+__global__ void __launch_bounds__(256) softmax_bwd_kernel(const SoftmaxBwdParams p) {
   pdl_sync();
-  __shared__ float tP[32][33], tD[32][33];
+  // 64 queries x 64 keys per block; thread (row, chunk) owns 8 consecutive keys of one query row (two rows per thread)
+  __shared__ __align__(16) __nv_bfloat16 tP[64 * kTcPitch], tD[64 * kTcPitch];     // [s][n]
   const int bh = blockIdx.z, b = bh / p.H, h = bh % p.H;
-  const int n0 = blockIdx.y * 32, s0 = blockIdx.x * 32;
+  const int n0 = blockIdx.y * 64, s0 = blockIdx.x * 64;
+  const int t = threadIdx.x, chunk = t & 7;
   const int64_t base = static_cast<int64_t>(bh) * p.N * p.ld;
-  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
-    const int n = n0 + i, s = s0 + threadIdx.x;
-    float pv = 0.f, dv = 0.f;
+#pragma unroll
+  for (int it = 0; it < 2; ++it) {
+    const int nl = (t >> 3) + it * 32;
+    const int n = n0 + nl, s = s0 + chunk * 8;
+    float pv[8], dv[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { pv[j] = 0.f; dv[j] = 0.f; }
     if (n < p.N && s < p.ld) {
-      bool masked = s >= p.S;
-      if (!masked && p.mask_bits != nullptr) {
-        const uint32_t word = p.mask_bits[b * p.mask_b_stride + h * p.mask_h_stride + n * p.mask_q_stride + (s >> 5)];
-        masked = (word >> (s & 31)) & 1u;
+      const int64_t row = static_cast<int64_t>(bh) * p.N + n;
+      const int64_t off = base + static_cast<int64_t>(n) * p.ld + s;
+      if (s < p.S) {
+        uint32_t mbits = 0;
+        if (p.mask_bits != nullptr)
+          mbits = (p.mask_bits[b * p.mask_b_stride + h * p.mask_h_stride + n * p.mask_q_stride + (s >> 5)] >> (s & 31)) & 0xffu;
+        const float m = p.m[row], inv_l = 1.f / p.l[row], dl = p.delta[row];
+        const float4 sa = *reinterpret_cast<const float4*>(p.S2 + off), sb = *reinterpret_cast<const float4*>(p.S2 + off + 4);
+        const float4 da = *reinterpret_cast<const float4*>(p.dP + off), db = *reinterpret_cast<const float4*>(p.dP + off + 4);
+        float sc[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
+        const float dp[8] = {da.x, da.y, da.z, da.w, db.x, db.y, db.z, db.w};
+        if (p.bias != nullptr) {
+          const float4 ba = *reinterpret_cast<const float4*>(p.bias + row * p.bias_ld + s);
+          const float4 bb = *reinterpret_cast<const float4*>(p.bias + row * p.bias_ld + s + 4);
+          sc[0] += ba.x; sc[1] += ba.y; sc[2] += ba.z; sc[3] += ba.w; sc[4] += bb.x; sc[5] += bb.y; sc[6] += bb.z; sc[7] += bb.w;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (s + j < p.S && !((mbits >> j) & 1u)) {
+            pv[j] = exp2f(sc[j] - m) * inv_l;
+            dv[j] = 0.6931471805599453f * pv[j] * (dp[j] - dl);
+          }
+        }
       }
-      if (!masked) {
-        const int64_t st = (static_cast<int64_t>(bh)) * p.N + n;
-        float sc = p.S2[base + static_cast<int64_t>(n) * p.ld + s];
-        if (p.bias != nullptr) sc += p.bias[st * p.bias_ld + s];
-        pv = exp2f(sc - p.m[st]) / p.l[st];
-        dv = 0.6931471805599453f * pv * (p.dP[base + static_cast<int64_t>(n) * p.ld + s] - p.delta[st]);
+      uint4 o;
+      o.x = pack_bf16x2(dv[0], dv[1]); o.y = pack_bf16x2(dv[2], dv[3]); o.z = pack_bf16x2(dv[4], dv[5]); o.w = pack_bf16x2(dv[6], dv[7]);
+      *reinterpret_cast<uint4*>(p.dS + off) = o;
+      if (p.P != nullptr) {
+        o.x = pack_bf16x2(pv[0], pv[1]); o.y = pack_bf16x2(pv[2], pv[3]); o.z = pack_bf16x2(pv[4], pv[5]); o.w = pack_bf16x2(pv[6], pv[7]);
+        *reinterpret_cast<uint4*>(p.P + off) = o;
       }
-      p.P[base + static_cast<int64_t>(n) * p.ld + s] = __float2bfloat16_rn(pv);
-      p.dS[base + static_cast<int64_t>(n) * p.ld + s] = __float2bfloat16_rn(dv);
     }
-    tP[i][threadIdx.x] = pv;
-    tD[i][threadIdx.x] = dv;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      tP[(chunk * 8 + j) * kTcPitch + nl] = __float2bfloat16_rn(pv[j]);
+      tD[(chunk * 8 + j) * kTcPitch + nl] = __float2bfloat16_rn(dv[j]);
+    }
   }
   __syncthreads();
   const int64_t tbase = static_cast<int64_t>(bh) * p.ld * p.Np;
-  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
-    const int s = s0 + i, n = n0 + threadIdx.x;
+#pragma unroll
+  for (int it = 0; it < 2; ++it) {
+    const int sl = (t >> 3) + it * 32;
+    const int s = s0 + sl, n = n0 + chunk * 8;
     if (s < p.ld && n < p.Np) {
-      p.Pt[tbase + static_cast<int64_t>(s) * p.Np + n] = __float2bfloat16_rn(tP[threadIdx.x][i]);
-      p.dSt[tbase + static_cast<int64_t>(s) * p.Np + n] = __float2bfloat16_rn(tD[threadIdx.x][i]);
+      const uint32_t* a = reinterpret_cast<const uint32_t*>(&tP[sl * kTcPitch + chunk * 8]);
+      const uint32_t* d = reinterpret_cast<const uint32_t*>(&tD[sl * kTcPitch + chunk * 8]);
+      *reinterpret_cast<uint4*>(p.Pt + tbase + static_cast<int64_t>(s) * p.Np + n) = make_uint4(a[0], a[1], a[2], a[3]);
+      *reinterpret_cast<uint4*>(p.dSt + tbase + static_cast<int64_t>(s) * p.Np + n) = make_uint4(d[0], d[1], d[2], d[3]);
     }
   }
 }
@@ -351,6 +469,17 @@ extern "C" int pq3d_transpose_cast(const void* in, int in_fp32, int64_t ld_in, i
   p.ld_t = ld_t; p.t_b1 = t_b1; p.t_b2 = t_b2;
   p.ld_c = ld_c; p.c_b1 = c_b1; p.c_b2 = c_b2;
   p.R = R; p.C = C; p.Rp = Rp; p.B2 = B2; p.in_fp32 = in_fp32; p.scale = scale;
+  auto m8 = [](int64_t v) { return v % 8 == 0; };
+  auto a16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  const bool vec = m8(C) && m8(Rp) && m8(ld_in) && m8(in_b1) && m8(in_b2) && a16(in) &&
+                   (!gate || (m8(ld_gate) && m8(gate_b1) && m8(gate_b2) && a16(gate))) &&
+                   (!out_t || (m8(ld_t) && m8(t_b1) && m8(t_b2) && a16(out_t))) &&
+                   (!out_c || (m8(ld_c) && m8(c_b1) && m8(c_b2) && a16(out_c)));
+  if (vec) {
+    dim3 grid((C + 63) / 64, (Rp + 63) / 64, B1 * B2);
+    PQ3D_CUDA(launch_kernel(transpose_cast_vec_kernel, grid, dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), p));
+    return PQ3D_OK;
+  }
   dim3 grid((C + 31) / 32, (Rp + 31) / 32, B1 * B2), block(32, 8);
   PQ3D_CUDA(launch_kernel(transpose_cast_kernel, grid, block, 0, reinterpret_cast<cudaStream_t>(stream), p));
   return PQ3D_OK;
@@ -359,8 +488,18 @@ extern "C" int pq3d_transpose_cast(const void* in, int in_fp32, int64_t ld_in, i
 extern "C" int pq3d_colsum(const void* in, int in_fp32, int64_t ld, const void* gate, int64_t ld_gate, float* out, int R,
                            int C, int accumulate, void* stream) {
   PQ3D_CHECK_ARG(in && out && R > 0 && C > 0, "pq3d_colsum: bad argument");
-  PQ3D_CUDA(launch_kernel(colsum_kernel, dim3((C + 31) / 32), dim3(32, 8), 0, reinterpret_cast<cudaStream_t>(stream), in,
-                          in_fp32, ld, reinterpret_cast<const __nv_bfloat16*>(gate), ld_gate, out, R, C, accumulate));
+  PQ3D_CHECK_ARG(C % 2 == 0 && ld % 2 == 0 && ld_gate % 2 == 0 && (reinterpret_cast<uintptr_t>(in) & 7) == 0,
+                 "pq3d_colsum: C, ld must be even and the input 8-byte aligned");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (!accumulate) PQ3D_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * C, st));
+  const int col_blocks = (C + 63) / 64;
+  int chunks = (sm_count() * 4 + col_blocks - 1) / col_blocks;        // ~4 blocks per SM in total
+  const int max_chunks = (R + 63) / 64;                               // at least 64 rows per block
+  if (chunks > max_chunks) chunks = max_chunks;
+  if (chunks < 1) chunks = 1;
+  const int rows_per_block = (R + chunks - 1) / chunks;
+  PQ3D_CUDA(launch_kernel(colsum_kernel, dim3(col_blocks, (R + rows_per_block - 1) / rows_per_block), dim3(256), 0, st, in,
+                          in_fp32, ld, reinterpret_cast<const __nv_bfloat16*>(gate), ld_gate, out, R, C, rows_per_block));
   return PQ3D_OK;
 }
 
@@ -400,8 +539,10 @@ extern "C" int pq3d_softmax_bwd(const float* S2, const float* dP, const float* d
                                 const float* bias, int64_t bias_ld, const uint32_t* mask_bits, int64_t mask_b_stride,
                                 int64_t mask_h_stride, int64_t mask_q_stride, void* P, void* dS, void* Pt, void* dSt,
                                 int B, int H, int N, int S, int ld, int Np, void* stream) {
-  PQ3D_CHECK_ARG(S2 && dP && delta && m && l && P && dS && Pt && dSt, "pq3d_softmax_bwd: null argument");
+  PQ3D_CHECK_ARG(S2 && dP && delta && m && l && dS && Pt && dSt, "pq3d_softmax_bwd: null argument");
   PQ3D_CHECK_ARG(B > 0 && H > 0 && N > 0 && S > 0 && ld >= S && Np >= N, "pq3d_softmax_bwd: bad shape");
+  PQ3D_CHECK_ARG(ld % 32 == 0 && Np % 8 == 0 && bias_ld % 4 == 0,
+                 "pq3d_softmax_bwd: ld must be a multiple of 32, Np of 8, bias_ld of 4 (16-byte vector accesses)");
   SoftmaxBwdParams p;
   p.S2 = S2; p.dP = dP; p.delta = delta; p.m = m; p.l = l; p.bias = bias; p.bias_ld = bias_ld;
   p.mask_bits = mask_bits; p.mask_b_stride = mask_b_stride; p.mask_h_stride = mask_h_stride;
@@ -410,8 +551,8 @@ extern "C" int pq3d_softmax_bwd(const float* S2, const float* dP, const float* d
   p.Pt = reinterpret_cast<__nv_bfloat16*>(Pt); p.dSt = reinterpret_cast<__nv_bfloat16*>(dSt);
   p.B = B; p.H = H; p.N = N; p.S = S; p.ld = ld; p.Np = Np;
   const int rows = Np > N ? Np : N;
-  dim3 grid((ld + 31) / 32, (rows + 31) / 32, B * H), block(32, 8);
-  PQ3D_CUDA(launch_kernel(softmax_bwd_kernel, grid, block, 0, reinterpret_cast<cudaStream_t>(stream), p));
+  dim3 grid((ld + 63) / 64, (rows + 63) / 64, B * H);
+  PQ3D_CUDA(launch_kernel(softmax_bwd_kernel, grid, dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), p));
   return PQ3D_OK;
 }
 

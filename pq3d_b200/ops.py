@@ -350,7 +350,7 @@ def softmax_bwd(S2, dP, delta, m, l, P, dS, Pt, dSt, B, H, N, S, ld, Np, bias=No
                 mask_strides=(0, 0, 0)):
     rc = _lib.lib().pq3d_softmax_bwd(S2.data_ptr(), dP.data_ptr(), delta.data_ptr(), m.data_ptr(), l.data_ptr(),
                                      _p(bias), 0 if bias is None else bias.shape[-1], _p(mask_bits), *mask_strides,
-                                     P.data_ptr(), dS.data_ptr(), Pt.data_ptr(), dSt.data_ptr(), B, H, N, S, ld, Np,
+                                     _p(P), dS.data_ptr(), Pt.data_ptr(), dSt.data_ptr(), B, H, N, S, ld, Np,
                                      _stream())
     _lib.check(rc, "pq3d_softmax_bwd")
     _count()

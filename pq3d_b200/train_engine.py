@@ -69,7 +69,12 @@ def forward(enc, query, query_pos, query_masks, mems: List[Tuple[str, torch.Tens
     B, N, D = query.shape
     H, L = enc.num_heads, enc.num_layers
     R = B * N
+    # weights change every step and fused optimizers update them without bumping the tensors' version counters
+    # (which is what QueryMaskEncoder.packed() keys its cache on): always repack here, and leave no cached copy
+    # behind for a later inference call to pick up
+    enc._packed = None
     pk = enc.packed(dev)
+    enc._packed = None
     program = [g for g in enc._program() if len(g) > 0]
     sv: Dict = dict(B=B, N=N, D=D, H=H, L=L, R=R, program=program, pk=pk, layers=[], mems={})
 
@@ -223,9 +228,9 @@ class _Bwd:
         ops.bgemm(dOv, Vv, sub(dP))
         delta = _e((B, H, N), f32, dev)
         ops.attn_delta(dO2d, O2d, delta, B, H, N)
-        P, dS = _e((B, H, N, ld), bf16, dev), _e((B, H, N, ld), bf16, dev)
+        dS = _e((B, H, N, ld), bf16, dev)
         Pt, dSt = _e((B, H, ld, Npad), bf16, dev), _e((B, H, ld, Npad), bf16, dev)
-        ops.softmax_bwd(S2, dP, delta, st_m, st_l, P, dS, Pt, dSt, B, H, N, S, ld, Npad, bias=bias, mask_bits=mask_bits,
+        ops.softmax_bwd(S2, dP, delta, st_m, st_l, None, dS, Pt, dSt, B, H, N, S, ld, Npad, bias=bias, mask_bits=mask_bits,
                         mask_strides=mask_strides)
         dOt, Qt = _e((B, H, 64, Npad), bf16, dev), _e((B, H, 64, Npad), bf16, dev)
         ops.transpose_cast(dOv, dOt)
