@@ -192,6 +192,15 @@ int pq3d_spatial_bias_bwd(const float* pairwise_locs, const float* loc_w, const 
 /* out = a + b (+ c), fp32, n multiple of 4. */
 int pq3d_add3(const float* a, const float* b, const float* c, float* out, int64_t n, void* stream);
 
+/* Per-step refresh of the kernels' operand copies of the fp32 parameters, ONE launch for the whole decoder.
+ * segs_dev: DEVICE array of n_seg x 8 int64 words {src, dst_c, dst_t, rows, cols, ld_c, ld_t, flags}: src fp32
+ * [rows, cols] dense -> dst_c[r*ld_c + c] (bf16, or fp32 when flags & 1; may be 0) and dst_t[c*ld_t + r] (bf16
+ * transposed copy for the dgrad GEMMs; may be 0).  tile_start_dev: DEVICE int32 [n_seg] — index of each segment's
+ * first 64x64 tile; total_tiles = number of tiles over all segments.  Replaces autocast's per-call weight casts
+ * (every nn.Linear / MHA projection under torch.autocast in the reference's training step). */
+int pq3d_pack_segments(const int64_t* segs_dev, const int32_t* tile_start_dev, int n_seg, int total_tiles,
+                       void* stream);
+
 #ifdef __cplusplus
 }
 #endif

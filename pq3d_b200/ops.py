@@ -367,3 +367,12 @@ def add3(a, b, c, out):
     rc = _lib.lib().pq3d_add3(a.data_ptr(), b.data_ptr(), _p(c), out.data_ptr(), out.numel(), _stream())
     _lib.check(rc, "pq3d_add3")
     _count()
+
+
+def pack_segments(segs: torch.Tensor, tile_start: torch.Tensor, total_tiles: int):
+    """segs: int64 (n_seg, 8) device table, tile_start: int32 (n_seg,) device (see pq3d_pack_segments)."""
+    _chk(segs, torch.int64, "segs", 2)
+    _chk(tile_start, torch.int32, "tile_start", 1)
+    rc = _lib.lib().pq3d_pack_segments(segs.data_ptr(), tile_start.data_ptr(), segs.shape[0], total_tiles, _stream())
+    _lib.check(rc, "pq3d_pack_segments")
+    _count()

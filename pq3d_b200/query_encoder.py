@@ -162,28 +162,39 @@ class _Packed:
     """bf16 operand copies of the fp32 parameters, laid out for the kernels:
        per memory  : Wk / Wv stacked over layers   [L*D, D]  (K/V projections hoisted out of the layer loop)
        per layer   : per CA group Wq stacked over the group's memories [g*D, D], out_proj [g*D, D],
-                     LN gamma/beta [g, D]; self-attention [Wq;Wk] [2D, D], Wv, fc; FFN W1, W2."""
+                     LN gamma/beta [g, D]; self-attention [Wq;Wk] [2D, D], Wv, fc; FFN W1, W2.
+    The buffers are allocated once; `refresh()` rewrites all of them from the live parameters with ONE kernel
+    launch (pq3d_pack_segments reading a device-side segment table), so a training step re-packs for the cost of
+    one pass over the weights, CUDA graphs that captured these pointers stay valid, and `train=True` adds the
+    transposed copies the dgrad GEMMs take (`T(w)`)."""
 
-    def __init__(self, enc: "QueryMaskEncoder", device):
+    def __init__(self, enc: "QueryMaskEncoder", device, train: bool = False):
         D, L = enc.hidden_size, enc.num_layers
         layers = enc.unified_encoder
         mems = enc.memories
-        f32 = dict(device=device, dtype=torch.float32)
+        self.device, self.train, self.stale = device, train, False
+        self._order, self._fused_copy = list(mems), False
+        self._segs: List[tuple] = []        # (src view, dst_c, dst_t, row0, fp32?)
+        self._t: Dict[int, torch.Tensor] = {}
+        self._keep: List[torch.Tensor] = []
+        self._table = None
 
-        def w16(t):
-            return t.detach().to(device=device, dtype=bf16).contiguous()
-
-        def f(t):
-            return t.detach().to(**f32).contiguous()
-
+        w16, f = self._w16, self._f32
         self.wk, self.bk, self.wv, self.bv = {}, {}, {}, {}
+        n_mem = len(mems)
+        # every memory's Wk (Wv) in one buffer, in `memories` order: consecutive memories fuse into one grouped GEMM
+        self._wk_all = self._alloc_w(n_mem * L * D, D) if n_mem else None
+        self._wv_all = self._alloc_w(n_mem * L * D, D) if n_mem else None
+        self._bk_all = torch.empty(n_mem * L * D, dtype=torch.float32, device=device)
+        self._bv_all = torch.empty(n_mem * L * D, dtype=torch.float32, device=device)
         for j, m in enumerate(mems):
             ipw = [layers[i].cross_attn_list[j].multihead_attn.in_proj_weight for i in range(L)]
             ipb = [layers[i].cross_attn_list[j].multihead_attn.in_proj_bias for i in range(L)]
-            self.wk[m] = w16(torch.cat([w[D:2 * D] for w in ipw], 0))
-            self.bk[m] = f(torch.cat([b[D:2 * D] for b in ipb], 0))
-            self.wv[m] = w16(torch.cat([w[2 * D:] for w in ipw], 0))
-            self.bv[m] = f(torch.cat([b[2 * D:] for b in ipb], 0))
+            sl = slice(j * L * D, (j + 1) * L * D)
+            self.wk[m] = w16([w[D:2 * D] for w in ipw], into=self._wk_all, row0=j * L * D)
+            self.wv[m] = w16([w[2 * D:] for w in ipw], into=self._wv_all, row0=j * L * D)
+            self.bk[m] = f([b[D:2 * D] for b in ipb], into=self._bk_all[sl])
+            self.bv[m] = f([b[2 * D:] for b in ipb], into=self._bv_all[sl])
         self.layers = []
         for i in range(L):
             lay = layers[i]
@@ -192,45 +203,133 @@ class _Packed:
                 idx = [mems.index(m) for m in grp]
                 cas = [lay.cross_attn_list[j] for j in idx]
                 d["groups"][grp] = dict(
-                    wq=w16(torch.cat([c.multihead_attn.in_proj_weight[:D] for c in cas], 0)),
-                    bq=f(torch.cat([c.multihead_attn.in_proj_bias[:D] for c in cas], 0)),
-                    wo=w16(torch.cat([c.multihead_attn.out_proj.weight for c in cas], 0)),
-                    bo=f(torch.stack([c.multihead_attn.out_proj.bias for c in cas], 0)),
-                    gamma=f(torch.stack([c.norm.weight for c in cas], 0)),
-                    beta=f(torch.stack([c.norm.bias for c in cas], 0)),
+                    wq=w16([c.multihead_attn.in_proj_weight[:D] for c in cas]),
+                    bq=f([c.multihead_attn.in_proj_bias[:D] for c in cas]),
+                    wo=w16([c.multihead_attn.out_proj.weight for c in cas]),
+                    bo=f([c.multihead_attn.out_proj.bias for c in cas]).view(len(cas), D),
+                    gamma=f([c.norm.weight for c in cas]).view(len(cas), D),
+                    beta=f([c.norm.bias for c in cas]).view(len(cas), D),
                     eps=cas[0].norm.eps)
             sa = lay.self_attn
             if isinstance(sa, SpatialSelfAttentionLayer):
                 a = sa.self_attn
-                d["sa"] = dict(wqk=w16(torch.cat([a.w_qs.weight, a.w_ks.weight], 0)),
-                               bqk=f(torch.cat([a.w_qs.bias, a.w_ks.bias], 0)),
-                               wv=w16(a.w_vs.weight), bv=f(a.w_vs.bias), wo=w16(a.fc.weight), bo=f(a.fc.bias),
-                               loc_w=f(a.pairwise_loc_fc.weight), loc_b=f(a.pairwise_loc_fc.bias))
+                d["sa"] = dict(wqk=w16([a.w_qs.weight, a.w_ks.weight]), bqk=f([a.w_qs.bias, a.w_ks.bias]),
+                               wv=w16([a.w_vs.weight]), bv=f([a.w_vs.bias]), wo=w16([a.fc.weight]), bo=f([a.fc.bias]),
+                               loc_w=True, loc_b=True)
             else:
                 a = sa.self_attn
-                d["sa"] = dict(wqk=w16(a.in_proj_weight[:2 * D]), bqk=f(a.in_proj_bias[:2 * D]),
-                               wv=w16(a.in_proj_weight[2 * D:]), bv=f(a.in_proj_bias[2 * D:]),
-                               wo=w16(a.out_proj.weight), bo=f(a.out_proj.bias), loc_w=None, loc_b=None)
-            d["sa"].update(gamma=f(sa.norm.weight)[None], beta=f(sa.norm.bias)[None], eps=sa.norm.eps)
+                d["sa"] = dict(wqk=w16([a.in_proj_weight[:2 * D]]), bqk=f([a.in_proj_bias[:2 * D]]),
+                               wv=w16([a.in_proj_weight[2 * D:]]), bv=f([a.in_proj_bias[2 * D:]]),
+                               wo=w16([a.out_proj.weight]), bo=f([a.out_proj.bias]), loc_w=None, loc_b=None)
+            d["sa"].update(gamma=f([sa.norm.weight])[None], beta=f([sa.norm.bias])[None], eps=sa.norm.eps)
             ffn = lay.ffn
-            d["ffn"] = dict(w1=w16(ffn.linear1.weight), b1=f(ffn.linear1.bias), w2=w16(ffn.linear2.weight),
-                            b2=f(ffn.linear2.bias), gamma=f(ffn.norm.weight)[None], beta=f(ffn.norm.bias)[None],
+            d["ffn"] = dict(w1=w16([ffn.linear1.weight]), b1=f([ffn.linear1.bias]), w2=w16([ffn.linear2.weight]),
+                            b2=f([ffn.linear2.bias]), gamma=f([ffn.norm.weight])[None], beta=f([ffn.norm.bias])[None],
                             eps=ffn.norm.eps, F=ffn.linear1.out_features)
             if lay.structure == "gate":
-                d["gate"] = dict(w=w16(lay.gate_proj.weight), b=f(lay.gate_proj.bias))
+                d["gate"] = dict(w=w16([lay.gate_proj.weight]), b=f([lay.gate_proj.bias]))
             self.layers.append(d)
         self._fused_kv = {}
         if self.layers[0]["sa"]["loc_w"] is not None:
-            self.loc_w = torch.stack([d["sa"]["loc_w"] for d in self.layers], 0).contiguous()      # (L, H, 5)
-            self.loc_b = torch.stack([d["sa"]["loc_b"] for d in self.layers], 0).contiguous()      # (L, H)
+            H = enc.num_heads
+            self.loc_w = f([layers[i].self_attn.self_attn.pairwise_loc_fc.weight.view(-1) for i in range(L)]).view(L, H, 5)
+            self.loc_b = f([layers[i].self_attn.self_attn.pairwise_loc_fc.bias for i in range(L)]).view(L, H)
+            for i, d in enumerate(self.layers):
+                d["sa"]["loc_w"], d["sa"]["loc_b"] = self.loc_w[i], self.loc_b[i]
         else:
             self.loc_w = self.loc_b = None
+        self.refresh()
 
+    # ---- registration ------------------------------------------------------------------------------
+    def _alloc_w(self, rows, cols):
+        w = torch.empty((rows, cols), dtype=bf16, device=self.device)
+        if self.train:
+            self._t[w.data_ptr()] = torch.empty((cols, rows), dtype=bf16, device=self.device)
+            self._keep.append(w)
+        return w
+
+    def _src(self, p: torch.Tensor) -> torch.Tensor:
+        p = p.detach()
+        if p.dtype != torch.float32 or not p.is_cuda or not p.is_contiguous():
+            raise TypeError("pq3d_b200: decoder parameters must be contiguous fp32 CUDA tensors (the kernels' bf16 "
+                            f"operand copies are packed from them on the device); got {p.dtype} on {p.device}")
+        return p
+
+    def _w16(self, parts, into=None, row0=0):
+        """bf16 copy of the row-wise concatenation of `parts` (2-D fp32 parameter views, same width)."""
+        parts = [self._src(p) for p in parts]
+        rows, cols = sum(p.shape[0] for p in parts), parts[0].shape[1]
+        base = self._alloc_w(rows, cols) if into is None else into
+        base_t = self._t.get(base.data_ptr())
+        r = row0
+        for p in parts:
+            self._segs.append((p, base, base_t, r, False))
+            r += p.shape[0]
+        self._table = None
+        return base if into is None else base[row0:row0 + rows]
+
+    def _f32(self, parts, into=None):
+        """fp32 copy of the concatenation of 1-D parameter views."""
+        parts = [self._src(p) for p in parts]
+        n = sum(p.numel() for p in parts)
+        dst = torch.empty(n, dtype=torch.float32, device=self.device) if into is None else into
+        o = 0
+        for p in parts:
+            self._segs.append((p.reshape(1, -1), dst[o:o + p.numel()].view(1, -1), None, 0, True))
+            o += p.numel()
+        self._table = None
+        return dst
+
+    def T(self, w: torch.Tensor, row0: int = 0, rows: Optional[int] = None) -> torch.Tensor:
+        """Transposed bf16 copy [cols, rows] of a packed weight (train=True only); `row0/rows` select a row block of w,
+        returned as the matching column block of the transpose."""
+        t = self._t.get(w.data_ptr())
+        if t is None:
+            raise RuntimeError("transposed weight copies exist only for training (packed(train=True))")
+        if t.shape[1] != w.shape[0]:            # w is a row slice of a larger buffer (wk[m] inside _wk_all)
+            raise RuntimeError("T(): pass the base buffer and a row block")
+        return t if rows is None else t[:, row0:row0 + rows]
+
+    def T_mem(self, which: str, j: int, L: int, D: int) -> torch.Tensor:
+        """Transpose [D, L*D] of memory j's stacked Wk / Wv."""
+        base = self._wk_all if which == "k" else self._wv_all
+        return self._t[base.data_ptr()][:, j * L * D:(j + 1) * L * D]
+
+    # ---- the per-step refresh ------------------------------------------------------------------------
+    def _build_table(self):
+        rows, starts, total = [], [], 0
+        for src, dst_c, dst_t, r0, is_f32 in self._segs:
+            R, Cc = src.shape
+            es = 4 if is_f32 else 2
+            ld_c = dst_c.stride(0) if dst_c.ndim == 2 and dst_c.shape[0] > 1 else Cc
+            pc = dst_c.data_ptr() + r0 * ld_c * es
+            pt, ld_t = (0, 0) if dst_t is None else (dst_t.data_ptr() + r0 * 2, dst_t.stride(0))
+            rows.append([src.data_ptr(), pc, pt, R, Cc, ld_c, ld_t, 1 if is_f32 else 0])
+            starts.append(total)
+            total += ((R + 63) // 64) * ((Cc + 63) // 64)
+        self._table = (torch.tensor(rows, dtype=torch.int64).to(self.device),
+                       torch.tensor(starts, dtype=torch.int32).to(self.device), total)
+
+    def refresh(self):
+        if self._table is None:
+            self._build_table()
+        ops.pack_segments(*self._table)
+        self.stale = False
 
     def _fused(self, mems):
+        """Stacked Wk / bk / Wv / bv of several memories (one grouped GEMM): a view when they are consecutive in the
+        configured order, else an extra packed copy."""
         if mems not in self._fused_kv:
-            self._fused_kv[mems] = (torch.cat([self.wk[m] for m in mems], 0), torch.cat([self.bk[m] for m in mems], 0),
-                                    torch.cat([self.wv[m] for m in mems], 0), torch.cat([self.bv[m] for m in mems], 0))
+            order = self._order
+            idx = [order.index(m) for m in mems]
+            LD = self.wk[mems[0]].shape[0]
+            if idx == list(range(idx[0], idx[0] + len(idx))):
+                sl = slice(idx[0] * LD, (idx[-1] + 1) * LD)
+                self._fused_kv[mems] = (self._wk_all[sl], self._bk_all[sl], self._wv_all[sl], self._bv_all[sl])
+            else:
+                self._fused_kv[mems] = (torch.cat([self.wk[m] for m in mems], 0), torch.cat([self.bk[m] for m in mems], 0),
+                                        torch.cat([self.wv[m] for m in mems], 0), torch.cat([self.bv[m] for m in mems], 0))
+                self._fused_copy = True
         return self._fused_kv[mems]
 
     fused_kv = _fused
@@ -282,6 +381,7 @@ class QueryMaskEncoder(nn.Module):
         _reference_init(self)
         self._packed: Optional[_Packed] = None
         self._packed_key = None
+        self._packed_ver = None
         self._ws: Dict[tuple, dict] = {}
         self.use_cuda_graph = True
         self.train_dropout = 0.1      # the reference's sublayer dropout; the training path requires 0.0 (no RNG kernels)
@@ -290,6 +390,8 @@ class QueryMaskEncoder(nn.Module):
         # speed up (it is bound by TMEM->register bandwidth, not HBM) and the narrower GEMMs cost +63 us/step, so
         # the per-layer mode is off unless the hoisted buffers would exceed this many bytes.
         self.kv_hoist_bytes = 8 << 30
+        # training backward: fork parameter-gradient work and the per-memory attention backwards onto side streams
+        self.train_streams = True
 
     # ---- structure -> cross-attention program ------------------------------------------------
     def _active(self) -> List[str]:
@@ -312,14 +414,33 @@ class QueryMaskEncoder(nn.Module):
         return list(dict.fromkeys(g for g in self._program() if len(g) > 0))
 
     # ---- packed weights ------------------------------------------------------------------------
-    def packed(self, device) -> _Packed:
-        key = (str(device), tuple(self.drop_memories_test), tuple(p._version for p in self.parameters()),
-               tuple(p.data_ptr() for p in self.parameters()))
-        if self._packed is None or self._packed_key != key:
-            self._packed = _Packed(self, device)
-            self._packed_key = key
+    def packed(self, device, train: bool = False) -> _Packed:
+        """The kernels' operand copies of the parameters: built once per (device, parameter storage), refreshed by
+        one kernel launch whenever a parameter's version moved, after a training step (`stale`), or always in
+        training (fused optimizers update parameters without bumping version counters)."""
+        params = list(self.parameters())
+        key = (str(device), tuple(self.drop_memories_test), tuple(p.data_ptr() for p in params))
+        ver = tuple(p._version for p in params)
+        pk = self._packed
+        if pk is None or self._packed_key != key or (train and not pk.train):
+            pk = self._packed = _Packed(self, device, train or (pk is not None and pk.train))
+            self._packed_key, self._packed_ver = key, ver
             self._ws.clear()
-        return self._packed
+        elif train or pk.stale or ver != self._packed_ver:
+            if pk._fused_copy:           # torch.cat copies of non-consecutive fused memories: rebuild them
+                pk._fused_kv.clear()
+                self._ws.clear()
+            pk.refresh()
+            self._packed_ver = ver
+        if train:
+            pk.stale = True          # the optimizer step that follows leaves these copies one step behind
+        return pk
+
+    def mark_weights_changed(self):
+        """Tell the decoder its parameters were updated behind autograd's back (CUDA-graph replay of an optimizer
+        step): the next forward re-packs the operand copies."""
+        if self._packed is not None:
+            self._packed.stale = True
 
     def _buf(self, ws: dict, name: str, shape, dtype, device, zero: bool = False):
         t = ws.get(name)

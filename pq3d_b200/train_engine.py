@@ -46,17 +46,17 @@ def _heads(t2d: torch.Tensor, B: int, rows: int, pitch: int, H: int, col0: int =
     return t2d.as_strided((B, H, rows, 64), (pitch * ld, 64, ld, 1), t2d.storage_offset() + col0)
 
 
-class TrainTranspose:
-    """Transposed bf16 weight copies for the dgrad GEMMs, cached per packed-weight object."""
+_SIDE: Dict = {}
 
-    def __init__(self, pk):
-        self.pk, self.cache = pk, {}
 
-    def get(self, key, w: torch.Tensor) -> torch.Tensor:
-        t = self.cache.get(key)
-        if t is None:
-            t = self.cache[key] = w.t().contiguous()
-        return t
+def _side_streams(dev, n):
+    """Per-device pool of side streams: work off the backward's critical path (weight / bias gradients, operand
+    transposes) and the independent per-memory attention backwards run next to the main chain."""
+    key = (dev.type, dev.index)
+    pool = _SIDE.setdefault(key, [])
+    while len(pool) < n:
+        pool.append(torch.cuda.Stream(device=dev))
+    return pool[:n]
 
 
 # ------------------------------------------------------------------------------------------------
@@ -69,12 +69,9 @@ def forward(enc, query, query_pos, query_masks, mems: List[Tuple[str, torch.Tens
     B, N, D = query.shape
     H, L = enc.num_heads, enc.num_layers
     R = B * N
-    # weights change every step and fused optimizers update them without bumping the tensors' version counters
-    # (which is what QueryMaskEncoder.packed() keys its cache on): always repack here, and leave no cached copy
-    # behind for a later inference call to pick up
-    enc._packed = None
-    pk = enc.packed(dev)
-    enc._packed = None
+    # weights change every step (and fused optimizers update them without bumping the tensors' version counters):
+    # one pq3d_pack_segments launch rewrites every bf16 operand copy, plain and transposed, from the live parameters
+    pk = enc.packed(dev, train=True)
     program = [g for g in enc._program() if len(g) > 0]
     sv: Dict = dict(B=B, N=N, D=D, H=H, L=L, R=R, program=program, pk=pk, layers=[], mems={})
 
@@ -167,17 +164,48 @@ def forward(enc, query, query_pos, query_masks, mems: List[Tuple[str, torch.Tens
 # backward
 # ------------------------------------------------------------------------------------------------
 class _Bwd:
+    """One backward pass.  Stream plan: the MAIN stream carries the critical chain (LayerNorm backward -> dgrad ->
+    attention backward -> dgrad ...); everything that only feeds parameter gradients (column sums, operand
+    transposes, wgrad GEMMs) is forked onto a SIDE stream as soon as its inputs exist, and the independent
+    per-memory attention backwards of a parallel group each take their own stream.  All streams join before the
+    gradients are handed to autograd.  Every tensor that crosses streams is kept alive in `self.keep` until the
+    join (the caching allocator reuses a freed block on its allocation stream immediately)."""
+
     def __init__(self, enc, sv):
         self.enc, self.sv = enc, sv
         self.pk = sv["pk"]
-        tt = getattr(self.pk, "_train_t", None)
-        if tt is None:
-            tt = self.pk._train_t = TrainTranspose(self.pk)
-        self.tt = tt
         self.B, self.N, self.D, self.H, self.L, self.R = (sv[k] for k in ("B", "N", "D", "H", "L", "R"))
         self.Rp = ops.pad64(self.R)
         self.grads: Dict[str, torch.Tensor] = {}
         self.dev = sv["qpos"].device
+        self.keep: List = []
+        self.main = torch.cuda.current_stream(self.dev)
+        n_par = max([len(g) for g in sv["program"]] + [1])
+        pool = _side_streams(self.dev, n_par) if enc.train_streams else []
+        self.side = pool[0] if pool else None
+        self.par = pool[1:] if pool else []
+        self.forked = set()
+        n_mem = len(enc.memories)
+        # in_proj gradients of every cross-attention are written in place by the wgrad GEMMs: rows [0, D) from the
+        # query side, [D, 2D) / [2D, 3D) from the hoisted K / V projections
+        self.G_ca = _e((self.L, n_mem, 3 * self.D, self.D), f32, self.dev)
+
+    # ---- streams ----------------------------------------------------------------------------------
+    def on(self, stream, *deps):
+        """Context: run on `stream` after everything issued so far on the main stream; deps are kept alive."""
+        self.keep.extend(d for d in deps if d is not None)
+        if stream is None:
+            return torch.cuda.stream(self.main)
+        stream.wait_stream(torch.cuda.current_stream(self.dev))
+        self.forked.add(stream)
+        return torch.cuda.stream(stream)
+
+    def join(self, streams=None):
+        cur = torch.cuda.current_stream(self.dev)
+        for st in (list(self.forked) if streams is None else streams):
+            if st is not None and st in self.forked:
+                cur.wait_stream(st)
+                self.forked.discard(st)
 
     # ---- small helpers --------------------------------------------------------------------------
     def acc(self, name: str, g: torch.Tensor):
@@ -194,10 +222,12 @@ class _Bwd:
         ops.transpose_cast(x, xt, xc, gate=gate)
         return xt, xc
 
-    def wgrad(self, dyT, xT, n_out, n_in):
-        """dW [n_out, n_in] = dy^T x from the K-major transposes (contraction over padded rows)."""
-        dW = _e((n_out, n_in), f32, self.dev)
-        ops.linear(dyT, xT, dW, M=n_out, N=n_in, K=dyT.shape[1])
+    def wgrad(self, dyT, xT, n_out, n_in, out=None, groups=1, c_group_stride=0):
+        """dW [n_out, n_in] = dy^T x from the K-major transposes (contraction over padded rows).  With groups > 1,
+        dyT holds `groups` row blocks of n_out rows and block g lands at out + g*c_group_stride."""
+        dW = _e((n_out, n_in), f32, self.dev) if out is None else out
+        ops.linear(dyT, xT, dW, M=n_out, N=n_in, K=dyT.shape[1], groups=groups, a_group_rows=n_out if groups > 1 else 0,
+                   w_group_rows=0, ldc=n_in, c_group_stride=c_group_stride)
         return dW
 
     def dgrad(self, dy16, w_t, n_in, out_dtype=f32):
@@ -242,43 +272,52 @@ class _Bwd:
 
     # ---- blocks ---------------------------------------------------------------------------------------
     def ffn_bwd(self, i, s, d_out):
-        R, D, dev = self.R, self.D, self.dev
-        ff = self.pk.layers[i]["ffn"]
+        R, D, dev, pk = self.R, self.D, self.dev, self.pk
+        ff = pk.layers[i]["ffn"]
         F = ff["F"]
         pre = f"unified_encoder.{i}.ffn."
         d_y = _e((R, D), f32, dev)
         dg, db = _z((1, D), f32, dev), _z((1, D), f32, dev)
         ops.layernorm_bwd(s["y"], s["res"], ff["gamma"], d_out, ff["eps"], R, D, d_x=d_y, d_gamma=dg, d_beta=db)
         self.acc(pre + "norm.weight", dg[0]); self.acc(pre + "norm.bias", db[0])
-        self.acc(pre + "linear2.bias", self.colsum(d_y))
         d_yT, d_y16 = self.tcast(d_y, R, D, want_c=True)
-        hT, _ = self.tcast(s["h"], R, F)
-        self.acc(pre + "linear2.weight", self.wgrad(d_yT, hT, D, F))
-        d_h = self.dgrad(d_y16, self.tt.get(("ffn2", i), ff["w2"]), F)
-        self.acc(pre + "linear1.bias", self.colsum(d_h, gate=s["h"]))
+        with self.on(self.side, d_y, d_yT, dg, db):
+            self.acc(pre + "linear2.bias", self.colsum(d_y))
+            hT, _ = self.tcast(s["h"], R, F)
+            self.acc(pre + "linear2.weight", self.wgrad(d_yT, hT, D, F))
+        d_h = self.dgrad(d_y16, pk.T(ff["w2"]), F)
         d_preT, d_pre16 = self.tcast(d_h, R, F, want_c=True, gate=s["h"])
-        xvT, _ = self.tcast(s["xv"], R, D)
-        self.acc(pre + "linear1.weight", self.wgrad(d_preT, xvT, F, D))
-        d_xv = self.dgrad(d_pre16, self.tt.get(("ffn1", i), ff["w1"]), D)
+        with self.on(self.side, d_h, d_preT, d_y16):
+            self.acc(pre + "linear1.bias", self.colsum(d_h, gate=s["h"]))
+            xvT, _ = self.tcast(s["xv"], R, D)
+            self.acc(pre + "linear1.weight", self.wgrad(d_preT, xvT, F, D))
+        d_xv = self.dgrad(d_pre16, pk.T(ff["w1"]), D)
         d_in = _e((R, D), f32, dev)
         ops.add3(d_y, d_xv, None, d_in)
+        self.keep += [d_pre16, d_xv]
         return d_in
 
     def sa_bwd(self, i, s, d_out, d_pos):
-        R, D, B, N, H, dev = self.R, self.D, self.B, self.N, self.H, self.dev
-        sa = self.pk.layers[i]["sa"]
+        R, D, B, N, H, dev, pk = self.R, self.D, self.B, self.N, self.H, self.dev, self.pk
+        sa = pk.layers[i]["sa"]
         spatial = sa["loc_w"] is not None
         pre = f"unified_encoder.{i}.self_attn."
+        a = pre + "self_attn."
         d_y = _e((R, D), f32, dev)
         dg, db = _z((1, D), f32, dev), _z((1, D), f32, dev)
         ops.layernorm_bwd(s["y"], s["res"], sa["gamma"], d_out, sa["eps"], R, D, d_x=d_y, d_gamma=dg, d_beta=db)
         self.acc(pre + "norm.weight", dg[0]); self.acc(pre + "norm.bias", db[0])
-        d_bo = self.colsum(d_y)
         d_yT, d_y16 = self.tcast(d_y, R, D, want_c=True)
         O2d = s["O"].view(R, D)
-        OT, _ = self.tcast(O2d, R, D)
-        d_wo = self.wgrad(d_yT, OT, D, D)
-        dO = self.dgrad(d_y16, self.tt.get(("sa_o", i), sa["wo"]), D, out_dtype=bf16)
+        if not spatial:
+            g_in, g_inb = _e((3 * D, D), f32, dev), _e((3 * D,), f32, dev)
+        with self.on(self.side, d_y, d_yT, dg, db):
+            d_bo = self.colsum(d_y)
+            OT, _ = self.tcast(O2d, R, D)
+            d_wo = self.wgrad(d_yT, OT, D, D)
+            self.acc(a + ("fc.weight" if spatial else "out_proj.weight"), d_wo)
+            self.acc(a + ("fc.bias" if spatial else "out_proj.bias"), d_bo)
+        dO = self.dgrad(d_y16, pk.T(sa["wo"]), D, out_dtype=bf16)
         # operands of the attention backward
         QK = s["QK"]
         Np8, ld = ops.pad8(N), ops.pad64(N)
@@ -296,40 +335,40 @@ class _Bwd:
         dS = self.attention_bwd(Qv, Kv, Vv, Ktp, dO, O2d, s["m"][0], s["l"][0], N, ld, _heads(dQK, B, N, N, H, 0),
                                 _heads(dQK, B, N, N, H, D), _heads(dV, B, N, N, H), bias=bias, mask_bits=qbits,
                                 mask_strides=(qbits.stride(0), 0, 0))
-        d_bqk = self.colsum(dQK)
-        dQKT, _ = self.tcast(dQK, R, 2 * D)
-        xqT, _ = self.tcast(s["xq"], R, D)
-        d_wqk = self.wgrad(dQKT, xqT, 2 * D, D)
-        d_xq = self.dgrad(dQK, self.tt.get(("sa_qk", i), sa["wqk"]), D)
-        d_bv = self.colsum(dV)
-        dVT, _ = self.tcast(dV, R, D)
-        xvT, _ = self.tcast(s["xv"], R, D)
-        d_wv = self.wgrad(dVT, xvT, D, D)
-        d_xv = self.dgrad(dV, self.tt.get(("sa_v", i), sa["wv"]), D)
-        if spatial:
-            a = pre + "self_attn."
-            self.acc(a + "w_qs.weight", d_wqk[:D]); self.acc(a + "w_ks.weight", d_wqk[D:])
-            self.acc(a + "w_qs.bias", d_bqk[:D]); self.acc(a + "w_ks.bias", d_bqk[D:])
-            self.acc(a + "w_vs.weight", d_wv); self.acc(a + "w_vs.bias", d_bv)
-            self.acc(a + "fc.weight", d_wo); self.acc(a + "fc.bias", d_bo)
-            d_lw, d_lb = _z((H, 5), f32, dev), _z((H,), f32, dev)
-            ops.spatial_bias_bwd(self.sv["pw"], sa["loc_w"], sa["loc_b"], dS, ld, d_lw, d_lb, B, H, N)
-            self.acc(a + "pairwise_loc_fc.weight", d_lw); self.acc(a + "pairwise_loc_fc.bias", d_lb)
-        else:
-            a = pre + "self_attn."
-            self.acc(a + "in_proj_weight", torch.cat([d_wqk, d_wv], 0))
-            self.acc(a + "in_proj_bias", torch.cat([d_bqk, d_bv], 0))
-            self.acc(a + "out_proj.weight", d_wo); self.acc(a + "out_proj.bias", d_bo)
+        with self.on(self.side, dQK, dV, dS, d_y16, dO):
+            d_bqk = self.colsum(dQK)
+            dQKT, _ = self.tcast(dQK, R, 2 * D)
+            xqT, _ = self.tcast(s["xq"], R, D)
+            d_bv = self.colsum(dV)
+            dVT, _ = self.tcast(dV, R, D)
+            xvT, _ = self.tcast(s["xv"], R, D)
+            if spatial:
+                d_wqk = self.wgrad(dQKT, xqT, 2 * D, D)
+                d_wv = self.wgrad(dVT, xvT, D, D)
+                self.acc(a + "w_qs.weight", d_wqk[:D]); self.acc(a + "w_ks.weight", d_wqk[D:])
+                self.acc(a + "w_qs.bias", d_bqk[:D]); self.acc(a + "w_ks.bias", d_bqk[D:])
+                self.acc(a + "w_vs.weight", d_wv); self.acc(a + "w_vs.bias", d_bv)
+                d_lw, d_lb = _z((H, 5), f32, dev), _z((H,), f32, dev)
+                ops.spatial_bias_bwd(self.sv["pw"], sa["loc_w"], sa["loc_b"], dS, ld, d_lw, d_lb, B, H, N)
+                self.acc(a + "pairwise_loc_fc.weight", d_lw); self.acc(a + "pairwise_loc_fc.bias", d_lb)
+            else:
+                self.wgrad(dQKT, xqT, 2 * D, D, out=g_in[:2 * D])
+                self.wgrad(dVT, xvT, D, D, out=g_in[2 * D:])
+                g_inb[:2 * D].copy_(d_bqk); g_inb[2 * D:].copy_(d_bv)
+                self.acc(a + "in_proj_weight", g_in); self.acc(a + "in_proj_bias", g_inb)
+        d_xq = self.dgrad(dQK, pk.T(sa["wqk"]), D)
+        d_xv = self.dgrad(dV, pk.T(sa["wv"]), D)
         d_in = _e((R, D), f32, dev)
         ops.add3(d_y, d_xq, d_xv, d_in)
         ops.add3(d_pos, d_xq, None, d_pos)
+        self.keep += [d_xq, d_xv, V, Ktp]
         return d_in
 
     def group_bwd(self, i, s, d_out, d_pos, mem_grads):
-        R, D, B, N, H, dev = self.R, self.D, self.B, self.N, self.H, self.dev
+        R, D, B, N, H, dev, pk = self.R, self.D, self.B, self.N, self.H, self.dev, self.pk
         grp = s["grp"]
         g = len(grp)
-        w = self.pk.layers[i]["groups"][grp]
+        w = pk.layers[i]["groups"][grp]
         idx = [self.enc.memories.index(m) for m in grp]
         d_y = _e((g, R, D), f32, dev)
         d_res = _e((R, D), f32, dev)
@@ -337,42 +376,62 @@ class _Bwd:
         ops.layernorm_bwd(s["y"], s["res"], w["gamma"], d_out, w["eps"], R, D, G=g, y_group_stride=R * D, d_x=d_y,
                           dx_group_stride=R * D, d_res=d_res, d_gamma=dg, d_beta=db)
         dQ = _e((R, g * D), bf16, dev)
-        for jj, (m, j) in enumerate(zip(grp, idx)):
-            pre = f"unified_encoder.{i}.cross_attn_list.{j}."
+        self.keep += [d_y, dg, db, dQ, d_out]
+        casts = [self.tcast(d_y[jj], R, D, want_c=True) for jj in range(g)]
+        self.keep += casts
+        with self.on(self.side):
+            for jj, j in enumerate(idx):
+                pre = f"unified_encoder.{i}.cross_attn_list.{j}."
+                self.acc(pre + "norm.weight", dg[jj]); self.acc(pre + "norm.bias", db[jj])
+                self.acc(pre + "multihead_attn.out_proj.bias", self.colsum(d_y[jj]))
+                OT, _ = self.tcast(s["O"][jj], R, D)
+                self.acc(pre + "multihead_attn.out_proj.weight", self.wgrad(casts[jj][0], OT, D, D))
+        used = []
+        for jj, m in enumerate(grp):
+            # each memory's chain (dgrad -> attention backward) is independent of the others': own stream
+            stream = self.par[jj - 1] if (jj > 0 and jj - 1 < len(self.par)) else None
             st = self.sv["mems"][m]
-            self.acc(pre + "norm.weight", dg[jj]); self.acc(pre + "norm.bias", db[jj])
-            self.acc(pre + "multihead_attn.out_proj.bias", self.colsum(d_y[jj]))
-            d_yT, d_y16 = self.tcast(d_y[jj], R, D, want_c=True)
-            O2d = s["O"][jj]
-            OT, _ = self.tcast(O2d, R, D)
-            self.acc(pre + "multihead_attn.out_proj.weight", self.wgrad(d_yT, OT, D, D))
-            dO = self.dgrad(d_y16, self.tt.get(("ca_o", i, grp, jj), w["wo"][jj * D:(jj + 1) * D]), D, out_dtype=bf16)
-            mg = mem_grads[m]
-            S, Sp = st.S, st.Sp
-            Qv = _heads(s["Q"], B, N, N, H, jj * D)
-            Kv = _heads(st.K, B, S, Sp, H, i * D)
-            Vv = _heads(mg["V"], B, S, Sp, H, i * D)
-            Kt = mg["Kt"]                                               # [L*D, B*Sp]
-            Ktp = Kt.as_strided((B, H, 64, Sp), (Sp, 64 * Kt.stride(0), Kt.stride(0), 1), i * D * Kt.stride(0))
-            self.attention_bwd(Qv, Kv, Vv, Ktp, dO, O2d, s["m"][jj], s["l"][jj], S, Sp, _heads(dQ, B, N, N, H, jj * D),
-                               _heads(mg["dK"], B, S, Sp, H, i * D), _heads(mg["dV"], B, S, Sp, H, i * D),
-                               mask_bits=st.bits, mask_strides=st.strides)
-        d_bq = self.colsum(dQ)
-        dQT, _ = self.tcast(dQ, R, g * D)
-        xqT, _ = self.tcast(s["xq"], R, D)
-        d_wq = self.wgrad(dQT, xqT, g * D, D)
-        d_xq = self.dgrad(dQ, self.tt.get(("ca_q", i, grp), w["wq"]), D)
+            with self.on(stream):
+                used.append(stream)
+                dO = self.dgrad(casts[jj][1], pk.T(w["wo"], jj * D, D), D, out_dtype=bf16)
+                mg = mem_grads[m]
+                S, Sp = st.S, st.Sp
+                Qv = _heads(s["Q"], B, N, N, H, jj * D)
+                Kv = _heads(st.K, B, S, Sp, H, i * D)
+                Vv = _heads(mg["V"], B, S, Sp, H, i * D)
+                Kt = mg["Kt"]                                               # [L*D, B*Sp]
+                Ktp = Kt.as_strided((B, H, 64, Sp), (Sp, 64 * Kt.stride(0), Kt.stride(0), 1), i * D * Kt.stride(0))
+                self.attention_bwd(Qv, Kv, Vv, Ktp, dO, s["O"][jj], s["m"][jj], s["l"][jj], S, Sp,
+                                   _heads(dQ, B, N, N, H, jj * D), _heads(mg["dK"], B, S, Sp, H, i * D),
+                                   _heads(mg["dV"], B, S, Sp, H, i * D), mask_bits=st.bits, mask_strides=st.strides)
+                self.keep.append(dO)
+        self.join([st_ for st_ in used if st_ is not None])
+        G = self.G_ca[i]
+        step = idx[1] - idx[0] if g > 1 else 0
+        regular = all(idx[k + 1] - idx[k] == step for k in range(g - 1)) and (g == 1 or step > 0)
+        with self.on(self.side):
+            d_bq = self.colsum(dQ)
+            dQT, _ = self.tcast(dQ, R, g * D)
+            xqT, _ = self.tcast(s["xq"], R, D)
+            if regular:
+                self.wgrad(dQT, xqT, D, D, out=G[idx[0], :D], groups=g, c_group_stride=step * 3 * D * D)
+            else:
+                for jj, j in enumerate(idx):
+                    self.wgrad(dQT[jj * D:(jj + 1) * D], xqT, D, D, out=G[j, :D])
         mg_q = mem_grads["_q"]
         for jj, j in enumerate(idx):
-            mg_q[(i, j)] = (d_wq[jj * D:(jj + 1) * D], d_bq[jj * D:(jj + 1) * D])
+            mg_q[(i, j)] = d_bq[jj * D:(jj + 1) * D]
+        d_xq = self.dgrad(dQ, pk.T(w["wq"]), D)
         d_in = _e((R, D), f32, dev)
         ops.add3(d_res, d_xq, None, d_in)
         ops.add3(d_pos, d_xq, None, d_pos)
+        self.keep += [d_xq, d_res]
         return d_in
 
     # ---- whole decoder ------------------------------------------------------------------------------------
     def run(self, d_out: torch.Tensor):
-        sv, B, N, D, L, R, dev = self.sv, self.B, self.N, self.D, self.L, self.R, self.dev
+        sv, B, N, D, L, R, dev, pk = self.sv, self.B, self.N, self.D, self.L, self.R, self.dev, self.pk
+        n_mem = len(self.enc.memories)
         mem_grads: Dict = {"_q": {}}
         for name, st in sv["mems"].items():
             V = _e((B * st.Sp, L * D), bf16, dev)
@@ -388,30 +447,38 @@ class _Bwd:
             d_q = self.sa_bwd(i, lay["sa"], d_q, d_pos)
             for s in reversed(lay["groups"]):
                 d_q = self.group_bwd(i, s, d_q, d_pos, mem_grads)
+            self.keep.append(d_q)
         # memory side: weight / bias gradients of the hoisted K and V projections, input gradients
         d_mem = {}
+        G_b = _e((L, n_mem, 3 * D), f32, dev)
         for name, st in sv["mems"].items():
             mg = mem_grads[name]
             j = self.enc.memories.index(name)
             rows = B * st.Sp
-            d_bk, d_bv = self.colsum(mg["dK"]), self.colsum(mg["dV"])
-            dKT, _ = self.tcast(mg["dK"], rows, L * D)
-            xkT, _ = self.tcast(st.xk, rows, D)
-            d_wk = self.wgrad(dKT, xkT, L * D, D)
-            dVT, _ = self.tcast(mg["dV"], rows, L * D)
-            xvT = xkT if not st.has_pos else self.tcast(st.xv, rows, D)[0]
-            d_wv = self.wgrad(dVT, xvT, L * D, D)
-            d_xk = self.dgrad(mg["dK"], self.tt.get(("mem_k", name), self.pk.wk[name]), D)
-            d_xv = self.dgrad(mg["dV"], self.tt.get(("mem_v", name), self.pk.wv[name]), D)
+            with self.on(self.side):
+                d_bk, d_bv = self.colsum(mg["dK"]), self.colsum(mg["dV"])
+                dKT, _ = self.tcast(mg["dK"], rows, L * D)
+                xkT, _ = self.tcast(st.xk, rows, D)
+                self.wgrad(dKT, xkT, D, D, out=self.G_ca[0, j, D:2 * D], groups=L, c_group_stride=n_mem * 3 * D * D)
+                dVT, _ = self.tcast(mg["dV"], rows, L * D)
+                xvT = xkT if not st.has_pos else self.tcast(st.xv, rows, D)[0]
+                self.wgrad(dVT, xvT, D, D, out=self.G_ca[0, j, 2 * D:], groups=L, c_group_stride=n_mem * 3 * D * D)
+                G_b[:, j, D:2 * D].copy_(d_bk.view(L, D))
+                G_b[:, j, 2 * D:].copy_(d_bv.view(L, D))
+                for i in range(L):
+                    G_b[i, j, :D].copy_(mem_grads["_q"][(i, j)])
+            d_xk = self.dgrad(mg["dK"], pk.T_mem("k", j, L, D), D)
+            d_xv = self.dgrad(mg["dV"], pk.T_mem("v", j, L, D), D)
             for i in range(L):
                 pre = f"unified_encoder.{i}.cross_attn_list.{j}.multihead_attn."
-                d_wq, d_bq = mem_grads["_q"][(i, j)]
-                sl = slice(i * D, (i + 1) * D)
-                self.acc(pre + "in_proj_weight", torch.cat([d_wq, d_wk[sl], d_wv[sl]], 0))
-                self.acc(pre + "in_proj_bias", torch.cat([d_bq, d_bk[sl], d_bv[sl]], 0))
+                self.acc(pre + "in_proj_weight", self.G_ca[i, j])
+                self.acc(pre + "in_proj_bias", G_b[i, j])
             d_feat = _e((rows, D), f32, dev)
             ops.add3(d_xk, d_xv, None, d_feat)
+            self.keep += [d_xk, d_xv]
             d_mem[name] = (d_feat.view(B, st.Sp, D)[:, :st.S], d_xk.view(B, st.Sp, D)[:, :st.S] if st.has_pos else None)
+        self.join()
+        self.keep.clear()
         return d_q.view(B, N, D), d_pos.view(B, N, D), d_mem, self.grads
 
 

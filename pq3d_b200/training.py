@@ -52,7 +52,7 @@ class GraphedTrainStep:
 
     def __init__(self, encoder, optimizer, loss_fn: Callable, reducer: Optional[Callable] = None, warmup: int = 3):
         self.enc, self.opt, self.loss_fn, self.reducer = encoder, optimizer, loss_fn, reducer
-        self.warmup, self.calls = warmup, 0
+        self.warmup, self.calls = max(1, warmup), 0   # >= 1: buffers the capture reuses are created eagerly
         self.graph = None
         self.static = None
         self.loss = None
@@ -79,7 +79,7 @@ class GraphedTrainStep:
             _copy_into(self.static, (input_dict, pairwise_locs, loss_args), set())
             self.graph.replay()
             ops._count(self.launches)
-            self.enc._packed = None          # packed weights inside the graph pool trail the parameters by one step
+            self.enc.mark_weights_changed()  # the packed operand copies trail the parameters by one step
             return self.loss
         if self.calls < self.warmup:
             self.calls += 1
@@ -95,7 +95,6 @@ class GraphedTrainStep:
         inp, pw, largs = self.static
         torch.cuda.synchronize()
         self.opt.zero_grad(set_to_none=True)
-        self.enc._packed = None              # the weight repack must be part of the captured work
         before = ops.LAUNCHES
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
@@ -109,5 +108,5 @@ class GraphedTrainStep:
         ops.LAUNCHES = before
         self.graph.replay()
         ops._count(self.launches)
-        self.enc._packed = None
+        self.enc.mark_weights_changed()
         return self.loss
