@@ -201,6 +201,26 @@ int pq3d_add3(const float* a, const float* b, const float* c, float* out, int64_
 int pq3d_pack_segments(const int64_t* segs_dev, const int32_t* tile_start_dev, int n_seg, int total_tiles,
                        void* stream);
 
+/* Backward of the attention core in one kernel (scores never leave the SM).  Per (scene b, head h):
+ *   S2 = Q2 K^T + bias (log2 domain, Q2 = Q pre-scaled as in pq3d_attention_fwd), P = ex2(S2 - m) / l (0 where masked),
+ *   dP = dO V^T, dS2 = ln2 * P o (dP - delta);   dV = P^T dO,  dK = dS2^T Q2,  dQ += q_scale * dS2 K.
+ *   Q  : bf16 [B*Nq, ldq], head h at columns q_col0 + h*64;  dO likewise (lddo, do_col0)
+ *   K,V: bf16 row-major [B*S_pitch, ld], scene b at rows b*S_pitch, S valid rows; head h at columns col0 + h*64
+ *   mask_bits / strides, bias / bias_ld: as in pq3d_attention_fwd (bias: fp32 [B, H, Nq, bias_ld])
+ *   stat_m, stat_l: [B, H, Nq] saved by the forward; delta: [B, H, Nq] from pq3d_attn_delta
+ *   dK, dV: bf16, same row layout as K / V (ld_dk, dk_col0, ...): rows < S of every head block are overwritten
+ *   dQ: fp32 [B*Nq, ld_dq], ACCUMULATED with atomics at columns dq_col0 + h*64 (zero-fill before the call)
+ *   dS_out: optional bf16 [B, H, Nq, ds_ld] (for the spatial-bias backward)
+ * Requires Nq <= 128.  Replaces autograd through torch/nn/functional.py:6630-6647 and
+ * modules/layers/transformers.py:224-236 in the reference's training step. */
+int pq3d_attention_bwd(const void* Q, int64_t ldq, int q_col0, const void* dO, int64_t lddo, int do_col0,
+                       const void* K, int64_t ldk, int k_col0, const void* V, int64_t ldv, int v_col0, int S,
+                       int S_pitch, const uint32_t* mask_bits, int64_t mask_b_stride, int64_t mask_h_stride,
+                       int64_t mask_q_stride, const float* bias, int64_t bias_ld, const float* stat_m,
+                       const float* stat_l, const float* delta, void* dK, int64_t ld_dk, int dk_col0, void* dV,
+                       int64_t ld_dv, int dv_col0, float* dQ, int64_t ld_dq, int dq_col0, void* dS_out,
+                       int64_t ds_ld, int B, int H, int Nq, float q_scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -376,3 +376,34 @@ def pack_segments(segs: torch.Tensor, tile_start: torch.Tensor, total_tiles: int
     rc = _lib.lib().pq3d_pack_segments(segs.data_ptr(), tile_start.data_ptr(), segs.shape[0], total_tiles, _stream())
     _lib.check(rc, "pq3d_pack_segments")
     _count()
+
+
+def attention_bwd(Q, q_col0, dO, do_col0, K, k_col0, V, v_col0, S, S_pitch, stat_m, stat_l, delta, dK, dk_col0, dV,
+                  dv_col0, dQ32, dq_col0, B, H, Nq, *, mask_bits=None, mask_strides=(0, 0, 0), bias=None, dS_out=None):
+    """Fused attention backward (pq3d_attention_bwd).  Q, dO, K, V, dK, dV: 2-D bf16 with unit inner stride; dQ32: 2-D
+    fp32, accumulated (zero-fill first); stats / delta: fp32 (B, H, Nq)."""
+    for t, nm in ((Q, "Q"), (dO, "dO"), (K, "K"), (V, "V"), (dK, "dK"), (dV, "dV")):
+        _chk(t, bf16, nm, 2)
+        if t.stride(1) != 1:
+            raise ValueError(f"{nm} needs unit inner stride")
+    _chk(dQ32, torch.float32, "dQ32", 2)
+    for t, nm in ((stat_m, "stat_m"), (stat_l, "stat_l"), (delta, "delta")):
+        _chk(t, torch.float32, nm)
+        if not t.is_contiguous() or t.numel() != B * H * Nq:
+            raise ValueError(f"{nm} must be contiguous (B, H, Nq)")
+    bias_ld = 0
+    if bias is not None:
+        _chk(bias, torch.float32, "bias", 4)
+        bias_ld = bias.shape[3]
+    ds_ld = 0
+    if dS_out is not None:
+        _chk(dS_out, bf16, "dS_out", 4)
+        ds_ld = dS_out.shape[3]
+    rc = _lib.lib().pq3d_attention_bwd(
+        Q.data_ptr(), Q.stride(0), q_col0, dO.data_ptr(), dO.stride(0), do_col0, K.data_ptr(), K.stride(0), k_col0,
+        V.data_ptr(), V.stride(0), v_col0, S, S_pitch, _p(mask_bits), *mask_strides, _p(bias), bias_ld,
+        stat_m.data_ptr(), stat_l.data_ptr(), delta.data_ptr(), dK.data_ptr(), dK.stride(0), dk_col0, dV.data_ptr(),
+        dV.stride(0), dv_col0, dQ32.data_ptr(), dQ32.stride(0), dq_col0, _p(dS_out), ds_ld, B, H, Nq, float(Q_SCALE),
+        _stream())
+    _lib.check(rc, "pq3d_attention_bwd")
+    _count()

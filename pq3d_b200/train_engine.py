@@ -270,6 +270,18 @@ class _Bwd:
         ops.bgemm(dS, Ktp, dQv, alpha=ops.Q_SCALE)
         return dS
 
+    def fused_ok(self) -> bool:
+        return self.N <= 128 and getattr(self.enc, "fused_attn_bwd", True)
+
+    def attention_bwd_fused(self, Q, q_col0, dO, O2d, K, k_col0, V, v_col0, S, S_pitch, st_m, st_l, dK, dk_col0, dV,
+                            dv_col0, dQ32, dq_col0, bias=None, mask_bits=None, mask_strides=(0, 0, 0), dS_out=None):
+        """One pq3d_attention_bwd launch (+ the row-dot delta): scores are recomputed and consumed on chip."""
+        B, H, N = self.B, self.H, self.N
+        delta = _e((B, H, N), f32, self.dev)
+        ops.attn_delta(dO, O2d, delta, B, H, N)
+        ops.attention_bwd(Q, q_col0, dO, 0, K, k_col0, V, v_col0, S, S_pitch, st_m, st_l, delta, dK, dk_col0, dV, dv_col0,
+                          dQ32, dq_col0, B, H, N, mask_bits=mask_bits, mask_strides=mask_strides, bias=bias, dS_out=dS_out)
+
     # ---- blocks ---------------------------------------------------------------------------------------
     def ffn_bwd(self, i, s, d_out):
         R, D, dev, pk = self.R, self.D, self.dev, self.pk
@@ -326,15 +338,24 @@ class _Bwd:
         Vt = s["Vt"]
         ops.transpose_cast(Vt.as_strided((B, 1, D, N), (Np8, 0, Vt.stride(0), 1)), V.view(B, 1, N, D))
         Vv = _heads(V, B, N, N, H)
-        Ktp = _e((B, H, 64, ld), bf16, dev)
-        ops.transpose_cast(Kv, Ktp)
         dQK = _e((R, 2 * D), bf16, dev)
         dV = _e((R, D), bf16, dev)
         qbits = self.sv["qbits"]
         bias = None if self.sv["sbias"] is None else self.sv["sbias"][i]
-        dS = self.attention_bwd(Qv, Kv, Vv, Ktp, dO, O2d, s["m"][0], s["l"][0], N, ld, _heads(dQK, B, N, N, H, 0),
-                                _heads(dQK, B, N, N, H, D), _heads(dV, B, N, N, H), bias=bias, mask_bits=qbits,
-                                mask_strides=(qbits.stride(0), 0, 0))
+        Ktp = None
+        if self.fused_ok():
+            dQ32 = _z((R, D), f32, dev)
+            dS = _e((B, H, N, ld), bf16, dev) if spatial else None
+            self.attention_bwd_fused(QK, 0, dO, O2d, QK, D, V, 0, N, N, s["m"][0], s["l"][0], dQK, D, dV, 0, dQ32, 0,
+                                     bias=bias, mask_bits=qbits, mask_strides=(qbits.stride(0), 0, 0), dS_out=dS)
+            ops.transpose_cast(dQ32, None, dQK[:, :D])
+            self.keep.append(dQ32)
+        else:
+            Ktp = _e((B, H, 64, ld), bf16, dev)
+            ops.transpose_cast(Kv, Ktp)
+            dS = self.attention_bwd(Qv, Kv, Vv, Ktp, dO, O2d, s["m"][0], s["l"][0], N, ld, _heads(dQK, B, N, N, H, 0),
+                                    _heads(dQK, B, N, N, H, D), _heads(dV, B, N, N, H), bias=bias, mask_bits=qbits,
+                                    mask_strides=(qbits.stride(0), 0, 0))
         with self.on(self.side, dQK, dV, dS, d_y16, dO):
             d_bqk = self.colsum(dQK)
             dQKT, _ = self.tcast(dQK, R, 2 * D)
@@ -375,7 +396,8 @@ class _Bwd:
         dg, db = _z((g, D), f32, dev), _z((g, D), f32, dev)
         ops.layernorm_bwd(s["y"], s["res"], w["gamma"], d_out, w["eps"], R, D, G=g, y_group_stride=R * D, d_x=d_y,
                           dx_group_stride=R * D, d_res=d_res, d_gamma=dg, d_beta=db)
-        dQ = _e((R, g * D), bf16, dev)
+        fused = self.fused_ok()
+        dQ = _z((R, g * D), f32, dev) if fused else _e((R, g * D), bf16, dev)     # fused: fp32, accumulated by atomics
         self.keep += [d_y, dg, db, dQ, d_out]
         casts = [self.tcast(d_y[jj], R, D, want_c=True) for jj in range(g)]
         self.keep += casts
@@ -396,22 +418,30 @@ class _Bwd:
                 dO = self.dgrad(casts[jj][1], pk.T(w["wo"], jj * D, D), D, out_dtype=bf16)
                 mg = mem_grads[m]
                 S, Sp = st.S, st.Sp
-                Qv = _heads(s["Q"], B, N, N, H, jj * D)
-                Kv = _heads(st.K, B, S, Sp, H, i * D)
-                Vv = _heads(mg["V"], B, S, Sp, H, i * D)
-                Kt = mg["Kt"]                                               # [L*D, B*Sp]
-                Ktp = Kt.as_strided((B, H, 64, Sp), (Sp, 64 * Kt.stride(0), Kt.stride(0), 1), i * D * Kt.stride(0))
-                self.attention_bwd(Qv, Kv, Vv, Ktp, dO, s["O"][jj], s["m"][jj], s["l"][jj], S, Sp,
-                                   _heads(dQ, B, N, N, H, jj * D), _heads(mg["dK"], B, S, Sp, H, i * D),
-                                   _heads(mg["dV"], B, S, Sp, H, i * D), mask_bits=st.bits, mask_strides=st.strides)
+                if fused:
+                    self.attention_bwd_fused(s["Q"], jj * D, dO, s["O"][jj], st.K, i * D, mg["V"], i * D, S, Sp, s["m"][jj],
+                                             s["l"][jj], mg["dK"], i * D, mg["dV"], i * D, dQ, jj * D, mask_bits=st.bits,
+                                             mask_strides=st.strides)
+                else:
+                    Qv = _heads(s["Q"], B, N, N, H, jj * D)
+                    Kv = _heads(st.K, B, S, Sp, H, i * D)
+                    Vv = _heads(mg["V"], B, S, Sp, H, i * D)
+                    Kt = mg["Kt"]                                               # [L*D, B*Sp]
+                    Ktp = Kt.as_strided((B, H, 64, Sp), (Sp, 64 * Kt.stride(0), Kt.stride(0), 1), i * D * Kt.stride(0))
+                    self.attention_bwd(Qv, Kv, Vv, Ktp, dO, s["O"][jj], s["m"][jj], s["l"][jj], S, Sp,
+                                       _heads(dQ, B, N, N, H, jj * D), _heads(mg["dK"], B, S, Sp, H, i * D),
+                                       _heads(mg["dV"], B, S, Sp, H, i * D), mask_bits=st.bits, mask_strides=st.strides)
                 self.keep.append(dO)
         self.join([st_ for st_ in used if st_ is not None])
         G = self.G_ca[i]
         step = idx[1] - idx[0] if g > 1 else 0
         regular = all(idx[k + 1] - idx[k] == step for k in range(g - 1)) and (g == 1 or step > 0)
+        dQT, dQ16 = self.tcast(dQ, R, g * D, want_c=fused)
+        if not fused:
+            dQ16 = dQ
+        self.keep += [dQT, dQ16]
         with self.on(self.side):
             d_bq = self.colsum(dQ)
-            dQT, _ = self.tcast(dQ, R, g * D)
             xqT, _ = self.tcast(s["xq"], R, D)
             if regular:
                 self.wgrad(dQT, xqT, D, D, out=G[idx[0], :D], groups=g, c_group_stride=step * 3 * D * D)
@@ -421,7 +451,7 @@ class _Bwd:
         mg_q = mem_grads["_q"]
         for jj, j in enumerate(idx):
             mg_q[(i, j)] = d_bq[jj * D:(jj + 1) * D]
-        d_xq = self.dgrad(dQ, pk.T(w["wq"]), D)
+        d_xq = self.dgrad(dQ16, pk.T(w["wq"]), D)
         d_in = _e((R, D), f32, dev)
         ops.add3(d_res, d_xq, None, d_in)
         ops.add3(d_pos, d_xq, None, d_pos)
@@ -436,8 +466,10 @@ class _Bwd:
         for name, st in sv["mems"].items():
             V = _e((B * st.Sp, L * D), bf16, dev)
             ops.transpose_cast(st.Vt, V)                               # V^T [L*D, B*Sp] -> V [B*Sp, L*D]
-            Kt = _e((L * D, B * st.Sp), bf16, dev)
-            ops.transpose_cast(st.K, Kt)
+            Kt = None
+            if not self.fused_ok():
+                Kt = _e((L * D, B * st.Sp), bf16, dev)
+                ops.transpose_cast(st.K, Kt)
             mem_grads[name] = dict(V=V, Kt=Kt, dK=_z((B * st.Sp, L * D), bf16, dev), dV=_z((B * st.Sp, L * D), bf16, dev))
         d_q = d_out.detach().reshape(R, D).float().contiguous()
         d_pos = _z((R, D), f32, dev)

@@ -520,6 +520,77 @@ def check_attention_bwd():
     assert max(e_p, e_v, e_k, e_q) <= 4 * TOL_BF16       # P, dS and the outputs are each rounded to bf16
 
 
+def _attn_bwd_fused_case(B, H, N, S, mask_kind, zero_attn, with_bias, seed):
+    g = gen(seed)
+    D, Sp = H * 64, ops.pad8(S)
+    ln2 = math.log(2.0)
+    Q2 = rnd((B * N, D), g).bfloat16()
+    Kb = rnd((B * Sp, D), g).bfloat16()
+    Vb = rnd((B * Sp, D), g).bfloat16()
+    dO = rnd((B * N, D), g).bfloat16()
+    if mask_kind == "kpm":
+        mask = (torch.rand(B, S, generator=g) < 0.2).to(DEV)
+        bits = ops.pack_mask(mask)
+        strides = (bits.stride(0), 0, 0)
+        full = mask[:, None, None, :].expand(B, H, N, S)
+    else:                                   # per-query mask shared by the heads: (B, N, S)
+        mask = (torch.rand(B, N, S, generator=g) < 0.3).to(DEV)
+        mask[:, 0] = True                   # a fully masked row
+        bits = ops.pack_mask(mask)
+        strides = (bits.stride(0), 0, bits.stride(1))
+        full = mask[:, None].expand(B, H, N, S)
+    bias = None
+    if with_bias:
+        bias = torch.zeros(B, H, N, ops.bias_ld(S), device=DEV)
+        bias[..., :S] = rnd((B, H, N, S), g)
+    Vt = torch.zeros(D, B * Sp, dtype=torch.bfloat16, device=DEV)
+    Vt.copy_(Vb.t())
+    O = torch.empty(1, B * N, D, dtype=torch.bfloat16, device=DEV)
+    st_m, st_l = torch.empty(B, H, N, device=DEV), torch.empty(B, H, N, device=DEV)
+    ops.attention(Q2, 0, [ops.AttnMemory(Kb, 0, Vt, 0, S, Sp, bits, *strides)], O, B * N * D, B, H, N, zero_attn, bias,
+                  stats=(st_m, st_l))
+    # reference (fp64 autograd)
+    q = Q2.double().view(B, N, H, 64).permute(0, 2, 1, 3).requires_grad_(True)
+    k = Kb.double().view(B, Sp, H, 64)[:, :S].permute(0, 2, 1, 3).requires_grad_(True)
+    v = Vb.double().view(B, Sp, H, 64)[:, :S].permute(0, 2, 1, 3).requires_grad_(True)
+    s = q @ k.transpose(-1, -2)
+    if with_bias:
+        s = s + bias[..., :S].double()
+    s = (s * ln2).masked_fill(full, float("-inf"))
+    if zero_attn:
+        s = torch.cat([s, torch.zeros_like(s[..., :1])], -1)
+    pr = torch.softmax(s, -1)
+    pr = torch.nan_to_num(pr, nan=0.0)[..., :S]
+    o_ref = pr @ v
+    o_ref.backward(dO.double().view(B, N, H, 64).permute(0, 2, 1, 3))
+    # ours
+    delta = torch.empty(B, H, N, device=DEV)
+    ops.attn_delta(dO, O[0], delta, B, H, N)
+    dK = torch.zeros(B * Sp, D, dtype=torch.bfloat16, device=DEV)
+    dV = torch.zeros(B * Sp, D, dtype=torch.bfloat16, device=DEV)
+    dQ = torch.zeros(B * N, D, device=DEV)
+    dS = torch.full((B, H, N, ops.pad64(S)), float("nan"), dtype=torch.bfloat16, device=DEV) if with_bias else None
+    ops.attention_bwd(Q2, 0, dO, 0, Kb, 0, Vb, 0, S, Sp, st_m, st_l, delta, dK, 0, dV, 0, dQ, 0, B, H, N, mask_bits=bits,
+                      mask_strides=strides, bias=bias, dS_out=dS)
+    torch.cuda.synchronize()
+    e_v = rel(dV.view(B, Sp, H, 64)[:, :S].permute(0, 2, 1, 3), v.grad)
+    e_k = rel(dK.view(B, Sp, H, 64)[:, :S].permute(0, 2, 1, 3), k.grad)
+    e_q = rel(dQ.view(B, N, H, 64).permute(0, 2, 1, 3) / ops.Q_SCALE, q.grad)
+    print(f"fused attention backward B={B} H={H} N={N} S={S} {mask_kind} zero_attn={zero_attn} bias={with_bias}: "
+          f"dV {e_v:.2e}  dK {e_k:.2e}  dQ {e_q:.2e}")
+    assert max(e_v, e_k, e_q) <= 4 * TOL_BF16
+    if dS is not None:
+        assert torch.isfinite(dS[..., :S].float()).all()
+
+
+def check_attention_bwd_fused():
+    """pq3d_attention_bwd (one kernel, MN-major operand re-use) against fp64 autograd of the softmax attention."""
+    _attn_bwd_fused_case(2, 3, 100, 300, "kpm", True, False, 70)        # cross-attention, key padding, 3 key tiles
+    _attn_bwd_fused_case(1, 2, 128, 1100, "kpm", True, False, 71)       # 9 tiles -> split over chunks, dQ atomics
+    _attn_bwd_fused_case(2, 2, 48, 200, "attn", True, False, 72)        # per-query masks, a fully masked row
+    _attn_bwd_fused_case(2, 3, 100, 100, "kpm", False, True, 73)        # self-attention shape: score bias, no zero-attn
+
+
 CHECKS = {k[6:]: v for k, v in list(globals().items()) if k.startswith("check_")}
 
 if __name__ == "__main__":
