@@ -167,11 +167,12 @@ int pq3d_transpose_cast(const void* in, int in_fp32, int64_t ld_in, int64_t in_b
 int pq3d_colsum(const void* in, int in_fp32, int64_t ld, const void* gate, int64_t ld_gate, float* out, int R, int C,
                 int accumulate, void* stream);
 
-/* Backward of pq3d_add_layernorm: d_x[g] (grad of residual + y[g]), d_res = sum_g d_x[g], d_gamma / d_beta accumulated
- * with atomics into zero-initialised fp32 [G,D].  Any output may be NULL. */
+/* Backward of pq3d_add_layernorm: d_x[g] (grad of residual + y[g]; fp32 and / or its bf16 copy d_x_bf16, the operand
+ * of the dgrad GEMM that follows, same group stride), d_res = sum_g d_x[g], d_gamma / d_beta accumulated with atomics
+ * into zero-initialised fp32 [G,D].  Any output may be NULL. */
 int pq3d_layernorm_bwd(const float* y, int64_t y_group_stride, const float* residual, const float* gamma,
                        const float* d_out, int G, float eps, int R, int D, float* d_x, int64_t dx_group_stride,
-                       float* d_res, float* d_gamma, float* d_beta, void* stream);
+                       void* d_x_bf16, float* d_res, float* d_gamma, float* d_beta, void* stream);
 
 /* delta[b,h,n] = sum_d dO[b*N+n, h*64+d] * O[b*N+n, h*64+d] (bf16 in, fp32 out). */
 int pq3d_attn_delta(const void* dO, const void* O, int64_t ld, float* delta, int B, int H, int N, void* stream);

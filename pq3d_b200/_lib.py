@@ -30,7 +30,7 @@ SIGNATURES: Dict[str, list] = {
     "pq3d_transpose_cast": [_vp, _i32, _i64, _i64, _i64, _vp, _i64, _i64, _i64, _vp, _i64, _i64, _i64, _vp, _i64, _i64,
                             _i64, _i32, _i32, _i32, _i32, _i32, _f32, _vp],
     "pq3d_colsum": [_vp, _i32, _i64, _vp, _i64, _vp, _i32, _i32, _i32, _vp],
-    "pq3d_layernorm_bwd": [_vp, _i64, _vp, _vp, _vp, _i32, _f32, _i32, _i32, _vp, _i64, _vp, _vp, _vp, _vp],
+    "pq3d_layernorm_bwd": [_vp, _i64, _vp, _vp, _vp, _i32, _f32, _i32, _i32, _vp, _i64, _vp, _vp, _vp, _vp, _vp],
     "pq3d_attn_delta": [_vp, _vp, _i64, _vp, _i32, _i32, _i32, _vp],
     "pq3d_softmax_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _i32, _i32,
                          _i32, _i32, _i32, _i32, _vp],

@@ -180,26 +180,28 @@ __global__ void colsum_kernel(const void* __restrict__ in, int in_fp32, int64_t 
 // One warp per row, statistics recomputed (nothing but x is saved).  Affine gradients: per-block partial sums in
 // shared memory, then one atomicAdd per column per block (caller zero-initialises d_gamma / d_beta).
 // ------------------------------------------------------------------------------------------------
-constexpr int kLnbWarps = 8;
+constexpr int kLnbWarps = 4;
 
 template <int NV>
-__global__ void layernorm_bwd_kernel(const float* __restrict__ y, int64_t y_group_stride,
-                                     const float* __restrict__ residual, const float* __restrict__ gamma,
-                                     const float* __restrict__ d_out, int G, float eps, int R,
-                                     float* __restrict__ d_x, int64_t dx_group_stride, float* __restrict__ d_res,
-                                     float* __restrict__ d_gamma, float* __restrict__ d_beta) {
+__global__ void __launch_bounds__(kLnbWarps * 32)
+layernorm_bwd_kernel(const float* __restrict__ y, int64_t y_group_stride, const float* __restrict__ residual,
+                     const float* __restrict__ gamma, const float* __restrict__ d_out, int G, float eps, int R,
+                     float* __restrict__ d_x, int64_t dx_group_stride, __nv_bfloat16* __restrict__ d_x16,
+                     float* __restrict__ d_res, float* __restrict__ d_gamma, float* __restrict__ d_beta) {
   pdl_sync();
   constexpr int D = NV * 128;
-  __shared__ float s_dg[D], s_db[D];
+  // per-warp partial affine gradients meet here once per group: no atomics inside the row loop
+  __shared__ float s_dg[kLnbWarps][D], s_db[kLnbWarps][D];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const float inv_g = 1.f / static_cast<float>(G);
   constexpr float inv_d = 1.f / static_cast<float>(D);
   for (int g = 0; g < G; ++g) {
-    for (int i = threadIdx.x; i < D; i += blockDim.x) {
-      s_dg[i] = 0.f;
-      s_db[i] = 0.f;
-    }
-    __syncthreads();
+    float4 pg[NV], pb[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) pg[i] = pb[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 ga[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) ga[i] = __ldg(reinterpret_cast<const float4*>(gamma + g * D) + i * 32 + lane);
     for (int row = blockIdx.x * kLnbWarps + wid; row < R; row += gridDim.x * kLnbWarps) {
       const int64_t base = static_cast<int64_t>(row) * D;
       float4 x[NV], go[NV];
@@ -233,16 +235,12 @@ __global__ void layernorm_bwd_kernel(const float* __restrict__ y, int64_t y_grou
       float4 dxh[NV];
 #pragma unroll
       for (int i = 0; i < NV; ++i) {
-        const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma + g * D) + i * 32 + lane);
         x[i].x *= rstd; x[i].y *= rstd; x[i].z *= rstd; x[i].w *= rstd;   // xhat
-        dxh[i] = make_float4(go[i].x * ga.x, go[i].y * ga.y, go[i].z * ga.z, go[i].w * ga.w);
+        dxh[i] = make_float4(go[i].x * ga[i].x, go[i].y * ga[i].y, go[i].z * ga[i].z, go[i].w * ga[i].w);
         m1 += (dxh[i].x + dxh[i].y) + (dxh[i].z + dxh[i].w);
         m2 += (dxh[i].x * x[i].x + dxh[i].y * x[i].y) + (dxh[i].z * x[i].z + dxh[i].w * x[i].w);
-        const int col = (i * 32 + lane) * 4;
-        atomicAdd(&s_dg[col], go[i].x * x[i].x); atomicAdd(&s_dg[col + 1], go[i].y * x[i].y);
-        atomicAdd(&s_dg[col + 2], go[i].z * x[i].z); atomicAdd(&s_dg[col + 3], go[i].w * x[i].w);
-        atomicAdd(&s_db[col], go[i].x); atomicAdd(&s_db[col + 1], go[i].y);
-        atomicAdd(&s_db[col + 2], go[i].z); atomicAdd(&s_db[col + 3], go[i].w);
+        pg[i].x += go[i].x * x[i].x; pg[i].y += go[i].y * x[i].y; pg[i].z += go[i].z * x[i].z; pg[i].w += go[i].w * x[i].w;
+        pb[i].x += go[i].x; pb[i].y += go[i].y; pb[i].z += go[i].z; pb[i].w += go[i].w;
       }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
@@ -260,6 +258,11 @@ __global__ void layernorm_bwd_kernel(const float* __restrict__ y, int64_t y_grou
         dx.w = rstd * (dxh[i].w - m1 - x[i].w * m2);
         const int64_t off = base + (i * 32 + lane) * 4;
         if (d_x != nullptr) *reinterpret_cast<float4*>(d_x + g * dx_group_stride + off) = dx;
+        if (d_x16 != nullptr) {
+          uint2 o;
+          o.x = pack_bf16x2(dx.x, dx.y); o.y = pack_bf16x2(dx.z, dx.w);
+          *reinterpret_cast<uint2*>(d_x16 + g * dx_group_stride + off) = o;
+        }
         if (d_res != nullptr) {
           float4* dr = reinterpret_cast<float4*>(d_res + off);
           if (g == 0) {
@@ -272,12 +275,22 @@ __global__ void layernorm_bwd_kernel(const float* __restrict__ y, int64_t y_grou
         }
       }
     }
-    __syncthreads();
-    for (int i = threadIdx.x; i < D; i += blockDim.x) {
-      if (d_gamma != nullptr) atomicAdd(&d_gamma[g * D + i], s_dg[i]);
-      if (d_beta != nullptr) atomicAdd(&d_beta[g * D + i], s_db[i]);
+    if (d_gamma != nullptr || d_beta != nullptr) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        *reinterpret_cast<float4*>(&s_dg[wid][(i * 32 + lane) * 4]) = pg[i];
+        *reinterpret_cast<float4*>(&s_db[wid][(i * 32 + lane) * 4]) = pb[i];
+      }
+      __syncthreads();
+      for (int i = threadIdx.x; i < D; i += blockDim.x) {
+        float tg = 0.f, tb = 0.f;
+#pragma unroll
+        for (int w = 0; w < kLnbWarps; ++w) { tg += s_dg[w][i]; tb += s_db[w][i]; }
+        if (d_gamma != nullptr) atomicAdd(&d_gamma[g * D + i], tg);
+        if (d_beta != nullptr) atomicAdd(&d_beta[g * D + i], tb);
+      }
+      __syncthreads();
     }
-    __syncthreads();
   }
 }
 
@@ -505,16 +518,19 @@ extern "C" int pq3d_colsum(const void* in, int in_fp32, int64_t ld, const void* 
 
 extern "C" int pq3d_layernorm_bwd(const float* y, int64_t y_group_stride, const float* residual, const float* gamma,
                                   const float* d_out, int G, float eps, int R, int D, float* d_x,
-                                  int64_t dx_group_stride, float* d_res, float* d_gamma, float* d_beta, void* stream) {
+                                  int64_t dx_group_stride, void* d_x_bf16, float* d_res, float* d_gamma, float* d_beta,
+                                  void* stream) {
   PQ3D_CHECK_ARG((y || residual) && gamma && d_out && G >= 1 && R > 0 && D % 128 == 0 && D <= 1024,
-                 "pq3d_layernorm_bwd: bad argument");
-  const int blocks = (R + kLnbWarps - 1) / kLnbWarps < sm_count() ? (R + kLnbWarps - 1) / kLnbWarps : sm_count();
+                 "pq3d_layernorm_bwd: bad argument (D must be a multiple of 128, at most 1024)");
+  int blocks = (R + kLnbWarps - 1) / kLnbWarps;
+  if (blocks > 2 * sm_count()) blocks = 2 * sm_count();
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   cudaError_t err = cudaSuccess;
 #define PQ3D_LNB_CASE(NV)                                                                                            \
   case NV:                                                                                                           \
     err = launch_kernel(layernorm_bwd_kernel<NV>, dim3(blocks), dim3(kLnbWarps * 32), 0, st, y, y_group_stride,      \
-                        residual, gamma, d_out, G, eps, R, d_x, dx_group_stride, d_res, d_gamma, d_beta);            \
+                        residual, gamma, d_out, G, eps, R, d_x, dx_group_stride,                                     \
+                        reinterpret_cast<__nv_bfloat16*>(d_x_bf16), d_res, d_gamma, d_beta);                         \
     break;
   switch (D / 128) {
     PQ3D_LNB_CASE(1) PQ3D_LNB_CASE(2) PQ3D_LNB_CASE(3) PQ3D_LNB_CASE(4) PQ3D_LNB_CASE(5) PQ3D_LNB_CASE(6)

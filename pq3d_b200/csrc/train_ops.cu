@@ -13,7 +13,7 @@ namespace pq3d {
 // One segment: src fp32 [rows, cols] (dense, ld = cols) ->
 //   dst_c [rows, cols] with pitch ld_c (bf16, or fp32 when flags & 1), optional
 //   dst_t [cols, rows] with pitch ld_t (bf16), optional.
-// Eight int64 words per segment: src, dst_c, dst_t, rows, cols, ld_c, ld_t, flags.
+// Eight int64 words per segment: src, dst_c, dst_t, rows, cols, ld_c, ld_t, flags (1: dst_c is fp32; 2: vector path).
 constexpr int kSegWords = 8;
 
 __global__ void __launch_bounds__(256) pack_segments_kernel(const int64_t* __restrict__ segs,
@@ -36,6 +36,42 @@ __global__ void __launch_bounds__(256) pack_segments_kernel(const int64_t* __res
   const int tiles_c = (cols + 63) / 64;
   const int local = static_cast<int>(blockIdx.x) - tile_start[lo];
   const int r0 = (local / tiles_c) * 64, c0 = (local % tiles_c) * 64;
+  if (sg[7] & 2) {
+    // vector path (host guarantees rows, cols, pitches multiples of 4 and 16-byte aligned bases): float4 loads,
+    // 8-byte bf16x4 stores in both orientations
+    const int q = threadIdx.x & 15, rr = threadIdx.x >> 4;
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int i = rr + it * 16, r = r0 + i, c = c0 + q * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r < rows && c < cols) {
+        v = __ldg(reinterpret_cast<const float4*>(src + static_cast<int64_t>(r) * cols + c));
+        if (dst_c != nullptr) {
+          if (c_fp32) {
+            *reinterpret_cast<float4*>(reinterpret_cast<float*>(dst_c) + r * ld_c + c) = v;
+          } else {
+            uint2 o;
+            o.x = pack_bf16x2(v.x, v.y); o.y = pack_bf16x2(v.z, v.w);
+            *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(dst_c) + r * ld_c + c) = o;
+          }
+        }
+      }
+      tile[i][q * 4] = v.x; tile[i][q * 4 + 1] = v.y; tile[i][q * 4 + 2] = v.z; tile[i][q * 4 + 3] = v.w;
+    }
+    if (dst_t == nullptr) return;
+    __syncthreads();
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int i = rr + it * 16, c = c0 + i, r = r0 + q * 4;
+      if (c < cols && r < rows) {
+        uint2 o;
+        o.x = pack_bf16x2(tile[q * 4][i], tile[q * 4 + 1][i]);
+        o.y = pack_bf16x2(tile[q * 4 + 2][i], tile[q * 4 + 3][i]);
+        *reinterpret_cast<uint2*>(dst_t + c * ld_t + r) = o;
+      }
+    }
+    return;
+  }
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   for (int i = ty; i < 64; i += 8) {
     const int r = r0 + i;

@@ -330,10 +330,12 @@ def colsum(x: torch.Tensor, out: torch.Tensor, accumulate: bool = False, gate: O
 
 
 def layernorm_bwd(y, residual, gamma, d_out, eps, R, D, G=1, y_group_stride=0, d_x=None, dx_group_stride=0, d_res=None,
-                  d_gamma=None, d_beta=None):
+                  d_gamma=None, d_beta=None, d_x16=None):
+    if d_x16 is not None:
+        _chk(d_x16, bf16, "d_x16")
     rc = _lib.lib().pq3d_layernorm_bwd(_p(y), y_group_stride, _p(residual), gamma.data_ptr(), d_out.data_ptr(), G,
-                                       float(eps), R, D, _p(d_x), dx_group_stride, _p(d_res), _p(d_gamma), _p(d_beta),
-                                       _stream())
+                                       float(eps), R, D, _p(d_x), dx_group_stride, _p(d_x16), _p(d_res), _p(d_gamma),
+                                       _p(d_beta), _stream())
     _lib.check(rc, "pq3d_layernorm_bwd")
     _count()
 

@@ -304,7 +304,9 @@ class _Packed:
             ld_c = dst_c.stride(0) if dst_c.ndim == 2 and dst_c.shape[0] > 1 else Cc
             pc = dst_c.data_ptr() + r0 * ld_c * es
             pt, ld_t = (0, 0) if dst_t is None else (dst_t.data_ptr() + r0 * 2, dst_t.stride(0))
-            rows.append([src.data_ptr(), pc, pt, R, Cc, ld_c, ld_t, 1 if is_f32 else 0])
+            vec = (R % 4 == 0 and Cc % 4 == 0 and ld_c % 4 == 0 and ld_t % 4 == 0 and src.data_ptr() % 16 == 0
+                   and pc % 16 == 0 and pt % 8 == 0)
+            rows.append([src.data_ptr(), pc, pt, R, Cc, ld_c, ld_t, (1 if is_f32 else 0) | (2 if vec else 0)])
             starts.append(total)
             total += ((R + 63) // 64) * ((Cc + 63) // 64)
         self._table = (torch.tensor(rows, dtype=torch.int64).to(self.device),

@@ -290,11 +290,12 @@ class _Bwd:
         pre = f"unified_encoder.{i}.ffn."
         d_y = _e((R, D), f32, dev)
         dg, db = _z((1, D), f32, dev), _z((1, D), f32, dev)
-        ops.layernorm_bwd(s["y"], s["res"], ff["gamma"], d_out, ff["eps"], R, D, d_x=d_y, d_gamma=dg, d_beta=db)
+        d_y16 = _e((R, D), bf16, dev)
+        ops.layernorm_bwd(s["y"], s["res"], ff["gamma"], d_out, ff["eps"], R, D, d_x=d_y, d_gamma=dg, d_beta=db, d_x16=d_y16)
         self.acc(pre + "norm.weight", dg[0]); self.acc(pre + "norm.bias", db[0])
-        d_yT, d_y16 = self.tcast(d_y, R, D, want_c=True)
-        with self.on(self.side, d_y, d_yT, dg, db):
+        with self.on(self.side, d_y, dg, db):
             self.acc(pre + "linear2.bias", self.colsum(d_y))
+            d_yT, _ = self.tcast(d_y, R, D)
             hT, _ = self.tcast(s["h"], R, F)
             self.acc(pre + "linear2.weight", self.wgrad(d_yT, hT, D, F))
         d_h = self.dgrad(d_y16, pk.T(ff["w2"]), F)
@@ -317,14 +318,15 @@ class _Bwd:
         a = pre + "self_attn."
         d_y = _e((R, D), f32, dev)
         dg, db = _z((1, D), f32, dev), _z((1, D), f32, dev)
-        ops.layernorm_bwd(s["y"], s["res"], sa["gamma"], d_out, sa["eps"], R, D, d_x=d_y, d_gamma=dg, d_beta=db)
+        d_y16 = _e((R, D), bf16, dev)
+        ops.layernorm_bwd(s["y"], s["res"], sa["gamma"], d_out, sa["eps"], R, D, d_x=d_y, d_gamma=dg, d_beta=db, d_x16=d_y16)
         self.acc(pre + "norm.weight", dg[0]); self.acc(pre + "norm.bias", db[0])
-        d_yT, d_y16 = self.tcast(d_y, R, D, want_c=True)
         O2d = s["O"].view(R, D)
         if not spatial:
             g_in, g_inb = _e((3 * D, D), f32, dev), _e((3 * D,), f32, dev)
-        with self.on(self.side, d_y, d_yT, dg, db):
+        with self.on(self.side, d_y, dg, db):
             d_bo = self.colsum(d_y)
+            d_yT, _ = self.tcast(d_y, R, D)
             OT, _ = self.tcast(O2d, R, D)
             d_wo = self.wgrad(d_yT, OT, D, D)
             self.acc(a + ("fc.weight" if spatial else "out_proj.weight"), d_wo)
@@ -381,7 +383,8 @@ class _Bwd:
         d_xv = self.dgrad(dV, pk.T(sa["wv"]), D)
         d_in = _e((R, D), f32, dev)
         ops.add3(d_y, d_xq, d_xv, d_in)
-        ops.add3(d_pos, d_xq, None, d_pos)
+        with self.on(self.side, d_xq):
+            ops.add3(d_pos, d_xq, None, d_pos)
         self.keep += [d_xq, d_xv, V, Ktp]
         return d_in
 
@@ -394,20 +397,21 @@ class _Bwd:
         d_y = _e((g, R, D), f32, dev)
         d_res = _e((R, D), f32, dev)
         dg, db = _z((g, D), f32, dev), _z((g, D), f32, dev)
+        d_y16 = _e((g, R, D), bf16, dev)
         ops.layernorm_bwd(s["y"], s["res"], w["gamma"], d_out, w["eps"], R, D, G=g, y_group_stride=R * D, d_x=d_y,
-                          dx_group_stride=R * D, d_res=d_res, d_gamma=dg, d_beta=db)
+                          dx_group_stride=R * D, d_res=d_res, d_gamma=dg, d_beta=db, d_x16=d_y16)
         fused = self.fused_ok()
         dQ = _z((R, g * D), f32, dev) if fused else _e((R, g * D), bf16, dev)     # fused: fp32, accumulated by atomics
         self.keep += [d_y, dg, db, dQ, d_out]
-        casts = [self.tcast(d_y[jj], R, D, want_c=True) for jj in range(g)]
-        self.keep += casts
+        self.keep.append(d_y16)
         with self.on(self.side):
             for jj, j in enumerate(idx):
                 pre = f"unified_encoder.{i}.cross_attn_list.{j}."
                 self.acc(pre + "norm.weight", dg[jj]); self.acc(pre + "norm.bias", db[jj])
                 self.acc(pre + "multihead_attn.out_proj.bias", self.colsum(d_y[jj]))
+                d_yT, _ = self.tcast(d_y[jj], R, D)
                 OT, _ = self.tcast(s["O"][jj], R, D)
-                self.acc(pre + "multihead_attn.out_proj.weight", self.wgrad(casts[jj][0], OT, D, D))
+                self.acc(pre + "multihead_attn.out_proj.weight", self.wgrad(d_yT, OT, D, D))
         used = []
         for jj, m in enumerate(grp):
             # each memory's chain (dgrad -> attention backward) is independent of the others': own stream
@@ -415,7 +419,7 @@ class _Bwd:
             st = self.sv["mems"][m]
             with self.on(stream):
                 used.append(stream)
-                dO = self.dgrad(casts[jj][1], pk.T(w["wo"], jj * D, D), D, out_dtype=bf16)
+                dO = self.dgrad(d_y16[jj], pk.T(w["wo"], jj * D, D), D, out_dtype=bf16)
                 mg = mem_grads[m]
                 S, Sp = st.S, st.Sp
                 if fused:
@@ -454,7 +458,8 @@ class _Bwd:
         d_xq = self.dgrad(dQ16, pk.T(w["wq"]), D)
         d_in = _e((R, D), f32, dev)
         ops.add3(d_res, d_xq, None, d_in)
-        ops.add3(d_pos, d_xq, None, d_pos)
+        with self.on(self.side, d_xq):
+            ops.add3(d_pos, d_xq, None, d_pos)
         self.keep += [d_xq, d_res]
         return d_in
 
