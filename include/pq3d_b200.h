@@ -95,6 +95,20 @@ int pq3d_attention_fwd(int n_mem, const void* Q, int64_t ldq, int64_t q_mem_stri
                        const float* score_bias, int64_t bias_ld, float* stat_m, float* stat_l,
                        int64_t stat_mem_stride, void* stream);
 
+/* Training-mode forward: pq3d_attention_fwd plus dropout on the attention probabilities (nn.MultiheadAttention(dropout=p):
+ * applied after the softmax normalisation).  Probability (b, h, n, key) of memory i is kept iff the counter RNG says so
+ * for element ((b*H + h)*Nq + n)*ceil128(S[i]) + key of stream sites[i] (host array) in the step seeded by *seed_dev. */
+int pq3d_attention_fwd_train(int n_mem, const void* Q, int64_t ldq, int64_t q_mem_stride,
+                       const void* const* K, const int64_t* ldk, const int64_t* k_col0,
+                       const void* const* Vt, const int64_t* ldvt, const int64_t* vt_row0, const int64_t* vt_rows,
+                       const int32_t* S, const int32_t* S_pitch, const int32_t* Vt_pitch,
+                       const uint32_t* const* mask_bits, const int64_t* mask_b_stride,
+                       const int64_t* mask_h_stride, const int64_t* mask_q_stride, const int32_t* const* kv_tiles,
+                       void* O, int64_t ldo, int64_t o_mem_stride, int B, int H, int Nq, int zero_attn,
+                       const float* score_bias, int64_t bias_ld, float* stat_m, float* stat_l,
+                       int64_t stat_mem_stride, float drop_p,
+                       const uint32_t* seed_dev, const uint32_t* sites, void* stream);
+
 /* Score bias of MultiHeadAttentionSpatial 'mul' for L layers at once:
  * out[l,b,h,n,m] = log2(max(relu(pairwise_locs[b,n,m,:] · loc_w[l,h,:] + loc_b[l,h]), 1e-6)), rows padded to ld
  * (pad columns are left untouched).  Replaces modules/layers/transformers.py:196-199,231-232. */
@@ -163,16 +177,33 @@ int pq3d_transpose_cast(const void* in, int in_fp32, int64_t ld_in, int64_t in_b
                         void* out_c, int64_t ld_c, int64_t c_b1, int64_t c_b2,
                         int R, int C, int Rp, int B1, int B2, float scale, void* stream);
 
-/* out[c] (+)= sum_r in[r][c] * (gate[r][c] > 0 ? 1 : 0) — bias gradients; in fp32 or bf16, gate optional (bf16). */
+/* out[c] (+)= scale * sum_r in[r][c] * (gate[r][c] > 0 ? 1 : 0) — bias gradients; in fp32 or bf16, gate optional (bf16). */
 int pq3d_colsum(const void* in, int in_fp32, int64_t ld, const void* gate, int64_t ld_gate, float* out, int R, int C,
-                int accumulate, void* stream);
+                int accumulate, float scale, void* stream);
 
-/* Backward of pq3d_add_layernorm: d_x[g] (grad of residual + y[g]; fp32 and / or its bf16 copy d_x_bf16, the operand
- * of the dgrad GEMM that follows, same group stride), d_res = sum_g d_x[g], d_gamma / d_beta accumulated with atomics
- * into zero-initialised fp32 [G,D].  Any output may be NULL. */
+/* Backward of pq3d_add_layernorm / pq3d_add_layernorm_train: d_x[g] = gradient of the branch input y[g] (fp32 and / or
+ * its bf16 copy d_x_bf16, the operand of the dgrad GEMM that follows, same group stride; with dropout it carries the
+ * forward's keep mask and 1/(1-p)), d_res = sum_g (gradient of residual + dropout(y[g])), d_gamma / d_beta accumulated
+ * with atomics into zero-initialised fp32 [G,D].  drop_p / seed_dev / site / row_w / rows_per_scene: exactly the
+ * forward call's (0 / NULL without dropout or memory dropout).  Any output may be NULL. */
 int pq3d_layernorm_bwd(const float* y, int64_t y_group_stride, const float* residual, const float* gamma,
                        const float* d_out, int G, float eps, int R, int D, float* d_x, int64_t dx_group_stride,
-                       void* d_x_bf16, float* d_res, float* d_gamma, float* d_beta, void* stream);
+                       void* d_x_bf16, float* d_res, float* d_gamma, float* d_beta, float drop_p,
+                       const uint32_t* seed_dev, uint32_t site, const float* row_w, int rows_per_scene, void* stream);
+
+/* Training-mode tail of a residual block: out = sum_g w[b,g] * LN_g(residual + dropout_p(y[g])), w = 1/G or the
+ * memory-dropout weights row_w [R/rows_per_scene, G] (keep / #kept per scene; query_encoder.py:145-153).  Dropout keeps
+ * element e = (g*R + row)*D + col iff hash32(e ^ hash32(*seed_dev + site*0x9E3779B9)) >= p*2^32 (csrc/ptx.cuh,
+ * restated in pq3d_b200/rng.py); the backward regenerates the mask from the same (seed, site).  Outputs as in
+ * pq3d_add_layernorm.  Replaces `tgt = norm(tgt + dropout(tgt2))` (query_encoder.py:304-305, 386-387, 449-450). */
+int pq3d_add_layernorm_train(const float* y, int64_t y_group_stride, const float* residual, const float* gamma,
+                             const float* beta, int G, float eps, int R, int D, const float* pos, float* out_f32,
+                             void* out_bf16, void* out_pos_bf16, float drop_p, const uint32_t* seed_dev, uint32_t site,
+                             const float* row_w, int rows_per_scene, void* stream);
+
+/* In-place dropout of a bf16 array (FFN hidden activations, query_encoder.py:384): element e kept iff the counter RNG
+ * says so (see pq3d_add_layernorm_train), kept values scaled by 1/(1-p).  n multiple of 8. */
+int pq3d_dropout_bf16(void* x, int64_t n, float drop_p, const uint32_t* seed_dev, uint32_t site, void* stream);
 
 /* delta[b,h,n] = sum_d dO[b*N+n, h*64+d] * O[b*N+n, h*64+d] (bf16 in, fp32 out). */
 int pq3d_attn_delta(const void* dO, const void* O, int64_t ld, float* delta, int B, int H, int N, void* stream);
@@ -212,6 +243,7 @@ int pq3d_pack_segments(const int64_t* segs_dev, const int32_t* tile_start_dev, i
  *   dK, dV: bf16, same row layout as K / V (ld_dk, dk_col0, ...): rows < S of every head block are overwritten
  *   dQ: fp32 [B*Nq, ld_dq], ACCUMULATED with atomics at columns dq_col0 + h*64 (zero-fill before the call)
  *   dS_out: optional bf16 [B, H, Nq, ds_ld] (for the spatial-bias backward)
+ *   drop_p / seed_dev / site: the forward's attention-probability dropout (pq3d_attention_fwd_train), regenerated here
  * Requires Nq <= 128.  Replaces autograd through torch/nn/functional.py:6630-6647 and
  * modules/layers/transformers.py:224-236 in the reference's training step. */
 int pq3d_attention_bwd(const void* Q, int64_t ldq, int q_col0, const void* dO, int64_t lddo, int do_col0,
@@ -220,7 +252,8 @@ int pq3d_attention_bwd(const void* Q, int64_t ldq, int q_col0, const void* dO, i
                        int64_t mask_q_stride, const float* bias, int64_t bias_ld, const float* stat_m,
                        const float* stat_l, const float* delta, void* dK, int64_t ld_dk, int dk_col0, void* dV,
                        int64_t ld_dv, int dv_col0, float* dQ, int64_t ld_dq, int dq_col0, void* dS_out,
-                       int64_t ds_ld, int B, int H, int Nq, float q_scale, void* stream);
+                       int64_t ds_ld, int B, int H, int Nq, float q_scale, float drop_p, const uint32_t* seed_dev,
+                       uint32_t site, void* stream);
 
 #ifdef __cplusplus
 }

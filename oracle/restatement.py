@@ -45,6 +45,13 @@ class DecoderCfg:
     drop_memories_test: Sequence[str] = field(default_factory=list)
     use_self_mask: bool = False
     num_blocks: int = 1
+    # Training mode (module.train()): an object supplying the random decisions the reference draws from torch's RNG, so
+    # a checker can replay the exact masks another implementation used.  None = eval mode.  Methods:
+    #   sublayer(layer, kind, x)  -> dropout(x): kind = ('ca', memory name) | 'sa' | 'ffn'   (nn.Dropout on tgt2)
+    #   probs(layer, kind, P)     -> dropout(P) on attention probabilities (B*H, L, S[+1]); kind = ('ca', name) | 'sa'
+    #   hidden(layer, h)          -> dropout(h) on the FFN hidden activations
+    #   memory_keep(layer, memories, B) -> bool (B, len(memories)) keep mask BEFORE the keep-all fix-up, or None
+    train: Optional[object] = None
 
 
 # --------------------------------------------------------------------------------------------
@@ -55,7 +62,8 @@ def layer_norm(x: Tensor, sd: SD, prefix: str, eps: float = 1e-5) -> Tensor:
 
 
 def mha(q_in: Tensor, k_in: Tensor, v_in: Tensor, sd: SD, prefix: str, nhead: int,
-        key_padding_mask: Optional[Tensor], attn_mask: Optional[Tensor], add_zero_attn: bool) -> Tensor:
+        key_padding_mask: Optional[Tensor], attn_mask: Optional[Tensor], add_zero_attn: bool,
+        prob_dropout: Optional[Callable] = None) -> Tensor:
     """nn.MultiheadAttention(batch_first=True) forward, eval mode, need_weights=True branch.
 
     torch/nn/functional.py:5867-5873 (separate q/k/v in-projections from the packed weight),
@@ -101,6 +109,8 @@ def mha(q_in: Tensor, k_in: Tensor, v_in: Tensor, sd: SD, prefix: str, nhead: in
     else:
         scores = torch.bmm(q_scaled, k.transpose(-2, -1))
     probs = F.softmax(scores, dim=-1)
+    if prob_dropout is not None:                                # training: dropout(attn_output_weights), :6645-6646
+        probs = prob_dropout(probs)
     out = torch.bmm(probs, v)                                   # (B*H, L, dh)
     out = out.view(B, nhead, L, dh).transpose(1, 2).reshape(B, L, E)
     return F.linear(out, sd[prefix + "out_proj.weight"], sd[prefix + "out_proj.bias"])
@@ -108,20 +118,26 @@ def mha(q_in: Tensor, k_in: Tensor, v_in: Tensor, sd: SD, prefix: str, nhead: in
 
 def cross_attention_layer(tgt: Tensor, memory: Tensor, sd: SD, prefix: str, nhead: int,
                           attn_mask: Optional[Tensor], key_padding_mask: Optional[Tensor],
-                          pos: Optional[Tensor], query_pos: Optional[Tensor]) -> Tensor:
+                          pos: Optional[Tensor], query_pos: Optional[Tensor], prob_dropout: Optional[Callable] = None,
+                          dropout: Optional[Callable] = None) -> Tensor:
     """CrossAttentionLayer.forward_post (modules/grounding/query_encoder.py:288-307);
-    MHA built with add_zero_attn=True (:268-270)."""
+    MHA built with add_zero_attn=True and dropout=p (:268-270); `tgt + dropout(tgt2)` (:304)."""
     q_in = tgt if query_pos is None else tgt + query_pos
     k_in = memory if pos is None else memory + pos
-    upd = mha(q_in, k_in, memory, sd, prefix + "multihead_attn.", nhead, key_padding_mask, attn_mask, True)
+    upd = mha(q_in, k_in, memory, sd, prefix + "multihead_attn.", nhead, key_padding_mask, attn_mask, True, prob_dropout)
+    if dropout is not None:
+        upd = dropout(upd)
     return layer_norm(tgt + upd, sd, prefix + "norm.")
 
 
 def self_attention_layer(tgt: Tensor, sd: SD, prefix: str, nhead: int,
-                         key_padding_mask: Optional[Tensor], query_pos: Optional[Tensor]) -> Tensor:
+                         key_padding_mask: Optional[Tensor], query_pos: Optional[Tensor],
+                         prob_dropout: Optional[Callable] = None, dropout: Optional[Callable] = None) -> Tensor:
     """SelfAttentionLayer.forward_post (query_encoder.py:213-227): q = k = tgt+pos, v = tgt."""
     x = tgt if query_pos is None else tgt + query_pos
-    upd = mha(x, x, tgt, sd, prefix + "self_attn.", nhead, key_padding_mask, None, False)
+    upd = mha(x, x, tgt, sd, prefix + "self_attn.", nhead, key_padding_mask, None, False, prob_dropout)
+    if dropout is not None:
+        upd = dropout(upd)
     return layer_norm(tgt + upd, sd, prefix + "norm.")
 
 
@@ -155,17 +171,25 @@ def spatial_mha(x: Tensor, v_in: Tensor, pairwise_locs: Tensor, sd: SD, prefix: 
 
 def spatial_self_attention_layer(tgt: Tensor, sd: SD, prefix: str, nhead: int,
                                  key_padding_mask: Optional[Tensor], query_pos: Optional[Tensor],
-                                 pairwise_locs: Tensor) -> Tensor:
-    """SpatialSelfAttentionLayer.forward_post (query_encoder.py:438-452)."""
+                                 pairwise_locs: Tensor, dropout: Optional[Callable] = None) -> Tensor:
+    """SpatialSelfAttentionLayer.forward_post (query_encoder.py:438-452).  MultiHeadAttentionSpatial never applies its
+    `dropout` argument (transformers.py:158-240), so only the sublayer dropout (:449) exists in training."""
     x = tgt if query_pos is None else tgt + query_pos
     upd = spatial_mha(x, tgt, pairwise_locs, sd, prefix + "self_attn.", nhead, key_padding_mask)
+    if dropout is not None:
+        upd = dropout(upd)
     return layer_norm(tgt + upd, sd, prefix + "norm.")
 
 
-def ffn_layer(tgt: Tensor, sd: SD, prefix: str) -> Tensor:
-    """FFNLayer.forward_post, relu (query_encoder.py:384-388)."""
+def ffn_layer(tgt: Tensor, sd: SD, prefix: str, hidden_dropout: Optional[Callable] = None,
+              dropout: Optional[Callable] = None) -> Tensor:
+    """FFNLayer.forward_post, relu (query_encoder.py:384-388): linear2(dropout(relu(linear1 x))), tgt + dropout(tgt2)."""
     h = F.relu(F.linear(tgt, sd[prefix + "linear1.weight"], sd[prefix + "linear1.bias"]))
+    if hidden_dropout is not None:
+        h = hidden_dropout(h)
     upd = F.linear(h, sd[prefix + "linear2.weight"], sd[prefix + "linear2.bias"])
+    if dropout is not None:
+        upd = dropout(upd)
     return layer_norm(tgt + upd, sd, prefix + "norm.")
 
 
@@ -173,28 +197,45 @@ def ffn_layer(tgt: Tensor, sd: SD, prefix: str) -> Tensor:
 # one decoder layer / the stacked decoder
 # --------------------------------------------------------------------------------------------
 def query_encoder_layer(query: Tensor, input_dict: dict, pairwise_locs: Optional[Tensor], sd: SD,
-                        prefix: str, cfg: DecoderCfg) -> Tensor:
-    """QueryEncoderLayer.forward in eval mode (query_encoder.py:114-181)."""
+                        prefix: str, cfg: DecoderCfg, layer: int = 0) -> Tensor:
+    """QueryEncoderLayer.forward (query_encoder.py:114-181); eval mode unless cfg.train supplies the random draws."""
     H = cfg.num_attention_heads
     _, query_masks, query_pos = input_dict["query"]
     mem_index = {m: j for j, m in enumerate(cfg.memories)}            # memory2ca, :105
+    tr = cfg.train
+
+    def hook(name, *key):
+        return None if tr is None else (lambda x: getattr(tr, name)(layer, *key, x))
 
     def one_ca(q, memory):
         feat, mask, pos = input_dict[memory]
         kpm, am = (mask, None) if mask.ndim == 2 else (None, mask)     # :121-126
         return cross_attention_layer(q, feat, sd, f"{prefix}cross_attn_list.{mem_index[memory]}.", H,
-                                     am, kpm, pos, query_pos)
+                                     am, kpm, pos, query_pos, hook("probs", ("ca", memory)),
+                                     hook("sublayer", ("ca", memory)))
 
     def sequential_ca(q, memories):                                    # :117-129
         for m in memories:
             q = one_ca(q, m)
         return q
 
-    def parallel_ca(q, memories):                                      # :131-154 (eval branch)
+    def parallel_ca(q, memories):                                      # :131-154
         assert "prompt" not in memories
-        return torch.stack([one_ca(q, m) for m in memories], dim=1).mean(dim=1)
+        stack = torch.stack([one_ca(q, m) for m in memories], dim=1)
+        keep = None
+        if tr is not None and cfg.memory_dropout > 0.0:               # :145-152
+            keep = tr.memory_keep(layer, list(memories), q.shape[0])
+        if keep is None:
+            return stack.mean(dim=1)
+        n_left = keep.sum(dim=1)
+        keep = torch.logical_or(keep, n_left.unsqueeze(-1) == 0)
+        n_left = keep.sum(dim=1)
+        return (stack * keep.unsqueeze(-1).unsqueeze(-1)).sum(dim=1) / n_left.unsqueeze(-1).unsqueeze(-1).float()
 
-    memories = [m for m in cfg.memories if m not in cfg.drop_memories_test]   # :156
+    if tr is not None:
+        memories = list(cfg.memories)                                  # training: every memory, :156
+    else:
+        memories = [m for m in cfg.memories if m not in cfg.drop_memories_test]   # :156
     if cfg.structure == "sequential":
         query = sequential_ca(query, memories)
     elif cfg.structure == "parallel":
@@ -211,10 +252,12 @@ def query_encoder_layer(query: Tensor, input_dict: dict, pairwise_locs: Optional
         raise NotImplementedError(f"Unknow structure type: {cfg.structure}")
 
     if cfg.spatial_selfattn:                                           # :174-178
-        query = spatial_self_attention_layer(query, sd, prefix + "self_attn.", H, query_masks, query_pos, pairwise_locs)
+        query = spatial_self_attention_layer(query, sd, prefix + "self_attn.", H, query_masks, query_pos, pairwise_locs,
+                                             hook("sublayer", "sa"))
     else:
-        query = self_attention_layer(query, sd, prefix + "self_attn.", H, query_masks, query_pos)
-    return ffn_layer(query, sd, prefix + "ffn.")                        # :179
+        query = self_attention_layer(query, sd, prefix + "self_attn.", H, query_masks, query_pos, hook("probs", "sa"),
+                                     hook("sublayer", "sa"))
+    return ffn_layer(query, sd, prefix + "ffn.", hook("hidden"), hook("sublayer", "ffn"))        # :179
 
 
 def query_mask_encoder(sd: SD, cfg: DecoderCfg, input_dict: dict, pairwise_locs: Optional[Tensor],
@@ -240,7 +283,7 @@ def query_mask_encoder(sd: SD, cfg: DecoderCfg, input_dict: dict, pairwise_locs:
             if isinstance(voxel_feat, list):
                 input_dict["voxel"][0] = voxel_feat[i]                     # :90-91
             query = query_encoder_layer(query, input_dict, pairwise_locs, sd,
-                                        f"{prefix}unified_encoder.{i}.", cfg)
+                                        f"{prefix}unified_encoder.{i}.", cfg, layer=i)
     return query, predictions_class, predictions_mask
 
 

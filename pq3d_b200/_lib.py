@@ -23,14 +23,21 @@ SIGNATURES: Dict[str, list] = {
                         _i32, _i32, _f32, _i32, _vp],
     "pq3d_attention_fwd": [_i32, _vp, _i64, _i64, _pp, _pi64, _pi64, _pp, _pi64, _pi64, _pi64, _pi32, _pi32, _pi32,
                            _pp, _pi64, _pi64, _pi64, _pp, _vp, _i64, _i64, _i32, _i32, _i32, _i32, _vp, _i64, _vp, _vp, _i64, _vp],
+    "pq3d_attention_fwd_train": [_i32, _vp, _i64, _i64, _pp, _pi64, _pi64, _pp, _pi64, _pi64, _pi64, _pi32, _pi32, _pi32,
+                                 _pp, _pi64, _pi64, _pi64, _pp, _vp, _i64, _i64, _i32, _i32, _i32, _i32, _vp, _i64, _vp, _vp,
+                                 _i64, _f32, _vp, C.POINTER(C.c_uint32), _vp],
     "pq3d_spatial_bias": [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i64, _vp],
     "pq3d_debug_set_timeline": [_vp],
     "pq3d_debug_set_attention_timeline": [_vp],
     "pq3d_debug_force_two_pass": [_i32],
     "pq3d_transpose_cast": [_vp, _i32, _i64, _i64, _i64, _vp, _i64, _i64, _i64, _vp, _i64, _i64, _i64, _vp, _i64, _i64,
                             _i64, _i32, _i32, _i32, _i32, _i32, _f32, _vp],
-    "pq3d_colsum": [_vp, _i32, _i64, _vp, _i64, _vp, _i32, _i32, _i32, _vp],
-    "pq3d_layernorm_bwd": [_vp, _i64, _vp, _vp, _vp, _i32, _f32, _i32, _i32, _vp, _i64, _vp, _vp, _vp, _vp, _vp],
+    "pq3d_colsum": [_vp, _i32, _i64, _vp, _i64, _vp, _i32, _i32, _i32, _f32, _vp],
+    "pq3d_layernorm_bwd": [_vp, _i64, _vp, _vp, _vp, _i32, _f32, _i32, _i32, _vp, _i64, _vp, _vp, _vp, _vp, _f32, _vp,
+                           C.c_uint32, _vp, _i32, _vp],
+    "pq3d_add_layernorm_train": [_vp, _i64, _vp, _vp, _vp, _i32, _f32, _i32, _i32, _vp, _vp, _vp, _vp, _f32, _vp,
+                                 C.c_uint32, _vp, _i32, _vp],
+    "pq3d_dropout_bf16": [_vp, _i64, _f32, _vp, C.c_uint32, _vp],
     "pq3d_attn_delta": [_vp, _vp, _i64, _vp, _i32, _i32, _i32, _vp],
     "pq3d_softmax_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _i32, _i32,
                          _i32, _i32, _i32, _i32, _vp],
@@ -39,7 +46,7 @@ SIGNATURES: Dict[str, list] = {
     "pq3d_pack_segments": [_vp, _vp, _i32, _i32, _vp],
     "pq3d_attention_bwd": [_vp, _i64, _i32, _vp, _i64, _i32, _vp, _i64, _i32, _vp, _i64, _i32, _i32, _i32, _vp, _i64, _i64,
                            _i64, _vp, _i64, _vp, _vp, _vp, _vp, _i64, _i32, _vp, _i64, _i32, _vp, _i64, _i32, _vp, _i64,
-                           _i32, _i32, _i32, _f32, _vp],
+                           _i32, _i32, _i32, _f32, _f32, _vp, C.c_uint32, _vp],
     "pq3d_ingest_memory": [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp],
     "pq3d_add_layernorm": [_vp, _i64, _vp, _vp, _vp, _i32, _f32, _i32, _i32, _vp, _vp, _vp, _vp, _vp],
     "pq3d_pack_mask": [_vp, _vp, _i64, _i32, _i32, _vp, _vp, _i64, _vp],

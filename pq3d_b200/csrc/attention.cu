@@ -77,6 +77,12 @@ struct AttnParams {
   int64_t bias_ld;
   float *stat_m, *stat_l;      // optional [n_mem][B][H][Nq]: softmax reference and denominator, saved for the backward
   int64_t stat_mem_stride;
+  // training only: dropout on the attention probabilities (nn.MultiheadAttention(dropout=p), applied after the
+  // softmax normalisation); element ((b*H + h)*Nq + n)*ceil128(S) + key of stream site[mem] (csrc/ptx.cuh RNG)
+  uint32_t drop_thresh;
+  float drop_scale;
+  const uint32_t* seed;
+  uint32_t site[kMaxMem];
   unsigned long long* dbg;
 };
 
@@ -300,6 +306,9 @@ __device__ __forceinline__ bool attn_softmax(const AttnParams& p, const AttnMem&
     if (MODE == kResident) g = 0;                // sweep 2 re-reads the resident score tiles
   }
   if (dbg != nullptr && threadIdx.x == 64) dbg[2] = clock64();
+  const uint32_t dkey = p.drop_thresh != 0 ? drop_key(__ldg(p.seed), p.site[c.mi]) : 0u;
+  const uint32_t drow = static_cast<uint32_t>(((static_cast<int64_t>(c.b) * p.H + c.h) * p.Nq + n_c) *
+                                              (((mem.S + kKvTile - 1) / kKvTile) * kKvTile));
   float l = 0.f;
   for (int t = 0; t < c.T; ++t, ++g) {           // ---- probabilities, row sums, P tiles
     const int sb = g & 1;
@@ -316,6 +325,11 @@ __device__ __forceinline__ bool attn_softmax(const AttnParams& p, const AttnMem&
     for (int j = 0; j < 32; ++j) {
       sc[j] = ex2_approx(MODE == kOnePass ? sc[j] : sc[j] - m);    // ex2(-inf) = 0 for masked keys
       l += sc[j];
+    }
+    if (p.drop_thresh != 0) {                    // the denominator keeps every key; P V uses the dropped, rescaled weights
+      const uint32_t e0 = drow + t * kKvTile + cc * 32;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) sc[j] = drop_keep(dkey, e0 + j, p.drop_thresh) ? sc[j] * p.drop_scale : 0.f;
     }
     mbar_wait(&c.p_empty[pb], ((t >> 1) & 1) ^ 1, 320 + pb);
     write_probs(pb, sc);
@@ -510,7 +524,7 @@ extern "C" int pq3d_spatial_bias(const float* pairwise_locs, const float* loc_w,
   return PQ3D_OK;
 }
 
-extern "C" int pq3d_attention_fwd(int n_mem, const void* Q, int64_t ldq, int64_t q_mem_stride, const void* const* K,
+static int attention_fwd_impl(int n_mem, const void* Q, int64_t ldq, int64_t q_mem_stride, const void* const* K,
                                   const int64_t* ldk, const int64_t* k_col0, const void* const* Vt,
                                   const int64_t* ldvt, const int64_t* vt_row0, const int64_t* vt_rows,
                                   const int32_t* S, const int32_t* S_pitch, const int32_t* Vt_pitch,
@@ -519,7 +533,9 @@ extern "C" int pq3d_attention_fwd(int n_mem, const void* Q, int64_t ldq, int64_t
                                   const int32_t* const* kv_tiles, void* O, int64_t ldo,
                                   int64_t o_mem_stride, int B, int H, int Nq, int zero_attn, const float* score_bias,
                                   int64_t bias_ld, float* stat_m, float* stat_l, int64_t stat_mem_stride,
-                                  void* stream) {
+                                  float drop_p, const uint32_t* seed_dev, const uint32_t* sites, void* stream) {
+  PQ3D_CHECK_ARG(drop_p >= 0.f && drop_p < 1.f && (drop_p == 0.f || (seed_dev != nullptr && sites != nullptr)),
+                 "pq3d_attention_fwd: dropout needs p in [0,1), a device seed and one site id per memory");
   PQ3D_CHECK_ARG(n_mem >= 1 && n_mem <= kMaxMem, "pq3d_attention_fwd: n_mem=%d not in [1,%d]", n_mem, kMaxMem);
   PQ3D_CHECK_ARG(Q && O && K && Vt && S && S_pitch && Vt_pitch, "pq3d_attention_fwd: null argument");
   PQ3D_CHECK_ARG(B > 0 && H > 0 && Nq > 0, "pq3d_attention_fwd: bad shape B=%d H=%d Nq=%d", B, H, Nq);
@@ -593,6 +609,16 @@ extern "C" int pq3d_attention_fwd(int n_mem, const void* Q, int64_t ldq, int64_t
   p.stat_mem_stride = stat_mem_stride;
   PQ3D_CHECK_ARG((stat_m == nullptr) == (stat_l == nullptr), "pq3d_attention_fwd: stat_m and stat_l go together");
   p.dbg = g_attn_timeline;
+  if (drop_p > 0.f) {
+    p.drop_thresh = drop_threshold(drop_p);
+    p.drop_scale = 1.f / (1.f - drop_p);
+    p.seed = seed_dev;
+    for (int i = 0; i < n_mem; ++i) {
+      p.site[i] = sites[i];
+      PQ3D_CHECK_ARG(static_cast<int64_t>(B) * H * Nq * (((S[i] + kKvTile - 1) / kKvTile) * kKvTile) < (int64_t(1) << 32),
+                     "pq3d_attention_fwd: memory %d has too many score elements for the 32-bit dropout counter", i);
+    }
+  }
   static bool configured = false;
   if (!configured) {
     PQ3D_CUDA(cudaFuncSetAttribute(attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
@@ -602,4 +628,37 @@ extern "C" int pq3d_attention_fwd(int n_mem, const void* Q, int64_t ldq, int64_t
   PQ3D_CUDA(launch_kernel(attention_fwd_kernel, grid, dim3(kAttnThreads), kAttnSmem,
                           reinterpret_cast<cudaStream_t>(stream), maps, p));
   return PQ3D_OK;
+}
+
+extern "C" int pq3d_attention_fwd(int n_mem, const void* Q, int64_t ldq, int64_t q_mem_stride, const void* const* K,
+                                  const int64_t* ldk, const int64_t* k_col0, const void* const* Vt,
+                                  const int64_t* ldvt, const int64_t* vt_row0, const int64_t* vt_rows,
+                                  const int32_t* S, const int32_t* S_pitch, const int32_t* Vt_pitch,
+                                  const uint32_t* const* mask_bits, const int64_t* mask_b_stride,
+                                  const int64_t* mask_h_stride, const int64_t* mask_q_stride,
+                                  const int32_t* const* kv_tiles, void* O, int64_t ldo,
+                                  int64_t o_mem_stride, int B, int H, int Nq, int zero_attn, const float* score_bias,
+                                  int64_t bias_ld, float* stat_m, float* stat_l, int64_t stat_mem_stride,
+                                  void* stream) {
+  return attention_fwd_impl(n_mem, Q, ldq, q_mem_stride, K, ldk, k_col0, Vt, ldvt, vt_row0, vt_rows, S, S_pitch, Vt_pitch,
+                            mask_bits, mask_b_stride, mask_h_stride, mask_q_stride, kv_tiles, O, ldo, o_mem_stride, B, H,
+                            Nq, zero_attn, score_bias, bias_ld, stat_m, stat_l, stat_mem_stride, 0.f, nullptr, nullptr,
+                            stream);
+}
+
+// Training-mode forward: same as pq3d_attention_fwd plus dropout on the attention probabilities.
+extern "C" int pq3d_attention_fwd_train(int n_mem, const void* Q, int64_t ldq, int64_t q_mem_stride, const void* const* K,
+                                        const int64_t* ldk, const int64_t* k_col0, const void* const* Vt,
+                                        const int64_t* ldvt, const int64_t* vt_row0, const int64_t* vt_rows,
+                                        const int32_t* S, const int32_t* S_pitch, const int32_t* Vt_pitch,
+                                        const uint32_t* const* mask_bits, const int64_t* mask_b_stride,
+                                        const int64_t* mask_h_stride, const int64_t* mask_q_stride,
+                                        const int32_t* const* kv_tiles, void* O, int64_t ldo, int64_t o_mem_stride,
+                                        int B, int H, int Nq, int zero_attn, const float* score_bias, int64_t bias_ld,
+                                        float* stat_m, float* stat_l, int64_t stat_mem_stride, float drop_p,
+                                        const uint32_t* seed_dev, const uint32_t* sites, void* stream) {
+  return attention_fwd_impl(n_mem, Q, ldq, q_mem_stride, K, ldk, k_col0, Vt, ldvt, vt_row0, vt_rows, S, S_pitch, Vt_pitch,
+                            mask_bits, mask_b_stride, mask_h_stride, mask_q_stride, kv_tiles, O, ldo, o_mem_stride, B, H,
+                            Nq, zero_attn, score_bias, bias_ld, stat_m, stat_l, stat_mem_stride, drop_p, seed_dev, sites,
+                            stream);
 }

@@ -54,6 +54,10 @@ struct AttnBwdParams {
   int32_t q_col0, do_col0, k_col0, v_col0, dk_col0, dv_col0, dq_col0;
   int32_t tiles_per_chunk, atomic_dq;
   float q_scale;
+  uint32_t drop_thresh;        // attention-probability dropout of the forward (0 = none): same (seed, site, element)
+  float drop_scale;
+  const uint32_t* seed;
+  uint32_t site;
 };
 
 __device__ __forceinline__ float bwd_ex2(float x) {
@@ -209,6 +213,8 @@ attention_bwd_kernel(const __grid_constant__ AttnBwdMaps maps, const AttnBwdPara
         s_dl[r] = ok ? p.delta[bh * p.Nq + r] : 0.f;
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
+      const uint32_t dkey = p.drop_thresh != 0 ? drop_key(__ldg(p.seed), p.site) : 0u;
+      const uint32_t s_pad = static_cast<uint32_t>(tiles_total * 128);
       const uint32_t* mbase =
           p.mask_bits == nullptr ? nullptr : p.mask_bits + b * p.mask_b_stride + h * p.mask_h_stride;
       for (int i = 0; i < Tn; ++i) {
@@ -240,8 +246,14 @@ attention_bwd_kernel(const __grid_constant__ AttnBwdMaps maps, const AttnBwdPara
             if (mrow != nullptr && n < p.Nq) masked = masked || ((__ldg(mrow + n * p.mask_q_stride) >> lane_id()) & 1u);
             if (p.bias != nullptr && n < p.Nq && key_ok) sc += __ldg(p.bias + (bh * p.Nq + n) * p.bias_ld + kk);
             const float pv = masked ? 0.f : bwd_ex2(sc - s_m[n]) * s_il[n];
-            pr[j] = pv;
-            ds[j] = 0.6931471805599453f * pv * (__uint_as_float(dv[j]) - s_dl[n]);
+            float ks = 1.f;             // dropout factor of this probability in the forward
+            if (p.drop_thresh != 0) {
+              const int nc = n < p.Nq ? n : p.Nq - 1;
+              const uint32_t e = static_cast<uint32_t>(bh * p.Nq + nc) * s_pad + static_cast<uint32_t>(kk);
+              ks = drop_keep(dkey, e, p.drop_thresh) ? p.drop_scale : 0.f;
+            }
+            pr[j] = pv * ks;
+            ds[j] = 0.6931471805599453f * pv * (__uint_as_float(dv[j]) * ks - s_dl[n]);
           }
           if (p.dS_out != nullptr && kk < p.ds_ld) {
 #pragma unroll
@@ -347,7 +359,10 @@ extern "C" int pq3d_attention_bwd(const void* Q, int64_t ldq, int q_col0, const 
                                   int64_t mask_q_stride, const float* bias, int64_t bias_ld, const float* stat_m,
                                   const float* stat_l, const float* delta, void* dK, int64_t ld_dk, int dk_col0, void* dV,
                                   int64_t ld_dv, int dv_col0, float* dQ, int64_t ld_dq, int dq_col0, void* dS_out,
-                                  int64_t ds_ld, int B, int H, int Nq, float q_scale, void* stream) {
+                                  int64_t ds_ld, int B, int H, int Nq, float q_scale, float drop_p,
+                                  const uint32_t* seed_dev, uint32_t site, void* stream) {
+  PQ3D_CHECK_ARG(drop_p >= 0.f && drop_p < 1.f && (drop_p == 0.f || seed_dev != nullptr),
+                 "pq3d_attention_bwd: dropout needs p in [0,1) and a device seed");
   PQ3D_CHECK_ARG(Q && dO && K && V && stat_m && stat_l && delta && dK && dV && dQ, "pq3d_attention_bwd: null argument");
   PQ3D_CHECK_ARG(B > 0 && H > 0 && Nq > 0 && Nq <= 128 && S > 0 && S_pitch >= S,
                  "pq3d_attention_bwd: bad shape B=%d H=%d Nq=%d (<= 128) S=%d S_pitch=%d", B, H, Nq, S, S_pitch);
@@ -383,6 +398,12 @@ extern "C" int pq3d_attention_bwd(const void* Q, int64_t ldq, int q_col0, const 
   p.q_col0 = q_col0; p.do_col0 = do_col0; p.k_col0 = k_col0; p.v_col0 = v_col0;
   p.dk_col0 = dk_col0; p.dv_col0 = dv_col0; p.dq_col0 = dq_col0;
   p.q_scale = q_scale;
+  if (drop_p > 0.f) {
+    p.drop_thresh = drop_threshold(drop_p);
+    p.drop_scale = 1.f / (1.f - drop_p);
+    p.seed = seed_dev;
+    p.site = site;
+  }
   // split the key range over enough CTAs to fill the device; dQ then meets in fp32 atomics (caller zero-fills dQ's
   // [*, dq_col0 + H*64) block in that case — see the return value)
   const int tiles = (S + 127) / 128;

@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(256) transpose_cast_vec_kernel(const Transpose
 // per column (the host zero-fills `out` first unless accumulating).  C must be even.
 // ------------------------------------------------------------------------------------------------
 __global__ void colsum_kernel(const void* __restrict__ in, int in_fp32, int64_t ld, const __nv_bfloat16* __restrict__ gate,
-                              int64_t ld_gate, float* __restrict__ out, int R, int C, int rows_per_block) {
+                              int64_t ld_gate, float* __restrict__ out, int R, int C, int rows_per_block, float scale) {
   pdl_sync();
   __shared__ float part[8][64];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -168,7 +168,7 @@ __global__ void colsum_kernel(const void* __restrict__ in, int in_fp32, int64_t 
       float t = 0.f;
 #pragma unroll
       for (int i = 0; i < 8; ++i) t += part[i][threadIdx.x];
-      atomicAdd(&out[cc], t);
+      atomicAdd(&out[cc], t * scale);
     }
   }
 }
@@ -187,9 +187,12 @@ __global__ void __launch_bounds__(kLnbWarps * 32)
 layernorm_bwd_kernel(const float* __restrict__ y, int64_t y_group_stride, const float* __restrict__ residual,
                      const float* __restrict__ gamma, const float* __restrict__ d_out, int G, float eps, int R,
                      float* __restrict__ d_x, int64_t dx_group_stride, __nv_bfloat16* __restrict__ d_x16,
-                     float* __restrict__ d_res, float* __restrict__ d_gamma, float* __restrict__ d_beta) {
+                     float* __restrict__ d_res, float* __restrict__ d_gamma, float* __restrict__ d_beta,
+                     uint32_t drop_thresh, float drop_scale, const uint32_t* __restrict__ seed, uint32_t site,
+                     const float* __restrict__ row_w, int rows_per_scene) {
   pdl_sync();
   constexpr int D = NV * 128;
+  const uint32_t key = drop_thresh != 0 ? drop_key(__ldg(seed), site) : 0u;
   // per-warp partial affine gradients meet here once per group: no atomics inside the row loop
   __shared__ float s_dg[kLnbWarps][D], s_db[kLnbWarps][D];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -205,18 +208,28 @@ layernorm_bwd_kernel(const float* __restrict__ y, int64_t y_group_stride, const 
     for (int row = blockIdx.x * kLnbWarps + wid; row < R; row += gridDim.x * kLnbWarps) {
       const int64_t base = static_cast<int64_t>(row) * D;
       float4 x[NV], go[NV];
+      uint32_t km[NV];                  // dropout keep bits of this lane's 4 columns per chunk
       float sum = 0.f;
+      const float wrow = row_w != nullptr ? __ldg(row_w + (row / rows_per_scene) * G + g) : inv_g;
 #pragma unroll
       for (int i = 0; i < NV; ++i) {
         float4 v = residual != nullptr ? __ldg(reinterpret_cast<const float4*>(residual + base) + i * 32 + lane)
                                        : make_float4(0, 0, 0, 0);
+        km[i] = 0xfu;
         if (y != nullptr) {
-          const float4 t = __ldg(reinterpret_cast<const float4*>(y + g * y_group_stride + base) + i * 32 + lane);
+          float4 t = __ldg(reinterpret_cast<const float4*>(y + g * y_group_stride + base) + i * 32 + lane);
+          if (drop_thresh != 0) {
+            const uint32_t e = static_cast<uint32_t>((static_cast<int64_t>(g) * R + row) * D + (i * 32 + lane) * 4);
+            km[i] = (drop_keep(key, e, drop_thresh) ? 1u : 0u) | (drop_keep(key, e + 1, drop_thresh) ? 2u : 0u) |
+                    (drop_keep(key, e + 2, drop_thresh) ? 4u : 0u) | (drop_keep(key, e + 3, drop_thresh) ? 8u : 0u);
+            t.x = (km[i] & 1u) ? t.x * drop_scale : 0.f; t.y = (km[i] & 2u) ? t.y * drop_scale : 0.f;
+            t.z = (km[i] & 4u) ? t.z * drop_scale : 0.f; t.w = (km[i] & 8u) ? t.w * drop_scale : 0.f;
+          }
           v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
         }
         x[i] = v;
         go[i] = __ldg(reinterpret_cast<const float4*>(d_out + base) + i * 32 + lane);
-        go[i].x *= inv_g; go[i].y *= inv_g; go[i].z *= inv_g; go[i].w *= inv_g;
+        go[i].x *= wrow; go[i].y *= wrow; go[i].z *= wrow; go[i].w *= wrow;
         sum += (v.x + v.y) + (v.z + v.w);
       }
 #pragma unroll
@@ -257,10 +270,15 @@ layernorm_bwd_kernel(const float* __restrict__ y, int64_t y_group_stride, const 
         dx.z = rstd * (dxh[i].z - m1 - x[i].z * m2);
         dx.w = rstd * (dxh[i].w - m1 - x[i].w * m2);
         const int64_t off = base + (i * 32 + lane) * 4;
-        if (d_x != nullptr) *reinterpret_cast<float4*>(d_x + g * dx_group_stride + off) = dx;
+        float4 dy = dx;                 // gradient of the branch input y: through the dropout mask
+        if (drop_thresh != 0) {
+          dy.x = (km[i] & 1u) ? dx.x * drop_scale : 0.f; dy.y = (km[i] & 2u) ? dx.y * drop_scale : 0.f;
+          dy.z = (km[i] & 4u) ? dx.z * drop_scale : 0.f; dy.w = (km[i] & 8u) ? dx.w * drop_scale : 0.f;
+        }
+        if (d_x != nullptr) *reinterpret_cast<float4*>(d_x + g * dx_group_stride + off) = dy;
         if (d_x16 != nullptr) {
           uint2 o;
-          o.x = pack_bf16x2(dx.x, dx.y); o.y = pack_bf16x2(dx.z, dx.w);
+          o.x = pack_bf16x2(dy.x, dy.y); o.y = pack_bf16x2(dy.z, dy.w);
           *reinterpret_cast<uint2*>(d_x16 + g * dx_group_stride + off) = o;
         }
         if (d_res != nullptr) {
@@ -499,7 +517,7 @@ extern "C" int pq3d_transpose_cast(const void* in, int in_fp32, int64_t ld_in, i
 }
 
 extern "C" int pq3d_colsum(const void* in, int in_fp32, int64_t ld, const void* gate, int64_t ld_gate, float* out, int R,
-                           int C, int accumulate, void* stream) {
+                           int C, int accumulate, float scale, void* stream) {
   PQ3D_CHECK_ARG(in && out && R > 0 && C > 0, "pq3d_colsum: bad argument");
   PQ3D_CHECK_ARG(C % 2 == 0 && ld % 2 == 0 && ld_gate % 2 == 0 && (reinterpret_cast<uintptr_t>(in) & 7) == 0,
                  "pq3d_colsum: C, ld must be even and the input 8-byte aligned");
@@ -512,14 +530,21 @@ extern "C" int pq3d_colsum(const void* in, int in_fp32, int64_t ld, const void* 
   if (chunks < 1) chunks = 1;
   const int rows_per_block = (R + chunks - 1) / chunks;
   PQ3D_CUDA(launch_kernel(colsum_kernel, dim3(col_blocks, (R + rows_per_block - 1) / rows_per_block), dim3(256), 0, st, in,
-                          in_fp32, ld, reinterpret_cast<const __nv_bfloat16*>(gate), ld_gate, out, R, C, rows_per_block));
+                          in_fp32, ld, reinterpret_cast<const __nv_bfloat16*>(gate), ld_gate, out, R, C, rows_per_block, scale));
   return PQ3D_OK;
 }
 
 extern "C" int pq3d_layernorm_bwd(const float* y, int64_t y_group_stride, const float* residual, const float* gamma,
                                   const float* d_out, int G, float eps, int R, int D, float* d_x,
                                   int64_t dx_group_stride, void* d_x_bf16, float* d_res, float* d_gamma, float* d_beta,
-                                  void* stream) {
+                                  float drop_p, const uint32_t* seed_dev, uint32_t site, const float* row_w,
+                                  int rows_per_scene, void* stream) {
+  PQ3D_CHECK_ARG(drop_p >= 0.f && drop_p < 1.f && (drop_p == 0.f || seed_dev != nullptr),
+                 "pq3d_layernorm_bwd: dropout needs p in [0,1) and a device seed");
+  PQ3D_CHECK_ARG(row_w == nullptr || (rows_per_scene > 0 && R % rows_per_scene == 0),
+                 "pq3d_layernorm_bwd: row weights need rows_per_scene dividing R");
+  const uint32_t thresh = drop_p > 0.f ? drop_threshold(drop_p) : 0u;
+  const float dscale = 1.f / (1.f - drop_p);
   PQ3D_CHECK_ARG((y || residual) && gamma && d_out && G >= 1 && R > 0 && D % 128 == 0 && D <= 1024,
                  "pq3d_layernorm_bwd: bad argument (D must be a multiple of 128, at most 1024)");
   int blocks = (R + kLnbWarps - 1) / kLnbWarps;
@@ -530,7 +555,8 @@ extern "C" int pq3d_layernorm_bwd(const float* y, int64_t y_group_stride, const 
   case NV:                                                                                                           \
     err = launch_kernel(layernorm_bwd_kernel<NV>, dim3(blocks), dim3(kLnbWarps * 32), 0, st, y, y_group_stride,      \
                         residual, gamma, d_out, G, eps, R, d_x, dx_group_stride,                                     \
-                        reinterpret_cast<__nv_bfloat16*>(d_x_bf16), d_res, d_gamma, d_beta);                         \
+                        reinterpret_cast<__nv_bfloat16*>(d_x_bf16), d_res, d_gamma, d_beta, thresh, dscale,         \
+                        seed_dev, site, row_w, rows_per_scene);                                                      \
     break;
   switch (D / 128) {
     PQ3D_LNB_CASE(1) PQ3D_LNB_CASE(2) PQ3D_LNB_CASE(3) PQ3D_LNB_CASE(4) PQ3D_LNB_CASE(5) PQ3D_LNB_CASE(6)

@@ -286,4 +286,24 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Counter-based dropout RNG shared by the training kernels: the keep decision of element `idx` at dropout site
+// `site` in the step whose seed is `seed` is a pure function (no state, no saved masks): the backward regenerates
+// exactly the forward's mask.  hash32 is the "lowbias32" integer finaliser; pq3d_b200/rng.py restates it on tensors.
+// ------------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ uint32_t hash32(uint32_t x) {
+  x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+  return x;
+}
+__host__ __device__ __forceinline__ uint32_t drop_key(uint32_t seed, uint32_t site) {
+  return hash32(seed + site * 0x9E3779B9u);
+}
+__host__ __device__ __forceinline__ bool drop_keep(uint32_t key, uint32_t idx, uint32_t thresh) {
+  return hash32(idx ^ key) >= thresh;
+}
+__host__ __forceinline__ uint32_t drop_threshold(float p) {
+  const double t = static_cast<double>(p) * 4294967296.0;
+  return t >= 4294967295.0 ? 4294967295u : static_cast<uint32_t>(t);
+}
+
 }  // namespace pq3d

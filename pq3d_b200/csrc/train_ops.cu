@@ -101,6 +101,114 @@ __global__ void __launch_bounds__(256) pack_segments_kernel(const int64_t* __res
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// add_layernorm_train: the training-mode residual block tail,
+//   out = sum_g w[b,g] * LN_g(residual + dropout(y_g))       (post-norm: query_encoder.py:304-305, 386-387, 449-450)
+// with w[b,g] = 1/G (plain mean over the parallel memories, :153) or the memory-dropout weights keep[b,g] / #kept[b]
+// (:145-152).  dropout(y) = y * keep / (1 - p), keep from the counter RNG at element (g*R + row)*D + col.
+// Same outputs as pq3d_add_layernorm.  One warp per row.
+// ------------------------------------------------------------------------------------------------
+constexpr int kLnTrainMaxGroups = 4;
+
+template <int NV>
+__global__ void add_layernorm_train_kernel(const float* __restrict__ y, int64_t y_group_stride,
+                                           const float* __restrict__ residual, const float* __restrict__ gamma,
+                                           const float* __restrict__ beta, int G, float eps, int R,
+                                           const float* __restrict__ pos, float* __restrict__ out_f32,
+                                           __nv_bfloat16* __restrict__ out_bf16, __nv_bfloat16* __restrict__ out_pos_bf16,
+                                           uint32_t drop_thresh, float drop_scale, const uint32_t* __restrict__ seed,
+                                           uint32_t site, const float* __restrict__ row_w, int rows_per_scene) {
+  pdl_sync();
+  constexpr int D = NV * 128;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= R) return;
+  const int lane = threadIdx.x & 31;
+  const int64_t base = static_cast<int64_t>(row) * D;
+  const uint32_t key = drop_thresh != 0 ? drop_key(__ldg(seed), site) : 0u;
+  float4 res[NV], acc[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    acc[i] = make_float4(0, 0, 0, 0);
+    res[i] = residual != nullptr ? __ldg(reinterpret_cast<const float4*>(residual + base) + i * 32 + lane)
+                                 : make_float4(0, 0, 0, 0);
+  }
+  constexpr float inv_d = 1.f / static_cast<float>(D);
+  for (int g = 0; g < G; ++g) {
+    const float w = row_w != nullptr ? __ldg(row_w + (row / rows_per_scene) * G + g) : 1.f / static_cast<float>(G);
+    float4 x[NV];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      float4 v = y != nullptr ? __ldg(reinterpret_cast<const float4*>(y + g * y_group_stride + base) + i * 32 + lane)
+                              : make_float4(0, 0, 0, 0);
+      if (drop_thresh != 0) {
+        const uint32_t e = static_cast<uint32_t>((static_cast<int64_t>(g) * R + row) * D + (i * 32 + lane) * 4);
+        v.x = drop_keep(key, e, drop_thresh) ? v.x * drop_scale : 0.f;
+        v.y = drop_keep(key, e + 1, drop_thresh) ? v.y * drop_scale : 0.f;
+        v.z = drop_keep(key, e + 2, drop_thresh) ? v.z * drop_scale : 0.f;
+        v.w = drop_keep(key, e + 3, drop_thresh) ? v.w * drop_scale : 0.f;
+      }
+      x[i] = make_float4(res[i].x + v.x, res[i].y + v.y, res[i].z + v.z, res[i].w + v.w);
+      sum += (x[i].x + x[i].y) + (x[i].z + x[i].w);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum * inv_d;
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const float a = x[i].x - mean, b = x[i].y - mean, c = x[i].z - mean, d = x[i].w - mean;
+      sq += (a * a + b * b) + (c * c + d * d);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    const float rstd = rsqrtf(sq * inv_d + eps);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma + g * D) + i * 32 + lane);
+      const float4 be = __ldg(reinterpret_cast<const float4*>(beta + g * D) + i * 32 + lane);
+      acc[i].x += w * ((x[i].x - mean) * rstd * ga.x + be.x);
+      acc[i].y += w * ((x[i].y - mean) * rstd * ga.y + be.y);
+      acc[i].z += w * ((x[i].z - mean) * rstd * ga.z + be.z);
+      acc[i].w += w * ((x[i].w - mean) * rstd * ga.w + be.w);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const float4 o = acc[i];
+    const int64_t off = base + (i * 32 + lane) * 4;
+    if (out_f32 != nullptr) *reinterpret_cast<float4*>(out_f32 + off) = o;
+    if (out_bf16 != nullptr)
+      *reinterpret_cast<uint2*>(out_bf16 + off) = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
+    if (out_pos_bf16 != nullptr) {
+      const float4 pp = __ldg(reinterpret_cast<const float4*>(pos + base) + i * 32 + lane);
+      *reinterpret_cast<uint2*>(out_pos_bf16 + off) =
+          make_uint2(pack_bf16x2(o.x + pp.x, o.y + pp.y), pack_bf16x2(o.z + pp.z, o.w + pp.w));
+    }
+  }
+}
+
+// x = dropout(x) in place on a bf16 array (the FFN's hidden activations, query_encoder.py:384): element idx kept with
+// probability 1 - p and scaled by 1 / (1 - p).  n multiple of 8.
+__global__ void dropout_bf16_kernel(__nv_bfloat16* __restrict__ x, int64_t n8, uint32_t drop_thresh, float drop_scale,
+                                    const uint32_t* __restrict__ seed, uint32_t site) {
+  pdl_sync();
+  const uint32_t key = drop_key(__ldg(seed), site);
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n8;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    uint4 u = reinterpret_cast<uint4*>(x)[i];
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+    const uint32_t e = static_cast<uint32_t>(i * 8);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float a = drop_keep(key, e + 2 * j, drop_thresh) ? __bfloat162float(h[j].x) * drop_scale : 0.f;
+      const float b = drop_keep(key, e + 2 * j + 1, drop_thresh) ? __bfloat162float(h[j].y) * drop_scale : 0.f;
+      h[j] = __floats2bfloat162_rn(a, b);
+    }
+    reinterpret_cast<uint4*>(x)[i] = u;
+  }
+}
+
 }  // namespace pq3d
 
 using namespace pq3d;
@@ -110,5 +218,54 @@ extern "C" int pq3d_pack_segments(const int64_t* segs_dev, const int32_t* tile_s
   PQ3D_CHECK_ARG(segs_dev && tile_start_dev && n_seg > 0 && total_tiles > 0, "pq3d_pack_segments: bad argument");
   PQ3D_CUDA(launch_kernel(pack_segments_kernel, dim3(total_tiles), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream),
                           segs_dev, tile_start_dev, n_seg));
+  return PQ3D_OK;
+}
+
+extern "C" int pq3d_add_layernorm_train(const float* y, int64_t y_group_stride, const float* residual, const float* gamma,
+                                        const float* beta, int G, float eps, int R, int D, const float* pos,
+                                        float* out_f32, void* out_bf16, void* out_pos_bf16, float drop_p,
+                                        const uint32_t* seed_dev, uint32_t site, const float* row_w, int rows_per_scene,
+                                        void* stream) {
+  PQ3D_CHECK_ARG((y || residual) && gamma && beta, "pq3d_add_layernorm_train: null argument");
+  PQ3D_CHECK_ARG(G >= 1 && G <= kLnTrainMaxGroups && R > 0 && D % 128 == 0 && D <= 1024,
+                 "pq3d_add_layernorm_train: bad shape G=%d R=%d D=%d", G, R, D);
+  PQ3D_CHECK_ARG(drop_p >= 0.f && drop_p < 1.f && (drop_p == 0.f || seed_dev != nullptr),
+                 "pq3d_add_layernorm_train: dropout needs p in [0,1) and a device seed");
+  PQ3D_CHECK_ARG(row_w == nullptr || (rows_per_scene > 0 && R % rows_per_scene == 0),
+                 "pq3d_add_layernorm_train: row weights need rows_per_scene dividing R");
+  PQ3D_CHECK_ARG(out_pos_bf16 == nullptr || pos != nullptr, "pq3d_add_layernorm_train: out_pos_bf16 needs pos");
+  PQ3D_CHECK_ARG(static_cast<int64_t>(G) * R * D < (int64_t(1) << 32), "pq3d_add_layernorm_train: too many elements");
+  const int warps = 2;
+  const dim3 grid((R + warps - 1) / warps), block(warps * 32);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const uint32_t thresh = drop_p > 0.f ? drop_threshold(drop_p) : 0u;
+  const float scale = 1.f / (1.f - drop_p);
+  cudaError_t err = cudaSuccess;
+#define PQ3D_LNT_CASE(NV)                                                                                            \
+  case NV:                                                                                                           \
+    err = launch_kernel(add_layernorm_train_kernel<NV>, grid, block, 0, st, y, y_group_stride, residual, gamma, beta, \
+                        G, eps, R, pos, out_f32, reinterpret_cast<__nv_bfloat16*>(out_bf16),                         \
+                        reinterpret_cast<__nv_bfloat16*>(out_pos_bf16), thresh, scale, seed_dev, site, row_w,        \
+                        rows_per_scene);                                                                             \
+    break;
+  switch (D / 128) {
+    PQ3D_LNT_CASE(1) PQ3D_LNT_CASE(2) PQ3D_LNT_CASE(3) PQ3D_LNT_CASE(4) PQ3D_LNT_CASE(5) PQ3D_LNT_CASE(6)
+    PQ3D_LNT_CASE(7) PQ3D_LNT_CASE(8)
+  }
+#undef PQ3D_LNT_CASE
+  PQ3D_CUDA(err);
+  return PQ3D_OK;
+}
+
+extern "C" int pq3d_dropout_bf16(void* x, int64_t n, float drop_p, const uint32_t* seed_dev, uint32_t site,
+                                 void* stream) {
+  PQ3D_CHECK_ARG(x && seed_dev && n > 0 && n % 8 == 0 && n < (int64_t(1) << 32) && drop_p > 0.f && drop_p < 1.f &&
+                     (reinterpret_cast<uintptr_t>(x) & 15) == 0,
+                 "pq3d_dropout_bf16: bad argument (n multiple of 8, 0 < p < 1, 16-byte aligned)");
+  int64_t blocks = (n / 8 + 255) / 256;
+  if (blocks > sm_count() * 8) blocks = sm_count() * 8;
+  PQ3D_CUDA(launch_kernel(dropout_bf16_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0,
+                          reinterpret_cast<cudaStream_t>(stream), reinterpret_cast<__nv_bfloat16*>(x), n / 8,
+                          drop_threshold(drop_p), 1.f / (1.f - drop_p), seed_dev, site));
   return PQ3D_OK;
 }

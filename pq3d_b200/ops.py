@@ -112,8 +112,10 @@ class AttnMemory:
 
 def attention(Q: torch.Tensor, q_mem_stride: int, mems: Sequence[AttnMemory], O: torch.Tensor, o_mem_stride: int,
               B: int, H: int, Nq: int, zero_attn: bool, score_bias: Optional[torch.Tensor] = None,
-              stats: Optional[Tuple[torch.Tensor, torch.Tensor]] = None) -> torch.Tensor:
-    """score_bias: optional fp32 (B, H, Nq, ld) added to the scores (ld = keys padded to a multiple of 128)."""
+              stats: Optional[Tuple[torch.Tensor, torch.Tensor]] = None, drop_p: float = 0.0,
+              seed: Optional[torch.Tensor] = None, sites: Optional[Sequence[int]] = None) -> torch.Tensor:
+    """score_bias: optional fp32 (B, H, Nq, ld) added to the scores (ld = keys padded to a multiple of 128).
+    drop_p > 0 (training): dropout on the probabilities, seed = device int32 tensor, sites = one stream id per memory."""
     _chk(Q, bf16, "Q", 2)
     _chk(O, bf16, "O")
     n = len(mems)
@@ -132,7 +134,13 @@ def attention(Q: torch.Tensor, q_mem_stride: int, mems: Sequence[AttnMemory], O:
             raise ValueError("score_bias must be contiguous (B, H, Nq, ld)")
         bias_ld = score_bias.shape[3]
     has_mask = any(m.mask_bits is not None for m in mems)
-    rc = _lib.lib().pq3d_attention_fwd(
+    train_args = ()
+    fn = _lib.lib().pq3d_attention_fwd
+    if drop_p > 0.0:
+        _chk(seed, torch.int32, "seed")
+        fn = _lib.lib().pq3d_attention_fwd_train
+        train_args = (float(drop_p), seed.data_ptr(), (C.c_uint32 * n)(*sites))
+    rc = fn(
         n, Q.data_ptr(), Q.stride(0), q_mem_stride,
         vp(*[m.K.data_ptr() for m in mems]), i64(*[m.K.stride(0) for m in mems]), i64(*[m.k_col0 for m in mems]),
         vp(*[m.Vt.data_ptr() for m in mems]), i64(*[m.Vt.stride(0) for m in mems]), i64(*[m.vt_row0 for m in mems]),
@@ -144,7 +152,7 @@ def attention(Q: torch.Tensor, q_mem_stride: int, mems: Sequence[AttnMemory], O:
         vp(*[_p(m.kv_tiles) for m in mems]) if any(m.kv_tiles is not None for m in mems) else None,
         O.data_ptr(), O.stride(-2), o_mem_stride, B, H, Nq, int(zero_attn), _p(score_bias), bias_ld,
         None if stats is None else stats[0].data_ptr(), None if stats is None else stats[1].data_ptr(),
-        0 if stats is None else B * H * Nq, _stream())
+        0 if stats is None else B * H * Nq, *train_args, _stream())
     _lib.check(rc, "pq3d_attention_fwd")
     _count()
     return O
@@ -317,25 +325,28 @@ def transpose_cast(x: torch.Tensor, out_t: Optional[torch.Tensor], out_c: Option
     _count()
 
 
-def colsum(x: torch.Tensor, out: torch.Tensor, accumulate: bool = False, gate: Optional[torch.Tensor] = None):
+def colsum(x: torch.Tensor, out: torch.Tensor, accumulate: bool = False, gate: Optional[torch.Tensor] = None,
+           scale: float = 1.0):
     """out[c] (+)= sum_r x[r, c] * (gate[r, c] > 0); x fp32 or bf16 2-D view with unit inner stride."""
     if x.dtype not in (torch.float32, bf16) or x.ndim != 2 or x.stride(1) != 1:
         raise TypeError("colsum input must be a 2-D fp32/bf16 view with unit inner stride")
     _chk(out, torch.float32, "out")
     rc = _lib.lib().pq3d_colsum(x.data_ptr(), int(x.dtype == torch.float32), x.stride(0), _p(gate),
                                 0 if gate is None else gate.stride(0), out.data_ptr(), x.shape[0], x.shape[1],
-                                int(accumulate), _stream())
+                                int(accumulate), float(scale), _stream())
     _lib.check(rc, "pq3d_colsum")
     _count()
 
 
 def layernorm_bwd(y, residual, gamma, d_out, eps, R, D, G=1, y_group_stride=0, d_x=None, dx_group_stride=0, d_res=None,
-                  d_gamma=None, d_beta=None, d_x16=None):
+                  d_gamma=None, d_beta=None, d_x16=None, drop_p=0.0, seed=None, site=0, row_w=None, rows_per_scene=0):
     if d_x16 is not None:
         _chk(d_x16, bf16, "d_x16")
+    if row_w is not None:
+        _chk(row_w, torch.float32, "row_w")
     rc = _lib.lib().pq3d_layernorm_bwd(_p(y), y_group_stride, _p(residual), gamma.data_ptr(), d_out.data_ptr(), G,
                                        float(eps), R, D, _p(d_x), dx_group_stride, _p(d_x16), _p(d_res), _p(d_gamma),
-                                       _p(d_beta), _stream())
+                                       _p(d_beta), float(drop_p), _p(seed), site, _p(row_w), rows_per_scene, _stream())
     _lib.check(rc, "pq3d_layernorm_bwd")
     _count()
 
@@ -381,7 +392,8 @@ def pack_segments(segs: torch.Tensor, tile_start: torch.Tensor, total_tiles: int
 
 
 def attention_bwd(Q, q_col0, dO, do_col0, K, k_col0, V, v_col0, S, S_pitch, stat_m, stat_l, delta, dK, dk_col0, dV,
-                  dv_col0, dQ32, dq_col0, B, H, Nq, *, mask_bits=None, mask_strides=(0, 0, 0), bias=None, dS_out=None):
+                  dv_col0, dQ32, dq_col0, B, H, Nq, *, mask_bits=None, mask_strides=(0, 0, 0), bias=None, dS_out=None,
+                  drop_p=0.0, seed=None, site=0):
     """Fused attention backward (pq3d_attention_bwd).  Q, dO, K, V, dK, dV: 2-D bf16 with unit inner stride; dQ32: 2-D
     fp32, accumulated (zero-fill first); stats / delta: fp32 (B, H, Nq)."""
     for t, nm in ((Q, "Q"), (dO, "dO"), (K, "K"), (V, "V"), (dK, "dK"), (dV, "dV")):
@@ -406,6 +418,35 @@ def attention_bwd(Q, q_col0, dO, do_col0, K, k_col0, V, v_col0, S, S_pitch, stat
         V.data_ptr(), V.stride(0), v_col0, S, S_pitch, _p(mask_bits), *mask_strides, _p(bias), bias_ld,
         stat_m.data_ptr(), stat_l.data_ptr(), delta.data_ptr(), dK.data_ptr(), dK.stride(0), dk_col0, dV.data_ptr(),
         dV.stride(0), dv_col0, dQ32.data_ptr(), dQ32.stride(0), dq_col0, _p(dS_out), ds_ld, B, H, Nq, float(Q_SCALE),
-        _stream())
+        float(drop_p), _p(seed), site, _stream())
     _lib.check(rc, "pq3d_attention_bwd")
+    _count()
+
+
+def add_layernorm_train(y, residual, gamma, beta, eps, R, D, G=1, y_group_stride=0, pos=None, out_f32=None, out_bf16=None,
+                        out_pos_bf16=None, drop_p=0.0, seed=None, site=0, row_w=None, rows_per_scene=0):
+    """Training-mode add_layernorm: dropout on y (counter RNG, device seed tensor) and per-scene memory weights."""
+    for t, nm in ((y, "y"), (residual, "residual"), (gamma, "gamma"), (beta, "beta"), (pos, "pos"), (out_f32, "out_f32"),
+                  (row_w, "row_w")):
+        if t is not None:
+            _chk(t, torch.float32, nm)
+    for t, nm in ((out_bf16, "out_bf16"), (out_pos_bf16, "out_pos_bf16")):
+        if t is not None:
+            _chk(t, bf16, nm)
+    if seed is not None:
+        _chk(seed, torch.int32, "seed")
+    rc = _lib.lib().pq3d_add_layernorm_train(_p(y), y_group_stride, _p(residual), gamma.data_ptr(), beta.data_ptr(), G,
+                                             float(eps), R, D, _p(pos), _p(out_f32), _p(out_bf16), _p(out_pos_bf16),
+                                             float(drop_p), _p(seed), site, _p(row_w), rows_per_scene, _stream())
+    _lib.check(rc, "pq3d_add_layernorm_train")
+    _count()
+
+
+def dropout_bf16(x: torch.Tensor, drop_p: float, seed: torch.Tensor, site: int):
+    _chk(x, bf16, "x")
+    _chk(seed, torch.int32, "seed")
+    if not x.is_contiguous():
+        raise ValueError("dropout_bf16 works in place on a contiguous tensor")
+    rc = _lib.lib().pq3d_dropout_bf16(x.data_ptr(), x.numel(), float(drop_p), seed.data_ptr(), site, _stream())
+    _lib.check(rc, "pq3d_dropout_bf16")
     _count()

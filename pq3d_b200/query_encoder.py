@@ -386,7 +386,9 @@ class QueryMaskEncoder(nn.Module):
         self._packed_ver = None
         self._ws: Dict[tuple, dict] = {}
         self.use_cuda_graph = True
-        self.train_dropout = 0.1      # the reference's sublayer dropout; the training path requires 0.0 (no RNG kernels)
+        self.train_dropout = 0.1      # QueryEncoderLayer(dropout=0.1): sublayer / attention-probability / FFN dropout
+        self._drop_seed = None
+        self.last_memory_keep: List[torch.Tensor] = []
         # K / V^T of all layers are hoisted into one grouped GEMM per forward.  Projecting layer by layer (so a
         # layer's 75 MB stays L2-resident for its attention) was measured at config 3: the attention kernel did not
         # speed up (it is bound by TMEM->register bandwidth, not HBM) and the narrower GEMMs cost +63 us/step, so
@@ -397,7 +399,14 @@ class QueryMaskEncoder(nn.Module):
 
     # ---- structure -> cross-attention program ------------------------------------------------
     def _active(self) -> List[str]:
+        if self.training:
+            return list(self.memories)                                              # training uses every memory, :156
         return [m for m in self.memories if m not in self.drop_memories_test]      # eval, :156
+
+    def _group_is_parallel(self, gi: int) -> bool:
+        """Whether group gi of `_program()` is a parallel_ca call (the only place memory dropout applies)."""
+        return (self.structure == "parallel" or (self.structure == "mixed" and gi == 0)
+                or (self.structure == "gate" and gi == 1))
 
     def _program(self) -> List[Tuple[str, ...]]:
         act = self._active()
@@ -421,7 +430,8 @@ class QueryMaskEncoder(nn.Module):
         one kernel launch whenever a parameter's version moved, after a training step (`stale`), or always in
         training (fused optimizers update parameters without bumping version counters)."""
         params = list(self.parameters())
-        key = (str(device), tuple(self.drop_memories_test), tuple(p.data_ptr() for p in params))
+        key = (str(device), tuple(self.drop_memories_test) if not self.training else (),
+               tuple(p.data_ptr() for p in params))
         ver = tuple(p._version for p in params)
         pk = self._packed
         if pk is None or self._packed_key != key or (train and not pk.train):

@@ -22,7 +22,7 @@ from typing import Dict, List, Optional, Tuple
 
 import torch
 
-from . import ops
+from . import ops, rng
 
 bf16 = torch.bfloat16
 f32 = torch.float32
@@ -74,6 +74,21 @@ def forward(enc, query, query_pos, query_masks, mems: List[Tuple[str, torch.Tens
     pk = enc.packed(dev, train=True)
     program = [g for g in enc._program() if len(g) > 0]
     sv: Dict = dict(B=B, N=N, D=D, H=H, L=L, R=R, program=program, pk=pk, layers=[], mems={})
+    # train-time dropout (QueryEncoderLayer(dropout=0.1), query_encoder.py:97): counter RNG keyed by a per-forward device
+    # seed, so the backward regenerates every mask and a CUDA-graph replay draws fresh ones
+    p_drop = float(enc.train_dropout) if enc.training else 0.0
+    p_mem = float(enc.memory_dropout) if enc.training else 0.0
+    seed = None
+    if p_drop > 0.0:
+        if N > 128:
+            raise NotImplementedError("pq3d_b200 training path: dropout needs the fused attention backward (N <= 128 "
+                                      "queries); set `encoder.train_dropout = 0.0` for more queries")
+        if getattr(enc, "_drop_seed", None) is None or enc._drop_seed.device != dev:
+            enc._drop_seed = torch.randint(0, 2 ** 31 - 1, (1,), dtype=torch.int32, device=dev)
+        enc._drop_seed.add_(0x3C6EF35F)
+        seed = enc._drop_seed.clone()
+    sv.update(p_drop=p_drop, seed=seed)
+    spatial = enc.spatial_selfattn
 
     ws: Dict = {}
     for name, feat, mask, pos in mems:
@@ -108,10 +123,17 @@ def forward(enc, query, query_pos, query_masks, mems: List[Tuple[str, torch.Tens
     sv.update(qpos=qpos, qbits=qbits, sbias=sbias, pw=pw)
     Np = ops.pad8(N)
 
+    def add_ln(y, res, w, G, site_id, row_w=None, **outs):
+        if p_drop > 0.0 or row_w is not None:
+            ops.add_layernorm_train(y, res, w["gamma"], w["beta"], w["eps"], R, D, G=G, y_group_stride=R * D,
+                                    drop_p=p_drop, seed=seed, site=site_id, row_w=row_w, rows_per_scene=N, **outs)
+        else:
+            ops.add_layernorm(y, res, w["gamma"], w["beta"], w["eps"], R, D, G=G, y_group_stride=R * D, **outs)
+
     for i in range(L):
         lw = pk.layers[i]
         lay = dict(groups=[])
-        for grp in program:
+        for gi, grp in enumerate(program):
             g = len(grp)
             w = lw["groups"][grp]
             Q = _e((R, g * D), bf16, dev)
@@ -120,14 +142,23 @@ def forward(enc, query, query_pos, query_masks, mems: List[Tuple[str, torch.Tens
             st_m, st_l = _e((g, B, H, N), f32, dev), _e((g, B, H, N), f32, dev)
             am = [ops.AttnMemory(sv["mems"][m].K, i * D, sv["mems"][m].Vt, i * D, sv["mems"][m].S, sv["mems"][m].Sp,
                                  sv["mems"][m].bits, *sv["mems"][m].strides, kv_tiles=sv["mems"][m].tiles) for m in grp]
-            ops.attention(Q, D, am, O, R * D, B, H, N, True, stats=(st_m, st_l))
+            psites = [rng.site(i, rng.SITE_CA_PROBS + enc.memories.index(m)) for m in grp]
+            ops.attention(Q, D, am, O, R * D, B, H, N, True, stats=(st_m, st_l), drop_p=p_drop, seed=seed, sites=psites)
             y = _e((g, R, D), f32, dev)
             ops.linear(O.view(g * R, D), w["wo"], y, M=R, N=D, K=D, bias=w["bo"], bias_group_stride=D, groups=g,
                        a_group_rows=R, w_group_rows=D, ldc=D, c_group_stride=R * D)
+            # train-time memory dropout of a parallel group (query_encoder.py:145-152): keep each (scene, memory) with
+            # probability 1 - p, keep all when none survived, average over the survivors
+            row_w = None
+            if p_mem > 0.0 and g > 1 and enc._group_is_parallel(gi):
+                keep = torch.rand(B, g, device=dev) > p_mem
+                keep = torch.logical_or(keep, (keep.sum(dim=1) == 0).unsqueeze(-1))
+                row_w = (keep.float() / keep.sum(dim=1, keepdim=True).float()).contiguous()
+                enc.last_memory_keep.append(keep)
             q_new, xq_new, xv_new = _e((R, D), f32, dev), _e((R, D), bf16, dev), _e((R, D), bf16, dev)
-            ops.add_layernorm(y, q32, w["gamma"], w["beta"], w["eps"], R, D, G=g, y_group_stride=R * D, pos=qpos,
-                              out_f32=q_new, out_bf16=xv_new, out_pos_bf16=xq_new)
-            lay["groups"].append(dict(grp=grp, xq=xq, Q=Q, O=O, m=st_m, l=st_l, y=y, res=q32))
+            add_ln(y, q32, w, g, rng.site(i, rng.SITE_CA_SUBLAYER + gi), row_w, pos=qpos, out_f32=q_new, out_bf16=xv_new,
+                   out_pos_bf16=xq_new)
+            lay["groups"].append(dict(grp=grp, gi=gi, xq=xq, Q=Q, O=O, m=st_m, l=st_l, y=y, res=q32, row_w=row_w))
             q32, xq, xv = q_new, xq_new, xv_new
         sa = lw["sa"]
         QK = _e((R, 2 * D), bf16, dev)
@@ -138,22 +169,28 @@ def forward(enc, query, query_pos, query_masks, mems: List[Tuple[str, torch.Tens
         Os = _e((1, R, D), bf16, dev)
         s_m, s_l = _e((1, B, H, N), f32, dev), _e((1, B, H, N), f32, dev)
         mem = ops.AttnMemory(QK, D, Vt, 0, N, N, qbits, qbits.stride(0), 0, 0, Vt_pitch=Np)
-        ops.attention(QK, 0, [mem], Os, R * D, B, H, N, False, None if sbias is None else sbias[i], stats=(s_m, s_l))
+        # MultiHeadAttentionSpatial applies no dropout to its probabilities (transformers.py:158-240: the ctor's
+        # `dropout` is unused); the stock MHA of SelfAttentionLayer does (query_encoder.py:195)
+        sa_p = 0.0 if spatial else p_drop
+        ops.attention(QK, 0, [mem], Os, R * D, B, H, N, False, None if sbias is None else sbias[i], stats=(s_m, s_l),
+                      drop_p=sa_p, seed=seed, sites=[rng.site(i, rng.SITE_SA_PROBS)])
         ys = _e((R, D), f32, dev)
         ops.linear(Os.view(R, D), sa["wo"], ys, M=R, N=D, K=D, bias=sa["bo"])
         q_new, xv_new = _e((R, D), f32, dev), _e((R, D), bf16, dev)
-        ops.add_layernorm(ys, q32, sa["gamma"], sa["beta"], sa["eps"], R, D, out_f32=q_new, out_bf16=xv_new)
+        add_ln(ys, q32, sa, 1, rng.site(i, rng.SITE_SA_SUBLAYER), out_f32=q_new, out_bf16=xv_new)
         lay["sa"] = dict(xq=xq, xv=xv, QK=QK, Vt=Vt, O=Os, m=s_m, l=s_l, y=ys, res=q32)
         q32, xv = q_new, xv_new
         ff = lw["ffn"]
         F = ff["F"]
         h = _e((R, F), bf16, dev)
         ops.linear(xv, ff["w1"], h, M=R, N=F, K=D, bias=ff["b1"], relu=True)
+        if p_drop > 0.0:                 # dropout(relu(linear1(x))) (query_encoder.py:384); h is saved dropped + rescaled
+            ops.dropout_bf16(h, p_drop, seed, rng.site(i, rng.SITE_FFN_HIDDEN))
         yf = _e((R, D), f32, dev)
         ops.linear(h, ff["w2"], yf, M=R, N=D, K=F, bias=ff["b2"])
         q_new, xq_new, xv_new = _e((R, D), f32, dev), _e((R, D), bf16, dev), _e((R, D), bf16, dev)
-        ops.add_layernorm(yf, q32, ff["gamma"], ff["beta"], ff["eps"], R, D, pos=qpos, out_f32=q_new, out_bf16=xv_new,
-                          out_pos_bf16=xq_new)
+        add_ln(yf, q32, ff, 1, rng.site(i, rng.SITE_FFN_SUBLAYER), pos=qpos, out_f32=q_new, out_bf16=xv_new,
+               out_pos_bf16=xq_new)
         lay["ffn"] = dict(xv=xv, h=h, y=yf, res=q32)
         q32, xq, xv = q_new, xq_new, xv_new
         sv["layers"].append(lay)
@@ -215,12 +252,16 @@ class _Bwd:
         else:
             self.grads[name] = g
 
-    def tcast(self, x, rows, cols, want_c=False, gate=None):
+    def tcast(self, x, rows, cols, want_c=False, gate=None, scale=1.0):
         """x [rows, cols] (fp32/bf16) -> (bf16 x^T [cols, pad64(rows)], bf16 copy or None)."""
         xt = _e((cols, ops.pad64(rows)), bf16, self.dev)
         xc = _e((rows, cols), bf16, self.dev) if want_c else None
-        ops.transpose_cast(x, xt, xc, gate=gate)
+        ops.transpose_cast(x, xt, xc, gate=gate, scale=scale)
         return xt, xc
+
+    def drop(self, i, kind):
+        """kwargs of the dropout stream `kind` of layer i for layernorm_bwd / attention_bwd."""
+        return dict(drop_p=self.sv["p_drop"], seed=self.sv["seed"], site=rng.site(i, kind))
 
     def wgrad(self, dyT, xT, n_out, n_in, out=None, groups=1, c_group_stride=0):
         """dW [n_out, n_in] = dy^T x from the K-major transposes (contraction over padded rows).  With groups > 1,
@@ -237,9 +278,9 @@ class _Bwd:
         ops.linear(dy16, w_t, dx, M=rows, N=n_in, K=n_out)
         return dx
 
-    def colsum(self, x, gate=None):
+    def colsum(self, x, gate=None, scale=1.0):
         out = _e((x.shape[1],), f32, self.dev)
-        ops.colsum(x, out, gate=gate)
+        ops.colsum(x, out, gate=gate, scale=scale)
         return out
 
     # ---- attention backward for one (scene batch, key set) -----------------------------------------
@@ -274,13 +315,15 @@ class _Bwd:
         return self.N <= 128 and getattr(self.enc, "fused_attn_bwd", True)
 
     def attention_bwd_fused(self, Q, q_col0, dO, O2d, K, k_col0, V, v_col0, S, S_pitch, st_m, st_l, dK, dk_col0, dV,
-                            dv_col0, dQ32, dq_col0, bias=None, mask_bits=None, mask_strides=(0, 0, 0), dS_out=None):
+                            dv_col0, dQ32, dq_col0, bias=None, mask_bits=None, mask_strides=(0, 0, 0), dS_out=None,
+                            drop=None):
         """One pq3d_attention_bwd launch (+ the row-dot delta): scores are recomputed and consumed on chip."""
         B, H, N = self.B, self.H, self.N
         delta = _e((B, H, N), f32, self.dev)
         ops.attn_delta(dO, O2d, delta, B, H, N)
         ops.attention_bwd(Q, q_col0, dO, 0, K, k_col0, V, v_col0, S, S_pitch, st_m, st_l, delta, dK, dk_col0, dV, dv_col0,
-                          dQ32, dq_col0, B, H, N, mask_bits=mask_bits, mask_strides=mask_strides, bias=bias, dS_out=dS_out)
+                          dQ32, dq_col0, B, H, N, mask_bits=mask_bits, mask_strides=mask_strides, bias=bias, dS_out=dS_out,
+                          **(drop or {}))
 
     # ---- blocks ---------------------------------------------------------------------------------------
     def ffn_bwd(self, i, s, d_out):
@@ -291,7 +334,11 @@ class _Bwd:
         d_y = _e((R, D), f32, dev)
         dg, db = _z((1, D), f32, dev), _z((1, D), f32, dev)
         d_y16 = _e((R, D), bf16, dev)
-        ops.layernorm_bwd(s["y"], s["res"], ff["gamma"], d_out, ff["eps"], R, D, d_x=d_y, d_gamma=dg, d_beta=db, d_x16=d_y16)
+        p_drop = self.sv["p_drop"]
+        kscale = 1.0 / (1.0 - p_drop)
+        d_res = _e((R, D), f32, dev) if p_drop > 0.0 else d_y        # without dropout the two gradients coincide
+        ops.layernorm_bwd(s["y"], s["res"], ff["gamma"], d_out, ff["eps"], R, D, d_x=d_y, d_gamma=dg, d_beta=db, d_x16=d_y16,
+                          d_res=d_res if p_drop > 0.0 else None, **self.drop(i, rng.SITE_FFN_SUBLAYER))
         self.acc(pre + "norm.weight", dg[0]); self.acc(pre + "norm.bias", db[0])
         with self.on(self.side, d_y, dg, db):
             self.acc(pre + "linear2.bias", self.colsum(d_y))
@@ -299,15 +346,15 @@ class _Bwd:
             hT, _ = self.tcast(s["h"], R, F)
             self.acc(pre + "linear2.weight", self.wgrad(d_yT, hT, D, F))
         d_h = self.dgrad(d_y16, pk.T(ff["w2"]), F)
-        d_preT, d_pre16 = self.tcast(d_h, R, F, want_c=True, gate=s["h"])
+        d_preT, d_pre16 = self.tcast(d_h, R, F, want_c=True, gate=s["h"], scale=kscale)   # relu and hidden-dropout gates
         with self.on(self.side, d_h, d_preT, d_y16):
-            self.acc(pre + "linear1.bias", self.colsum(d_h, gate=s["h"]))
+            self.acc(pre + "linear1.bias", self.colsum(d_h, gate=s["h"], scale=kscale))
             xvT, _ = self.tcast(s["xv"], R, D)
             self.acc(pre + "linear1.weight", self.wgrad(d_preT, xvT, F, D))
         d_xv = self.dgrad(d_pre16, pk.T(ff["w1"]), D)
         d_in = _e((R, D), f32, dev)
-        ops.add3(d_y, d_xv, None, d_in)
-        self.keep += [d_pre16, d_xv]
+        ops.add3(d_res, d_xv, None, d_in)
+        self.keep += [d_pre16, d_xv, d_res]
         return d_in
 
     def sa_bwd(self, i, s, d_out, d_pos):
@@ -319,7 +366,10 @@ class _Bwd:
         d_y = _e((R, D), f32, dev)
         dg, db = _z((1, D), f32, dev), _z((1, D), f32, dev)
         d_y16 = _e((R, D), bf16, dev)
-        ops.layernorm_bwd(s["y"], s["res"], sa["gamma"], d_out, sa["eps"], R, D, d_x=d_y, d_gamma=dg, d_beta=db, d_x16=d_y16)
+        p_drop = self.sv["p_drop"]
+        d_res = _e((R, D), f32, dev) if p_drop > 0.0 else d_y
+        ops.layernorm_bwd(s["y"], s["res"], sa["gamma"], d_out, sa["eps"], R, D, d_x=d_y, d_gamma=dg, d_beta=db, d_x16=d_y16,
+                          d_res=d_res if p_drop > 0.0 else None, **self.drop(i, rng.SITE_SA_SUBLAYER))
         self.acc(pre + "norm.weight", dg[0]); self.acc(pre + "norm.bias", db[0])
         O2d = s["O"].view(R, D)
         if not spatial:
@@ -349,7 +399,8 @@ class _Bwd:
             dQ32 = _z((R, D), f32, dev)
             dS = _e((B, H, N, ld), bf16, dev) if spatial else None
             self.attention_bwd_fused(QK, 0, dO, O2d, QK, D, V, 0, N, N, s["m"][0], s["l"][0], dQK, D, dV, 0, dQ32, 0,
-                                     bias=bias, mask_bits=qbits, mask_strides=(qbits.stride(0), 0, 0), dS_out=dS)
+                                     bias=bias, mask_bits=qbits, mask_strides=(qbits.stride(0), 0, 0), dS_out=dS,
+                                     drop=None if (spatial or p_drop == 0.0) else self.drop(i, rng.SITE_SA_PROBS))
             ops.transpose_cast(dQ32, None, dQK[:, :D])
             self.keep.append(dQ32)
         else:
@@ -382,7 +433,8 @@ class _Bwd:
         d_xq = self.dgrad(dQK, pk.T(sa["wqk"]), D)
         d_xv = self.dgrad(dV, pk.T(sa["wv"]), D)
         d_in = _e((R, D), f32, dev)
-        ops.add3(d_y, d_xq, d_xv, d_in)
+        ops.add3(d_res, d_xq, d_xv, d_in)
+        self.keep.append(d_res)
         with self.on(self.side, d_xq):
             ops.add3(d_pos, d_xq, None, d_pos)
         self.keep += [d_xq, d_xv, V, Ktp]
@@ -399,7 +451,8 @@ class _Bwd:
         dg, db = _z((g, D), f32, dev), _z((g, D), f32, dev)
         d_y16 = _e((g, R, D), bf16, dev)
         ops.layernorm_bwd(s["y"], s["res"], w["gamma"], d_out, w["eps"], R, D, G=g, y_group_stride=R * D, d_x=d_y,
-                          dx_group_stride=R * D, d_res=d_res, d_gamma=dg, d_beta=db, d_x16=d_y16)
+                          dx_group_stride=R * D, d_res=d_res, d_gamma=dg, d_beta=db, d_x16=d_y16, row_w=s["row_w"],
+                          rows_per_scene=N, **self.drop(i, rng.SITE_CA_SUBLAYER + s["gi"]))
         fused = self.fused_ok()
         dQ = _z((R, g * D), f32, dev) if fused else _e((R, g * D), bf16, dev)     # fused: fp32, accumulated by atomics
         self.keep += [d_y, dg, db, dQ, d_out]
@@ -425,7 +478,9 @@ class _Bwd:
                 if fused:
                     self.attention_bwd_fused(s["Q"], jj * D, dO, s["O"][jj], st.K, i * D, mg["V"], i * D, S, Sp, s["m"][jj],
                                              s["l"][jj], mg["dK"], i * D, mg["dV"], i * D, dQ, jj * D, mask_bits=st.bits,
-                                             mask_strides=st.strides)
+                                             mask_strides=st.strides,
+                                             drop=None if self.sv["p_drop"] == 0.0 else
+                                             self.drop(i, rng.SITE_CA_PROBS + self.enc.memories.index(m)))
                 else:
                     Qv = _heads(s["Q"], B, N, N, H, jj * D)
                     Kv = _heads(st.K, B, S, Sp, H, i * D)
@@ -556,10 +611,7 @@ def run(enc, input_dict: dict, pairwise_locs):
         raise NotImplementedError("pq3d_b200 training path: structure='gate' is inference-only in this build")
     if enc.num_blocks != 1:
         raise NotImplementedError("pq3d_b200 training path: num_blocks must be 1")
-    if enc.training and (getattr(enc, "train_dropout", 0.1) > 0 or enc.memory_dropout > 0):
-        raise NotImplementedError(
-            "pq3d_b200 training path: dropout / memory dropout kernels are not built — set "
-            "`encoder.train_dropout = 0.0` and memory_dropout=0 (or call .eval()) to train without dropout")
+    enc.last_memory_keep = []          # memory-dropout keep masks of this forward, in (layer, group) order (for tests)
     query, query_masks, query_pos = input_dict["query"]
     names = [m for g in enc._program() for m in g]
     masks, flat = [], []

@@ -51,6 +51,61 @@ def test_state_dict_schema_matches_live_reference():
         assert list(synth.decoder_param_shapes(**kw)) == list(ref)          # same order too
 
 
+class TorchRngTrain:
+    """cfg.train hook that draws every random decision from torch's global RNG in the reference's own order and
+    shapes: F.dropout per call site, torch.rand for the memory-dropout mask."""
+
+    def __init__(self, p, p_mem, spatial):
+        self.p, self.p_mem, self.spatial = p, p_mem, spatial
+
+    def sublayer(self, layer, kind, x):
+        if isinstance(kind, tuple) or (kind == "sa" and not self.spatial):
+            # nn.MultiheadAttention(batch_first=True) returns a transposed view of an (L, B, E) buffer and nn.Dropout
+            # fills its noise in memory order: reproduce that layout so the same draws land on the same elements
+            x = x.transpose(0, 1).contiguous().transpose(0, 1)
+        return torch.nn.functional.dropout(x, self.p, True)
+
+    def probs(self, layer, kind, P):
+        return torch.nn.functional.dropout(P, self.p, True)
+
+    def hidden(self, layer, h):
+        return torch.nn.functional.dropout(h, self.p, True)
+
+    def memory_keep(self, layer, memories, B):
+        return torch.rand(B, len(memories)) > self.p_mem
+
+
+@needs_ref
+@pytest.mark.parametrize("structure,spatial,p_mem", [("mixed", True, 0.6), ("parallel", False, 0.5),
+                                                     ("sequential", True, 0.0)])
+def test_training_mode_matches_live_reference(structure, spatial, p_mem):
+    """module.train(): sublayer / attention-probability / FFN dropout (p = 0.1) and memory dropout.  With the same
+    torch seed the oracle's training branch consumes the RNG exactly like the reference modules do, so outputs AND
+    gradients agree to fp32 rounding."""
+    ns = ref_loader.load()
+    mems = ["mv", "pc", "voxel"] + (["prompt"] if structure != "parallel" else [])
+    w = synth.Workload("t", 2, 13, 37, mems, structure, T=5, num_layers=2, spatial_selfattn=spatial)
+    kw = dict(w.decoder_kwargs(), memory_dropout=p_mem)
+    sd = synth.decoder_state_dict(w, seed=31, sharp=2.0)
+    enc = ns.query_encoder.QueryMaskEncoder(None, **kw).train()
+    enc.load_state_dict(sd, strict=True)
+    inp, pw, _ = synth.make_decoder_inputs(w)
+    torch.manual_seed(77)
+    ref, _, _ = enc(synth.clone_input_dict(inp), pw)
+    ref.square().sum().backward()
+    sdd = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    cfg = O.DecoderCfg(**kw)
+    cfg.train = TorchRngTrain(0.1, p_mem, spatial)
+    torch.manual_seed(77)
+    out, _, _ = O.query_mask_encoder(sdd, cfg, synth.clone_input_dict(inp), pw)
+    out.square().sum().backward()
+    assert (ref - out).abs().max() / ref.abs().max() <= 1e-5
+    gmax = max(float(p_ref.grad.abs().max()) for _, p_ref in enc.named_parameters())
+    for k, p_ref in enc.named_parameters():
+        g = sdd[k].grad       # key biases have an exactly-zero true gradient (softmax shift invariance): global floor
+        assert g is not None and float((g - p_ref.grad).abs().max()) <= 1e-4 * max(float(p_ref.grad.abs().max()), 1e-3 * gmax), k
+
+
 # ---- known-answer properties ---------------------------------------------------------------
 def _one_ca(S=40, N=9, seed=5):
     w = synth.Workload("t", 2, N, S, ["pc"], "parallel", num_layers=1)

@@ -207,3 +207,149 @@ def test_training_trajectory_matches_oracle_eager_and_graphed():
         for a, b in zip(traj["oracle"], traj[mode]):
             assert abs(a - b) <= 1e-2 * abs(a), f"{mode} trajectory leaves the oracle's"
     assert traj["oracle"][-1] < 0.5 * traj["oracle"][0]
+
+
+# ------------------------------------------------------------------------------------------------
+# training mode proper: dropout (p = 0.1) and memory dropout
+# ------------------------------------------------------------------------------------------------
+class KernelRngTrain:
+    """cfg.train hook for the oracle that rebuilds the kernels' keep masks from (seed, site, element index) with the
+    tensor restatement of the counter RNG (pq3d_b200/rng.py) — element indexing as documented in include/pq3d_b200.h."""
+
+    def __init__(self, enc, seed, p, B, N, H):
+        from pq3d_b200 import rng
+        self.rng, self.enc, self.seed, self.p, self.B, self.N, self.H = rng, enc, seed, p, B, N, H
+        self.program = [g for g in enc._program() if len(g) > 0]
+        self.keeps = list(enc.last_memory_keep)
+
+    def _apply(self, x, keep):
+        return x * keep.to(x.dtype) / (1.0 - self.p)
+
+    def sublayer(self, layer, kind, x):
+        rng, (B, N, D) = self.rng, x.shape
+        R = B * N
+        e = torch.arange(R * D, device=x.device).view(B, N, D)
+        if isinstance(kind, tuple):
+            gi = next(i for i, g in enumerate(self.program) if kind[1] in g)
+            e = e + self.program[gi].index(kind[1]) * R * D
+            site = rng.site(layer, rng.SITE_CA_SUBLAYER + gi)
+        else:
+            site = rng.site(layer, rng.SITE_SA_SUBLAYER if kind == "sa" else rng.SITE_FFN_SUBLAYER)
+        return self._apply(x, rng.keep_mask(self.seed, site, e, self.p))
+
+    def probs(self, layer, kind, P):
+        rng, H = self.rng, self.H
+        BH, L, S2 = P.shape
+        S = S2 - 1 if isinstance(kind, tuple) else S2            # cross-attention carries the zero-attn column
+        s_pad = (S + 127) // 128 * 128
+        rows = torch.arange(BH * L, device=P.device).view(BH, L, 1)          # (b*H + h)*N + n
+        e = rows * s_pad + torch.arange(S, device=P.device).view(1, 1, S)
+        site = (rng.site(layer, rng.SITE_CA_PROBS + self.enc.memories.index(kind[1])) if isinstance(kind, tuple)
+                else rng.site(layer, rng.SITE_SA_PROBS))
+        keep = rng.keep_mask(self.seed, site, e, self.p)
+        if S2 != S:
+            keep = torch.cat([keep, torch.ones_like(keep[..., :1])], -1)
+        return self._apply(P, keep)
+
+    def hidden(self, layer, h):
+        e = torch.arange(h.numel(), device=h.device).view(h.shape)
+        return self._apply(h, self.rng.keep_mask(self.seed, self.rng.site(layer, self.rng.SITE_FFN_HIDDEN), e, self.p))
+
+    def memory_keep(self, layer, memories, B):
+        return self.keeps.pop(0)
+
+
+def _run_dropout_case(w, p_drop, p_mem, seed=5):
+    from pq3d_b200.query_encoder import QueryMaskEncoder
+    sd = C.to_dev(synth.decoder_state_dict(w, seed=seed, sharp=1.0), DEV)
+    kw = dict(w.decoder_kwargs(), memory_dropout=p_mem)
+    enc = QueryMaskEncoder(None, **kw)
+    enc.load_state_dict(sd, strict=True)
+    enc = enc.to(DEV).train()
+    enc.train_dropout = p_drop
+    inp, pw, up = _inputs(w, seed + 1)
+    x, leaves = _leafify(inp)
+    torch.manual_seed(123)
+    out = enc(x, pw)[0]
+    (out * up).sum().backward()
+    torch.cuda.synchronize()
+    ours = {k: p.grad for k, p in enc.named_parameters()}
+    ours.update({k: v.grad for k, v in leaves.items()})
+    step_seed = int(enc._drop_seed.item()) & 0xFFFFFFFF if p_drop > 0 else 0
+    # oracle replaying the same masks, fp32 and under bf16 autocast
+    res = {}
+    for autocast in (False, True):
+        cfg = O.DecoderCfg(**kw)
+        cfg.train = KernelRngTrain(enc, step_seed, p_drop, w.B, w.N, w.num_heads)
+        sdd = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+        xo, lo = _leafify(inp)
+        torch.backends.cuda.matmul.allow_tf32 = False
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+            o = O.query_mask_encoder(sdd, cfg, xo, pw)[0]
+        (o.float() * up).sum().backward()
+        g = {k: v.grad for k, v in sdd.items()}
+        g.update({k: v.grad for k, v in lo.items()})
+        res[autocast] = (o.detach().float(), g)
+    out32, g32 = res[False]
+    out16, g16 = res[True]
+    e_o, e16_o = rel(out, out32), rel(out16, out32)
+    print(f"dropout p={p_drop} memory_dropout={p_mem}: forward err(ours) {e_o:.3e}  err(autocast oracle) {e16_o:.3e}")
+    assert e_o <= 1.25 * e16_o + 2e-3 and e_o <= 3e-2
+    floor = 1e-3 * max(float(v.abs().max()) for k, v in g32.items() if v is not None and k in sd)
+    worst = []
+    for k, ref in g32.items():
+        if ref is None:
+            continue
+        assert ours.get(k) is not None, f"{k}: no gradient produced"
+        if k.endswith("w_ks.bias"):
+            continue
+        worst.append((rel(ours[k], ref, floor), rel(g16[k], ref, floor), k))
+    worst.sort(reverse=True)
+    for e, e16, k in worst[:5]:
+        print(f"  {k}: ours {e:.3e}  autocast oracle {e16:.3e}")
+    # tolerance: no worse than 1.5x the reference's own bf16 path + 2e-2.  (Memory dropout leaves some scenes with a single
+    # surviving memory and the hidden dropout rescales activations, so bf16 rounding flips more ReLU gates than in the
+    # dropout-free cases: the autocast oracle itself sits at 0.1-0.2 on the FFN weights here.)
+    for e, e16, k in worst:
+        assert e <= 1.5 * e16 + 2e-2, f"{k}: gradient error {e:.3e} (autocast oracle {e16:.3e})"
+    return enc
+
+
+def test_dropout_and_memory_dropout_match_oracle_with_replayed_masks():
+    """Stage-2 training config shape (mixed, memory_dropout 0.6, dropout 0.1): the oracle replays the kernels' counter-RNG
+    masks (rebuilt on the host by pq3d_b200/rng.py), so outputs and gradients must agree like the dropout-free cases."""
+    w = synth.Workload("tdrop", 2, 100, 300, ["mv", "pc", "voxel", "prompt"], "mixed", T=20, num_layers=2, ragged=(150, 300))
+    enc = _run_dropout_case(w, 0.1, 0.6)
+    assert len(enc.last_memory_keep) == 2 and enc.last_memory_keep[0].shape == (2, 3)
+
+
+def test_dropout_plain_selfattn_sequential():
+    """Stock-MHA self-attention (probability dropout inside the self-attention too), sequential cross-attentions."""
+    w = synth.Workload("tdrop2", 2, 48, 200, ["pc", "voxel"], "sequential", num_layers=2, spatial_selfattn=False)
+    _run_dropout_case(w, 0.1, 0.0)
+
+
+def test_dropout_statistics_and_fresh_masks_per_step():
+    """Keep rate of the counter RNG ~ 1 - p; two forwards draw different masks; eval() is deterministic."""
+    from pq3d_b200 import ops
+    seed = torch.tensor([1234], dtype=torch.int32, device=DEV)
+    x = torch.ones(1 << 20, dtype=torch.bfloat16, device=DEV)
+    ops.dropout_bf16(x, 0.1, seed, 7)
+    kept = (x != 0).float().mean().item()
+    assert abs(kept - 0.9) < 3e-3, kept
+    assert abs(x.float().max().item() - 1 / 0.9) < 1e-2
+    y = torch.ones(1 << 20, dtype=torch.bfloat16, device=DEV)
+    ops.dropout_bf16(y, 0.1, seed + 1, 7)
+    assert ((x != 0) != (y != 0)).float().mean().item() > 0.1
+    from pq3d_b200.query_encoder import QueryMaskEncoder
+    w = synth.Workload("tdrop3", 1, 64, 128, ["pc"], "parallel", num_layers=1)
+    enc = QueryMaskEncoder(None, **w.decoder_kwargs()).to(DEV).train()
+    inp, pw, _ = _inputs(w, 3)
+    a = enc(synth.clone_input_dict(inp), pw)[0].detach()
+    b = enc(synth.clone_input_dict(inp), pw)[0].detach()
+    assert not torch.equal(a, b), "two training-mode forwards must draw different dropout masks"
+    enc.eval()
+    with torch.no_grad():
+        c = enc(synth.clone_input_dict(inp), pw)[0]
+        d = enc(synth.clone_input_dict(inp), pw)[0]
+    assert torch.equal(c, d)
