@@ -75,6 +75,16 @@ def cpu_reference_run(w, steps, warmup, budget_s, train=False):
     ws.B = 1
     sd = synth.decoder_state_dict(ws, seed=0)
     cfg = O.DecoderCfg(**ws.decoder_kwargs())
+    if train:
+        class _TorchDropout:              # module.train(): the reference's dropout sites (p = 0.1), torch RNG
+            @staticmethod
+            def _d(x):
+                return torch.nn.functional.dropout(x, 0.1, True)
+            sublayer = staticmethod(lambda layer, kind, x: _TorchDropout._d(x))
+            probs = staticmethod(lambda layer, kind, x: _TorchDropout._d(x))
+            hidden = staticmethod(lambda layer, x: _TorchDropout._d(x))
+            memory_keep = staticmethod(lambda layer, memories, B: None)
+        cfg.train = _TorchDropout
     inp, pw, _ = synth.make_decoder_inputs(ws)
     times = []
     t_begin = time.perf_counter()
@@ -177,8 +187,7 @@ def run_train(args, w, enc, inp_host, pw_host, rank, world, local_rank, dev, bar
     from pq3d_b200 import ops, synth
     from pq3d_b200.dist import FlatGradAllReduce
 
-    enc.train()
-    enc.train_dropout = 0.0          # dropout-free training path (no RNG kernels in this build); stated in config
+    enc.train()                      # training mode as the reference trains: dropout 0.1 at every site
     params = list(enc.parameters())
     graphed = not args.no_graph
     opt = torch.optim.AdamW(params, lr=1e-4, betas=(0.9, 0.98), fused=True, capturable=graphed)
@@ -323,7 +332,8 @@ def run_train(args, w, enc, inp_host, pw_host, rank, world, local_rank, dev, bar
             "config": dict(workload_config(w, world), mode="training step: forward + backward + AdamW (torch fused AdamW)"
                            + (", whole step replayed as one CUDA graph" if graphed else ", eager launches")
                            + (", one flat NCCL all-reduce (mean) over all gradients" if world > 1 else ""),
-                           dropout="0.0 (the training path has no RNG kernels; the reference trains with 0.1)",
+                           dropout=f"{enc.train_dropout} (sublayer, attention-probability and FFN-hidden dropout, counter RNG "
+                                   "regenerated in backward), memory_dropout 0",
                            l2="per-step working set > 1 GB (saved K/V^T, dK/dV, score tiles) exceeds the 126 MB L2; no flush",
                            parallelism=f"batch-axis shard x{world}, weights replicated, gradient all-reduce"),
             "clocks": clocks, "final_loss": last_loss,

@@ -32,7 +32,7 @@ constexpr int kBwdThreads = 64 + 32 * kBwdSoftmaxWarps;
 constexpr int kBwdStages = 2;
 constexpr int kTileBytes = 128 * 64 * 2;              // one [128 rows x 64 bf16] swizzled tile: 16 KB
 constexpr int kSqBytes = 128 * 128 * 2;               // P^T / dS^T tile: two atom columns of 16 KB
-constexpr int kBwdSmem = 2 * kTileBytes + kBwdStages * 2 * kTileBytes + 2 * kSqBytes + 256 + 3 * 128 * 4 + 1024;
+constexpr int kBwdSmem = 2 * kTileBytes + kBwdStages * 2 * kTileBytes + 2 * kSqBytes + 256 + 1024;
 
 struct AttnBwdMaps {
   CUtensorMap q, d_o, k, v;
@@ -78,8 +78,12 @@ __device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint3
   return d;
 }
 
+// QMASK: per-query mask bits (mask_q_stride != 0); BIAS: additive score bias; DROP: probability dropout.  The common
+// cross-attention case (key padding only) compiles to ~7 instructions per score.
+template <bool QMASK, bool BIAS, bool DROP>
 __global__ void __launch_bounds__(kBwdThreads, 1)
 attention_bwd_kernel(const __grid_constant__ AttnBwdMaps maps, const AttnBwdParams p) {
+  __shared__ float2 s_stat[128];     // per query: {m + log2(l), ln2 * delta}; +inf reference for absent rows
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;
@@ -99,9 +103,6 @@ attention_bwd_kernel(const __grid_constant__ AttnBwdMaps maps, const AttnBwdPara
   uint64_t* dkv_empty = dkv_full + 1;
   uint64_t* dq_full = dkv_empty + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dq_full + 1);
-  float* s_m = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);
-  float* s_il = s_m + 128;
-  float* s_dl = s_il + 128;
 
   const int warp = threadIdx.x >> 5;
   const int h = blockIdx.x, b = blockIdx.y, chunk = blockIdx.z;
@@ -207,26 +208,27 @@ attention_bwd_kernel(const __grid_constant__ AttnBwdMaps maps, const AttnBwdPara
       const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
       const int64_t bh = static_cast<int64_t>(b) * p.H + h;
       if (half == 0) {
-        const bool ok = r < p.Nq;
-        s_m[r] = ok ? p.stat_m[bh * p.Nq + r] : 0.f;
-        s_il[r] = ok ? 1.f / p.stat_l[bh * p.Nq + r] : 0.f;
-        s_dl[r] = ok ? p.delta[bh * p.Nq + r] : 0.f;
+        // P = ex2(S2 - m) / l = ex2(S2 - (m + log2 l));  dS2 = P * (ln2 * dP - ln2 * delta)
+        float m2 = __int_as_float(0x7f800000), d2 = 0.f;
+        if (r < p.Nq) {
+          const float l = p.stat_l[bh * p.Nq + r];
+          if (l > 0.f) m2 = p.stat_m[bh * p.Nq + r] + __log2f(l);
+          d2 = 0.6931471805599453f * p.delta[bh * p.Nq + r];
+        }
+        s_stat[r] = make_float2(m2, d2);
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
-      const uint32_t dkey = p.drop_thresh != 0 ? drop_key(__ldg(p.seed), p.site) : 0u;
+      const uint32_t dkey = DROP ? drop_key(__ldg(p.seed), p.site) : 0u;
       const uint32_t s_pad = static_cast<uint32_t>(tiles_total * 128);
       const uint32_t* mbase =
           p.mask_bits == nullptr ? nullptr : p.mask_bits + b * p.mask_b_stride + h * p.mask_h_stride;
+#pragma unroll 1
       for (int i = 0; i < Tn; ++i) {
         const int t = t0 + i;
         const int kk = t * 128 + r;
         const bool key_ok = kk < p.S;
         bool key_masked = !key_ok;
-        const uint32_t* mrow = nullptr;
-        if (mbase != nullptr) {
-          if (p.mask_q_stride == 0) key_masked = key_masked || ((__ldg(mbase + t * 4 + quad) >> lane_id()) & 1u);
-          else mrow = mbase + t * 4 + quad;
-        }
+        if (!QMASK && mbase != nullptr) key_masked = key_masked || ((__ldg(mbase + t * 4 + quad) >> lane_id()) & 1u);
         mbar_wait(s_full, i & 1, 600);
         tc_fence_after();
 #pragma unroll 1
@@ -235,25 +237,43 @@ attention_bwd_kernel(const __grid_constant__ AttnBwdMaps maps, const AttnBwdPara
           uint32_t sv[32], dv[32];
           tmem_ld_32x32(tmem_S + lane_off + col0, sv);
           tmem_ld_32x32(tmem_dP + lane_off + col0, dv);
+          uint32_t qword = 0;             // QMASK: lane j holds the mask word of query col0 + j for this warp's 32 keys
+          if (QMASK) {
+            const int nq = col0 + static_cast<int>(lane_id());
+            qword = nq < p.Nq ? __ldg(mbase + nq * p.mask_q_stride + t * 4 + quad) : 0xffffffffu;
+          }
           tmem_ld_wait();
-          float* pr = reinterpret_cast<float*>(sv);      // results overwrite their inputs: 64 live registers, not 128
+          float* pr = reinterpret_cast<float*>(sv);      // results overwrite their inputs
           float* ds = reinterpret_cast<float*>(dv);
+          if (!QMASK && key_masked) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int n = col0 + j;
-            float sc = __uint_as_float(sv[j]);
-            bool masked = key_masked;
-            if (mrow != nullptr && n < p.Nq) masked = masked || ((__ldg(mrow + n * p.mask_q_stride) >> lane_id()) & 1u);
-            if (p.bias != nullptr && n < p.Nq && key_ok) sc += __ldg(p.bias + (bh * p.Nq + n) * p.bias_ld + kk);
-            const float pv = masked ? 0.f : bwd_ex2(sc - s_m[n]) * s_il[n];
-            float ks = 1.f;             // dropout factor of this probability in the forward
-            if (p.drop_thresh != 0) {
-              const int nc = n < p.Nq ? n : p.Nq - 1;
-              const uint32_t e = static_cast<uint32_t>(bh * p.Nq + nc) * s_pad + static_cast<uint32_t>(kk);
-              ks = drop_keep(dkey, e, p.drop_thresh) ? p.drop_scale : 0.f;
+            for (int j = 0; j < 32; ++j) { pr[j] = 0.f; ds[j] = 0.f; }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int n = col0 + j;
+              const float2 st = s_stat[n];
+              float sc = __uint_as_float(sv[j]);
+              if (BIAS) {
+                if (n < p.Nq && key_ok) sc += __ldg(p.bias + (bh * p.Nq + n) * p.bias_ld + kk);
+              }
+              float pv = bwd_ex2(sc - st.x);
+              if (QMASK) {
+                const uint32_t w = __shfl_sync(0xffffffffu, qword, j);
+                if (key_masked || ((w >> lane_id()) & 1u)) pv = 0.f;
+              }
+              float dpv = __uint_as_float(dv[j]);
+              if (DROP) {
+                const int nc = n < p.Nq ? n : p.Nq - 1;
+                const uint32_t e = static_cast<uint32_t>(bh * p.Nq + nc) * s_pad + static_cast<uint32_t>(kk);
+                const float ks = drop_keep(dkey, e, p.drop_thresh) ? p.drop_scale : 0.f;
+                pr[j] = pv * ks;
+                dpv *= ks;
+              } else {
+                pr[j] = pv;
+              }
+              ds[j] = pv * fmaf(dpv, 0.6931471805599453f, -st.y);
             }
-            pr[j] = pv * ks;
-            ds[j] = 0.6931471805599453f * pv * (__uint_as_float(dv[j]) * ks - s_dl[n]);
           }
           if (p.dS_out != nullptr && kk < p.ds_ld) {
 #pragma unroll
@@ -413,12 +433,24 @@ extern "C" int pq3d_attention_bwd(const void* Q, int64_t ldq, int q_col0, const 
   p.tiles_per_chunk = (tiles + chunks - 1) / chunks;
   chunks = (tiles + p.tiles_per_chunk - 1) / p.tiles_per_chunk;
   p.atomic_dq = 1;      // dQ is always accumulated: the caller zero-fills it (one memset for all memories of a group)
-  static bool configured = false;
-  if (!configured) {
-    PQ3D_CUDA(cudaFuncSetAttribute(attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem));
-    configured = true;
+  const bool qmask = mask_bits != nullptr && mask_q_stride != 0, has_bias = bias != nullptr, drop = drop_p > 0.f;
+  const dim3 grid(H, B, chunks), block(kBwdThreads);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  cudaError_t err = cudaSuccess;
+#define PQ3D_BWD_CASE(Q_, B_, D_)                                                                                     \
+  if (qmask == Q_ && has_bias == B_ && drop == D_) {                                                                  \
+    static bool configured = false;                                                                                   \
+    if (!configured) {                                                                                                \
+      PQ3D_CUDA(cudaFuncSetAttribute(attention_bwd_kernel<Q_, B_, D_>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
+                                     kBwdSmem));                                                                      \
+      configured = true;                                                                                              \
+    }                                                                                                                 \
+    err = launch_kernel(attention_bwd_kernel<Q_, B_, D_>, grid, block, kBwdSmem, st, maps, p);                        \
   }
-  PQ3D_CUDA(launch_kernel(attention_bwd_kernel, dim3(H, B, chunks), dim3(kBwdThreads), kBwdSmem,
-                          reinterpret_cast<cudaStream_t>(stream), maps, p));
+  PQ3D_BWD_CASE(false, false, false) PQ3D_BWD_CASE(false, false, true) PQ3D_BWD_CASE(false, true, false)
+  PQ3D_BWD_CASE(false, true, true) PQ3D_BWD_CASE(true, false, false) PQ3D_BWD_CASE(true, false, true)
+  PQ3D_BWD_CASE(true, true, false) PQ3D_BWD_CASE(true, true, true)
+#undef PQ3D_BWD_CASE
+  PQ3D_CUDA(err);
   return PQ3D_OK;
 }

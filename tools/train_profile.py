@@ -10,7 +10,6 @@ dev = "cuda"
 enc = QueryMaskEncoder(None, **w.decoder_kwargs())
 enc.load_state_dict(synth.decoder_state_dict(w, seed=0), strict=True)
 enc = enc.to(dev).train()
-enc.train_dropout = 0.0
 opt = torch.optim.AdamW(enc.parameters(), lr=1e-4, fused=True)
 inp, pw, _ = synth.make_decoder_inputs(w, device=dev)
 target = torch.randn(w.B, w.N, w.hidden_size, device=dev)
