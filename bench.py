@@ -44,6 +44,8 @@ def parse():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--streams", type=int, default=4,
+                    help="batches in flight (CUDA streams) in the device-resident throughput loop; 1 = strictly serial")
     ap.add_argument("--train", action="store_true",
                     help="training step (fwd + bwd + AdamW, gradient all-reduce for N>1); implied by --workload c5")
     return ap.parse_args()
@@ -427,25 +429,41 @@ def main():
         with torch.no_grad():
             return enc(synth.clone_input_dict(inp_dev), pw_dev, mask_head)[0]
 
-    for _ in range(max(args.warmup, 3)):
-        step_resident()
-    barrier()
+    def timed_steps(n_streams, steps):
+        """`steps` forwards, round-robin over n_streams CUDA streams (each stream = one batch in flight with its own
+        workspace and captured graph); device time from the first launch to the last completion."""
+        cur = torch.cuda.current_stream()
+        streams = [cur] if n_streams <= 1 else [torch.cuda.Stream(device=dev) for _ in range(n_streams)]
+        for st in streams:                                   # warm-up: eager pass, capture, first replays — per stream
+            st.wait_stream(cur)
+            with torch.cuda.stream(st):
+                for _ in range(max(args.warmup, 3)):
+                    step_resident()
+        for st in streams:
+            cur.wait_stream(st)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n0 = ops.LAUNCHES
+        e0.record()
+        for st in streams:
+            st.wait_stream(cur)
+        for i in range(steps):
+            with torch.cuda.stream(streams[i % len(streams)]):
+                step_resident()
+        for st in streams:
+            cur.wait_stream(st)
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item() / steps, ops.LAUNCHES - n0
+
+    ms_serial, _ = timed_steps(1, args.steps)                # one batch at a time: the latency of a forward
     sampler = ClockSampler(local_rank)
     sampler.start()
-    l0 = ops.LAUNCHES
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        out = step_resident()
-    e1.record()
-    barrier()
+    ms_per_step, launches = timed_steps(args.streams, args.steps)
     clocks = sampler.stop()
-    launches = ops.LAUNCHES - l0
-    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms_total = ms.item()
-    ms_per_step = ms_total / args.steps
     value = world * w.B * w.N / (ms_per_step * 1e-3)
 
     # ---------------- e2e: host (pinned) inputs -> H2D -> forward -> D2H, every step
@@ -587,7 +605,10 @@ def main():
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": dict(workload_config(w, world),
                            l2="per-step working set ~0.5 GB (fp32 inputs + bf16 K/V^T for 4 layers) exceeds the 126 MB L2; no flush",
-                           cuda_graph=enc.use_cuda_graph),
+                           cuda_graph=enc.use_cuda_graph, streams=args.streams,
+                           in_flight=f"{args.streams} batches in flight on {args.streams} CUDA streams (each K steps round-robin); "
+                                     f"strictly serial: {ms_serial:.4f} ms/step = {world * w.B * w.N / (ms_serial * 1e-3):.0f} queries/s"),
+            "serial": {"ms_per_step": ms_serial, "value": world * w.B * w.N / (ms_serial * 1e-3)},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "serial_value": e2e_serial,

@@ -267,8 +267,56 @@ def test_rejects_non_bool_masks_and_training_mode():
         enc(bad, pw)
     with pytest.raises(NotImplementedError):
         enc(synth.clone_input_dict(inp), pw, lambda q: (None, None, None))   # grad enabled + mask head: no backward
-    enc.train()
-    with torch.no_grad(), pytest.raises(NotImplementedError):
-        enc(synth.clone_input_dict(inp), pw)              # train-mode forward without grads: dropout not built
+    enc.train()                                           # module.train(): the reference's dropout 0.1 is active
+    with torch.no_grad():
+        a = enc(synth.clone_input_dict(inp), pw)[0]
+        b = enc(synth.clone_input_dict(inp), pw)[0]
+    assert torch.isfinite(a).all() and not torch.equal(a, b)     # two draws of the dropout masks
     with pytest.raises(NotImplementedError):
-        enc(synth.clone_input_dict(inp), pw)              # train mode with the reference's dropout 0.1: refuses
+        enc(synth.clone_input_dict(inp), pw, lambda q: (None, None, None))   # train mode + mask head: no backward
+
+
+def test_whole_forward_graph_on_stable_buffers_and_concurrent_streams():
+    """Serving-loop paths: (1) the same device tensors handed in again -> the prologue is captured with the body (one
+    graph launch per forward) and still reads the buffers' CURRENT contents; (2) two batches in flight on two CUDA
+    streams use separate workspaces.  Both must reproduce the plain eager-prologue result bit for bit."""
+    w = synth.Workload("tfull", 2, 100, 384, ["mv", "pc", "voxel", "prompt"], "mixed", T=12, num_layers=2)
+    sd = synth.decoder_state_dict(w, seed=3)
+    enc = build_decoder(w, sd)
+    inp_a, pw, _ = synth.make_decoder_inputs(w, device=DEV)
+    w2 = synth.Workload("tfull", 2, 100, 384, ["mv", "pc", "voxel", "prompt"], "mixed", T=12, num_layers=2, seed=999)
+    inp_b, pw_b, _ = synth.make_decoder_inputs(w2, device=DEV)
+    enc.use_cuda_graph = False
+    with torch.no_grad():
+        ref_a = enc(synth.clone_input_dict(inp_a), pw)[0].clone()
+        ref_b = enc(synth.clone_input_dict(inp_b), pw_b)[0].clone()
+    assert not torch.equal(ref_a, ref_b)
+    enc.use_cuda_graph = True
+    enc._ws.clear()
+    with torch.no_grad():
+        outs = [enc(synth.clone_input_dict(inp_a), pw)[0].clone() for _ in range(6)]     # eager, body graph, full graph
+    ws = next(iter(enc._ws.values()))
+    assert any(e.get("graph") is not None for e in ws.get("full", {}).values()), "whole-forward graph was not captured"
+    for o in outs:
+        assert torch.equal(o, ref_a)
+    # new contents written into the SAME buffers are picked up by the replay
+    flat_a = [t for v in inp_a.values() for t in enc._flat_tensors(list(v))]
+    flat_b = [t for v in inp_b.values() for t in enc._flat_tensors(list(v))]
+    with torch.no_grad():
+        for ta, tb in zip(flat_a, flat_b):
+            ta.copy_(tb)
+        pw.copy_(pw_b)
+        assert torch.equal(enc(synth.clone_input_dict(inp_a), pw)[0], ref_b)
+    # two streams, two batches in flight
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    inp_c, pw_c, _ = synth.make_decoder_inputs(w, device=DEV)
+    res = {}
+    with torch.no_grad():
+        for _ in range(5):
+            for st, (name, i_, p_) in ((s1, ("a", inp_c, pw_c)), (s2, ("b", inp_a, pw))):
+                st.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(st):
+                    res[name] = enc(synth.clone_input_dict(i_), p_)[0]
+    torch.cuda.synchronize()
+    assert torch.equal(res["a"], ref_a) and torch.equal(res["b"], ref_b)
+    assert len(enc._ws) >= 3
