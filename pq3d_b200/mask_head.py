@@ -91,6 +91,7 @@ class MaskHeadSegLevel(nn.Module):
         self._cls = MlpHeadRunner(self.cls_head, neg_inf_cols=cols)
         self._wkey, self._w = None, None
         self._prep = None
+        self._prep_slots = {}
         self._bufs = {}
 
     def _weights(self, dev):
@@ -104,7 +105,7 @@ class MaskHeadSegLevel(nn.Module):
             self._wkey = key
         return self._w
 
-    def prepare(self, seg_fts_for_match, seg_masks):
+    def prepare(self, seg_fts_for_match, seg_masks, slot=0):
         """Hoisted, query-independent part, once per forward (the reference redoes it on each of its K*L+1 calls):
         Kcat [B*S, n*D] = concat_m valid_m * k_proj_m(feat_m).  Everything lands in persistent buffers (static
         addresses for CUDA-graph capture); nothing is cached across calls — tensor identity is not a safe key."""
@@ -113,7 +114,7 @@ class MaskHeadSegLevel(nn.Module):
         w = self._weights(dev)
         n, D = len(feats), self.hidden_size
         B, S = feats[0][0].shape[:2]
-        key = ("prep", B, S)
+        key = ("prep", B, S, slot)         # slot: one workspace per caller context (decoder workspace / CUDA stream)
         kcat = self._ws(key, "kcat", (B * S, n * D), bf16, dev)
         x16 = self._ws(key, "x16", (B * S, D), bf16, dev)
         masks = self._ws(key, "masks", (n + 1, B, S), torch.bool, dev)
@@ -131,6 +132,7 @@ class MaskHeadSegLevel(nn.Module):
             ptrs.copy_(torch.tensor([masks[j].data_ptr() for j in range(n)], dtype=torch.int64))
             self._bufs[key]["ptrs_set"] = True
         self._prep = (kcat, masks, ptrs, B, S)
+        self._prep_slots[slot] = self._prep
         return self._prep
 
     def _ws(self, key, name, shape, dtype, dev):
@@ -141,14 +143,14 @@ class MaskHeadSegLevel(nn.Module):
         return t
 
     def run_into(self, q2d: torch.Tensor, B: int, N: int, out_cls: torch.Tensor, out_logits: torch.Tensor,
-                 out_attn: torch.Tensor):
+                 out_attn: torch.Tensor, slot=0):
         """The per-call part, after prepare(): reads and writes static addresses only (caller-provided outputs, a
         persistent workspace), so the decoder can capture it into its CUDA graph.  q2d: fp32 [B*N, D]."""
         dev = q2d.device
         D, R, n = self.hidden_size, B * N, len(self.mask_pred_list)
         w = self._weights(dev)
-        kcat, masks, ptrs, Bk, S = self._prep
-        key = (B, N, S)
+        kcat, masks, ptrs, Bk, S = self._prep_slots[slot]
+        key = (B, N, S, slot)
         x16 = self._ws(key, "x16", (R, D), bf16, dev)
         ops.cast_bf16(q2d, x16)
         cw = self._cls._weights(dev)
@@ -178,8 +180,9 @@ class MaskHeadSegLevel(nn.Module):
         cls_logits = torch.empty(B, N, C, dtype=torch.float32, device=dev)
         mask_logits = torch.empty(B, S, N, dtype=torch.float32, device=dev)
         attn_mask = torch.empty(B, N, S, dtype=torch.bool, device=dev)
-        self.prepare(seg_fts_for_match, seg_masks)
-        self.run_into(query.reshape(B * N, D).contiguous().float(), B, N, cls_logits, mask_logits, attn_mask)
+        slot = ("stream", torch.cuda.current_stream(dev).cuda_stream)
+        self.prepare(seg_fts_for_match, seg_masks, slot)
+        self.run_into(query.reshape(B * N, D).contiguous().float(), B, N, cls_logits, mask_logits, attn_mask, slot)
         if offline_attn_masks is not None:
             attn_mask = offline_attn_masks
         return cls_logits, mask_logits, attn_mask

@@ -670,7 +670,8 @@ class QueryMaskEncoder(nn.Module):
             # ---------------- our own MaskHeadSegLevel in the loop: its hoisted part runs once here, its per-layer
             # part writes static buffers, so blocks x layers x (mask head + mask packing + layer) is one CUDA graph
             kw = mask_head.keywords
-            mh.prepare(kw["seg_fts_for_match"], kw["seg_masks"])
+            slot = ("decoder", id(ws))
+            mh.prepare(kw["seg_fts_for_match"], kw["seg_masks"], slot)
             S_m, C = kw["seg_masks"].shape[1], mh.cls_head[4].out_features
             n_calls = self.num_blocks * L
             cls_buf = buf("mh_cls", (n_calls, B, N, C), torch.float32)
@@ -683,7 +684,7 @@ class QueryMaskEncoder(nn.Module):
             def body():
                 project_memories()
                 for k in range(n_calls):
-                    mh.run_into(q32, B, N, cls_buf[k], logit_buf[k], attn_buf)
+                    mh.run_into(q32, B, N, cls_buf[k], logit_buf[k], attn_buf, slot)
                     if self.use_self_mask:
                         ops.pack_mask(attn_buf, am_bits, unmask_full_rows=True, mask_fixed=fixed.view(torch.uint8),
                                       active_tiles=am_tiles)
