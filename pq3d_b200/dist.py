@@ -70,10 +70,16 @@ def max_over_ranks(value: float, device="cpu", group=None) -> float:
 
 
 class FlatGradAllReduce:
-    """One flat buffer for all gradients -> a single all-reduce (mean) per step: on an NVSwitch box the
-    collective is latency-, not link-bound, so one ~240 MB fp32 call beats DDP's 25 MB buckets.
-    Parameters without a gradient this step contribute zeros (the reference runs DDP with
-    find_unused_parameters=True, trainer/build.py:66)."""
+    """One flat buffer for all gradients -> a single all-reduce (mean) per step: on an NVSwitch box the collective is
+    latency-, not link-bound, so one ~240 MB fp32 call beats DDP's 25 MB buckets.  Per step: ONE multi-tensor copy of
+    the gradients into the flat buffer, the all-reduce, one division, and then `p.grad` is re-pointed at its view of
+    the flat buffer (no copy back; the optimizer reads the averaged gradients in place).  The first version issued
+    three small kernels per parameter (~500 launches, +1.5 ms on a 3.2 ms step at 2 GPUs).  Capturable in the training
+    step's CUDA graph.  Parameters without a gradient this step contribute zeros (the reference runs DDP with
+    find_unused_parameters=True, trainer/build.py:66).
+
+    PQ3D_COALESCED_ALLREDUCE=1 selects an in-place variant (every gradient all-reduced inside one ncclGroup through
+    torch's coalescing manager, no staging copy at all); it is experimental: not verified under CUDA-graph capture."""
 
     def __init__(self, params: Sequence[torch.nn.Parameter], group=None):
         self.params = [p for p in params if p.requires_grad]
@@ -85,18 +91,26 @@ class FlatGradAllReduce:
         for p in self.params:
             self.views.append(self.flat[off: off + p.numel()].view_as(p))
             off += p.numel()
+        import os
+        self.coalesced = os.environ.get("PQ3D_COALESCED_ALLREDUCE", "0") == "1"
 
     def __call__(self):
         world = dist.get_world_size(self.group)
+        if self.coalesced and dist.get_backend(self.group) == "nccl":
+            for p in self.params:
+                if p.grad is None:
+                    p.grad = torch.zeros_like(p)
+            with dist._coalescing_manager(group=self.group, device=self.params[0].device, async_ops=False):
+                for p in self.params:
+                    dist.all_reduce(p.grad, op=dist.ReduceOp.AVG, group=self.group)
+            return
+        have = [(p, v) for p, v in zip(self.params, self.views) if p.grad is not None and p.grad.data_ptr() != v.data_ptr()]
         for p, v in zip(self.params, self.views):
             if p.grad is None:
                 v.zero_()
-            else:
-                v.copy_(p.grad)
+        if have:
+            torch._foreach_copy_([v for _, v in have], [p.grad for p, _ in have])
         dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
         self.flat.div_(world)
         for p, v in zip(self.params, self.views):
-            if p.grad is None:
-                p.grad = v.clone()
-            else:
-                p.grad.copy_(v)
+            p.grad = v
