@@ -169,6 +169,8 @@ class _Packed:
     one pass over the weights, CUDA graphs that captured these pointers stay valid, and `train=True` adds the
     transposed copies the dgrad GEMMs take (`T(w)`)."""
 
+    ALLOW_CPU = False      # set by tests/_cpu_ops.py, whose emulated `refresh` copies on the host
+
     def __init__(self, enc: "QueryMaskEncoder", device, train: bool = False):
         D, L = enc.hidden_size, enc.num_layers
         layers = enc.unified_encoder
@@ -251,7 +253,7 @@ class _Packed:
 
     def _src(self, p: torch.Tensor) -> torch.Tensor:
         p = p.detach()
-        if p.dtype != torch.float32 or not p.is_cuda or not p.is_contiguous():
+        if p.dtype != torch.float32 or not (p.is_cuda or _Packed.ALLOW_CPU) or not p.is_contiguous():
             raise TypeError("pq3d_b200: decoder parameters must be contiguous fp32 CUDA tensors (the kernels' bf16 "
                             f"operand copies are packed from them on the device); got {p.dtype} on {p.device}")
         return p
@@ -488,7 +490,7 @@ class QueryMaskEncoder(nn.Module):
         # idle, two or three interleaved batches fill them (bench.py --streams)
         key = (B, N, tuple((m, tuple(input_dict[m][0][0].shape if isinstance(input_dict[m][0], list)
                                      else input_dict[m][0].shape)) for m in active),
-               torch.cuda.current_stream(dev).cuda_stream)
+               torch.cuda.current_stream(dev).cuda_stream if dev.type == "cuda" else 0)
         ws = self._ws.setdefault(key, {})
         buf = lambda name, shape, dtype: self._buf(ws, name, shape, dtype, dev)  # noqa: E731
 

@@ -18,6 +18,7 @@ memory, no in-loop mask head, dropout disabled (`enc.train_dropout = 0.0`, memor
 """
 from __future__ import annotations
 
+import contextlib
 from typing import Dict, List, Optional, Tuple
 
 import torch
@@ -216,9 +217,10 @@ class _Bwd:
         self.grads: Dict[str, torch.Tensor] = {}
         self.dev = sv["qpos"].device
         self.keep: List = []
-        self.main = torch.cuda.current_stream(self.dev)
+        self.cuda = self.dev.type == "cuda"          # (the host logic also runs against tests/_cpu_ops.py's emulation)
+        self.main = torch.cuda.current_stream(self.dev) if self.cuda else None
         n_par = max([len(g) for g in sv["program"]] + [1])
-        pool = _side_streams(self.dev, n_par) if enc.train_streams else []
+        pool = _side_streams(self.dev, n_par) if (enc.train_streams and self.cuda) else []
         self.side = pool[0] if pool else None
         self.par = pool[1:] if pool else []
         self.forked = set()
@@ -231,6 +233,8 @@ class _Bwd:
     def on(self, stream, *deps):
         """Context: run on `stream` after everything issued so far on the main stream; deps are kept alive."""
         self.keep.extend(d for d in deps if d is not None)
+        if not self.cuda:
+            return contextlib.nullcontext()
         if stream is None:
             return torch.cuda.stream(self.main)
         stream.wait_stream(torch.cuda.current_stream(self.dev))
@@ -238,6 +242,8 @@ class _Bwd:
         return torch.cuda.stream(stream)
 
     def join(self, streams=None):
+        if not self.cuda:
+            return
         cur = torch.cuda.current_stream(self.dev)
         for st in (list(self.forked) if streams is None else streams):
             if st is not None and st in self.forked:
