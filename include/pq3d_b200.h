@@ -255,6 +255,13 @@ int pq3d_attention_bwd(const void* Q, int64_t ldq, int q_col0, const void* dO, i
                        int64_t ds_ld, int B, int H, int Nq, float q_scale, float drop_p, const uint32_t* seed_dev,
                        uint32_t site, void* stream);
 
+/* Backward of pq3d_mask_head_finalize: d_raw[b,s,n] = d_logits[b,s,n] / (#valid memories at (b,s) + 1e-8), 0 where the
+ * segment is padded (its logit was overwritten by -1e6) — written as the bf16 operand [B*S, Np] (columns N..Np zero) of
+ * the products d_q = d_raw^T k and d_k = d_raw q.  masks: uint8 [n_mem + 1][B*S], memory masks first (1 = ignore), the
+ * segment padding mask last.  Replaces autograd through modules/heads/mask_head.py:36-40. */
+int pq3d_mask_head_finalize_bwd(const float* d_logits, const uint8_t* masks, int n_mem, void* d_raw_bf16, int B, int S,
+                                int N, int Np, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -290,20 +290,23 @@ def query_mask_encoder(sd: SD, cfg: DecoderCfg, input_dict: dict, pairwise_locs:
 # --------------------------------------------------------------------------------------------
 # mask head (in-loop consumer/producer of the attention mask)
 # --------------------------------------------------------------------------------------------
-def mlp_head(x: Tensor, sd: SD, prefix: str) -> Tensor:
-    """get_mlp_head: Linear-ReLU-LayerNorm(eps 1e-12)-Dropout-Linear (modules/utils.py:18-25)."""
+def mlp_head(x: Tensor, sd: SD, prefix: str, dropout: Optional[Callable] = None) -> Tensor:
+    """get_mlp_head: Linear-ReLU-LayerNorm(eps 1e-12)-Dropout-Linear (modules/utils.py:18-25); `dropout` (training
+    only) is applied where the nn.Dropout sits."""
     h = F.relu(F.linear(x, sd[prefix + "0.weight"], sd[prefix + "0.bias"]))
     h = F.layer_norm(h, (h.shape[-1],), sd[prefix + "2.weight"], sd[prefix + "2.bias"], 1e-12)
+    if dropout is not None:
+        h = dropout(h)
     return F.linear(h, sd[prefix + "4.weight"], sd[prefix + "4.bias"])
 
 
 def mask_head_seg_level(query: Tensor, sd: SD, prefix: str, seg_fts_for_match: list, seg_masks: Tensor,
                         filter_out_classes=None, offline_attn_masks: Optional[Tensor] = None,
-                        skip_prediction: bool = False):
+                        skip_prediction: bool = False, cls_dropout: Optional[Callable] = None):
     """MaskHeadSegLevel.forward + MaskPredictionLayer (modules/heads/mask_head.py:24-57)."""
     if skip_prediction:
         return None, None, offline_attn_masks
-    cls_logits = mlp_head(query, sd, prefix + "cls_head.")
+    cls_logits = mlp_head(query, sd, prefix + "cls_head.", cls_dropout)
     # NB the reference indexes unconditionally (mask_head.py:28); with filter_out_classes=None the
     # index `[..., None]` addresses every class, so all logits become -inf.  Reproduced as is.
     cls_logits[..., filter_out_classes] = float("-inf")

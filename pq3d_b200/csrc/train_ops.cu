@@ -209,6 +209,28 @@ __global__ void dropout_bf16_kernel(__nv_bfloat16* __restrict__ x, int64_t n8, u
   }
 }
 
+// Backward of pq3d_mask_head_finalize (modules/heads/mask_head.py:36-40): mask_logits = raw / (sum_m valid_m + 1e-8),
+// rows of padded segments overwritten by a constant -> d_raw = d_logits / (cnt + 1e-8), 0 on padded segments.  Emits the
+// bf16 operand of the two products that follow (d_q = d_raw^T k, d_k = d_raw q): [B*S, Np] with zero pad columns.
+// masks: uint8 [n_mem + 1][B*S], memory validity masks first (1 = ignore), the segment padding mask last.
+__global__ void mask_head_finalize_bwd_kernel(const float* __restrict__ d_logits, const uint8_t* __restrict__ masks,
+                                              int n_mem, __nv_bfloat16* __restrict__ d_raw, int64_t rows, int N, int Np) {
+  pdl_sync();
+  const int64_t total = rows * Np;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int n = static_cast<int>(i % Np);
+    const int64_t row = i / Np;
+    float v = 0.f;
+    if (n < N && masks[n_mem * rows + row] == 0) {
+      int cnt = 0;
+      for (int m = 0; m < n_mem; ++m) cnt += (masks[m * rows + row] == 0) ? 1 : 0;
+      v = __fdiv_rn(d_logits[row * N + n], static_cast<float>(cnt) + 1e-8f);
+    }
+    d_raw[i] = __float2bfloat16_rn(v);
+  }
+}
+
 }  // namespace pq3d
 
 using namespace pq3d;
@@ -267,5 +289,18 @@ extern "C" int pq3d_dropout_bf16(void* x, int64_t n, float drop_p, const uint32_
   PQ3D_CUDA(launch_kernel(dropout_bf16_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0,
                           reinterpret_cast<cudaStream_t>(stream), reinterpret_cast<__nv_bfloat16*>(x), n / 8,
                           drop_threshold(drop_p), 1.f / (1.f - drop_p), seed_dev, site));
+  return PQ3D_OK;
+}
+
+extern "C" int pq3d_mask_head_finalize_bwd(const float* d_logits, const uint8_t* masks, int n_mem, void* d_raw_bf16, int B,
+                                           int S, int N, int Np, void* stream) {
+  PQ3D_CHECK_ARG(d_logits && masks && d_raw_bf16 && n_mem >= 1 && B > 0 && S > 0 && N > 0 && Np >= N,
+                 "pq3d_mask_head_finalize_bwd: bad argument");
+  const int64_t rows = static_cast<int64_t>(B) * S;
+  int64_t blocks = (rows * Np + 255) / 256;
+  if (blocks > sm_count() * 16) blocks = sm_count() * 16;
+  PQ3D_CUDA(launch_kernel(mask_head_finalize_bwd_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0,
+                          reinterpret_cast<cudaStream_t>(stream), d_logits, masks, n_mem,
+                          reinterpret_cast<__nv_bfloat16*>(d_raw_bf16), rows, N, Np));
   return PQ3D_OK;
 }

@@ -166,13 +166,20 @@ class MaskHeadSegLevel(nn.Module):
         raw = self._ws(key, "raw", (B, S, N), torch.float32, dev)
         ops.linear(kcat, qcat, raw, M=S, N=N, K=n * D, groups=B, a_group_rows=S, w_group_rows=N, ldc=N,
                    c_group_stride=S * N)
-        ops.mask_head_finalize(raw, ptrs, n, masks[n], out_logits, out_attn, B, S, N)
+        ops.mask_head_finalize(raw, ptrs, n, masks[n], out_logits, out_attn, B, S, N, masks=masks)
 
     def forward(self, query, seg_fts_for_match, seg_masks, offline_attn_masks=None, skip_prediction=False):
         if skip_prediction:
             return None, None, offline_attn_masks
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            raise NotImplementedError("pq3d_b200.MaskHeadSegLevel: inference path only — call under torch.no_grad()")
+        if self.training or (torch.is_grad_enabled() and (any(p.requires_grad for p in self.parameters())
+                                                          or query.requires_grad)):
+            # training: forward + backward composed from the same kernels (MaskHeadTrain); no autograd fallback
+            feats = list(seg_fts_for_match)[:len(self.mask_pred_list)]
+            meta = dict(feats=feats, seg_masks=seg_masks)
+            cls_logits, mask_logits = _MaskHeadFunction.apply(self, meta, query, *[f[0] for f in feats],
+                                                              *list(self.parameters()))
+            attn_mask = meta["attn"] if offline_attn_masks is None else offline_attn_masks
+            return cls_logits, mask_logits, attn_mask
         dev = query.device
         B, N, D = query.shape
         S = seg_fts_for_match[0][0].shape[1]
@@ -186,3 +193,254 @@ class MaskHeadSegLevel(nn.Module):
         if offline_attn_masks is not None:
             attn_mask = offline_attn_masks
         return cls_logits, mask_logits, attn_mask
+
+
+# ------------------------------------------------------------------------------------------------------------
+# training: forward that keeps what the backward needs + the backward, composed from the same kernels
+# ------------------------------------------------------------------------------------------------------------
+def _pad64(n):
+    return (n + 63) // 64 * 64
+
+
+class MaskHeadTrain:
+    """One forward pass' worth of mask-head calls in training (the decoder calls the head once per layer application,
+    Query3DUnified once more at the end — modules/grounding/query_encoder.py:78-81, model/query3d_unified.py:184-190).
+
+    The k-projection is hoisted as in inference; its gradient is the SUM over all calls of `d_raw q`, accumulated in
+    fp32 and turned into `k_proj.weight` / feature gradients once, in `finish()`.  Everything GEMM-shaped runs on
+    pq3d_linear_bf16 (dgrad with transposed weights, wgrad on K-major transposes); the cls head's Dropout
+    (`MaskHeadSegLevel(dropout=0.1)`) uses the counter RNG (stream rng.SITE_MASK_HEAD + call index)."""
+
+    def __init__(self, mh: "MaskHeadSegLevel", seg_fts_for_match, seg_masks, B, N, seed=None):
+        from . import rng
+        self.rng = rng
+        self.mh, self.B, self.N = mh, B, N
+        feats = list(seg_fts_for_match)[:len(mh.mask_pred_list)]
+        self.n, self.D = len(feats), mh.hidden_size
+        n, D = self.n, self.D
+        dev = feats[0][0].device
+        self.dev = dev
+        self.S = S = feats[0][0].shape[1]
+        self.p = float(mh.cls_head[3].p) if mh.training else 0.0
+        self.seed = seed
+        if self.p > 0.0 and seed is None:
+            raise ValueError("mask head dropout needs the step's device seed")
+        l0, ln, l4 = mh.cls_head[0], mh.cls_head[2], mh.cls_head[4]
+        f = lambda t: t.detach().float().contiguous()                 # noqa: E731
+        w16 = lambda t: t.detach().to(bf16).contiguous()              # noqa: E731
+        self.C = C = l4.out_features
+        self.Cp = Cp = _pad64(C)
+        b4 = f(l4.bias).clone()
+        cols = slice(None) if mh.filter_out_classes is None else list(mh.filter_out_classes)
+        b4[..., cols] = float("-inf")
+        self.cols = cols
+        w4t = torch.zeros(l4.in_features, Cp, dtype=bf16, device=dev)
+        w4t[:, :C] = l4.weight.detach().t().to(bf16)
+        self.w = dict(w0=w16(l0.weight), w0t=w16(l0.weight.t()), b0=f(l0.bias), g=f(ln.weight)[None], be=f(ln.bias)[None],
+                      eps=ln.eps, w4=w16(l4.weight), w4t=w4t, b4=b4,
+                      wq=w16(torch.cat([l.q_proj.weight for l in mh.mask_pred_list], 0)),
+                      wqt=w16(torch.cat([l.q_proj.weight for l in mh.mask_pred_list], 0).t()),
+                      bq=f(torch.cat([l.q_proj.bias for l in mh.mask_pred_list], 0)),
+                      wk=[w16(l.k_proj.weight) for l in mh.mask_pred_list],
+                      wkt=[w16(l.k_proj.weight.t()) for l in mh.mask_pred_list])
+        self.masks = torch.empty(n + 1, B, S, dtype=torch.bool, device=dev)
+        self.x16 = []
+        self.kcat = torch.empty(B * S, n * D, dtype=bf16, device=dev)
+        for j, (feat, mask, _pos) in enumerate(feats):
+            if mask.ndim != 2 or mask.dtype != torch.bool:
+                raise ValueError("mask head: per-memory masks must be bool (B, S), True = ignore")
+            self.masks[j].copy_(mask)
+            x = torch.empty(B * S, D, dtype=bf16, device=dev)
+            ops.ingest_memory(feat.detach().contiguous().float(), None, None, x, S)
+            ops.linear(x, self.w["wk"][j], self.kcat[:, j * D:(j + 1) * D], M=B * S, N=D, K=D, ldc=n * D,
+                       row_zero=self.masks[j])
+            self.x16.append(x)
+        if seg_masks.dtype != torch.bool:
+            raise TypeError("mask head: seg_masks must be torch.bool (True = padded segment)")
+        self.masks[n].copy_(seg_masks)
+        self.ptrs = torch.tensor([self.masks[j].data_ptr() for j in range(n)], dtype=torch.int64).to(dev)
+        self.kcatT = None
+        self.d_kcat = None
+        self.grads = {}
+        self.calls = 0
+
+    def _acc(self, name, g):
+        self.grads[name] = g if name not in self.grads else self.grads[name] + g
+
+    def _site(self, call):
+        return self.rng.SITE_MASK_HEAD + call
+
+    # ---- one call -------------------------------------------------------------------------------------------
+    def call(self, q2d: torch.Tensor):
+        """q2d fp32 [B*N, D] -> (cls (B,N,C), mask_logits (B,S,N), attn_mask (B,N,S) bool, saved)."""
+        B, N, S, n, D, dev, w = self.B, self.N, self.S, self.n, self.D, self.dev, self.w
+        R = B * N
+        Hd = w["w0"].shape[0]
+        x16 = torch.empty(R, D, dtype=bf16, device=dev)
+        ops.cast_bf16(q2d, x16)
+        h = torch.empty(R, Hd, dtype=torch.float32, device=dev)
+        ops.linear(x16, w["w0"], h, M=R, N=Hd, K=D, bias=w["b0"], relu=True)
+        hg16 = torch.empty(R, Hd, dtype=bf16, device=dev)                 # ReLU gate of the backward
+        ops.cast_bf16(h, hg16)
+        hn16 = torch.empty(R, Hd, dtype=bf16, device=dev)
+        ops.add_layernorm(h, None, w["g"], w["be"], w["eps"], R, Hd, out_bf16=hn16)
+        call = self.calls
+        self.calls += 1
+        if self.p > 0.0:
+            ops.dropout_bf16(hn16, self.p, self.seed, self._site(call))
+        cls = torch.empty(B, N, self.C, dtype=torch.float32, device=dev)
+        ops.linear(hn16, w["w4"], cls, M=R, N=self.C, K=Hd, bias=w["b4"], ldc=self.C)
+        qcat = torch.empty(R, n * D, dtype=bf16, device=dev)
+        ops.linear(x16, w["wq"], qcat, M=R, N=n * D, K=D, bias=w["bq"])
+        raw = torch.empty(B, S, N, dtype=torch.float32, device=dev)
+        ops.linear(self.kcat, qcat, raw, M=S, N=N, K=n * D, groups=B, a_group_rows=S, w_group_rows=N, ldc=N,
+                   c_group_stride=S * N)
+        logits = torch.empty(B, S, N, dtype=torch.float32, device=dev)
+        attn = torch.empty(B, N, S, dtype=torch.bool, device=dev)
+        ops.mask_head_finalize(raw, self.ptrs, n, self.masks[n], logits, attn, B, S, N, masks=self.masks)
+        return cls, logits, attn, dict(x16=x16, h=h, hg16=hg16, hn16=hn16, qcat=qcat, call=call)
+
+    # ---- its backward ---------------------------------------------------------------------------------------
+    def _tcast(self, x, rows, cols, want_c=False, gate=None):
+        xt = torch.empty(cols, _pad64(rows), dtype=bf16, device=self.dev)
+        xc = torch.empty(rows, cols, dtype=bf16, device=self.dev) if want_c else None
+        ops.transpose_cast(x, xt, xc, gate=gate)
+        return xt, xc
+
+    def _wgrad(self, dyT, xT, n_out, n_in):
+        dW = torch.empty(n_out, n_in, dtype=torch.float32, device=self.dev)
+        ops.linear(dyT, xT, dW, M=n_out, N=n_in, K=dyT.shape[1])
+        return dW
+
+    def _colsum(self, x, gate=None):
+        out = torch.empty(x.shape[1], dtype=torch.float32, device=self.dev)
+        ops.colsum(x, out, gate=gate)
+        return out
+
+    def call_bwd(self, sv, d_cls, d_logits):
+        """-> d_q fp32 [B*N, D] (or None when neither prediction carries a gradient)."""
+        B, N, S, n, D, dev, w = self.B, self.N, self.S, self.n, self.D, self.dev, self.w
+        R, C, Cp = B * N, self.C, self.Cp
+        Hd = w["w0"].shape[0]
+        parts = []
+        xT = None
+        if d_cls is not None:
+            dc = d_cls.detach().reshape(R, C).float().clone()
+            dc[:, self.cols] = 0.0                                  # cls_logits[..., filter] = -inf overwrote those columns
+            self._acc("cls_head.4.bias", self._colsum(dc))
+            dc16 = torch.zeros(R, Cp, dtype=bf16, device=dev)
+            dcT = torch.empty(C, _pad64(R), dtype=bf16, device=dev)
+            ops.transpose_cast(dc, dcT, dc16[:, :C])
+            hnT, _ = self._tcast(sv["hn16"], R, Hd)
+            self._acc("cls_head.4.weight", self._wgrad(dcT, hnT, C, Hd))
+            d_hd16 = torch.empty(R, Hd, dtype=bf16, device=dev)
+            ops.linear(dc16, w["w4t"], d_hd16, M=R, N=Hd, K=Cp)
+            if self.p > 0.0:
+                ops.dropout_bf16(d_hd16, self.p, self.seed, self._site(sv["call"]))
+            d_hn = d_hd16.float()
+            d_h = torch.empty(R, Hd, dtype=torch.float32, device=dev)
+            dg = torch.zeros(1, Hd, dtype=torch.float32, device=dev)
+            db = torch.zeros(1, Hd, dtype=torch.float32, device=dev)
+            ops.layernorm_bwd(sv["h"], None, w["g"], d_hn, w["eps"], R, Hd, d_x=d_h, d_gamma=dg, d_beta=db)
+            self._acc("cls_head.2.weight", dg[0])
+            self._acc("cls_head.2.bias", db[0])
+            self._acc("cls_head.0.bias", self._colsum(d_h, gate=sv["hg16"]))
+            d_preT, d_pre16 = self._tcast(d_h, R, Hd, want_c=True, gate=sv["hg16"])
+            xT, _ = self._tcast(sv["x16"], R, D)
+            self._acc("cls_head.0.weight", self._wgrad(d_preT, xT, Hd, D))
+            d_xa = torch.empty(R, D, dtype=torch.float32, device=dev)
+            ops.linear(d_pre16, w["w0t"], d_xa, M=R, N=D, K=Hd)
+            parts.append(d_xa)
+        if d_logits is not None:
+            Np, Sp = _pad64(N), _pad64(S)
+            d_raw16 = torch.empty(B * S, Np, dtype=bf16, device=dev)
+            ops.mask_head_finalize_bwd(d_logits.detach().float().contiguous(), self.masks, n, d_raw16, B, S, N)
+            d_rawT = torch.empty(B, 1, Np, Sp, dtype=bf16, device=dev)
+            ops.transpose_cast(d_raw16.view(B, 1, S, Np), d_rawT)
+            if self.kcatT is None:
+                self.kcatT = torch.empty(B, 1, n * D, Sp, dtype=bf16, device=dev)
+                ops.transpose_cast(self.kcat.view(B, 1, S, n * D), self.kcatT)
+            d_qcat = torch.empty(R, n * D, dtype=torch.float32, device=dev)
+            ops.linear(d_rawT.view(B * Np, Sp), self.kcatT.view(B * n * D, Sp), d_qcat, M=N, N=n * D, K=Sp, groups=B,
+                       a_group_rows=Np, w_group_rows=n * D, ldc=n * D, c_group_stride=N * n * D)
+            qcatT = torch.empty(B, 1, n * D, Np, dtype=bf16, device=dev)
+            ops.transpose_cast(sv["qcat"].view(B, 1, N, n * D), qcatT)
+            tmp = torch.empty(B * S, n * D, dtype=torch.float32, device=dev)
+            q2 = qcatT.view(B * n * D, Np)
+            for j in range(n):
+                ops.linear(d_raw16, q2[j * D:], tmp[:, j * D:(j + 1) * D], M=S, N=D, K=Np, groups=B, a_group_rows=S,
+                           w_group_rows=n * D, ldc=n * D, c_group_stride=S * n * D, row_zero=self.masks[j],
+                           row_zero_group_stride=S)
+            if self.d_kcat is None:
+                self.d_kcat = tmp
+            else:
+                ops.add3(self.d_kcat, tmp, None, self.d_kcat)
+            d_bq = self._colsum(d_qcat)
+            d_qcatT, d_qcat16 = self._tcast(d_qcat, R, n * D, want_c=True)
+            if xT is None:
+                xT, _ = self._tcast(sv["x16"], R, D)
+            d_wq = self._wgrad(d_qcatT, xT, n * D, D)
+            for j in range(n):
+                self._acc(f"mask_pred_list.{j}.q_proj.weight", d_wq[j * D:(j + 1) * D])
+                self._acc(f"mask_pred_list.{j}.q_proj.bias", d_bq[j * D:(j + 1) * D])
+            d_xb = torch.empty(R, D, dtype=torch.float32, device=dev)
+            ops.linear(d_qcat16, w["wqt"], d_xb, M=R, N=D, K=n * D)
+            parts.append(d_xb)
+        if not parts:
+            return None
+        if len(parts) == 1:
+            return parts[0]
+        d_q = torch.empty(R, D, dtype=torch.float32, device=dev)
+        ops.add3(parts[0], parts[1], None, d_q)
+        return d_q
+
+    def finish(self, want_feat_grads=True):
+        """k_proj weight gradients (and d_feat per memory) from the accumulated d_kcat; returns (param grads, d_feats)."""
+        B, S, n, D, dev, w = self.B, self.S, self.n, self.D, self.dev, self.w
+        d_feats = [None] * n
+        if self.d_kcat is not None:
+            rows = B * S
+            for j in range(n):
+                dk = self.d_kcat[:, j * D:(j + 1) * D]
+                dkT = torch.empty(D, _pad64(rows), dtype=bf16, device=dev)
+                dk16 = torch.empty(rows, D, dtype=bf16, device=dev)
+                ops.transpose_cast(dk, dkT, dk16)
+                xT, _ = self._tcast(self.x16[j], rows, D)
+                self._acc(f"mask_pred_list.{j}.k_proj.weight", self._wgrad(dkT, xT, D, D))
+                if want_feat_grads:
+                    d_f = torch.empty(rows, D, dtype=torch.float32, device=dev)
+                    ops.linear(dk16, w["wkt"][j], d_f, M=rows, N=D, K=D)
+                    d_feats[j] = d_f.view(B, S, D)
+        return self.grads, d_feats
+
+
+class _MaskHeadFunction(torch.autograd.Function):
+    """Standalone training call of MaskHeadSegLevel (the one Query3DUnified makes after the decoder)."""
+
+    @staticmethod
+    def forward(ctx, mh, meta, query, *rest):
+        n = len(mh.mask_pred_list)
+        B, N, D = query.shape
+        seed = None
+        if mh.training and float(mh.cls_head[3].p) > 0.0:
+            seed = torch.randint(0, 2 ** 31 - 1, (1,), dtype=torch.int32, device=query.device)
+        t = MaskHeadTrain(mh, meta["feats"], meta["seg_masks"], B, N, seed)
+        cls, logits, attn, sv = t.call(query.detach().reshape(B * N, D).float().contiguous())
+        meta["attn"] = attn
+        ctx.t, ctx.sv, ctx.mh, ctx.n = t, sv, mh, n
+        ctx.in_dtype = query.dtype
+        return cls, logits
+
+    @staticmethod
+    def backward(ctx, d_cls, d_logits):
+        t, mh, n = ctx.t, ctx.mh, ctx.n
+        B, N, D = t.B, t.N, t.D
+        d_q = t.call_bwd(ctx.sv, d_cls, d_logits)
+        grads, d_feats = t.finish(want_feat_grads=any(ctx.needs_input_grad[3:3 + n]))
+        out = [None, None, None if d_q is None else d_q.view(B, N, D).to(ctx.in_dtype)]
+        out += [d_feats[j] if ctx.needs_input_grad[3 + j] else None for j in range(n)]
+        for name, p in mh.named_parameters():
+            g = grads.get(name)
+            out.append(None if g is None else g.reshape(p.shape).to(p.dtype))
+        ctx.t = ctx.sv = None
+        return tuple(out)

@@ -237,7 +237,9 @@ def pack_mask(mask: torch.Tensor, bits: Optional[torch.Tensor] = None, unmask_fu
 
 
 def mask_head_finalize(raw: torch.Tensor, mem_mask_ptrs: torch.Tensor, n_mem: int, seg_masks: torch.Tensor,
-                       mask_logits: torch.Tensor, attn_mask: torch.Tensor, B: int, S: int, N: int):
+                       mask_logits: torch.Tensor, attn_mask: torch.Tensor, B: int, S: int, N: int, masks=None):
+    """masks: the [n_mem + 1, B, S] bool tensor the pointer table refers to (unused here; the CPU emulation of the
+    tests reads it instead of dereferencing device pointers)."""
     _chk(raw, torch.float32, "raw")
     _chk(mask_logits, torch.float32, "mask_logits")
     rc = _lib.lib().pq3d_mask_head_finalize(raw.data_ptr(), mem_mask_ptrs.data_ptr(), n_mem, seg_masks.data_ptr(),
@@ -449,4 +451,17 @@ def dropout_bf16(x: torch.Tensor, drop_p: float, seed: torch.Tensor, site: int):
         raise ValueError("dropout_bf16 works in place on a contiguous tensor")
     rc = _lib.lib().pq3d_dropout_bf16(x.data_ptr(), x.numel(), float(drop_p), seed.data_ptr(), site, _stream())
     _lib.check(rc, "pq3d_dropout_bf16")
+    _count()
+
+
+def mask_head_finalize_bwd(d_logits: torch.Tensor, masks: torch.Tensor, n_mem: int, d_raw16: torch.Tensor, B: int, S: int,
+                           N: int):
+    """d_logits fp32 (B, S, N) contiguous, masks bool [n_mem + 1, B, S] contiguous -> d_raw16 bf16 [B*S, Np]."""
+    _chk(d_logits, torch.float32, "d_logits")
+    _chk(d_raw16, bf16, "d_raw16", 2)
+    if not d_logits.is_contiguous() or not masks.is_contiguous() or not d_raw16.is_contiguous():
+        raise ValueError("mask_head_finalize_bwd operands must be contiguous")
+    rc = _lib.lib().pq3d_mask_head_finalize_bwd(d_logits.data_ptr(), masks.data_ptr(), n_mem, d_raw16.data_ptr(), B, S, N,
+                                                d_raw16.shape[1], _stream())
+    _lib.check(rc, "pq3d_mask_head_finalize_bwd")
     _count()

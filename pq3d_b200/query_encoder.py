@@ -470,13 +470,8 @@ class QueryMaskEncoder(nn.Module):
                                                           or input_dict["query"][0].requires_grad)):
             # training path: forward (with the train-mode dropouts) + backward composed from the same kernels
             # (train_engine.py); scope limits raise.  module.train() under no_grad runs the same forward.
-            if mask_head is not None or self.use_self_mask:
-                raise NotImplementedError(
-                    "pq3d_b200.QueryMaskEncoder: the in-loop mask head / use_self_mask have no backward kernels yet — "
-                    "train with mask_head=None, or call under torch.no_grad(); there is deliberately no PyTorch "
-                    "autograd fallback")
             from . import train_engine
-            return train_engine.run(self, input_dict, pairwise_locs), [], []
+            return train_engine.run(self, input_dict, pairwise_locs, mask_head)
         query, query_masks, query_pos = input_dict["query"]
         dev = query.device
         B, N, D = query.shape

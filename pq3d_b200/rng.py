@@ -13,6 +13,7 @@ SITE_FFN_SUBLAYER = 5
 SITE_FFN_HIDDEN = 6       # idx = row*F + col
 SITE_SA_PROBS = 7         # plain self-attention probabilities, idx = ((b*H+h)*N + n)*ceil128(S) + key
 SITE_CA_PROBS = 8         # + memory index in `memories` order
+SITE_MASK_HEAD = 1 << 16  # + call index: the cls head's Dropout on LN(relu(linear0 q)), idx = row*hidden + col
 
 
 def site(layer: int, kind: int) -> int:

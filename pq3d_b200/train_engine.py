@@ -64,8 +64,9 @@ def _side_streams(dev, n):
 # forward
 # ------------------------------------------------------------------------------------------------
 def forward(enc, query, query_pos, query_masks, mems: List[Tuple[str, torch.Tensor, torch.Tensor, Optional[torch.Tensor]]],
-            pairwise_locs):
-    """mems: [(name, feat (B,S,D), mask bool, pos or None)] for the active memories.  Returns (q_out (B,N,D) fp32, saved)."""
+            pairwise_locs, mh=None, mh_kw=None):
+    """mems: [(name, feat (B,S,D), mask bool, pos or None)] for the active memories; mh / mh_kw: our MaskHeadSegLevel and
+    the keyword tensors Query3DUnified binds to it (in-loop mask head).  Returns (q_out (B,N,D) fp32, predictions, saved)."""
     dev = query.device
     B, N, D = query.shape
     H, L = enc.num_heads, enc.num_layers
@@ -80,10 +81,12 @@ def forward(enc, query, query_pos, query_masks, mems: List[Tuple[str, torch.Tens
     p_drop = float(enc.train_dropout) if enc.training else 0.0
     p_mem = float(enc.memory_dropout) if enc.training else 0.0
     seed = None
-    if p_drop > 0.0:
-        if N > 128:
-            raise NotImplementedError("pq3d_b200 training path: dropout needs the fused attention backward (N <= 128 "
-                                      "queries); set `encoder.train_dropout = 0.0` for more queries")
+    if p_drop > 0.0 and N > 128:
+        raise NotImplementedError("pq3d_b200 training path: dropout needs the fused attention backward (N <= 128 "
+                                  "queries); set `encoder.train_dropout = 0.0` for more queries")
+    if enc.num_blocks > 1 and N > 128:
+        raise NotImplementedError("pq3d_b200 training path: num_blocks > 1 needs the fused attention backward (N <= 128)")
+    if p_drop > 0.0 or (mh is not None and mh.training and float(mh.cls_head[3].p) > 0.0):
         if getattr(enc, "_drop_seed", None) is None or enc._drop_seed.device != dev:
             enc._drop_seed = torch.randint(0, 2 ** 31 - 1, (1,), dtype=torch.int32, device=dev)
         enc._drop_seed.add_(0x3C6EF35F)
@@ -131,9 +134,37 @@ def forward(enc, query, query_pos, query_masks, mems: List[Tuple[str, torch.Tens
         else:
             ops.add_layernorm(y, res, w["gamma"], w["beta"], w["eps"], R, D, G=G, y_group_stride=R * D, **outs)
 
-    for i in range(L):
+    mht = None
+    if mh is not None:
+        from .mask_head import MaskHeadTrain
+        mht = MaskHeadTrain(mh, mh_kw["seg_fts_for_match"], mh_kw["seg_masks"], B, N, seed)
+    sv["mht"] = mht
+    preds: List[torch.Tensor] = []
+    for step in range(enc.num_blocks * L):
+        i = step % L
         lw = pk.layers[i]
-        lay = dict(groups=[])
+        lay = dict(groups=[], i=i, blk=step // L)
+        step_masks: Dict = {}
+        if mht is not None:
+            # in-loop mask head on the layer's input query (query_encoder.py:78-81); its attention mask (detached, bool)
+            # replaces the scene memories' masks for this layer when use_self_mask (:82-88)
+            cls, logits, attn, lay["mh"] = mht.call(q32)
+            preds += [cls, logits]
+            if enc.use_self_mask:
+                fixed = torch.empty(attn.shape, dtype=torch.bool, device=dev)
+                tiles = torch.empty(B, dtype=torch.int32, device=dev)
+                bits = ops.pack_mask(attn, None, unmask_full_rows=True, mask_fixed=fixed.view(torch.uint8),
+                                     active_tiles=tiles)
+                sv["final_mask"] = fixed
+                for m in sv["mems"]:
+                    if m != "prompt":
+                        step_masks[m] = (bits, (bits.stride(0), 0, bits.stride(1)), tiles)
+        elif enc.use_self_mask:
+            raise ValueError("use_self_mask=True needs a mask_head that returns an attention mask")
+
+        def mem_mask(m):
+            st_ = sv["mems"][m]
+            return step_masks.get(m, (st_.bits, st_.strides, st_.tiles))
         for gi, grp in enumerate(program):
             g = len(grp)
             w = lw["groups"][grp]
@@ -142,7 +173,7 @@ def forward(enc, query, query_pos, query_masks, mems: List[Tuple[str, torch.Tens
             O = _e((g, R, D), bf16, dev)
             st_m, st_l = _e((g, B, H, N), f32, dev), _e((g, B, H, N), f32, dev)
             am = [ops.AttnMemory(sv["mems"][m].K, i * D, sv["mems"][m].Vt, i * D, sv["mems"][m].S, sv["mems"][m].Sp,
-                                 sv["mems"][m].bits, *sv["mems"][m].strides, kv_tiles=sv["mems"][m].tiles) for m in grp]
+                                 mem_mask(m)[0], *mem_mask(m)[1], kv_tiles=mem_mask(m)[2]) for m in grp]
             psites = [rng.site(i, rng.SITE_CA_PROBS + enc.memories.index(m)) for m in grp]
             ops.attention(Q, D, am, O, R * D, B, H, N, True, stats=(st_m, st_l), drop_p=p_drop, seed=seed, sites=psites)
             y = _e((g, R, D), f32, dev)
@@ -159,7 +190,8 @@ def forward(enc, query, query_pos, query_masks, mems: List[Tuple[str, torch.Tens
             q_new, xq_new, xv_new = _e((R, D), f32, dev), _e((R, D), bf16, dev), _e((R, D), bf16, dev)
             add_ln(y, q32, w, g, rng.site(i, rng.SITE_CA_SUBLAYER + gi), row_w, pos=qpos, out_f32=q_new, out_bf16=xv_new,
                    out_pos_bf16=xq_new)
-            lay["groups"].append(dict(grp=grp, gi=gi, xq=xq, Q=Q, O=O, m=st_m, l=st_l, y=y, res=q32, row_w=row_w))
+            lay["groups"].append(dict(grp=grp, gi=gi, xq=xq, Q=Q, O=O, m=st_m, l=st_l, y=y, res=q32, row_w=row_w,
+                                      masks={m: mem_mask(m) for m in grp}))
             q32, xq, xv = q_new, xq_new, xv_new
         sa = lw["sa"]
         QK = _e((R, 2 * D), bf16, dev)
@@ -195,7 +227,7 @@ def forward(enc, query, query_pos, query_masks, mems: List[Tuple[str, torch.Tens
         lay["ffn"] = dict(xv=xv, h=h, y=yf, res=q32)
         q32, xq, xv = q_new, xq_new, xv_new
         sv["layers"].append(lay)
-    return q32.view(B, N, D), sv
+    return q32.view(B, N, D), preds, sv
 
 
 # ------------------------------------------------------------------------------------------------
@@ -226,8 +258,12 @@ class _Bwd:
         self.forked = set()
         n_mem = len(enc.memories)
         # in_proj gradients of every cross-attention are written in place by the wgrad GEMMs: rows [0, D) from the
-        # query side, [D, 2D) / [2D, 3D) from the hoisted K / V projections
-        self.G_ca = _e((self.L, n_mem, 3 * self.D, self.D), f32, self.dev)
+        # query side, [D, 2D) / [2D, 3D) from the hoisted K / V projections.  One buffer per block (the same layers are
+        # re-applied num_blocks times): block 0 also receives the K / V rows, the others start from zero.
+        self.G_blk = [(_e if blk == 0 else _z)((self.L, n_mem, 3 * self.D, self.D), f32, self.dev)
+                      for blk in range(enc.num_blocks)]
+        self.G_ca = self.G_blk[0]
+        self.kv_written = set()
 
     # ---- streams ----------------------------------------------------------------------------------
     def on(self, stream, *deps):
@@ -446,7 +482,7 @@ class _Bwd:
         self.keep += [d_xq, d_xv, V, Ktp]
         return d_in
 
-    def group_bwd(self, i, s, d_out, d_pos, mem_grads):
+    def group_bwd(self, i, s, d_out, d_pos, mem_grads, blk=0):
         R, D, B, N, H, dev, pk = self.R, self.D, self.B, self.N, self.H, self.dev, self.pk
         grp = s["grp"]
         g = len(grp)
@@ -481,12 +517,22 @@ class _Bwd:
                 dO = self.dgrad(d_y16[jj], pk.T(w["wo"], jj * D, D), D, out_dtype=bf16)
                 mg = mem_grads[m]
                 S, Sp = st.S, st.Sp
+                m_bits, m_strides, _ = s["masks"][m]
                 if fused:
+                    first = (m, i) not in self.kv_written          # later blocks of the same layer: accumulate
+                    self.kv_written.add((m, i))
+                    if first:
+                        dK_dst, dV_dst, col = mg["dK"], mg["dV"], i * D
+                    else:
+                        dK_dst, dV_dst, col = _z((B * Sp, D), bf16, dev), _z((B * Sp, D), bf16, dev), 0
                     self.attention_bwd_fused(s["Q"], jj * D, dO, s["O"][jj], st.K, i * D, mg["V"], i * D, S, Sp, s["m"][jj],
-                                             s["l"][jj], mg["dK"], i * D, mg["dV"], i * D, dQ, jj * D, mask_bits=st.bits,
-                                             mask_strides=st.strides,
+                                             s["l"][jj], dK_dst, col, dV_dst, col, dQ, jj * D, mask_bits=m_bits,
+                                             mask_strides=m_strides,
                                              drop=None if self.sv["p_drop"] == 0.0 else
                                              self.drop(i, rng.SITE_CA_PROBS + self.enc.memories.index(m)))
+                    if not first:
+                        mg["dK"][:, i * D:(i + 1) * D].add_(dK_dst)
+                        mg["dV"][:, i * D:(i + 1) * D].add_(dV_dst)
                 else:
                     Qv = _heads(s["Q"], B, N, N, H, jj * D)
                     Kv = _heads(st.K, B, S, Sp, H, i * D)
@@ -495,10 +541,10 @@ class _Bwd:
                     Ktp = Kt.as_strided((B, H, 64, Sp), (Sp, 64 * Kt.stride(0), Kt.stride(0), 1), i * D * Kt.stride(0))
                     self.attention_bwd(Qv, Kv, Vv, Ktp, dO, s["O"][jj], s["m"][jj], s["l"][jj], S, Sp,
                                        _heads(dQ, B, N, N, H, jj * D), _heads(mg["dK"], B, S, Sp, H, i * D),
-                                       _heads(mg["dV"], B, S, Sp, H, i * D), mask_bits=st.bits, mask_strides=st.strides)
+                                       _heads(mg["dV"], B, S, Sp, H, i * D), mask_bits=m_bits, mask_strides=m_strides)
                 self.keep.append(dO)
         self.join([st_ for st_ in used if st_ is not None])
-        G = self.G_ca[i]
+        G = self.G_blk[blk][i]
         step = idx[1] - idx[0] if g > 1 else 0
         regular = all(idx[k + 1] - idx[k] == step for k in range(g - 1)) and (g == 1 or step > 0)
         dQT, dQ16 = self.tcast(dQ, R, g * D, want_c=fused)
@@ -515,7 +561,8 @@ class _Bwd:
                     self.wgrad(dQT[jj * D:(jj + 1) * D], xqT, D, D, out=G[j, :D])
         mg_q = mem_grads["_q"]
         for jj, j in enumerate(idx):
-            mg_q[(i, j)] = d_bq[jj * D:(jj + 1) * D]
+            prev = mg_q.get((i, j))
+            mg_q[(i, j)] = d_bq[jj * D:(jj + 1) * D] if prev is None else prev + d_bq[jj * D:(jj + 1) * D]
         d_xq = self.dgrad(dQ16, pk.T(w["wq"]), D)
         d_in = _e((R, D), f32, dev)
         ops.add3(d_res, d_xq, None, d_in)
@@ -525,7 +572,7 @@ class _Bwd:
         return d_in
 
     # ---- whole decoder ------------------------------------------------------------------------------------
-    def run(self, d_out: torch.Tensor):
+    def run(self, d_out: torch.Tensor, d_preds=()):
         sv, B, N, D, L, R, dev, pk = self.sv, self.B, self.N, self.D, self.L, self.R, self.dev, self.pk
         n_mem = len(self.enc.memories)
         mem_grads: Dict = {"_q": {}}
@@ -539,12 +586,23 @@ class _Bwd:
             mem_grads[name] = dict(V=V, Kt=Kt, dK=_z((B * st.Sp, L * D), bf16, dev), dV=_z((B * st.Sp, L * D), bf16, dev))
         d_q = d_out.detach().reshape(R, D).float().contiguous()
         d_pos = _z((R, D), f32, dev)
-        for i in reversed(range(L)):
-            lay = sv["layers"][i]
+        mht = sv.get("mht")
+        for step in reversed(range(len(sv["layers"]))):
+            lay = sv["layers"][step]
+            i = lay["i"]
             d_q = self.ffn_bwd(i, lay["ffn"], d_q)
             d_q = self.sa_bwd(i, lay["sa"], d_q, d_pos)
             for s in reversed(lay["groups"]):
-                d_q = self.group_bwd(i, s, d_q, d_pos, mem_grads)
+                d_q = self.group_bwd(i, s, d_q, d_pos, mem_grads, lay["blk"])
+            if mht is not None:                 # the mask head read this layer's input query
+                d_cls, d_logits = d_preds[2 * step], d_preds[2 * step + 1]
+                if d_cls is not None or d_logits is not None:
+                    d_mh = mht.call_bwd(lay["mh"], d_cls, d_logits)
+                    if d_mh is not None:
+                        d_sum = _e((R, D), f32, dev)
+                        ops.add3(d_q, d_mh, None, d_sum)
+                        self.keep += [d_q, d_mh]
+                        d_q = d_sum
             self.keep.append(d_q)
         # memory side: weight / bias gradients of the hoisted K and V projections, input gradients
         d_mem = {}
@@ -569,54 +627,77 @@ class _Bwd:
             d_xv = self.dgrad(mg["dV"], pk.T_mem("v", j, L, D), D)
             for i in range(L):
                 pre = f"unified_encoder.{i}.cross_attn_list.{j}.multihead_attn."
-                self.acc(pre + "in_proj_weight", self.G_ca[i, j])
+                for G in self.G_blk:
+                    self.acc(pre + "in_proj_weight", G[i, j])
                 self.acc(pre + "in_proj_bias", G_b[i, j])
             d_feat = _e((rows, D), f32, dev)
             ops.add3(d_xk, d_xv, None, d_feat)
             self.keep += [d_xk, d_xv]
             d_mem[name] = (d_feat.view(B, st.Sp, D)[:, :st.S], d_xk.view(B, st.Sp, D)[:, :st.S] if st.has_pos else None)
+        mh_out = (None, None)
+        if mht is not None:
+            mh_out = mht.finish()
         self.join()
         self.keep.clear()
-        return d_q.view(B, N, D), d_pos.view(B, N, D), d_mem, self.grads
+        return d_q.view(B, N, D), d_pos.view(B, N, D), d_mem, self.grads, mh_out
 
 
 class DecoderFunction(torch.autograd.Function):
-    """forward(enc, meta, query, query_pos, feat_0, pos_0, ..., *params) -> decoded queries (B, N, D)."""
+    """forward(enc, meta, query, query_pos, feat_0, pos_0, ..., *mask-head features, *decoder params, *mask-head params)
+    -> (decoded queries (B, N, D), cls_0, mask_logits_0, cls_1, ...)."""
 
     @staticmethod
     def forward(ctx, enc, meta, query, query_pos, *rest):
         n = len(meta["names"])
         feats, poss = rest[0:2 * n:2], rest[1:2 * n:2]
         mems = [(meta["names"][k], feats[k], meta["masks"][k], poss[k]) for k in range(n)]
-        out, sv = forward(enc, query, query_pos, meta["query_masks"], mems, meta["pairwise_locs"])
+        out, preds, sv = forward(enc, query, query_pos, meta["query_masks"], mems, meta["pairwise_locs"], meta["mh"],
+                                 meta["mh_kw"])
         sv["canon"] = meta["canon"]
+        meta["final_mask"] = sv.get("final_mask")
         ctx.enc, ctx.sv, ctx.meta = enc, sv, meta
         ctx.in_dtypes = (query.dtype, query_pos.dtype, [None if t is None else t.dtype for t in rest[:2 * n]])
-        return out
+        return (out, *preds)
 
     @staticmethod
-    def backward(ctx, d_out):
+    def backward(ctx, d_out, *d_preds):
         enc, sv, meta = ctx.enc, ctx.sv, ctx.meta
-        d_q, d_pos, d_mem, grads = _Bwd(enc, sv).run(d_out)
+        if d_out is None:
+            d_out = torch.zeros(sv["B"], sv["N"], sv["D"], dtype=f32, device=sv["qpos"].device)
+        d_q, d_pos, d_mem, grads, (mh_grads, mh_dfeats) = _Bwd(enc, sv).run(d_out, d_preds)
         ctx.sv = None
+        n = len(meta["names"])
         out = [None, None, d_q.to(ctx.in_dtypes[0]), d_pos.to(ctx.in_dtypes[1])]
         for k, name in enumerate(meta["names"]):
             d_feat, d_p = d_mem[name]
             out.append(d_feat.to(ctx.in_dtypes[2][2 * k]) if ctx.needs_input_grad[4 + 2 * k] else None)
             out.append(d_p.to(ctx.in_dtypes[2][2 * k + 1])
                        if d_p is not None and ctx.needs_input_grad[5 + 2 * k] else None)
+        for j in range(meta["n_mh_feats"]):
+            g = None if mh_dfeats is None else mh_dfeats[j]
+            out.append(g if (g is not None and ctx.needs_input_grad[4 + 2 * n + j]) else None)
         for pname, p in meta["param_names"]:
             g = grads.get(pname)
+            out.append(None if g is None else g.reshape(p.shape).to(p.dtype))
+        for pname, p in meta["mh_param_names"]:
+            g = None if mh_grads is None else mh_grads.get(pname)
             out.append(None if g is None else g.reshape(p.shape).to(p.dtype))
         return tuple(out)
 
 
-def run(enc, input_dict: dict, pairwise_locs):
-    """Entry used by QueryMaskEncoder.forward when gradients are enabled."""
+def run(enc, input_dict: dict, pairwise_locs, mask_head=None):
+    """Entry used by QueryMaskEncoder.forward in training.  Returns (query, predictions_class, predictions_mask)."""
     if enc.structure == "gate":
         raise NotImplementedError("pq3d_b200 training path: structure='gate' is inference-only in this build")
-    if enc.num_blocks != 1:
-        raise NotImplementedError("pq3d_b200 training path: num_blocks must be 1")
+    mh, mh_kw = None, None
+    if mask_head is not None:
+        mh = enc._own_mask_head(mask_head)
+        if mh is None:
+            raise NotImplementedError(
+                "pq3d_b200 training path: the in-loop mask head must be pq3d_b200.MaskHeadSegLevel bound with "
+                "functools.partial(seg_fts_for_match=..., seg_masks=..., offline_attn_masks=None, skip_prediction=False) "
+                "as Query3DUnified wires it — an arbitrary callable has no backward here and there is no autograd fallback")
+        mh_kw = mask_head.keywords
     enc.last_memory_keep = []          # memory-dropout keep masks of this forward, in (layer, group) order (for tests)
     query, query_masks, query_pos = input_dict["query"]
     names = [m for g in enc._program() for m in g]
@@ -627,8 +708,17 @@ def run(enc, input_dict: dict, pairwise_locs):
             raise NotImplementedError("pq3d_b200 training path: multi-scale (list) memory features are inference-only")
         masks.append(mask)
         flat += [feat, pos]
+    mh_feats = [] if mh is None else [f[0] for f in list(mh_kw["seg_fts_for_match"])[:len(mh.mask_pred_list)]]
     params = list(enc.named_parameters())
+    mh_params = [] if mh is None else list(mh.named_parameters())
     first = {id(p): n for n, p in reversed(params)}
     canon = {n: first[id(p)] for n, p in enc.named_parameters(remove_duplicate=False)}
-    meta = dict(canon=canon, names=names, masks=masks, query_masks=query_masks, pairwise_locs=pairwise_locs, param_names=params)
-    return DecoderFunction.apply(enc, meta, query, query_pos, *flat, *[p for _, p in params])
+    meta = dict(canon=canon, names=names, masks=masks, query_masks=query_masks, pairwise_locs=pairwise_locs,
+                param_names=params, mh=mh, mh_kw=mh_kw, n_mh_feats=len(mh_feats), mh_param_names=mh_params)
+    outs = DecoderFunction.apply(enc, meta, query, query_pos, *flat, *mh_feats, *[p for _, p in params],
+                                 *[p for _, p in mh_params])
+    if enc.use_self_mask and meta.get("final_mask") is not None:
+        for m in input_dict.keys():                # the reference leaves the last attention mask in input_dict (:85-88)
+            if m not in ("query", "prompt"):
+                input_dict[m][1] = meta["final_mask"]
+    return outs[0], list(outs[1::2]), list(outs[2::2])

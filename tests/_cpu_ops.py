@@ -310,8 +310,22 @@ def gate_mix(gate_logits, query, update, out):
     ops._count()
 
 
-def mask_head_finalize(raw, mem_mask_ptrs, n_mem, seg_masks, mask_logits, attn_mask, B, S, N, mem_masks=None):
-    raise NotImplementedError("emulated through tests/_cpu_ops.mask_head hooks only")
+def mask_head_finalize(raw, mem_mask_ptrs, n_mem, seg_masks, mask_logits, attn_mask, B, S, N, masks=None):
+    cnt = (~masks[:n_mem]).sum(0).float()
+    v = raw.view(B, S, N) / (cnt[..., None] + 1e-8)
+    v = v.masked_fill(seg_masks.view(B, S, 1), -1e6)
+    mask_logits.view(B, S, N).copy_(v)
+    attn_mask.view(B, N, S).copy_((1.0 / (1.0 + torch.exp(-v)) < 0.5).permute(0, 2, 1))
+    ops._count()
+
+
+def mask_head_finalize_bwd(d_logits, masks, n_mem, d_raw16, B, S, N):
+    cnt = (~masks[:n_mem]).sum(0).float()
+    v = d_logits.view(B, S, N) / (cnt[..., None] + 1e-8)
+    v = v.masked_fill(masks[n_mem].view(B, S, 1), 0.0)
+    d_raw16.zero_()
+    d_raw16.view(B, S, -1)[..., :N].copy_(v.to(bf16))
+    ops._count()
 
 
 def _refresh(self):
@@ -330,7 +344,7 @@ def _refresh(self):
 
 PATCHED = ["linear", "bgemm", "attention", "attn_delta", "attention_bwd", "spatial_bias", "spatial_bias_bwd", "ingest_memory",
            "add_layernorm", "add_layernorm_train", "layernorm_bwd", "pack_mask", "cast_bf16", "transpose_cast", "colsum",
-           "add3", "dropout_bf16", "gate_mix"]
+           "add3", "dropout_bf16", "gate_mix", "mask_head_finalize", "mask_head_finalize_bwd"]
 
 
 @contextlib.contextmanager

@@ -134,3 +134,117 @@ def test_training_host_logic_dropout_and_memory_dropout():
         r = sdd[k].grad
         e = ((p.grad - r).norm() / r.norm().clamp_min(1e-12)).item()
         assert e <= 0.12, f"{k}: {e:.3e}"
+
+
+def _mask_head_setup(B=2, N=20, S=90, n=2, seed=8):
+    from pq3d_b200.mask_head import MaskHeadSegLevel
+    g = torch.Generator().manual_seed(seed)
+    mems = ["voxel", "mv", "pc"][:n]
+    mh = MaskHeadSegLevel(None, 768, 201, memories_for_match=mems, filter_out_classes=[0, 2], dropout=0.0)
+    sd = synth.draw_state_dict(synth.mask_head_param_shapes(n), seed)
+    mh.load_state_dict(sd, strict=True)
+    feats = []
+    for j in range(n):
+        mask = torch.rand(B, S, generator=g) < 0.2
+        feats.append([torch.randn(B, S, 768, generator=g), mask, None])
+    seg_masks = torch.zeros(B, S, dtype=torch.bool)
+    seg_masks[1, S - 7:] = True
+    for f in feats:
+        f[1][1, S - 7:] = True
+    q = torch.randn(B, N, 768, generator=g) * 0.5
+    return mh, sd, feats, seg_masks, q, g
+
+
+def test_mask_head_training_host_logic():
+    """MaskHeadSegLevel.forward under autograd (the call Query3DUnified makes after the decoder) on the emulated
+    kernels: predictions, query gradient, feature gradients and every parameter gradient against oracle autograd."""
+    mh, sd, feats, seg_masks, q, g = _mask_head_setup()
+    mh.train()
+    B, N, _ = q.shape
+    S = seg_masks.shape[1]
+    up_c, up_m = torch.randn(B, N, 201, generator=g), torch.randn(B, S, N, generator=g)
+    ql = q.clone().requires_grad_(True)
+    fl = [[f[0].clone().requires_grad_(True), f[1], None] for f in feats]
+    with _cpu_ops.cpu_backend():
+        cls, ml, attn = mh(ql, fl, seg_masks)
+        fin = torch.isfinite(cls)
+        ((cls.masked_fill(~fin, 0.0) * up_c).sum() + (ml * up_m).sum()).backward()
+    sdd = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    qo = q.clone().requires_grad_(True)
+    fo = [[f[0].clone().requires_grad_(True), f[1], None] for f in feats]
+    cls_o, ml_o, attn_o = O.mask_head_seg_level(qo, sdd, "", fo, seg_masks, filter_out_classes=[0, 2])
+    ((cls_o.masked_fill(~torch.isfinite(cls_o), 0.0) * up_c).sum() + (ml_o * up_m).sum()).backward()
+    assert torch.equal(torch.isfinite(cls), torch.isfinite(cls_o))
+    assert rel(cls.masked_fill(~fin, 0.0), cls_o.masked_fill(~fin, 0.0)) <= 2e-2
+    assert rel(ml, ml_o) <= 2e-2
+    l2 = lambda a, b: ((a.float() - b.float()).norm() / b.float().norm().clamp_min(1e-12)).item()     # noqa: E731
+    assert l2(ql.grad, qo.grad) <= 5e-2
+    for a, b in zip(fl, fo):
+        assert l2(a[0].grad, b[0].grad) <= 5e-2
+    for k, p in mh.named_parameters():
+        assert p.grad is not None, k
+        assert l2(p.grad, sdd[k].grad) <= 5e-2, (k, l2(p.grad, sdd[k].grad))
+
+
+def test_stage1_training_host_logic_mask_head_selfmask_blocks():
+    """Stage-1 (instance segmentation) training shape on the emulated kernels: parallel cross-attentions, the in-loop
+    mask head whose detached attention mask replaces the memory masks (use_self_mask), two blocks re-applying the same
+    layers, losses on every per-layer prediction — gradients of decoder and mask-head parameters vs oracle autograd."""
+    from functools import partial
+    from pq3d_b200.mask_head import MaskHeadSegLevel
+    B, N, S, L, K = 2, 16, 80, 2, 2
+    w = synth.Workload("s1", B, N, S, ["mv", "pc", "voxel"], "parallel", num_layers=L, num_blocks=K, use_self_mask=True,
+                       spatial_selfattn=True)
+    sd = synth.decoder_state_dict(w, seed=13, sharp=1.0)
+    inp, pw, dd = synth.make_decoder_inputs(w)
+    g = torch.Generator().manual_seed(21)
+    q, qm, qp = inp["query"]
+    inp["query"] = (torch.randn(q.shape, generator=g) * 0.5, qm, qp)
+    msd = synth.draw_state_dict(synth.mask_head_param_shapes(3), 17)
+    mh = MaskHeadSegLevel(None, 768, 201, memories_for_match=list(w.memories), filter_out_classes=[0, 2], dropout=0.0)
+    mh.load_state_dict(msd, strict=True)
+    mh.train()
+    seg_pad = ~dd["seg_pad_masks"]
+    enc = _build(w, sd).train()
+    enc.train_dropout = 0.0
+    n_pred = K * L
+    ups = [(torch.randn(B, N, 201, generator=g), torch.randn(B, S, N, generator=g)) for _ in range(n_pred)]
+    up_q = torch.randn(B, N, 768, generator=g)
+
+    def loss_of(out, pcs, pms):
+        tot = (out * up_q).sum()
+        for (uc, um), c, m in zip(ups, pcs, pms):
+            tot = tot + (c.masked_fill(~torch.isfinite(c), 0.0) * uc).sum() * 0.1 + (m.clamp_min(-100.0) * um).sum() * 0.1
+        return tot
+    x = synth.clone_input_dict(inp)
+    feats = [list(x[m]) for m in w.memories]
+    head = partial(mh, seg_fts_for_match=feats, seg_masks=seg_pad, offline_attn_masks=None, skip_prediction=False)
+    with _cpu_ops.cpu_backend():
+        out, pcs, pms = enc(x, pw, head)
+        assert len(pcs) == n_pred and len(pms) == n_pred
+        loss_of(out, pcs, pms).backward()
+    assert x["mv"][1].shape == (B, N, S) and x["mv"][1].dtype == torch.bool      # reference side effect (:85-88)
+    # oracle
+    sdd = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    msdd = {k: v.clone().requires_grad_(True) for k, v in msd.items()}
+    xo = synth.clone_input_dict(inp)
+    feats_o = [list(xo[m]) for m in w.memories]
+    head_o = lambda qq: O.mask_head_seg_level(qq, msdd, "", feats_o, seg_pad, filter_out_classes=[0, 2])   # noqa: E731
+    ro, pco, pmo = O.query_mask_encoder(sdd, O.DecoderCfg(**w.decoder_kwargs()), xo, pw, head_o)
+    loss_of(ro, pco, pmo).backward()
+    flips = sum(int(((a < 0) != (b < 0)).sum()) for a, b in zip(pms, pmo))
+    print(f"mask-logit sign flips vs oracle: {flips} of {sum(a.numel() for a in pms)}")
+    assert rel(out, ro) <= 5e-2
+    l2 = lambda a, b: ((a.float() - b.float()).norm() / b.float().norm().clamp_min(1e-12)).item()     # noqa: E731
+    worst = []
+    for k, p in enc.named_parameters():
+        if k.endswith("w_ks.bias"):
+            continue
+        assert p.grad is not None, k
+        worst.append((l2(p.grad, sdd[k].grad), k))
+    for k, p in mh.named_parameters():
+        assert p.grad is not None, k
+        worst.append((l2(p.grad, msdd[k].grad), "mask_head." + k))
+    worst.sort(reverse=True)
+    print(worst[:6])
+    assert worst[0][0] <= 0.15, worst[:4]
