@@ -13,8 +13,8 @@ through ONE `torch.autograd.Function` whose backward runs:
   streaming work     LayerNorm backward, softmax backward (both orientations), bias column sums, the
                      spatial-bias backward -> backward.cu
 
-Scope (raises otherwise): structures sequential / parallel / mixed, num_blocks = 1, one feature tensor per
-memory, no in-loop mask head, dropout disabled (`enc.train_dropout = 0.0`, memory_dropout = 0).
+Scope: structures sequential / parallel / mixed (`gate` raises), any num_blocks, multi-scale (per-layer) memory
+features, the in-loop mask head (our MaskHeadSegLevel) with use_self_mask, train-mode dropout and memory dropout.
 """
 from __future__ import annotations
 
@@ -38,7 +38,7 @@ def _z(shape, dtype, dev):
 
 
 class _Mem:
-    __slots__ = ("name", "S", "Sp", "xk", "xv", "K", "Vt", "bits", "strides", "tiles", "has_pos", "S_pitch")
+    __slots__ = ("name", "S", "Sp", "xk", "xv", "K", "Vt", "bits", "strides", "tiles", "has_pos", "S_pitch", "multi")
 
 
 def _heads(t2d: torch.Tensor, B: int, rows: int, pitch: int, H: int, col0: int = 0) -> torch.Tensor:
@@ -96,18 +96,35 @@ def forward(enc, query, query_pos, query_masks, mems: List[Tuple[str, torch.Tens
 
     ws: Dict = {}
     for name, feat, mask, pos in mems:
-        S = feat.shape[1]
+        multi = isinstance(feat, (list, tuple))          # multi-scale voxel memory: layer i attends feat[i] (:90-91)
+        S = (feat[0] if multi else feat).shape[1]
         Sp = ops.pad64(S)
         st = _Mem()
-        st.name, st.S, st.Sp, st.S_pitch, st.has_pos = name, S, Sp, Sp, pos is not None
-        st.xv = _e((B * Sp, D), bf16, dev)
-        st.xk = _e((B * Sp, D), bf16, dev) if pos is not None else st.xv
-        ops.ingest_memory(feat.detach().contiguous().float(), None if pos is None else pos.detach().contiguous().float(),
-                          st.xk if pos is not None else None, st.xv, Sp)
+        st.name, st.S, st.Sp, st.S_pitch, st.has_pos, st.multi = name, S, Sp, Sp, pos is not None, multi
+        pos32 = None if pos is None else pos.detach().contiguous().float()
         st.K = _e((B * Sp, L * D), bf16, dev)
         st.Vt = _e((L * D, B * Sp), bf16, dev)
-        ops.linear(st.xk, pk.wk[name], st.K, M=B * Sp, N=L * D, K=D, bias=pk.bk[name])
-        ops.linear(pk.wv[name], st.xv, st.Vt, M=L * D, N=B * Sp, K=D, bias=pk.bv[name], bias_along_m=True)
+
+        def ingest(f):
+            xv_ = _e((B * Sp, D), bf16, dev)
+            xk_ = _e((B * Sp, D), bf16, dev) if pos is not None else xv_
+            ops.ingest_memory(f.detach().contiguous().float(), pos32, xk_ if pos is not None else None, xv_, Sp)
+            return xk_, xv_
+        if multi:
+            if len(feat) < L:
+                raise ValueError(f"memory '{name}': {len(feat)} feature scales for {L} layers")
+            st.xk, st.xv = [], []
+            for l in range(L):
+                xk_, xv_ = ingest(feat[l])
+                st.xk.append(xk_)
+                st.xv.append(xv_)
+                sl = slice(l * D, (l + 1) * D)
+                ops.linear(xk_, pk.wk[name][sl], st.K[:, sl], M=B * Sp, N=D, K=D, bias=pk.bk[name][sl], ldc=L * D)
+                ops.linear(pk.wv[name][sl], xv_, st.Vt[sl], M=D, N=B * Sp, K=D, bias=pk.bv[name][sl], bias_along_m=True)
+        else:
+            st.xk, st.xv = ingest(feat)
+            ops.linear(st.xk, pk.wk[name], st.K, M=B * Sp, N=L * D, K=D, bias=pk.bk[name])
+            ops.linear(pk.wv[name], st.xv, st.Vt, M=L * D, N=B * Sp, K=D, bias=pk.bv[name], bias_along_m=True)
         enc._set_mask(st, mask, B, N, H, ws, dev)
         sv["mems"][name] = st
 
@@ -613,27 +630,58 @@ class _Bwd:
             rows = B * st.Sp
             with self.on(self.side):
                 d_bk, d_bv = self.colsum(mg["dK"]), self.colsum(mg["dV"])
-                dKT, _ = self.tcast(mg["dK"], rows, L * D)
-                xkT, _ = self.tcast(st.xk, rows, D)
-                self.wgrad(dKT, xkT, D, D, out=self.G_ca[0, j, D:2 * D], groups=L, c_group_stride=n_mem * 3 * D * D)
-                dVT, _ = self.tcast(mg["dV"], rows, L * D)
-                xvT = xkT if not st.has_pos else self.tcast(st.xv, rows, D)[0]
-                self.wgrad(dVT, xvT, D, D, out=self.G_ca[0, j, 2 * D:], groups=L, c_group_stride=n_mem * 3 * D * D)
+                if st.multi:                     # one feature table per layer: a wgrad per layer
+                    for l in range(L):
+                        sl = slice(l * D, (l + 1) * D)
+                        dKT, _ = self.tcast(mg["dK"][:, sl], rows, D)
+                        xkT, _ = self.tcast(st.xk[l], rows, D)
+                        self.wgrad(dKT, xkT, D, D, out=self.G_ca[l, j, D:2 * D])
+                        dVT, _ = self.tcast(mg["dV"][:, sl], rows, D)
+                        xvT = xkT if not st.has_pos else self.tcast(st.xv[l], rows, D)[0]
+                        self.wgrad(dVT, xvT, D, D, out=self.G_ca[l, j, 2 * D:])
+                else:
+                    dKT, _ = self.tcast(mg["dK"], rows, L * D)
+                    xkT, _ = self.tcast(st.xk, rows, D)
+                    self.wgrad(dKT, xkT, D, D, out=self.G_ca[0, j, D:2 * D], groups=L, c_group_stride=n_mem * 3 * D * D)
+                    dVT, _ = self.tcast(mg["dV"], rows, L * D)
+                    xvT = xkT if not st.has_pos else self.tcast(st.xv, rows, D)[0]
+                    self.wgrad(dVT, xvT, D, D, out=self.G_ca[0, j, 2 * D:], groups=L, c_group_stride=n_mem * 3 * D * D)
                 G_b[:, j, D:2 * D].copy_(d_bk.view(L, D))
                 G_b[:, j, 2 * D:].copy_(d_bv.view(L, D))
                 for i in range(L):
                     G_b[i, j, :D].copy_(mem_grads["_q"][(i, j)])
-            d_xk = self.dgrad(mg["dK"], pk.T_mem("k", j, L, D), D)
-            d_xv = self.dgrad(mg["dV"], pk.T_mem("v", j, L, D), D)
             for i in range(L):
                 pre = f"unified_encoder.{i}.cross_attn_list.{j}.multihead_attn."
                 for G in self.G_blk:
                     self.acc(pre + "in_proj_weight", G[i, j])
                 self.acc(pre + "in_proj_bias", G_b[i, j])
-            d_feat = _e((rows, D), f32, dev)
-            ops.add3(d_xk, d_xv, None, d_feat)
-            self.keep += [d_xk, d_xv]
-            d_mem[name] = (d_feat.view(B, st.Sp, D)[:, :st.S], d_xk.view(B, st.Sp, D)[:, :st.S] if st.has_pos else None)
+            cut = lambda t: t.view(B, st.Sp, D)[:, :st.S]              # noqa: E731
+            if st.multi:
+                d_feats, d_p = [], None
+                for l in range(L):
+                    sl = slice(l * D, (l + 1) * D)
+                    d_xk = self.dgrad(mg["dK"][:, sl], pk.T_mem("k", j, L, D)[:, sl], D)
+                    d_xv = self.dgrad(mg["dV"][:, sl], pk.T_mem("v", j, L, D)[:, sl], D)
+                    d_f = _e((rows, D), f32, dev)
+                    ops.add3(d_xk, d_xv, None, d_f)
+                    d_feats.append(cut(d_f))
+                    if st.has_pos:
+                        if d_p is None:
+                            d_p = d_xk
+                        else:
+                            d_new = _e((rows, D), f32, dev)
+                            ops.add3(d_p, d_xk, None, d_new)
+                            self.keep.append(d_p)
+                            d_p = d_new
+                    self.keep += [d_xk, d_xv]
+                d_mem[name] = (d_feats, cut(d_p) if st.has_pos else None)
+            else:
+                d_xk = self.dgrad(mg["dK"], pk.T_mem("k", j, L, D), D)
+                d_xv = self.dgrad(mg["dV"], pk.T_mem("v", j, L, D), D)
+                d_feat = _e((rows, D), f32, dev)
+                ops.add3(d_xk, d_xv, None, d_feat)
+                self.keep += [d_xk, d_xv]
+                d_mem[name] = (cut(d_feat), cut(d_xk) if st.has_pos else None)
         mh_out = (None, None)
         if mht is not None:
             mh_out = mht.finish()
@@ -648,15 +696,19 @@ class DecoderFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, enc, meta, query, query_pos, *rest):
-        n = len(meta["names"])
-        feats, poss = rest[0:2 * n:2], rest[1:2 * n:2]
-        mems = [(meta["names"][k], feats[k], meta["masks"][k], poss[k]) for k in range(n)]
+        mems, o = [], 0
+        for k, name in enumerate(meta["names"]):
+            nf = meta["nfeat"][k]                          # 1, or one feature tensor per layer (multi-scale voxels)
+            feat = rest[o] if nf == 1 and not meta["is_list"][k] else list(rest[o:o + nf])
+            mems.append((name, feat, meta["masks"][k], rest[o + nf]))
+            o += nf + 1
+        ctx.n_mem_inputs = o
         out, preds, sv = forward(enc, query, query_pos, meta["query_masks"], mems, meta["pairwise_locs"], meta["mh"],
                                  meta["mh_kw"])
         sv["canon"] = meta["canon"]
         meta["final_mask"] = sv.get("final_mask")
         ctx.enc, ctx.sv, ctx.meta = enc, sv, meta
-        ctx.in_dtypes = (query.dtype, query_pos.dtype, [None if t is None else t.dtype for t in rest[:2 * n]])
+        ctx.in_dtypes = (query.dtype, query_pos.dtype, [None if t is None else t.dtype for t in rest[:o]])
         return (out, *preds)
 
     @staticmethod
@@ -666,16 +718,18 @@ class DecoderFunction(torch.autograd.Function):
             d_out = torch.zeros(sv["B"], sv["N"], sv["D"], dtype=f32, device=sv["qpos"].device)
         d_q, d_pos, d_mem, grads, (mh_grads, mh_dfeats) = _Bwd(enc, sv).run(d_out, d_preds)
         ctx.sv = None
-        n = len(meta["names"])
         out = [None, None, d_q.to(ctx.in_dtypes[0]), d_pos.to(ctx.in_dtypes[1])]
+        o = 0
         for k, name in enumerate(meta["names"]):
             d_feat, d_p = d_mem[name]
-            out.append(d_feat.to(ctx.in_dtypes[2][2 * k]) if ctx.needs_input_grad[4 + 2 * k] else None)
-            out.append(d_p.to(ctx.in_dtypes[2][2 * k + 1])
-                       if d_p is not None and ctx.needs_input_grad[5 + 2 * k] else None)
+            for g in (d_feat if isinstance(d_feat, list) else [d_feat]):
+                out.append(g.to(ctx.in_dtypes[2][o]) if ctx.needs_input_grad[4 + o] else None)
+                o += 1
+            out.append(d_p.to(ctx.in_dtypes[2][o]) if d_p is not None and ctx.needs_input_grad[4 + o] else None)
+            o += 1
         for j in range(meta["n_mh_feats"]):
             g = None if mh_dfeats is None else mh_dfeats[j]
-            out.append(g if (g is not None and ctx.needs_input_grad[4 + 2 * n + j]) else None)
+            out.append(g if (g is not None and ctx.needs_input_grad[4 + o + j]) else None)
         for pname, p in meta["param_names"]:
             g = grads.get(pname)
             out.append(None if g is None else g.reshape(p.shape).to(p.dtype))
@@ -701,24 +755,28 @@ def run(enc, input_dict: dict, pairwise_locs, mask_head=None):
     enc.last_memory_keep = []          # memory-dropout keep masks of this forward, in (layer, group) order (for tests)
     query, query_masks, query_pos = input_dict["query"]
     names = [m for g in enc._program() for m in g]
-    masks, flat = [], []
+    masks, flat, nfeat, is_list = [], [], [], []
     for m in names:
         feat, mask, pos = input_dict[m]
-        if isinstance(feat, list):
-            raise NotImplementedError("pq3d_b200 training path: multi-scale (list) memory features are inference-only")
         masks.append(mask)
-        flat += [feat, pos]
+        fl = list(feat[:enc.num_layers]) if isinstance(feat, (list, tuple)) else [feat]
+        nfeat.append(len(fl))
+        is_list.append(isinstance(feat, (list, tuple)))
+        flat += fl + [pos]
     mh_feats = [] if mh is None else [f[0] for f in list(mh_kw["seg_fts_for_match"])[:len(mh.mask_pred_list)]]
     params = list(enc.named_parameters())
     mh_params = [] if mh is None else list(mh.named_parameters())
     first = {id(p): n for n, p in reversed(params)}
     canon = {n: first[id(p)] for n, p in enc.named_parameters(remove_duplicate=False)}
     meta = dict(canon=canon, names=names, masks=masks, query_masks=query_masks, pairwise_locs=pairwise_locs,
-                param_names=params, mh=mh, mh_kw=mh_kw, n_mh_feats=len(mh_feats), mh_param_names=mh_params)
+                param_names=params, mh=mh, mh_kw=mh_kw, n_mh_feats=len(mh_feats), mh_param_names=mh_params, nfeat=nfeat,
+                is_list=is_list)
     outs = DecoderFunction.apply(enc, meta, query, query_pos, *flat, *mh_feats, *[p for _, p in params],
                                  *[p for _, p in mh_params])
     if enc.use_self_mask and meta.get("final_mask") is not None:
         for m in input_dict.keys():                # the reference leaves the last attention mask in input_dict (:85-88)
             if m not in ("query", "prompt"):
                 input_dict[m][1] = meta["final_mask"]
+    if "voxel" in input_dict and isinstance(input_dict["voxel"][0], (list, tuple)):
+        input_dict["voxel"][0] = input_dict["voxel"][0][enc.num_layers - 1]      # what the reference's loop leaves (:90-91)
     return outs[0], list(outs[1::2]), list(outs[2::2])

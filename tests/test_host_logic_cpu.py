@@ -248,3 +248,41 @@ def test_stage1_training_host_logic_mask_head_selfmask_blocks():
     worst.sort(reverse=True)
     print(worst[:6])
     assert worst[0][0] <= 0.15, worst[:4]
+
+
+def test_training_host_logic_multiscale_voxel():
+    """Multi-scale voxel memory (a list with one feature table per layer, query_encoder.py:90-91) in training: every
+    scale's feature gradient and the per-layer K / V weight gradients against oracle autograd."""
+    w = synth.Workload("ms", 2, 20, 100, ["voxel", "pc"], "parallel", num_layers=2, voxel_multiscale=True,
+                       spatial_selfattn=False)
+    sd = synth.decoder_state_dict(w, seed=19, sharp=1.0)
+    inp, pw, _ = synth.make_decoder_inputs(w)
+    assert isinstance(inp["voxel"][0], list)
+    g = torch.Generator().manual_seed(2)
+    up = torch.randn(inp["query"][0].shape, generator=g)
+    enc = _build(w, sd).train()
+    enc.train_dropout = 0.0
+    x = synth.clone_input_dict(inp)
+    vox = [t.clone().requires_grad_(True) for t in x["voxel"][0]]
+    x["voxel"][0] = list(vox)
+    with _cpu_ops.cpu_backend():
+        out = enc(x, pw)[0]
+        (out * up).sum().backward()
+    assert torch.is_tensor(x["voxel"][0])
+    sdd = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    xo = synth.clone_input_dict(inp)
+    vo = [t.clone().requires_grad_(True) for t in xo["voxel"][0]]
+    xo["voxel"][0] = list(vo)
+    ref = O.query_mask_encoder(sdd, O.DecoderCfg(**w.decoder_kwargs()), xo, pw)[0]
+    (ref * up).sum().backward()
+    assert rel(out, ref) <= 3e-2
+    l2 = lambda a, b: ((a.float() - b.float()).norm() / b.float().norm().clamp_min(1e-12)).item()     # noqa: E731
+    assert sum(b.grad is not None for b in vo) == w.num_layers          # layer i attends scale i; the rest are unused
+    for a, b in zip(vox, vo):
+        if b.grad is None:
+            assert a.grad is None
+        else:
+            assert a.grad is not None and l2(a.grad, b.grad) <= 8e-2
+    for k, p in enc.named_parameters():
+        assert p.grad is not None, k
+        assert l2(p.grad, sdd[k].grad) <= 0.12, (k, l2(p.grad, sdd[k].grad))
