@@ -325,14 +325,13 @@ class MaskHeadTrain:
         parts = []
         xT = None
         if d_cls is not None:
-            dc = d_cls.detach().reshape(R, C).float().clone()
-            dc[:, self.cols] = 0.0                                  # cls_logits[..., filter] = -inf overwrote those columns
-            self._acc("cls_head.4.bias", self._colsum(dc))
-            dc16 = torch.zeros(R, Cp, dtype=bf16, device=dev)
-            dcT = torch.empty(C, _pad64(R), dtype=bf16, device=dev)
-            ops.transpose_cast(dc, dcT, dc16[:, :C])
+            dc = torch.zeros(R, Cp, dtype=torch.float32, device=dev)       # class dimension padded to the GEMMs' K granule
+            dc[:, :C] = d_cls.detach().reshape(R, C)
+            dc[:, :C][:, self.cols] = 0.0                           # cls_logits[..., filter] = -inf overwrote those columns
+            self._acc("cls_head.4.bias", self._colsum(dc)[:C])
+            dcT, dc16 = self._tcast(dc, R, Cp, want_c=True)
             hnT, _ = self._tcast(sv["hn16"], R, Hd)
-            self._acc("cls_head.4.weight", self._wgrad(dcT, hnT, C, Hd))
+            self._acc("cls_head.4.weight", self._wgrad(dcT[:C], hnT, C, Hd))
             d_hd16 = torch.empty(R, Hd, dtype=bf16, device=dev)
             ops.linear(dc16, w["w4t"], d_hd16, M=R, N=Hd, K=Cp)
             if self.p > 0.0:

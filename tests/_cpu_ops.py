@@ -27,6 +27,9 @@ def linear(A, W, out, *, M, N, K, bias=None, bias_along_m=False, bias_group_stri
            w_group_rows=0, ldc=None, c_group_stride=0, row_zero=None, row_zero_group_stride=0, alpha=1.0, alpha_ncols=0,
            relu=False, block_n=0):
     assert A.dtype == bf16 and W.dtype == bf16 and K % 64 == 0
+    # the ABI's documented constraints (TMA: 16-byte aligned bases, 16-byte granular pitches >= K)
+    assert A.stride(0) % 8 == 0 and W.stride(0) % 8 == 0 and A.stride(0) >= K and W.stride(0) >= K
+    assert A.storage_offset() % 8 == 0 and W.storage_offset() % 8 == 0 and A.stride(1) == 1 and W.stride(1) == 1
     ldc = out.stride(-2) if ldc is None else ldc
     lda, ldw = A.stride(0), W.stride(0)
     # TMA zero-fills rows past the operand's extent
@@ -118,6 +121,10 @@ def attention_bwd(Q, q_col0, dO, do_col0, K, k_col0, V, v_col0, S, S_pitch, stat
                   dQ32, dq_col0, B, H, Nq, *, mask_bits=None, mask_strides=(0, 0, 0), bias=None, dS_out=None, drop_p=0.0,
                   seed=None, site=0):
     assert Nq <= 128
+    for t in (Q, dO, K, V, dK, dV):
+        assert t.stride(0) % 8 == 0 and t.storage_offset() % 8 == 0 and t.stride(1) == 1
+    assert all(c % 8 == 0 for c in (q_col0, do_col0, k_col0, v_col0, dk_col0, dv_col0)) and dq_col0 % 4 == 0
+    assert dQ32.stride(0) % 4 == 0 and S_pitch >= S
     q, k, s2 = _scores(Q, Q.stride(0), q_col0, K, K.stride(0), k_col0, S, S_pitch, B, H, Nq)
     v = _as(V, (B, S, H, 64), (S_pitch * V.stride(0), V.stride(0), 64, 1), v_col0).float()
     do = _as(dO, (B, Nq, H, 64), (Nq * dO.stride(0), dO.stride(0), 64, 1), do_col0).float()
@@ -263,6 +270,7 @@ def pack_mask(mask, bits=None, unmask_full_rows=False, mask_fixed=None, active_t
 
 
 def cast_bf16(x, out, add=None):
+    assert x.numel() % 4 == 0 and x.is_contiguous() and out.is_contiguous()
     out.copy_((x if add is None else x + add).to(bf16))
     ops._count()
 
@@ -285,6 +293,8 @@ def transpose_cast(x, out_t, out_c=None, gate=None, scale=1.0):
 
 
 def colsum(x, out, accumulate=False, gate=None, scale=1.0):
+    assert x.shape[1] % 2 == 0 and x.stride(0) % 2 == 0 and x.stride(1) == 1, "pq3d_colsum: C, ld must be even"
+    assert (x.storage_offset() * x.element_size()) % 8 == 0
     v = x.float()
     if gate is not None:
         v = torch.where(gate.float() > 0, v, torch.zeros_like(v))
@@ -294,6 +304,7 @@ def colsum(x, out, accumulate=False, gate=None, scale=1.0):
 
 
 def add3(a, b, c, out):
+    assert out.numel() % 4 == 0 and a.is_contiguous() and b.is_contiguous() and out.is_contiguous()
     out.copy_(a + b + (0 if c is None else c))
     ops._count()
 

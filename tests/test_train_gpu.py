@@ -309,3 +309,150 @@ def test_dropout_statistics_and_fresh_masks_per_step():
         c = enc(synth.clone_input_dict(inp), pw)[0]
         d = enc(synth.clone_input_dict(inp), pw)[0]
     assert torch.equal(c, d)
+
+
+# ------------------------------------------------------------------------------------------------
+# stage-1 training: in-loop mask head (+ its backward), use_self_mask, two blocks, multi-scale voxel memory
+# ------------------------------------------------------------------------------------------------
+def l2rel(a, b, floor=1e-12):
+    return ((a.float() - b.float()).norm() / b.float().norm().clamp_min(floor)).item()
+
+
+def test_mask_head_training_matches_oracle():
+    """MaskHeadSegLevel.forward under autograd (the call Query3DUnified makes after the decoder): predictions, query /
+    feature gradients and every parameter gradient vs fp32 oracle autograd, the autocast oracle as yardstick."""
+    from pq3d_b200.mask_head import MaskHeadSegLevel
+    B, N, S, n = 2, 100, 300, 3
+    g = torch.Generator().manual_seed(8)
+    mh = MaskHeadSegLevel(None, 768, 201, memories_for_match=["voxel", "mv", "pc"], filter_out_classes=[0, 2], dropout=0.0)
+    sd = synth.draw_state_dict(synth.mask_head_param_shapes(n), 8)
+    mh.load_state_dict(sd, strict=True)
+    mh = mh.to(DEV).train()
+    sd = C.to_dev(sd, DEV)
+    feats = []
+    for j in range(n):
+        mask = torch.rand(B, S, generator=g) < 0.2
+        mask[1, S - 40:] = True
+        feats.append([torch.randn(B, S, 768, generator=g).to(DEV), mask.to(DEV), None])
+    seg_masks = torch.zeros(B, S, dtype=torch.bool)
+    seg_masks[1, S - 40:] = True
+    seg_masks = seg_masks.to(DEV)
+    q = (torch.randn(B, N, 768, generator=g) * 0.5).to(DEV)
+    up_c, up_m = torch.randn(B, N, 201, generator=g).to(DEV), torch.randn(B, S, N, generator=g).to(DEV)
+
+    def loss(cls, ml):
+        return (cls.float().masked_fill(~torch.isfinite(cls.float()), 0.0) * up_c).sum() + (ml.float().clamp_min(-100.0) * up_m).sum()
+    ql = q.clone().requires_grad_(True)
+    fl = [[f[0].clone().requires_grad_(True), f[1], None] for f in feats]
+    cls, ml, attn = mh(ql, fl, seg_masks)
+    loss(cls, ml).backward()
+    res = {}
+    for autocast in (False, True):
+        sdd = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+        qo = q.clone().requires_grad_(True)
+        fo = [[f[0].clone().requires_grad_(True), f[1], None] for f in feats]
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+            co, mo, ao = O.mask_head_seg_level(qo, sdd, "", fo, seg_masks, filter_out_classes=[0, 2])
+        loss(co, mo).backward()
+        gr = {k: v.grad for k, v in sdd.items()}
+        gr["query"] = qo.grad
+        for j, f in enumerate(fo):
+            gr[f"feat{j}"] = f[0].grad
+        res[autocast] = (co.detach().float(), mo.detach().float(), ao, gr)
+    c32, m32, a32, g32 = res[False]
+    c16, m16, _, g16 = res[True]
+    fin = torch.isfinite(c32)
+    assert torch.equal(torch.isfinite(cls), fin)
+    assert rel(cls.masked_fill(~fin, 0), c32.masked_fill(~fin, 0)) <= 1.25 * rel(c16.masked_fill(~fin, 0), c32.masked_fill(~fin, 0)) + 1e-3
+    assert rel(ml, m32) <= 1.25 * rel(m16, m32) + 1e-3
+    ours = {k: p.grad for k, p in mh.named_parameters()}
+    ours["query"] = ql.grad
+    for j, f in enumerate(fl):
+        ours[f"feat{j}"] = f[0].grad
+    for k, r in g32.items():
+        assert ours.get(k) is not None, k
+        e, e16 = l2rel(ours[k], r), l2rel(g16[k], r)
+        assert e <= 1.5 * e16 + 2e-2, f"{k}: {e:.3e} (autocast oracle {e16:.3e})"
+
+
+def test_stage1_training_mask_head_selfmask_blocks_multiscale():
+    """Stage-1 (instance segmentation) training shape: parallel cross-attentions over [mv, pc, multi-scale voxel], the
+    in-loop mask head whose detached attention mask replaces the memory masks, two blocks re-applying the same layers,
+    losses on every per-layer prediction.  Decoder and mask-head parameter gradients vs fp32 oracle autograd (2-norm,
+    the autocast oracle as yardstick: a handful of mask bits flip under bf16 in either implementation)."""
+    from functools import partial
+    from pq3d_b200.mask_head import MaskHeadSegLevel
+    from pq3d_b200.query_encoder import QueryMaskEncoder
+    B, N, S, L, K = 2, 100, 300, 2, 2
+    w = synth.Workload("s1", B, N, S, ["mv", "pc", "voxel"], "parallel", num_layers=L, num_blocks=K, use_self_mask=True,
+                       spatial_selfattn=True, voxel_multiscale=True, ragged=(200, 300))
+    sd = C.to_dev(synth.decoder_state_dict(w, seed=13, sharp=1.0), DEV)
+    inp, pw, dd = synth.make_decoder_inputs(w, device=DEV)
+    g = torch.Generator().manual_seed(21)
+    q, qm, qp = inp["query"]
+    inp["query"] = ((torch.randn(q.shape, generator=g) * 0.5).to(DEV), qm, qp)
+    msd = C.to_dev(synth.draw_state_dict(synth.mask_head_param_shapes(3), 17), DEV)
+    mh = MaskHeadSegLevel(None, 768, 201, memories_for_match=list(w.memories), filter_out_classes=[0, 2], dropout=0.0)
+    mh.load_state_dict(msd, strict=True)
+    mh = mh.to(DEV).train()
+    seg_pad = (~dd["seg_pad_masks"]).to(DEV)
+    enc = QueryMaskEncoder(None, **w.decoder_kwargs())
+    enc.load_state_dict(sd, strict=True)
+    enc = enc.to(DEV).train()
+    enc.train_dropout = 0.0
+    n_pred = K * L
+    ups = [(torch.randn(B, N, 201, generator=g).to(DEV), torch.randn(B, S, N, generator=g).to(DEV)) for _ in range(n_pred)]
+    up_q = torch.randn(B, N, 768, generator=g).to(DEV)
+
+    def loss_of(out, pcs, pms):
+        tot = (out.float() * up_q).sum()
+        for (uc, um), c, m in zip(ups, pcs, pms):
+            c, m = c.float(), m.float()
+            tot = tot + (c.masked_fill(~torch.isfinite(c), 0.0) * uc).sum() * 0.1 + (m.clamp_min(-100.0) * um).sum() * 0.1
+        return tot
+
+    def match_feats(x):
+        fs = []
+        for m in w.memories:
+            f = list(x[m])
+            if isinstance(f[0], list):
+                f[0] = f[0][-1]                      # Query3DUnified matches against the last voxel scale (:167-174)
+            fs.append(f)
+        return fs
+    x = synth.clone_input_dict(inp)
+    head = partial(mh, seg_fts_for_match=match_feats(x), seg_masks=seg_pad, offline_attn_masks=None, skip_prediction=False)
+    out, pcs, pms = enc(x, pw, head)
+    assert len(pcs) == n_pred and len(pms) == n_pred
+    loss_of(out, pcs, pms).backward()
+    torch.cuda.synchronize()
+    res = {}
+    for autocast in (False, True):
+        sdd = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+        msdd = {k: v.clone().requires_grad_(True) for k, v in msd.items()}
+        xo = synth.clone_input_dict(inp)
+        fo = match_feats(xo)
+        head_o = lambda qq: O.mask_head_seg_level(qq, msdd, "", fo, seg_pad, filter_out_classes=[0, 2])   # noqa: E731
+        torch.backends.cuda.matmul.allow_tf32 = False
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+            ro, pco, pmo = O.query_mask_encoder(sdd, O.DecoderCfg(**w.decoder_kwargs()), xo, pw, head_o)
+        loss_of(ro, pco, pmo).backward()
+        gr = {k: v.grad for k, v in sdd.items()}
+        gr.update({"mask_head." + k: v.grad for k, v in msdd.items()})
+        res[autocast] = (ro.detach().float(), gr)
+    r32, g32 = res[False]
+    r16, g16 = res[True]
+    print(f"stage-1 training forward: err(ours) {rel(out, r32):.3e}  err(autocast oracle) {rel(r16, r32):.3e}")
+    assert rel(out, r32) <= 1.25 * rel(r16, r32) + 5e-3
+    ours = {k: p.grad for k, p in enc.named_parameters()}
+    ours.update({"mask_head." + k: p.grad for k, p in mh.named_parameters()})
+    worst = []
+    for k, r in g32.items():
+        if r is None or k.endswith("w_ks.bias"):
+            continue
+        assert ours.get(k) is not None, f"{k}: no gradient"
+        worst.append((l2rel(ours[k], r), l2rel(g16[k], r), k))
+    worst.sort(reverse=True)
+    for e, e16, k in worst[:6]:
+        print(f"  {k}: ours {e:.3e}  autocast oracle {e16:.3e}")
+    for e, e16, k in worst:
+        assert e <= 1.5 * e16 + 3e-2, f"{k}: {e:.3e} (autocast oracle {e16:.3e})"
