@@ -131,7 +131,7 @@ def run_reference_arm(args, w, rank, world):
             "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -344,12 +344,31 @@ def run_train(args, w, enc, inp_host, pw_host, rank, world, local_rank, dev, bar
                     "timing": "wall clock, max over ranks; each step copies its batch from pinned host memory, runs "
                               "fwd+bwd+all-reduce+AdamW and reads the loss back"},
             "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------
+_REAL_STDOUT = None
+
+
+def emit(line: dict):
+    """The ONE JSON line of the contract, on the process's original stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    global _REAL_STDOUT
     args = parse()
+    # libraries write to stdout too (NCCL prints "NCCL version ..." at communicator set-up): route fd 1 to stderr for
+    # the whole run and keep the original stdout for the single JSON line
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
@@ -619,7 +638,7 @@ def main():
                               "result back; value = double-buffered (H2D of step i+1 overlaps forward of step i), "
                               "serial_value = strictly H2D->forward->D2H one step at a time"},
             "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
