@@ -221,24 +221,14 @@ class MaskHeadTrain:
         dev = feats[0][0].device
         self.dev = dev
         self.S = S = feats[0][0].shape[1]
-        self.p = float(mh.cls_head[3].p) if mh.training else 0.0
         self.seed = seed
-        if self.p > 0.0 and seed is None:
-            raise ValueError("mask head dropout needs the step's device seed")
-        l0, ln, l4 = mh.cls_head[0], mh.cls_head[2], mh.cls_head[4]
+        from .train_blocks import MlpHeadTrain
         f = lambda t: t.detach().float().contiguous()                 # noqa: E731
         w16 = lambda t: t.detach().to(bf16).contiguous()              # noqa: E731
-        self.C = C = l4.out_features
-        self.Cp = Cp = _pad64(C)
-        b4 = f(l4.bias).clone()
         cols = slice(None) if mh.filter_out_classes is None else list(mh.filter_out_classes)
-        b4[..., cols] = float("-inf")
-        self.cols = cols
-        w4t = torch.zeros(l4.in_features, Cp, dtype=bf16, device=dev)
-        w4t[:, :C] = l4.weight.detach().t().to(bf16)
-        self.w = dict(w0=w16(l0.weight), w0t=w16(l0.weight.t()), b0=f(l0.bias), g=f(ln.weight)[None], be=f(ln.bias)[None],
-                      eps=ln.eps, w4=w16(l4.weight), w4t=w4t, b4=b4,
-                      wq=w16(torch.cat([l.q_proj.weight for l in mh.mask_pred_list], 0)),
+        self.cls = MlpHeadTrain(mh.cls_head, cols, seed)
+        self.C = self.cls.C
+        self.w = dict(wq=w16(torch.cat([l.q_proj.weight for l in mh.mask_pred_list], 0)),
                       wqt=w16(torch.cat([l.q_proj.weight for l in mh.mask_pred_list], 0).t()),
                       bq=f(torch.cat([l.q_proj.bias for l in mh.mask_pred_list], 0)),
                       wk=[w16(l.k_proj.weight) for l in mh.mask_pred_list],
@@ -275,21 +265,12 @@ class MaskHeadTrain:
         """q2d fp32 [B*N, D] -> (cls (B,N,C), mask_logits (B,S,N), attn_mask (B,N,S) bool, saved)."""
         B, N, S, n, D, dev, w = self.B, self.N, self.S, self.n, self.D, self.dev, self.w
         R = B * N
-        Hd = w["w0"].shape[0]
         x16 = torch.empty(R, D, dtype=bf16, device=dev)
         ops.cast_bf16(q2d, x16)
-        h = torch.empty(R, Hd, dtype=torch.float32, device=dev)
-        ops.linear(x16, w["w0"], h, M=R, N=Hd, K=D, bias=w["b0"], relu=True)
-        hg16 = torch.empty(R, Hd, dtype=bf16, device=dev)                 # ReLU gate of the backward
-        ops.cast_bf16(h, hg16)
-        hn16 = torch.empty(R, Hd, dtype=bf16, device=dev)
-        ops.add_layernorm(h, None, w["g"], w["be"], w["eps"], R, Hd, out_bf16=hn16)
         call = self.calls
         self.calls += 1
-        if self.p > 0.0:
-            ops.dropout_bf16(hn16, self.p, self.seed, self._site(call))
-        cls = torch.empty(B, N, self.C, dtype=torch.float32, device=dev)
-        ops.linear(hn16, w["w4"], cls, M=R, N=self.C, K=Hd, bias=w["b4"], ldc=self.C)
+        cls2d, csv = self.cls.fwd(x16, R, self._site(call))
+        cls = cls2d.view(B, N, self.C)
         qcat = torch.empty(R, n * D, dtype=bf16, device=dev)
         ops.linear(x16, w["wq"], qcat, M=R, N=n * D, K=D, bias=w["bq"])
         raw = torch.empty(B, S, N, dtype=torch.float32, device=dev)
@@ -298,7 +279,7 @@ class MaskHeadTrain:
         logits = torch.empty(B, S, N, dtype=torch.float32, device=dev)
         attn = torch.empty(B, N, S, dtype=torch.bool, device=dev)
         ops.mask_head_finalize(raw, self.ptrs, n, self.masks[n], logits, attn, B, S, N, masks=self.masks)
-        return cls, logits, attn, dict(x16=x16, h=h, hg16=hg16, hn16=hn16, qcat=qcat, call=call)
+        return cls, logits, attn, dict(x16=x16, cls=csv, qcat=qcat, call=call)
 
     # ---- its backward ---------------------------------------------------------------------------------------
     def _tcast(self, x, rows, cols, want_c=False, gate=None):
@@ -320,36 +301,12 @@ class MaskHeadTrain:
     def call_bwd(self, sv, d_cls, d_logits):
         """-> d_q fp32 [B*N, D] (or None when neither prediction carries a gradient)."""
         B, N, S, n, D, dev, w = self.B, self.N, self.S, self.n, self.D, self.dev, self.w
-        R, C, Cp = B * N, self.C, self.Cp
-        Hd = w["w0"].shape[0]
+        R = B * N
         parts = []
         xT = None
         if d_cls is not None:
-            dc = torch.zeros(R, Cp, dtype=torch.float32, device=dev)       # class dimension padded to the GEMMs' K granule
-            dc[:, :C] = d_cls.detach().reshape(R, C)
-            dc[:, :C][:, self.cols] = 0.0                           # cls_logits[..., filter] = -inf overwrote those columns
-            self._acc("cls_head.4.bias", self._colsum(dc)[:C])
-            dcT, dc16 = self._tcast(dc, R, Cp, want_c=True)
-            hnT, _ = self._tcast(sv["hn16"], R, Hd)
-            self._acc("cls_head.4.weight", self._wgrad(dcT[:C], hnT, C, Hd))
-            d_hd16 = torch.empty(R, Hd, dtype=bf16, device=dev)
-            ops.linear(dc16, w["w4t"], d_hd16, M=R, N=Hd, K=Cp)
-            if self.p > 0.0:
-                ops.dropout_bf16(d_hd16, self.p, self.seed, self._site(sv["call"]))
-            d_hn = d_hd16.float()
-            d_h = torch.empty(R, Hd, dtype=torch.float32, device=dev)
-            dg = torch.zeros(1, Hd, dtype=torch.float32, device=dev)
-            db = torch.zeros(1, Hd, dtype=torch.float32, device=dev)
-            ops.layernorm_bwd(sv["h"], None, w["g"], d_hn, w["eps"], R, Hd, d_x=d_h, d_gamma=dg, d_beta=db)
-            self._acc("cls_head.2.weight", dg[0])
-            self._acc("cls_head.2.bias", db[0])
-            self._acc("cls_head.0.bias", self._colsum(d_h, gate=sv["hg16"]))
-            d_preT, d_pre16 = self._tcast(d_h, R, Hd, want_c=True, gate=sv["hg16"])
             xT, _ = self._tcast(sv["x16"], R, D)
-            self._acc("cls_head.0.weight", self._wgrad(d_preT, xT, Hd, D))
-            d_xa = torch.empty(R, D, dtype=torch.float32, device=dev)
-            ops.linear(d_pre16, w["w0t"], d_xa, M=R, N=D, K=Hd)
-            parts.append(d_xa)
+            parts.append(self.cls.bwd(sv["cls"], d_cls.detach().reshape(R, self.C).float(), xT))
         if d_logits is not None:
             Np, Sp = _pad64(N), _pad64(S)
             d_raw16 = torch.empty(B * S, Np, dtype=bf16, device=dev)
@@ -410,6 +367,8 @@ class MaskHeadTrain:
                     d_f = torch.empty(rows, D, dtype=torch.float32, device=dev)
                     ops.linear(dk16, w["wkt"][j], d_f, M=rows, N=D, K=D)
                     d_feats[j] = d_f.view(B, S, D)
+        for k, g in self.cls.grads.items():
+            self.grads["cls_head." + k] = g
         return self.grads, d_feats
 
 

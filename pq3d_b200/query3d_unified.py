@@ -92,7 +92,14 @@ class LinearLN(nn.Sequential):
         ops.add_layernorm(y, None, w["g"], w["be"], w["eps"], R, D, out_f32=out32)
         return out32
 
+    def _needs_grad(self, x=None) -> bool:
+        return torch.is_grad_enabled() and (any(p.requires_grad for p in self.parameters())
+                                            or (x is not None and x.requires_grad))
+
     def forward(self, x: torch.Tensor) -> torch.Tensor:
+        if self._needs_grad(x):            # training: forward + backward composed from the kernels (train_blocks.py)
+            from .train_blocks import linear_ln_train
+            return linear_ln_train(x, self[0], self[1])
         lead, din = x.shape[:-1], x.shape[-1]
         R = x.numel() // din
         w = self._weights(x.device)
@@ -126,6 +133,9 @@ class CoordinateEncoder(nn.Module):
         D = self.pos_enc.gauss_B.shape[1] * 2
         x16 = torch.empty(B * L, D, dtype=bf16, device=coords.device)
         ops.fourier_pos(coords.float(), input_range[0].float(), input_range[1].float(), self.pos_enc.gauss_B.float(), x16)
+        if self.feat_proj._needs_grad():   # the Fourier features carry no gradient (computed under no_grad, :22-24)
+            from .train_blocks import linear_ln_train
+            return linear_ln_train(None, self.feat_proj[0], self.feat_proj[1], x16=x16).view(B, L, D)
         out = torch.empty(B * L, D, dtype=torch.float32, device=coords.device)
         return self.feat_proj.run16(x16, B * L, out).view(B, L, D)
 
@@ -149,6 +159,8 @@ class ObjectEncoder(nn.Module):
             self.input_feat_proj = LinearLN(input_feat_size, hidden_size)
         elif input_feat_size != hidden_size:
             raise AssertionError("input_feat_size should be equal to hidden_size!")
+        if dropout > 0:
+            self.dropout = nn.Dropout(dropout)       # object_encoder.py:39-40,75-76
         with torch.no_grad():                                     # _init_weights_bert (modules/weights.py)
             for m in self.modules():
                 if isinstance(m, nn.Linear):
@@ -156,9 +168,12 @@ class ObjectEncoder(nn.Module):
                     m.bias.zero_()
 
     def forward(self, obj_feats, data_dict=None, **kwargs):
-        if self.training:
-            raise NotImplementedError("pq3d_b200.ObjectEncoder: inference path only — call .eval()")
-        return self.input_feat_proj(obj_feats) if self.use_projection else obj_feats
+        obj_embeds = self.input_feat_proj(obj_feats) if self.use_projection else obj_feats
+        if self.training and hasattr(self, "dropout"):
+            # the only torch op on this module's path: an elementwise Bernoulli mask on the producer side of the
+            # decoder (§8f-1), drawn from torch's RNG exactly like the reference's nn.Dropout (object_encoder.py:75-76)
+            obj_embeds = self.dropout(obj_embeds)
+        return obj_embeds
 
 
 class GroundHead(nn.Module):
@@ -171,6 +186,13 @@ class GroundHead(nn.Module):
 
     def forward(self, obj_embeds, obj_masks=None, **kwargs):
         B, N, D = obj_embeds.shape
+        if self.training or (torch.is_grad_enabled() and (obj_embeds.requires_grad
+                                                          or any(p.requires_grad for p in self.parameters()))):
+            from .train_blocks import mlp_head_train
+            logits = mlp_head_train(self.og3d_head, obj_embeds).squeeze(2)
+            if obj_masks is not None:
+                logits = logits.masked_fill(obj_masks.logical_not(), -float("inf"))
+            return logits
         x16 = torch.empty(B * N, D, dtype=bf16, device=obj_embeds.device)
         ops.cast_bf16(obj_embeds.reshape(B * N, D).contiguous().float(), x16)
         logits = self._run(x16, B * N).view(B, N)

@@ -339,6 +339,24 @@ def mask_head_finalize_bwd(d_logits, masks, n_mem, d_raw16, B, S, N):
     ops._count()
 
 
+def fourier_pos(xyz, coord_min, coord_max, gauss_B, out):
+    B, L = xyz.shape[:2]
+    x = (xyz[..., :3].float() - coord_min[:, None, :]) / (coord_max[:, None, :] - coord_min[:, None, :]) * (2 * math.pi)
+    proj = (x.reshape(-1, 3) @ gauss_B).view(B * L, -1)
+    out.copy_(torch.cat([proj.sin(), proj.cos()], dim=1).to(bf16))
+    ops._count()
+
+
+def pairwise_locs(centers, out=None, eps=1e-10):
+    from pq3d_b200 import synth
+    r = synth.pairwise_locs_cpu(centers[..., :3].float())
+    if out is not None:
+        out.copy_(r)
+        r = out
+    ops._count()
+    return r
+
+
 def _refresh(self):
     """_Packed.refresh without the device-side segment table: the same copies, on the host."""
     for src, dst_c, dst_t, r0, is_f32 in self._segs:
@@ -355,7 +373,8 @@ def _refresh(self):
 
 PATCHED = ["linear", "bgemm", "attention", "attn_delta", "attention_bwd", "spatial_bias", "spatial_bias_bwd", "ingest_memory",
            "add_layernorm", "add_layernorm_train", "layernorm_bwd", "pack_mask", "cast_bf16", "transpose_cast", "colsum",
-           "add3", "dropout_bf16", "gate_mix", "mask_head_finalize", "mask_head_finalize_bwd"]
+           "add3", "dropout_bf16", "gate_mix", "mask_head_finalize", "mask_head_finalize_bwd",
+           "fourier_pos", "pairwise_locs"]
 
 
 @contextlib.contextmanager

@@ -48,3 +48,76 @@ class KernelRngTrain:
 
     def memory_keep(self, layer, memories, B):
         return self.keeps.pop(0)
+
+
+def run_model_training_case(stage, device, ctx):
+    """Query3DUnified in .train() (dropouts off): gradients of every model parameter vs autograd through the oracle's
+    query3d_unified_forward, fp32, with the oracle under bf16 autocast as the yardstick.  `ctx`: a context manager
+    active during the product's forward + backward (the CPU kernel emulation, or a null context on the GPU)."""
+    from oracle import restatement as O
+    from pq3d_b200 import synth
+    import _cases as C
+    from pq3d_b200.query3d_unified import Query3DUnified
+    if stage == "stage1_mask":
+        case = dict(base="c2", over=dict(B=2, N=16, S=72, num_layers=2, use_self_mask=True), dim_loc=3, heads=["mask"],
+                    skip=False, wseed=41, sharp=1.0)
+    else:
+        case = dict(base="c3", over=dict(B=2, N=16, S=72, T=6, num_layers=2), dim_loc=6, heads=["ground"], skip=False,
+                    wseed=42, sharp=1.0)
+    w, cfg = C.model_cfg(case)
+    for m in w.memories:
+        if m != "prompt":
+            cfg["model"][f"{m}_encoder"]["args"]["dropout"] = 0.0
+    if "mask" in case["heads"]:
+        cfg["model"]["mask_head"]["args"]["dropout"] = 0.0
+    if "ground" in case["heads"]:
+        cfg["model"]["ground_head"]["args"]["dropout"] = 0.0
+    sd = C.to_dev(synth.draw_state_dict(synth.model_param_shapes(cfg), case["wseed"], case["sharp"]), device)
+    model = Query3DUnified(cfg)
+    model.load_state_dict(sd, strict=True)
+    model = model.to(device).train()
+    model.unified_encoder.train_dropout = 0.0
+    if device == "cpu":
+        model.unified_encoder.use_cuda_graph = False
+        model.unified_encoder.train_streams = False
+    d = C.to_dev(synth.make_model_data_dict(w, cfg), device)
+    g = torch.Generator().manual_seed(9)
+
+    def loss_of(out):
+        tot = 0.0
+        if "mask" in case["heads"]:
+            for c, m in zip(out["predictions_class"], out["predictions_mask"]):
+                uc = torch.randn(c.shape, generator=torch.Generator().manual_seed(c.shape[0] * 7 + 1)).to(device)
+                um = torch.randn(m.shape, generator=torch.Generator().manual_seed(m.shape[1] * 3 + 2)).to(device)
+                tot = tot + (c.float().masked_fill(~torch.isfinite(c.float()), 0.0) * uc).sum() * 0.1
+                tot = tot + (m.float().clamp_min(-100.0) * um).sum() * 0.1
+        if "ground" in case["heads"]:
+            lg = out["ground_logits"].float()
+            ug = torch.randn(lg.shape, generator=torch.Generator().manual_seed(5)).to(device)
+            tot = tot + (lg.masked_fill(~torch.isfinite(lg), 0.0) * ug).sum()
+        return tot
+    with ctx:
+        out = model({k: (v.clone() if torch.is_tensor(v) else v) for k, v in d.items()})
+        loss_of(out).backward()
+    def oracle(autocast):
+        sdd = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and not k.endswith("gauss_B") else v.clone())
+               for k, v in sd.items()}
+        with torch.autocast(device, dtype=torch.bfloat16, enabled=autocast):
+            ref = O.query3d_unified_forward(sdd, C.oracle_model_cfg(w, cfg),
+                                            {k: (v.clone() if torch.is_tensor(v) else v) for k, v in d.items()})
+        loss_of(ref).backward()
+        return {k: v.grad for k, v in sdd.items() if v.is_floating_point()}
+    g32, g16 = oracle(False), oracle(True)
+    l2 = lambda a, b: ((a.float() - b.float()).norm() / b.float().norm().clamp_min(1e-12)).item()     # noqa: E731
+    worst = []
+    for k, p in model.named_parameters():
+        r = g32[k]
+        if r is None or float(r.norm()) == 0.0 or k.endswith("w_ks.bias"):
+            continue
+        assert p.grad is not None, f"{k}: no gradient"
+        worst.append((l2(p.grad, r), l2(g16[k], r), k))
+    worst.sort(reverse=True)
+    print(worst[:5])
+    assert len(worst) > 20
+    for e, e16, k in worst:          # the reference's own bf16 path is the yardstick, as on the GPU
+        assert e <= 1.5 * e16 + 3e-2, f"{k}: {e:.3e} (autocast oracle {e16:.3e})"

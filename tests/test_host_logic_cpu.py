@@ -286,3 +286,12 @@ def test_training_host_logic_multiscale_voxel():
     for k, p in enc.named_parameters():
         assert p.grad is not None, k
         assert l2(p.grad, sdd[k].grad) <= 0.12, (k, l2(p.grad, sdd[k].grad))
+
+
+@pytest.mark.parametrize("stage", ["stage1_mask", "stage2_ground"])
+def test_model_level_training_host_logic(stage):
+    """Query3DUnified in .train() on the emulated kernels, dropouts off: gradients of EVERY model parameter (object
+    encoders, coordinate encoder(s), decoder, mask head / ground head) against autograd through the oracle's
+    query3d_unified_forward — the trainer-facing boundary (`loss.backward()` after `model(data_dict)`)."""
+    from _train_hooks import run_model_training_case
+    run_model_training_case(stage, "cpu", _cpu_ops.cpu_backend())

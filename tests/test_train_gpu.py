@@ -456,3 +456,12 @@ def test_stage1_training_mask_head_selfmask_blocks_multiscale():
         print(f"  {k}: ours {e:.3e}  autocast oracle {e16:.3e}")
     for e, e16, k in worst:
         assert e <= 1.5 * e16 + 3e-2, f"{k}: {e:.3e} (autocast oracle {e16:.3e})"
+
+
+@pytest.mark.parametrize("stage", ["stage1_mask", "stage2_ground"])
+def test_model_level_training(stage):
+    """The trainer-facing boundary on the GPU: `model(data_dict)` in .train(), `loss.backward()`, every parameter of
+    Query3DUnified (object encoders, coordinate encoders, decoder, mask / ground head) against oracle autograd."""
+    import contextlib
+    from _train_hooks import run_model_training_case
+    run_model_training_case(stage, DEV, contextlib.nullcontext())
