@@ -262,6 +262,13 @@ int pq3d_attention_bwd(const void* Q, int64_t ldq, int q_col0, const void* dO, i
 int pq3d_mask_head_finalize_bwd(const float* d_logits, const uint8_t* masks, int n_mem, void* d_raw_bf16, int B, int S,
                                 int N, int Np, void* stream);
 
+/* Backward of pq3d_gate_mix: g = sigmoid(gate_logits); d_update = d_out*g, d_query = d_out*(1-g),
+ * d_gate_logits = d_out*(update - query)*g*(1-g) (fp32 and its bf16 copy).  Replaces autograd through
+ * modules/grounding/query_encoder.py:168-170. */
+int pq3d_gate_mix_bwd(const float* gate_logits, const float* query, const float* update, const float* d_out,
+                      float* d_gate_logits, void* d_gate_logits_bf16, float* d_update, float* d_query, int64_t n,
+                      void* stream);
+
 #ifdef __cplusplus
 }
 #endif

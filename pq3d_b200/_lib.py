@@ -44,6 +44,7 @@ SIGNATURES: Dict[str, list] = {
     "pq3d_spatial_bias_bwd": [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _i32, _i32, _i32, _vp],
     "pq3d_add3": [_vp, _vp, _vp, _vp, _i64, _vp],
     "pq3d_pack_segments": [_vp, _vp, _i32, _i32, _vp],
+    "pq3d_gate_mix_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp],
     "pq3d_mask_head_finalize_bwd": [_vp, _vp, _i32, _vp, _i32, _i32, _i32, _i32, _vp],
     "pq3d_attention_bwd": [_vp, _i64, _i32, _vp, _i64, _i32, _vp, _i64, _i32, _vp, _i64, _i32, _i32, _i32, _vp, _i64, _i64,
                            _i64, _vp, _i64, _vp, _vp, _vp, _vp, _i64, _i32, _vp, _i64, _i32, _vp, _i64, _i32, _vp, _i64,

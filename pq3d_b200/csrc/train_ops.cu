@@ -231,6 +231,25 @@ __global__ void mask_head_finalize_bwd_kernel(const float* __restrict__ d_logits
   }
 }
 
+// Backward of pq3d_gate_mix (structure 'gate', query_encoder.py:166-170): out = (1 - g) q + g u, g = sigmoid(gl):
+//   d_u = d g,  d_q = d (1 - g),  d_gl = d (u - q) g (1 - g)   (fp32, plus the bf16 copy of d_gl the dgrad GEMM takes)
+__global__ void gate_mix_bwd_kernel(const float* __restrict__ gl, const float* __restrict__ q, const float* __restrict__ u,
+                                    const float* __restrict__ d_out, float* __restrict__ d_gl,
+                                    __nv_bfloat16* __restrict__ d_gl16, float* __restrict__ d_u, float* __restrict__ d_q,
+                                    int64_t n) {
+  pdl_sync();
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const float g = __fdiv_rn(1.f, 1.f + expf(-gl[i]));
+    const float d = d_out[i];
+    const float dg = d * (u[i] - q[i]) * g * (1.f - g);
+    d_gl[i] = dg;
+    d_gl16[i] = __float2bfloat16_rn(dg);
+    d_u[i] = d * g;
+    d_q[i] = d * (1.f - g);
+  }
+}
+
 }  // namespace pq3d
 
 using namespace pq3d;
@@ -302,5 +321,18 @@ extern "C" int pq3d_mask_head_finalize_bwd(const float* d_logits, const uint8_t*
   PQ3D_CUDA(launch_kernel(mask_head_finalize_bwd_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0,
                           reinterpret_cast<cudaStream_t>(stream), d_logits, masks, n_mem,
                           reinterpret_cast<__nv_bfloat16*>(d_raw_bf16), rows, N, Np));
+  return PQ3D_OK;
+}
+
+extern "C" int pq3d_gate_mix_bwd(const float* gate_logits, const float* query, const float* update, const float* d_out,
+                                 float* d_gate_logits, void* d_gate_logits_bf16, float* d_update, float* d_query, int64_t n,
+                                 void* stream) {
+  PQ3D_CHECK_ARG(gate_logits && query && update && d_out && d_gate_logits && d_gate_logits_bf16 && d_update && d_query &&
+                     n > 0, "pq3d_gate_mix_bwd: bad argument");
+  int64_t blocks = (n + 255) / 256;
+  if (blocks > sm_count() * 16) blocks = sm_count() * 16;
+  PQ3D_CUDA(launch_kernel(gate_mix_bwd_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0,
+                          reinterpret_cast<cudaStream_t>(stream), gate_logits, query, update, d_out, d_gate_logits,
+                          reinterpret_cast<__nv_bfloat16*>(d_gate_logits_bf16), d_update, d_query, n));
   return PQ3D_OK;
 }

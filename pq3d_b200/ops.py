@@ -465,3 +465,17 @@ def mask_head_finalize_bwd(d_logits: torch.Tensor, masks: torch.Tensor, n_mem: i
                                                 d_raw16.shape[1], _stream())
     _lib.check(rc, "pq3d_mask_head_finalize_bwd")
     _count()
+
+
+def gate_mix_bwd(gate_logits, query, update, d_out, d_gl, d_gl16, d_update, d_query):
+    for t, nm in ((gate_logits, "gate_logits"), (query, "query"), (update, "update"), (d_out, "d_out"), (d_gl, "d_gl"),
+                  (d_update, "d_update"), (d_query, "d_query")):
+        _chk(t, torch.float32, nm)
+        if not t.is_contiguous():
+            raise ValueError(f"{nm} must be contiguous")
+    _chk(d_gl16, bf16, "d_gl16")
+    rc = _lib.lib().pq3d_gate_mix_bwd(gate_logits.data_ptr(), query.data_ptr(), update.data_ptr(), d_out.data_ptr(),
+                                      d_gl.data_ptr(), d_gl16.data_ptr(), d_update.data_ptr(), d_query.data_ptr(),
+                                      d_out.numel(), _stream())
+    _lib.check(rc, "pq3d_gate_mix_bwd")
+    _count()

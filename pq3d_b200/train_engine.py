@@ -13,7 +13,7 @@ through ONE `torch.autograd.Function` whose backward runs:
   streaming work     LayerNorm backward, softmax backward (both orientations), bias column sums, the
                      spatial-bias backward -> backward.cu
 
-Scope: structures sequential / parallel / mixed (`gate` raises), any num_blocks, multi-scale (per-layer) memory
+Scope: structures sequential / parallel / mixed / gate, any num_blocks, multi-scale (per-layer) memory
 features, the in-loop mask head (our MaskHeadSegLevel) with use_self_mask, train-mode dropout and memory dropout.
 """
 from __future__ import annotations
@@ -182,11 +182,14 @@ def forward(enc, query, query_pos, query_masks, mems: List[Tuple[str, torch.Tens
         def mem_mask(m):
             st_ = sv["mems"][m]
             return step_masks.get(m, (st_.bits, st_.strides, st_.tiles))
-        for gi, grp in enumerate(program):
+        def ca_group(gi, grp, xq_in, res, **outs):
+            """One cross-attention group (a parallel_ca / sequential_ca call) from the query operands xq_in / res:
+            Q projection, one attention launch over the group's memories, grouped out-projection, add + LayerNorm
+            (+ sublayer dropout, memory-dropout weights) into `outs`.  Returns the record the backward needs."""
             g = len(grp)
             w = lw["groups"][grp]
             Q = _e((R, g * D), bf16, dev)
-            ops.linear(xq, w["wq"], Q, M=R, N=g * D, K=D, bias=w["bq"], alpha=ops.Q_SCALE, alpha_ncols=g * D)
+            ops.linear(xq_in, w["wq"], Q, M=R, N=g * D, K=D, bias=w["bq"], alpha=ops.Q_SCALE, alpha_ncols=g * D)
             O = _e((g, R, D), bf16, dev)
             st_m, st_l = _e((g, B, H, N), f32, dev), _e((g, B, H, N), f32, dev)
             am = [ops.AttnMemory(sv["mems"][m].K, i * D, sv["mems"][m].Vt, i * D, sv["mems"][m].S, sv["mems"][m].Sp,
@@ -204,12 +207,33 @@ def forward(enc, query, query_pos, query_masks, mems: List[Tuple[str, torch.Tens
                 keep = torch.logical_or(keep, (keep.sum(dim=1) == 0).unsqueeze(-1))
                 row_w = (keep.float() / keep.sum(dim=1, keepdim=True).float()).contiguous()
                 enc.last_memory_keep.append(keep)
+            add_ln(y, res, w, g, rng.site(i, rng.SITE_CA_SUBLAYER + gi), row_w, **outs)
+            return dict(grp=grp, gi=gi, xq=xq_in, Q=Q, O=O, m=st_m, l=st_l, y=y, res=res, row_w=row_w,
+                        masks={m: mem_mask(m) for m in grp})
+
+        if enc.structure == "gate":
+            # prompt = CA(query); gate = sigmoid(gate_proj(prompt)); update = parallel_ca(query, scene memories);
+            # query = (1 - gate) * query + gate * update   (query_encoder.py:166-170) — both groups read the SAME query
+            grp_p, grp_s = program
+            pb16 = _e((R, D), bf16, dev)
+            rec_p = ca_group(0, grp_p, xq, q32, out_bf16=pb16)
+            gl = _e((R, D), f32, dev)
+            ops.linear(pb16, lw["gate"]["w"], gl, M=R, N=D, K=D, bias=lw["gate"]["b"])
+            upd = _e((R, D), f32, dev)
+            rec_s = ca_group(1, grp_s, xq, q32, out_f32=upd)
             q_new, xq_new, xv_new = _e((R, D), f32, dev), _e((R, D), bf16, dev), _e((R, D), bf16, dev)
-            add_ln(y, q32, w, g, rng.site(i, rng.SITE_CA_SUBLAYER + gi), row_w, pos=qpos, out_f32=q_new, out_bf16=xv_new,
-                   out_pos_bf16=xq_new)
-            lay["groups"].append(dict(grp=grp, gi=gi, xq=xq, Q=Q, O=O, m=st_m, l=st_l, y=y, res=q32, row_w=row_w,
-                                      masks={m: mem_mask(m) for m in grp}))
+            ops.gate_mix(gl, q32, upd, q_new)
+            ops.cast_bf16(q_new, xq_new, add=qpos)
+            ops.cast_bf16(q_new, xv_new)
+            lay["groups"] = [rec_p, rec_s]
+            lay["gate"] = dict(gl=gl, upd=upd, q=q32, pb16=pb16)
             q32, xq, xv = q_new, xq_new, xv_new
+        else:
+            for gi, grp in enumerate(program):
+                q_new, xq_new, xv_new = _e((R, D), f32, dev), _e((R, D), bf16, dev), _e((R, D), bf16, dev)
+                lay["groups"].append(ca_group(gi, grp, xq, q32, pos=qpos, out_f32=q_new, out_bf16=xv_new,
+                                              out_pos_bf16=xq_new))
+                q32, xq, xv = q_new, xq_new, xv_new
         sa = lw["sa"]
         QK = _e((R, 2 * D), bf16, dev)
         ops.linear(xq, sa["wqk"], QK, M=R, N=2 * D, K=D, bias=sa["bqk"], alpha=ops.Q_SCALE, alpha_ncols=D)
@@ -588,6 +612,28 @@ class _Bwd:
         self.keep += [d_xq, d_res]
         return d_in
 
+    def gate_bwd(self, i, lay, d_out, d_pos, mem_grads):
+        """structure 'gate': through the mix, gate_proj, and BOTH cross-attention groups (same input query)."""
+        R, D, dev, pk = self.R, self.D, self.dev, self.pk
+        gt = lay["gate"]
+        wg = pk.layers[i]["gate"]["w"]
+        d_gl, d_gl16 = _e((R, D), f32, dev), _e((R, D), bf16, dev)
+        d_upd, d_qdir = _e((R, D), f32, dev), _e((R, D), f32, dev)
+        ops.gate_mix_bwd(gt["gl"], gt["q"], gt["upd"], d_out, d_gl, d_gl16, d_upd, d_qdir)
+        with self.on(self.side, d_gl, d_out):
+            self.acc(f"unified_encoder.{i}.gate_proj.bias", self.colsum(d_gl))
+            d_glT, _ = self.tcast(d_gl, R, D)
+            pbT, _ = self.tcast(gt["pb16"], R, D)
+            self.acc(f"unified_encoder.{i}.gate_proj.weight", self.wgrad(d_glT, pbT, D, D))
+        d_pf = self.dgrad(d_gl16, pk.T(wg), D)
+        rec_p, rec_s = lay["groups"]
+        d_in_p = self.group_bwd(i, rec_p, d_pf, d_pos, mem_grads, lay["blk"])
+        d_in_s = self.group_bwd(i, rec_s, d_upd, d_pos, mem_grads, lay["blk"])
+        d_in = _e((R, D), f32, dev)
+        ops.add3(d_qdir, d_in_p, d_in_s, d_in)
+        self.keep += [d_gl16, d_upd, d_qdir, d_pf, d_in_p, d_in_s]
+        return d_in
+
     # ---- whole decoder ------------------------------------------------------------------------------------
     def run(self, d_out: torch.Tensor, d_preds=()):
         sv, B, N, D, L, R, dev, pk = self.sv, self.B, self.N, self.D, self.L, self.R, self.dev, self.pk
@@ -609,8 +655,11 @@ class _Bwd:
             i = lay["i"]
             d_q = self.ffn_bwd(i, lay["ffn"], d_q)
             d_q = self.sa_bwd(i, lay["sa"], d_q, d_pos)
-            for s in reversed(lay["groups"]):
-                d_q = self.group_bwd(i, s, d_q, d_pos, mem_grads, lay["blk"])
+            if "gate" in lay:
+                d_q = self.gate_bwd(i, lay, d_q, d_pos, mem_grads)
+            else:
+                for s in reversed(lay["groups"]):
+                    d_q = self.group_bwd(i, s, d_q, d_pos, mem_grads, lay["blk"])
             if mht is not None:                 # the mask head read this layer's input query
                 d_cls, d_logits = d_preds[2 * step], d_preds[2 * step + 1]
                 if d_cls is not None or d_logits is not None:
@@ -741,8 +790,6 @@ class DecoderFunction(torch.autograd.Function):
 
 def run(enc, input_dict: dict, pairwise_locs, mask_head=None):
     """Entry used by QueryMaskEncoder.forward in training.  Returns (query, predictions_class, predictions_mask)."""
-    if enc.structure == "gate":
-        raise NotImplementedError("pq3d_b200 training path: structure='gate' is inference-only in this build")
     mh, mh_kw = None, None
     if mask_head is not None:
         mh = enc._own_mask_head(mask_head)

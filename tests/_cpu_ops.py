@@ -321,6 +321,16 @@ def gate_mix(gate_logits, query, update, out):
     ops._count()
 
 
+def gate_mix_bwd(gate_logits, query, update, d_out, d_gl, d_gl16, d_update, d_query):
+    g = torch.sigmoid(gate_logits)
+    dg = d_out * (update - query) * g * (1.0 - g)
+    d_gl.copy_(dg)
+    d_gl16.copy_(dg.to(bf16))
+    d_update.copy_(d_out * g)
+    d_query.copy_(d_out * (1.0 - g))
+    ops._count()
+
+
 def mask_head_finalize(raw, mem_mask_ptrs, n_mem, seg_masks, mask_logits, attn_mask, B, S, N, masks=None):
     cnt = (~masks[:n_mem]).sum(0).float()
     v = raw.view(B, S, N) / (cnt[..., None] + 1e-8)
@@ -374,7 +384,7 @@ def _refresh(self):
 PATCHED = ["linear", "bgemm", "attention", "attn_delta", "attention_bwd", "spatial_bias", "spatial_bias_bwd", "ingest_memory",
            "add_layernorm", "add_layernorm_train", "layernorm_bwd", "pack_mask", "cast_bf16", "transpose_cast", "colsum",
            "add3", "dropout_bf16", "gate_mix", "mask_head_finalize", "mask_head_finalize_bwd",
-           "fourier_pos", "pairwise_locs"]
+           "fourier_pos", "pairwise_locs", "gate_mix_bwd"]
 
 
 @contextlib.contextmanager

@@ -44,7 +44,7 @@ def test_inference_host_logic(structure, spatial):
     assert rel(out, ref) <= 3e-2
 
 
-@pytest.mark.parametrize("structure,spatial", [("mixed", True), ("sequential", False)])
+@pytest.mark.parametrize("structure,spatial", [("mixed", True), ("sequential", False), ("gate", True)])
 def test_training_host_logic_gradients(structure, spatial):
     w, sd, inp, pw, up = _case(structure, spatial)
     enc = _build(w, sd).train()

@@ -465,3 +465,9 @@ def test_model_level_training(stage):
     import contextlib
     from _train_hooks import run_model_training_case
     run_model_training_case(stage, DEV, contextlib.nullcontext())
+
+
+def test_grads_gate_structure():
+    """structure='gate': query = (1 - g) * query + g * parallel_ca(query), g = sigmoid(gate_proj(prompt_ca(query)))."""
+    w = synth.Workload("tgate", 2, 64, 200, ["mv", "pc", "prompt"], "gate", T=12, num_layers=2)
+    _run_case(w)
