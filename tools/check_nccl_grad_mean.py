@@ -1,5 +1,12 @@
-"""torchrun --nproc-per-node 2 tools/check_nccl_grad_mean.py — the coalesced in-place NCCL gradient mean
-(pq3d_b200.dist.FlatGradAllReduce) against an all_gather + mean, eagerly and captured in a CUDA graph."""
+"""timeout 120 torchrun --nproc-per-node 2 tools/check_nccl_grad_mean.py — pq3d_b200.dist.FlatGradAllReduce (the default
+flat-buffer path, or the experimental in-place coalesced one with PQ3D_COALESCED_ALLREDUCE=1) against an all_gather +
+mean, eagerly and captured in a CUDA graph.
+
+ALWAYS run under `timeout`: the first run of this script on a 2-GPU box (coalesced variant) never returned and burned the
+box's whole time limit; the script also arms its own 90 s alarm."""
+import signal
+
+signal.alarm(90)
 import os
 import sys
 
