@@ -386,6 +386,34 @@ class ModelCfg:
     projected_memories: Sequence[str] = ("mv", "pc", "voxel")   # ObjectEncoder use_projection=True
 
 
+def prompt_encoder(sd: SD, cfg: "ModelCfg", data_dict: dict):
+    """Query3DUnified.prompt_encoder (model/query3d_unified.py:80-108) with the text tower factored out: rows of type
+    TXT (PromptType.TXT = 1, data/datasets/constant.py:628-631) take `data_dict['prompt_feat']`, rows of type LOC (= 3)
+    are encoded from their location by the coordinate (+ box) encoder, broadcast over the T slots, and keep only slot 0
+    valid (`mask[:, 1:] = False`, written back into data_dict['prompt_pad_masks'] like the reference does).
+    Returns (feat (B, T, D), mask with True = ignore)."""
+    if "prompt_type" not in data_dict or "prompt" not in data_dict:
+        return data_dict["prompt_feat"], data_dict["prompt_pad_masks"].logical_not()
+    prompt, ptype, pad = data_dict["prompt"], data_dict["prompt_type"], data_dict["prompt_pad_masks"]
+    D = sd["coord_encoder.feat_proj.0.weight" if cfg.dim_loc <= 3 else "coord_encoder.0.weight"].shape[0]
+    feat = torch.zeros(tuple(prompt.shape) + (D,), device=prompt.device)
+    txt, loc = ptype == 1, ptype == 3
+    if bool(txt.any()):
+        feat[txt] = data_dict["prompt_feat"][txt].to(feat.dtype)
+    if bool(loc.any()):
+        lp = prompt[loc][:, :cfg.dim_loc].float()
+        if cfg.dim_loc > 3:
+            f = linear_ln(lp[:, :3], sd, "coord_encoder.").unsqueeze(1) + linear_ln(lp[:, 3:6], sd, "box_encoder.").unsqueeze(1)
+        else:
+            f = coordinate_encoder(lp[:, :3].unsqueeze(1), sd, "coord_encoder.", data_dict["coord_min"][loc],
+                                   data_dict["coord_max"][loc])
+        feat[loc] = f.to(feat.dtype)          # (CPU autocast leaves LayerNorm outputs in bf16; CUDA autocast does not)
+        m = pad[loc]
+        m[:, 1:] = False
+        pad[loc] = m
+    return feat, pad.logical_not()
+
+
 def query3d_unified_forward(sd: SD, cfg: ModelCfg, data_dict: dict) -> dict:
     """Query3DUnified.forward, eval mode (model/query3d_unified.py:110-222), restricted to the
     in-scope producers: offline voxel features (ObjectEncoder projection, or an already projected
@@ -411,7 +439,8 @@ def query3d_unified_forward(sd: SD, cfg: ModelCfg, data_dict: dict) -> dict:
 
     for m in cfg.memories:                                                      # :133-160
         if m == "prompt":
-            feat, mask, pos = data_dict["prompt_feat"], data_dict["prompt_pad_masks"].logical_not(), None
+            feat, mask = prompt_encoder(sd, cfg, data_dict)
+            pos = None
         elif m in ("mv", "pc"):
             feat = obj_enc(m, data_dict[f"{m}_seg_fts"])
             mask, pos = data_dict[f"{m}_seg_pad_masks"].logical_not(), fts_pos

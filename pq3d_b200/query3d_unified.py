@@ -63,6 +63,9 @@ def cfg_plain(cfg: Any):
     return cfg
 
 
+PROMPT_TYPE_TXT, PROMPT_TYPE_LOC = 1, 3          # data/datasets/constant.py:628-631 (PromptType)
+
+
 class LinearLN(nn.Sequential):
     """nn.Sequential(Linear, LayerNorm) evaluated by the GEMM + LayerNorm kernels."""
 
@@ -258,6 +261,31 @@ class Query3DUnified(nn.Module):
     def prompt_encoder(self, data_dict):
         """model/query3d_unified.py:80-108 with the text tower factored out: `prompt_feat` (B,T,D) is
         whatever txt_encoder would have produced; returns (feat, mask True=ignore)."""
+        if "prompt_type" in data_dict and "prompt" in data_dict:
+            # mixed batches (:80-108): location prompts go through coord_encoder (+ box_encoder), are broadcast over
+            # the T prompt slots and keep only slot 0 valid; text prompts take their precomputed features
+            prompt, ptype, pad = data_dict["prompt"], data_dict["prompt_type"], data_dict["prompt_pad_masks"]
+            feat = torch.zeros(tuple(prompt.shape) + (self.hidden_size,), device=prompt.device)
+            txt, loc = ptype == PROMPT_TYPE_TXT, ptype == PROMPT_TYPE_LOC
+            if bool(((~txt) & (~loc)).any()):
+                raise NotImplementedError("prompt types other than TXT (1) and LOC (3) are not implemented")
+            if bool(txt.any()):
+                if "prompt_feat" not in data_dict:
+                    raise NotImplementedError("pq3d_b200.Query3DUnified takes precomputed text-prompt features in "
+                                              "data_dict['prompt_feat'] (the CLIP text tower is out of scope)")
+                feat[txt] = data_dict["prompt_feat"][txt].to(feat.dtype)
+            if bool(loc.any()):
+                lp = prompt[loc][:, :self.dim_loc].float()
+                if self.dim_loc > 3:
+                    f = self.coord_encoder(lp[:, :3]).unsqueeze(1) + self.box_encoder(lp[:, 3:6]).unsqueeze(1)
+                else:
+                    f = self.coord_encoder(lp[:, :3].unsqueeze(1),
+                                           input_range=[data_dict["coord_min"][loc], data_dict["coord_max"][loc]])
+                feat[loc] = f.to(feat.dtype)                       # (n, 1, D) broadcast over the T slots, as the reference
+                m = pad[loc]
+                m[:, 1:] = False
+                pad[loc] = m
+            return feat, pad.logical_not()
         if "prompt_feat" not in data_dict:
             raise NotImplementedError("pq3d_b200.Query3DUnified takes precomputed prompt features in "
                                       "data_dict['prompt_feat'] (the CLIP text tower is out of scope)")

@@ -121,3 +121,40 @@ def run_model_training_case(stage, device, ctx):
     assert len(worst) > 20
     for e, e16, k in worst:          # the reference's own bf16 path is the yardstick, as on the GPU
         assert e <= 1.5 * e16 + 3e-2, f"{k}: {e:.3e} (autocast oracle {e16:.3e})"
+
+
+def run_prompt_loc_case(dim_loc, device, ctx):
+    """Query3DUnified forward (eval) on a batch mixing text prompts (precomputed features) and location prompts (encoded
+    by the coordinate encoders, model/query3d_unified.py:80-108) against the oracle's model forward."""
+    from oracle import restatement as O
+    from pq3d_b200 import synth
+    import _cases as C
+    from pq3d_b200.query3d_unified import Query3DUnified
+    case = dict(base="c3", over=dict(B=4, N=16, S=72, T=6, num_layers=2), dim_loc=dim_loc, heads=["ground"], skip=False,
+                wseed=44, sharp=1.0)
+    w, cfg = C.model_cfg(case)
+    sd = C.to_dev(synth.draw_state_dict(synth.model_param_shapes(cfg), case["wseed"], case["sharp"]), device)
+    model = Query3DUnified(cfg).eval()
+    model.load_state_dict(sd, strict=True)
+    model = model.to(device)
+    if device == "cpu":
+        model.unified_encoder.use_cuda_graph = False
+    d = C.to_dev(synth.make_model_data_dict(w, cfg), device)
+    g = torch.Generator().manual_seed(4)
+    d["prompt"] = (torch.rand(w.B, w.T, generator=g) * 3).to(device)
+    d["prompt_type"] = torch.tensor([1, 3, 3, 1]).to(device)
+    clone = lambda dd: {k: (v.clone() if torch.is_tensor(v) else v) for k, v in dd.items()}     # noqa: E731
+    d1, d2 = clone(d), clone(d)
+    with ctx, torch.no_grad():
+        out = model(d1)
+    with torch.no_grad():
+        ref = O.query3d_unified_forward(sd, C.oracle_model_cfg(w, cfg), d2)
+        with torch.autocast(device, dtype=torch.bfloat16):
+            ref16 = O.query3d_unified_forward(sd, C.oracle_model_cfg(w, cfg), clone(d))
+    assert torch.equal(d1["prompt_pad_masks"], d2["prompt_pad_masks"])          # slot mask write-back (:102, :107)
+    a, b, b16 = out["ground_logits"].float(), ref["ground_logits"].float(), ref16["ground_logits"].float()
+    fin = torch.isfinite(b)
+    assert torch.equal(torch.isfinite(a), fin)
+    e = ((a[fin] - b[fin]).abs().max() / b[fin].abs().max()).item()
+    e16 = ((b16[fin] - b[fin]).abs().max() / b[fin].abs().max()).item()
+    assert e <= 1.25 * e16 + 5e-3, (e, e16)

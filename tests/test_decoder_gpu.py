@@ -320,3 +320,11 @@ def test_whole_forward_graph_on_stable_buffers_and_concurrent_streams():
     torch.cuda.synchronize()
     assert torch.equal(res["a"], ref_a) and torch.equal(res["b"], ref_b)
     assert len(enc._ws) >= 3
+
+
+@pytest.mark.parametrize("dim_loc", [3, 6])
+def test_location_prompts(dim_loc):
+    """prompt_encoder's location branch (model/query3d_unified.py:95-102) through the coordinate-encoder kernels."""
+    import contextlib
+    from _train_hooks import run_prompt_loc_case
+    run_prompt_loc_case(dim_loc, DEV, contextlib.nullcontext())

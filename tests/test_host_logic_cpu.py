@@ -295,3 +295,37 @@ def test_model_level_training_host_logic(stage):
     query3d_unified_forward — the trainer-facing boundary (`loss.backward()` after `model(data_dict)`)."""
     from _train_hooks import run_model_training_case
     run_model_training_case(stage, "cpu", _cpu_ops.cpu_backend())
+
+
+@pytest.mark.parametrize("dim_loc", [3, 6])
+def test_location_prompts_host_logic(dim_loc):
+    from _train_hooks import run_prompt_loc_case
+    run_prompt_loc_case(dim_loc, "cpu", _cpu_ops.cpu_backend())
+
+
+def test_training_host_logic_share_layer():
+    """share_layer=True (one QueryEncoderLayer object used by every layer, modules/utils.py:28-32): the gradient of each
+    shared parameter is the sum over the layers that use it."""
+    w, sd, inp, pw, up = _case("mixed", True)
+    L = w.num_layers
+    for k in list(sd):                                   # every layer carries layer 0's weights
+        if k.startswith("unified_encoder.0."):
+            for l in range(1, L):
+                sd[k.replace("unified_encoder.0.", f"unified_encoder.{l}.")] = sd[k].clone()
+    enc = _build(w, sd, share_layer=True).train()
+    enc.train_dropout = 0.0
+    with _cpu_ops.cpu_backend():
+        out = enc(synth.clone_input_dict(inp), pw)[0]
+        (out * up).sum().backward()
+    sdd = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    ref = O.query_mask_encoder(sdd, O.DecoderCfg(**w.decoder_kwargs()), synth.clone_input_dict(inp), pw)[0]
+    (ref * up).sum().backward()
+    assert rel(out, ref) <= 3e-2
+    named = dict(enc.named_parameters())                 # de-duplicated: names of layer 0
+    assert all(k.startswith("unified_encoder.0.") for k in named)
+    for k, p in named.items():
+        if k.endswith("w_ks.bias"):
+            continue
+        r = sum(sdd[k.replace("unified_encoder.0.", f"unified_encoder.{l}.")].grad for l in range(L))
+        e = ((p.grad - r).norm() / r.norm().clamp_min(1e-12)).item()
+        assert e <= 0.12, f"{k}: {e:.3e}"

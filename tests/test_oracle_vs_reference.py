@@ -169,3 +169,48 @@ def test_fully_masked_rows_become_fully_visible():
     a, _, _ = O.query_mask_encoder(sd, O.DecoderCfg(**w.decoder_kwargs()), synth.clone_input_dict(inp), pw, head_all)
     b, _, _ = O.query_mask_encoder(sd, O.DecoderCfg(**w.decoder_kwargs()), synth.clone_input_dict(inp), pw, head_vis)
     assert torch.equal(a, b)
+
+
+@needs_ref
+@pytest.mark.parametrize("dim_loc", [3, 6])
+def test_prompt_encoder_loc_and_txt_rows_match_live_reference(dim_loc):
+    """Query3DUnified.prompt_encoder on a mixed batch: location prompts through the coordinate (+ box) encoder,
+    broadcast over the prompt slots with only slot 0 valid; text rows from a stub tower that returns fixed features
+    (CLIP is out of scope).  The oracle must reproduce features, masks and the in-place mask write-back."""
+    import torch.nn as nn
+    from oracle import make_golden
+    ns = ref_loader.load()
+    case = dict(base="c3", over=dict(B=4, N=12, S=20, T=6, num_layers=1), dim_loc=dim_loc, heads=["ground"], skip=False,
+                wseed=3, sharp=1.0)
+    w, cfg = C.model_cfg(case)
+    g = torch.Generator().manual_seed(12)
+    txt_feat = torch.randn(w.B, w.T, 768, generator=g)
+
+    class _StubTxt(nn.Module):
+        def __init__(self, cfg=None, **kw):
+            super().__init__()
+            self.rows = None
+
+        def forward(self, ids, mask):
+            return txt_feat[self.rows]
+    cfg["model"]["txt_encoder"] = {"name": "_StubTxt"}
+    ns.build.LANGUAGE_REGISTRY._map["_StubTxt"] = _StubTxt
+    sd = synth.draw_state_dict(synth.model_param_shapes(cfg), 3, 1.0)
+    model = ns.query3d_unified.Query3DUnified(ref_loader.to_attr(cfg)).eval()
+    model.load_state_dict(sd, strict=True)
+    ptype = torch.tensor([1, 3, 3, 1])
+    model.txt_encoder.rows = ptype == 1
+    prompt = torch.rand(w.B, w.T, generator=g) * 3
+    pad = torch.rand(w.B, w.T, generator=g) < 0.7
+    pad[:, 0] = True
+    d = dict(prompt=prompt.clone(), prompt_pad_masks=pad.clone(), prompt_type=ptype,
+             coord_min=torch.zeros(w.B, 3), coord_max=torch.full((w.B, 3), 4.0))
+    with torch.no_grad():
+        ref_feat, ref_mask = model.prompt_encoder(d)
+    d2 = dict(prompt=prompt.clone(), prompt_pad_masks=pad.clone(), prompt_type=ptype, prompt_feat=txt_feat,
+              coord_min=torch.zeros(w.B, 3), coord_max=torch.full((w.B, 3), 4.0))
+    with torch.no_grad():
+        feat, mask = O.prompt_encoder(sd, C.oracle_model_cfg(w, cfg), d2)
+    assert torch.equal(mask, ref_mask) and torch.equal(d2["prompt_pad_masks"], d["prompt_pad_masks"])
+    assert torch.allclose(feat, ref_feat, atol=1e-5)
+    assert torch.equal(feat[1, 0], feat[1, w.T - 1])                  # broadcast over the slots
