@@ -220,6 +220,11 @@ class MaskHeadTrain:
         n, D = self.n, self.D
         dev = feats[0][0].device
         self.dev = dev
+        if dev.type == "cuda" and torch.cuda.is_current_stream_capturing():
+            raise NotImplementedError(
+                "pq3d_b200: the mask head's training path builds host-side tables (mask pointer table, class-filter "
+                "index) per forward and cannot be captured into a CUDA graph yet — run stage-1 training steps eagerly "
+                "(GraphedTrainStep covers the decoder-only training step)")
         self.S = S = feats[0][0].shape[1]
         self.seed = seed
         from .train_blocks import MlpHeadTrain
