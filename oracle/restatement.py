@@ -384,6 +384,11 @@ class ModelCfg:
     filter_out_classes: Optional[List[int]] = None
     memories_for_match: Sequence[str] = ()
     projected_memories: Sequence[str] = ("mv", "pc", "voxel")   # ObjectEncoder use_projection=True
+    # Training mode of the modules around the decoder (the decoder's own draws come from decoder.train): an object with
+    #   obj_dropout(memory name, x)  -> dropout(x) after ObjectEncoder's projection (modules/vision/object_encoder.py:75-76)
+    #   head_dropout(head name, h)   -> the Dropout inside get_mlp_head ('mask' cls head / 'ground' head)
+    # None = eval mode.
+    train: Optional[object] = None
 
 
 def prompt_encoder(sd: SD, cfg: "ModelCfg", data_dict: dict):
@@ -435,7 +440,8 @@ def query3d_unified_forward(sd: SD, cfg: ModelCfg, data_dict: dict) -> dict:
     input_dict["query"] = (torch.zeros_like(query_pos), qmask, query_pos)       # :121-123
 
     def obj_enc(name, x):
-        return linear_ln(x, sd, f"{name}_encoder.input_feat_proj.") if name in cfg.projected_memories else x
+        x = linear_ln(x, sd, f"{name}_encoder.input_feat_proj.") if name in cfg.projected_memories else x
+        return x if cfg.train is None else cfg.train.obj_dropout(name, x)
 
     for m in cfg.memories:                                                      # :133-160
         if m == "prompt":
@@ -468,7 +474,8 @@ def query3d_unified_forward(sd: SD, cfg: ModelCfg, data_dict: dict) -> dict:
 
     def mask_head(query, skip=cfg.skip_query_encoder_mask_pred):
         return mask_head_seg_level(query, sd, "mask_head.", seg_fts_for_match, seg_masks,
-                                   cfg.filter_out_classes, None, skip)
+                                   cfg.filter_out_classes, None, skip,
+                                   None if cfg.train is None else (lambda h: cfg.train.head_dropout("mask", h)))
 
     pairwise = calc_pairwise_locs(query_locs[:, :, :3]) if cfg.decoder.spatial_selfattn else None  # :182-187
     query, pcls, pmask = query_mask_encoder(sd, cfg.decoder, input_dict, pairwise,
@@ -483,7 +490,8 @@ def query3d_unified_forward(sd: SD, cfg: ModelCfg, data_dict: dict) -> dict:
             pmask.append(m_)
             data_dict["predictions_class"], data_dict["predictions_mask"] = pcls, pmask
         elif head == "ground":
-            logits = mlp_head(query, sd, "ground_head.og3d_head.").squeeze(2)   # grounding_head.py:51-55
+            logits = mlp_head(query, sd, "ground_head.og3d_head.",
+                              None if cfg.train is None else (lambda h: cfg.train.head_dropout("ground", h))).squeeze(2)   # grounding_head.py:51-55
             logits = logits.masked_fill(data_dict["query_pad_masks"].logical_not(), float("-inf"))
             data_dict["ground_logits"] = logits
             data_dict["og3d_logits"] = logits

@@ -214,3 +214,82 @@ def test_prompt_encoder_loc_and_txt_rows_match_live_reference(dim_loc):
     assert torch.equal(mask, ref_mask) and torch.equal(d2["prompt_pad_masks"], d["prompt_pad_masks"])
     assert torch.allclose(feat, ref_feat, atol=1e-5)
     assert torch.equal(feat[1, 0], feat[1, w.T - 1])                  # broadcast over the slots
+
+
+@needs_ref
+@pytest.mark.parametrize("stage", ["stage1_mask", "stage2_ground"])
+def test_model_training_mode_matches_live_reference(stage):
+    """Query3DUnified in .train() — ObjectEncoder dropout, the decoder's dropouts, the mask head's / ground head's MLP
+    dropout — against the oracle's model forward whose hooks replay torch's RNG in the reference's own order: outputs
+    and the gradient of every parameter agree to fp32 rounding.  (Text tower stubbed: CLIP is out of scope.)"""
+    import torch.nn as nn
+    ns = ref_loader.load()
+    if stage == "stage1_mask":
+        case = dict(base="c2", over=dict(B=2, N=14, S=40, num_layers=2, use_self_mask=True), dim_loc=3, heads=["mask"],
+                    skip=False, wseed=51, sharp=1.0)
+    else:
+        case = dict(base="c3", over=dict(B=2, N=14, S=40, T=5, num_layers=2), dim_loc=6, heads=["ground"], skip=False,
+                    wseed=52, sharp=1.0)
+    w, cfg = C.model_cfg(case)
+    g = torch.Generator().manual_seed(2)
+    txt_feat = torch.randn(w.B, max(w.T, 1), 768, generator=g)
+
+    class _StubTxt(nn.Module):
+        def __init__(self, cfg=None, **kw):
+            super().__init__()
+    if "prompt" in w.memories:
+        cfg["model"]["txt_encoder"] = {"name": "_StubTxt2"}
+        ns.build.LANGUAGE_REGISTRY._map["_StubTxt2"] = _StubTxt
+    sd = synth.draw_state_dict(synth.model_param_shapes(cfg), case["wseed"], case["sharp"])
+    model = ns.query3d_unified.Query3DUnified(ref_loader.to_attr(cfg)).train()
+    model.load_state_dict(sd, strict=True)
+    model.prompt_encoder = lambda dd: (dd["prompt_feat"], dd["prompt_pad_masks"].logical_not())
+    d = synth.make_model_data_dict(w, cfg)
+    if "ground" in case["heads"]:
+        d["tgt_object_id"] = torch.zeros(w.B, dtype=torch.long)
+    clone = lambda dd: {k: (v.clone() if torch.is_tensor(v) else v) for k, v in dd.items()}     # noqa: E731
+
+    def loss_of(out):
+        tot = 0.0
+        if "mask" in case["heads"]:
+            for c, m in zip(out["predictions_class"], out["predictions_mask"]):
+                tot = tot + c.masked_fill(~torch.isfinite(c), 0.0).square().sum() * 0.01 + m.clamp_min(-100.0).square().sum() * 1e-4
+        if "ground" in case["heads"]:
+            lg = out["ground_logits"]
+            tot = tot + lg.masked_fill(~torch.isfinite(lg), 0.0).square().sum()
+        return tot
+    torch.manual_seed(99)
+    ref = model(clone(d))
+    loss_of(ref).backward()
+
+    class Hook(TorchRngTrain):
+        def obj_dropout(self, name, x):
+            return torch.nn.functional.dropout(x, 0.1, True)
+
+        def head_dropout(self, head, h):
+            return torch.nn.functional.dropout(h, 0.3 if head == "ground" else 0.1, True)
+    ocfg = C.oracle_model_cfg(w, cfg)
+    hook = Hook(0.1, 0.0, w.spatial_selfattn)
+    ocfg.train = hook
+    ocfg.decoder.train = hook
+    sdd = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and not k.endswith("gauss_B") else v.clone())
+           for k, v in sd.items()}
+    torch.manual_seed(99)
+    out = O.query3d_unified_forward(sdd, ocfg, clone(d))
+    loss_of(out).backward()
+    if "mask" in case["heads"]:
+        a, b = out["predictions_mask"][-1], ref["predictions_mask"][-1]
+        assert (a - b).abs().max() <= 1e-4 * b.abs().clamp_max(1e3).max()
+    else:
+        fin = torch.isfinite(ref["ground_logits"])
+        assert torch.allclose(out["ground_logits"][fin], ref["ground_logits"][fin], atol=1e-5)
+    gmax = max(float(p.grad.abs().max()) for _, p in model.named_parameters() if p.grad is not None)
+    n = 0
+    for k, p in model.named_parameters():
+        if p.grad is None:
+            continue
+        gg = sdd[k].grad
+        assert gg is not None, k
+        assert float((gg - p.grad).abs().max()) <= 1e-4 * max(float(p.grad.abs().max()), 1e-3 * gmax), k
+        n += 1
+    assert n > 50
