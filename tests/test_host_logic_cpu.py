@@ -329,3 +329,82 @@ def test_training_host_logic_share_layer():
         r = sum(sdd[k.replace("unified_encoder.0.", f"unified_encoder.{l}.")].grad for l in range(L))
         e = ((p.grad - r).norm() / r.norm().clamp_min(1e-12)).item()
         assert e <= 0.12, f"{k}: {e:.3e}"
+
+
+def test_inference_host_logic_in_loop_mask_head_selfmask_blocks():
+    """Inference with our MaskHeadSegLevel in the loop (the path that goes into ONE CUDA graph on the GPU: hoisted
+    k-projection, per-layer head + mask packing + layer on static buffers), use_self_mask, two blocks, on the emulated
+    kernels: per-layer predictions and the decoded queries vs the oracle; the attention-mask side effect on input_dict."""
+    from functools import partial
+    from pq3d_b200.mask_head import MaskHeadSegLevel
+    B, N, S, L, K = 2, 16, 80, 2, 2
+    w = synth.Workload("i1", B, N, S, ["mv", "pc", "voxel"], "parallel", num_layers=L, num_blocks=K, use_self_mask=True)
+    sd = synth.decoder_state_dict(w, seed=23, sharp=1.0)
+    inp, pw, dd = synth.make_decoder_inputs(w)
+    msd = synth.draw_state_dict(synth.mask_head_param_shapes(3), 27)
+    mh = MaskHeadSegLevel(None, 768, 201, memories_for_match=list(w.memories), filter_out_classes=[0, 2]).eval()
+    mh.load_state_dict(msd, strict=True)
+    seg_pad = ~dd["seg_pad_masks"]
+    enc = _build(w, sd).eval()
+    x = synth.clone_input_dict(inp)
+    head = partial(mh, seg_fts_for_match=[list(x[m]) for m in w.memories], seg_masks=seg_pad, offline_attn_masks=None,
+                   skip_prediction=False)
+    with _cpu_ops.cpu_backend(), torch.no_grad():
+        out, pcs, pms = enc(x, pw, head)
+    xo = synth.clone_input_dict(inp)
+    fo = [list(xo[m]) for m in w.memories]
+    with torch.no_grad():
+        ro, pco, pmo = O.query_mask_encoder(sd, O.DecoderCfg(**w.decoder_kwargs()), xo, pw,
+                                            lambda q: O.mask_head_seg_level(q, msd, "", fo, seg_pad, filter_out_classes=[0, 2]))
+    assert len(pcs) == len(pco) == K * L
+    assert rel(out, ro) <= 5e-2
+    for a, b in zip(pms, pmo):
+        keep = b > -1e5
+        assert rel(a[keep], b[keep]) <= 5e-2
+    for a, b in zip(pcs, pco):
+        fin = torch.isfinite(b)
+        assert torch.equal(torch.isfinite(a), fin) and rel(a[fin], b[fin]) <= 5e-2
+    assert x["mv"][1].dtype == torch.bool and x["mv"][1].shape == (B, N, S)
+
+
+def test_inference_host_logic_query_encoder_and_dropped_memories():
+    """QueryEncoder (the mask-less class) and drop_memories_test in eval on the emulated kernels vs the oracle."""
+    from pq3d_b200.query_encoder import QueryEncoder
+    w, sd, inp, pw, _ = _case("mixed", True)
+    enc = _build(w, sd, drop_memories_test=["pc"]).eval()
+    with _cpu_ops.cpu_backend(), torch.no_grad():
+        out = enc(synth.clone_input_dict(inp), pw)[0]
+    cfg = O.DecoderCfg(**dict(w.decoder_kwargs(), drop_memories_test=["pc"]))
+    ref = O.query_mask_encoder(sd, cfg, synth.clone_input_dict(inp), pw)[0]
+    assert rel(out, ref) <= 3e-2
+    kw = {k: v for k, v in w.decoder_kwargs().items() if k not in ("use_self_mask", "num_blocks")}
+    qe = QueryEncoder(None, **kw)
+    qe.load_state_dict(sd, strict=True)
+    qe.use_cuda_graph = False
+    qe.eval()
+    with _cpu_ops.cpu_backend(), torch.no_grad():
+        out2 = qe(synth.clone_input_dict(inp), pw)
+    ref2 = O.query_mask_encoder(sd, O.DecoderCfg(**w.decoder_kwargs()), synth.clone_input_dict(inp), pw)[0]
+    assert rel(out2, ref2) <= 3e-2
+
+
+def test_dropout_sites_are_distinct_streams():
+    """Site numbering of the counter RNG: every dropout call site of every layer (and every mask-head call) gets its own
+    stream, for up to 8 memories and 64 layers; masks of different sites are decorrelated."""
+    from pq3d_b200 import rng
+    sites = set()
+    for layer in range(64):
+        kinds = [rng.SITE_CA_SUBLAYER + g for g in range(4)] + [rng.SITE_SA_SUBLAYER, rng.SITE_FFN_SUBLAYER,
+                                                                rng.SITE_FFN_HIDDEN, rng.SITE_SA_PROBS]
+        kinds += [rng.SITE_CA_PROBS + j for j in range(8)]
+        assert max(kinds) < rng.SITES_PER_LAYER and len(set(kinds)) == len(kinds)
+        for k in kinds:
+            sites.add(rng.site(layer, k))
+    assert len(sites) == 64 * 16 and max(sites) < rng.SITE_MASK_HEAD
+    idx = torch.arange(1 << 14)
+    a = rng.keep_mask(123, rng.site(0, rng.SITE_FFN_HIDDEN), idx, 0.5)
+    b = rng.keep_mask(123, rng.site(1, rng.SITE_FFN_HIDDEN), idx, 0.5)
+    c = rng.keep_mask(124, rng.site(0, rng.SITE_FFN_HIDDEN), idx, 0.5)
+    for other in (b, c):
+        agree = (a == other).float().mean().item()
+        assert 0.45 < agree < 0.55
