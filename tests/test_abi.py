@@ -43,3 +43,20 @@ def test_missing_library_fails_loudly(monkeypatch):
     monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/libpq3d_b200.so")
     with pytest.raises(RuntimeError, match="no CPU or PyTorch fallback"):
         _lib.lib()
+
+
+def test_product_modules_refuse_cpu_tensors():
+    """No CPU path in the product: without the test-only kernel emulation (tests/_cpu_ops.py, which monkeypatches
+    pq3d_b200.ops inside a context manager) the decoder, in eval and in training, raises on CPU tensors."""
+    import torch
+    from pq3d_b200 import synth
+    from pq3d_b200.query_encoder import QueryMaskEncoder
+    w = synth.Workload("t", 1, 8, 16, ["pc"], "parallel", num_layers=1)
+    enc = QueryMaskEncoder(None, **w.decoder_kwargs())
+    inp, pw, _ = synth.make_decoder_inputs(w)
+    enc.eval()
+    with torch.no_grad(), pytest.raises((TypeError, ValueError), match="CUDA"):
+        enc(synth.clone_input_dict(inp), pw)
+    enc.train()
+    with pytest.raises((TypeError, ValueError), match="CUDA"):
+        enc(synth.clone_input_dict(inp), pw)
