@@ -83,14 +83,14 @@ inline cudaError_t launch_kernel_cluster(void (*kernel)(KArgs...), dim3 grid, di
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
+// SM count of the CURRENT device (cached per device index: one process may drive several GPUs).
 inline int sm_count() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-  }
-  return n;
+  static int n[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const int slot = dev >= 0 && dev < 64 ? dev : 0;
+  if (n[slot] == 0) cudaDeviceGetAttribute(&n[slot], cudaDevAttrMultiProcessorCount, dev);
+  return n[slot];
 }
 
 }  // namespace pq3d

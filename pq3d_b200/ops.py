@@ -26,6 +26,11 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+def require_device_tensor(t: torch.Tensor) -> bool:
+    """True when `t` lives where the kernels can read it (the tests' host-logic emulation replaces this)."""
+    return t.is_cuda
+
+
 def _p(t: Optional[torch.Tensor]):
     return None if t is None else t.data_ptr()
 
@@ -33,6 +38,10 @@ def _p(t: Optional[torch.Tensor]):
 def _chk(t: torch.Tensor, dtype, name: str, ndim: Optional[int] = None):
     if not t.is_cuda:
         raise ValueError(f"{name} must be a CUDA tensor (pq3d_b200 has no CPU path)")
+    if t.device.index != torch.cuda.current_device():
+        # launches go to the CURRENT device's stream; a tensor on another GPU would be touched from the wrong context
+        raise ValueError(f"{name} lives on {t.device} but the current CUDA device is cuda:{torch.cuda.current_device()} "
+                         "(call torch.cuda.set_device(local_rank) as DDP launchers do)")
     if t.dtype != dtype:
         raise TypeError(f"{name} must be {dtype}, got {t.dtype}")
     if ndim is not None and t.ndim != ndim:

@@ -169,8 +169,6 @@ class _Packed:
     one pass over the weights, CUDA graphs that captured these pointers stay valid, and `train=True` adds the
     transposed copies the dgrad GEMMs take (`T(w)`)."""
 
-    ALLOW_CPU = False      # set by tests/_cpu_ops.py, whose emulated `refresh` copies on the host
-
     def __init__(self, enc: "QueryMaskEncoder", device, train: bool = False):
         D, L = enc.hidden_size, enc.num_layers
         layers = enc.unified_encoder
@@ -253,7 +251,7 @@ class _Packed:
 
     def _src(self, p: torch.Tensor) -> torch.Tensor:
         p = p.detach()
-        if p.dtype != torch.float32 or not (p.is_cuda or _Packed.ALLOW_CPU) or not p.is_contiguous():
+        if p.dtype != torch.float32 or not ops.require_device_tensor(p) or not p.is_contiguous():
             raise TypeError("pq3d_b200: decoder parameters must be contiguous fp32 CUDA tensors (the kernels' bf16 "
                             f"operand copies are packed from them on the device); got {p.dtype} on {p.device}")
         return p
@@ -483,8 +481,11 @@ class QueryMaskEncoder(nn.Module):
         # one workspace (static buffers + captured graph) per input-shape signature AND per CUDA stream, so several
         # batches can be in flight at once: a single batch's query-side chain is latency-bound and leaves most SMs
         # idle, two or three interleaved batches fill them (bench.py --streams)
+        # (the captured body bakes in the mask buffers' pointers / strides and whether xk aliases xv, so mask rank and
+        # the presence of a positional table are part of the key)
         key = (B, N, tuple((m, tuple(input_dict[m][0][0].shape if isinstance(input_dict[m][0], list)
-                                     else input_dict[m][0].shape)) for m in active),
+                                     else input_dict[m][0].shape), input_dict[m][1].ndim, input_dict[m][2] is None)
+                           for m in active),
                torch.cuda.current_stream(dev).cuda_stream if dev.type == "cuda" else 0)
         ws = self._ws.setdefault(key, {})
         buf = lambda name, shape, dtype: self._buf(ws, name, shape, dtype, dev)  # noqa: E731
@@ -693,10 +694,12 @@ class QueryMaskEncoder(nn.Module):
             predictions_class = [cls_buf[k].clone() for k in range(n_calls)]
             predictions_mask = [logit_buf[k].clone() for k in range(n_calls)]
             if self.use_self_mask:
-                out_mask = fixed.clone()
+                # what the reference leaves behind (query_encoder.py:84-88): attn_mask.repeat_interleave(H, 0),
+                # shape (B*H, N, S), row b*H + h — materialised once per forward, outside the graph
+                out_mask = fixed.repeat_interleave(H, 0)
                 for m in input_dict.keys():
                     if m not in ("query", "prompt"):
-                        input_dict[m][1] = out_mask      # reference: attn_mask.repeat_interleave(H, 0), see below
+                        input_dict[m][1] = out_mask
             if isinstance(voxel_feat, list):
                 input_dict["voxel"][0] = voxel_feat[L - 1]
             return q32.view(B, N, D).clone(), predictions_class, predictions_mask
@@ -719,12 +722,15 @@ class QueryMaskEncoder(nn.Module):
                                          buf("am_bits", (B, N, ops.mask_words(attn_mask.shape[-1])), torch.int32),
                                          unmask_full_rows=True, mask_fixed=fixed.view(torch.uint8),
                                          active_tiles=am_tiles)
+                    rep = None
                     for m in input_dict.keys():
                         if m in ("query", "prompt"):
                             continue
-                        # the reference stores attn_mask.repeat_interleave(H, 0) here (query_encoder.py:84-88);
-                        # the kernels read the packed (B, N, S) bits with a zero head stride instead
-                        input_dict[m][1] = fixed
+                        # the reference stores attn_mask.repeat_interleave(H, 0) here (query_encoder.py:84-88); the
+                        # kernels read the packed (B, N, S) bits with a zero head stride instead
+                        if rep is None:
+                            rep = fixed.repeat_interleave(H, 0)
+                        input_dict[m][1] = rep
                         if m in states:
                             st = states[m]
                             st.bits, st.strides, st.tiles = bits, (bits.stride(0), 0, bits.stride(1)), am_tiles
@@ -863,20 +869,45 @@ class QueryMaskEncoder(nn.Module):
 
 
 class QueryEncoder(QueryMaskEncoder):
-    """modules/grounding/query_encoder.py:11-49: the mask-less variant (`forward(input_dict,
-    pairwise_locs) -> query`).  Its eval-time `dropout_memory` zeroing of dropped memories is the
-    reference's behaviour for `drop_memories_test` here (feat and pos zeroed, memory still attended)."""
+    """modules/grounding/query_encoder.py:11-49: the mask-less variant (`forward(input_dict, pairwise_locs) -> query`).
+    Its layers are built WITHOUT memory_dropout / drop_memories_test (:18); the class drops memories itself
+    (`dropout_memory`, :26-36): in training each scene's feat / pos of every scene memory is zeroed with probability
+    `memory_dropout`, in eval the memories in `drop_memories_test` are zeroed for every scene — the memory is still
+    attended (zero keys / values), unlike QueryMaskEncoder's layer-level drop."""
 
     def __init__(self, cfg=None, memories=[], memory_dropout=0.0, hidden_size=768, num_attention_heads=12,
                  num_layers=4, share_layer=False, spatial_selfattn=False, structure="sequential",
                  drop_memories_test=[]):
-        super().__init__(cfg, memories, memory_dropout, hidden_size, num_attention_heads, num_layers, share_layer,
+        super().__init__(cfg, memories, 0.0, hidden_size, num_attention_heads, num_layers, share_layer,
                          spatial_selfattn, structure, [], False, 1)
-        self._zero_memories = list(drop_memories_test)
+        self.memory_dropout = memory_dropout          # the reference attribute (:22); layers keep memory_dropout = 0
+        self.layer_memory_dropout = 0.0
+        self.drop_memories_test = list(drop_memories_test)
+        self.last_scene_drop: Dict[str, torch.Tensor] = {}
+
+    def _active(self) -> List[str]:
+        return list(self.memories)                    # layer-level drop_memories_test is empty for this class (:18)
+
+    def dropout_memory(self, input_dict):
+        """:26-36, in place on the caller's tensors like the reference."""
+        self.last_scene_drop = {}
+        for memory in self.scene_meomories:
+            if memory not in input_dict:
+                continue
+            feat, mask, pos = input_dict[memory]
+            nb = feat.shape[0]
+            if self.training:
+                drop_mask = torch.rand(nb, device=feat.device) < self.memory_dropout
+            elif memory in self.drop_memories_test:
+                drop_mask = torch.ones(nb, device=feat.device, dtype=torch.bool)
+            else:
+                drop_mask = torch.zeros(nb, device=feat.device, dtype=torch.bool)
+            self.last_scene_drop[memory] = drop_mask
+            feat[drop_mask] = 0.
+            if pos is not None:
+                pos[drop_mask] = 0.
 
     def forward(self, input_dict, pairwise_locs):
-        for m in self._zero_memories:                      # dropout_memory, eval branch (:31-36)
-            if m in input_dict and m != "prompt":
-                input_dict[m][0].zero_()
-                input_dict[m][2].zero_()
+        if (self.training and self.memory_dropout > 0) or (not self.training and self.drop_memories_test):
+            self.dropout_memory(input_dict)
         return super().forward(input_dict, pairwise_locs, None)[0]

@@ -79,7 +79,7 @@ def forward(enc, query, query_pos, query_masks, mems: List[Tuple[str, torch.Tens
     # train-time dropout (QueryEncoderLayer(dropout=0.1), query_encoder.py:97): counter RNG keyed by a per-forward device
     # seed, so the backward regenerates every mask and a CUDA-graph replay draws fresh ones
     p_drop = float(enc.train_dropout) if enc.training else 0.0
-    p_mem = float(enc.memory_dropout) if enc.training else 0.0
+    p_mem = float(getattr(enc, "layer_memory_dropout", enc.memory_dropout)) if enc.training else 0.0
     seed = None
     if p_drop > 0.0 and N > 128:
         raise NotImplementedError("pq3d_b200 training path: dropout needs the fused attention backward (N <= 128 "
@@ -288,12 +288,13 @@ class _Bwd:
         self.B, self.N, self.D, self.H, self.L, self.R = (sv[k] for k in ("B", "N", "D", "H", "L", "R"))
         self.Rp = ops.pad64(self.R)
         self.grads: Dict[str, torch.Tensor] = {}
+        self.pending: Dict[str, List[torch.Tensor]] = {}
         self.dev = sv["qpos"].device
         self.keep: List = []
-        self.cuda = self.dev.type == "cuda"          # (the host logic also runs against tests/_cpu_ops.py's emulation)
-        self.main = torch.cuda.current_stream(self.dev) if self.cuda else None
+        self.streams_on = bool(enc.train_streams)    # False: everything on the caller's stream, in program order
+        self.main = torch.cuda.current_stream(self.dev) if self.streams_on else None
         n_par = max([len(g) for g in sv["program"]] + [1])
-        pool = _side_streams(self.dev, n_par) if (enc.train_streams and self.cuda) else []
+        pool = _side_streams(self.dev, n_par) if self.streams_on else []
         self.side = pool[0] if pool else None
         self.par = pool[1:] if pool else []
         self.forked = set()
@@ -310,7 +311,7 @@ class _Bwd:
     def on(self, stream, *deps):
         """Context: run on `stream` after everything issued so far on the main stream; deps are kept alive."""
         self.keep.extend(d for d in deps if d is not None)
-        if not self.cuda:
+        if not self.streams_on:
             return contextlib.nullcontext()
         if stream is None:
             return torch.cuda.stream(self.main)
@@ -319,7 +320,7 @@ class _Bwd:
         return torch.cuda.stream(stream)
 
     def join(self, streams=None):
-        if not self.cuda:
+        if not self.streams_on:
             return
         cur = torch.cuda.current_stream(self.dev)
         for st in (list(self.forked) if streams is None else streams):
@@ -329,11 +330,20 @@ class _Bwd:
 
     # ---- small helpers --------------------------------------------------------------------------
     def acc(self, name: str, g: torch.Tensor):
+        """Record a gradient contribution.  Contributions are produced on different streams (main, side, per-memory);
+        they are only SUMMED in `finish_grads`, after every stream has joined — an add issued here would read tensors
+        whose producer may still be queued on another stream (num_blocks > 1, share_layer)."""
         name = self.sv["canon"].get(name, name)           # share_layer: one parameter under several names
-        if name in self.grads:
-            self.grads[name] = self.grads[name] + g
-        else:
+        self.pending.setdefault(name, []).append(g)
+
+    def finish_grads(self):
+        """After the final join: one tensor per parameter (sums where a parameter received several contributions)."""
+        for name, parts in self.pending.items():
+            g = parts[0]
+            for extra in parts[1:]:
+                g = g + extra
             self.grads[name] = g
+        self.pending.clear()
 
     def tcast(self, x, rows, cols, want_c=False, gate=None, scale=1.0):
         """x [rows, cols] (fp32/bf16) -> (bf16 x^T [cols, pad64(rows)], bf16 copy or None)."""
@@ -601,9 +611,8 @@ class _Bwd:
                 for jj, j in enumerate(idx):
                     self.wgrad(dQT[jj * D:(jj + 1) * D], xqT, D, D, out=G[j, :D])
         mg_q = mem_grads["_q"]
-        for jj, j in enumerate(idx):
-            prev = mg_q.get((i, j))
-            mg_q[(i, j)] = d_bq[jj * D:(jj + 1) * D] if prev is None else prev + d_bq[jj * D:(jj + 1) * D]
+        for jj, j in enumerate(idx):          # d_bq lives on the side stream: summed there (memory-side tail of run())
+            mg_q.setdefault((i, j), []).append(d_bq[jj * D:(jj + 1) * D])
         d_xq = self.dgrad(dQ16, pk.T(w["wq"]), D)
         d_in = _e((R, D), f32, dev)
         ops.add3(d_res, d_xq, None, d_in)
@@ -698,7 +707,10 @@ class _Bwd:
                 G_b[:, j, D:2 * D].copy_(d_bk.view(L, D))
                 G_b[:, j, 2 * D:].copy_(d_bv.view(L, D))
                 for i in range(L):
-                    G_b[i, j, :D].copy_(mem_grads["_q"][(i, j)])
+                    parts = mem_grads["_q"][(i, j)]
+                    G_b[i, j, :D].copy_(parts[0])
+                    for extra in parts[1:]:
+                        G_b[i, j, :D].add_(extra)
             for i in range(L):
                 pre = f"unified_encoder.{i}.cross_attn_list.{j}.multihead_attn."
                 for G in self.G_blk:
@@ -735,6 +747,7 @@ class _Bwd:
         if mht is not None:
             mh_out = mht.finish()
         self.join()
+        self.finish_grads()
         self.keep.clear()
         return d_q.view(B, N, D), d_pos.view(B, N, D), d_mem, self.grads, mh_out
 
@@ -821,9 +834,10 @@ def run(enc, input_dict: dict, pairwise_locs, mask_head=None):
     outs = DecoderFunction.apply(enc, meta, query, query_pos, *flat, *mh_feats, *[p for _, p in params],
                                  *[p for _, p in mh_params])
     if enc.use_self_mask and meta.get("final_mask") is not None:
+        rep = meta["final_mask"].repeat_interleave(enc.num_heads, 0)      # (B*H, N, S), row b*H + h (:84)
         for m in input_dict.keys():                # the reference leaves the last attention mask in input_dict (:85-88)
             if m not in ("query", "prompt"):
-                input_dict[m][1] = meta["final_mask"]
+                input_dict[m][1] = rep
     if "voxel" in input_dict and isinstance(input_dict["voxel"][0], (list, tuple)):
         input_dict["voxel"][0] = input_dict["voxel"][0][enc.num_layers - 1]      # what the reference's loop leaves (:90-91)
     return outs[0], list(outs[1::2]), list(outs[2::2])

@@ -46,12 +46,27 @@ class GraphedTrainStep:
     loss_fn      loss_fn(decoded_queries, *loss_args) -> scalar tensor
     reducer      optional callable run between backward and optimizer.step (pq3d_b200.dist.FlatGradAllReduce)
 
+    pre_step     optional callable run after the reducer and before optimizer.step, inside the captured step — the hook
+                 for the reference's `clip_grad_norm_` (trainer/query3d_trainer.py:24); it must be capturable (torch's
+                 foreach clip_grad_norm_ with error_if_nonfinite=False is)
+
     The first `warmup` calls run eagerly on a side stream (allocator / kernel-attribute warm-up), the next call
     captures, later calls copy the new batch into the captured input buffers and replay.  Shapes must not change.
+
+    Learning rate: a CUDA graph freezes Python floats.  Build the optimizer with `lr=torch.tensor(lr, device=...)`
+    (torch's capturable optimizers read a tensor lr on the device) and let the scheduler write into that tensor
+    (`set_lr`), otherwise the reference's warm-up / cosine LambdaLR has no effect on replayed steps.  A float lr is
+    converted to a device tensor here for exactly that reason.
     """
 
-    def __init__(self, encoder, optimizer, loss_fn: Callable, reducer: Optional[Callable] = None, warmup: int = 3):
+    def __init__(self, encoder, optimizer, loss_fn: Callable, reducer: Optional[Callable] = None, warmup: int = 3,
+                 pre_step: Optional[Callable] = None):
         self.enc, self.opt, self.loss_fn, self.reducer = encoder, optimizer, loss_fn, reducer
+        self.pre_step = pre_step
+        dev = next(encoder.parameters()).device
+        for grp in optimizer.param_groups:            # float lr -> device tensor, so schedulers act on replayed steps
+            if not isinstance(grp.get("lr"), torch.Tensor) and dev.type == "cuda":
+                grp["lr"] = torch.tensor(float(grp["lr"]), dtype=torch.float32, device=dev)
         self.warmup, self.calls = max(1, warmup), 0   # >= 1: buffers the capture reuses are created eagerly
         self.graph = None
         self.static = None
@@ -66,8 +81,19 @@ class GraphedTrainStep:
         loss.backward()
         if self.reducer is not None:
             self.reducer()
+        if self.pre_step is not None:
+            self.pre_step()
         self.opt.step()
         return loss
+
+    def set_lr(self, lr: float, group: Optional[int] = None):
+        """Write a new learning rate into the optimizer's device-side lr tensors (takes effect on the next replay)."""
+        for gi, grp in enumerate(self.opt.param_groups):
+            if group is None or gi == group:
+                if isinstance(grp["lr"], torch.Tensor):
+                    grp["lr"].fill_(float(lr))
+                else:
+                    grp["lr"] = float(lr)
 
     @staticmethod
     def _clone_struct(inp):
@@ -103,6 +129,8 @@ class GraphedTrainStep:
             self.loss.backward()
             if self.reducer is not None:
                 self.reducer()
+            if self.pre_step is not None:
+                self.pre_step()
             self.opt.step()
         self.launches = ops.LAUNCHES - before
         ops.LAUNCHES = before

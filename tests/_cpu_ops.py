@@ -391,15 +391,15 @@ PATCHED = ["linear", "bgemm", "attention", "attn_delta", "attention_bwd", "spati
 def cpu_backend():
     """Route `pq3d_b200.ops` through the emulation for the duration of the block."""
     saved = {n: getattr(ops, n) for n in PATCHED}
-    saved_refresh, saved_allow = query_encoder._Packed.refresh, query_encoder._Packed.ALLOW_CPU
+    saved_refresh, saved_req = query_encoder._Packed.refresh, ops.require_device_tensor
     try:
         for n in PATCHED:
             setattr(ops, n, globals()[n])
         query_encoder._Packed.refresh = _refresh
-        query_encoder._Packed.ALLOW_CPU = True
+        ops.require_device_tensor = lambda t: True
         yield
     finally:
         for n, f in saved.items():
             setattr(ops, n, f)
         query_encoder._Packed.refresh = saved_refresh
-        query_encoder._Packed.ALLOW_CPU = saved_allow
+        ops.require_device_tensor = saved_req

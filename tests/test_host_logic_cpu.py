@@ -26,6 +26,11 @@ def _case(structure="mixed", spatial=True, N=24, S=150, L=2):
     return w, sd, inp, pw, torch.randn(q.shape, generator=g)
 
 
+def xo_mask_expected(rep, H):
+    """(B*H, N, S) built by repeat_interleave(H, 0): rows b*H .. b*H+H-1 are identical copies."""
+    return rep.view(-1, H, *rep.shape[1:])[:, :1].expand(-1, H, -1, -1).reshape(rep.shape)
+
+
 def _build(w, sd, **kw):
     enc = QueryMaskEncoder(None, **dict(w.decoder_kwargs(), **kw))
     enc.load_state_dict(sd, strict=True)
@@ -223,7 +228,8 @@ def test_stage1_training_host_logic_mask_head_selfmask_blocks():
         out, pcs, pms = enc(x, pw, head)
         assert len(pcs) == n_pred and len(pms) == n_pred
         loss_of(out, pcs, pms).backward()
-    assert x["mv"][1].shape == (B, N, S) and x["mv"][1].dtype == torch.bool      # reference side effect (:85-88)
+    assert x["mv"][1].shape == (B * enc.num_heads, N, S) and x["mv"][1].dtype == torch.bool   # reference side effect (:84-88)
+    assert torch.equal(x["mv"][1], xo_mask_expected(x["mv"][1], enc.num_heads))
     # oracle
     sdd = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
     msdd = {k: v.clone().requires_grad_(True) for k, v in msd.items()}
@@ -364,7 +370,8 @@ def test_inference_host_logic_in_loop_mask_head_selfmask_blocks():
     for a, b in zip(pcs, pco):
         fin = torch.isfinite(b)
         assert torch.equal(torch.isfinite(a), fin) and rel(a[fin], b[fin]) <= 5e-2
-    assert x["mv"][1].dtype == torch.bool and x["mv"][1].shape == (B, N, S)
+    assert x["mv"][1].dtype == torch.bool and x["mv"][1].shape == (B * enc.num_heads, N, S)
+    assert x["mv"][1].shape == xo["mv"][1].shape                      # same layout as the oracle / reference leaves
 
 
 def test_inference_host_logic_query_encoder_and_dropped_memories():
@@ -386,6 +393,44 @@ def test_inference_host_logic_query_encoder_and_dropped_memories():
         out2 = qe(synth.clone_input_dict(inp), pw)
     ref2 = O.query_mask_encoder(sd, O.DecoderCfg(**w.decoder_kwargs()), synth.clone_input_dict(inp), pw)[0]
     assert rel(out2, ref2) <= 3e-2
+
+
+@pytest.mark.skipif(not __import__("oracle.ref_loader", fromlist=["x"]).available(), reason="/root/reference not present")
+def test_query_encoder_train_mode_memory_dropout_matches_live_reference():
+    """QueryEncoder.train() (query_encoder.py:26-36): each scene's feat / pos of every scene memory is zeroed with
+    probability memory_dropout (torch.rand per memory, in place), the layers themselves drop nothing.  Same torch seed
+    -> same draws as the LIVE reference class; outputs compared with the reference's sublayer dropouts switched off."""
+    from oracle import ref_loader
+    from pq3d_b200.query_encoder import QueryEncoder
+    ns = ref_loader.load()
+    w, sd, inp, pw, _ = _case("mixed", True)
+    kw = {k: v for k, v in w.decoder_kwargs().items() if k not in ("use_self_mask", "num_blocks")}
+    kw["memory_dropout"] = 0.5
+    ref = ns.query_encoder.QueryEncoder(None, **kw).train()
+    ref.load_state_dict(sd, strict=True)
+    for m in ref.modules():
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0
+        if isinstance(m, torch.nn.MultiheadAttention):
+            m.dropout = 0.0
+    ours = QueryEncoder(None, **kw).train()
+    ours.load_state_dict(sd, strict=True)
+    ours.use_cuda_graph, ours.train_streams, ours.train_dropout = False, False, 0.0
+    assert ours.memory_dropout == 0.5 and all(l.memory_dropout == 0 for l in ours.unified_encoder)
+    hit = False
+    for seed in (3, 4, 5):
+        xr, xo = synth.clone_input_dict(inp), synth.clone_input_dict(inp)
+        torch.manual_seed(seed)
+        with torch.no_grad():
+            r = ref(xr, pw)
+        torch.manual_seed(seed)
+        with _cpu_ops.cpu_backend(), torch.no_grad():
+            o = ours(xo, pw)
+        for m in ("mv", "pc", "voxel"):                     # the caller's tensors are zeroed in place, identically
+            assert torch.equal(xr[m][0], xo[m][0]) and torch.equal(xr[m][2], xo[m][2])
+            hit = hit or bool(ours.last_scene_drop[m].any())
+        assert rel(o, r) <= 3e-2
+    assert hit, "no scene was dropped in three draws at p = 0.5"
 
 
 def test_dropout_sites_are_distinct_streams():
