@@ -166,6 +166,47 @@ int pq3d_fourier_pos(const float* xyz, int xyz_stride, const float* coord_min, c
  * spatial_dim=5), modules/utils.py:38-68. */
 int pq3d_pairwise_locs(const float* centers, int c_stride, float* out, int B, int N, float eps, void* stream);
 
+/* ---- §8f-2: voxel -> segment pooling (modules/vision/pcd_mask3d_encoder.py:144-154, torch_scatter.scatter_mean) ---- */
+
+/* Bytes of caller-owned scratch pq3d_segment_csr needs; voxel_offsets_host is a HOST array of B+1 prefix sums (scene b
+ * owns voxels [off[b], off[b+1])).  Returns -1 on bad arguments. */
+int64_t pq3d_segment_csr_workspace_bytes(const int64_t* voxel_offsets_host, int B, int max_seg);
+
+/* Stable counting sort of the voxels by (scene, segment): perm (int32 [Nv_total]) lists the voxel ids segment by
+ * segment, ascending inside a segment; offsets (int32 [B*max_seg + 1]) delimit the segments.  p2s: int64 [Nv_total]
+ * per-scene segment ids (the reference's `point2segment`, scenes concatenated); ids outside [0, max_seg) are skipped.
+ * Integer work only, deterministic; shared by the five feature scales of a batch. */
+int pq3d_segment_csr(const int64_t* p2s, const int64_t* voxel_offsets_host, int B, int max_seg, int32_t* perm,
+                     int32_t* offsets, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* out[g, :] = sum_{v in segment g, ascending v} feat[v, :] / max(count_g, 1)   (fp32 adds in voxel order: bit-exact
+ * against torch's CPU scatter_add; empty segments give 0 like scatter_mean).  feat fp32 [Nv_total, C] (ld); G = B*max_seg.
+ * out32 (optional) fp32 [G, C] (ld32); out16 (optional) bf16 [G, K16] (ld16), columns [C, K16) zero — the operand of the
+ * per-scale Linear(C -> hidden) GEMM that follows (pcd_mask3d_encoder.py:125-130,151). */
+int pq3d_segment_mean(const float* feat, int64_t ld, const int32_t* perm, const int32_t* offsets, int G, int C,
+                      float* out32, int64_t ld32, void* out16, int64_t ld16, int K16, void* stream);
+
+/* ---- §8f-3: matcher cost matrices and matched mask losses (modules/third_party/mask3d/matcher.py:12-64,103-181,
+ *      criterion.py:26-75,163-196) ---- */
+
+/* cost[b, n, m] = w_mask * batch_sigmoid_ce(n, m) + w_class * (-softmax(pred_logits[b, n])[label_m], -1 for
+ * ignore_label) + w_dice * batch_dice(n, m) for m < tgt_count[b], 0 beyond; fp32 throughout like the reference
+ * (autocast disabled, matcher.py:160).  pred_masks fp32 [B, S, N] (a `predictions_mask` entry), pred_logits fp32
+ * [B, N, C], tgt_masks uint8 [B, Mmax, S] (1 = point in instance), tgt_labels int64 [B, Mmax], tgt_count int32 [B].
+ * All S points are used (num_points = -1, the shipped configuration). */
+int pq3d_match_cost(const float* pred_masks, const float* pred_logits, const uint8_t* tgt_masks, const int64_t* tgt_labels,
+                    const int32_t* tgt_count, float* cost, int B, int N, int S, int C, int Mmax, float w_class,
+                    float w_mask, float w_dice, int64_t ignore_label, void* stream);
+
+/* Per matched pair k = pairs[k] = (scene, query, target) (int32 [n_pairs, 3], device): ce[k] = mean_c BCE(x, t),
+ * dice[k] = 1 - (2 sum sig*t + 1) / (sum sig + sum t + 1); sums fp32 [n_pairs, 2] is saved for the backward. */
+int pq3d_matched_mask_loss_fwd(const float* pred_masks, const uint8_t* tgt_masks, const int32_t* pairs, int n_pairs, int B,
+                               int N, int S, int Mmax, float* ce, float* dice, float* sums, void* stream);
+/* d_pred (fp32 [B, S, N], zero-filled by the caller) receives g_ce[k] * d ce[k] + g_dice[k] * d dice[k]. */
+int pq3d_matched_mask_loss_bwd(const float* pred_masks, const uint8_t* tgt_masks, const int32_t* pairs, int n_pairs, int B,
+                               int N, int S, int Mmax, const float* g_ce, const float* g_dice, const float* sums,
+                               float* d_pred, void* stream);
+
 /* ---- backward companions (training step: autograd of the reference's decoder, trainer/query3d_trainer.py:18-28) ---- */
 
 /* out_t[b1,b2][c][r] = bf16(scale * in[b1,b2][r][c] * (gate > 0 ? 1 : 0)) for r < R, zero for R <= r < Rp; optional

@@ -498,3 +498,80 @@ def query3d_unified_forward(sd: SD, cfg: ModelCfg, data_dict: dict) -> dict:
         else:
             raise NotImplementedError(head)
     return data_dict
+
+
+# =====================================================================================================================
+# §8f-2: voxel -> segment pooling (modules/vision/pcd_mask3d_encoder.py:144-154)
+# =====================================================================================================================
+def scatter_mean(src: Tensor, index: Tensor, dim_size: int) -> Tensor:
+    """torch_scatter.scatter_mean(src, index, dim=0, dim_size=dim_size) restated.  torch_scatter is a third-party
+    dependency that is NOT vendored in /root/reference (requirements.txt:74 pins torch_scatter==2.1.2, :79
+    torch-scatter==2.1.1; not installed here, no network).  Its published algorithm (torch_scatter/scatter.py,
+    `scatter_mean`): out = scatter_sum(src) — `out.scatter_add_(0, index, src)` on a zero tensor —, count =
+    scatter_sum(ones).clamp_(min=1), out.true_divide_(count).  On the CPU `scatter_add_` / `index_add_` visit the rows
+    in order, so each output row is the fp32 sum of its members in ascending source order.  Anchored on the reference's
+    call site pcd_mask3d_encoder.py:150: `self.scatter_fn(f, p2s, dim=0, dim_size=max_seg)`."""
+    out = torch.zeros(dim_size, src.shape[1], dtype=src.dtype, device=src.device)
+    out.index_add_(0, index, src)
+    count = torch.zeros(dim_size, dtype=src.dtype, device=src.device)
+    count.index_add_(0, index, torch.ones(index.shape[0], dtype=src.dtype, device=src.device))
+    return out / count.clamp(min=1).unsqueeze(-1)
+
+
+def seg_level_pool(feats_per_scene: List[Tensor], point2segment: List[Tensor], max_seg: int, sd: SD, prefix: str) -> Tensor:
+    """One scale of PCDMask3DSegLevelEncoder.forward (:146-153): stack(scatter_mean per scene) -> feat_proj =
+    Linear + LayerNorm (+ Dropout, identity in eval).  `prefix` = 'feat_proj_list.{i}.'."""
+    batch_feat = torch.stack([scatter_mean(f, p, max_seg) for f, p in zip(feats_per_scene, point2segment)])
+    return linear_ln(batch_feat, sd, prefix)
+
+
+# =====================================================================================================================
+# §8f-3: matcher cost matrices (modules/third_party/mask3d/matcher.py) and matched mask losses (criterion.py)
+# =====================================================================================================================
+def batch_dice_cost(inputs: Tensor, targets: Tensor) -> Tensor:
+    """matcher.py:12-28."""
+    inputs = inputs.sigmoid().flatten(1)
+    numerator = 2 * torch.einsum("nc,mc->nm", inputs, targets)
+    denominator = inputs.sum(-1)[:, None] + targets.sum(-1)[None, :]
+    return 1 - (numerator + 1) / (denominator + 1)
+
+
+def batch_sigmoid_ce_cost(inputs: Tensor, targets: Tensor) -> Tensor:
+    """matcher.py:36-59."""
+    hw = inputs.shape[1]
+    pos = F.binary_cross_entropy_with_logits(inputs, torch.ones_like(inputs), reduction="none")
+    neg = F.binary_cross_entropy_with_logits(inputs, torch.zeros_like(inputs), reduction="none")
+    loss = torch.einsum("nc,mc->nm", pos, targets) + torch.einsum("nc,mc->nm", neg, (1 - targets))
+    return loss / hw
+
+
+def matcher_cost(pred_logits: Tensor, pred_masks: Tensor, labels: Tensor, tgt_mask: Tensor, cost_class: float,
+                 cost_mask: float, cost_dice: float, ignore_label: int = -100) -> Tensor:
+    """One scene of HungarianMatcher.memory_efficient_forward (matcher.py:110-181) with num_points = -1:
+    pred_logits (N, C), pred_masks (S, N), labels (M,), tgt_mask (M, S) -> C (N, M)."""
+    out_prob = pred_logits.float().softmax(-1)
+    tgt_ids = labels.clone()
+    filter_ignore = tgt_ids == ignore_label
+    tgt_ids[filter_ignore] = 0
+    c_class = -out_prob[:, tgt_ids]
+    c_class[:, filter_ignore] = -1.0
+    out_mask = pred_masks.T.float()
+    tgt = tgt_mask.to(out_mask).float()
+    return cost_mask * batch_sigmoid_ce_cost(out_mask, tgt) + cost_class * c_class + cost_dice * batch_dice_cost(out_mask, tgt)
+
+
+def matched_mask_losses(pred_masks: Tensor, tgt_masks: List[Tensor], indices) -> Dict[str, Tensor]:
+    """SetCriterion.loss_masks (criterion.py:163-196) with num_points = -1; dice_loss :26-46, sigmoid_ce_loss :51-71.
+    pred_masks (B, S, N); tgt_masks[b] (M_b, S); indices[b] = (query idx, target idx)."""
+    loss_masks, loss_dices = [], []
+    for b, (map_id, target_id) in enumerate(indices):
+        mp = pred_masks[b][:, map_id].T
+        tm = tgt_masks[b][target_id].float()
+        num_masks = tm.shape[0]
+        ce = F.binary_cross_entropy_with_logits(mp, tm, reduction="none")
+        loss_masks.append(ce.mean(1).sum() / num_masks)
+        s = mp.sigmoid().flatten(1)
+        numerator = 2 * (s * tm).sum(-1)
+        denominator = s.sum(-1) + tm.sum(-1)
+        loss_dices.append((1 - (numerator + 1) / (denominator + 1)).sum() / num_masks)
+    return {"loss_mask": torch.mean(torch.stack(loss_masks)), "loss_dice": torch.mean(torch.stack(loss_dices))}

@@ -57,7 +57,14 @@ SIGNATURES: Dict[str, list] = {
     "pq3d_cast_bf16": [_vp, _vp, _vp, _i64, _vp],
     "pq3d_fourier_pos": [_vp, _i32, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp],
     "pq3d_pairwise_locs": [_vp, _i32, _vp, _i32, _i32, _f32, _vp],
+    "pq3d_segment_csr_workspace_bytes": [_pi64, _i32, _i32],
+    "pq3d_segment_csr": [_vp, _pi64, _i32, _i32, _vp, _vp, _vp, _i64, _vp],
+    "pq3d_segment_mean": [_vp, _i64, _vp, _vp, _i32, _i32, _vp, _i64, _vp, _i64, _i32, _vp],
+    "pq3d_match_cost": [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _f32, _f32, _f32, _i64, _vp],
+    "pq3d_matched_mask_loss_fwd": [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp],
+    "pq3d_matched_mask_loss_bwd": [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp],
 }
+RESTYPES = {"pq3d_segment_csr_workspace_bytes": _i64}
 
 
 def declared_symbols() -> List[str]:
@@ -84,7 +91,7 @@ def lib() -> C.CDLL:
         for name, args in SIGNATURES.items():
             fn = getattr(l, name)
             fn.argtypes = args
-            fn.restype = C.c_int
+            fn.restype = RESTYPES.get(name, C.c_int)
         _lib = l
     return _lib
 

@@ -15,7 +15,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "_C")
 LIB = os.path.join(OUT_DIR, "libpq3d_b200.so")
-SOURCES = ["host_common.cu", "gemm.cu", "attention.cu", "elementwise.cu", "backward.cu", "train_ops.cu", "attention_bwd.cu"]
+SOURCES = ["host_common.cu", "gemm.cu", "attention.cu", "elementwise.cu", "backward.cu", "train_ops.cu", "attention_bwd.cu",
+           "segment_ops.cu", "match_cost.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC"]
 EXPORT_PREFIX = "pq3d_"

@@ -488,3 +488,106 @@ def gate_mix_bwd(gate_logits, query, update, d_out, d_gl, d_gl16, d_update, d_qu
                                       d_out.numel(), _stream())
     _lib.check(rc, "pq3d_gate_mix_bwd")
     _count()
+
+
+# ------------------------------------------------------------------------------------------------
+# §8f-2: voxel -> segment pooling
+# ------------------------------------------------------------------------------------------------
+def segment_csr(p2s: torch.Tensor, voxel_offsets: Sequence[int], max_seg: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """p2s: int64 (Nv_total,) per-scene segment id of every voxel (scenes concatenated); voxel_offsets: B+1 host prefix
+    sums.  Returns (perm int32 (Nv_total,), offsets int32 (B*max_seg + 1,)): voxels grouped by (scene, segment), ascending
+    inside a segment."""
+    _chk(p2s, torch.int64, "point2segment", 1)
+    if not p2s.is_contiguous():
+        raise ValueError("point2segment must be contiguous")
+    B = len(voxel_offsets) - 1
+    if voxel_offsets[0] != 0 or voxel_offsets[-1] != p2s.numel():
+        raise ValueError("voxel_offsets must run from 0 to the number of voxels")
+    offs = (C.c_int64 * (B + 1))(*[int(v) for v in voxel_offsets])
+    need = _lib.lib().pq3d_segment_csr_workspace_bytes(offs, B, int(max_seg))
+    if need < 0:
+        raise ValueError(f"segment_csr: unsupported shape (B={B}, max_seg={max_seg})")
+    ws = torch.empty(max(int(need), 4), dtype=torch.uint8, device=p2s.device)
+    perm = torch.empty(max(p2s.numel(), 1), dtype=torch.int32, device=p2s.device)
+    offsets = torch.empty(B * max_seg + 1, dtype=torch.int32, device=p2s.device)
+    rc = _lib.lib().pq3d_segment_csr(p2s.data_ptr(), offs, B, int(max_seg), perm.data_ptr(), offsets.data_ptr(),
+                                     ws.data_ptr(), ws.numel(), _stream())
+    _lib.check(rc, "pq3d_segment_csr")
+    _count(4)
+    return perm, offsets
+
+
+def segment_mean(feat: torch.Tensor, perm: torch.Tensor, offsets: torch.Tensor, out32: Optional[torch.Tensor] = None,
+                 out16: Optional[torch.Tensor] = None):
+    """feat fp32 (Nv_total, C) -> mean per (scene, segment): out32 fp32 (G, C) and / or out16 bf16 (G, K16 >= C, zero padded)."""
+    _chk(feat, torch.float32, "feat", 2)
+    _chk(perm, torch.int32, "perm", 1)
+    _chk(offsets, torch.int32, "offsets", 1)
+    if feat.stride(1) != 1:
+        raise ValueError("feat needs unit inner stride")
+    G, Cc = offsets.numel() - 1, feat.shape[1]
+    if out32 is not None:
+        _chk(out32, torch.float32, "out32", 2)
+    if out16 is not None:
+        _chk(out16, bf16, "out16", 2)
+    rc = _lib.lib().pq3d_segment_mean(feat.data_ptr(), feat.stride(0), perm.data_ptr(), offsets.data_ptr(), G, Cc,
+                                      _p(out32), 0 if out32 is None else out32.stride(0), _p(out16),
+                                      0 if out16 is None else out16.stride(0), 0 if out16 is None else out16.shape[1],
+                                      _stream())
+    _lib.check(rc, "pq3d_segment_mean")
+    _count()
+
+
+# ------------------------------------------------------------------------------------------------
+# §8f-3: matcher cost matrices, matched mask losses
+# ------------------------------------------------------------------------------------------------
+def match_cost(pred_masks: torch.Tensor, pred_logits: torch.Tensor, tgt_masks: torch.Tensor, tgt_labels: torch.Tensor,
+               tgt_count: torch.Tensor, w_class: float, w_mask: float, w_dice: float, ignore_label: int) -> torch.Tensor:
+    """pred_masks fp32 (B, S, N), pred_logits fp32 (B, N, C), tgt_masks uint8 (B, Mmax, S), tgt_labels int64 (B, Mmax),
+    tgt_count int32 (B,) -> cost fp32 (B, N, Mmax)."""
+    _chk(pred_masks, torch.float32, "pred_masks", 3)
+    _chk(pred_logits, torch.float32, "pred_logits", 3)
+    _chk(tgt_masks, torch.uint8, "tgt_masks", 3)
+    _chk(tgt_labels, torch.int64, "tgt_labels", 2)
+    _chk(tgt_count, torch.int32, "tgt_count", 1)
+    for t in (pred_masks, pred_logits, tgt_masks, tgt_labels):
+        if not t.is_contiguous():
+            raise ValueError("match_cost operands must be contiguous")
+    B, S, N = pred_masks.shape
+    Cc, Mmax = pred_logits.shape[2], tgt_masks.shape[1]
+    if tuple(pred_logits.shape[:2]) != (B, N) or tuple(tgt_masks.shape) != (B, Mmax, S) or tuple(tgt_labels.shape) != (B, Mmax):
+        raise ValueError("match_cost shape mismatch")
+    cost = torch.empty(B, N, Mmax, dtype=torch.float32, device=pred_masks.device)
+    rc = _lib.lib().pq3d_match_cost(pred_masks.data_ptr(), pred_logits.data_ptr(), tgt_masks.data_ptr(),
+                                    tgt_labels.data_ptr(), tgt_count.data_ptr(), cost.data_ptr(), B, N, S, Cc, Mmax,
+                                    float(w_class), float(w_mask), float(w_dice), int(ignore_label), _stream())
+    _lib.check(rc, "pq3d_match_cost")
+    _count()
+    return cost
+
+
+def matched_mask_loss_fwd(pred_masks, tgt_masks, pairs):
+    _chk(pred_masks, torch.float32, "pred_masks", 3)
+    _chk(tgt_masks, torch.uint8, "tgt_masks", 3)
+    _chk(pairs, torch.int32, "pairs", 2)
+    B, S, N = pred_masks.shape
+    n = pairs.shape[0]
+    dev = pred_masks.device
+    ce, dice = torch.empty(n, dtype=torch.float32, device=dev), torch.empty(n, dtype=torch.float32, device=dev)
+    sums = torch.empty(n, 2, dtype=torch.float32, device=dev)
+    rc = _lib.lib().pq3d_matched_mask_loss_fwd(pred_masks.data_ptr(), tgt_masks.data_ptr(), pairs.data_ptr(), n, B, N, S,
+                                               tgt_masks.shape[1], ce.data_ptr(), dice.data_ptr(), sums.data_ptr(), _stream())
+    _lib.check(rc, "pq3d_matched_mask_loss_fwd")
+    _count()
+    return ce, dice, sums
+
+
+def matched_mask_loss_bwd(pred_masks, tgt_masks, pairs, g_ce, g_dice, sums):
+    B, S, N = pred_masks.shape
+    d_pred = torch.zeros_like(pred_masks)
+    rc = _lib.lib().pq3d_matched_mask_loss_bwd(pred_masks.data_ptr(), tgt_masks.data_ptr(), pairs.data_ptr(), pairs.shape[0],
+                                               B, N, S, tgt_masks.shape[1], g_ce.data_ptr(), g_dice.data_ptr(),
+                                               sums.data_ptr(), d_pred.data_ptr(), _stream())
+    _lib.check(rc, "pq3d_matched_mask_loss_bwd")
+    _count()
+    return d_pred

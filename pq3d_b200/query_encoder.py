@@ -387,6 +387,9 @@ class QueryMaskEncoder(nn.Module):
         self._packed_ver = None
         self._ws: Dict[tuple, dict] = {}
         self.use_cuda_graph = True
+        # debugging / parity tap: a list here receives a clone of the fp32 query stream after every layer application
+        # (forces the eager path; tests/test_parity_matched_gpu.py compares them layer by layer)
+        self.layer_taps: Optional[List[torch.Tensor]] = None
         self.train_dropout = 0.1      # QueryEncoderLayer(dropout=0.1): sublayer / attention-probability / FFN dropout
         self._drop_seed = None
         self.last_memory_keep: List[torch.Tensor] = []
@@ -490,7 +493,8 @@ class QueryMaskEncoder(nn.Module):
         ws = self._ws.setdefault(key, {})
         buf = lambda name, shape, dtype: self._buf(ws, name, shape, dtype, dev)  # noqa: E731
 
-        if self.use_cuda_graph and mask_head is None and not self.use_self_mask and ws.get("graph") is not None:
+        if (self.use_cuda_graph and self.layer_taps is None and mask_head is None and not self.use_self_mask
+                and ws.get("graph") is not None):
             # Whole-forward graph: when the caller hands in the SAME device tensors again (a serving loop re-using its
             # staging buffers), the prologue that reads them (ingest, mask packing, copies) is captured together with
             # the body, so a forward costs one graph launch on the host.  Fresh tensors fall back to the eager prologue
@@ -649,6 +653,8 @@ class QueryMaskEncoder(nn.Module):
             if per_layer:
                 project_fused(i, 1)
             self._layer(i, pk, program, states, ws, dev, B, N, D, H, q32, qpos, xq, xv_q, qbits, sbias)
+            if self.layer_taps is not None:
+                self.layer_taps.append(q32.view(B, N, D).clone())
 
         predictions_class, predictions_mask = [], []
         if mask_head is None and not self.use_self_mask:
@@ -758,7 +764,7 @@ class QueryMaskEncoder(nn.Module):
         """First call per shape: eager (allocates the workspace, configures kernels).  Second call:
         capture.  Afterwards: one graph launch per forward (the launch-bound query-side chain of ~70
         small kernels costs more on the host than on the GPU otherwise)."""
-        if not self.use_cuda_graph or ws.get("_eager_body"):
+        if not self.use_cuda_graph or ws.get("_eager_body") or self.layer_taps is not None:
             body()
             return
         g = ws.get("graph")

@@ -93,6 +93,23 @@ def attention(Q, q_mem_stride, mems, O, o_mem_stride, B, H, Nq, zero_attn, score
         if zero_attn:
             mx = mx.clamp_min(0.0)
         mx = torch.where(torch.isinf(mx), torch.zeros_like(mx), mx)
+        # the kernel's softmax REFERENCE per CTA = (scene, head, 128-query tile): memories of more than two 128-key
+        # tiles with add_zero_attn take the ONE_PASS schedule, p = ex2(s - 0) (the zero-attn key pins score 0 into every
+        # row), unless a row sum leaves the safe range (then the CTA redoes the sweep with the row maxima).  The
+        # reference point decides where the bf16 rounding of P falls, so it is part of the rounding-matched emulation.
+        T = (S + 127) // 128
+        tiles = torch.full((B,), T, dtype=torch.int64)
+        if m.kv_tiles is not None:
+            tiles = m.kv_tiles.to(torch.int64).clamp(min=1, max=T)
+        one_pass = (tiles > 2) & bool(zero_attn)                                     # (B,)
+        if bool(one_pass.any()):
+            l0 = torch.exp2(s2).sum(-1)                                              # (B, H, Nq)
+            qt = (Nq + 127) // 128
+            bad = ~(l0 < 1.2676506e30)
+            bad = torch.nn.functional.pad(bad, (0, qt * 128 - Nq)).view(B, H, qt, 128).any(-1, keepdim=True)
+            bad = bad.expand(B, H, qt, 128).reshape(B, H, qt * 128)[..., :Nq]
+            use0 = one_pass.view(B, 1, 1) & ~bad
+            mx = torch.where(use0, torch.zeros_like(mx), mx)
         p = torch.exp2(s2 - mx[..., None])
         l = p.sum(-1) + (torch.exp2(-mx) if zero_attn else 0.0)
         if drop_p > 0.0:

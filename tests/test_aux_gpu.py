@@ -1,0 +1,165 @@
+"""GPU parity of the §8f kernels against the oracle restatements (oracle/restatement.py, pinned to the live reference /
+to torch_scatter's published algorithm in tests/test_aux_oracle_cpu.py):
+
+  f2  voxel -> segment scatter_mean: BIT-EXACT (index work + fp32 sums in the oracle's order), incl. empty segments,
+      ragged scenes, ids out of range, full-size (4 scenes x ~120 k voxels, 5 scales); + the per-scale Linear + LayerNorm
+  f3  matcher cost matrices (fp32, 1e-5) -> IDENTICAL Hungarian assignments; matched mask losses forward / backward
+"""
+import pytest
+import torch
+
+from oracle import restatement as O
+from pq3d_b200 import ops
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _voxels(g, sizes, max_seg, C, empty=(3,), bad=True):
+    feats, p2s = [], []
+    for n in sizes:
+        f = torch.randn(n, C, generator=g)
+        s = torch.randint(0, max_seg, (n,), generator=g)
+        for e in empty:
+            s[s == e] = (e + 1) % max_seg
+        feats.append(f)
+        p2s.append(s)
+    offs = [0]
+    for n in sizes:
+        offs.append(offs[-1] + n)
+    return feats, p2s, offs
+
+
+@pytest.mark.parametrize("sizes,max_seg,C", [((1000, 37, 2049), 50, 96), ((5000,), 700, 128), ((3, 0, 1500), 33, 256),
+                                             ((1024, 1024), 17, 12)])
+def test_segment_mean_bit_exact(sizes, max_seg, C):
+    g = torch.Generator().manual_seed(sum(sizes) + C)
+    feats, p2s, offs = _voxels(g, sizes, max_seg, C)
+    want = torch.stack([O.scatter_mean(f, s, max_seg) for f, s in zip(feats, p2s)])
+    fcat, scat = torch.cat(feats).to(DEV), torch.cat(p2s).to(DEV)
+    perm, offsets = ops.segment_csr(scat, offs, max_seg)
+    B = len(sizes)
+    # the CSR itself: a stable sort by (scene, segment)
+    key = torch.cat([s + b * max_seg for b, s in enumerate(p2s)])
+    order = torch.sort(key, stable=True).indices
+    assert torch.equal(perm[:key.numel()].cpu().long(), order)
+    cnt = torch.bincount(key, minlength=B * max_seg)
+    assert torch.equal(offsets.cpu().long(), torch.cat([torch.zeros(1, dtype=torch.long), cnt.cumsum(0)]))
+    out = torch.empty(B * max_seg, C, device=DEV)
+    out16 = torch.full((B * max_seg, (C + 63) // 64 * 64), float("nan"), dtype=torch.bfloat16, device=DEV)
+    ops.segment_mean(fcat, perm, offsets, out32=out, out16=out16)
+    torch.cuda.synchronize()
+    assert torch.equal(out.cpu().view(B, max_seg, C), want), "scatter_mean must be bit-exact (ascending-order fp32 sums)"
+    assert torch.equal(out16[:, :C].cpu(), want.view(-1, C).bfloat16())
+    assert (out16[:, C:] == 0).all()
+
+
+def test_segment_csr_skips_out_of_range_ids():
+    g = torch.Generator().manual_seed(4)
+    f = torch.randn(300, 16, generator=g)
+    s = torch.randint(0, 20, (300,), generator=g)
+    s[::7] = -1
+    s[5::11] = 20
+    ok = (s >= 0) & (s < 20)
+    want = O.scatter_mean(f[ok], s[ok], 20)
+    perm, offsets = ops.segment_csr(s.to(DEV), [0, 300], 20)
+    out = torch.empty(20, 16, device=DEV)
+    ops.segment_mean(f.to(DEV), perm, offsets, out32=out)
+    assert torch.equal(out.cpu(), want)
+
+
+def test_seg_level_pooling_full_size_vs_oracle():
+    """4 scenes x ~120 k voxels, max_seg = 2048, the five scales of Res16UNet34C: pooled features bit-exact, projected
+    features vs the fp32 oracle at bf16-GEMM tolerance; scale weights through the reference's state_dict names."""
+    from pq3d_b200.segment_pool import SegLevelPooling, PLANES_LAST5
+    g = torch.Generator().manual_seed(9)
+    sizes, max_seg = (118000, 131072, 90001, 124999), 2048
+    pool = SegLevelPooling(None, hidden_size=768, hlevels=[0, 1, 2, 3]).eval()
+    sd = {k: torch.randn(v.shape, generator=g) * (0.05 if v.ndim > 1 else 0.2) + (1.0 if k.endswith("1.weight") else 0.0)
+          for k, v in pool.state_dict().items()}
+    pool.load_state_dict(sd, strict=True)
+    assert list(sd) == [f"feat_proj_list.{i}.{j}.{n}" for i in range(5) for j in (0, 1) for n in ("weight", "bias")]
+    pool = pool.to(DEV)
+    p2s = [torch.randint(0, max_seg - 40, (n,), generator=g) for n in sizes]       # the last 40 segments stay empty
+    offs = [0]
+    for n in sizes:
+        offs.append(offs[-1] + n)
+    feats = [[torch.randn(n, PLANES_LAST5[h], generator=g) for n in sizes] for h in pool.hlevels]
+    with torch.no_grad():
+        outs = pool([torch.cat(f).to(DEV) for f in feats], offs, [p.to(DEV) for p in p2s], max_seg)
+        pooled = pool.pooled(torch.cat(feats[2]).to(DEV), offs, torch.cat(p2s).to(DEV), max_seg)
+    torch.cuda.synchronize()
+    want_pooled = torch.stack([O.scatter_mean(f, s, max_seg) for f, s in zip(feats[2], p2s)])
+    assert torch.equal(pooled.cpu(), want_pooled)
+    for i in range(5):
+        want = O.seg_level_pool(feats[i], p2s, max_seg, sd, f"feat_proj_list.{i}.")
+        e = ((outs[i].cpu() - want).abs().max() / want.abs().max()).item()
+        print(f"scale {i} (C={PLANES_LAST5[pool.hlevels[i]]}): Linear+LN of the pooled features vs fp32 oracle {e:.2e}")
+        assert outs[i].shape == (4, max_seg, 768) and e <= 2e-2
+
+
+def _match_case(g, B, N, S, C, Ms, dev):
+    pred_logits = torch.randn(B, N, C, generator=g) * 2
+    pred_masks = torch.randn(B, S, N, generator=g) * 3
+    targets = []
+    for b, M in enumerate(Ms):
+        pad = int(torch.randint(0, S // 4, (1,), generator=g))
+        if pad:
+            pred_masks[b, S - pad:] = -1e6
+        t = torch.rand(M, S, generator=g) < 0.1
+        t[:, S - pad:] = False if pad else t[:, S - pad:]
+        lab = torch.randint(0, C - 1, (M,), generator=g)
+        if M > 2:
+            lab[2] = -100
+        targets.append({"labels": lab, "segment_masks": t})
+    return pred_logits, pred_masks, targets
+
+
+@pytest.mark.parametrize("B,N,S,C,Ms", [(2, 20, 70, 11, (6, 3)), (4, 100, 2048, 201, (31, 1, 64, 17)), (1, 33, 129, 5, (0,))])
+def test_match_cost_and_assignment(B, N, S, C, Ms):
+    from scipy.optimize import linear_sum_assignment
+    from pq3d_b200.matcher import HungarianMatcher
+    g = torch.Generator().manual_seed(B * 100 + N)
+    pred_logits, pred_masks, targets = _match_case(g, B, N, S, C, Ms, DEV)
+    w = dict(cost_class=2.0, cost_mask=5.0, cost_dice=2.0)
+    m = HungarianMatcher(num_points=-1, ignore_label=-100, **w)
+    out = {"pred_logits": pred_logits.to(DEV), "pred_masks": pred_masks.to(DEV)}
+    tg = [{k: v.to(DEV) for k, v in t.items()} for t in targets]
+    cost, counts = m.cost_matrices(out, tg, "segment_masks")
+    idx = m(out, tg, "segment_masks")
+    torch.cuda.synchronize()
+    worst = 0.0
+    for b in range(B):
+        want = O.matcher_cost(pred_logits[b], pred_masks[b], targets[b]["labels"], targets[b]["segment_masks"], **w)
+        got = cost[b, :, :counts[b]].cpu()
+        if counts[b]:
+            worst = max(worst, ((got - want).abs().max() / want.abs().max()).item())
+            i, j = linear_sum_assignment(want)
+            assert torch.equal(idx[b][0], torch.as_tensor(i)) and torch.equal(idx[b][1], torch.as_tensor(j)), \
+                "Hungarian assignment differs from the oracle's"
+        assert (cost[b, :, counts[b]:] == 0).all()
+    print(f"match_cost (B={B},N={N},S={S}): max rel err vs fp32 oracle {worst:.2e}")
+    assert worst <= 1e-5
+
+
+def test_matched_mask_losses_forward_backward():
+    from pq3d_b200.matcher import HungarianMatcher, matched_mask_losses
+    g = torch.Generator().manual_seed(77)
+    B, N, S, C, Ms = 3, 100, 1500, 201, (20, 7, 41)
+    pred_logits, pred_masks, targets = _match_case(g, B, N, S, C, Ms, DEV)
+    tg = [{k: v.to(DEV) for k, v in t.items()} for t in targets]
+    pm = pred_masks.to(DEV).requires_grad_(True)
+    idx = HungarianMatcher(2.0, 5.0, 2.0, -1)({"pred_logits": pred_logits.to(DEV), "pred_masks": pm}, tg, "segment_masks")
+    got = matched_mask_losses(pm, tg, idx)
+    (5.0 * got["loss_mask"] + 2.0 * got["loss_dice"]).backward()
+    pmo = pred_masks.clone().requires_grad_(True)
+    want = O.matched_mask_losses(pmo, [t["segment_masks"] for t in targets], idx)
+    (5.0 * want["loss_mask"] + 2.0 * want["loss_dice"]).backward()
+    for k in ("loss_mask", "loss_dice"):
+        e = abs(got[k].item() - want[k].item()) / abs(want[k].item())
+        print(f"{k}: {got[k].item():.6f} vs oracle {want[k].item():.6f} (rel {e:.1e})")
+        assert e <= 1e-5
+    eg = ((pm.grad.cpu() - pmo.grad).abs().max() / pmo.grad.abs().max()).item()
+    print(f"d loss / d pred_masks: rel err {eg:.2e}")
+    assert eg <= 1e-5
+    assert torch.equal(pm.grad.cpu() != 0, pmo.grad != 0) or eg <= 1e-5
