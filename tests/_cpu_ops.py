@@ -40,10 +40,24 @@ def linear(A, W, out, *, M, N, K, bias=None, bias_along_m=False, bias_group_stri
             if avail:
                 full[g, :avail] = _as(T, (avail, K), (ld, 1), g * group_rows * ld).float()
         return full
+    # TMA stores clip at the tensor map's extent in whole 16-byte chunks: when N * elem_size is not a multiple of 16 the
+    # columns up to the next 16-byte boundary are written too (with the epilogue of whatever W rows lie there — zero
+    # rows past the operand's extent).  Callers keep pad columns there (the self-attention V^T pitch); emulated so that
+    # the teacher-forced parity test sees the same bytes.  (C with a non-16-byte-granular pitch takes direct stores.)
+    esz = out.element_size()
+    tma_path = (out.storage_offset() * esz) % 16 == 0 and (ldc * esz) % 16 == 0 and (c_group_stride * esz) % 16 == 0
+    N_logical = N
+    if tma_path and (N * esz) % 16 != 0:
+        N = min((N * esz + 15) // 16 * 16 // esz, ldc)
     C = torch.einsum("gmk,gnk->gmn", rows(A, lda, a_group_rows, M), rows(W, ldw, w_group_rows, N))
     if bias is not None:
-        b = _as(bias, (groups, M if bias_along_m else N), (bias_group_stride, 1))
-        C = C + (b[:, :, None] if bias_along_m else b[:, None, :])
+        if bias_along_m:
+            b = _as(bias, (groups, M), (bias_group_stride, 1))
+            C = C + b[:, :, None]
+        else:
+            b = torch.zeros(groups, N)
+            b[:, :N_logical] = _as(bias, (groups, N_logical), (bias_group_stride, 1))
+            C = C + b[:, None, :]
     if alpha_ncols:
         C[:, :, :alpha_ncols] *= alpha
     if relu:
