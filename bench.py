@@ -46,6 +46,10 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--streams", type=int, default=4,
                     help="batches in flight (CUDA streams) in the device-resident throughput loop; 1 = strictly serial")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the sub-records that cost extra seconds: sustained loop, reference-on-this-GPU timing, "
+                         "training sub-record")
+    ap.add_argument("--sustained-seconds", type=float, default=3.0)
     ap.add_argument("--train", action="store_true",
                     help="training step (fwd + bwd + AdamW, gradient all-reduce for N>1); implied by --workload c5")
     return ap.parse_args()
@@ -62,7 +66,7 @@ def workload_config(w, n_gpus):
 # ------------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the oracle port on host cores
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_run(w, steps, warmup, budget_s, train=False):
+def cpu_reference_run(w, steps, warmup, budget_s, train=False, sample_scenes=0):
     """Times the reference algorithm (oracle restatement == reference modules to 1e-5, fp32)
     on the host cores with all threads, on a BOUNDED sample: one scene of the workload per step.
     train=True: forward + autograd backward + AdamW, what trainer/query3d_trainer.py:18-28 does per step."""
@@ -74,7 +78,7 @@ def cpu_reference_run(w, steps, warmup, budget_s, train=False):
     ws = synth.workload(w.name)
     for k in ("N", "S", "T", "num_layers", "num_blocks", "structure"):
         setattr(ws, k, getattr(w, k))
-    ws.B = 1
+    ws.B = sample_scenes if sample_scenes else w.B
     sd = synth.decoder_state_dict(ws, seed=0)
     cfg = O.DecoderCfg(**ws.decoder_kwargs())
     if train:
@@ -113,19 +117,21 @@ def cpu_reference_run(w, steps, warmup, budget_s, train=False):
                 warmup = i + 1          # slow host: cut the warm-up short
     med = statistics.median(times)
     return {"value": ws.B * ws.N / med, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"1 of {w.B} scenes per step (N={ws.N}, S={ws.S}, same memories/layers), fp32, "
+            "sample": f"{ws.B} of {w.B} scenes per step (N={ws.N}, S={ws.S}, same memories/layers), fp32, "
                       f"{len(times)} timed {'training steps (fwd+bwd+AdamW)' if train else 'forwards'}, "
                       f"median {med * 1e3:.1f} ms",
-            "ms_per_step": med * 1e3, "steps": len(times)}
+            "ms_per_step": med * 1e3, "steps": len(times), "warmup": warmup}
 
 
 def run_reference_arm(args, w, rank, world):
     if rank != 0:
         return
     train = args.train or w.name == "c5"
-    r = cpu_reference_run(w, args.steps, min(args.warmup, 3), budget_s=120.0, train=train)
+    # the reference's own algorithm at the SAME configuration (all scenes of the per-GPU shard, same warm-up count);
+    # the time budget only cuts the number of timed steps short on a slow host
+    r = cpu_reference_run(w, args.steps, args.warmup, budget_s=150.0, train=train)
     line = {"impl": "reference", "metric": TRAIN_METRIC if train else METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
-            "steps": r["steps"], "warmup": min(args.warmup, 3), "ms_per_step": r["ms_per_step"],
+            "steps": r["steps"], "warmup": r["warmup"], "ms_per_step": r["ms_per_step"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(w, args.gpus),
             "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
@@ -181,9 +187,135 @@ class ClockSampler(threading.Thread):
 
 
 # ------------------------------------------------------------------------------------------------
+# sub-records of the inference line
+# ------------------------------------------------------------------------------------------------
+def attention_roofline(w, dev, peaks):
+    """The north-star's named kernel — the cross-attention core Q.K^T / softmax / P.V of the scene memories — timed live
+    with CUDA events: one launch = all scene memories x scenes x heads of one layer (what the decoder issues per layer).
+    Reported against BOTH denominators: tensor (algorithmic 4.N.(S+1).D FLOP per scene-memory) and HBM
+    (K + V read once: 2.S.D.2 bytes per scene-memory, + Q and O).  `cold`: every launch reads a different layer-sized
+    K / V^T set (4 sets = 302 MB at config 3 > the 126 MB L2), as in the real step; `l2_warm`: the same set again."""
+    import torch
+    from pq3d_b200 import ops
+    B, N, S, D, H = w.B, w.N, w.S, w.hidden_size, w.num_heads
+    scene = [m for m in w.memories if m != "prompt"]
+    nm = len(scene)
+    if nm == 0:
+        return None
+    Sp = ops.pad8(S)
+    R = B * N
+    Q = (torch.randn(R, nm * D, device=dev) * 0.2).bfloat16()
+    n_sets = 4
+    sets = []
+    for _ in range(n_sets):
+        mems = []
+        for _i in range(nm):
+            Kb = torch.randn(B * Sp, D, device=dev).bfloat16()
+            Vt = torch.randn(D, B * Sp, device=dev).bfloat16()
+            bits = ops.pack_mask(torch.rand(B, S, device=dev) < 0.1)
+            mems.append(ops.AttnMemory(Kb, 0, Vt, 0, S, Sp, bits, bits.stride(0), 0, 0))
+        sets.append(mems)
+    O = torch.empty(nm, R, D, dtype=torch.bfloat16, device=dev)
+
+    def run(rotate, reps=48):
+        for i in range(8):
+            ops.attention(Q, D, sets[i % n_sets if rotate else 0], O, R * D, B, H, N, True)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(reps):
+            ops.attention(Q, D, sets[i % n_sets if rotate else 0], O, R * D, B, H, N, True)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps * 1e3                     # us per launch
+    us_cold, us_warm = run(True), run(False)
+    flops = nm * B * 4.0 * N * (S + 1) * D
+    bytes_ = nm * B * (2.0 * S * D * 2 + 2.0 * N * D * 2)
+    tpk, hbm = peaks.get("bf16_tflops", 1590.0), peaks.get("hbm_gbs", 6650.0)
+    return {"kernel": f"attention_fwd_kernel: {nm} scene memories x {B} scenes x {H} heads, N={N} queries (padded to 128 "
+                      f"rows in TMEM: 22 % of the MMA slots idle by construction), S={S} keys + zero-attn key",
+            "us_per_launch": us_cold, "us_per_launch_l2_warm": us_warm, "flops_per_launch": flops,
+            "bytes_per_launch": bytes_,
+            "tensor": {"achieved": flops / us_cold / 1e6, "peak": tpk, "unit": "TFLOP/s", "frac": flops / us_cold / 1e6 / tpk},
+            "hbm": {"achieved": bytes_ / us_cold / 1e3, "peak": hbm, "unit": "GB/s", "frac": bytes_ / us_cold / 1e3 / hbm},
+            "bound": "hbm",
+            "why": "arithmetic intensity 4.N.(S+1).D / (4.S.D) = N = 100 FLOP/B < ridge (~215): with K / V resident in "
+                   "HBM the core is HBM-bound; on chip it is paced by TMEM reads (64 B/clk: 1024 clk per 128x128 fp32 score "
+                   "tile) and MUFU ex2 (16/clk: 1024 clk per tile) against 512 clk of MMA per tile, so the tensor pipe "
+                   "cannot exceed ~50 % inside this kernel whatever the memory system does",
+            "peak_source": "MEASURED_PEAKS.json (burst; kernel timed alone)" if peaks else "fallback 1590 TF/s / 6650 GB/s"}
+
+
+def gpu_reference_timing(w, dev, iters=8):
+    """The reference's own PyTorch path ON THIS GPU (SURVEY.md §8d "reference PyTorch GPU path to beat"): the oracle
+    restatement (== the reference modules to 1e-5, tests/test_oracle_vs_reference.py) run eagerly under
+    torch.autocast(bf16) — what a user of the reference gets on a B200 — CUDA-event timed on the same workload."""
+    import torch
+    from oracle import restatement as O
+    from pq3d_b200 import synth
+    sd = {k: v.to(dev) for k, v in synth.decoder_state_dict(w, seed=0).items()}
+    cfg = O.DecoderCfg(**w.decoder_kwargs())
+    inp, pw, _ = synth.make_decoder_inputs(w, device=dev)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+        for _ in range(3):
+            O.query_mask_encoder(sd, cfg, synth.clone_input_dict(inp), pw)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            O.query_mask_encoder(sd, cfg, synth.clone_input_dict(inp), pw)
+        e1.record()
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    return {"what": "oracle restatement of the reference decoder, eager PyTorch under torch.autocast(bf16) on this GPU "
+                    "(cuBLAS / torch kernels; none of this repo's kernels)", "ms_per_step": ms,
+            "value": w.B * w.N / (ms * 1e-3), "unit": UNIT, "iters": iters, "n_gpus": 1}
+
+
+class PowerSampler(threading.Thread):
+    """SM clock, power draw and throttle reasons every 50 ms (the sustained-load record)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.mhz, self.watts, self.reasons = [], [], set()
+        self._stop_evt = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv, self.h = pynvml, pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:  # noqa: BLE001
+            self.nv, self.max_mhz = None, None
+
+    def run(self):
+        while self.nv is not None and not self._stop_evt.is_set():
+            try:
+                self.mhz.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                self.watts.append(self.nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+                mask = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for bit, name in ClockSampler.REASONS.items():
+                    if mask & bit and name != "gpu_idle":
+                        self.reasons.add(name)
+            except Exception:  # noqa: BLE001
+                return
+            time.sleep(0.05)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        med = lambda v: statistics.median(v) if v else None  # noqa: E731
+        return {"sm_mhz": med(self.mhz), "sm_mhz_min": min(self.mhz) if self.mhz else None, "sm_max_mhz": self.max_mhz,
+                "power_w_median": med(self.watts), "power_w_max": max(self.watts) if self.watts else None,
+                "reasons": sorted(self.reasons), "samples": len(self.mhz)}
+
+
+# ------------------------------------------------------------------------------------------------
 # training step (BASELINE config 5): fwd + bwd + AdamW, one flat gradient all-reduce per step for N > 1
 # ------------------------------------------------------------------------------------------------
-def run_train(args, w, enc, inp_host, pw_host, rank, world, local_rank, dev, barrier):
+def run_train(args, w, enc, inp_host, pw_host, rank, world, local_rank, dev, barrier, brief=False):
+    """Returns the JSON line of the training step (rank 0; None elsewhere).  brief=True: the sub-record attached to the
+    inference line (no e2e loop, no roofline micro-benchmark, no CPU leg)."""
     import torch
     import torch.distributed as dist
     from pq3d_b200 import ops, synth
@@ -193,7 +325,7 @@ def run_train(args, w, enc, inp_host, pw_host, rank, world, local_rank, dev, bar
     params = list(enc.parameters())
     graphed = not args.no_graph
     opt = torch.optim.AdamW(params, lr=1e-4, betas=(0.9, 0.98), fused=True, capturable=graphed)
-    reducer = FlatGradAllReduce(params) if world > 1 else None
+    reducer = FlatGradAllReduce(params, encoder=enc) if world > 1 else None
     g = torch.Generator().manual_seed(99 + rank)
     target_host = torch.randn(w.B, w.N, w.hidden_size, generator=g).pin_memory()
 
@@ -268,6 +400,39 @@ def run_train(args, w, enc, inp_host, pw_host, rank, world, local_rank, dev, bar
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_per_step = ms.item() / args.steps
     value = world * w.B * w.N / (ms_per_step * 1e-3)
+    comm = None
+    if world > 1:
+        # exposed communication = step time with the gradient all-reduce minus the same step without it (measured on the
+        # same ranks, same graph structure otherwise); bytes = what one rank contributes per step
+        comm = {"allreduce_bytes_per_step": reducer.bytes_per_step, "dtype": reducer.wire_dtype, "buckets": reducer.n_buckets,
+                "overlapped_with_backward": reducer.overlapped}
+        if True:
+            reducer.enabled = False
+            if graphed:
+                gstep2 = GraphedTrainStep(enc, opt, loss_fn, reducer)
+                step2 = lambda: gstep2(inp_dev, pw_dev, target_dev)      # noqa: E731
+            else:
+                step2 = lambda: train_step(inp_dev, pw_dev, target_dev)  # noqa: E731
+            for _ in range(5 + (4 if graphed else 0)):
+                step2()
+            barrier()
+            n0, n1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            n0.record()
+            for _ in range(args.steps):
+                step2()
+            n1.record()
+            barrier()
+            t2 = torch.tensor([n0.elapsed_time(n1)], device=dev)
+            dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+            reducer.enabled = True
+            comm["ms_per_step_without_allreduce"] = t2.item() / args.steps
+            comm["exposed_comm_ms"] = ms_per_step - comm["ms_per_step_without_allreduce"]
+    if brief:
+        if rank != 0:
+            return None
+        return {"metric": TRAIN_METRIC, "workload": workload_config(w, world)["workload"], "value": value, "unit": UNIT,
+                "ms_per_step": ms_per_step, "steps": args.steps, "n_gpus": world, "cuda_graph": graphed,
+                "dropout": enc.train_dropout, "gpu_launches": launches, "clocks": clocks, "comm": comm}
 
     # e2e: every step copies its batch from pinned host memory and reads the loss back
     h2d = (sum(t.numel() * t.element_size() for t in pinned.values()) + pw_pin.numel() * pw_pin.element_size()
@@ -291,7 +456,7 @@ def run_train(args, w, enc, inp_host, pw_host, rank, world, local_rank, dev, bar
         dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
     e2e_value = world * w.B * w.N * e2e_steps / t_e2e.item()
     if rank != 0:
-        return
+        return None
 
     # roofline of the dominant backward kernel: weight gradient of the hoisted K (or V) projection of one memory,
     # dW [L*D, D] = dK^T [L*D, B*Sp] . xk^T [D, B*Sp]^T  — pq3d_linear_bf16, contraction over all tokens
@@ -326,7 +491,7 @@ def run_train(args, w, enc, inp_host, pw_host, rank, world, local_rank, dev, bar
                 "us_per_launch": k_ms * 1e3, "flops_per_launch": flops}
     cpu = None
     if not args.no_cpu_baseline:
-        cpu = cpu_reference_run(w, steps=1000, warmup=1, budget_s=args.cpu_seconds, train=True)
+        cpu = cpu_reference_run(w, steps=1000, warmup=1, budget_s=args.cpu_seconds, train=True, sample_scenes=1)
         cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
     line = {"metric": TRAIN_METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
@@ -343,8 +508,8 @@ def run_train(args, w, enc, inp_host, pw_host, rank, world, local_rank, dev, bar
                     "steps": e2e_steps,
                     "timing": "wall clock, max over ranks; each step copies its batch from pinned host memory, runs "
                               "fwd+bwd+all-reduce+AdamW and reads the loss back"},
-            "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu}
-    emit(line)
+            "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "comm": comm}
+    return line
 
 
 # ------------------------------------------------------------------------------------------------
@@ -402,7 +567,9 @@ def main():
     inp_host, pw_host, _dd = synth.make_decoder_inputs(w, rank=rank)        # this rank's scenes
     to_dev = lambda x: x.to(dev, non_blocking=True)  # noqa: E731
     if args.train or w.name == "c5":
-        run_train(args, w, enc, inp_host, pw_host, rank, world, local_rank, dev, barrier)
+        line = run_train(args, w, enc, inp_host, pw_host, rank, world, local_rank, dev, barrier)
+        if line is not None:
+            emit(line)
         if world > 1:
             dist.destroy_process_group()
         return
@@ -557,6 +724,32 @@ def main():
     e2e_value = world * w.B * w.N * e2e_steps / t_e2e.item()
     e2e_serial = world * w.B * w.N * e2e_steps / t_serial.item()
 
+    # ---------------- sustained: the same loop for >= 3 s with clocks / power sampled (the --steps window above is a burst)
+    sustained = None
+    if not args.no_extras:
+        n_sus = max(args.steps, int(args.sustained_seconds / (ms_per_step * 1e-3)))
+        ps = PowerSampler(local_rank)
+        ps.start()
+        ms_sus, _ = timed_steps(n_streams, n_sus)
+        rec = ps.stop()
+        ms_sus_serial, _ = timed_steps(1, max(args.steps, int(1.0 / (ms_serial * 1e-3))))
+        sustained = {"value": world * w.B * w.N / (ms_sus * 1e-3), "unit": UNIT, "ms_per_step": ms_sus, "steps": n_sus,
+                     "seconds": n_sus * ms_sus * 1e-3, "streams": n_streams, "clocks": rec,
+                     "serial": {"ms_per_step": ms_sus_serial, "value": world * w.B * w.N / (ms_sus_serial * 1e-3)}}
+
+    # ---------------- training sub-record: BASELINE config 5 shard (the only path with a collective), every rank
+    train_rec = None
+    if not args.no_extras and not w.use_self_mask:
+        w5 = synth.workload("c5")
+        enc5 = QueryMaskEncoder(None, **w5.decoder_kwargs())
+        enc5.load_state_dict(synth.decoder_state_dict(w5, seed=0), strict=True)
+        enc5 = enc5.to(dev)
+        inp5, pw5, _ = synth.make_decoder_inputs(w5, rank=rank)
+        targs = argparse.Namespace(**vars(args))
+        targs.steps, targs.warmup = max(20, min(args.steps, 50)), 3
+        train_rec = run_train(targs, w5, enc5, inp5, pw5, rank, world, local_rank, dev, barrier, brief=True)
+        del enc5
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -617,9 +810,13 @@ def main():
     roofline["step_tflops"] = step_flops / (ms_per_step * 1e-3) / 1e12
     roofline["step_frac_of_sustained"] = roofline["step_tflops"] / peaks.get("bf16_tflops_sustained", 1400.0)
 
+    roofline["step_serial_tflops"] = step_flops / (ms_serial * 1e-3) / 1e12
+    roofline["step_serial_frac_of_sustained"] = roofline["step_serial_tflops"] / peaks.get("bf16_tflops_sustained", 1400.0)
+    roofline_attention = attention_roofline(w, dev, peaks)
+
     cpu = None
     if not args.no_cpu_baseline:
-        cpu = cpu_reference_run(w, steps=1000, warmup=1, budget_s=args.cpu_seconds)
+        cpu = cpu_reference_run(w, steps=1000, warmup=1, budget_s=args.cpu_seconds, sample_scenes=1)
         cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -637,7 +834,15 @@ def main():
                     "timing": "wall clock, max over ranks; every step copies its inputs from pinned host memory and reads its "
                               "result back; value = double-buffered (H2D of step i+1 overlaps forward of step i), "
                               "serial_value = strictly H2D->forward->D2H one step at a time"},
-            "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu}
+            "gpu_launches": launches, "roofline": roofline, "roofline_attention": roofline_attention,
+            "cpu_baseline": cpu, "sustained": sustained, "train": train_rec}
+    if not args.no_extras and world == 1:
+        try:
+            line["gpu_reference"] = gpu_reference_timing(w, dev)
+            line["gpu_reference"]["speedup_serial"] = line["gpu_reference"]["ms_per_step"] / ms_serial
+            line["gpu_reference"]["speedup_in_flight"] = line["gpu_reference"]["ms_per_step"] / ms_per_step
+        except Exception as e:  # noqa: BLE001
+            line["gpu_reference"] = {"error": repr(e)}
     emit(line)
     if world > 1:
         dist.destroy_process_group()

@@ -19,6 +19,8 @@ _pi32 = C.POINTER(C.c_int32)
 SIGNATURES: Dict[str, list] = {
     "pq3d_linear_bf16": [_vp, _i64, _i64, _i64, _vp, _i64, _i64, _i64, _vp, _i64, _i64, _i32, _vp, _i64, _i32,
                          _vp, _i64, _i32, _i32, _i32, _i32, _f32, _i32, _i32, _i32, _vp],
+    "pq3d_linear_bf16_ex": [_vp, _i64, _i64, _i64, _vp, _i64, _i64, _i64, _vp, _i64, _i64, _i32, _vp, _i64, _i32,
+                            _vp, _i64, _i32, _i32, _i32, _i32, _f32, _i32, _i32, _i32, _i32, _pi32, _i32, _vp],
     "pq3d_bgemm_bf16": [_vp, _i64, _i64, _i64, _vp, _i64, _i64, _i64, _vp, _i64, _i64, _i64, _i32, _i32, _i32, _i32,
                         _i32, _i32, _f32, _i32, _vp],
     "pq3d_attention_fwd": [_i32, _vp, _i64, _i64, _pp, _pi64, _pi64, _pp, _pi64, _pi64, _pi64, _pi32, _pi32, _pi32,

@@ -51,7 +51,11 @@ struct LinearParams {
   int32_t batched;          // operands / result addressed through 4-D tensor maps {inner, rows, g2, g1} (pq3d_bgemm_bf16)
   int32_t G2;               // size of the inner group level when batched (group g -> g1 = g / G2, g2 = g % G2)
   int32_t dbg_flags;        // PQ3D_GEMM_DEBUG: 1 = skip the TMA stores, 2 = skip staging + stores (WRONG RESULTS; timing only)
+  int32_t w_prefetch;       // W is constant (weights): its first ring pass may be fetched before griddepcontrol.wait
+  int32_t use_a_off;        // group g's A rows start at a_off[g] instead of g * a_group_rows (groups <= kMaxAOff)
+  int32_t a_off[8];
 };
+constexpr int kMaxAOff = 8;
 
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;  // 64 bf16 = 128 B = one swizzle atom row
@@ -77,7 +81,11 @@ struct GemmCfg {
 // both shared memories and write both tensor memories.  With one CTA per tile the shared-memory port is the
 // limit (MMA operand reads 96 B/clk + TMA fill 96 B/clk against 128 B/clk: measured 66 % of the MMA floor, and
 // multicasting W into both CTAs changed nothing); the pair halves the W traffic on both sides of that port.
-template <int BN, int CL>
+// MC = 4 (with CL = 1, opt-in): a cluster of four CTAs owns four NEIGHBOURING column tiles of one row tile.  They need
+// the same A tile, so each fetches a quarter of its rows and multicasts it into all four shared memories: per k-block a
+// CTA pulls 4 KB of A + its 8 KB of W instead of 16 + 8 KB.  A ring slot is reusable once all four CTAs consumed it
+// (multicast commit).  Correct (the kernel checks run it) but measured slower for the query-side GEMMs, see the host side.
+template <int BN, int CL, int MC = 1>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 linear_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
                    const __grid_constant__ CUtensorMap tmap_c, const LinearParams p) {
@@ -93,9 +101,16 @@ linear_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
 
   const int warp = threadIdx.x >> 5;
   const int num_kb = p.K / kBlockK;
-  const int rank = CL > 1 ? static_cast<int>(cluster_ctarank()) : 0;
-  const int first_tile = blockIdx.x / CL, tile_step = gridDim.x / CL;   // p.num_tiles counts tile PAIRS when CL = 2
-  const int tiles_per_group = ((p.num_m + CL - 1) / CL) * p.num_n;
+  static_assert(MC == 1 || CL == 1, "multicast clusters use cta_group::1");
+  constexpr int kClusterSize = CL * MC;
+  const int crank = kClusterSize > 1 ? static_cast<int>(cluster_ctarank()) : 0;
+  const int rank = CL > 1 ? crank : 0;                                  // position inside a cta_group::2 pair
+  // p.num_tiles counts the units a CLUSTER walks: tiles (CL = MC = 1), tile pairs (CL = 2) or groups of MC column tiles
+  const int first_tile = blockIdx.x / kClusterSize, tile_step = gridDim.x / kClusterSize;
+  const int n_units = p.num_n / MC;                                     // column units per row tile
+  const int tiles_per_group = ((p.num_m + CL - 1) / CL) * n_units;
+  auto m_tile_of = [&](int rem) { return (rem / n_units) * CL + rank; };
+  auto n_tile_of = [&](int rem) { return (rem % n_units) * MC + (MC > 1 ? crank : 0); };
 
   if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) {
     printf("pq3d: dynamic shared memory is not 1024-byte aligned\n");
@@ -107,7 +122,7 @@ linear_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     if (p.tma_store) tma_prefetch_desc(&tmap_c);
     for (int s = 0; s < Cfg::kStages; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], MC);      // multicast clusters: every CTA that received the slot's A rows frees it
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
@@ -119,10 +134,29 @@ linear_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     if (CL > 1) tmem_alloc_pair<Cfg::kTmemCols>(tmem_slot); else tmem_alloc<Cfg::kTmemCols>(tmem_slot);
   }
   tc_fence_before();
-  if (CL > 1) cluster_sync_all(); else __syncthreads();   // peers' barriers exist before anything signals them
+  if (kClusterSize > 1) cluster_sync_all(); else __syncthreads();   // peers' barriers exist before anything signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  pdl_sync();   // everything above overlapped the previous kernel's tail; global memory is touched only below
+  // Programmatic dependent launch: everything above overlapped the previous kernel's tail.  When the caller declares W
+  // a constant operand (weights: written before the stream's current chain of kernels began), the producer also
+  // issues the W tiles of the first ring pass BEFORE waiting on the previous kernel — only A (activations) depends on
+  // it — so the weight fetch (HBM latency + ~100 KB per CTA) hides behind the predecessor's tail as well.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  int w_prefetched = 0;
+  if (p.w_prefetch && CL == 1 && !p.batched && warp == 0 && elect_one()) {
+    const int t = first_tile;
+    if (t < p.num_tiles) {
+      const int g = t / tiles_per_group, rem = t % tiles_per_group;
+      const int w_row = g * p.w_group_rows + n_tile_of(rem) * BN;
+      const int n_pre = num_kb < Cfg::kStages ? num_kb : Cfg::kStages;
+      for (int kb = 0; kb < n_pre; ++kb) {
+        mbar_arrive_expect_tx(&full_bar[kb], Cfg::kStageBytes);      // A's bytes complete the phase later
+        tma_load_2d(smem + kb * Cfg::kStageBytes + Cfg::kABytes, &tmap_w, &full_bar[kb], kb * kBlockK, w_row);
+      }
+      w_prefetched = n_pre;
+    }
+  }
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   unsigned long long* dbg = p.dbg == nullptr ? nullptr : p.dbg + 8ull * blockIdx.x;
   if (dbg != nullptr && threadIdx.x == 0) {
     dbg[0] = global_timer_ns();
@@ -138,8 +172,8 @@ linear_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       int it = 0;
       for (int t = first_tile; t < p.num_tiles; t += tile_step) {
         const int g = t / tiles_per_group, rem = t % tiles_per_group;
-        const int a_row = g * p.a_group_rows + ((rem / p.num_n) * CL + rank) * kBlockM;
-        const int w_row = g * p.w_group_rows + (rem % p.num_n) * BN;
+        const int a_row = (p.use_a_off ? p.a_off[g] : g * p.a_group_rows) + m_tile_of(rem) * kBlockM;
+        const int w_row = g * p.w_group_rows + n_tile_of(rem) * BN;
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           const int s = it % Cfg::kStages;
           mbar_wait(&empty_bar[s], ((it / Cfg::kStages) & 1) ^ 1, 100 + s);
@@ -150,6 +184,17 @@ linear_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
             if (rank == 0) mbar_arrive_expect_tx(&full_bar[s], CL * Cfg::kStageBytes);
             tma_load_2d_pair(sa, &tmap_a, lead_bar, kb * kBlockK, a_row);
             tma_load_2d_pair(sa + Cfg::kABytes, &tmap_w, lead_bar, kb * kBlockK, w_row + rank * (BN / CL));
+          } else if (MC > 1) {
+            // this CTA's quarter of the A rows goes to every CTA of the cluster; W is private
+            constexpr uint16_t kMcMask = static_cast<uint16_t>((1u << MC) - 1);
+            if (it >= w_prefetched) {
+              mbar_arrive_expect_tx(&full_bar[s], Cfg::kStageBytes);
+              tma_load_2d(sa + Cfg::kABytes, &tmap_w, &full_bar[s], kb * kBlockK, w_row);
+            }
+            tma_load_2d_multicast(sa + crank * (Cfg::kABytes / MC), &tmap_a, &full_bar[s], kb * kBlockK,
+                                  a_row + crank * (kBlockM / MC), kMcMask);
+          } else if (it < w_prefetched) {
+            tma_load_2d(sa, &tmap_a, &full_bar[s], kb * kBlockK, a_row);      // W of this slot is already in flight
           } else {
             mbar_arrive_expect_tx(&full_bar[s], Cfg::kStageBytes);
             if (p.batched) {      // strided batches: per-group offsets live in the tensor maps' outer dimensions
@@ -193,6 +238,7 @@ linear_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
                       (kb | k) != 0 ? 1u : 0u);
           }
           if (CL > 1) tc_commit_pair(&empty_bar[s], kPairMask);   // frees the slot in BOTH CTAs
+          else if (MC > 1) tc_commit_multicast(&empty_bar[s], static_cast<uint16_t>((1u << MC) - 1));
           else tc_commit(&empty_bar[s]);
         }
         if (CL > 1) tc_commit_pair(&tfull_bar[buf], kPairMask);   // each CTA's epilogue reads its own TMEM half
@@ -211,7 +257,7 @@ linear_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     int lt = 0, bx = 0;
     for (int t = first_tile; t < p.num_tiles; t += tile_step, ++lt) {
       const int g = t / tiles_per_group, rem = t % tiles_per_group;
-      const int m0 = ((rem / p.num_n) * CL + rank) * kBlockM, n0 = (rem % p.num_n) * BN;
+      const int m0 = m_tile_of(rem) * kBlockM, n0 = n_tile_of(rem) * BN;
       const int buf = lt & 1;
       float* bias_s = s_bias + buf * BN;
       for (int c = threadIdx.x - 64; c < BN; c += 128) {
@@ -353,7 +399,7 @@ linear_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     tc_fence_before();
     if (dbg != nullptr && threadIdx.x == 64) dbg[5] = clock64();
   }
-  if (CL > 1) cluster_sync_all(); else __syncthreads();   // no CTA leaves while its peer may still signal it
+  if (kClusterSize > 1) cluster_sync_all(); else __syncthreads();   // no CTA leaves while its peer may still signal it
   if (warp == 1) {
     tc_fence_after();
     if (CL > 1) tmem_dealloc_pair<Cfg::kTmemCols>(tmem_base); else tmem_dealloc<Cfg::kTmemCols>(tmem_base);
@@ -361,20 +407,23 @@ linear_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   if (dbg != nullptr && threadIdx.x == 0) dbg[6] = clock64();
 }
 
-template <int BN, int CL>
+template <int BN, int CL, int MC = 1>
 static int launch_linear(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& tc, const LinearParams& p,
-                         cudaStream_t stream) {
+                         cudaStream_t stream, int max_ctas = 0) {
   using Cfg = GemmCfg<BN, CL>;
+  constexpr int kCluster = CL * MC;
   static bool configured = false;
   if (!configured) {
-    PQ3D_CUDA(cudaFuncSetAttribute(linear_bf16_kernel<BN, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    PQ3D_CUDA(cudaFuncSetAttribute(linear_bf16_kernel<BN, CL, MC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    Cfg::kSmemBytes));
     configured = true;
   }
-  const int max_clusters = sm_count() / CL;
-  const int grid = CL * (p.num_tiles < max_clusters ? p.num_tiles : max_clusters);
-  PQ3D_CUDA(launch_kernel_cluster(linear_bf16_kernel<BN, CL>, dim3(grid), dim3(kGemmThreads), Cfg::kSmemBytes, stream,
-                                  CL, ta, tw, tc, p));
+  int sms = sm_count();
+  if (max_ctas > 0 && max_ctas < sms) sms = max_ctas;      // leave SMs to kernels running next to this one
+  const int max_clusters = sms / kCluster > 0 ? sms / kCluster : 1;
+  const int grid = kCluster * (p.num_tiles < max_clusters ? p.num_tiles : max_clusters);
+  PQ3D_CUDA(launch_kernel_cluster(linear_bf16_kernel<BN, CL, MC>, dim3(grid), dim3(kGemmThreads), Cfg::kSmemBytes, stream,
+                                  kCluster, ta, tw, tc, p));
   return PQ3D_OK;
 }
 
@@ -390,12 +439,13 @@ extern "C" int pq3d_debug_set_timeline(void* buf) {
   return PQ3D_OK;
 }
 
-extern "C" int pq3d_linear_bf16(const void* A, int64_t lda, int64_t a_rows_total, int64_t a_group_rows,
+static int linear_impl(const void* A, int64_t lda, int64_t a_rows_total, int64_t a_group_rows,
                                 const void* W, int64_t ldw, int64_t w_rows_total, int64_t w_group_rows, void* C,
                                 int64_t ldc, int64_t c_group_stride, int out_fp32, const float* bias,
                                 int64_t bias_group_stride, int bias_along_m, const uint8_t* row_zero,
                                 int64_t row_zero_group_stride, int M, int N, int K, int groups, float alpha,
-                                int alpha_ncols, int relu, int block_n, void* stream) {
+                                int alpha_ncols, int relu, int block_n, void* stream, int max_ctas,
+                                const int32_t* a_row_offsets, int w_is_constant) {
   PQ3D_CHECK_ARG(A && W && C, "pq3d_linear_bf16: null operand");
   PQ3D_CHECK_ARG(M > 0 && N > 0 && K > 0 && groups > 0, "pq3d_linear_bf16: bad shape M=%d N=%d K=%d groups=%d", M, N,
                  K, groups);
@@ -405,9 +455,15 @@ extern "C" int pq3d_linear_bf16(const void* A, int64_t lda, int64_t a_rows_total
                  (long long)lda, (long long)ldw);
   PQ3D_CHECK_ARG((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0,
                  "pq3d_linear_bf16: A / W must be 16-byte aligned");
-  PQ3D_CHECK_ARG(a_rows_total >= (int64_t)(groups - 1) * a_group_rows + M &&
+  PQ3D_CHECK_ARG((a_row_offsets != nullptr || a_rows_total >= (int64_t)(groups - 1) * a_group_rows + M) &&
                      w_rows_total >= (int64_t)(groups - 1) * w_group_rows + N,
                  "pq3d_linear_bf16: group offsets exceed the operand extents");
+  PQ3D_CHECK_ARG(a_row_offsets == nullptr || groups <= kMaxAOff, "pq3d_linear_bf16_ex: a_row_offsets supports <= %d groups",
+                 kMaxAOff);
+  if (a_row_offsets != nullptr)
+    for (int g = 0; g < groups; ++g)
+      PQ3D_CHECK_ARG(a_row_offsets[g] >= 0 && a_rows_total >= (int64_t)a_row_offsets[g] + M,
+                     "pq3d_linear_bf16_ex: a_row_offsets[%d]=%d exceeds the operand extent", g, a_row_offsets[g]);
   if (block_n == 0) {
     // big problems: 128x256 tiles; fewer than a wave of those: narrower tiles for parallelism
     const int64_t tiles256 = (int64_t)((M + 127) / 128) * ((N + 255) / 256) * groups;
@@ -424,13 +480,26 @@ extern "C" int pq3d_linear_bf16(const void* A, int64_t lda, int64_t a_rows_total
     return e == nullptr || e[0] != '0';
   }();
   const int num_m_tiles = (M + kBlockM - 1) / kBlockM;
-  const int cl = (cluster_ok && block_n == 256 && num_m_tiles >= 2 &&
+  const int cl = (cluster_ok && a_row_offsets == nullptr && block_n == 256 && num_m_tiles >= 2 &&
                   (int64_t)num_m_tiles * ((N + 255) / 256) * groups >= 2 * sm_count()) ? 2 : 1;
+  // Opt-in (PQ3D_GEMM_MULTICAST=1): clusters of 4 neighbouring column tiles share their A tile through TMA multicast.
+  // MEASURED on B200 (round 2, M = 400 query rows, in-graph): it does NOT pay — N=768: 5.22 -> 5.44 us, N=2048 (128
+  // CTAs): 5.27 -> 6.11 us, N=2304 (144 CTAs): 5.28 -> 10.8 us (clusters of 4 leave 16 of the 148 SMs unusable, so 144
+  // CTAs need two waves).  These GEMMs are bound by a chain of latencies (launch, first TMA round trip, epilogue, store,
+  // grid completion), not by the 288 KB each SM pulls; kept for shapes where A traffic does dominate.
+  static const bool multicast_ok = [] {
+    const char* e = getenv("PQ3D_GEMM_MULTICAST");
+    return e != nullptr && e[0] == '1';
+  }();
+  constexpr int kMc = 4;
+  const int n_tiles64 = (N + 63) / 64;
+  const int mc = (multicast_ok && block_n == 64 && cl == 1 && n_tiles64 % kMc == 0 &&
+                  (int64_t)num_m_tiles * n_tiles64 * groups <= 2 * sm_count()) ? kMc : 1;
   CUtensorMap ta, tw;
   {
     uint64_t dims[2] = {(uint64_t)K, (uint64_t)a_rows_total};
     uint64_t strides[1] = {(uint64_t)lda * 2};
-    uint32_t box[2] = {(uint32_t)kBlockK, (uint32_t)kBlockM};
+    uint32_t box[2] = {(uint32_t)kBlockK, (uint32_t)(kBlockM / mc)};   // multicast: each CTA fetches a quarter of the rows
     int rc = make_tmap_bf16(&ta, A, 2, dims, strides, box);
     if (rc != PQ3D_OK) return rc;
   }
@@ -456,7 +525,7 @@ extern "C" int pq3d_linear_bf16(const void* A, int64_t lda, int64_t a_rows_total
   p.K = K;
   p.num_m = (M + kBlockM - 1) / kBlockM;
   p.num_n = (N + block_n - 1) / block_n;
-  p.num_tiles = ((p.num_m + cl - 1) / cl) * p.num_n * groups;   // tile PAIRS when cl = 2
+  p.num_tiles = ((p.num_m + cl - 1) / cl) * (p.num_n / mc) * groups;   // tile PAIRS when cl = 2, tile quads when mc = 4
   p.out_fp32 = out_fp32;
   p.bias_along_m = bias_along_m;
   p.relu = relu;
@@ -470,6 +539,9 @@ extern "C" int pq3d_linear_bf16(const void* A, int64_t lda, int64_t a_rows_total
   p.dbg_flags = dbg_flags;
   p.batched = 0;
   p.G2 = 1;
+  p.w_prefetch = (w_is_constant && pdl_enabled()) ? 1 : 0;
+  p.use_a_off = a_row_offsets != nullptr;
+  for (int g = 0; g < kMaxAOff; ++g) p.a_off[g] = (a_row_offsets != nullptr && g < groups) ? a_row_offsets[g] : 0;
   const int esz = out_fp32 ? 4 : 2;
   p.tma_store = ((reinterpret_cast<uintptr_t>(C) & 15) == 0) && ((ldc * esz) % 16 == 0) &&
                 ((c_group_stride * esz) % 16 == 0);
@@ -485,10 +557,43 @@ extern "C" int pq3d_linear_bf16(const void* A, int64_t lda, int64_t a_rows_total
   }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   switch (block_n) {
-    case 64: return launch_linear<64, 1>(ta, tw, tc, p, st);
-    case 128: return launch_linear<128, 1>(ta, tw, tc, p, st);
-    default: return cl == 2 ? launch_linear<256, 2>(ta, tw, tc, p, st) : launch_linear<256, 1>(ta, tw, tc, p, st);
+    case 64: return mc == kMc ? launch_linear<64, 1, kMc>(ta, tw, tc, p, st, max_ctas)
+                              : launch_linear<64, 1>(ta, tw, tc, p, st, max_ctas);
+    case 128: return launch_linear<128, 1>(ta, tw, tc, p, st, max_ctas);
+    default: return cl == 2 ? launch_linear<256, 2>(ta, tw, tc, p, st, max_ctas)
+                            : launch_linear<256, 1>(ta, tw, tc, p, st, max_ctas);
   }
+}
+
+extern "C" int pq3d_linear_bf16(const void* A, int64_t lda, int64_t a_rows_total, int64_t a_group_rows,
+                                const void* W, int64_t ldw, int64_t w_rows_total, int64_t w_group_rows, void* C,
+                                int64_t ldc, int64_t c_group_stride, int out_fp32, const float* bias,
+                                int64_t bias_group_stride, int bias_along_m, const uint8_t* row_zero,
+                                int64_t row_zero_group_stride, int M, int N, int K, int groups, float alpha,
+                                int alpha_ncols, int relu, int block_n, void* stream) {
+  return linear_impl(A, lda, a_rows_total, a_group_rows, W, ldw, w_rows_total, w_group_rows, C, ldc, c_group_stride,
+                     out_fp32, bias, bias_group_stride, bias_along_m, row_zero, row_zero_group_stride, M, N, K, groups,
+                     alpha, alpha_ncols, relu, block_n, stream, 0, nullptr, 0);
+}
+
+// pq3d_linear_bf16 with two scheduling / addressing extras:
+//   max_ctas       > 0: the persistent grid uses at most this many CTAs (SMs), so a long GEMM can run NEXT TO a chain of
+//                  small latency-bound kernels on another stream instead of holding every SM until it finishes
+//   a_row_offsets  host array [groups] (<= 8) or NULL: group g's A rows start at a_row_offsets[g] (instead of
+//                  g * a_group_rows) — groups that share or permute their A operand, e.g. the self-attention q / k / v
+//                  projections reading (x + pos), (x + pos), x
+//   w_is_constant  1: W holds weights that no kernel of the current dependency chain writes — its first tiles are
+//                  fetched before the programmatic-dependent-launch wait on the previous kernel (only A depends on it)
+extern "C" int pq3d_linear_bf16_ex(const void* A, int64_t lda, int64_t a_rows_total, int64_t a_group_rows,
+                                   const void* W, int64_t ldw, int64_t w_rows_total, int64_t w_group_rows, void* C,
+                                   int64_t ldc, int64_t c_group_stride, int out_fp32, const float* bias,
+                                   int64_t bias_group_stride, int bias_along_m, const uint8_t* row_zero,
+                                   int64_t row_zero_group_stride, int M, int N, int K, int groups, float alpha,
+                                   int alpha_ncols, int relu, int block_n, int max_ctas, const int32_t* a_row_offsets,
+                                   int w_is_constant, void* stream) {
+  return linear_impl(A, lda, a_rows_total, a_group_rows, W, ldw, w_rows_total, w_group_rows, C, ldc, c_group_stride,
+                     out_fp32, bias, bias_group_stride, bias_along_m, row_zero, row_zero_group_stride, M, N, K, groups,
+                     alpha, alpha_ncols, relu, block_n, stream, max_ctas, a_row_offsets, w_is_constant);
 }
 
 // Strided batched GEMM: C[g1,g2] = alpha * A[g1,g2] · W[g1,g2]ᵀ for G1 x G2 independent problems whose operands are

@@ -140,6 +140,19 @@ __device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const void* tma
       : "memory");
 }
 
+// TMA multicast: the box lands at the SAME shared-memory offset in every CTA of `cta_mask`, and each destination CTA's
+// mbarrier (same offset) receives the bytes.  Used to share one A tile between the CTAs of a cluster that own
+// neighbouring column tiles (each CTA fetches a quarter of the rows and multicasts it).
+__device__ __forceinline__ void tma_load_2d_multicast(void* smem_dst, const void* tmap, uint64_t* bar, int32_t c0,
+                                                      int32_t c1, uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster "
+      "[%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1),
+      "h"(cta_mask)
+      : "memory");
+}
+
 __device__ __forceinline__ void tma_load_4d(void* smem_dst, const void* tmap, uint64_t* bar, int32_t c0, int32_t c1,
                                             int32_t c2, int32_t c3) {
   asm volatile(
@@ -200,6 +213,16 @@ __device__ __forceinline__ void tc_fence_after() {
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
+}
+
+// cta_group::1 commit that arrives on the mbarrier at this offset in EVERY CTA of cta_mask (frees a ring slot that all
+// of them filled by multicast).
+__device__ __forceinline__ void tc_commit_multicast(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"(cta_mask)
+      : "memory");
 }
 
 // CTA-pair (cta_group::2) variants: issued by the leader CTA's MMA thread; the commit arrives on the mbarrier

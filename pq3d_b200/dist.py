@@ -70,47 +70,140 @@ def max_over_ranks(value: float, device="cpu", group=None) -> float:
 
 
 class FlatGradAllReduce:
-    """One flat buffer for all gradients -> a single all-reduce (mean) per step: on an NVSwitch box the collective is
-    latency-, not link-bound, so one ~240 MB fp32 call beats DDP's 25 MB buckets.  Per step: ONE multi-tensor copy of
-    the gradients into the flat buffer, the all-reduce, one division, and then `p.grad` is re-pointed at its view of
-    the flat buffer (no copy back; the optimizer reads the averaged gradients in place).  The first version issued
-    three small kernels per parameter (~500 launches, +1.5 ms on a 3.2 ms step at 2 GPUs).  Capturable in the training
-    step's CUDA graph.  Parameters without a gradient this step contribute zeros (the reference runs DDP with
-    find_unused_parameters=True, trainer/build.py:66).
+    """Gradient mean over the ranks for the training step — the one collective of the path (the reference: DDP through
+    accelerate, trainer/build.py:66-75, whose buckets overlap backward by construction).
 
-    PQ3D_COALESCED_ALLREDUCE=1 selects an in-place variant (every gradient all-reduced inside one ncclGroup through
-    torch's coalescing manager, no staging copy at all); it is experimental: not verified under CUDA-graph capture."""
+    Two cooperating parts:
 
-    def __init__(self, params: Sequence[torch.nn.Parameter], group=None):
+    * IN-BACKWARD BUCKETS (when constructed with `encoder=`: the decoder whose hand-composed backward,
+      pq3d_b200/train_engine.py, calls back): as soon as the backward of decoder layer i has produced that layer's
+      query-side gradients (self-attention, FFN, out-projections, LayerNorms — final once `group_bwd` of the layer
+      returns), they are packed as bf16 into one bucket and all-reduced on a COMMUNICATION STREAM while the backward of
+      layer i-1 runs; the in-projection gradients (their K / V rows are only final after the memory-side tail) go out
+      as a last bucket.  The backward joins the communication stream before it hands the (already averaged) gradients
+      to autograd.  bf16 on the wire halves the bytes (120 MB instead of 240 MB per step for the 60 M-parameter
+      decoder; the same compression torch's `bf16_compress_hook` applies to DDP buckets); the sum over ranks is
+      upcast to fp32 and divided by the world size on arrival.
+    * `__call__()` (between backward and optimizer.step): all-reduces whatever the buckets did not cover — parameters
+      outside the decoder, or everything when no encoder was given / `num_blocks > 1` / shared layers — through one
+      flat fp32 buffer, and re-points `p.grad` at its view (no copy back).
+
+    Parameters without a gradient this step contribute zeros (the reference runs DDP with
+    find_unused_parameters=True, trainer/build.py:66).  Capturable in the training step's CUDA graph
+    (pq3d_b200/training.py).  `enabled = False` skips every collective (single-rank timing of the same step)."""
+
+    def __init__(self, params: Sequence[torch.nn.Parameter], group=None, encoder=None, wire_dtype=torch.bfloat16):
         self.params = [p for p in params if p.requires_grad]
         self.group = group
+        self.enabled = True
+        self.wire = wire_dtype
         n = sum(p.numel() for p in self.params)
-        dev = self.params[0].device if self.params else "cpu"
+        dev = self.params[0].device if self.params else torch.device("cpu")
+        self.dev = dev
         self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
         self.views, off = [], 0
         for p in self.params:
             self.views.append(self.flat[off: off + p.numel()].view_as(p))
             off += p.numel()
-        import os
-        self.coalesced = os.environ.get("PQ3D_COALESCED_ALLREDUCE", "0") == "1"
+        self.encoder = encoder
+        self.overlapped = False
+        self._name_of = {}
+        self._reduced = set()          # ids of parameters whose gradient was averaged inside this step's backward
+        self._buckets = {}             # bucket key -> (wire buffer, [(name, offset, numel, shape)])
+        self._live = []                # (bucket key, names) launched in the current backward
+        self.comm_stream = None
+        if encoder is not None:
+            self._name_of = {n_: p for n_, p in encoder.named_parameters()}
+            ours = {id(p) for p in self.params}
+            shared = len({id(p) for p in encoder.parameters()}) != len(list(encoder.named_parameters(remove_duplicate=False)))
+            if all(id(p) in ours for p in self._name_of.values()) and getattr(encoder, "num_blocks", 1) == 1 and not shared:
+                encoder.grad_sink = self
+                self.overlapped = True
+                if dev.type == "cuda":
+                    self.comm_stream = torch.cuda.Stream(device=dev)
+        esz = torch.empty(0, dtype=self.wire).element_size() if self.overlapped else 4
+        self.bytes_per_step = n * esz
+        self.wire_dtype = str(self.wire if self.overlapped else torch.float32).replace("torch.", "")
+        self.n_buckets = (getattr(encoder, "num_layers", 0) + 1) if self.overlapped else 1
 
-    def __call__(self):
-        world = dist.get_world_size(self.group)
-        if self.coalesced and dist.get_backend(self.group) == "nccl":
-            for p in self.params:
-                if p.grad is None:
-                    p.grad = torch.zeros_like(p)
-            with dist._coalescing_manager(group=self.group, device=self.params[0].device, async_ops=False):
-                for p in self.params:
-                    dist.all_reduce(p.grad, op=dist.ReduceOp.AVG, group=self.group)
+    # ---- called by train_engine._Bwd -------------------------------------------------------------------
+    def begin_backward(self):
+        self._reduced.clear()
+        self._live.clear()
+
+    def reduce_async(self, key, grads: Dict[str, torch.Tensor], producers=()):
+        """Pack `grads` (name -> final fp32 gradient) into bucket `key` as bf16 and all-reduce it on the communication
+        stream, after everything queued so far on the `producers` streams (CUDA) has run."""
+        if not self.enabled or not grads:
             return
-        have = [(p, v) for p, v in zip(self.params, self.views) if p.grad is not None and p.grad.data_ptr() != v.data_ptr()]
-        for p, v in zip(self.params, self.views):
+        names = sorted(grads)
+        ent = self._buckets.get(key)
+        if ent is None or [e[0] for e in ent[1]] != names:
+            layout, off = [], 0
+            for n_ in names:
+                layout.append((n_, off, grads[n_].numel(), tuple(grads[n_].shape)))
+                off += grads[n_].numel()
+            ent = self._buckets[key] = (torch.empty(off, dtype=self.wire, device=self.dev), layout)
+        buf, layout = ent
+        cur = torch.cuda.current_stream(self.dev) if self.comm_stream is not None else None
+        if self.comm_stream is not None:
+            for st in tuple(producers) + (cur,):
+                if st is not None:
+                    self.comm_stream.wait_stream(st)
+        ctx = torch.cuda.stream(self.comm_stream) if self.comm_stream is not None else _null()
+        with ctx:
+            torch._foreach_copy_([buf[o:o + k].view(shp) for _, o, k, shp in layout], [grads[n_] for n_ in names])
+            dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.group)
+        self._live.append(key)
+
+    def finish_backward(self, grads: Dict[str, torch.Tensor]):
+        """Join the communication stream and replace the entries of `grads` that went out in buckets by their mean over
+        the ranks (fp32).  Called once, at the end of the backward, on the backward's main stream."""
+        if not self._live:
+            return
+        if self.comm_stream is not None:
+            torch.cuda.current_stream(self.dev).wait_stream(self.comm_stream)
+        inv = 1.0 / dist.get_world_size(self.group)
+        for key in self._live:
+            buf, layout = self._buckets[key]
+            avg = buf.float().mul_(inv)
+            for n_, o, k, shp in layout:
+                grads[n_] = avg[o:o + k].view(shp)
+                p = self._name_of.get(n_)
+                if p is not None:
+                    self._reduced.add(id(p))
+        self._live.clear()
+
+    # ---- between backward and optimizer.step -------------------------------------------------------------
+    def __call__(self):
+        if not self.enabled:
+            self._reduced.clear()
+            return
+        world = dist.get_world_size(self.group)
+        rest = [(p, v) for p, v in zip(self.params, self.views) if id(p) not in self._reduced]
+        self._reduced.clear()
+        if not rest:
+            return
+        have = [(p, v) for p, v in rest if p.grad is not None and p.grad.data_ptr() != v.data_ptr()]
+        for p, v in rest:
             if p.grad is None:
                 v.zero_()
         if have:
             torch._foreach_copy_([v for _, v in have], [p.grad for p, _ in have])
-        dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
-        self.flat.div_(world)
-        for p, v in zip(self.params, self.views):
+        if len(rest) == len(self.params):
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
+            self.flat.div_(world)
+        else:                                    # a subset: reduce its views one by one (rare: parameters outside the decoder)
+            for _, v in rest:
+                dist.all_reduce(v, op=dist.ReduceOp.SUM, group=self.group)
+                v.div_(world)
+        for p, v in rest:
             p.grad = v
+
+
+class _null:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False

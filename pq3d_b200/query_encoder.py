@@ -14,6 +14,7 @@ not cover raises instead of silently falling back.
 from __future__ import annotations
 
 import math
+import os
 import weakref
 from typing import Callable, Dict, List, Optional, Sequence, Tuple
 
@@ -398,6 +399,16 @@ class QueryMaskEncoder(nn.Module):
         # speed up (it is bound by TMEM->register bandwidth, not HBM) and the narrower GEMMs cost +63 us/step, so
         # the per-layer mode is off unless the hoisted buffers would exceed this many bytes.
         self.kv_hoist_bytes = 8 << 30
+        # K / V^T of layer i+1 are query independent: project them on a SIDE stream (a fork inside the captured graph)
+        # while layer i's latency-bound query-side chain (<= 48 CTAs per kernel) runs, with the GEMM's persistent grid
+        # capped so the chain keeps SMs to run on.  One layer-sized K / V^T buffer (75 MB at config 3: L2-sized) is
+        # reused by every layer.  Off: hoisted projection of all layers up front (num_blocks > 1 always hoists).
+        # MEASURED (config 3 shard, B200, round 2): one batch at a time 0.773 -> 0.756 ms (-2 %; the background GEMM's
+        # 100 CTAs and the chain's 48-144-CTA kernels slow each other down: out-projection 7 -> 24 us), but with four
+        # batches in flight 0.503 -> 0.531 ms (+5 %: the narrower per-layer GEMMs are less efficient and the streams
+        # already fill the machine).  Hence OFF by default; PQ3D_KV_OVERLAP=1 enables it for latency-bound serving.
+        self.kv_overlap = os.environ.get("PQ3D_KV_OVERLAP", "0") != "0"
+        self.kv_overlap_ctas = int(os.environ.get("PQ3D_KV_OVERLAP_CTAS", "100"))
         # training backward: fork parameter-gradient work and the per-memory attention backwards onto side streams
         self.train_streams = True
 
@@ -568,11 +579,12 @@ class QueryMaskEncoder(nn.Module):
             xk_all, xv_all = buf(f"xk_{tag}", (nf * B * Sp, D), bf16), buf(f"xv_{tag}", (nf * B * Sp, D), bf16)
             # K / V^T of all L layers for these memories: nf*B*Sp*L*D*4 bytes (302 MB at config 3); past
             # kv_hoist_bytes project layer by layer into one layer-sized buffer instead (bounds memory).
-            per_layer = self.num_blocks == 1 and nf * B * Sp * L * D * 4 > self.kv_hoist_bytes
+            overlap = bool(self.kv_overlap and self.num_blocks == 1 and L > 1 and dev.type == "cuda")
+            per_layer = self.num_blocks == 1 and (overlap or nf * B * Sp * L * D * 4 > self.kv_hoist_bytes)
             Lk = 1 if per_layer else L
             K_all, Vt_all = buf(f"K_{tag}", (nf, B * Sp, Lk * D), bf16), buf(f"Vt_{tag}", (nf, Lk * D, B * Sp), bf16)
         else:
-            fused, per_layer = [], False
+            fused, per_layer, overlap = [], False, False
         for m in active:
             feat, mask, pos = input_dict[m]
             multi = isinstance(feat, list)
@@ -616,15 +628,16 @@ class QueryMaskEncoder(nn.Module):
         # spatial score bias of all L layers, computed once per forward from the (layer independent) geometry
         sbias = buf("sbias", (L, B, H, N, ops.bias_ld(N)), torch.float32) if pk.loc_w is not None else None
 
-        def project_fused(l0, nl):
+        def project_fused(l0, nl, max_ctas=0):
             """K / V^T of layers [l0, l0+nl) for the fused memories: one grouped GEMM launch each."""
             nf, Sp = len(fused), states[fused[0]].S_pitch
             wk, bk, wv, bv = pk.fused_kv(tuple(fused))
             ops.linear(xk_all, wk[l0 * D:], K_all, M=B * Sp, N=nl * D, K=D, bias=bk[l0 * D:], bias_group_stride=L * D,
-                       groups=nf, a_group_rows=B * Sp, w_group_rows=L * D, ldc=nl * D, c_group_stride=B * Sp * nl * D)
+                       groups=nf, a_group_rows=B * Sp, w_group_rows=L * D, ldc=nl * D, c_group_stride=B * Sp * nl * D,
+                       max_ctas=max_ctas)
             ops.linear(wv[l0 * D:], xv_all, Vt_all, M=nl * D, N=B * Sp, K=D, bias=bv[l0 * D:], bias_along_m=True,
                        bias_group_stride=L * D, groups=nf, a_group_rows=L * D, w_group_rows=B * Sp, ldc=B * Sp,
-                       c_group_stride=nl * D * B * Sp)
+                       c_group_stride=nl * D * B * Sp, max_ctas=max_ctas)
 
         def project_memories():
             """Hoisted K / V^T projections of every memory for all L layers (query independent)."""
@@ -649,10 +662,33 @@ class QueryMaskEncoder(nn.Module):
             if sbias is not None:
                 ops.spatial_bias(pw, pk.loc_w, pk.loc_b, sbias)
 
-        def run_layer(i):
-            if per_layer:
+        side = None
+        if overlap:
+            side = ws.get("kv_side")
+            if side is None:
+                side = ws["kv_side"] = torch.cuda.Stream(device=dev)
+
+        def kv_ready(i):
+            """Called right before layer i's first attention over the fused memories."""
+            if not per_layer:
+                return
+            if not overlap:
                 project_fused(i, 1)
-            self._layer(i, pk, program, states, ws, dev, B, N, D, H, q32, qpos, xq, xv_q, qbits, sbias)
+            elif i == 0:
+                project_fused(0, 1)
+            else:
+                torch.cuda.current_stream(dev).wait_stream(side)          # join: K / V^T of layer i are complete
+
+        def kv_done(i):
+            """Called right after layer i's last attention over the fused memories: their buffer is free again."""
+            if overlap and i + 1 < L:
+                side.wait_stream(torch.cuda.current_stream(dev))          # fork
+                with torch.cuda.stream(side):
+                    project_fused(i + 1, 1, max_ctas=self.kv_overlap_ctas)
+
+        def run_layer(i):
+            self._layer(i, pk, program, states, ws, dev, B, N, D, H, q32, qpos, xq, xv_q, qbits, sbias,
+                        fused=fused, kv_ready=kv_ready, kv_done=kv_done)
             if self.layer_taps is not None:
                 self.layer_taps.append(q32.view(B, N, D).clone())
 
@@ -807,34 +843,48 @@ class QueryMaskEncoder(nn.Module):
         else:
             raise ValueError(f"memory '{st.name}': mask must be 2-D or 3-D")
 
-    def _cross_group(self, grp, i, pk, states, ws, dev, B, N, D, H, x_in, tag):
+    def _cross_group(self, grp, i, pk, states, ws, dev, B, N, D, H, x_in, tag, after_attention=None):
         """Q projection for the group's memories, one attention launch, grouped out-projection.
         Returns y [g, R, D] fp32 (pre-residual updates)."""
         R, g = B * N, len(grp)
         w = pk.layers[i]["groups"][grp]
         Q = self._buf(ws, f"Q_{tag}", (R, g * D), bf16, dev)
-        ops.linear(x_in, w["wq"], Q, M=R, N=g * D, K=D, bias=w["bq"], alpha=ops.Q_SCALE, alpha_ncols=g * D)
+        ops.linear(x_in, w["wq"], Q, M=R, N=g * D, K=D, bias=w["bq"], alpha=ops.Q_SCALE, alpha_ncols=g * D, w_const=True)
         O = self._buf(ws, f"O_{tag}", (g, R, D), bf16, dev)
         mems = [ops.AttnMemory(states[m].K, 0 if states[m].per_layer else i * D, states[m].Vt,
                                0 if states[m].per_layer else i * D, states[m].S, states[m].S_pitch, states[m].bits,
                                *states[m].strides, kv_tiles=states[m].tiles) for m in grp]
         ops.attention(Q, D, mems, O, R * D, B, H, N, True)
+        if after_attention is not None:
+            after_attention()
         y = self._buf(ws, f"y_{tag}", (g, R, D), torch.float32, dev)
         ops.linear(O.view(g * R, D), w["wo"], y, M=R, N=D, K=D, bias=w["bo"], bias_group_stride=D, groups=g,
-                   a_group_rows=R, w_group_rows=D, ldc=D, c_group_stride=R * D)
+                   a_group_rows=R, w_group_rows=D, ldc=D, c_group_stride=R * D, w_const=True)
         return y, w
 
-    def _layer(self, i, pk, program, states, ws, dev, B, N, D, H, q32, qpos, xq, xv_q, qbits, sbias):
+    def _layer(self, i, pk, program, states, ws, dev, B, N, D, H, q32, qpos, xq, xv_q, qbits, sbias, fused=(),
+               kv_ready=None, kv_done=None):
         R = B * N
         lw = pk.layers[i]
+        # groups that attend the fused (per-layer projected) memories: K / V^T must be ready before the first of them
+        # and their buffer is released after the last one
+        uses = [gi for gi, grp in enumerate(program) if any(m in fused for m in grp)]
+        first_use, last_use = (uses[0], uses[-1]) if uses else (-1, -1)
+
+        def cross(gi, grp, x_in, tag):
+            if gi == first_use and kv_ready is not None:
+                kv_ready(i)
+            out = self._cross_group(grp, i, pk, states, ws, dev, B, N, D, H, x_in, tag,
+                                    after_attention=(lambda: kv_done(i)) if (gi == last_use and kv_done is not None) else None)
+            return out
         if self.structure == "gate":
             grp_p, grp_s = program
-            y, w = self._cross_group(grp_p, i, pk, states, ws, dev, B, N, D, H, xq, "p")
+            y, w = cross(0, grp_p, xq, "p")
             pb = self._buf(ws, "gate_p16", (R, D), bf16, dev)
             ops.add_layernorm(y, q32, w["gamma"], w["beta"], w["eps"], R, D, G=1, out_bf16=pb)
             gl = self._buf(ws, "gate_logits", (R, D), torch.float32, dev)
-            ops.linear(pb, lw["gate"]["w"], gl, M=R, N=D, K=D, bias=lw["gate"]["b"])
-            y, w = self._cross_group(grp_s, i, pk, states, ws, dev, B, N, D, H, xq, "s")
+            ops.linear(pb, lw["gate"]["w"], gl, M=R, N=D, K=D, bias=lw["gate"]["b"], w_const=True)
+            y, w = cross(1, grp_s, xq, "s")
             upd = self._buf(ws, "gate_upd", (R, D), torch.float32, dev)
             ops.add_layernorm(y, q32, w["gamma"], w["beta"], w["eps"], R, D, G=len(grp_s), y_group_stride=R * D,
                               out_f32=upd)
@@ -845,13 +895,13 @@ class QueryMaskEncoder(nn.Module):
             for gi, grp in enumerate(program):
                 if len(grp) == 0:
                     continue
-                y, w = self._cross_group(grp, i, pk, states, ws, dev, B, N, D, H, xq, f"g{gi}")
+                y, w = cross(gi, grp, xq, f"g{gi}")
                 ops.add_layernorm(y, q32, w["gamma"], w["beta"], w["eps"], R, D, G=len(grp), y_group_stride=R * D,
                                   pos=qpos, out_f32=q32, out_bf16=xv_q, out_pos_bf16=xq)
         # ---- query self-attention (spatially biased when configured)
         sa = lw["sa"]
         QK = self._buf(ws, "sa_QK", (R, 2 * D), bf16, dev)
-        ops.linear(xq, sa["wqk"], QK, M=R, N=2 * D, K=D, bias=sa["bqk"], alpha=ops.Q_SCALE, alpha_ncols=D)
+        ops.linear(xq, sa["wqk"], QK, M=R, N=2 * D, K=D, bias=sa["bqk"], alpha=ops.Q_SCALE, alpha_ncols=D, w_const=True)
         # V^T [D, B*Np]: scene b's queries at columns b*Np .. b*Np+N (Np = N rounded up to 8 for the TMA
         # stride); one GEMM group per scene, pad columns stay at their zero initialisation
         Np = ops.pad8(N)
@@ -862,14 +912,14 @@ class QueryMaskEncoder(nn.Module):
         mem = ops.AttnMemory(QK, D, Vt, 0, N, N, qbits, qbits.stride(0), 0, 0, Vt_pitch=Np)
         ops.attention(QK, 0, [mem], Os, R * D, B, H, N, False, None if sbias is None else sbias[i])
         ys = self._buf(ws, "sa_y", (R, D), torch.float32, dev)
-        ops.linear(Os.view(R, D), sa["wo"], ys, M=R, N=D, K=D, bias=sa["bo"])
+        ops.linear(Os.view(R, D), sa["wo"], ys, M=R, N=D, K=D, bias=sa["bo"], w_const=True)
         ops.add_layernorm(ys, q32, sa["gamma"], sa["beta"], sa["eps"], R, D, out_f32=q32, out_bf16=xv_q)
         # ---- FFN
         ff = lw["ffn"]
         h = self._buf(ws, "ffn_h", (R, ff["F"]), bf16, dev)
-        ops.linear(xv_q, ff["w1"], h, M=R, N=ff["F"], K=D, bias=ff["b1"], relu=True)
+        ops.linear(xv_q, ff["w1"], h, M=R, N=ff["F"], K=D, bias=ff["b1"], relu=True, w_const=True)
         yf = self._buf(ws, "ffn_y", (R, D), torch.float32, dev)
-        ops.linear(h, ff["w2"], yf, M=R, N=D, K=ff["F"], bias=ff["b2"])
+        ops.linear(h, ff["w2"], yf, M=R, N=D, K=ff["F"], bias=ff["b2"], w_const=True)
         ops.add_layernorm(yf, q32, ff["gamma"], ff["beta"], ff["eps"], R, D, pos=qpos, out_f32=q32, out_bf16=xv_q,
                           out_pos_bf16=xq)
 

@@ -50,6 +50,11 @@ def _heads(t2d: torch.Tensor, B: int, rows: int, pitch: int, H: int, col0: int =
 _SIDE: Dict = {}
 
 
+def dist_ready() -> bool:
+    import torch.distributed as dist
+    return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+
+
 def _side_streams(dev, n):
     """Per-device pool of side streams: work off the backward's critical path (weight / bias gradients, operand
     transposes) and the independent per-memory attention backwards run next to the main chain."""
@@ -289,6 +294,7 @@ class _Bwd:
         self.Rp = ops.pad64(self.R)
         self.grads: Dict[str, torch.Tensor] = {}
         self.pending: Dict[str, List[torch.Tensor]] = {}
+        self.sent = set()              # gradients already handed to the multi-GPU bucket all-reduce
         self.dev = sv["qpos"].device
         self.keep: List = []
         self.streams_on = bool(enc.train_streams)    # False: everything on the caller's stream, in program order
@@ -659,6 +665,12 @@ class _Bwd:
         d_q = d_out.detach().reshape(R, D).float().contiguous()
         d_pos = _z((R, D), f32, dev)
         mht = sv.get("mht")
+        # multi-GPU: gradient buckets leave for the all-reduce while the backward is still running (dist.FlatGradAllReduce)
+        sink = getattr(self.enc, "grad_sink", None)
+        if sink is not None and not (sink.enabled and dist_ready()):
+            sink = None
+        if sink is not None:
+            sink.begin_backward()
         for step in reversed(range(len(sv["layers"]))):
             lay = sv["layers"][step]
             i = lay["i"]
@@ -679,6 +691,14 @@ class _Bwd:
                         self.keep += [d_q, d_mh]
                         d_q = d_sum
             self.keep.append(d_q)
+            if sink is not None:
+                # layer i's query-side gradients are final (num_blocks == 1, no shared layers: one contribution each);
+                # the in-projection rows of the K / V projections only complete in the memory-side tail below
+                pre = f"unified_encoder.{i}."
+                ready = {n: parts[0] for n, parts in self.pending.items()
+                         if n.startswith(pre) and "in_proj" not in n and len(parts) == 1 and n not in self.sent}
+                self.sent.update(ready)
+                sink.reduce_async(("layer", i), ready, producers=[self.side] + list(self.par))
         # memory side: weight / bias gradients of the hoisted K and V projections, input gradients
         d_mem = {}
         G_b = _e((L, n_mem, 3 * D), f32, dev)
@@ -748,6 +768,10 @@ class _Bwd:
             mh_out = mht.finish()
         self.join()
         self.finish_grads()
+        if sink is not None:
+            rest = {n: g for n, g in self.grads.items() if n not in self.sent}
+            sink.reduce_async(("tail",), rest)
+            sink.finish_backward(self.grads)
         self.keep.clear()
         return d_q.view(B, N, D), d_pos.view(B, N, D), d_mem, self.grads, mh_out
 

@@ -25,7 +25,7 @@ def _as(t, size, stride, extra_offset=0):
 
 def linear(A, W, out, *, M, N, K, bias=None, bias_along_m=False, bias_group_stride=0, groups=1, a_group_rows=0,
            w_group_rows=0, ldc=None, c_group_stride=0, row_zero=None, row_zero_group_stride=0, alpha=1.0, alpha_ncols=0,
-           relu=False, block_n=0):
+           relu=False, block_n=0, max_ctas=0, a_row_offsets=None, w_const=False):
     assert A.dtype == bf16 and W.dtype == bf16 and K % 64 == 0
     # the ABI's documented constraints (TMA: 16-byte aligned bases, 16-byte granular pitches >= K)
     assert A.stride(0) % 8 == 0 and W.stride(0) % 8 == 0 and A.stride(0) >= K and W.stride(0) >= K
@@ -33,12 +33,13 @@ def linear(A, W, out, *, M, N, K, bias=None, bias_along_m=False, bias_group_stri
     ldc = out.stride(-2) if ldc is None else ldc
     lda, ldw = A.stride(0), W.stride(0)
     # TMA zero-fills rows past the operand's extent
-    def rows(T, ld, group_rows, n):
+    def rows(T, ld, group_rows, n, offsets=None):
         full = torch.zeros(groups, n, K)
         for g in range(groups):
-            avail = max(0, min(n, T.shape[0] - g * group_rows))
+            r0 = g * group_rows if offsets is None else int(offsets[g])
+            avail = max(0, min(n, T.shape[0] - r0))
             if avail:
-                full[g, :avail] = _as(T, (avail, K), (ld, 1), g * group_rows * ld).float()
+                full[g, :avail] = _as(T, (avail, K), (ld, 1), r0 * ld).float()
         return full
     # TMA stores clip at the tensor map's extent in whole 16-byte chunks: when N * elem_size is not a multiple of 16 the
     # columns up to the next 16-byte boundary are written too (with the epilogue of whatever W rows lie there — zero
@@ -49,7 +50,7 @@ def linear(A, W, out, *, M, N, K, bias=None, bias_along_m=False, bias_group_stri
     N_logical = N
     if tma_path and (N * esz) % 16 != 0:
         N = min((N * esz + 15) // 16 * 16 // esz, ldc)
-    C = torch.einsum("gmk,gnk->gmn", rows(A, lda, a_group_rows, M), rows(W, ldw, w_group_rows, N))
+    C = torch.einsum("gmk,gnk->gmn", rows(A, lda, a_group_rows, M, a_row_offsets), rows(W, ldw, w_group_rows, N))
     if bias is not None:
         if bias_along_m:
             b = _as(bias, (groups, M), (bias_group_stride, 1))

@@ -182,6 +182,11 @@ def _teacher_forced(w, sd, head=None, dev=DEV):
                     if not fin.any() or torch.equal(g, m):
                         continue
                     gv, mv = g.float()[fin], m.float()[fin]
+                    if name == "spatial_bias":
+                        # log2(clamp(relu(w.loc + b), 1e-6)) is compared as the factor it contributes to the softmax,
+                        # 2^bias = clamp(relu(.), 1e-6) (transformers.py:231-232: log(clamp(loc, 1e-6)) + attn): next to
+                        # the clamp a 1e-7 difference of the argument is a finite jump of the logarithm
+                        gv, mv = torch.exp2(gv), torch.exp2(mv)
                     rec = dict(op=name, call=len(report), dtype=str(t.dtype).split(".")[1], shape=tuple(t.shape),
                                kw={k: v for k, v in kw.items() if isinstance(v, (int, float, bool))},
                                inf=((gv - mv).abs().max() / mv.abs().max().clamp_min(1e-30)).item(),
@@ -288,8 +293,8 @@ def test_free_running_c4_ragged_selfmask():
     The mask head thresholds its logits at 0 and the result gates the next layer's attention, so a logit that lies
     within the two implementations' distance of 0 may fall on either side.  (Bit-exactness 'given equal logits' is what
     the teacher-forced test asserts.)  Here every differing bit must belong to a logit within 2e-2 * max|logit| of the
-    threshold; the query stream is compared on the queries whose mask rows agreed in every earlier layer application,
-    and the count of differing bits is printed."""
+    threshold and the differing bits must stay a small fraction (< 0.5 %) of all bits; the query stream and the mask
+    logits are compared on all queries."""
     w = synth.workload("c4")
     sd = synth.decoder_state_dict(w, seed=0, sharp=1.0)
     sd_mh = synth.draw_state_dict(synth.mask_head_param_shapes(3), 100)
@@ -297,28 +302,22 @@ def test_free_running_c4_ragged_selfmask():
     taps_g, og, pmg = g
     taps_c, oc, pmc = c
     assert len(pmg) == len(pmc) == len(taps_g)
-    B, N = og.shape[:2]
-    clean = torch.ones(B, N, dtype=torch.bool)           # queries whose masks agreed in every call so far
-    total_flips = 0
-    worst = 0.0
+    worst_inf = worst_l2 = 0.0
+    total_flips = total_bits = 0
     for k, (lg, lc) in enumerate(zip(pmg, pmc)):         # call k produced the mask layer k attends with
         lg, lc = lg.float().cpu(), lc.float().cpu()      # (B, S, N)
         valid = lc > -1e5
         scale = lc[valid].abs().max()
-        bits_g, bits_c = lg < 0, lc < 0
-        diff = (bits_g != bits_c) & valid
+        diff = ((lg < 0) != (lc < 0)) & valid
         total_flips += int(diff.sum())
-        if diff.any():       # a bit can only differ where the two logits straddle 0, i.e. |logit| <= |logit difference|
-            assert (lc[diff].abs() <= (lg - lc).abs()[diff] + 1e-12).all()
+        total_bits += int(valid.sum())
+        if diff.any():       # a bit can only differ where the two logits straddle 0
             assert (lc[diff].abs() <= 2e-2 * scale).all(), "mask bits differ away from the decision threshold"
-        # logits of the queries still in the clean set (their inputs agreed so far), padded segments (-1e6) excluded
-        e_logit = ((lg - lc).abs().masked_fill(~valid, 0.0) * clean[:, None, :].float()).max().item() / scale.item()
-        clean &= ~diff.any(dim=1)                        # (B, N): a query with a flipped bit leaves the clean set
-        a, b = taps_g[k].float().cpu(), taps_c[k].float().cpu()
-        e_layer = ((a - b).abs() * clean[..., None].float()).max().item() / b.abs().max().item()
-        worst = max(worst, e_layer, e_logit)
-        print(f"c4 call {k}: mask bits differing {int(diff.sum())} / {int(valid.sum())} (all within 1e-3*max|logit| of 0); "
-              f"mask logits {e_logit:.2e}; query stream on {int(clean.sum())}/{B * N} unaffected queries {e_layer:.2e}")
-    print(f"c4: {total_flips} mask bits differ in total; worst error on unaffected queries {worst:.2e}")
-    assert clean.float().mean() >= 0.5, "too many queries touched by threshold flips for the comparison to mean anything"
-    assert worst <= 2e-2, f"c4: {worst:.3e}"
+        e_logit = ((lg - lc).abs().masked_fill(~valid, 0.0)).max().item() / scale.item()
+        e_inf, e_l2 = rel(taps_g[k], taps_c[k]), rel2(taps_g[k], taps_c[k])
+        worst_inf, worst_l2 = max(worst_inf, e_inf), max(worst_l2, e_l2)
+        print(f"c4 call {k}: mask bits differing {int(diff.sum())} / {int(valid.sum())}; mask logits {e_logit:.2e}; "
+              f"query stream after the layer: max-norm {e_inf:.2e}, relative L2 {e_l2:.2e}")
+    print(f"c4: {total_flips} of {total_bits} mask bits differ; worst query-stream max-norm {worst_inf:.2e}, L2 {worst_l2:.2e}")
+    assert total_flips <= 5e-3 * total_bits
+    assert worst_inf <= 5e-2 and worst_l2 <= 2e-2

@@ -37,7 +37,8 @@ for (N, K, bn, f32) in ((768, 768, 64, True), (768, 768, 128, True), (2304, 768,
     C = torch.empty(R, N, dtype=torch.float32 if f32 else torch.bfloat16, device=dev)
     A = x[:, :K]
     us = graph_time(lambda: ops.linear(A, W, C, M=R, N=N, K=K, bias=b, block_n=bn))
-    print(f"linear M=400 N={N} K={K} bn={bn} {'f32' if f32 else 'bf16'}: {us:.2f} us/launch in-graph")
+    us2 = graph_time(lambda: ops.linear(A, W, C, M=R, N=N, K=K, bias=b, block_n=bn, w_const=True))
+    print(f"linear M=400 N={N} K={K} bn={bn} {'f32' if f32 else 'bf16'}: {us:.2f} us/launch in-graph; W prefetched before the PDL wait: {us2:.2f}")
 W = (torch.randn(3 * 768, 768, device=dev) * 0.02).bfloat16()
 O = torch.randn(3 * R, 768, device=dev).bfloat16()
 y = torch.empty(3, R, 768, device=dev)
