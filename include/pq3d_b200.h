@@ -137,6 +137,12 @@ int pq3d_spatial_bias(const float* pairwise_locs, const float* loc_w, const floa
 int pq3d_ingest_memory(const float* feat, const float* pos, void* xk, void* xv, int B, int S, int S_pitch, int D,
                        void* stream);
 
+/* The same for n_mem (1..4) memories of identical shape that share ONE positional table (the scene memories all add
+ * fts_pos, model/query3d_unified.py:139-155): pos is read once.  feats: HOST array of device pointers; memory m's
+ * operands land at xk + m*mem_stride, xv + m*mem_stride (elements). */
+int pq3d_ingest_memories(int n_mem, const float* const* feats, const float* pos, void* xk, void* xv, int64_t mem_stride,
+                         int B, int S, int S_pitch, int D, void* stream);
+
 /* out = (1/G) * sum_g LayerNorm_g(residual + y[g]); y: fp32 [G][R,D] (group stride in elements) or NULL,
  * residual fp32 [R,D] or NULL, gamma/beta fp32 [G,D].  Optional outputs (NULL to skip): out_f32,
  * out_bf16 = bf16(out), out_pos_bf16 = bf16(out + pos).  D multiple of 128, <= 1024.

@@ -52,6 +52,7 @@ SIGNATURES: Dict[str, list] = {
                            _i64, _vp, _i64, _vp, _vp, _vp, _vp, _i64, _i32, _vp, _i64, _i32, _vp, _i64, _i32, _vp, _i64,
                            _i32, _i32, _i32, _f32, _f32, _vp, C.c_uint32, _vp],
     "pq3d_ingest_memory": [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp],
+    "pq3d_ingest_memories": [_i32, _pp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _vp],
     "pq3d_add_layernorm": [_vp, _i64, _vp, _vp, _vp, _i32, _f32, _i32, _i32, _vp, _vp, _vp, _vp, _vp],
     "pq3d_pack_mask": [_vp, _vp, _i64, _i32, _i32, _vp, _vp, _i64, _vp],
     "pq3d_mask_head_finalize": [_vp, _vp, _i32, _vp, _vp, _vp, _i32, _i32, _i32, _vp],

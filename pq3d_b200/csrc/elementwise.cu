@@ -43,6 +43,56 @@ __global__ void ingest_kernel(const float* __restrict__ feat, const float* __res
   }
 }
 
+// Several memories that share ONE positional table (the scene memories: mv / pc / voxel all add fts_pos,
+// model/query3d_unified.py:139-155): pos is read once per element instead of once per memory — per (token, feature)
+// 4*(n+1) bytes in instead of 8*n, 4*n bytes out.  Memory m's operands live at xk + m*mem_stride, xv + m*mem_stride.
+struct IngestMany {
+  const float* feat[4];
+  int32_t n;
+};
+__global__ void ingest_many_kernel(IngestMany in, const float* __restrict__ pos, __nv_bfloat16* __restrict__ xk,
+                                   __nv_bfloat16* __restrict__ xv, int64_t mem_stride, int B, int S, int S_pitch, int D) {
+  pdl_sync();
+  const int vec_per_row = D / 8;
+  const int64_t total = static_cast<int64_t>(B) * S_pitch * vec_per_row;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int v = static_cast<int>(i % vec_per_row);
+    const int64_t row = i / vec_per_row;
+    const int s = static_cast<int>(row % S_pitch);
+    const int b = static_cast<int>(row / S_pitch);
+    const int64_t dst = row * D + v * 8;
+    if (s >= S) {
+      for (int m = 0; m < in.n; ++m) {
+        *reinterpret_cast<uint4*>(xv + m * mem_stride + dst) = make_uint4(0, 0, 0, 0);
+        *reinterpret_cast<uint4*>(xk + m * mem_stride + dst) = make_uint4(0, 0, 0, 0);
+      }
+      continue;
+    }
+    const int64_t src = (static_cast<int64_t>(b) * S + s) * D + v * 8;
+    const float4 p0 = __ldg(reinterpret_cast<const float4*>(pos + src));
+    const float4 p1 = __ldg(reinterpret_cast<const float4*>(pos + src) + 1);
+    float4 f0[4], f1[4];
+#pragma unroll
+    for (int m = 0; m < 4; ++m)
+      if (m < in.n) {                                   // every load in flight before the first use
+        f0[m] = __ldg(reinterpret_cast<const float4*>(in.feat[m] + src));
+        f1[m] = __ldg(reinterpret_cast<const float4*>(in.feat[m] + src) + 1);
+      }
+#pragma unroll
+    for (int m = 0; m < 4; ++m)
+      if (m < in.n) {
+        uint4 ov, ok;
+        ov.x = pack_bf16x2(f0[m].x, f0[m].y); ov.y = pack_bf16x2(f0[m].z, f0[m].w);
+        ov.z = pack_bf16x2(f1[m].x, f1[m].y); ov.w = pack_bf16x2(f1[m].z, f1[m].w);
+        ok.x = pack_bf16x2(f0[m].x + p0.x, f0[m].y + p0.y); ok.y = pack_bf16x2(f0[m].z + p0.z, f0[m].w + p0.w);
+        ok.z = pack_bf16x2(f1[m].x + p1.x, f1[m].y + p1.y); ok.w = pack_bf16x2(f1[m].z + p1.z, f1[m].w + p1.w);
+        *reinterpret_cast<uint4*>(xv + m * mem_stride + dst) = ov;
+        *reinterpret_cast<uint4*>(xk + m * mem_stride + dst) = ok;
+      }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // add_layernorm: out = (1/G) * sum_g LN_g(residual + y_g)   (post-norm residual blocks,
 // query_encoder.py:304-305,449-450,386-387; the mean over memories is parallel_ca's eval branch,
@@ -338,6 +388,29 @@ extern "C" int pq3d_ingest_memory(const float* feat, const float* pos, void* xk,
   PQ3D_CUDA(launch_kernel(ingest_kernel, dim3(grid_for(total, 256)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream),
                           feat, pos, reinterpret_cast<__nv_bfloat16*>(xk), reinterpret_cast<__nv_bfloat16*>(xv), B, S,
                           S_pitch, D));
+  return PQ3D_OK;
+}
+
+// n_mem (2..4) memories with the same (B, S, D) shape and ONE shared positional table: feats is a HOST array of device
+// pointers; memory m's operands are written at xk + m*mem_stride, xv + m*mem_stride (elements).
+extern "C" int pq3d_ingest_memories(int n_mem, const float* const* feats, const float* pos, void* xk, void* xv,
+                                    int64_t mem_stride, int B, int S, int S_pitch, int D, void* stream) {
+  PQ3D_CHECK_ARG(feats && pos && xk && xv && n_mem >= 1 && n_mem <= 4, "pq3d_ingest_memories: bad argument (n_mem=%d)", n_mem);
+  PQ3D_CHECK_ARG(B > 0 && S > 0 && S_pitch >= S && D % 8 == 0 && mem_stride % 8 == 0,
+                 "pq3d_ingest_memories: bad shape B=%d S=%d pitch=%d D=%d", B, S, S_pitch, D);
+  IngestMany in;
+  in.n = n_mem;
+  for (int m = 0; m < 4; ++m) {
+    in.feat[m] = m < n_mem ? feats[m] : nullptr;
+    PQ3D_CHECK_ARG(m >= n_mem || (feats[m] != nullptr && (reinterpret_cast<uintptr_t>(feats[m]) & 15) == 0),
+                   "pq3d_ingest_memories: feature table %d null or not 16-byte aligned", m);
+  }
+  PQ3D_CHECK_ARG((reinterpret_cast<uintptr_t>(pos) & 15) == 0 && (reinterpret_cast<uintptr_t>(xk) & 15) == 0 &&
+                     (reinterpret_cast<uintptr_t>(xv) & 15) == 0, "pq3d_ingest_memories: pointers must be 16-byte aligned");
+  const int64_t total = static_cast<int64_t>(B) * S_pitch * (D / 8);
+  PQ3D_CUDA(launch_kernel(ingest_many_kernel, dim3(grid_for(total, 256)), dim3(256), 0,
+                          reinterpret_cast<cudaStream_t>(stream), in, pos, reinterpret_cast<__nv_bfloat16*>(xk),
+                          reinterpret_cast<__nv_bfloat16*>(xv), mem_stride, B, S, S_pitch, D));
   return PQ3D_OK;
 }
 

@@ -206,6 +206,24 @@ def ingest_memory(feat: torch.Tensor, pos: Optional[torch.Tensor], xk: Optional[
     _count()
 
 
+def ingest_memories(feats: Sequence[torch.Tensor], pos: torch.Tensor, xk: torch.Tensor, xv: torch.Tensor, mem_stride: int,
+                    S_pitch: int):
+    """Several (B, S, D) fp32 feature tables sharing one positional table -> bf16 operands at xk/xv + m*mem_stride."""
+    B, S, D = feats[0].shape
+    for f in feats:
+        _chk(f, torch.float32, "feat", 3)
+        if not f.is_contiguous() or tuple(f.shape) != (B, S, D):
+            raise ValueError("feature tables must be contiguous and equally shaped")
+    _chk(pos, torch.float32, "pos", 3)
+    if not pos.is_contiguous() or pos.shape != feats[0].shape:
+        raise ValueError("pos must be contiguous and shaped like the feature tables")
+    ptrs = (C.c_void_p * len(feats))(*[f.data_ptr() for f in feats])
+    rc = _lib.lib().pq3d_ingest_memories(len(feats), ptrs, pos.data_ptr(), xk.data_ptr(), xv.data_ptr(), mem_stride, B, S,
+                                         S_pitch, D, _stream())
+    _lib.check(rc, "pq3d_ingest_memories")
+    _count()
+
+
 def add_layernorm(y: Optional[torch.Tensor], residual: Optional[torch.Tensor], gamma: torch.Tensor,
                   beta: torch.Tensor, eps: float, R: int, D: int, G: int = 1, y_group_stride: int = 0,
                   pos: Optional[torch.Tensor] = None, out_f32: Optional[torch.Tensor] = None,

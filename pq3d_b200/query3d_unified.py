@@ -11,6 +11,7 @@ backbone, PointNet++ tokenizer, CLIP / T5 towers.
 """
 from __future__ import annotations
 
+import os
 from copy import copy
 from functools import partial
 from typing import Any, Dict, Optional
@@ -87,19 +88,26 @@ class LinearLN(nn.Sequential):
             self._key = key
         return self._w
 
-    def run16(self, x16: torch.Tensor, R: int, out32: torch.Tensor):
+    def run16(self, x16: torch.Tensor, R: int, out32: torch.Tensor, emit=None):
+        """emit = (xv16, xk16, pos32): the LayerNorm epilogue also writes the decoder's bf16 operands of this memory,
+        xv = bf16(out) and xk = bf16(out + pos) (no fp32 round trip through a separate ingest pass)."""
         w = self._weights(x16.device)
         D = w["w"].shape[0]
         y = torch.empty(R, D, dtype=torch.float32, device=x16.device)
         ops.linear(x16, w["w"], y, M=R, N=D, K=w["k"], bias=w["b"])
-        ops.add_layernorm(y, None, w["g"], w["be"], w["eps"], R, D, out_f32=out32)
+        if emit is None:
+            ops.add_layernorm(y, None, w["g"], w["be"], w["eps"], R, D, out_f32=out32)
+        else:
+            xv16, xk16, pos32 = emit
+            ops.add_layernorm(y, None, w["g"], w["be"], w["eps"], R, D, pos=pos32, out_f32=out32, out_bf16=xv16,
+                              out_pos_bf16=xk16)
         return out32
 
     def _needs_grad(self, x=None) -> bool:
         return torch.is_grad_enabled() and (any(p.requires_grad for p in self.parameters())
                                             or (x is not None and x.requires_grad))
 
-    def forward(self, x: torch.Tensor) -> torch.Tensor:
+    def forward(self, x: torch.Tensor, emit=None) -> torch.Tensor:
         if self._needs_grad(x):            # training: forward + backward composed from the kernels (train_blocks.py)
             from .train_blocks import linear_ln_train
             return linear_ln_train(x, self[0], self[1])
@@ -112,7 +120,7 @@ class LinearLN(nn.Sequential):
         x16 = torch.empty(R, w["k"], dtype=bf16, device=x.device)
         ops.cast_bf16(x2.contiguous(), x16)
         out = torch.empty(R, w["w"].shape[0], dtype=torch.float32, device=x.device)
-        return self.run16(x16, R, out).view(*lead, -1)
+        return self.run16(x16, R, out, emit=emit).view(*lead, -1)
 
 
 class CoordinateEncoder(nn.Module):
@@ -170,8 +178,8 @@ class ObjectEncoder(nn.Module):
                     m.weight.normal_(0.0, 0.02)
                     m.bias.zero_()
 
-    def forward(self, obj_feats, data_dict=None, **kwargs):
-        obj_embeds = self.input_feat_proj(obj_feats) if self.use_projection else obj_feats
+    def forward(self, obj_feats, data_dict=None, emit=None, **kwargs):
+        obj_embeds = self.input_feat_proj(obj_feats, emit=emit) if self.use_projection else obj_feats
         if self.training and hasattr(self, "dropout"):
             # the only torch op on this module's path: an elementwise Bernoulli mask on the producer side of the
             # decoder (§8f-1), drawn from torch's RNG exactly like the reference's nn.Dropout (object_encoder.py:75-76)
@@ -307,20 +315,24 @@ class Query3DUnified(nn.Module):
             query_pos = self.coord_encoder(query_locs[:, :, :3], input_range=[coord_min, coord_max])
             fts_pos = self.coord_encoder(fts_locs[:, :, :3], input_range=[coord_min, coord_max])
         input_dict["query"] = (torch.zeros_like(query_pos), mask, query_pos)
+        # §8f-1: in inference the producers' LayerNorm epilogue writes the decoder's bf16 K / V operands of the scene
+        # memories directly (xv = bf16(feat), xk = bf16(feat + fts_pos)), stacked the way the grouped K / V^T projection
+        # reads them — the decoder then skips its ingest pass over the fp32 tables
+        emit_of = self._plan_preingest(fts_pos)
         for inp in self.inputs:
             feat, mask, pos = None, None, None
             if inp == "prompt":
                 feat, mask = self.prompt_encoder(data_dict)
             elif inp == "mv":
-                feat = self.mv_encoder(obj_feats=data_dict["mv_seg_fts"])
+                feat = self.mv_encoder(obj_feats=data_dict["mv_seg_fts"], emit=emit_of.get("mv"))
                 mask = data_dict["mv_seg_pad_masks"].logical_not()
                 pos = fts_pos
             elif inp == "pc":
-                feat = self.pc_encoder(obj_feats=data_dict["pc_seg_fts"])
+                feat = self.pc_encoder(obj_feats=data_dict["pc_seg_fts"], emit=emit_of.get("pc"))
                 mask = data_dict["pc_seg_pad_masks"].logical_not()
                 pos = fts_pos
             elif inp == "voxel":
-                feat = self.voxel_encoder(data_dict["voxel_seg_fts"])
+                feat = self.voxel_encoder(data_dict["voxel_seg_fts"], emit=emit_of.get("voxel"))
                 mask = data_dict["voxel_seg_pad_masks"].logical_not()
                 pos = fts_pos
             else:
@@ -366,6 +378,32 @@ class Query3DUnified(nn.Module):
             else:
                 raise NotImplementedError(f"Unknow head type: {head}")
         return data_dict
+
+    def _plan_preingest(self, fts_pos: torch.Tensor) -> dict:
+        """{memory: (xv16, xk16, pos32)} for the scene memories whose encoder can emit the decoder's operands, or {}."""
+        enc = self.unified_encoder
+        if hasattr(enc, "preingested"):
+            enc.preingested = None
+        if (self.training or torch.is_grad_enabled() or not isinstance(enc, QueryMaskEncoder)
+                or os.environ.get("PQ3D_PREINGEST", "1") == "0"):
+            return {}
+        mems = [m for m in enc._active() if m != "prompt"]
+        B, S, D = fts_pos.shape
+        ok = (len(mems) >= 2 and S % 8 == 0 and fts_pos.dtype == torch.float32 and fts_pos.is_contiguous()
+              and all(m in self.inputs and getattr(getattr(self, m + "_encoder"), "use_projection", False) for m in mems)
+              and all(getattr(self, m + "_encoder").input_feat_proj[0].out_features == D for m in mems))
+        if not ok:
+            return {}
+        key = (B, S, D, len(mems), str(fts_pos.device))
+        if getattr(self, "_pre_key", None) != key:
+            self._pre_key = key
+            self._pre_buf = (torch.empty(len(mems) * B * S, D, dtype=bf16, device=fts_pos.device),
+                             torch.empty(len(mems) * B * S, D, dtype=bf16, device=fts_pos.device))
+        xk_all, xv_all = self._pre_buf
+        pos2 = fts_pos.view(B * S, D)
+        plan = {m: (xv_all[j * B * S:(j + 1) * B * S], xk_all[j * B * S:(j + 1) * B * S], pos2) for j, m in enumerate(mems)}
+        enc.preingested = dict(mems=tuple(mems), xk=xk_all, xv=xv_all, pos=fts_pos, S=S, B=B)
+        return plan
 
     def get_opt_params(self):
         """model/query3d_unified.py:224-238 with optim/utils.py:1-18 inlined: per-submodule groups,

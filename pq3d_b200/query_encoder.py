@@ -344,6 +344,37 @@ class _MemState:
     __slots__ = ("name", "S", "S_pitch", "multi", "per_layer", "xk", "xv", "K", "Vt", "bits", "strides", "tiles")
 
 
+class _Branch:
+    """A side stream for work that is independent of the critical chain (fork / join, capturable inside a CUDA graph):
+    the small prologue kernels next to the memories' ingest + K / V^T projections, the self-attention V^T projection
+    next to the q / k projection.  Disabled (everything in program order on the caller's stream) off-GPU."""
+
+    def __init__(self, ws: dict, dev, enabled: bool):
+        self.on = bool(enabled and dev.type == "cuda")
+        self.dev = dev
+        self.forked = False
+        if self.on:
+            self.stream = ws.get("side_stream")
+            if self.stream is None:
+                self.stream = ws["side_stream"] = torch.cuda.Stream(device=dev)
+
+    def side(self):
+        """Context: run on the side stream, after everything queued so far on the current stream (first use since the
+        last join) — later uses keep queueing behind the side stream's own work."""
+        import contextlib
+        if not self.on:
+            return contextlib.nullcontext()
+        if not self.forked:
+            self.stream.wait_stream(torch.cuda.current_stream(self.dev))
+            self.forked = True
+        return torch.cuda.stream(self.stream)
+
+    def join(self):
+        if self.on and self.forked:
+            torch.cuda.current_stream(self.dev).wait_stream(self.stream)
+            self.forked = False
+
+
 # --------------------------------------------------------------------------------------------
 # the decoder
 # --------------------------------------------------------------------------------------------
@@ -409,6 +440,10 @@ class QueryMaskEncoder(nn.Module):
         # already fill the machine).  Hence OFF by default; PQ3D_KV_OVERLAP=1 enables it for latency-bound serving.
         self.kv_overlap = os.environ.get("PQ3D_KV_OVERLAP", "0") != "0"
         self.kv_overlap_ctas = int(os.environ.get("PQ3D_KV_OVERLAP_CTAS", "100"))
+        # independent small kernels (mask packing, query copies, the prompt's projections, the spatial bias; the
+        # self-attention V^T projection) run on a side branch of the graph next to the critical chain
+        self.side_branches = os.environ.get("PQ3D_SIDE_BRANCHES", "1") != "0"
+        self.preingested = None        # set by Query3DUnified when its producers emitted the scene memories' operands
         # training backward: fork parameter-gradient work and the per-memory attention backwards onto side streams
         self.train_streams = True
 
@@ -497,10 +532,12 @@ class QueryMaskEncoder(nn.Module):
         # idle, two or three interleaved batches fill them (bench.py --streams)
         # (the captured body bakes in the mask buffers' pointers / strides and whether xk aliases xv, so mask rank and
         # the presence of a positional table are part of the key)
+        pre = getattr(self, "preingested", None)
         key = (B, N, tuple((m, tuple(input_dict[m][0][0].shape if isinstance(input_dict[m][0], list)
                                      else input_dict[m][0].shape), input_dict[m][1].ndim, input_dict[m][2] is None)
                            for m in active),
-               torch.cuda.current_stream(dev).cuda_stream if dev.type == "cuda" else 0)
+               torch.cuda.current_stream(dev).cuda_stream if dev.type == "cuda" else 0,
+               None if pre is None else pre["xk"].data_ptr())
         ws = self._ws.setdefault(key, {})
         buf = lambda name, shape, dtype: self._buf(ws, name, shape, dtype, dev)  # noqa: E731
 
@@ -576,7 +613,16 @@ class QueryMaskEncoder(nn.Module):
             nf = len(fused)
             Sp = ops.pad8(input_dict[fused[0]][0].shape[1])
             tag = "+".join(fused)
-            xk_all, xv_all = buf(f"xk_{tag}", (nf * B * Sp, D), bf16), buf(f"xv_{tag}", (nf * B * Sp, D), bf16)
+            # the model's producers may already have written these memories' bf16 operands (Query3DUnified, §8f-1)
+            pre = getattr(self, "preingested", None)
+            self.preingested = None
+            if not (pre is not None and pre["mems"] == tuple(fused) and pre["S"] == Sp and pre["B"] == B
+                    and all(input_dict[m][2] is pre["pos"] for m in fused)):
+                pre = None
+            if pre is not None:
+                xk_all, xv_all = pre["xk"], pre["xv"]
+            else:
+                xk_all, xv_all = buf(f"xk_{tag}", (nf * B * Sp, D), bf16), buf(f"xv_{tag}", (nf * B * Sp, D), bf16)
             # K / V^T of all L layers for these memories: nf*B*Sp*L*D*4 bytes (302 MB at config 3); past
             # kv_hoist_bytes project layer by layer into one layer-sized buffer instead (bounds memory).
             overlap = bool(self.kv_overlap and self.num_blocks == 1 and L > 1 and dev.type == "cuda")
@@ -584,7 +630,13 @@ class QueryMaskEncoder(nn.Module):
             Lk = 1 if per_layer else L
             K_all, Vt_all = buf(f"K_{tag}", (nf, B * Sp, Lk * D), bf16), buf(f"Vt_{tag}", (nf, Lk * D, B * Sp), bf16)
         else:
-            fused, per_layer, overlap = [], False, False
+            fused, per_layer, overlap, pre = [], False, False, None
+            self.preingested = None
+        br = _Branch(ws, dev, self.side_branches)
+        ws["_branch"] = br
+        import contextlib
+        # the fused memories usually share ONE positional table object (fts_pos): ingest them in one launch
+        fused_shared_pos = bool(fused) and len(fused) <= 4 and all(input_dict[m][2] is input_dict[fused[0]][2] for m in fused)
         for m in active:
             feat, mask, pos = input_dict[m]
             multi = isinstance(feat, list)
@@ -604,27 +656,37 @@ class QueryMaskEncoder(nn.Module):
                 st.xk = buf(f"xk_{m}", (nsrc * B * Sp, D), bf16) if pos is not None else st.xv
                 st.K = buf(f"K_{m}", (B * Sp, L * D), bf16)
                 st.Vt = buf(f"Vt_{m}", (L * D, B * Sp), bf16)
-            for i in range(nsrc):
-                fi = (feat[i] if multi else feat).contiguous()
-                sl = slice(i * B * Sp, (i + 1) * B * Sp)
-                ops.ingest_memory(fi.float() if fi.dtype != torch.float32 else fi,
-                                  None if pos is None else pos.contiguous().float(),
-                                  st.xk[sl] if pos is not None else None, st.xv[sl], Sp)
-            self._set_mask(st, mask, B, N, H, ws, dev)
+            # the big memories' ingest (and below their K / V^T projections) form the critical chain; everything else of
+            # the prologue is independent of it and goes to the side branch
+            shared = m in fused and (fused_shared_pos or pre is not None)
+            if shared and m == fused[0] and pre is None:  # one launch for all fused memories: pos is read once
+                fl = [input_dict[x][0].contiguous() for x in fused]
+                ops.ingest_memories([t if t.dtype == torch.float32 else t.float() for t in fl], pos.contiguous().float(),
+                                    xk_all, xv_all, B * Sp * D, Sp)
+            with (contextlib.nullcontext() if (m in fused or not fused) else br.side()):
+                for i in range(0 if shared else nsrc):
+                    fi = (feat[i] if multi else feat).contiguous()
+                    sl = slice(i * B * Sp, (i + 1) * B * Sp)
+                    ops.ingest_memory(fi.float() if fi.dtype != torch.float32 else fi,
+                                      None if pos is None else pos.contiguous().float(),
+                                      st.xk[sl] if pos is not None else None, st.xv[sl], Sp)
+            with br.side():
+                self._set_mask(st, mask, B, N, H, ws, dev)
             states[m] = st
         q32 = buf("q32", (R, D), torch.float32)
-        q32.copy_(query.reshape(R, D))
         qpos = buf("qpos", (R, D), torch.float32)
-        qpos.copy_(query_pos.reshape(R, D))
         xq = buf("xq", (R, D), bf16)       # bf16(query + query_pos): q/k operand
         xv_q = buf("xvq", (R, D), bf16)    # bf16(query): v operand
-        qbits = ops.pack_mask(query_masks.contiguous(), buf("qbits", (B, ops.mask_words(N)), torch.int32))
-        pw = None
-        if self.spatial_selfattn:
-            if pairwise_locs is None:
-                raise ValueError("spatial_selfattn=True needs pairwise_locs (B, N, N, 5)")
-            pw = buf("pw", (B, N, N, 5), torch.float32)
-            pw.copy_(pairwise_locs)
+        if self.spatial_selfattn and pairwise_locs is None:
+            raise ValueError("spatial_selfattn=True needs pairwise_locs (B, N, N, 5)")
+        pw = buf("pw", (B, N, N, 5), torch.float32) if self.spatial_selfattn else None
+        with br.side():
+            q32.copy_(query.reshape(R, D))
+            qpos.copy_(query_pos.reshape(R, D))
+            qbits = ops.pack_mask(query_masks.contiguous(), buf("qbits", (B, ops.mask_words(N)), torch.int32))
+            if pw is not None:
+                pw.copy_(pairwise_locs)
+        br.join()          # (the eager prologue and the captured body are separate stream segments)
         # spatial score bias of all L layers, computed once per forward from the (layer independent) geometry
         sbias = buf("sbias", (L, B, H, N, ops.bias_ld(N)), torch.float32) if pk.loc_w is not None else None
 
@@ -641,8 +703,14 @@ class QueryMaskEncoder(nn.Module):
 
         def project_memories():
             """Hoisted K / V^T projections of every memory for all L layers (query independent)."""
+            # fork first: the small projections / casts / spatial bias must not queue behind the big GEMMs
+            with (br.side() if fused else contextlib.nullcontext()):
+                project_small()
             if fused and not per_layer:
                 project_fused(0, L)
+            br.join()
+
+        def project_small():
             for m in active:
                 if m in fused:
                     continue
@@ -906,8 +974,13 @@ class QueryMaskEncoder(nn.Module):
         # stride); one GEMM group per scene, pad columns stay at their zero initialisation
         Np = ops.pad8(N)
         Vt = self._buf(ws, "sa_Vt", (D, B * Np), bf16, dev, zero=True)
-        ops.linear(sa["wv"], xv_q, Vt, M=D, N=N, K=D, bias=sa["bv"], bias_along_m=True, groups=B, a_group_rows=0,
-                   w_group_rows=N, ldc=B * Np, c_group_stride=Np)
+        br = ws.get("_branch")
+        import contextlib
+        with (br.side() if br is not None else contextlib.nullcontext()):     # independent of the q / k projection above
+            ops.linear(sa["wv"], xv_q, Vt, M=D, N=N, K=D, bias=sa["bv"], bias_along_m=True, groups=B, a_group_rows=0,
+                       w_group_rows=N, ldc=B * Np, c_group_stride=Np)
+        if br is not None:
+            br.join()
         Os = self._buf(ws, "sa_O", (1, R, D), bf16, dev)
         mem = ops.AttnMemory(QK, D, Vt, 0, N, N, qbits, qbits.stride(0), 0, 0, Vt_pitch=Np)
         ops.attention(QK, 0, [mem], Os, R * D, B, H, N, False, None if sbias is None else sbias[i])

@@ -212,6 +212,16 @@ def ingest_memory(feat, pos, xk, xv, S_pitch):
     ops._count()
 
 
+def ingest_memories(feats, pos, xk, xv, mem_stride, S_pitch):
+    B, S, D = feats[0].shape
+    for m, f in enumerate(feats):
+        for dst, src in ((xv, f), (xk, f + pos)):
+            d3 = _as(dst, (B, S_pitch, D), (S_pitch * D, D, 1), m * mem_stride)
+            d3.zero_()
+            d3[:, :S].copy_(src.to(bf16))
+    ops._count()
+
+
 def _drop_keep(seed, site, G, R, D, p):
     e = torch.arange(G * R * D).view(G, R, D)
     return rng.keep_mask(int(seed.item()) & 0xFFFFFFFF, site, e, p)
@@ -414,6 +424,7 @@ def _refresh(self):
 
 
 PATCHED = ["linear", "bgemm", "attention", "attn_delta", "attention_bwd", "spatial_bias", "spatial_bias_bwd", "ingest_memory",
+           "ingest_memories",
            "add_layernorm", "add_layernorm_train", "layernorm_bwd", "pack_mask", "cast_bf16", "transpose_cast", "colsum",
            "add3", "dropout_bf16", "gate_mix", "mask_head_finalize", "mask_head_finalize_bwd",
            "fourier_pos", "pairwise_locs", "gate_mix_bwd"]

@@ -328,3 +328,40 @@ def test_location_prompts(dim_loc):
     import contextlib
     from _train_hooks import run_prompt_loc_case
     run_prompt_loc_case(dim_loc, DEV, contextlib.nullcontext())
+
+
+def test_model_producers_emit_decoder_operands_bit_identical(monkeypatch):
+    """in inference the ObjectEncoder LayerNorm epilogue writes the decoder's bf16 K / V operands
+    (xv = bf16(feat), xk = bf16(feat + fts_pos)) and the decoder skips its ingest pass.  Same rounding points as the
+    ingest kernel, so the model output must be BIT-IDENTICAL with the path switched off, and no ingest may be launched."""
+    from pq3d_b200 import ops
+    from pq3d_b200.query3d_unified import Query3DUnified
+    w = synth.Workload("pre", 2, 40, 256, ["mv", "pc", "voxel", "prompt"], "mixed", T=8, num_layers=2)
+    cfg = synth.model_cfg_dict(w, dim_loc=3, heads=("ground",))
+    model = Query3DUnified(cfg).eval()
+    model.load_state_dict(synth.draw_state_dict(synth.model_param_shapes(cfg), 5, 1.5), strict=True)
+    model = model.to(DEV)
+    d = C.to_dev(synth.make_model_data_dict(w, cfg), DEV)
+    calls = {"n": 0}
+    real_many, real_one = ops.ingest_memories, ops.ingest_memory
+
+    def count_many(*a, **k):
+        calls["n"] += 1
+        return real_many(*a, **k)
+
+    def count_one(feat, *a, **k):
+        calls["n"] += 1 if feat.shape[1] == 256 else 0          # the scene memories (the prompt keeps its own ingest)
+        return real_one(feat, *a, **k)
+    monkeypatch.setattr(ops, "ingest_memories", count_many)
+    monkeypatch.setattr(ops, "ingest_memory", count_one)
+    outs = {}
+    for flag in ("1", "0"):
+        monkeypatch.setenv("PQ3D_PREINGEST", flag)
+        calls["n"] = 0
+        with torch.no_grad():
+            for _ in range(3):                                   # eager, captured, replayed decoder body
+                outs[flag] = model(dict(d))["ground_logits"].clone()
+        torch.cuda.synchronize()
+        assert (calls["n"] == 0) == (flag == "1"), f"PQ3D_PREINGEST={flag}: {calls['n']} scene-memory ingest launches"
+    assert torch.equal(outs["1"], outs["0"])
+    assert torch.isfinite(outs["1"][d["query_pad_masks"]]).all()
