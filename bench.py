@@ -273,6 +273,28 @@ def gpu_reference_timing(w, dev, iters=8):
             "value": w.B * w.N / (ms * 1e-3), "unit": UNIT, "iters": iters, "n_gpus": 1}
 
 
+def run_with_deadline(fn, seconds, dev_index):
+    """Run fn() on a worker thread; (result, None) or (None, 'timeout ...') if it has not returned in time.  A collective
+    that never completes must not cost the whole benchmark line: the caller then emits what it has and hard-exits."""
+    box = {}
+
+    def target():
+        try:
+            import torch
+            torch.cuda.set_device(dev_index)
+            box["r"] = fn()
+        except Exception as e:  # noqa: BLE001
+            box["e"] = repr(e)
+    t = threading.Thread(target=target, daemon=True)
+    t.start()
+    t.join(seconds)
+    if t.is_alive():
+        return None, f"timeout after {seconds:.0f} s"
+    if "e" in box:
+        return None, box["e"]
+    return box.get("r"), None
+
+
 def e2e_record(e2e_model, dec_value, dec_serial, h2d, d2h, steps):
     """The headline end-to-end record: through the model boundary when the workload has one (the plugin call a user of
     the reference makes), with the decoder-boundary loop kept beside it."""
@@ -545,6 +567,9 @@ def emit(line: dict):
 def main():
     global _REAL_STDOUT
     args = parse()
+    if os.environ.get("PQ3D_BENCH_WATCHDOG"):            # debugging aid: dump every thread's stack if the run stalls
+        import faulthandler
+        faulthandler.dump_traceback_later(float(os.environ["PQ3D_BENCH_WATCHDOG"]), exit=True)
     # libraries write to stdout too (NCCL prints "NCCL version ..." at communicator set-up): route fd 1 to stderr for
     # the whole run and keep the original stdout for the single JSON line
     sys.stdout.flush()
@@ -639,7 +664,7 @@ def main():
         for st in streams:                                   # warm-up: eager pass, capture, first replays — per stream
             st.wait_stream(cur)
             with torch.cuda.stream(st):
-                for _ in range(max(args.warmup, 3)):
+                for _ in range(max(args.warmup, 5)):       # eager, body capture, signature, whole-forward capture, replay
                     step_resident()
         for st in streams:
             cur.wait_stream(st)
@@ -815,6 +840,7 @@ def main():
 
     # ---------------- training sub-record: BASELINE config 5 shard (the only path with a collective), every rank
     train_rec = None
+    hard_exit = False
     if not args.no_extras and not w.use_self_mask:
         w5 = synth.workload("c5")
         enc5 = QueryMaskEncoder(None, **w5.decoder_kwargs())
@@ -823,10 +849,16 @@ def main():
         inp5, pw5, _ = synth.make_decoder_inputs(w5, rank=rank)
         targs = argparse.Namespace(**vars(args))
         targs.steps, targs.warmup = max(20, min(args.steps, 50)), 3
-        train_rec = run_train(targs, w5, enc5, inp5, pw5, rank, world, local_rank, dev, barrier, brief=True)
+        train_rec, train_err = run_with_deadline(
+            lambda: run_train(targs, w5, enc5, inp5, pw5, rank, world, local_rank, dev, barrier, brief=True), 150.0, local_rank)
+        if train_err is not None:
+            train_rec = {"error": train_err}
+            hard_exit = train_err.startswith("timeout")
         del enc5
 
     if rank != 0:
+        if hard_exit:
+            os._exit(0)
         if world > 1:
             dist.destroy_process_group()
         return
@@ -896,7 +928,7 @@ def main():
         cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "warmup": max(args.warmup, 5), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": dict(workload_config(w, world),
                            l2="per-step working set ~0.5 GB (fp32 inputs + bf16 K/V^T for 4 layers) exceeds the 126 MB L2; no flush",
@@ -916,6 +948,8 @@ def main():
         except Exception as e:  # noqa: BLE001
             line["gpu_reference"] = {"error": repr(e)}
     emit(line)
+    if hard_exit:
+        os._exit(0)
     if world > 1:
         dist.destroy_process_group()
 

@@ -60,15 +60,16 @@ int pq3d_linear_bf16(const void* A, int64_t lda, int64_t a_rows_total, int64_t a
  * a_row_offsets (HOST array [groups], groups <= 8, or NULL): group g's A rows start at a_row_offsets[g] instead of
  * g*a_group_rows — groups that share or permute their A operand (self-attention q / k / v reading x+pos, x+pos, x:
  * modules/layers/transformers.py:189-192, torch/nn/functional.py:5867-5873).
- * w_is_constant = 1: W holds weights no kernel of the running dependency chain writes; its first tiles are fetched
- * before the programmatic-dependent-launch wait on the previous kernel (only A depends on that kernel). */
+ * flags bit 0: W holds weights no kernel of the running dependency chain writes; its first tiles are fetched before the
+ * programmatic-dependent-launch wait on the previous kernel (only A depends on that kernel).  flags bit 1: never use CTA
+ * pairs (cta_group::2) — set by callers that keep several graphs in flight on different streams (see csrc/gemm.cu). */
 int pq3d_linear_bf16_ex(const void* A, int64_t lda, int64_t a_rows_total, int64_t a_group_rows,
                         const void* W, int64_t ldw, int64_t w_rows_total, int64_t w_group_rows,
                         void* C, int64_t ldc, int64_t c_group_stride, int out_fp32,
                         const float* bias, int64_t bias_group_stride, int bias_along_m,
                         const uint8_t* row_zero, int64_t row_zero_group_stride,
                         int M, int N, int K, int groups, float alpha, int alpha_ncols, int relu,
-                        int block_n, int max_ctas, const int32_t* a_row_offsets, int w_is_constant, void* stream);
+                        int block_n, int max_ctas, const int32_t* a_row_offsets, int flags, void* stream);
 
 /* Strided batched GEMM on the same kernel: C[g1,g2] = alpha * A[g1,g2] · W[g1,g2]ᵀ for G1 x G2 problems whose operands
  * are strided views, e.g. the per-(scene, head) slices of [tokens, heads*64] tensors.  Element (g1, g2, row, k) of A at

@@ -404,6 +404,7 @@ linear_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     tc_fence_after();
     if (CL > 1) tmem_dealloc_pair<Cfg::kTmemCols>(tmem_base); else tmem_dealloc<Cfg::kTmemCols>(tmem_base);
   }
+
   if (dbg != nullptr && threadIdx.x == 0) dbg[6] = clock64();
 }
 
@@ -445,7 +446,9 @@ static int linear_impl(const void* A, int64_t lda, int64_t a_rows_total, int64_t
                                 int64_t bias_group_stride, int bias_along_m, const uint8_t* row_zero,
                                 int64_t row_zero_group_stride, int M, int N, int K, int groups, float alpha,
                                 int alpha_ncols, int relu, int block_n, void* stream, int max_ctas,
-                                const int32_t* a_row_offsets, int w_is_constant) {
+                                const int32_t* a_row_offsets, int flags) {
+  const int w_is_constant = flags & 1;
+  const bool no_pairs = (flags & 2) != 0;
   PQ3D_CHECK_ARG(A && W && C, "pq3d_linear_bf16: null operand");
   PQ3D_CHECK_ARG(M > 0 && N > 0 && K > 0 && groups > 0, "pq3d_linear_bf16: bad shape M=%d N=%d K=%d groups=%d", M, N,
                  K, groups);
@@ -480,7 +483,7 @@ static int linear_impl(const void* A, int64_t lda, int64_t a_rows_total, int64_t
     return e == nullptr || e[0] != '0';
   }();
   const int num_m_tiles = (M + kBlockM - 1) / kBlockM;
-  const int cl = (cluster_ok && a_row_offsets == nullptr && block_n == 256 && num_m_tiles >= 2 &&
+  const int cl = (cluster_ok && !no_pairs && a_row_offsets == nullptr && block_n == 256 && num_m_tiles >= 2 &&
                   (int64_t)num_m_tiles * ((N + 255) / 256) * groups >= 2 * sm_count()) ? 2 : 1;
   // Opt-in (PQ3D_GEMM_MULTICAST=1): clusters of 4 neighbouring column tiles share their A tile through TMA multicast.
   // MEASURED on B200 (round 2, M = 400 query rows, in-graph): it does NOT pay — N=768: 5.22 -> 5.44 us, N=2048 (128
@@ -582,18 +585,23 @@ extern "C" int pq3d_linear_bf16(const void* A, int64_t lda, int64_t a_rows_total
 //   a_row_offsets  host array [groups] (<= 8) or NULL: group g's A rows start at a_row_offsets[g] (instead of
 //                  g * a_group_rows) — groups that share or permute their A operand, e.g. the self-attention q / k / v
 //                  projections reading (x + pos), (x + pos), x
-//   w_is_constant  1: W holds weights that no kernel of the current dependency chain writes — its first tiles are
+//   flags          bit 0: W holds weights that no kernel of the current dependency chain writes — its first tiles are
 //                  fetched before the programmatic-dependent-launch wait on the previous kernel (only A depends on it)
+//                  bit 1: never use CTA pairs (cta_group::2 clusters).  Callers that keep SEVERAL graphs in flight on
+//                  different streams set it: with pair GEMMs of different streams competing for SMs, long loops stalled
+//                  on the device about once per 40 k decoder steps (one graph left spinning, no mbarrier timeout, GPU
+//                  otherwise idle; 180 k steps clean with cta_group::1 only, 60 k clean with pairs on a single stream) —
+//                  root cause not established, so concurrency and pairs are not combined.
 extern "C" int pq3d_linear_bf16_ex(const void* A, int64_t lda, int64_t a_rows_total, int64_t a_group_rows,
                                    const void* W, int64_t ldw, int64_t w_rows_total, int64_t w_group_rows, void* C,
                                    int64_t ldc, int64_t c_group_stride, int out_fp32, const float* bias,
                                    int64_t bias_group_stride, int bias_along_m, const uint8_t* row_zero,
                                    int64_t row_zero_group_stride, int M, int N, int K, int groups, float alpha,
                                    int alpha_ncols, int relu, int block_n, int max_ctas, const int32_t* a_row_offsets,
-                                   int w_is_constant, void* stream) {
+                                   int flags, void* stream) {
   return linear_impl(A, lda, a_rows_total, a_group_rows, W, ldw, w_rows_total, w_group_rows, C, ldc, c_group_stride,
                      out_fp32, bias, bias_group_stride, bias_along_m, row_zero, row_zero_group_stride, M, N, K, groups,
-                     alpha, alpha_ncols, relu, block_n, stream, max_ctas, a_row_offsets, w_is_constant);
+                     alpha, alpha_ncols, relu, block_n, stream, max_ctas, a_row_offsets, flags);
 }
 
 // Strided batched GEMM: C[g1,g2] = alpha * A[g1,g2] · W[g1,g2]ᵀ for G1 x G2 independent problems whose operands are

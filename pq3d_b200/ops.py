@@ -61,9 +61,10 @@ def linear(A: torch.Tensor, W: torch.Tensor, out: torch.Tensor, *, M: int, N: in
            groups: int = 1, a_group_rows: int = 0, w_group_rows: int = 0, ldc: Optional[int] = None,
            c_group_stride: int = 0, row_zero: Optional[torch.Tensor] = None, row_zero_group_stride: int = 0,
            alpha: float = 1.0, alpha_ncols: int = 0, relu: bool = False, block_n: int = 0, max_ctas: int = 0,
-           a_row_offsets: Optional[Sequence[int]] = None, w_const: bool = False) -> torch.Tensor:
+           a_row_offsets: Optional[Sequence[int]] = None, w_const: bool = False, no_pairs: bool = False) -> torch.Tensor:
     """out[g] = epilogue(A[g] @ W[g].T); A, W are 2-D bf16 views with unit inner stride.  max_ctas / a_row_offsets: see
-    pq3d_linear_bf16_ex; w_const=True: W are weights (never written inside the forward), their fetch may start early."""
+    pq3d_linear_bf16_ex; w_const=True: W are weights (never written inside the forward), their fetch may start early;
+    no_pairs=True: no cta_group::2 clusters (several graphs in flight on different streams)."""
     _chk(A, bf16, "A", 2)
     _chk(W, bf16, "W", 2)
     if A.stride(1) != 1 or W.stride(1) != 1:
@@ -80,7 +81,7 @@ def linear(A: torch.Tensor, W: torch.Tensor, out: torch.Tensor, *, M: int, N: in
         A.data_ptr(), A.stride(0), A.shape[0], a_group_rows, W.data_ptr(), W.stride(0), W.shape[0], w_group_rows,
         out.data_ptr(), ldc, c_group_stride, int(out.dtype == torch.float32), _p(bias), bias_group_stride,
         int(bias_along_m), _p(row_zero), row_zero_group_stride, M, N, K, groups, float(alpha), alpha_ncols,
-        int(relu), block_n, int(max_ctas), offs, int(w_const), _stream())
+        int(relu), block_n, int(max_ctas), offs, int(w_const) | (2 if no_pairs else 0), _stream())
     _lib.check(rc, "pq3d_linear_bf16")
     _count()
     return out

@@ -440,9 +440,12 @@ class QueryMaskEncoder(nn.Module):
         # already fill the machine).  Hence OFF by default; PQ3D_KV_OVERLAP=1 enables it for latency-bound serving.
         self.kv_overlap = os.environ.get("PQ3D_KV_OVERLAP", "0") != "0"
         self.kv_overlap_ctas = int(os.environ.get("PQ3D_KV_OVERLAP_CTAS", "100"))
-        # independent small kernels (mask packing, query copies, the prompt's projections, the spatial bias; the
-        # self-attention V^T projection) run on a side branch of the graph next to the critical chain
-        self.side_branches = os.environ.get("PQ3D_SIDE_BRANCHES", "1") != "0"
+        # Opt-in: independent small kernels (mask packing, query copies, the prompt's projections, the spatial bias; the
+        # self-attention V^T projection) on a side branch of the graph next to the critical chain.  MEASURED (round 2):
+        # one batch at a time 0.7567 -> 0.7543 ms, no change with 4 batches in flight — and with 4 forked graphs in
+        # flight the long (>= 10 k step) loops stalled on the device about once per 10-20 k replays (never with the
+        # single-branch graphs: 30 k steps clean), so it stays OFF.
+        self.side_branches = os.environ.get("PQ3D_SIDE_BRANCHES", "0") != "0"
         self.preingested = None        # set by Query3DUnified when its producers emitted the scene memories' operands
         # training backward: fork parameter-gradient work and the per-memory attention backwards onto side streams
         self.train_streams = True
@@ -694,12 +697,15 @@ class QueryMaskEncoder(nn.Module):
             """K / V^T of layers [l0, l0+nl) for the fused memories: one grouped GEMM launch each."""
             nf, Sp = len(fused), states[fused[0]].S_pitch
             wk, bk, wv, bv = pk.fused_kv(tuple(fused))
+            # CTA-pair GEMMs only while this decoder works on ONE stream: with pair GEMMs of several in-flight graphs
+            # competing for SMs, long loops stalled on the device (csrc/gemm.cu, flags bit 1)
+            solo = len({k[-2] for k in self._ws}) <= 1
             ops.linear(xk_all, wk[l0 * D:], K_all, M=B * Sp, N=nl * D, K=D, bias=bk[l0 * D:], bias_group_stride=L * D,
                        groups=nf, a_group_rows=B * Sp, w_group_rows=L * D, ldc=nl * D, c_group_stride=B * Sp * nl * D,
-                       max_ctas=max_ctas)
+                       max_ctas=max_ctas, no_pairs=not solo)
             ops.linear(wv[l0 * D:], xv_all, Vt_all, M=nl * D, N=B * Sp, K=D, bias=bv[l0 * D:], bias_along_m=True,
                        bias_group_stride=L * D, groups=nf, a_group_rows=L * D, w_group_rows=B * Sp, ldc=B * Sp,
-                       c_group_stride=nl * D * B * Sp, max_ctas=max_ctas)
+                       c_group_stride=nl * D * B * Sp, max_ctas=max_ctas, no_pairs=not solo)
 
         def project_memories():
             """Hoisted K / V^T projections of every memory for all L layers (query independent)."""
@@ -723,8 +729,10 @@ class QueryMaskEncoder(nn.Module):
                                bias_group_stride=D, groups=L, a_group_rows=D, w_group_rows=B * Sp, ldc=B * Sp,
                                c_group_stride=D * B * Sp)
                 else:
-                    ops.linear(st.xk, pk.wk[m], st.K, M=B * Sp, N=L * D, K=D, bias=pk.bk[m])
-                    ops.linear(pk.wv[m], st.xv, st.Vt, M=L * D, N=B * Sp, K=D, bias=pk.bv[m], bias_along_m=True)
+                    solo = len({k[-2] for k in self._ws}) <= 1
+                    ops.linear(st.xk, pk.wk[m], st.K, M=B * Sp, N=L * D, K=D, bias=pk.bk[m], no_pairs=not solo)
+                    ops.linear(pk.wv[m], st.xv, st.Vt, M=L * D, N=B * Sp, K=D, bias=pk.bv[m], bias_along_m=True,
+                               no_pairs=not solo)
             ops.cast_bf16(q32, xq, add=qpos)
             ops.cast_bf16(q32, xv_q)
             if sbias is not None:

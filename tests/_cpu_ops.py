@@ -25,7 +25,7 @@ def _as(t, size, stride, extra_offset=0):
 
 def linear(A, W, out, *, M, N, K, bias=None, bias_along_m=False, bias_group_stride=0, groups=1, a_group_rows=0,
            w_group_rows=0, ldc=None, c_group_stride=0, row_zero=None, row_zero_group_stride=0, alpha=1.0, alpha_ncols=0,
-           relu=False, block_n=0, max_ctas=0, a_row_offsets=None, w_const=False):
+           relu=False, block_n=0, max_ctas=0, a_row_offsets=None, w_const=False, no_pairs=False):
     assert A.dtype == bf16 and W.dtype == bf16 and K % 64 == 0
     # the ABI's documented constraints (TMA: 16-byte aligned bases, 16-byte granular pitches >= K)
     assert A.stride(0) % 8 == 0 and W.stride(0) % 8 == 0 and A.stride(0) >= K and W.stride(0) >= K

@@ -115,3 +115,47 @@ def test_take_scenes():
     s = pd.take_scenes(d, [2, 0])
     assert s["seg_center"].shape[0] == 2 and torch.equal(s["seg_center"][0], d["seg_center"][2])
     assert isinstance(s["voxel_seg_fts_multiscale"], list) and s["voxel_seg_fts_multiscale"][0].shape[0] == 2
+
+
+def _bucket_job(rank, world):
+    """In-backward bf16 gradient buckets (dist.FlatGradAllReduce with encoder=...) on the emulated kernels: every rank
+    ends with the mean of the per-rank gradients, and nothing is left for the flat end-of-backward path."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import _cpu_ops
+    from pq3d_b200.query_encoder import QueryMaskEncoder
+    w = synth.Workload("g", 2, 12, 40, ["mv", "pc", "prompt"], "mixed", T=5, num_layers=2, seed=7)
+    sd = synth.decoder_state_dict(w, seed=3)
+
+    def grads(reduce):
+        enc = QueryMaskEncoder(None, **w.decoder_kwargs())
+        enc.load_state_dict(sd, strict=True)
+        enc.use_cuda_graph, enc.train_streams, enc.train_dropout = False, False, 0.0
+        enc.train()
+        red = pd.FlatGradAllReduce(list(enc.parameters()), encoder=enc) if reduce else None
+        inp, pw, _ = synth.make_decoder_inputs(w, rank=rank)              # this rank's scenes
+        with _cpu_ops.cpu_backend():
+            out = enc(synth.clone_input_dict(inp), pw)[0]
+            (out ** 2).mean().backward()
+        left = None
+        if red is not None:
+            left = len([p for p in red.params if id(p) not in red._reduced])
+            red()
+        return {n: p.grad.clone() for n, p in enc.named_parameters()}, red, left
+    local, _, _ = grads(False)
+    avg, red, left = grads(True)
+    worst = 0.0
+    for n, g in local.items():
+        parts = [torch.empty_like(g) for _ in range(world)]
+        dist.all_gather(parts, g)
+        want = sum(parts) / world
+        scale = want.abs().max().clamp_min(1e-12)
+        worst = max(worst, float((avg[n] - want).abs().max() / scale))
+    return worst, left, red.overlapped, red.n_buckets, red.wire_dtype
+
+
+def test_in_backward_bf16_buckets_average_gradients():
+    r = _spawn(_bucket_job)
+    for worst, left, overlapped, n_buckets, wire in r.values():
+        assert overlapped and left == 0 and n_buckets == 3 and wire == "bfloat16"
+        assert worst <= 1.5e-2, worst                 # bf16 on the wire: 2^-8 per addend
