@@ -229,6 +229,29 @@ int pq3d_matched_mask_loss_bwd(const float* pred_masks, const uint8_t* tgt_masks
                                int N, int S, int Mmax, const float* g_ce, const float* g_dice, const float* sums,
                                float* d_pred, void* stream);
 
+/* ---- §8f-4: inference post-processing of the instance predictions, per scene
+ *      (evaluator/instseg_eval.py:85-150 eval_instance_step, :272-305 get_full_res_mask / get_mask_and_scores) ---- */
+
+/* probs[q, c] = softmax(logits[q, :])[c] for c < C1 - 1 (the last, no-object class is dropped, :106). */
+int pq3d_class_probs(const float* logits, float* probs, int Q, int C1, void* stream);
+/* Exact top-K of n floats, sorted descending, ties: lower index first (torch.topk(sorted=True), :287-289).
+ * K <= min(n, 1024), n <= 2^20. */
+int pq3d_topk(const float* vals, int n, int K, float* out_val, int32_t* out_idx, void* stream);
+/* out[b] = #{i : idx[i] == b} (int32, zero-filled here): voxels per segment, points per full-resolution segment. */
+int pq3d_bincount(const int64_t* idx, int64_t n, int32_t* out, int bins, void* stream);
+/* score[k] = cls_score[k] * sum_v sig(m) [m > 0] / (sum_v [m > 0] + 1e-6) for query q_k = sel_flat[k] / C, evaluated on
+ * SEGMENT logits pred_masks [S, Q] weighted by the voxel count of each segment (masks[voxel2segment] is never built). */
+int pq3d_instseg_scores(const float* pred_masks, const int32_t* seg_count, const int32_t* sel_flat, int C, int S, int Q,
+                        int K, const float* cls_score, float* score, void* stream);
+/* q_of[k] = flat[order[k]] / C, cls_of[k] = flat[order[k]] % C (order NULL = identity). */
+int pq3d_split_index(const int32_t* flat, const int32_t* order, int K, int C, int32_t* q_of, int32_t* cls_of, void* stream);
+/* Full-resolution masks [P, K] (float 0/1: integer majority vote of the points of each full-resolution segment, equal to
+ * scatter_mean(...) > 0.5 bit for bit) and heatmaps [P, K] = sigmoid of the point's segment logit, for the K queries q_of
+ * (already in output order).  votes int32 [n_fullseg, K] scratch, points = bincount(segment_to_full). */
+int pq3d_instseg_fullres(const float* pred_masks, const int32_t* q_of, const int64_t* voxel2segment,
+                         const int64_t* voxel_to_full, const int64_t* segment_to_full, int64_t P, int S, int Q, int K,
+                         int n_fullseg, int32_t* votes, const int32_t* points, float* mask, float* heat, void* stream);
+
 /* ---- backward companions (training step: autograd of the reference's decoder, trainer/query3d_trainer.py:18-28) ---- */
 
 /* out_t[b1,b2][c][r] = bf16(scale * in[b1,b2][r][c] * (gate > 0 ? 1 : 0)) for r < R, zero for R <= r < Rp; optional

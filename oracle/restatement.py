@@ -575,3 +575,37 @@ def matched_mask_losses(pred_masks: Tensor, tgt_masks: List[Tensor], indices) ->
         denominator = s.sum(-1) + tm.sum(-1)
         loss_dices.append((1 - (numerator + 1) / (denominator + 1)).sum() / num_masks)
     return {"loss_mask": torch.mean(torch.stack(loss_masks)), "loss_dice": torch.mean(torch.stack(loss_dices))}
+
+
+# =====================================================================================================================
+# §8f-4: inference post-processing (evaluator/instseg_eval.py:85-150, 272-305), one scene, no DBSCAN
+# =====================================================================================================================
+def instseg_postprocess(pred_logits: Tensor, pred_masks: Tensor, voxel2segment: Tensor, voxel_to_full: Tensor,
+                        segment_to_full: Tensor, topk_per_scene: int = -1) -> Dict[str, Tensor]:
+    """pred_logits (Q, C+1), pred_masks (S, Q).  Follows eval_instance_step line by line: :97 softmax, :103 segment ->
+    voxel gather, :111 drop the no-object class, :121 get_mask_and_scores, :124-131 get_full_res_mask, :137-143 sort."""
+    logits = F.softmax(pred_logits, dim=-1)[..., :-1]                      # :89, :111
+    masks = pred_masks[voxel2segment]                                      # :103  (V, Q)
+    num_queries, num_classes = logits.shape
+    labels = torch.arange(num_classes).unsqueeze(0).repeat(num_queries, 1).flatten(0, 1)
+    k = num_queries if topk_per_scene == -1 else topk_per_scene
+    scores_per_query, topk_indices = logits.flatten(0, 1).topk(k, sorted=True)     # :286-289
+    labels_per_query = labels[topk_indices]
+    topk_q = torch.div(topk_indices, num_classes, rounding_mode="trunc")
+    masks = masks[:, topk_q]
+    result_pred_mask = (masks > 0).float()
+    heatmap = masks.float().sigmoid()
+    mask_scores = (heatmap * result_pred_mask).sum(0) / (result_pred_mask.sum(0) + 1e-6)
+    score = scores_per_query * mask_scores
+
+    def full_res(mask, is_heatmap):                                        # :272-281
+        mask = mask[voxel_to_full]
+        if not is_heatmap:
+            mask = scatter_mean(mask, segment_to_full, int(segment_to_full.max()) + 1)
+            mask = (mask > 0.5).float()
+            mask = mask[segment_to_full]
+        return mask
+    m_full, h_full = full_res(result_pred_mask, False), full_res(heatmap, True)
+    order = score.sort(descending=True)                                    # :137
+    return {"scores": order.values, "classes": labels_per_query[order.indices], "masks": m_full[:, order.indices],
+            "heatmap": h_full[:, order.indices], "query": topk_q[order.indices]}

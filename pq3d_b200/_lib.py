@@ -66,6 +66,12 @@ SIGNATURES: Dict[str, list] = {
     "pq3d_match_cost": [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _f32, _f32, _f32, _i64, _vp],
     "pq3d_matched_mask_loss_fwd": [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp],
     "pq3d_matched_mask_loss_bwd": [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp],
+    "pq3d_class_probs": [_vp, _vp, _i32, _i32, _vp],
+    "pq3d_topk": [_vp, _i32, _i32, _vp, _vp, _vp],
+    "pq3d_bincount": [_vp, _i64, _vp, _i32, _vp],
+    "pq3d_instseg_scores": [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp],
+    "pq3d_split_index": [_vp, _vp, _i32, _i32, _vp, _vp, _vp],
+    "pq3d_instseg_fullres": [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp],
 }
 RESTYPES = {"pq3d_segment_csr_workspace_bytes": _i64}
 

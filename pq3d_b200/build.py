@@ -16,7 +16,7 @@ CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "_C")
 LIB = os.path.join(OUT_DIR, "libpq3d_b200.so")
 SOURCES = ["host_common.cu", "gemm.cu", "attention.cu", "elementwise.cu", "backward.cu", "train_ops.cu", "attention_bwd.cu",
-           "segment_ops.cu", "match_cost.cu"]
+           "segment_ops.cu", "match_cost.cu", "postprocess.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC"]
 EXPORT_PREFIX = "pq3d_"

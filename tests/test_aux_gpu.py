@@ -163,3 +163,48 @@ def test_matched_mask_losses_forward_backward():
     print(f"d loss / d pred_masks: rel err {eg:.2e}")
     assert eg <= 1e-5
     assert torch.equal(pm.grad.cpu() != 0, pmo.grad != 0) or eg <= 1e-5
+
+
+@pytest.mark.parametrize("n,K", [(20000, 100), (1000, 1000), (37, 5), (65536, 750), (300, 300)])
+def test_topk_exact_sorted(n, K):
+    g = torch.Generator().manual_seed(n + K)
+    v = torch.rand(n, generator=g)
+    if n >= 1000:                                  # ties straddling the cut: lower index first
+        v[torch.randperm(n, generator=g)[:n // 3]] = v[7]
+    from pq3d_b200 import _lib
+    vd = v.to(DEV)
+    ov, oi = torch.empty(K, device=DEV), torch.empty(K, dtype=torch.int32, device=DEV)
+    _lib.check(_lib.lib().pq3d_topk(vd.data_ptr(), n, K, ov.data_ptr(), oi.data_ptr(), ops._stream()), "topk")
+    torch.cuda.synchronize()
+    order = sorted(range(n), key=lambda i: (-v[i].item(), i))[:K]        # descending, ties by index
+    assert oi.cpu().tolist() == order
+    assert torch.equal(ov.cpu(), v[order])
+
+
+@pytest.mark.parametrize("topk", [-1, 300])
+def test_instseg_postprocess_vs_oracle(topk):
+    """§8f-4 at realistic size: 100 queries x 200 classes, 1500 segments, 60 k voxels, 150 k full-resolution points.
+    Masks (the integer majority vote) and classes must match the oracle exactly, scores / heatmaps to fp32 rounding."""
+    from pq3d_b200.postprocess import instseg_postprocess
+    g = torch.Generator().manual_seed(3 + topk)
+    Q, C, S, V, P, SF = 100, 200, 1500, 60000, 150000, 1300
+    pred_logits = torch.randn(Q, C + 1, generator=g) * 3
+    pred_masks = torch.randn(S, Q, generator=g) * 4
+    v2s = torch.randint(0, S, (V,), generator=g)
+    v2f = torch.randint(0, V, (P,), generator=g)
+    s2f = torch.randint(0, SF, (P,), generator=g)
+    want = O.instseg_postprocess(pred_logits, pred_masks, v2s, v2f, s2f, topk)
+    got = instseg_postprocess(pred_logits.to(DEV), pred_masks.to(DEV), v2s.to(DEV), v2f.to(DEV), s2f.to(DEV), topk)
+    torch.cuda.synchronize()
+    K = Q if topk == -1 else topk
+    assert got["scores"].shape == (K,) and got["masks"].shape == (P, K)
+    assert torch.allclose(got["scores"].cpu(), want["scores"], rtol=2e-5, atol=1e-7)
+    # the order can only differ between entries whose scores agree to rounding; compare as sets of (query, class) per rank
+    same = (got["query"].cpu() == want["query"]) & (got["classes"].cpu() == want["classes"])
+    close = torch.isclose(got["scores"].cpu(), want["scores"].roll(1), rtol=1e-5) | torch.isclose(got["scores"].cpu(), want["scores"].roll(-1), rtol=1e-5)
+    assert (same | close).all()
+    cols = same.nonzero().flatten()
+    assert cols.numel() >= 0.98 * K
+    assert torch.equal(got["masks"].cpu()[:, cols], want["masks"][:, cols]), "full-resolution masks must be bit-exact"
+    assert torch.allclose(got["heatmap"].cpu()[:, cols], want["heatmap"][:, cols], rtol=1e-5, atol=1e-6)
+    assert (got["scores"][:-1] >= got["scores"][1:]).all()

@@ -81,3 +81,61 @@ def test_matched_mask_losses_match_live_reference():
     got = O.matched_mask_losses(pred_masks, [s[3] for s in scenes], indices)
     for k in ("loss_mask", "loss_dice"):
         assert torch.allclose(got[k], want[k], rtol=1e-6, atol=1e-7), k
+
+
+@needs_ref
+def test_instseg_postprocess_matches_live_reference_methods():
+    """§8f-4: the oracle against the LIVE evaluator's own methods (`get_mask_and_scores`, `get_full_res_mask`,
+    evaluator/instseg_eval.py:272-303), imported with stubs for what is absent here (torch_scatter -> the restated
+    scatter_mean; the registry / metric / dataset modules are not touched by these two methods)."""
+    import sys
+    import types
+    ref_loader.load()
+
+    def scatter_mean(src, index, dim=0, dim_size=None):
+        return O.scatter_mean(src, index, int(index.max()) + 1 if dim_size is None else dim_size)
+    stubs = {"torch_scatter": dict(scatter_mean=scatter_mean), "sklearn": {}, "sklearn.cluster": dict(DBSCAN=object),
+             "evaluator": {}, "evaluator.build": dict(EVALUATOR_REGISTRY=types.SimpleNamespace(register=lambda: (lambda c: c)),
+                                                      BaseEvaluator=object),
+             "common.metric_utils": dict(IoU=object, ConfusionMatrix=object), "common.eval_det": dict(eval_det=None),
+             "common.eval_instseg": dict(eval_instseg=None), "common.misc": dict(gather_dict=None),
+             "data.datasets.constant": dict(VALID_CLASS_IDS_200_VALIDATION=(), HEAD_CATS_SCANNET_200=(),
+                                            COMMON_CATS_SCANNET_200=(), TAIL_CATS_SCANNET_200=())}
+    saved = {k: sys.modules.get(k) for k in stubs}
+    try:
+        for name, attrs in stubs.items():
+            m = types.ModuleType(name)
+            m.__dict__.update(attrs)
+            if name in ("evaluator", "sklearn"):
+                m.__path__ = []
+            sys.modules[name] = m
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("_ref_instseg_eval", ref_loader.REF_ROOT + "/evaluator/instseg_eval.py")
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    ev = mod.InstSegEval.__new__(mod.InstSegEval)
+    g = torch.Generator().manual_seed(11)
+    Q, C, S, V, P, SF = 12, 9, 40, 300, 700, 25
+    pred_logits = torch.randn(Q, C + 1, generator=g) * 2
+    pred_masks = torch.randn(S, Q, generator=g) * 3
+    v2s, v2f, s2f = (torch.randint(0, S, (V,), generator=g), torch.randint(0, V, (P,), generator=g),
+                     torch.randint(0, SF, (P,), generator=g))
+    for topk in (-1, 20):
+        ev.config = ref_loader.to_attr({"eval": {"topk_per_scene": topk}})
+        logits = torch.softmax(pred_logits, -1)[..., :-1]
+        masks = pred_masks[v2s]
+        scores, m, classes, heat = ev.get_mask_and_scores(logits, masks)
+        m_full = ev.get_full_res_mask(m, v2f, s2f)
+        h_full = ev.get_full_res_mask(heat, v2f, s2f, is_heatmap=True)
+        order = scores.sort(descending=True)
+        got = O.instseg_postprocess(pred_logits, pred_masks, v2s, v2f, s2f, topk)
+        assert torch.allclose(got["scores"], order.values, rtol=1e-6)
+        assert torch.equal(got["classes"], classes[order.indices])
+        assert torch.equal(got["masks"], m_full[:, order.indices])
+        assert torch.allclose(got["heatmap"], h_full[:, order.indices], rtol=1e-6)
