@@ -170,7 +170,7 @@ def test_topk_exact_sorted(n, K):
     g = torch.Generator().manual_seed(n + K)
     v = torch.rand(n, generator=g)
     if n >= 1000:                                  # ties straddling the cut: lower index first
-        v[torch.randperm(n, generator=g)[:n // 3]] = v[7]
+        v[torch.randperm(n, generator=g)[:n // 3]] = v[7].item()
     from pq3d_b200 import _lib
     vd = v.to(DEV)
     ov, oi = torch.empty(K, device=DEV), torch.empty(K, dtype=torch.int32, device=DEV)

@@ -1,9 +1,6 @@
-"""timeout 120 torchrun --nproc-per-node 2 tools/check_nccl_grad_mean.py — pq3d_b200.dist.FlatGradAllReduce (the default
-flat-buffer path, or the experimental in-place coalesced one with PQ3D_COALESCED_ALLREDUCE=1) against an all_gather +
-mean, eagerly and captured in a CUDA graph.
-
-ALWAYS run under `timeout`: the first run of this script on a 2-GPU box (coalesced variant) never returned and burned the
-box's whole time limit; the script also arms its own 90 s alarm."""
+"""timeout 120 torchrun --nproc-per-node 2 tools/check_nccl_grad_mean.py — pq3d_b200.dist.FlatGradAllReduce's flat fp32
+path (no encoder given) against an all_gather + mean, eagerly and captured in a CUDA graph.  The in-backward bf16 buckets
+are checked by tools/check_nccl_buckets.py.  ALWAYS run under `timeout`; the script also arms its own 90 s alarm."""
 import signal
 
 signal.alarm(90)
