@@ -113,6 +113,13 @@ def test_grads_mixed_spatial_prompt():
     _run_case(w)
 
 
+def test_grads_config5_full_shard_size():
+    """BASELINE config 5 at its FULL per-GPU shard size: 2 scenes, N = 100 queries, S = 2048 segment tokens, all three
+    scene memories + 32-token prompt, structure mixed, L = 4 — every parameter and input gradient against fp32 autograd
+    through the oracle (same criterion as the small cases)."""
+    _run_case(synth.workload("c5"))
+
+
 def test_grads_sequential_plain_selfattn():
     w = synth.Workload("tseq", 2, 48, 200, ["pc", "voxel"], "sequential", num_layers=2, spatial_selfattn=False)
     _run_case(w)
@@ -471,3 +478,42 @@ def test_grads_gate_structure():
     """structure='gate': query = (1 - g) * query + g * parallel_ca(query), g = sigmoid(gate_proj(prompt_ca(query)))."""
     w = synth.Workload("tgate", 2, 64, 200, ["mv", "pc", "prompt"], "gate", T=12, num_layers=2)
     _run_case(w)
+
+
+def test_cross_block_gradient_accumulation_is_stream_safe(monkeypatch):
+    """num_blocks > 1 (and shared layers) accumulate several contributions into one parameter gradient; the contributions
+    are produced on different streams (main / side / per-memory).  With the side streams artificially delayed by a long
+    device-side sleep, the gradients must still equal the single-stream (program order) result bit for bit — an add
+    issued on the main stream before the side stream's producers have run would read uninitialised memory."""
+    from pq3d_b200 import train_engine
+    from pq3d_b200.query_encoder import QueryMaskEncoder
+    w = synth.Workload("tblk", 2, 64, 256, ["mv", "pc", "prompt"], "mixed", T=8, num_layers=2, num_blocks=2)
+    sd = C.to_dev(synth.decoder_state_dict(w, seed=4, sharp=1.0), DEV)
+    inp, pw, up = _inputs(w, 9)
+
+    def grads(streams, delay):
+        enc = QueryMaskEncoder(None, **w.decoder_kwargs())
+        enc.load_state_dict(sd, strict=True)
+        enc = enc.to(DEV).train()
+        enc.train_dropout, enc.train_streams = 0.0, streams
+        real = train_engine._side_streams
+
+        def delayed(dev, n):
+            pool = real(dev, n)
+            if delay:
+                for st in pool:
+                    with torch.cuda.stream(st):
+                        torch.cuda._sleep(int(4e7))          # ~20 ms: far longer than the whole backward
+            return pool
+        monkeypatch.setattr(train_engine, "_side_streams", delayed)
+        x, _ = _leafify(inp)
+        out = enc(x, pw)[0]
+        (out * up).sum().backward()
+        torch.cuda.synchronize()
+        monkeypatch.setattr(train_engine, "_side_streams", real)
+        return {k: p.grad.clone() for k, p in enc.named_parameters()}
+    ref = grads(False, False)
+    for delay in (False, True):
+        got = grads(True, delay)
+        for k in ref:
+            assert torch.equal(got[k], ref[k]), f"{k}: multi-stream gradient differs from program order (delay={delay})"
