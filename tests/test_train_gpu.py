@@ -483,7 +483,7 @@ def test_grads_gate_structure():
 def test_cross_block_gradient_accumulation_is_stream_safe(monkeypatch):
     """num_blocks > 1 (and shared layers) accumulate several contributions into one parameter gradient; the contributions
     are produced on different streams (main / side / per-memory).  With the side streams artificially delayed by a long
-    device-side sleep, the gradients must still equal the single-stream (program order) result bit for bit — an add
+    device-side sleep, the gradients must still equal the single-stream (program order) result (to atomics noise) — an add
     issued on the main stream before the side stream's producers have run would read uninitialised memory."""
     from pq3d_b200 import train_engine
     from pq3d_b200.query_encoder import QueryMaskEncoder
@@ -516,4 +516,7 @@ def test_cross_block_gradient_accumulation_is_stream_safe(monkeypatch):
     for delay in (False, True):
         got = grads(True, delay)
         for k in ref:
-            assert torch.equal(got[k], ref[k]), f"{k}: multi-stream gradient differs from program order (delay={delay})"
+            # (dQ leaves the fused attention backward through fp32 red.global.add: last-bit run-to-run noise is expected;
+            # a value read before it was written would be off by orders of magnitude)
+            assert torch.isfinite(got[k]).all() and rel(got[k], ref[k], 1e-12) <= 1e-3, \
+                f"{k}: multi-stream gradient differs from program order (delay={delay}): {rel(got[k], ref[k], 1e-12):.3e}"
