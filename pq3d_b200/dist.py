@@ -75,12 +75,14 @@ class FlatGradAllReduce:
 
     Two cooperating parts:
 
-    * IN-BACKWARD BUCKETS (when constructed with `encoder=`: the decoder whose hand-composed backward,
+    * IN-BACKWARD BUCKETS (when constructed with `encoder=` and the world size is <= 2 — measured, see __init__ — or
+      PQ3D_GRAD_OVERLAP=1; the decoder is the one whose hand-composed backward,
       pq3d_b200/train_engine.py, calls back): as soon as the backward of decoder layer i has produced that layer's
       query-side gradients (self-attention, FFN, out-projections, LayerNorms — final once `group_bwd` of the layer
       returns), they are packed as bf16 into one bucket and all-reduced on a COMMUNICATION STREAM while the backward of
-      layer i-1 runs; the in-projection gradients (their K / V rows are only final after the memory-side tail) go out
-      as a last bucket.  The backward joins the communication stream before it hands the (already averaged) gradients
+      layer i-1 runs; the in-projection gradients (their K / V rows are only final in the memory-side tail) go out
+      per memory, as soon as that memory's weight-gradient GEMMs are queued, so the next memory's work hides them; what
+      is left forms a last, small bucket.  The backward joins the communication stream before it hands the (already averaged) gradients
       to autograd.  bf16 on the wire halves the bytes (120 MB instead of 240 MB per step for the 60 M-parameter
       decoder; the same compression torch's `bf16_compress_hook` applies to DDP buckets); the sum over ranks is
       upcast to fp32 and divided by the world size on arrival.
@@ -116,15 +118,25 @@ class FlatGradAllReduce:
             self._name_of = {n_: p for n_, p in encoder.named_parameters()}
             ours = {id(p) for p in self.params}
             shared = len({id(p) for p in encoder.parameters()}) != len(list(encoder.named_parameters(remove_duplicate=False)))
-            if all(id(p) in ours for p in self._name_of.values()) and getattr(encoder, "num_blocks", 1) == 1 and not shared:
+            import os
+            # MEASURED (config-5 shard, whole step one CUDA graph): 2 GPUs — buckets 3.78 ms/step vs one flat bf16 call
+            # 3.89; 8 GPUs — buckets 4.67 vs flat 4.14 (3.18 without any collective).  The persistent GEMMs of the
+            # backward need every SM, so a collective running next to them delays them by about its own duration and
+            # nine small collectives pay nine latencies at 8 ranks: overlap only pays for two ranks.
+            env = os.environ.get("PQ3D_GRAD_OVERLAP")
+            world = dist.get_world_size(group) if dist.is_initialized() else 1
+            want = (world <= 2) if env is None else (env != "0")
+            if want and all(id(p) in ours for p in self._name_of.values()) and getattr(encoder, "num_blocks", 1) == 1 and not shared:
                 encoder.grad_sink = self
                 self.overlapped = True
                 if dev.type == "cuda":
                     self.comm_stream = torch.cuda.Stream(device=dev)
-        esz = torch.empty(0, dtype=self.wire).element_size() if self.overlapped else 4
+        # the flat path (everything the buckets do not cover; all of it when nothing overlaps) also travels in `wire`
+        self.flat_wire = torch.empty(n, dtype=self.wire, device=dev) if (self.wire != torch.float32 and n) else None
+        esz = torch.empty(0, dtype=self.wire).element_size()
         self.bytes_per_step = n * esz
-        self.wire_dtype = str(self.wire if self.overlapped else torch.float32).replace("torch.", "")
-        self.n_buckets = (getattr(encoder, "num_layers", 0) + 1) if self.overlapped else 1
+        self.wire_dtype = str(self.wire).replace("torch.", "")
+        self.n_buckets = (getattr(encoder, "num_layers", 0) + len(getattr(encoder, "memories", [])) + 1) if self.overlapped else 1
 
     # ---- called by train_engine._Bwd -------------------------------------------------------------------
     def begin_backward(self):
@@ -191,7 +203,12 @@ class FlatGradAllReduce:
         if have:
             torch._foreach_copy_([v for _, v in have], [p.grad for p, _ in have])
         if len(rest) == len(self.params):
-            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
+            if self.flat_wire is not None:               # one pass down to the wire type, one collective, one pass back
+                self.flat_wire.copy_(self.flat)
+                dist.all_reduce(self.flat_wire, op=dist.ReduceOp.SUM, group=self.group)
+                self.flat.copy_(self.flat_wire)
+            else:
+                dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
             self.flat.div_(world)
         else:                                    # a subset: reduce its views one by one (rare: parameters outside the decoder)
             for _, v in rest:

@@ -736,6 +736,14 @@ class _Bwd:
                 for G in self.G_blk:
                     self.acc(pre + "in_proj_weight", G[i, j])
                 self.acc(pre + "in_proj_bias", G_b[i, j])
+            if sink is not None:
+                # this memory's in-projection gradients (all layers) are complete once its wgrads above have run on the
+                # side stream: send them now, the next memory's wgrad / dgrad work hides the transfer
+                tag = f".cross_attn_list.{j}.multihead_attn.in_proj"
+                ready = {n: parts[0] for n, parts in self.pending.items()
+                         if tag in n and len(parts) == 1 and n not in self.sent}
+                self.sent.update(ready)
+                sink.reduce_async(("mem", j), ready, producers=[self.side])
             cut = lambda t: t.view(B, st.Sp, D)[:, :st.S]              # noqa: E731
             if st.multi:
                 d_feats, d_p = [], None

@@ -157,5 +157,5 @@ def _bucket_job(rank, world):
 def test_in_backward_bf16_buckets_average_gradients():
     r = _spawn(_bucket_job)
     for worst, left, overlapped, n_buckets, wire in r.values():
-        assert overlapped and left == 0 and n_buckets == 3 and wire == "bfloat16"
+        assert overlapped and left == 0 and n_buckets == 2 + 3 + 1 and wire == "bfloat16"
         assert worst <= 1.5e-2, worst                 # bf16 on the wire: 2^-8 per addend
