@@ -309,31 +309,86 @@ __device__ __forceinline__ bool attn_softmax(const AttnParams& p, const AttnMem&
   const uint32_t dkey = p.drop_thresh != 0 ? drop_key(__ldg(p.seed), p.site[c.mi]) : 0u;
   const uint32_t drow = static_cast<uint32_t>(((static_cast<int64_t>(c.b) * p.H + c.h) * p.Nq + n_c) *
                                               (((mem.S + kKvTile - 1) / kKvTile) * kKvTile));
-  float l = 0.f;
-  for (int t = 0; t < c.T; ++t, ++g) {           // ---- probabilities, row sums, P tiles
-    const int sb = g & 1;
-    const int pb = t & 1;
-    const uint32_t word = mask_word(t);
-    if (MODE != kResident) {
-      mbar_wait(&c.s_full[sb], (g >> 1) & 1, 310 + sb);
-      tc_fence_after();
-    }
-    float sc[32];
-    load_scores(t, sb, word, sc);
-    if (MODE != kResident) release_scores(sb);
+  // ---- probabilities, row sums, P tiles.  Each warp's 32-key chunk is processed as two HALVES of 16 keys: the TMEM load
+  // of the next half is in flight while ex2 / packing work on the current one, and only 2 x 16 score registers are live
+  // (the kernel is capped at 96 registers per thread: 18 warps).  Scores land in float registers directly, the row sum
+  // runs as four interleaved partial sums, mask words are fetched one tile ahead.
+  float l4[4] = {0.f, 0.f, 0.f, 0.f};
+  {
+    float bufA[16], bufB[16];
+    const int g0 = g;
+    auto s_buffer = [&](int t) { return (g0 + t) & 1; };
+    auto wait_scores = [&](int t) {
+      if (MODE != kResident) {
+        mbar_wait(&c.s_full[s_buffer(t)], ((g0 + t) >> 1) & 1, 310 + s_buffer(t));
+        tc_fence_after();
+      }
+    };
+    auto issue = [&](int t, int h, float (&buf)[16]) {
+      tmem_ld_32x16f(c.tmem_S0 + s_buffer(t) * kKvTile + lane_off + cc * 32 + h * 16, buf);
+    };
+    // 16 scores -> 16 probabilities (bias, mask, ex2, row sum, dropout) -> two 16-byte chunks of the swizzled P tile
+    auto process_half = [&](int t, int h, float (&pr)[16], uint32_t bits, bool any_masked, int pb) {
+      if (brow != nullptr) {
+        const float4* b4 = reinterpret_cast<const float4*>(brow + t * kKvTile + cc * 32 + h * 16);
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      sc[j] = ex2_approx(MODE == kOnePass ? sc[j] : sc[j] - m);    // ex2(-inf) = 0 for masked keys
-      l += sc[j];
-    }
-    if (p.drop_thresh != 0) {                    // the denominator keeps every key; P V uses the dropped, rescaled weights
-      const uint32_t e0 = drow + t * kKvTile + cc * 32;
+        for (int j = 0; j < 4; ++j) {
+          const float4 v = __ldg(b4 + j);
+          pr[4 * j] += v.x; pr[4 * j + 1] += v.y; pr[4 * j + 2] += v.z; pr[4 * j + 3] += v.w;
+        }
+      }
+      if (any_masked) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) sc[j] = drop_keep(dkey, e0 + j, p.drop_thresh) ? sc[j] * p.drop_scale : 0.f;
+        for (int j = 0; j < 16; ++j) pr[j] = ((bits >> j) & 1u) ? kNegInf : pr[j];
+      }
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        pr[j] = ex2_approx(MODE == kOnePass ? pr[j] : pr[j] - m);    // ex2(-inf) = 0 for masked keys
+        l4[j & 3] += pr[j];
+      }
+      if (p.drop_thresh != 0) {                  // the denominator keeps every key; P V uses the dropped, rescaled weights
+        const uint32_t e0 = drow + t * kKvTile + cc * 32 + h * 16;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) pr[j] = drop_keep(dkey, e0 + j, p.drop_thresh) ? pr[j] * p.drop_scale : 0.f;
+      }
+      uint8_t* prow = c.sP + pb * kPBytes + r * 128;
+#pragma unroll
+      for (int q2 = 0; q2 < 2; ++q2) {
+        uint4 u;
+        u.x = pack_bf16x2(pr[q2 * 8 + 0], pr[q2 * 8 + 1]);
+        u.y = pack_bf16x2(pr[q2 * 8 + 2], pr[q2 * 8 + 3]);
+        u.z = pack_bf16x2(pr[q2 * 8 + 4], pr[q2 * 8 + 5]);
+        u.w = pack_bf16x2(pr[q2 * 8 + 6], pr[q2 * 8 + 7]);
+        const int ci = cc * 4 + h * 2 + q2;        // 16-byte chunk index along the 128 keys
+        const int atom = ci >> 3, c8 = ci & 7;     // swizzle-atom column, chunk inside its 128-B row
+        *reinterpret_cast<uint4*>(prow + atom * (kPBytes / 2) + ((c8 ^ (r & 7)) << 4)) = u;
+      }
+    };
+    uint32_t word_next = mask_word(0);
+    wait_scores(0);
+    issue(0, 0, bufA);
+    for (int t = 0; t < c.T; ++t, ++g) {
+      const int pb = t & 1;
+      const uint32_t word = word_next;
+      if (t + 1 < c.T) word_next = mask_word(t + 1);
+      const bool any_masked = __any_sync(0xffffffffu, word != 0u);
+      tmem_ld_wait();                            // half 0 of tile t is in bufA
+      issue(t, 1, bufB);
+      mbar_wait(&c.p_empty[pb], ((t >> 1) & 1) ^ 1, 320 + pb);
+      process_half(t, 0, bufA, word & 0xffffu, any_masked, pb);
+      tmem_ld_wait();                            // half 1 in bufB: the score buffer can go back to the MMA warp
+      if (MODE != kResident) release_scores(s_buffer(t));
+      if (t + 1 < c.T) {
+        wait_scores(t + 1);
+        issue(t + 1, 0, bufA);
+      }
+      process_half(t, 1, bufB, word >> 16, any_masked, pb);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane_id() == 0) mbar_arrive(&c.p_full[pb]);
     }
-    mbar_wait(&c.p_empty[pb], ((t >> 1) & 1) ^ 1, 320 + pb);
-    write_probs(pb, sc);
   }
+  float l = (l4[0] + l4[1]) + (l4[2] + l4[3]);
   if (dbg != nullptr && threadIdx.x == 64) dbg[3] = clock64();
   // ---- finalize: combine the partial row sums, zero-attn column, normalise, store
   c.s_part[cc * 128 + r] = l;
