@@ -13,9 +13,11 @@
 // TMA-loadable with the 128-byte swizzle.
 //
 // One CTA = (head, scene, memory, 128-query tile).  576 threads:
-//   warp 0      TMA producer: Q tile once, then K / K + V^T tiles of 128 keys into a 3-stage ring
+//   warp 0      TMA producer: Q tile once, then K / K + V^T tiles of 128 keys into a 5-stage ring
 //   warp 1      tcgen05.mma issuer: S = Q K^T (128x128, fp32 in TMEM, double-buffered),
-//               O += P V (128x64 in TMEM); P comes from shared memory (bf16, swizzled K-major)
+//               O += P V (128x64 in TMEM) in the TS form: the A operand P is read from TENSOR MEMORY
+//               (bf16 pairs, 64 columns per 128-key tile, double-buffered), V^T from shared memory.
+//               The softmax warps write P with tcgen05.st, so probabilities never touch shared memory.
 //   warps 2..17 softmax: 16 warps, four per TMEM lane quadrant, each owning one 32-key column chunk
 //               of every 128-key tile for its 32 query rows (TMEM lane = row); per-row partials are
 //               combined through shared memory once per pass.
@@ -44,7 +46,7 @@ constexpr int kMaxMem = 4;
 constexpr int kSoftmaxWarps = 16;                       // 4 per TMEM lane quadrant, one 32-key chunk each
 constexpr int kAttnThreads = 64 + 32 * kSoftmaxWarps;
 constexpr int kKvTile = 128;
-constexpr int kKvStages = 3;
+constexpr int kKvStages = 5;      // no P tiles in shared memory any more: the ring gets their space
 constexpr int kHeadDim = 64;
 
 enum AttnMode : int { kResident = 0, kTwoPass = 1, kOnePass = 2 };
@@ -89,9 +91,9 @@ struct AttnParams {
 constexpr int kQBytes = 128 * kHeadDim * 2;           // 16 KB
 constexpr int kKBytes = kKvTile * kHeadDim * 2;       // 16 KB
 constexpr int kVBytes = kHeadDim * kKvTile * 2;       // 16 KB (two [64 x 64] boxes)
-constexpr int kPBytes = 128 * kKvTile * 2;            // 32 KB (two [128 x 64] swizzle-atom columns)
+
 constexpr int kNumBars = 1 + 2 * kKvStages + 8 + 1;   // q_full, kv_full/empty, s_full/empty, p_full/empty, o_full
-constexpr int kAttnSmem = kQBytes + kKvStages * (kKBytes + kVBytes) + 2 * kPBytes + 256 + 2048 /*row partials*/;
+constexpr int kAttnSmem = kQBytes + kKvStages * (kKBytes + kVBytes) + 256 + 2048 /*row partials*/;
 
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
@@ -100,10 +102,10 @@ __device__ __forceinline__ float ex2_approx(float x) {
 }
 
 struct AttnCtx {
-  uint8_t *sQ, *sKV, *sP;
+  uint8_t *sQ, *sKV;
   uint64_t *q_full, *kv_full, *kv_empty, *s_full, *s_empty, *p_full, *p_empty, *o_full;
   float* s_part;
-  uint32_t tmem_S0, tmem_O;
+  uint32_t tmem_S0, tmem_O, tmem_P;
   int h, b, mi, qt, T;
 };
 
@@ -179,13 +181,13 @@ __device__ __forceinline__ void attn_mma(const AttnCtx& c) {
     tc_fence_after();
     const int s = ring_pos % kKvStages;
     const uint32_t v_addr = smem_u32(c.sKV + s * (kKBytes + kVBytes) + kKBytes);
-    const uint32_t p_addr = smem_u32(c.sP + pb * kPBytes);
+    const uint32_t p_tmem = c.tmem_P + pb * (kKvTile / 2);   // P tile: 128 lanes x 128 bf16 = 64 columns, A operand in TMEM
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
 #pragma unroll
       for (int k = 0; k < 4; ++k)
-        umma_ss(c.tmem_O, umma_desc_k_sw128(p_addr + j * (kPBytes / 2) + k * 32),
-                umma_desc_k_sw128(v_addr + j * (kVBytes / 2) + k * 32), idesc_o, (t | j | k) != 0 ? 1u : 0u);
+        umma_ts(c.tmem_O, p_tmem + (j * 4 + k) * 8, umma_desc_k_sw128(v_addr + j * (kVBytes / 2) + k * 32), idesc_o,
+                (t | j | k) != 0 ? 1u : 0u);
     }
     tc_commit(&c.kv_empty[s]);
     tc_commit(&c.p_empty[pb]);
@@ -264,24 +266,6 @@ __device__ __forceinline__ bool attn_softmax(const AttnParams& p, const AttnMem&
     __syncwarp();
     if (lane_id() == 0) mbar_arrive(&c.s_empty[sb]);
   };
-  auto write_probs = [&](int pb, const float (&pr)[32]) {
-    uint8_t* prow = c.sP + pb * kPBytes + r * 128;
-#pragma unroll
-    for (int q4 = 0; q4 < 4; ++q4) {
-      uint4 u;
-      u.x = pack_bf16x2(pr[q4 * 8 + 0], pr[q4 * 8 + 1]);
-      u.y = pack_bf16x2(pr[q4 * 8 + 2], pr[q4 * 8 + 3]);
-      u.z = pack_bf16x2(pr[q4 * 8 + 4], pr[q4 * 8 + 5]);
-      u.w = pack_bf16x2(pr[q4 * 8 + 6], pr[q4 * 8 + 7]);
-      const int ci = cc * 4 + q4;                // 16-byte chunk index along the 128 keys
-      const int atom = ci >> 3, c8 = ci & 7;     // swizzle-atom column, chunk inside its 128-B row
-      *reinterpret_cast<uint4*>(prow + atom * (kPBytes / 2) + ((c8 ^ (r & 7)) << 4)) = u;
-    }
-    fence_proxy_async_smem();
-    __syncwarp();
-    if (lane_id() == 0) mbar_arrive(&c.p_full[pb]);
-  };
-
   int g = 0;
   float m = 0.f;                                 // ONE_PASS: the zero-attn score is the reference
   if (MODE != kOnePass) {
@@ -351,18 +335,12 @@ __device__ __forceinline__ bool attn_softmax(const AttnParams& p, const AttnMem&
 #pragma unroll
         for (int j = 0; j < 16; ++j) pr[j] = drop_keep(dkey, e0 + j, p.drop_thresh) ? pr[j] * p.drop_scale : 0.f;
       }
-      uint8_t* prow = c.sP + pb * kPBytes + r * 128;
+      // 16 probabilities -> 8 packed bf16 pairs -> 8 TMEM columns of this row (keys cc*32 + h*16 ..): P never touches
+      // shared memory; the P.V product reads it as its tensor-memory A operand
+      uint32_t u[8];
 #pragma unroll
-      for (int q2 = 0; q2 < 2; ++q2) {
-        uint4 u;
-        u.x = pack_bf16x2(pr[q2 * 8 + 0], pr[q2 * 8 + 1]);
-        u.y = pack_bf16x2(pr[q2 * 8 + 2], pr[q2 * 8 + 3]);
-        u.z = pack_bf16x2(pr[q2 * 8 + 4], pr[q2 * 8 + 5]);
-        u.w = pack_bf16x2(pr[q2 * 8 + 6], pr[q2 * 8 + 7]);
-        const int ci = cc * 4 + h * 2 + q2;        // 16-byte chunk index along the 128 keys
-        const int atom = ci >> 3, c8 = ci & 7;     // swizzle-atom column, chunk inside its 128-B row
-        *reinterpret_cast<uint4*>(prow + atom * (kPBytes / 2) + ((c8 ^ (r & 7)) << 4)) = u;
-      }
+      for (int j = 0; j < 8; ++j) u[j] = pack_bf16x2(pr[2 * j], pr[2 * j + 1]);
+      tmem_st_32x8(c.tmem_P + pb * (kKvTile / 2) + lane_off + cc * 16 + h * 8, u);
     };
     uint32_t word_next = mask_word(0);
     wait_scores(0);
@@ -383,7 +361,8 @@ __device__ __forceinline__ bool attn_softmax(const AttnParams& p, const AttnMem&
         issue(t + 1, 0, bufA);
       }
       process_half(t, 1, bufB, word >> 16, any_masked, pb);
-      fence_proxy_async_smem();
+      tmem_st_wait();                            // this warp's part of the P tile is in tensor memory
+      tc_fence_before();
       __syncwarp();
       if (lane_id() == 0) mbar_arrive(&c.p_full[pb]);
     }
@@ -447,8 +426,8 @@ attention_fwd_kernel(const __grid_constant__ AttnMaps maps, const AttnParams p) 
   AttnCtx c;
   c.sQ = smem;
   c.sKV = c.sQ + kQBytes;
-  c.sP = c.sKV + kKvStages * (kKBytes + kVBytes);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(c.sP + 2 * kPBytes);
+  uint8_t* after_ring = c.sKV + kKvStages * (kKBytes + kVBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(after_ring);
   c.q_full = bars;
   c.kv_full = bars + 1;
   c.kv_empty = c.kv_full + kKvStages;
@@ -459,7 +438,7 @@ attention_fwd_kernel(const __grid_constant__ AttnMaps maps, const AttnParams p) 
   c.o_full = c.p_empty + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(c.o_full + 1);
   uint32_t* redo_flag = tmem_slot + 1;
-  c.s_part = reinterpret_cast<float*>(c.sP + 2 * kPBytes + 256);   // [4 column chunks][128 rows]
+  c.s_part = reinterpret_cast<float*>(after_ring + 256);   // [4 column chunks][128 rows]
 
   const int warp = threadIdx.x >> 5;
   c.h = blockIdx.x;
@@ -487,6 +466,7 @@ attention_fwd_kernel(const __grid_constant__ AttnMaps maps, const AttnParams p) 
   const uint32_t tmem_base = *tmem_slot;
   c.tmem_S0 = tmem_base;        // columns [0,128) and [128,256): S double buffer
   c.tmem_O = tmem_base + 256;   // columns [256,320): O
+  c.tmem_P = tmem_base + 320;   // columns [320,384) and [384,448): P double buffer (bf16 pairs), A operand of P.V
   pdl_sync();
   if (mem.kv_tiles != nullptr) {          // ragged scenes: skip the trailing tiles that are padding for every query
     const int act = __ldg(mem.kv_tiles + c.b);

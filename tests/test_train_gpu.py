@@ -6,7 +6,10 @@ same upstream gradient.  The reference trains by plain autograd through modules/
 Tolerance, written here: per tensor, with e(x) = ||x - g32||inf / ||g32||inf against the fp32-autograd gradient g32,
     e(ours) <= 1.5 * e(oracle under autocast-bf16) + 2e-2   and   e(ours) <= max(6e-2, 1.25 * e(autocast oracle))
 (gradients pass through twice as many bf16-rounded products as the forward; the oracle's own bf16 path is the
-yardstick).  Tensors whose true gradient is zero — the key biases: softmax is shift invariant — are measured against
+yardstick).  Where the autocast oracle itself is off by more than 6e-2 in max-norm (the FFN's first linear: a
+pre-activation within bf16 noise of 0 flips its ReLU gate and moves one row of dW by a whole sample's contribution,
+so the max-norm is set by WHICH gates flip, not by accuracy) the second clause is replaced by the relative L2 error:
+    ||ours - g32||2 / ||g32||2 <= 1.5 * (same for the autocast oracle) + 1e-2.  Tensors whose true gradient is zero — the key biases: softmax is shift invariant — are measured against
 1e-3 of the largest parameter gradient instead of their own (rounding-noise) norm.
 """
 import pytest
@@ -23,6 +26,11 @@ DEV = "cuda"
 def rel(a, b, floor=1e-20):
     a, b = a.float(), b.float()
     return ((a - b).abs().max() / b.abs().max().clamp_min(floor)).item()
+
+
+def rel_l2(a, b):
+    a, b = a.float(), b.float()
+    return ((a - b).norm() / b.norm().clamp_min(1e-20)).item()
 
 
 def _inputs(w, seed):
@@ -96,12 +104,16 @@ def _run_case(w, seed=3):
             assert float(ours[k].abs().max()) <= floor, f"{k}: {float(ours[k].abs().max()):.3e} > {floor:.3e}"
             continue
         e, e16 = rel(ours[k], ref, floor), rel(g16[k], ref, floor)
-        worst.append((e, e16, k))
+        worst.append((e, e16, k, rel_l2(ours[k], ref), rel_l2(g16[k], ref)))
     worst.sort(reverse=True)
-    for e, e16, k in worst[:8]:
-        print(f"  {k}: ours {e:.3e}  autocast oracle {e16:.3e}")
-    for e, e16, k in worst:
-        assert e <= 1.5 * e16 + 2e-2 and e <= max(6e-2, 1.25 * e16), f"{k}: gradient error {e:.3e} (autocast oracle {e16:.3e})"
+    for e, e16, k, l2, l2_16 in worst[:8]:
+        print(f"  {k}: ours {e:.3e}  autocast oracle {e16:.3e}   (relative L2: {l2:.3e} / {l2_16:.3e})")
+    for e, e16, k, l2, l2_16 in worst:
+        assert e <= 1.5 * e16 + 2e-2, f"{k}: gradient error {e:.3e} (autocast oracle {e16:.3e})"
+        if e16 > 6e-2:      # gate-flip dominated max-norm: judge the second clause in L2
+            assert l2 <= 1.5 * l2_16 + 1e-2, f"{k}: relative L2 gradient error {l2:.3e} (autocast oracle {l2_16:.3e})"
+        else:
+            assert e <= max(6e-2, 1.25 * e16), f"{k}: gradient error {e:.3e} (autocast oracle {e16:.3e})"
     return enc
 
 
