@@ -314,7 +314,9 @@ def e2e_record(e2e_model, dec_value, dec_serial, h2d, d2h, steps):
     """The headline end-to-end record: through the model boundary when the workload has one (the plugin call a user of
     the reference makes), with the decoder-boundary loop kept beside it."""
     timing = ("wall clock, max over ranks; every step copies its inputs from pinned host memory and reads its result "
-              "back; double-buffered: the H2D copy of step i+1 overlaps the forward of step i")
+              "back; double-buffered: the H2D copy of step i+1 (one copy of the batch's pinned staging arena) overlaps the "
+              "forward of step i (one CUDA-graph launch: the model captures its whole forward when it sees the same staging "
+              "buffers again)")
     dec = {"value": dec_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": steps,
            "serial_value": dec_serial,
            "boundary": "QueryMaskEncoder.forward(input_dict, pairwise_locs): projected (B,S,768) fp32 feature and positional "
@@ -796,11 +798,25 @@ def main():
         model = model.to(dev)
         model.unified_encoder.use_cuda_graph = enc.use_cuda_graph
         dd_host = synth.make_model_data_dict(w, mcfg, rank=rank)
-        dd_pin = {k: v.pin_memory() for k, v in dd_host.items() if isinstance(v, torch.Tensor)}
-        h2d_m = sum(t.numel() * t.element_size() for t in dd_pin.values())
+        # the batch is staged the way a serving loop stages it: ONE pinned arena on the host, one arena per device input
+        # set, every tensor a 256-byte-aligned view — a step's inputs cross PCIe as a single copy instead of 14
+        tens = {k: v for k, v in dd_host.items() if isinstance(v, torch.Tensor)}
+        offs, total = {}, 0
+        for k, v in tens.items():
+            offs[k] = total
+            total += (v.numel() * v.element_size() + 255) // 256 * 256
+
+        def views(arena):
+            return {k: arena[offs[k]:offs[k] + v.numel() * v.element_size()].view(v.dtype).view(v.shape) for k, v in tens.items()}
+        pin_arena = torch.empty(total, dtype=torch.uint8).pin_memory()
+        dd_pin = views(pin_arena)
+        for k, v in tens.items():
+            dd_pin[k].copy_(v)
+        h2d_m = total                                    # bytes the copy moves (tensor bytes + < 4 KB of alignment)
         msets = []
         for _ in range(2):
-            msets.append(dict(dd={k: torch.empty(v.shape, dtype=v.dtype, device=dev) for k, v in dd_pin.items()},
+            arena = torch.empty(total, dtype=torch.uint8, device=dev)
+            msets.append(dict(dd=views(arena), arena=arena,
                               h2d_done=torch.cuda.Event(), consumed=torch.cuda.Event(),
                               out=torch.empty(w.B, w.N, dtype=torch.float32).pin_memory()))
 
@@ -808,8 +824,7 @@ def main():
             st = msets[i % 2]
             with torch.cuda.stream(copy_stream):
                 copy_stream.wait_event(st["consumed"])
-                for k, v in dd_pin.items():
-                    st["dd"][k].copy_(v, non_blocking=True)
+                st["arena"].copy_(pin_arena, non_blocking=True)
                 st["h2d_done"].record(copy_stream)
 
         def run_model_pipelined(n):
@@ -827,7 +842,7 @@ def main():
                 st["out"].copy_(out, non_blocking=True)
             torch.cuda.synchronize()
 
-        run_model_pipelined(4)
+        run_model_pipelined(8)       # each input set: eager pass, whole-model graph capture, replays
         barrier()
         t0 = time.perf_counter()
         run_model_pipelined(e2e_steps)

@@ -12,6 +12,7 @@ backbone, PointNet++ tokenizer, CLIP / T5 towers.
 from __future__ import annotations
 
 import os
+import weakref
 from copy import copy
 from functools import partial
 from typing import Any, Dict, Optional
@@ -299,7 +300,75 @@ class Query3DUnified(nn.Module):
                                       "data_dict['prompt_feat'] (the CLIP text tower is out of scope)")
         return data_dict["prompt_feat"], data_dict["prompt_pad_masks"].logical_not()
 
+    # ---- whole-model CUDA graph (inference serving loops) ---------------------------------------------------------
+    def _graph_signature(self, data_dict):
+        """(hashable signature, tensors): every CUDA tensor of the batch by address / shape / strides / dtype, the CUDA
+        stream, and the switches the captured launch sequence depends on."""
+        items = [(k, v) for k, v in sorted(data_dict.items(), key=lambda kv: str(kv[0])) if isinstance(v, torch.Tensor)]
+        if not items or any(not v.is_cuda for _, v in items):
+            return None, None
+        dev = items[0][1].device
+        sig = (torch.cuda.current_stream(dev).cuda_stream, os.environ.get("PQ3D_PREINGEST", "1"),
+               tuple((k, v.data_ptr(), tuple(v.shape), v.stride(), v.dtype) for k, v in items))
+        return sig, [v for _, v in items]
+
+    def _forward_graphed(self, data_dict):
+        """A serving loop that hands in the SAME device tensors again (staging buffers refilled in place) gets the whole
+        forward — coordinate encoder, ObjectEncoder projections, pairwise geometry, decoder, grounding head: ~100 kernel
+        launches and as many torch ops, 1.3 ms of host time against 0.9 ms on the device — as ONE graph launch.  A batch
+        signature is captured the second time it is seen with the very same tensor objects (addresses alone could be
+        allocator re-use); the replay reads the buffers' current contents and the results are returned as fresh tensors.
+        Returns None when the call is not eligible (training, autograd, mixed prompt batches whose control flow depends
+        on device values, a mask head, layer taps) and the eager path runs."""
+        enc = self.unified_encoder
+        if (not getattr(self, "use_cuda_graph", True) or not getattr(enc, "use_cuda_graph", False) or self.training
+                or torch.is_grad_enabled() or "prompt_type" in data_dict or hasattr(self, "mask_head")
+                or any(h != "ground" for h in self.heads) or getattr(enc, "layer_taps", None) is not None
+                or type(enc) is not QueryMaskEncoder or not torch.cuda.is_available()
+                or torch.cuda.is_current_stream_capturing()):
+            return None
+        sig, tensors = self._graph_signature(data_dict)
+        if sig is None:
+            return None
+        graphs = self.__dict__.setdefault("_graphs", {})
+        ent = graphs.get(sig)
+        if ent is not None and ent.get("graph") is None and not all(r() is t for r, t in zip(ent["refs"], tensors)):
+            ent = None
+        if ent is None:
+            if len(graphs) >= 8:
+                graphs.pop(next(iter(graphs)))
+            graphs[sig] = {"refs": [weakref.ref(t) for t in tensors]}
+            return None                                          # first sighting: eager (allocates every workspace)
+        if ent.get("graph") is None:
+            torch.cuda.synchronize()
+            before = ops.LAUNCHES
+            g = torch.cuda.CUDAGraph()
+            dd = dict(data_dict)
+            enc._stream_key_override = sig[0]                    # capture runs on torch's side stream: keep the caller's workspace
+            try:
+                with torch.cuda.graph(g):
+                    self._forward_eager(dd)
+            finally:
+                enc._stream_key_override = None
+            outs = {k: v for k, v in dd.items()
+                    if isinstance(v, torch.Tensor) and data_dict.get(k) is not v and k != "ground_label"}
+            ent.update(graph=g, outs=outs, launches=ops.LAUNCHES - before, keep=tensors)
+            ops.LAUNCHES = before
+        ent["graph"].replay()
+        ops._count(ent["launches"])
+        fresh = {}
+        for k, v in ent["outs"].items():
+            if id(v) not in fresh:
+                fresh[id(v)] = v.clone()
+            data_dict[k] = fresh[id(v)]
+        data_dict["ground_label"] = data_dict.get("tgt_object_id")
+        return data_dict
+
     def forward(self, data_dict):
+        out = self._forward_graphed(data_dict)
+        return out if out is not None else self._forward_eager(data_dict)
+
+    def _forward_eager(self, data_dict):
         input_dict = {}
         mask = data_dict["query_pad_masks"].logical_not()
         query_locs = data_dict["query_locs"][:, :, :self.dim_loc]

@@ -344,6 +344,11 @@ class _MemState:
     __slots__ = ("name", "S", "S_pitch", "multi", "per_layer", "xk", "xv", "K", "Vt", "bits", "strides", "tiles")
 
 
+def _capturing() -> bool:
+    """True while an outer CUDA-graph capture (Query3DUnified's whole-model graph) is recording this stream."""
+    return torch.cuda.is_available() and torch.cuda.is_current_stream_capturing()
+
+
 class _Branch:
     """A side stream for work that is independent of the critical chain (fork / join, capturable inside a CUDA graph):
     the small prologue kernels next to the memories' ingest + K / V^T projections, the self-attention V^T projection
@@ -539,13 +544,14 @@ class QueryMaskEncoder(nn.Module):
         key = (B, N, tuple((m, tuple(input_dict[m][0][0].shape if isinstance(input_dict[m][0], list)
                                      else input_dict[m][0].shape), input_dict[m][1].ndim, input_dict[m][2] is None)
                            for m in active),
-               torch.cuda.current_stream(dev).cuda_stream if dev.type == "cuda" else 0,
+               (torch.cuda.current_stream(dev).cuda_stream if getattr(self, "_stream_key_override", None) is None
+                else self._stream_key_override) if dev.type == "cuda" else 0,
                None if pre is None else pre["xk"].data_ptr())
         ws = self._ws.setdefault(key, {})
         buf = lambda name, shape, dtype: self._buf(ws, name, shape, dtype, dev)  # noqa: E731
 
         if (self.use_cuda_graph and self.layer_taps is None and mask_head is None and not self.use_self_mask
-                and ws.get("graph") is not None):
+                and ws.get("graph") is not None and not _capturing()):
             # Whole-forward graph: when the caller hands in the SAME device tensors again (a serving loop re-using its
             # staging buffers), the prologue that reads them (ingest, mask packing, copies) is captured together with
             # the body, so a forward costs one graph launch on the host.  Fresh tensors fall back to the eager prologue
@@ -876,7 +882,8 @@ class QueryMaskEncoder(nn.Module):
         """First call per shape: eager (allocates the workspace, configures kernels).  Second call:
         capture.  Afterwards: one graph launch per forward (the launch-bound query-side chain of ~70
         small kernels costs more on the host than on the GPU otherwise)."""
-        if not self.use_cuda_graph or ws.get("_eager_body") or self.layer_taps is not None:
+        if (not self.use_cuda_graph or ws.get("_eager_body") or self.layer_taps is not None
+                or _capturing()):                                 # an outer capture (whole-model graph) records the launches
             body()
             return
         g = ws.get("graph")

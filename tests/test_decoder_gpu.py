@@ -365,3 +365,53 @@ def test_model_producers_emit_decoder_operands_bit_identical(monkeypatch):
         assert (calls["n"] == 0) == (flag == "1"), f"PQ3D_PREINGEST={flag}: {calls['n']} scene-memory ingest launches"
     assert torch.equal(outs["1"], outs["0"])
     assert torch.isfinite(outs["1"][d["query_pad_masks"]]).all()
+
+
+def test_model_whole_forward_graph_replays_current_buffer_contents():
+    """Query3DUnified.forward captures the WHOLE model forward into one CUDA graph when a serving loop hands in the same
+    device tensors again: results bit-identical to the eager path, the replay reads the buffers' current contents, fresh
+    tensors fall back to the eager path, and outputs are fresh tensors (never views of the graph's static memory)."""
+    from pq3d_b200.query3d_unified import Query3DUnified
+    w = synth.Workload("mgraph", 2, 40, 256, ["mv", "pc", "voxel", "prompt"], "mixed", T=8, num_layers=2)
+    cfg = synth.model_cfg_dict(w, dim_loc=3, heads=("ground",))
+    model = Query3DUnified(cfg).eval()
+    model.load_state_dict(synth.draw_state_dict(synth.model_param_shapes(cfg), 7, 1.5), strict=True)
+    model = model.to(DEV)
+    d = C.to_dev(synth.make_model_data_dict(w, cfg), DEV)
+    valid = d["query_pad_masks"]
+
+    def eager(dd):
+        model.use_cuda_graph = False
+        try:
+            with torch.no_grad():
+                return model(dict(dd))["ground_logits"].clone()
+        finally:
+            model.use_cuda_graph = True
+    ref1 = eager(d)
+    with torch.no_grad():
+        outs = [model(dict(d))["ground_logits"] for _ in range(4)]       # eager, capture + replay, replay, replay
+    torch.cuda.synchronize()
+    ents = [e for e in model._graphs.values() if e.get("graph") is not None]
+    assert len(ents) == 1 and ents[0]["launches"] > 50
+    for o in outs:
+        assert torch.equal(o, ref1)
+    assert len({o.data_ptr() for o in outs}) == len(outs)
+    # refill the staging buffers in place with another batch: the replay must see it
+    d2 = C.to_dev(synth.make_model_data_dict(w, cfg, rank=1), DEV)
+    for k, v in d.items():
+        if isinstance(v, torch.Tensor):
+            v.copy_(d2[k])
+    with torch.no_grad():
+        out2 = model(dict(d))["ground_logits"]
+    ref2 = eager(d)
+    assert torch.equal(out2, ref2)
+    assert not torch.equal(ref2[valid], ref1[valid])
+    assert torch.equal(outs[-1], ref1)                                   # earlier results were not overwritten
+    # different tensors of the same shapes: eager path (no stale replay), same numbers
+    with torch.no_grad():
+        out3 = model(dict(d2))["ground_logits"]
+    assert torch.equal(out3, ref2)
+    # autograd / training never take the graph
+    assert model._forward_graphed.__self__ is model
+    with torch.enable_grad():
+        assert model._forward_graphed(dict(d)) is None
