@@ -29,6 +29,11 @@ extern "C" {
 
 const char* pq3d_last_error(void);
 int pq3d_abi_version(void);
+/* Launch priority of the calling thread's subsequent kernel launches (cudaLaunchAttributePriority; 0 = default = least
+ * urgent, negative = more urgent, clamped to the device's range).  Recorded per kernel node when a CUDA graph captures the
+ * launches: with several batches in flight the latency-bound query-side kernels are marked urgent so that the long
+ * K / V^T projections of other batches do not hold them back.  (Scheduling only; no reference counterpart.) */
+int pq3d_set_launch_priority(int priority);
 /* Debug only: per-CTA timeline of pq3d_linear_bf16 (8 x uint64 per CTA) into a device buffer; NULL disables. */
 int pq3d_debug_set_timeline(void* buf);
 int pq3d_debug_set_attention_timeline(void* buf);

@@ -30,6 +30,7 @@ SIGNATURES: Dict[str, list] = {
                                  _i64, _f32, _vp, C.POINTER(C.c_uint32), _vp],
     "pq3d_spatial_bias": [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i64, _vp],
     "pq3d_debug_set_timeline": [_vp],
+    "pq3d_set_launch_priority": [C.c_int],
     "pq3d_debug_set_attention_timeline": [_vp],
     "pq3d_debug_force_two_pass": [_i32],
     "pq3d_transpose_cast": [_vp, _i32, _i64, _i64, _i64, _vp, _i64, _i64, _i64, _vp, _i64, _i64, _i64, _vp, _i64, _i64,

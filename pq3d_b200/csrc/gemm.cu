@@ -445,6 +445,9 @@ static int launch_linear(const CUtensorMap& ta, const CUtensorMap& tw, const CUt
   }
   int sms = sm_count();
   if (max_ctas > 0 && max_ctas < sms) sms = max_ctas;      // leave SMs to kernels running next to this one
+  // max_ctas < 0: -max_ctas WAVES of CTAs instead of one persistent wave — each CTA walks fewer tiles and gives its SM
+  // back earlier, so urgent kernels of other streams get in at that granularity (pq3d_set_launch_priority)
+  if (max_ctas < 0) sms = sms * (-max_ctas);
   const int max_clusters = sms / kCluster > 0 ? sms / kCluster : 1;
   const int grid = kCluster * (p.num_tiles < max_clusters ? p.num_tiles : max_clusters);
   PQ3D_CUDA(launch_kernel_cluster(linear_bf16_kernel<BN, CL, MC>, dim3(grid), dim3(kGemmThreads), Cfg::kSmemBytes, stream,

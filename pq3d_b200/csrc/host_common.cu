@@ -26,6 +26,10 @@ bool pdl_enabled() {
   return on == 1;
 }
 
+static thread_local int g_priority = 0;
+int launch_priority() { return g_priority; }
+void set_launch_priority(int p) { g_priority = p; }
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -76,3 +80,11 @@ int make_tmap(CUtensorMap* out, const void* base, int elem_bytes, int rank, cons
 
 extern "C" const char* pq3d_last_error(void) { return pq3d::last_error(); }
 extern "C" int pq3d_abi_version(void) { return 1; }
+extern "C" int pq3d_set_launch_priority(int priority) {
+  int least = 0, greatest = 0;
+  if (cudaDeviceGetStreamPriorityRange(&least, &greatest) != cudaSuccess) { least = 0; greatest = 0; }
+  if (priority < greatest) priority = greatest;        // numerically lower = more urgent
+  if (priority > least) priority = least;
+  pq3d::set_launch_priority(priority);
+  return PQ3D_OK;
+}

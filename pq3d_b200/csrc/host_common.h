@@ -46,6 +46,10 @@ inline int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const ui
 // the programmatic-stream-serialization attribute lets kernel N+1's set-up (barrier init, TMEM
 // allocation, tensor-map prefetch, launch latency) overlap kernel N's tail.  PQ3D_PDL=0 disables it.
 bool pdl_enabled();
+// Launch priority of the calling thread's next kernels (cudaLaunchAttributePriority; 0 = the device default = lowest,
+// negative = more urgent; recorded in CUDA-graph kernel nodes at capture).  Set through pq3d_set_launch_priority.
+int launch_priority();
+void set_launch_priority(int p);
 
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
@@ -55,11 +59,16 @@ inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block
   cfg.blockDim = block;
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  if (launch_priority() != 0) {
+    attr[1].id = cudaLaunchAttributePriority;
+    attr[1].val.priority = launch_priority();
+    cfg.numAttrs = 2;
+  }
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
@@ -71,15 +80,24 @@ inline cudaError_t launch_kernel_cluster(void (*kernel)(KArgs...), dim3 grid, di
   cfg.blockDim = block;
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[2];
+  cudaLaunchAttribute attr[3];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
-  attr[1].id = cudaLaunchAttributeClusterDimension;
-  attr[1].val.clusterDim.x = cluster_x;
-  attr[1].val.clusterDim.y = 1;
-  attr[1].val.clusterDim.z = 1;
+  int n = 1;
+  if (cluster_x > 1) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = cluster_x;
+    attr[n].val.clusterDim.y = 1;
+    attr[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  if (launch_priority() != 0) {
+    attr[n].id = cudaLaunchAttributePriority;
+    attr[n].val.priority = launch_priority();
+    ++n;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = cluster_x > 1 ? 2 : 1;
+  cfg.numAttrs = n;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 

@@ -4,6 +4,7 @@ modules/third_party/pointnet2/_ext_src/include/utils.h:5-25); the kernels see ra
 All launches go to torch's current CUDA stream, so they are CUDA-graph capturable."""
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
 from typing import List, Optional, Sequence, Tuple
 
@@ -15,6 +16,25 @@ bf16 = torch.bfloat16
 LOG2E = 1.4426950408889634
 Q_SCALE = LOG2E / 8.0     # attention kernels take Q pre-scaled by log2(e)/sqrt(head_dim=64): scores in the log2 domain
 LAUNCHES = 0          # kernels launched through this module (bench.py reports it as gpu_launches)
+
+
+_PRIORITY = [0]
+
+
+@contextlib.contextmanager
+def launch_priority(p: int):
+    """Kernels launched inside run with CUDA launch priority p (0 = default = least urgent, negative = more urgent;
+    recorded per node when a graph captures them).  pq3d_set_launch_priority."""
+    prev = _PRIORITY[0]
+    if p != prev:
+        _lib.lib().pq3d_set_launch_priority(int(p))
+        _PRIORITY[0] = int(p)
+    try:
+        yield
+    finally:
+        if _PRIORITY[0] != prev:
+            _lib.lib().pq3d_set_launch_priority(prev)
+            _PRIORITY[0] = prev
 
 
 def _count(n=1):

@@ -445,6 +445,13 @@ class QueryMaskEncoder(nn.Module):
         # already fill the machine).  Hence OFF by default; PQ3D_KV_OVERLAP=1 enables it for latency-bound serving.
         self.kv_overlap = os.environ.get("PQ3D_KV_OVERLAP", "0") != "0"
         self.kv_overlap_ctas = int(os.environ.get("PQ3D_KV_OVERLAP_CTAS", "100"))
+        # with several batches in flight (one graph per stream) the persistent K / V^T projection of one batch would hold
+        # every SM (232 KB of shared memory per CTA: nothing co-resides) while the other batches' latency-bound query-side
+        # kernels wait; capping its grid leaves them room (0 = all SMs)
+        self.shared_gemm_ctas = int(os.environ.get("PQ3D_SHARED_GEMM_CTAS", "0"))   # < 0: that many WAVES of CTAs
+        # with batches in flight, every kernel but the long projections is launched at this CUDA priority (negative =
+        # urgent; 0 = off): a stream's latency-bound chain then overtakes the other streams' projection CTAs
+        self.inflight_priority = int(os.environ.get("PQ3D_INFLIGHT_PRIORITY", "0"))
         # Opt-in: independent small kernels (mask packing, query copies, the prompt's projections, the spatial bias; the
         # self-attention V^T projection) on a side branch of the graph next to the critical chain.  MEASURED (round 2):
         # one batch at a time 0.7567 -> 0.7543 ms, no change with 4 batches in flight — and with 4 forked graphs in
@@ -527,6 +534,17 @@ class QueryMaskEncoder(nn.Module):
             # (train_engine.py); scope limits raise.  module.train() under no_grad runs the same forward.
             from . import train_engine
             return train_engine.run(self, input_dict, pairwise_locs, mask_head)
+        dev = input_dict["query"][0].device
+        prio = 0
+        if self.inflight_priority and dev.type == "cuda":
+            cur = torch.cuda.current_stream(dev).cuda_stream if getattr(self, "_stream_key_override", None) is None \
+                else self._stream_key_override
+            if len({k[-2] for k in self._ws} | {cur}) > 1:
+                prio = self.inflight_priority
+        with ops.launch_priority(prio):
+            return self._forward_inference(input_dict, pairwise_locs, mask_head)
+
+    def _forward_inference(self, input_dict: dict, pairwise_locs: Optional[torch.Tensor], mask_head: Optional[Callable]):
         query, query_masks, query_pos = input_dict["query"]
         dev = query.device
         B, N, D = query.shape
@@ -706,12 +724,15 @@ class QueryMaskEncoder(nn.Module):
             # CTA-pair GEMMs only while this decoder works on ONE stream: with pair GEMMs of several in-flight graphs
             # competing for SMs, long loops stalled on the device (csrc/gemm.cu, flags bit 1)
             solo = len({k[-2] for k in self._ws}) <= 1
-            ops.linear(xk_all, wk[l0 * D:], K_all, M=B * Sp, N=nl * D, K=D, bias=bk[l0 * D:], bias_group_stride=L * D,
-                       groups=nf, a_group_rows=B * Sp, w_group_rows=L * D, ldc=nl * D, c_group_stride=B * Sp * nl * D,
-                       max_ctas=max_ctas, no_pairs=not solo)
-            ops.linear(wv[l0 * D:], xv_all, Vt_all, M=nl * D, N=B * Sp, K=D, bias=bv[l0 * D:], bias_along_m=True,
-                       bias_group_stride=L * D, groups=nf, a_group_rows=L * D, w_group_rows=B * Sp, ldc=B * Sp,
-                       c_group_stride=nl * D * B * Sp, max_ctas=max_ctas, no_pairs=not solo)
+            if not solo and max_ctas == 0:
+                max_ctas = self.shared_gemm_ctas      # batches in flight: leave SMs to the other streams' small kernels
+            with ops.launch_priority(0):              # the long GEMMs yield to every urgent kernel (inflight_priority)
+                ops.linear(xk_all, wk[l0 * D:], K_all, M=B * Sp, N=nl * D, K=D, bias=bk[l0 * D:], bias_group_stride=L * D,
+                           groups=nf, a_group_rows=B * Sp, w_group_rows=L * D, ldc=nl * D, c_group_stride=B * Sp * nl * D,
+                           max_ctas=max_ctas, no_pairs=not solo)
+                ops.linear(wv[l0 * D:], xv_all, Vt_all, M=nl * D, N=B * Sp, K=D, bias=bv[l0 * D:], bias_along_m=True,
+                           bias_group_stride=L * D, groups=nf, a_group_rows=L * D, w_group_rows=B * Sp, ldc=B * Sp,
+                           c_group_stride=nl * D * B * Sp, max_ctas=max_ctas, no_pairs=not solo)
 
         def project_memories():
             """Hoisted K / V^T projections of every memory for all L layers (query independent)."""

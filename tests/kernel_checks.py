@@ -97,6 +97,25 @@ def check_gemm_pair():
     _gemm_case(8192, 1024, 256, 256, torch.float32, relu=True, seed=44)
 
 
+def check_gemm_scheduling_knobs():
+    """Launch priority (pq3d_set_launch_priority) and the multi-wave / capped grids (max_ctas < 0 / > 0) change scheduling
+    only: results are bit-identical to the default launch."""
+    g = gen(77)
+    M, N, K = 4096, 1536, 768
+    A, W, b = rnd((M, K), g).bfloat16(), rnd((N, K), g, 0.05).bfloat16(), rnd((N,), g)
+    outs = []
+    for prio, ctas in ((0, 0), (-2, 0), (0, -3), (-1, 40)):
+        out = torch.full((M, N), float("nan"), dtype=torch.bfloat16, device=DEV)
+        with ops.launch_priority(prio):
+            ops.linear(A, W, out, M=M, N=N, K=K, bias=b, block_n=256, max_ctas=ctas, no_pairs=True)
+        outs.append(out)
+    torch.cuda.synchronize()
+    for o in outs[1:]:
+        assert torch.equal(o, outs[0])
+    assert ops._PRIORITY[0] == 0
+    print("gemm: launch priority / multi-wave / capped grids bit-identical")
+
+
 def check_bgemm():
     """Strided batched GEMM: per-(scene, head) slices of packed [tokens, heads*64] tensors, ragged M / N per group."""
     g = gen(50)
