@@ -304,8 +304,10 @@ class Query3DUnified(nn.Module):
     def _graph_signature(self, data_dict):
         """(hashable signature, tensors): every CUDA tensor of the batch by address / shape / strides / dtype, the CUDA
         stream, and the switches the captured launch sequence depends on."""
-        items = [(k, v) for k, v in sorted(data_dict.items(), key=lambda kv: str(kv[0])) if isinstance(v, torch.Tensor)]
-        if not items or any(not v.is_cuda for _, v in items):
+        # host tensors (labels, ids) are not part of the signature: nothing on this path can read them
+        items = [(k, v) for k, v in sorted(data_dict.items(), key=lambda kv: str(kv[0]))
+                 if isinstance(v, torch.Tensor) and v.is_cuda]
+        if not items:
             return None, None
         dev = items[0][1].device
         sig = (torch.cuda.current_stream(dev).cuda_stream, os.environ.get("PQ3D_PREINGEST", "1"),
@@ -331,6 +333,16 @@ class Query3DUnified(nn.Module):
         if sig is None:
             return None
         graphs = self.__dict__.setdefault("_graphs", {})
+        # the captured launches read the kernels' operand copies of the parameters (bf16 weights, packed decoder tables):
+        # any in-place update (optimizer step, load_state_dict -> version counters) or move (.to(): addresses) since the
+        # capture re-creates those copies, so every graph is dropped and captured afresh
+        plist = self.__dict__.get("_graph_params")
+        if plist is None:
+            plist = self.__dict__["_graph_params"] = list(self.parameters()) + list(self.buffers())
+        wkey = (tuple(p._version for p in plist), tuple(p.data_ptr() for p in plist))
+        if self.__dict__.get("_graph_wkey") != wkey:
+            graphs.clear()
+            self.__dict__["_graph_wkey"] = wkey
         ent = graphs.get(sig)
         if ent is not None and ent.get("graph") is None and not all(r() is t for r, t in zip(ent["refs"], tensors)):
             ent = None
@@ -365,6 +377,11 @@ class Query3DUnified(nn.Module):
         return data_dict
 
     def forward(self, data_dict):
+        if self.training or torch.is_grad_enabled():
+            # fused optimizers update parameters without bumping version counters: a training-mode call invalidates
+            # the inference graphs outright
+            self.__dict__.get("_graphs", {}).clear()
+            return self._forward_eager(data_dict)
         out = self._forward_graphed(data_dict)
         return out if out is not None else self._forward_eager(data_dict)
 

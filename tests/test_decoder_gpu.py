@@ -412,6 +412,19 @@ def test_model_whole_forward_graph_replays_current_buffer_contents():
         out3 = model(dict(d2))["ground_logits"]
     assert torch.equal(out3, ref2)
     # autograd / training never take the graph
-    assert model._forward_graphed.__self__ is model
     with torch.enable_grad():
         assert model._forward_graphed(dict(d)) is None
+    # parameters updated in place (optimizer step / load_state_dict): the graphs are dropped, the next calls run the new
+    # weights eagerly and capture again
+    with torch.no_grad():
+        for _ in range(2):
+            model(dict(d))
+        assert any(e.get("graph") is not None for e in model._graphs.values())
+        model.ground_head.og3d_head[0].weight.mul_(1.5)
+        model.mv_encoder.input_feat_proj[0].weight.mul_(0.5)
+        model.unified_encoder.unified_encoder[0].ffn.linear1.weight.mul_(0.7)
+        got = [model(dict(d))["ground_logits"] for _ in range(3)]         # eager, capture + replay, replay
+    ref3 = eager(d)
+    assert not torch.equal(ref3[valid], ref2[valid])
+    for o in got:
+        assert torch.equal(o, ref3)
