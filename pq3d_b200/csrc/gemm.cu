@@ -63,12 +63,15 @@ constexpr int kBlockK = 64;  // 64 bf16 = 128 B = one swizzle atom row
 constexpr int kGemmThreads = 192;
 constexpr int kBoxBytes = 32 * 128;  // one epilogue box: 32 rows x 128 B
 
-template <int BN, int CL>
+constexpr int kFullRing = 196608;   // 192 KB of operands in flight: one CTA per SM
+constexpr int kHalfRing = 98304;    // 96 KB: two CTAs (of different streams' kernels) fit one SM
+
+template <int BN, int CL, int RING = kFullRing>
 struct GemmCfg {
   static constexpr int kABytes = kBlockM * kBlockK * 2;
   static constexpr int kBBytes = (BN / CL) * kBlockK * 2;                    // a CTA pair splits the W tile
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = 196608 / kStageBytes;                       // 192 KB of operands in flight
+  static constexpr int kStages = RING / kStageBytes;
   static constexpr int kRingBytes = kStages * kStageBytes;
   static constexpr int kStagingBytes = 4 * 2 * kBoxBytes;                    // 4 warps x double buffer
   static constexpr int kBarBytes = 256;
@@ -86,11 +89,11 @@ struct GemmCfg {
 // the same A tile, so each fetches a quarter of its rows and multicasts it into all four shared memories: per k-block a
 // CTA pulls 4 KB of A + its 8 KB of W instead of 16 + 8 KB.  A ring slot is reusable once all four CTAs consumed it
 // (multicast commit).  Correct (the kernel checks run it) but measured slower for the query-side GEMMs, see the host side.
-template <int BN, int CL, int MC = 1>
+template <int BN, int CL, int MC = 1, int RING = kFullRing>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 linear_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
                    const __grid_constant__ CUtensorMap tmap_c, const LinearParams p) {
-  using Cfg = GemmCfg<BN, CL>;
+  using Cfg = GemmCfg<BN, CL, RING>;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* staging = smem + Cfg::kRingBytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + Cfg::kStagingBytes);
@@ -432,14 +435,14 @@ linear_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   if (dbg != nullptr && threadIdx.x == 0) dbg[6] = clock64();
 }
 
-template <int BN, int CL, int MC = 1>
+template <int BN, int CL, int MC = 1, int RING = kFullRing>
 static int launch_linear(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& tc, const LinearParams& p,
                          cudaStream_t stream, int max_ctas = 0) {
-  using Cfg = GemmCfg<BN, CL>;
+  using Cfg = GemmCfg<BN, CL, RING>;
   constexpr int kCluster = CL * MC;
   static bool configured = false;
   if (!configured) {
-    PQ3D_CUDA(cudaFuncSetAttribute(linear_bf16_kernel<BN, CL, MC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    PQ3D_CUDA(cudaFuncSetAttribute(linear_bf16_kernel<BN, CL, MC, RING>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    Cfg::kSmemBytes));
     configured = true;
   }
@@ -450,8 +453,8 @@ static int launch_linear(const CUtensorMap& ta, const CUtensorMap& tw, const CUt
   if (max_ctas < 0) sms = sms * (-max_ctas);
   const int max_clusters = sms / kCluster > 0 ? sms / kCluster : 1;
   const int grid = kCluster * (p.num_tiles < max_clusters ? p.num_tiles : max_clusters);
-  PQ3D_CUDA(launch_kernel_cluster(linear_bf16_kernel<BN, CL, MC>, dim3(grid), dim3(kGemmThreads), Cfg::kSmemBytes, stream,
-                                  kCluster, ta, tw, tc, p));
+  PQ3D_CUDA(launch_kernel_cluster(linear_bf16_kernel<BN, CL, MC, RING>, dim3(grid), dim3(kGemmThreads), Cfg::kSmemBytes,
+                                  stream, kCluster, ta, tw, tc, p));
   return PQ3D_OK;
 }
 
@@ -476,6 +479,13 @@ static int linear_impl(const void* A, int64_t lda, int64_t a_rows_total, int64_t
                                 const int32_t* a_row_offsets, int flags) {
   const int w_is_constant = flags & 1;
   const bool no_pairs = (flags & 2) != 0;
+  // bit 2: the caller runs several batches concurrently — the 64- / 128-wide tiles keep only 96 KB of operands in flight
+  // so that two CTAs (of different streams' latency-bound kernels) share an SM
+  static const int half_ring_mode = [] {      // PQ3D_GEMM_HALF_RING: 0 = never, 1 = when flags bit 2 is set (default), 2 = always
+    const char* e = getenv("PQ3D_GEMM_HALF_RING");
+    return e == nullptr ? 1 : atoi(e);
+  }();
+  const bool half_ring = half_ring_mode == 2 || (half_ring_mode == 1 && (flags & 4) != 0);
   PQ3D_CHECK_ARG(A && W && C, "pq3d_linear_bf16: null operand");
   PQ3D_CHECK_ARG(M > 0 && N > 0 && K > 0 && groups > 0, "pq3d_linear_bf16: bad shape M=%d N=%d K=%d groups=%d", M, N,
                  K, groups);
@@ -599,8 +609,10 @@ static int linear_impl(const void* A, int64_t lda, int64_t a_rows_total, int64_t
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   switch (block_n) {
     case 64: return mc == kMc ? launch_linear<64, 1, kMc>(ta, tw, tc, p, st, max_ctas)
-                              : launch_linear<64, 1>(ta, tw, tc, p, st, max_ctas);
-    case 128: return launch_linear<128, 1>(ta, tw, tc, p, st, max_ctas);
+                   : half_ring ? launch_linear<64, 1, 1, kHalfRing>(ta, tw, tc, p, st, max_ctas)
+                               : launch_linear<64, 1>(ta, tw, tc, p, st, max_ctas);
+    case 128: return half_ring ? launch_linear<128, 1, 1, kHalfRing>(ta, tw, tc, p, st, max_ctas)
+                               : launch_linear<128, 1>(ta, tw, tc, p, st, max_ctas);
     default: return cl == 2 ? launch_linear<256, 2>(ta, tw, tc, p, st, max_ctas)
                             : launch_linear<256, 1>(ta, tw, tc, p, st, max_ctas);
   }

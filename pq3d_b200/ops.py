@@ -19,6 +19,19 @@ LAUNCHES = 0          # kernels launched through this module (bench.py reports i
 
 
 _PRIORITY = [0]
+_SHARED_SM = [False]
+
+
+@contextlib.contextmanager
+def shared_sm(on: bool):
+    """GEMMs launched inside use the narrow-tile variant that keeps 96 KB (not 192 KB) of operands in flight, so two CTAs
+    share an SM: for callers that run several batches concurrently on different streams (pq3d_linear_bf16_ex flags bit 2)."""
+    prev = _SHARED_SM[0]
+    _SHARED_SM[0] = bool(on)
+    try:
+        yield
+    finally:
+        _SHARED_SM[0] = prev
 
 
 @contextlib.contextmanager
@@ -101,7 +114,8 @@ def linear(A: torch.Tensor, W: torch.Tensor, out: torch.Tensor, *, M: int, N: in
         A.data_ptr(), A.stride(0), A.shape[0], a_group_rows, W.data_ptr(), W.stride(0), W.shape[0], w_group_rows,
         out.data_ptr(), ldc, c_group_stride, int(out.dtype == torch.float32), _p(bias), bias_group_stride,
         int(bias_along_m), _p(row_zero), row_zero_group_stride, M, N, K, groups, float(alpha), alpha_ncols,
-        int(relu), block_n, int(max_ctas), offs, int(w_const) | (2 if no_pairs else 0), _stream())
+        int(relu), block_n, int(max_ctas), offs, int(w_const) | (2 if no_pairs else 0) | (4 if _SHARED_SM[0] else 0),
+        _stream())
     _lib.check(rc, "pq3d_linear_bf16")
     _count()
     return out

@@ -452,6 +452,9 @@ class QueryMaskEncoder(nn.Module):
         # with batches in flight, every kernel but the long projections is launched at this CUDA priority (negative =
         # urgent; 0 = off): a stream's latency-bound chain then overtakes the other streams' projection CTAs
         self.inflight_priority = int(os.environ.get("PQ3D_INFLIGHT_PRIORITY", "0"))
+        # with batches in flight the narrow-tile GEMMs keep 96 KB instead of 192 KB of operands in flight, so the
+        # latency-bound query-side kernels of two streams share an SM (ops.shared_sm)
+        self.inflight_half_ring = os.environ.get("PQ3D_INFLIGHT_HALF_RING", "1") != "0"
         # Opt-in: independent small kernels (mask packing, query copies, the prompt's projections, the spatial bias; the
         # self-attention V^T projection) on a side branch of the graph next to the critical chain.  MEASURED (round 2):
         # one batch at a time 0.7567 -> 0.7543 ms, no change with 4 batches in flight — and with 4 forked graphs in
@@ -535,13 +538,14 @@ class QueryMaskEncoder(nn.Module):
             from . import train_engine
             return train_engine.run(self, input_dict, pairwise_locs, mask_head)
         dev = input_dict["query"][0].device
-        prio = 0
-        if self.inflight_priority and dev.type == "cuda":
+        prio, inflight = 0, False
+        if dev.type == "cuda":
             cur = torch.cuda.current_stream(dev).cuda_stream if getattr(self, "_stream_key_override", None) is None \
                 else self._stream_key_override
-            if len({k[-2] for k in self._ws} | {cur}) > 1:
+            inflight = len({k[-2] for k in self._ws} | {cur}) > 1       # this decoder serves several streams
+            if inflight:
                 prio = self.inflight_priority
-        with ops.launch_priority(prio):
+        with ops.launch_priority(prio), ops.shared_sm(inflight and self.inflight_half_ring):
             return self._forward_inference(input_dict, pairwise_locs, mask_head)
 
     def _forward_inference(self, input_dict: dict, pairwise_locs: Optional[torch.Tensor], mask_head: Optional[Callable]):

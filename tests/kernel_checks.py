@@ -114,6 +114,18 @@ def check_gemm_scheduling_knobs():
         assert torch.equal(o, outs[0])
     assert ops._PRIORITY[0] == 0
     print("gemm: launch priority / multi-wave / capped grids bit-identical")
+    # the 96 KB-ring variant of the narrow tiles (two CTAs per SM; ops.shared_sm) computes the same numbers
+    for bn, (M, N, K) in ((64, (400, 768, 2048)), (128, (1000, 1536, 768)), (64, (400, 2304, 768))):
+        A, W, b = rnd((M, K), g).bfloat16(), rnd((N, K), g, 0.05).bfloat16(), rnd((N,), g)
+        res = []
+        for on in (False, True):
+            out = torch.full((M, N), float("nan"), dtype=torch.float32, device=DEV)
+            with ops.shared_sm(on):
+                ops.linear(A, W, out, M=M, N=N, K=K, bias=b, block_n=bn, w_const=True)
+            res.append(out)
+        torch.cuda.synchronize()
+        assert torch.equal(res[0], res[1]), f"half-ring GEMM differs (bn={bn})"
+    print("gemm: half-ring (shared-SM) tiles bit-identical")
 
 
 def check_bgemm():
