@@ -650,6 +650,7 @@ def main():
 
     # configs with use_self_mask (BASELINE config 4) run the in-loop mask head, as Query3DUnified wires it
     mask_head = None
+    make_head = None
     if w.use_self_mask:
         from functools import partial
         from pq3d_b200.mask_head import MaskHeadSegLevel
@@ -659,30 +660,40 @@ def main():
         mh = mh.to(dev)
         seg_pad = to_dev(~_dd["seg_pad_masks"])
 
-        def make_head(inp):
+        def make_head(inp, seg_pad_=seg_pad):
             feats = []
             for m in scene_mems:
                 f = list(inp[m])
                 if isinstance(f[0], list):
                     f[0] = f[0][-1]
                 feats.append(f)
-            return partial(mh, seg_fts_for_match=feats, seg_masks=seg_pad, offline_attn_masks=None, skip_prediction=False)
+            return partial(mh, seg_fts_for_match=feats, seg_masks=seg_pad_, offline_attn_masks=None, skip_prediction=False)
         mask_head = make_head(inp_dev)
 
-    def step_resident():
+    # one resident batch PER STREAM: the batches in flight are different scenes (different seeds), not four replays of
+    # one set of tensors; batch 0 is this rank's batch of the serial loop and of the e2e loops
+    batches = [(inp_dev, pw_dev, mask_head)]
+    for i in range(1, max(1, args.streams)):
+        inp_i, pw_i, dd_i = synth.make_decoder_inputs(w, rank=rank + world * i)
+        (inp_i, _), pw_i = dict_to(inp_i, to_dev), to_dev(pw_i)
+        head_i = None if make_head is None else make_head(inp_i, to_dev(~dd_i["seg_pad_masks"]))
+        batches.append((inp_i, pw_i, head_i))
+
+    def step_resident(b=0):
+        inp_b, pw_b, head_b = batches[b]
         with torch.no_grad():
-            return enc(synth.clone_input_dict(inp_dev), pw_dev, mask_head)[0]
+            return enc(synth.clone_input_dict(inp_b), pw_b, head_b)[0]
 
     def timed_steps(n_streams, steps):
         """`steps` forwards, round-robin over n_streams CUDA streams (each stream = one batch in flight with its own
         workspace and captured graph); device time from the first launch to the last completion."""
         cur = torch.cuda.current_stream()
         streams = [cur] if n_streams <= 1 else [torch.cuda.Stream(device=dev) for _ in range(n_streams)]
-        for st in streams:                                   # warm-up: eager pass, capture, first replays — per stream
+        for si, st in enumerate(streams):                    # warm-up: eager pass, capture, first replays — per stream
             st.wait_stream(cur)
             with torch.cuda.stream(st):
                 for _ in range(max(args.warmup, 5)):       # eager, body capture, signature, whole-forward capture, replay
-                    step_resident()
+                    step_resident(si)
         for st in streams:
             cur.wait_stream(st)
         barrier()
@@ -693,7 +704,7 @@ def main():
             st.wait_stream(cur)
         for i in range(steps):
             with torch.cuda.stream(streams[i % len(streams)]):
-                step_resident()
+                step_resident(i % len(streams))
         for st in streams:
             cur.wait_stream(st)
         e1.record()
@@ -963,7 +974,8 @@ def main():
             "config": dict(workload_config(w, world),
                            l2="per-step working set ~0.5 GB (fp32 inputs + bf16 K/V^T for 4 layers) exceeds the 126 MB L2; no flush",
                            cuda_graph=enc.use_cuda_graph, streams=n_streams,
-                           in_flight=f"{n_streams} batch(es) in flight on {n_streams} CUDA stream(s) (K steps round-robin); "
+                           in_flight=f"{n_streams} batch(es) in flight on {n_streams} CUDA stream(s) (K steps round-robin), "
+                                     f"each stream its own batch of {w.B} scenes (different seeds, own device tensors); "
                                      f"strictly serial: {ms_serial:.4f} ms/step = {world * w.B * w.N / (ms_serial * 1e-3):.0f} queries/s"),
             "serial": {"ms_per_step": ms_serial, "value": world * w.B * w.N / (ms_serial * 1e-3)},
             "clocks": clocks,
