@@ -581,6 +581,31 @@ def emit(line: dict):
         os.write(_REAL_STDOUT, data)
 
 
+CPU_AFFINITY = None
+
+
+def pin_rank_to_cores(local_rank, world):
+    """N > 1: this rank's host thread (and the pinned staging memory it first-touches) stays on its own slice of the
+    cores NVML reports as local to its GPU, so eight ranks do not share cores or migrate across NUMA nodes."""
+    global CPU_AFFINITY
+    if world <= 1 or not hasattr(os, "sched_setaffinity"):
+        return
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        local = [64 * i + b for i, wd in enumerate(words) for b in range(64) if (wd >> b) & 1]
+        allowed = sorted(set(local) & os.sched_getaffinity(0)) or sorted(os.sched_getaffinity(0))
+        # the GPUs that share these cores split them evenly (all GPUs of one NUMA node report the same mask)
+        per = max(1, len(allowed) // world)
+        mine = allowed[(local_rank * per) % len(allowed):][:per] or allowed
+        os.sched_setaffinity(0, mine)
+        CPU_AFFINITY = mine
+    except Exception:  # noqa: BLE001 — pinning is an optimisation, never a reason to fail the run
+        CPU_AFFINITY = None
+
+
 def main():
     global _REAL_STDOUT
     args = parse()
@@ -607,6 +632,7 @@ def main():
     from pq3d_b200.query_encoder import QueryMaskEncoder
 
     assert torch.cuda.is_available(), "bench.py measures the CUDA path; no GPU is visible"
+    pin_rank_to_cores(local_rank, world)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -973,7 +999,7 @@ def main():
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": dict(workload_config(w, world),
                            l2="per-step working set ~0.5 GB (fp32 inputs + bf16 K/V^T for 4 layers) exceeds the 126 MB L2; no flush",
-                           cuda_graph=enc.use_cuda_graph, streams=n_streams,
+                           cuda_graph=enc.use_cuda_graph, streams=n_streams, cpu_affinity=CPU_AFFINITY,
                            in_flight=f"{n_streams} batch(es) in flight on {n_streams} CUDA stream(s) (K steps round-robin), "
                                      f"each stream its own batch of {w.B} scenes (different seeds, own device tensors); "
                                      f"strictly serial: {ms_serial:.4f} ms/step = {world * w.B * w.N / (ms_serial * 1e-3):.0f} queries/s"),
