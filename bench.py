@@ -715,11 +715,15 @@ def main():
         workspace and captured graph); device time from the first launch to the last completion."""
         cur = torch.cuda.current_stream()
         streams = [cur] if n_streams <= 1 else [torch.cuda.Stream(device=dev) for _ in range(n_streams)]
+        # the serial loop walks the same batches one at a time, so both figures average over the same scenes (the
+        # ragged config's batches differ in size)
+        mine = (lambda si: [si]) if n_streams > 1 else (lambda si: range(len(batches)))
         for si, st in enumerate(streams):                    # warm-up: eager pass, capture, first replays — per stream
             st.wait_stream(cur)
             with torch.cuda.stream(st):
-                for _ in range(max(args.warmup, 5)):       # eager, body capture, signature, whole-forward capture, replay
-                    step_resident(si)
+                for b in mine(si):
+                    for _ in range(max(args.warmup, 5)):   # eager, body capture, signature, whole-forward capture, replay
+                        step_resident(b)
         for st in streams:
             cur.wait_stream(st)
         barrier()
@@ -730,7 +734,7 @@ def main():
             st.wait_stream(cur)
         for i in range(steps):
             with torch.cuda.stream(streams[i % len(streams)]):
-                step_resident(i % len(streams))
+                step_resident(i % len(batches))
         for st in streams:
             cur.wait_stream(st)
         e1.record()

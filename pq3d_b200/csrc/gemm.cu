@@ -60,7 +60,7 @@ constexpr int kMaxAOff = 8;
 
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;  // 64 bf16 = 128 B = one swizzle atom row
-constexpr int kGemmThreads = 192;
+constexpr int kGemmThreads = 192;      // EW = 1: TMA warp + MMA warp + 4 epilogue warps; EW = 2: 8 epilogue warps (320 threads)
 constexpr int kBoxBytes = 32 * 128;  // one epilogue box: 32 rows x 128 B
 
 constexpr int kFullRing = 196608;   // 192 KB of operands in flight: one CTA per SM
@@ -73,7 +73,7 @@ struct GemmCfg {
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStages = RING / kStageBytes;
   static constexpr int kRingBytes = kStages * kStageBytes;
-  static constexpr int kStagingBytes = 4 * 2 * kBoxBytes;                    // 4 warps x double buffer
+  static constexpr int kStagingBytes = 4 * 2 * kBoxBytes;                    // EW = 1: 4 warps x double buffer; EW = 2: 8 warps x 1
   static constexpr int kBarBytes = 256;
   static constexpr int kSmemBytes = kRingBytes + kStagingBytes + kBarBytes + 2 * BN * 4;
   static constexpr uint32_t kTmemCols = 2 * BN;                              // two accumulator buffers
@@ -89,8 +89,8 @@ struct GemmCfg {
 // the same A tile, so each fetches a quarter of its rows and multicasts it into all four shared memories: per k-block a
 // CTA pulls 4 KB of A + its 8 KB of W instead of 16 + 8 KB.  A ring slot is reusable once all four CTAs consumed it
 // (multicast commit).  Correct (the kernel checks run it) but measured slower for the query-side GEMMs, see the host side.
-template <int BN, int CL, int MC = 1, int RING = kFullRing>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+template <int BN, int CL, int MC = 1, int RING = kFullRing, int EW = 1>
+__global__ void __launch_bounds__(64 + 128 * EW, 1)
 linear_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
                    const __grid_constant__ CUtensorMap tmap_c, const LinearParams p) {
   using Cfg = GemmCfg<BN, CL, RING>;
@@ -130,7 +130,7 @@ linear_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 4 * CL);   // pair: the leader's barrier collects the epilogue warps of both CTAs
+      mbar_init(&tempty_bar[i], 4 * EW * CL);   // pair: the leader's barrier collects the epilogue warps of both CTAs
     }
     fence_mbar_init();
   }
@@ -254,21 +254,27 @@ linear_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue warps 2..5
+    // ------------------------------------------------------------------ epilogue warps 2..5 (EW = 2: 2..9)
+    // EW = 2: two warps per TMEM lane quadrant, each taking every other box of the tile's columns — the epilogue of a
+    // 128 x 256 tile (TMEM loads, bias, bf16 pack, staging stores, proxy fence, TMA store per box) is a dependent chain
+    // of ~6 k cycles for one warp, the same as the tile's MMAs, so with four warps it paces the persistent loop
     const int quad = warp & 3;   // TMEM lane quadrant this warp may access
+    const int eh = (warp - 2) >> 2;            // which of the quadrant's EW warps
     const int r = lane_id();
-    uint8_t* stage = staging + (warp - 2) * 2 * kBoxBytes;
+    constexpr int kBoxBufs = EW == 1 ? 2 : 1;  // staging boxes per warp
+    uint8_t* stage = staging + (warp - 2) * kBoxBufs * kBoxBytes;
     int lt = 0, bx = 0;
     for (int t = first_tile; t < p.num_tiles; t += tile_step, ++lt) {
       const int g = t / tiles_per_group, rem = t % tiles_per_group;
       const int m0 = m_tile_of(rem) * kBlockM, n0 = n_tile_of(rem) * BN;
       const int buf = lt & 1;
       float* bias_s = s_bias + buf * BN;
-      for (int c = threadIdx.x - 64; c < BN; c += 128) {
+      for (int c = threadIdx.x - 64; c < BN; c += 128 * EW) {
         const int n = n0 + c;
         bias_s[c] = (p.bias != nullptr && !p.bias_along_m && n < p.N) ? p.bias[g * p.bias_group_stride + n] : 0.f;
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (EW == 1) asm volatile("bar.sync 1, 128;" ::: "memory");
+      else asm volatile("bar.sync 1, 256;" ::: "memory");
       const int m = m0 + quad * 32 + r;
       const bool row_ok = m < p.M;
       const bool zero_row = row_ok && p.row_zero != nullptr && p.row_zero[g * p.row_zero_group_stride + m] != 0;
@@ -325,10 +331,14 @@ linear_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
           else mbar_arrive(&tempty_bar[buf]);
         }
       };
-      auto claim_box = [&]() -> uint8_t* {   // double-buffered staging: wait until the box used 2 stores ago was read
-        if (bx >= 2 && r == 0) tma_store_wait_read<1>();
+      auto claim_box = [&]() -> uint8_t* {   // staging: wait until the box used kBoxBufs stores ago was read
+        if (kBoxBufs == 2) {
+          if (bx >= 2 && r == 0) tma_store_wait_read<1>();
+        } else {
+          if (bx >= 1 && r == 0) tma_store_wait_read<0>();
+        }
         __syncwarp();
-        return stage + (bx++ & 1) * kBoxBytes;
+        return stage + (bx++ & (kBoxBufs - 1)) * kBoxBytes;
       };
       auto store_box = [&](uint8_t* box, int c0) {
         fence_proxy_async_smem();
@@ -342,10 +352,11 @@ linear_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
 
       if (p.tma_store && p.out_fp32) {
         const int n_boxes = min(BN, p.N - n0 + 31) / 32;            // one box = 32 fp32 columns
-        for (int b = 0; b < n_boxes; ++b) {
+        if (eh >= n_boxes) release_accumulator();                   // nothing to read for this warp
+        for (int b = eh; b < n_boxes; b += EW) {
           float v[32];
           load_chunk(b * 32, v);
-          if (b == n_boxes - 1) release_accumulator();
+          if (b + EW >= n_boxes) release_accumulator();
           uint8_t* box = claim_box() + r * 128;
 #pragma unroll
           for (int j = 0; j < 8; ++j)
@@ -360,10 +371,11 @@ linear_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         __nv_bfloat16* c_row = reinterpret_cast<__nv_bfloat16*>(p.C) + static_cast<int64_t>(g) * p.c_group_stride +
                                static_cast<int64_t>(m) * p.ldc + n0;
         const int n_chunks = min(BN, p.N - n0 + 31) / 32;
-        for (int c = 0; c < n_chunks; ++c) {
+        if (eh >= n_chunks) release_accumulator();
+        for (int c = eh; c < n_chunks; c += EW) {
           float v[32];
           load_chunk(c * 32, v);
-          if (c == n_chunks - 1) release_accumulator();
+          if (c + EW >= n_chunks) release_accumulator();
           if (!row_ok) continue;
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -378,11 +390,12 @@ linear_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         }
       } else if (p.tma_store) {
         const int n_boxes = min(BN, p.N - n0 + 63) / 64;            // one box = 64 bf16 columns = two TMEM loads
-        for (int b = 0; b < n_boxes; ++b) {
+        if (eh >= n_boxes) release_accumulator();
+        for (int b = eh; b < n_boxes; b += EW) {
           float v0[32], v1[32];
           load_chunk(b * 64, v0);
           load_chunk(b * 64 + 32, v1);
-          if (b == n_boxes - 1) release_accumulator();
+          if (b + EW >= n_boxes) release_accumulator();
           uint8_t* box = claim_box() + r * 128;
           if (p.dbg_flags & 2) continue;
 #pragma unroll
@@ -406,7 +419,7 @@ linear_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         uint8_t* c_row = reinterpret_cast<uint8_t*>(p.C) +
                          (static_cast<int64_t>(g) * p.c_group_stride + static_cast<int64_t>(m) * p.ldc) *
                              (p.out_fp32 ? 4 : 2);
-        for (int c0 = 0; c0 < BN; c0 += 32) {
+        for (int c0 = eh * 32; c0 < BN; c0 += 32 * EW) {
           if (n0 + c0 >= p.N) break;
           float v[32];
           load_chunk(c0, v);
@@ -435,14 +448,14 @@ linear_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   if (dbg != nullptr && threadIdx.x == 0) dbg[6] = clock64();
 }
 
-template <int BN, int CL, int MC = 1, int RING = kFullRing>
+template <int BN, int CL, int MC = 1, int RING = kFullRing, int EW = 1>
 static int launch_linear(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& tc, const LinearParams& p,
                          cudaStream_t stream, int max_ctas = 0) {
   using Cfg = GemmCfg<BN, CL, RING>;
   constexpr int kCluster = CL * MC;
   static bool configured = false;
   if (!configured) {
-    PQ3D_CUDA(cudaFuncSetAttribute(linear_bf16_kernel<BN, CL, MC, RING>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    PQ3D_CUDA(cudaFuncSetAttribute(linear_bf16_kernel<BN, CL, MC, RING, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    Cfg::kSmemBytes));
     configured = true;
   }
@@ -453,8 +466,8 @@ static int launch_linear(const CUtensorMap& ta, const CUtensorMap& tw, const CUt
   if (max_ctas < 0) sms = sms * (-max_ctas);
   const int max_clusters = sms / kCluster > 0 ? sms / kCluster : 1;
   const int grid = kCluster * (p.num_tiles < max_clusters ? p.num_tiles : max_clusters);
-  PQ3D_CUDA(launch_kernel_cluster(linear_bf16_kernel<BN, CL, MC, RING>, dim3(grid), dim3(kGemmThreads), Cfg::kSmemBytes,
-                                  stream, kCluster, ta, tw, tc, p));
+  PQ3D_CUDA(launch_kernel_cluster(linear_bf16_kernel<BN, CL, MC, RING, EW>, dim3(grid), dim3(64 + 128 * EW),
+                                  Cfg::kSmemBytes, stream, kCluster, ta, tw, tc, p));
   return PQ3D_OK;
 }
 
@@ -485,7 +498,10 @@ static int linear_impl(const void* A, int64_t lda, int64_t a_rows_total, int64_t
     const char* e = getenv("PQ3D_GEMM_HALF_RING");
     return e == nullptr ? 1 : atoi(e);
   }();
-  const bool half_ring = half_ring_mode == 2 || (half_ring_mode == 1 && (flags & 4) != 0);
+  // ... and only when the concurrent batches can actually fill the machine: with a handful of tiles per GEMM (small
+  // scenes) SMs are free anyway and the deeper ring is faster (config 1: 0.152 vs 0.167 ms per step)
+  const int64_t tiles_here = (int64_t)((M + kBlockM - 1) / kBlockM) * ((N + 63) / 64) * groups;
+  const bool half_ring = half_ring_mode == 2 || (half_ring_mode == 1 && (flags & 4) != 0 && 4 * tiles_here > sm_count());
   PQ3D_CHECK_ARG(A && W && C, "pq3d_linear_bf16: null operand");
   PQ3D_CHECK_ARG(M > 0 && N > 0 && K > 0 && groups > 0, "pq3d_linear_bf16: bad shape M=%d N=%d K=%d groups=%d", M, N,
                  K, groups);
@@ -606,6 +622,10 @@ static int linear_impl(const void* A, int64_t lda, int64_t a_rows_total, int64_t
     int rc = make_tmap(&tc, C, esz, 3, dims, strides, box);
     if (rc != PQ3D_OK) return rc;
   }
+  static const int epi_warps = [] {      // PQ3D_GEMM_EPI_WARPS: epilogue warps per TMEM lane quadrant of the 256-wide tiles
+    const char* e = getenv("PQ3D_GEMM_EPI_WARPS");
+    return e == nullptr ? 2 : atoi(e);
+  }();
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   switch (block_n) {
     case 64: return mc == kMc ? launch_linear<64, 1, kMc>(ta, tw, tc, p, st, max_ctas)
@@ -613,8 +633,12 @@ static int linear_impl(const void* A, int64_t lda, int64_t a_rows_total, int64_t
                                : launch_linear<64, 1>(ta, tw, tc, p, st, max_ctas);
     case 128: return half_ring ? launch_linear<128, 1, 1, kHalfRing>(ta, tw, tc, p, st, max_ctas)
                                : launch_linear<128, 1>(ta, tw, tc, p, st, max_ctas);
-    default: return cl == 2 ? launch_linear<256, 2>(ta, tw, tc, p, st, max_ctas)
-                            : launch_linear<256, 1>(ta, tw, tc, p, st, max_ctas);
+    default:
+      if (epi_warps == 2)
+        return cl == 2 ? launch_linear<256, 2, 1, kFullRing, 2>(ta, tw, tc, p, st, max_ctas)
+                       : launch_linear<256, 1, 1, kFullRing, 2>(ta, tw, tc, p, st, max_ctas);
+      return cl == 2 ? launch_linear<256, 2>(ta, tw, tc, p, st, max_ctas)
+                     : launch_linear<256, 1>(ta, tw, tc, p, st, max_ctas);
   }
 }
 
