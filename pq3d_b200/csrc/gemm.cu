@@ -54,7 +54,6 @@ struct LinearParams {
   int32_t w_prefetch;       // W is constant (weights): its first ring pass may be fetched before griddepcontrol.wait
   int32_t use_a_off;        // group g's A rows start at a_off[g] instead of g * a_group_rows (groups <= kMaxAOff)
   int32_t a_off[8];
-  int32_t direct_store;     // bf16 C, 16-byte granular rows: the epilogue stores from registers (no shared-memory staging)
 };
 constexpr int kMaxAOff = 8;
 
@@ -364,30 +363,6 @@ linear_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
                 make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
           store_box(box - r * 128, b * 32);
         }
-      } else if (p.direct_store) {
-        // bf16 result straight from the accumulator registers: each thread owns one row and writes 64-byte runs of it.
-        // The shared-memory port is what bounds the main loop (TMA fill + MMA operand reads); the staged path adds a
-        // 64 KB write and a 64 KB TMA-store read per tile to it, this path adds nothing.
-        __nv_bfloat16* c_row = reinterpret_cast<__nv_bfloat16*>(p.C) + static_cast<int64_t>(g) * p.c_group_stride +
-                               static_cast<int64_t>(m) * p.ldc + n0;
-        const int n_chunks = min(BN, p.N - n0 + 31) / 32;
-        if (eh >= n_chunks) release_accumulator();
-        for (int c = eh; c < n_chunks; c += EW) {
-          float v[32];
-          load_chunk(c * 32, v);
-          if (c + EW >= n_chunks) release_accumulator();
-          if (!row_ok) continue;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            if (n0 + c * 32 + j * 8 + 8 > p.N) break;               // N is a multiple of 8 on this path
-            uint4 u;
-            u.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
-            u.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
-            u.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
-            u.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
-            *reinterpret_cast<uint4*>(c_row + c * 32 + j * 8) = u;
-          }
-        }
       } else if (p.tma_store) {
         const int n_boxes = min(BN, p.N - n0 + 63) / 64;            // one box = 64 bf16 columns = two TMEM loads
         if (eh >= n_boxes) release_accumulator();
@@ -601,17 +576,11 @@ static int linear_impl(const void* A, int64_t lda, int64_t a_rows_total, int64_t
   const int esz = out_fp32 ? 4 : 2;
   p.tma_store = ((reinterpret_cast<uintptr_t>(C) & 15) == 0) && ((ldc * esz) % 16 == 0) &&
                 ((c_group_stride * esz) % 16 == 0);
-  // Opt-in (PQ3D_GEMM_DIRECT_STORE=1: 256-wide tiles, 2: every bf16 GEMM): epilogue stores from registers, no staging.
-  // MEASURED on B200 (round 2, 3 x [8192 x 3072 x 768]): it does NOT pay — pairs 1252 -> 984 TFLOP/s, single CTA 1180 -> 969:
-  // a thread owns a row, so one store instruction touches 32 different 128-byte lines and the four epilogue warps
-  // become the limit; the staged TMA store writes whole lines.  (With the stores disabled altogether the main loop
-  // reaches 1393 TFLOP/s — the gap to that is not the staging traffic alone.)
-  static const int direct_mode = [] {
-    const char* e = getenv("PQ3D_GEMM_DIRECT_STORE");
-    return e == nullptr ? 0 : atoi(e);
-  }();
-  p.direct_store = (p.tma_store && !out_fp32 && N % 8 == 0 &&
-                    (direct_mode == 2 || (direct_mode == 1 && block_n == 256))) ? 1 : 0;
+  // An epilogue that stores from registers without the shared-memory staging was built and MEASURED (round 2,
+  // 3 x [8192 x 3072 x 768]): CTA pairs 1252 -> 984 TFLOP/s, single CTA 1180 -> 969 — a thread owns a row, so one store
+  // instruction touches 32 different 128-byte lines and the epilogue warps become the limit.  Its mere presence as a
+  // runtime branch also slowed the 64-wide tiles by 8 % (5.23 -> 5.64 us per chain GEMM: bigger kernel image), so the
+  // code was removed again (git history: "register-layout (unstaged) epilogue").
   CUtensorMap tc = ta;   // placeholder when the direct-store path is taken
   if (p.tma_store) {
     // {N, M, groups}: tails in N and M are clipped by TMA, a tile never spills into the next group
@@ -745,7 +714,6 @@ extern "C" int pq3d_bgemm_bf16(const void* A, int64_t a_row_stride, int64_t a_g2
   p.alpha = alpha;
   p.alpha_ncols = alpha == 1.f ? 0 : N;
   p.tma_store = 1;
-  p.direct_store = 0;
   p.batched = 1;
   p.G2 = G2;
   p.ldc = c_row_stride;

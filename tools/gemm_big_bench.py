@@ -1,5 +1,5 @@
 """The hoisted K / V^T projections of config 3 (3 scene memories x [8192 x 3072 x 768], grouped) timed inside a CUDA
-graph, with and without CTA pairs.  Run once per PQ3D_GEMM_DIRECT_STORE setting (the switch is read once per process)."""
+graph, with and without CTA pairs.  Run once per PQ3D_GEMM_EPI_WARPS setting (the switch is read once per process)."""
 import os
 import sys
 
@@ -47,12 +47,12 @@ def graph_time(fn, n=6, reps=6):
 
 
 flops = 2.0 * nf * BS * L * D * D
-mode = os.environ.get("PQ3D_GEMM_DIRECT_STORE", "default")
+mode = os.environ.get("PQ3D_GEMM_EPI_WARPS", "default")
 ref = (x.float().view(nf, BS, D) @ wk.float().view(nf, L * D, D).transpose(1, 2) + bk.view(nf, 1, L * D))
 for no_pairs in (False, True):
     for name, fn, out, want in (("K", k_proj, K_all, ref), ("V^T", vt_proj, Vt_all, ref.transpose(1, 2))):
         out.zero_()
         us = graph_time(lambda: fn(no_pairs))
         err = ((out.float() - want).abs().max() / want.abs().max()).item()
-        print(f"direct_store={mode} {'single CTA' if no_pairs else 'CTA pairs '} {name:>3} projection: {us:7.2f} us  "
+        print(f"epi_warps={mode} {'single CTA' if no_pairs else 'CTA pairs '} {name:>3} projection: {us:7.2f} us  "
               f"{flops / us / 1e6:7.1f} TFLOP/s   rel err {err:.2e}")
