@@ -60,3 +60,23 @@ def test_product_modules_refuse_cpu_tensors():
     enc.train()
     with pytest.raises((TypeError, ValueError), match="CUDA"):
         enc(synth.clone_input_dict(inp), pw)
+
+
+def test_scheduling_context_managers_restore_state():
+    """ops.launch_priority / ops.shared_sm are plain host state around the launches (no compute): nesting and
+    exceptions restore the previous value; without a GPU the C side clamps every priority to 0 and still returns OK."""
+    from pq3d_b200 import ops
+    assert ops._PRIORITY[0] == 0 and ops._SHARED_SM[0] is False
+    with ops.launch_priority(-2):
+        assert ops._PRIORITY[0] == -2
+        with ops.launch_priority(0):
+            assert ops._PRIORITY[0] == 0
+        assert ops._PRIORITY[0] == -2
+    assert ops._PRIORITY[0] == 0
+    try:
+        with ops.shared_sm(True), ops.launch_priority(-1):
+            assert ops._SHARED_SM[0] is True
+            raise KeyError("x")
+    except KeyError:
+        pass
+    assert ops._PRIORITY[0] == 0 and ops._SHARED_SM[0] is False
