@@ -351,6 +351,8 @@ class Query3DUnified(nn.Module):
                 graphs.pop(next(iter(graphs)))
             graphs[sig] = {"refs": [weakref.ref(t) for t in tensors]}
             return None                                          # first sighting: eager (allocates every workspace)
+        if ent.get("failed"):
+            return None
         if ent.get("graph") is None:
             torch.cuda.synchronize()
             before = ops.LAUNCHES
@@ -360,6 +362,16 @@ class Query3DUnified(nn.Module):
             try:
                 with torch.cuda.graph(g):
                     self._forward_eager(dd)
+            except RuntimeError as e:
+                # a configuration whose forward cannot be recorded (an op that synchronises): stay on the eager path for
+                # this signature and say so once — never a silent change of results, the eager forward is the reference
+                import warnings
+                warnings.warn(f"pq3d_b200.Query3DUnified: whole-model CUDA graph capture failed ({e}); this batch "
+                              "signature keeps the eager forward")
+                ent["failed"] = True
+                ops.LAUNCHES = before
+                torch.cuda.synchronize()
+                return None
             finally:
                 enc._stream_key_override = None
             outs = {k: v for k, v in dd.items()
